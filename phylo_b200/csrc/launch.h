@@ -1,0 +1,36 @@
+// Internal host-side launch prototypes shared by the translation units of libvcsmc_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vcsmc {
+
+// merge.cu
+int merge_tiles(int n_sites);
+int launch_merge_fwd(const uint8_t* codes, int64_t codes_stride, double* pool, int64_t slot_sites, const int32_t* lsrc,
+                     const int32_t* rsrc, const int32_t* dst, const double* P, const double* pi, int64_t K,
+                     int n_sites, int jc, int skip_unstored, double* ell_part, cudaStream_t st);
+int launch_ell_reduce(const double* ell_part, int tiles, int64_t K, double* ell, cudaStream_t st);
+int launch_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* pool, double* gpool, int64_t slot_sites,
+                     const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc, const double* P, const double* pi,
+                     const double* coef, int64_t K, int n_sites, int jc, int skip_zero, double* dP, double* dpi_each,
+                     cudaStream_t st);
+
+// transition.cu
+int launch_transition_fwd(const double* Q, const double* t, int64_t n, int jc, double* P, cudaStream_t st);
+int launch_transition_bwd(const double* Q, const double* t, const double* dP, int64_t n, int jc, double* dt,
+                          double* dQ_each, cudaStream_t st);
+
+// loader.cu
+int launch_pack_alignment(const double* genome, int N, int S, uint8_t* codes, int* status, cudaStream_t st);
+int launch_gather_sites(const uint8_t* codes, int N, int S, const int32_t* site_idx, int n_sel, uint8_t* out,
+                        cudaStream_t st);
+
+// smc.cu
+int launch_propose_pairs(const float* u, int64_t K, int n, int32_t* coal, int32_t* rem, cudaStream_t st);
+int launch_resample_cdf(const double* lw, int64_t K, double* cdf, double* stats /*[4]: lse,total,ess,max*/, cudaStream_t st);
+int launch_resample_search(const double* cdf, const double* stats, const double* u, int64_t K, int32_t* idx, cudaStream_t st);
+int launch_philox_step(uint64_t seed, int r, int64_t k0, int64_t K, int n, float* u_pair, double* u_bl, double* u_br,
+                       double* u_res, cudaStream_t st);
+
+}  // namespace vcsmc

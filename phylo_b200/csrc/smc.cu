@@ -1,0 +1,187 @@
+// (d) pair proposal, log-sum-exp normalisation + ESS + multinomial resampling, counter-based uniforms.
+//
+// propose_pairs : extend_partial_state, vcsmc.py:298-305
+// resample      : resample, vcsmc.py:284-285 (tf.random.categorical: running fp64 sum of exp(logit - max),
+//                 one uniform per draw, upper_bound(u * total)); logsumexp also feeds compute_log_ZSMC
+//                 (vcsmc.py:276).  The CDF is built by ONE CTA in a fixed blocked order, so every GPU that
+//                 holds the same K log-weights derives bit-identical ancestors.
+#include "launch.h"
+#include "smc_device.cuh"
+
+namespace vcsmc {
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) propose_pairs_kernel(const float* __restrict__ u, int64_t K, int n,
+                                                                         int32_t* __restrict__ coal,
+                                                                         int32_t* __restrict__ rem) {
+  extern __shared__ float su_all[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * kWarpsPerCta + wid;
+  if (k >= K) return;
+  float* su = su_all + wid * n;
+  for (int i = lane; i < n; i += 32) su[i] = u[k * n + i];
+  __syncwarp();
+  int c0, c1;
+  int32_t* rk = rem + k * (int64_t)(n - 2);
+  rank_pairs_warp(su, n, lane, c0, c1, [&](int pos, int i) { rk[pos] = i; });
+  if (lane == 0) {
+    coal[k * 2] = c0;
+    coal[k * 2 + 1] = c1;
+  }
+}
+
+constexpr int kCdfThreads = 1024;
+
+// stats[0] = logsumexp(lw), stats[1] = total = cdf[K-1], stats[2] = ESS, stats[3] = max(lw)
+__global__ void __launch_bounds__(kCdfThreads) resample_cdf_kernel(const double* __restrict__ lw, int64_t K,
+                                                                   double* __restrict__ cdf,
+                                                                   double* __restrict__ stats) {
+  __shared__ double sm[kCdfThreads / 32];
+  __shared__ double sm2[kCdfThreads / 32];
+  __shared__ double bc[2];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t chunk = (K + kCdfThreads - 1) / kCdfThreads;
+  const int64_t b = min((int64_t)tid * chunk, K), e = min(b + chunk, K);
+
+  // max
+  double m = -INFINITY;
+  for (int64_t i = b; i < e; ++i) m = fmax(m, lw[i]);
+  m = warp_max(m);
+  if (lane == 0) sm[wid] = m;
+  __syncthreads();
+  if (tid == 0) {
+    double t = sm[0];
+    for (int i = 1; i < kCdfThreads / 32; ++i) t = fmax(t, sm[i]);
+    bc[0] = t;
+  }
+  __syncthreads();
+  const double M = bc[0];
+
+  // logsumexp
+  double s = 0.0;
+  for (int64_t i = b; i < e; ++i) s += exp(lw[i] - M);
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) sm[wid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0;
+    for (int i = 0; i < kCdfThreads / 32; ++i) t += sm[i];
+    bc[1] = M + log(t);
+  }
+  __syncthreads();
+  const double lse = bc[1];
+  const double mlog = M - lse;  // max of the normalised logits (vcsmc.py:284)
+
+  // running sum of exp(logit - max): thread-local totals, CTA exclusive scan, then the prefix itself
+  double run = 0.0, sq = 0.0;
+  for (int64_t i = b; i < e; ++i) {
+    const double w = exp((lw[i] - lse) - mlog);
+    run += w;
+    sq = fma(w, w, sq);
+  }
+  double incl = run;  // inclusive warp scan
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const double sqw = warp_sum(sq);
+  __syncthreads();
+  if (lane == 31) sm[wid] = incl;
+  if (lane == 0) sm2[wid] = sqw;
+  __syncthreads();
+  if (tid == 0) {
+    double t = 0.0, q = 0.0;
+    for (int i = 0; i < kCdfThreads / 32; ++i) {
+      const double v = sm[i];
+      sm[i] = t;  // exclusive offset of warp i
+      t += v;
+      q += sm2[i];
+    }
+    stats[0] = lse;
+    stats[1] = t;
+    stats[2] = t * t / q;
+    stats[3] = M;
+  }
+  __syncthreads();
+  double off = sm[wid] + (incl - run);
+  for (int64_t i = b; i < e; ++i) {
+    off += exp((lw[i] - lse) - mlog);
+    cdf[i] = off;
+  }
+  // make the last entry exactly the reported total so that upper_bound(u*total) with u<1 always lands < K
+  if (e == K && b < e) cdf[K - 1] = fmax(cdf[K - 1], 0.0);
+}
+
+__global__ void resample_search_kernel(const double* __restrict__ cdf, const double* __restrict__ stats,
+                                       const double* __restrict__ u, int64_t K, int32_t* __restrict__ idx) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= K) return;
+  idx[j] = upper_bound_cdf(cdf, K, u[j] * cdf[K - 1]);
+}
+
+__global__ void philox_step_kernel(uint64_t seed, int r, int64_t k0, int64_t K, int n, float* __restrict__ u_pair,
+                                   double* __restrict__ u_bl, double* __restrict__ u_br, double* __restrict__ u_res) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K) return;
+  const uint64_t k = (uint64_t)(k0 + i);  // LOGICAL particle index: identical streams for any GPU count
+  const uint32_t s0 = (uint32_t)seed, s1 = (uint32_t)(seed >> 32);
+  uint32_t c[4] = {(uint32_t)k, (uint32_t)(k >> 32) | ((uint32_t)r << 8), 0u, 0u};
+  philox4x32_10(c, s0, s1);
+  const double tiny = 2.2250738585072014e-308;
+  if (u_bl) u_bl[i] = fmax(u64_to_unit_f64(c[0], c[1]), tiny);   // tfp Exponential: U in [tiny, 1)
+  if (u_br) u_br[i] = fmax(u64_to_unit_f64(c[2], c[3]), tiny);
+  if (u_res) {
+    uint32_t d[4] = {(uint32_t)k, (uint32_t)(k >> 32) | ((uint32_t)r << 8), 1u, 0u};
+    philox4x32_10(d, s0, s1);
+    u_res[i] = u64_to_unit_f64(d[0], d[1]);
+  }
+  if (u_pair) {
+    for (int j = 0; j < n; j += 4) {
+      uint32_t p[4] = {(uint32_t)k, (uint32_t)(k >> 32) | ((uint32_t)r << 8), 2u, (uint32_t)(j >> 2)};
+      philox4x32_10(p, s0, s1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (j + q < n) u_pair[i * n + j + q] = u32_to_unit_f32(p[q]);
+    }
+  }
+}
+
+}  // namespace
+
+int launch_propose_pairs(const float* u, int64_t K, int n, int32_t* coal, int32_t* rem, cudaStream_t st) {
+  if (K <= 0) return VCSMC_OK;
+  if (n < 2 || n > kMaxRoots) { set_error("propose_pairs: n=%d out of range [2,%d]", n, kMaxRoots); return VCSMC_ERR_ARG; }
+  const size_t smem = (size_t)kWarpsPerCta * n * sizeof(float);
+  propose_pairs_kernel<<<(unsigned)((K + kWarpsPerCta - 1) / kWarpsPerCta), kWarpsPerCta * 32, smem, st>>>(u, K, n, coal, rem);
+  VCSMC_LAUNCH_CHECK("propose_pairs_kernel");
+  return VCSMC_OK;
+}
+
+int launch_resample_cdf(const double* lw, int64_t K, double* cdf, double* stats, cudaStream_t st) {
+  if (K <= 0) return VCSMC_OK;
+  resample_cdf_kernel<<<1, kCdfThreads, 0, st>>>(lw, K, cdf, stats);
+  VCSMC_LAUNCH_CHECK("resample_cdf_kernel");
+  return VCSMC_OK;
+}
+
+int launch_resample_search(const double* cdf, const double* stats, const double* u, int64_t K, int32_t* idx,
+                           cudaStream_t st) {
+  if (K <= 0) return VCSMC_OK;
+  resample_search_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(cdf, stats, u, K, idx);
+  VCSMC_LAUNCH_CHECK("resample_search_kernel");
+  return VCSMC_OK;
+}
+
+int launch_philox_step(uint64_t seed, int r, int64_t k0, int64_t K, int n, float* u_pair, double* u_bl, double* u_br,
+                       double* u_res, cudaStream_t st) {
+  if (K <= 0) return VCSMC_OK;
+  philox_step_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(seed, r, k0, K, n, u_pair, u_bl, u_br, u_res);
+  VCSMC_LAUNCH_CHECK("philox_step_kernel");
+  return VCSMC_OK;
+}
+
+}  // namespace vcsmc

@@ -1,0 +1,998 @@
+// The SMC sweep: sample_phylogenies / body_rank_update (vcsmc.py:332-451) forward, and the reverse sweep that
+// TF autodiff of cost = -elbo performs (vcsmc.py:488-491) backward.
+//
+// B200-first data model (not the reference's): a subtree's partial-likelihood vector never changes once
+// computed, so it is written ONCE into a node pool; a particle is a row of int32 node references plus cached
+// per-node scalars.  The reference's three gathers + concat + resample gather per rank event (vcsmc.py:286,
+// :361-368), which copy the whole [K,n,S,4] state, become int-table gathers; compute_forest_posterior
+// (vcsmc.py:231-245) re-reads nothing: only the NEW node's sum_s log(pi.L) is computed (fused in the merge).
+//
+// Memory plan (H2): if every node of the sweep fits, nodes are direct-mapped (slot = r*K + k) and kept for
+// the backward pass.  Otherwise the forward runs on a garbage-collected slot pool (dead nodes are recycled
+// after every resampling) and the backward recomputes the forward per SITE CHUNK (sites are independent
+// once ancestors, pairs, branch lengths and the per-node coefficients are known from the scalar tables).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "launch.h"
+#include "smc_device.cuh"
+
+namespace vcsmc {
+namespace {
+
+inline int64_t align_up(int64_t x, int64_t a = 256) { return (x + a - 1) / a * a; }
+
+struct Layout {
+  int64_t off = 0;
+  template <typename T>
+  int64_t take(int64_t count) {
+    const int64_t o = off;
+    off = align_up(off + count * (int64_t)sizeof(T));
+    return o;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void leaf_ell_kernel(const uint8_t* __restrict__ codes, int64_t stride, int S, const double* __restrict__ pi,
+                                double* __restrict__ ell_node) {
+  // ell_leaf = sum_s log(pi . leaf[s])   (the leaves' share of compute_forest_posterior, vcsmc.py:238-242)
+  __shared__ double red[8];
+  const int leaf = blockIdx.x;
+  double p[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) p[j] = pi[j];
+  double acc = 0.0;
+  for (int s = threadIdx.x; s < S; s += 256) {
+    const d4 L = leaf_site(codes[(int64_t)leaf * stride + s]);
+    double x = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x = fma(p[j], L.v[j], x);
+    acc += log(x);
+  }
+  const double t = block_sum<256>(acc, red);
+  if (threadIdx.x == 0) ell_node[leaf] = t;
+}
+
+struct PrepArgs {
+  int r, n, N, gc;
+  int64_t K;
+  const double* cdf;
+  const double* u_res;
+  const float* u_pair;
+  const double* u_bl;
+  const double* u_br;
+  const double* lam_l;
+  const double* lam_r;
+  const int32_t* ids_old;
+  const int32_t* cnt_old;
+  const int32_t* slot_old;
+  int32_t* ids_new;
+  int32_t* cnt_new;
+  int32_t* slot_new;
+  const double* LL_prev;
+  int32_t* anc;
+  int32_t* lref;
+  int32_t* rref;
+  int32_t* nleaf;
+  uint8_t* rempos;
+  double* b_l;
+  double* b_r;
+  double* t2;
+  double* ll_tilde;
+  int32_t* lsrc;
+  int32_t* rsrc;
+  int32_t* dst;
+};
+
+constexpr int kPrepWarps = 8;
+
+// One warp per particle: resampling draw, pair proposal, forest-row update, branch lengths.
+// (resample vcsmc.py:284-289,318-325; extend_partial_state :298-305; Exponential sample :351-358; state update :361-373)
+__global__ void __launch_bounds__(kPrepWarps * 32) step_prepare_kernel(const PrepArgs a) {
+  extern __shared__ float su_all[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * kPrepWarps + wid;
+  if (k >= a.K) return;
+  const int n = a.n, N = a.N, r = a.r;
+  float* su = su_all + wid * n;
+  for (int i = lane; i < n; i += 32) su[i] = a.u_pair[k * n + i];
+
+  int idx = (int)k;
+  if (r > 0) {
+    if (lane == 0) idx = upper_bound_cdf(a.cdf, a.K, a.u_res[k] * a.cdf[a.K - 1]);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+  }
+  __syncwarp();
+  const int32_t* io = a.ids_old + (int64_t)idx * N;
+  const int32_t* co = a.cnt_old + (int64_t)idx * N;
+  const int32_t* so = a.slot_old + (int64_t)idx * N;
+  int32_t* in_ = a.ids_new + k * N;
+  int32_t* cn = a.cnt_new + k * N;
+  int32_t* sn = a.slot_new + k * N;
+  uint8_t* rp = a.rempos + k * (int64_t)(n - 2);
+  const bool first = (r == 0);  // initial forest = the N leaves, one each (vcsmc.py:414-415)
+  const int gc = a.gc;
+  int c0, c1;
+  rank_pairs_warp(su, n, lane, c0, c1, [&](int pos, int i) {
+    rp[pos] = (uint8_t)i;
+    in_[pos] = first ? i : io[i];
+    cn[pos] = first ? 1 : co[i];
+    if (gc) sn[pos] = first ? -1 : so[i];
+  });
+  if (lane == 0) {
+    const int lid = first ? c0 : io[c0], rid = first ? c1 : io[c1];
+    const int64_t e = (int64_t)r * a.K + k;
+    in_[n - 2] = (int32_t)(N + e);
+    const int nl = (first ? 1 : co[c0]) + (first ? 1 : co[c1]);
+    cn[n - 2] = nl;
+    a.nleaf[k] = nl;
+    a.anc[k] = idx;
+    a.lref[k] = lid;
+    a.rref[k] = rid;
+    a.lsrc[k] = lid < N ? -(lid + 1) : (gc ? so[c0] : lid - N);
+    a.rsrc[k] = rid < N ? -(rid + 1) : (gc ? so[c1] : rid - N);
+    if (!gc) a.dst[k] = (int32_t)e;  // direct map: slot = r*K + k (GC mode: gc_alloc_kernel assigns it)
+    const double bl = -log(a.u_bl[k]) / a.lam_l[r];
+    const double br = -log(a.u_br[k]) / a.lam_r[r];
+    a.b_l[k] = bl;
+    a.b_r[k] = br;
+    a.t2[2 * k] = bl;
+    a.t2[2 * k + 1] = br;
+    a.ll_tilde[k] = first ? log(1.0 / (double)a.K) : a.LL_prev[idx];
+  }
+}
+
+// --- slot pool garbage collection (forward, GC mode) ---
+__global__ void gc_mark_kernel(const int32_t* __restrict__ ids_new, const int32_t* __restrict__ slot_new, int N, int n,
+                               int64_t K, const int32_t* __restrict__ lsrc, const int32_t* __restrict__ rsrc,
+                               int32_t* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t k = i / n;
+  const int p = (int)(i - k * n);
+  if (k >= K) return;
+  if (p < n - 2) {
+    if (ids_new[k * N + p] >= N) flags[slot_new[k * N + p]] = 1;
+  } else if (p == n - 2) {
+    if (lsrc[k] >= 0) flags[lsrc[k]] = 1;
+  } else {
+    if (rsrc[k] >= 0) flags[rsrc[k]] = 1;
+  }
+}
+
+// The K lowest free slots, in order, go to particles 0..K-1.  Single CTA, fixed order.
+__global__ void __launch_bounds__(1024) gc_alloc_kernel(const int32_t* __restrict__ flags, int64_t P, int64_t K, int N, int n,
+                                                        int32_t* __restrict__ dst, int32_t* __restrict__ slot_new,
+                                                        int32_t* __restrict__ status) {
+  __shared__ int64_t warp_tot[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t chunk = (P + 1023) / 1024;
+  const int64_t b = min((int64_t)tid * chunk, P), e = min(b + chunk, P);
+  int64_t cnt = 0;
+  for (int64_t i = b; i < e; ++i) cnt += flags[i] == 0;
+  int64_t incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  if (tid == 0) {
+    int64_t t = 0;
+    for (int i = 0; i < 32; ++i) {
+      const int64_t v = warp_tot[i];
+      warp_tot[i] = t;
+      t += v;
+    }
+    if (t < K) status[0] = VCSMC_ERR_POOL;
+    const int64_t used = P - t + (t < K ? t : K);
+    if (used > status[1]) status[1] = (int32_t)used;
+    for (int64_t j = t; j < K; ++j) {  // pool exhausted: these particles compute ell only
+      dst[j] = -1;
+      slot_new[j * N + (n - 2)] = -1;
+    }
+  }
+  __syncthreads();
+  int64_t j = warp_tot[wid] + (incl - cnt);
+  for (int64_t i = b; i < e && j < K; ++i) {
+    if (flags[i] == 0) {
+      dst[j] = (int32_t)i;
+      slot_new[j * N + (n - 2)] = (int32_t)i;
+      ++j;
+    }
+  }
+}
+
+struct WeightArgs {
+  int r, n, N, tiles;
+  int64_t K;
+  const double* ell_part;
+  const int32_t* ids_new;
+  const int32_t* cnt_new;
+  const double* ldf;
+  const double* lam_l;
+  const double* lam_r;
+  const double* b_l;
+  const double* b_r;
+  const double* cum_l_prev;
+  const double* cum_r_prev;
+  double* cum_l;
+  double* cum_r;
+  const double* ll_tilde;
+  double* ell_node;
+  double* lw;
+  double* LL;
+  int32_t* vminus;
+  double q;
+};
+
+// compute_forest_posterior with cached per-node scalars + branch priors + v^- + weight (vcsmc.py:376-395)
+__global__ void step_weights_kernel(const WeightArgs a) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.K) return;
+  const int N = a.N, n = a.n, r = a.r;
+  double ell = 0.0;
+  for (int t = 0; t < a.tiles; ++t) ell += a.ell_part[k * a.tiles + t];
+  a.ell_node[N + (int64_t)r * a.K + k] = ell;
+  double F = 0.0, topo = 0.0;
+  int vm = 0;
+  for (int p = 0; p < n - 2; ++p) {
+    F += a.ell_node[a.ids_new[k * N + p]];
+    const int c = a.cnt_new[k * N + p];
+    topo -= a.ldf[2 * max(c, 2) - 3];
+    vm += c - (c == 1);
+  }
+  {
+    F += ell;
+    const int c = a.cnt_new[k * N + n - 2];
+    topo -= a.ldf[2 * max(c, 2) - 3];
+    vm += c - (c == 1);
+  }
+  const double laml = a.lam_l[r], lamr = a.lam_r[r];
+  const double bl = a.b_l[k], br = a.b_r[k];
+  const double cl = (r > 0 ? a.cum_l_prev[k] : 0.0) + bl;   // quirk Q1: slot-wise, un-resampled histories
+  const double cr = (r > 0 ? a.cum_r_prev[k] : 0.0) + br;
+  a.cum_l[k] = cl;
+  a.cum_r[k] = cr;
+  const double llog = log(laml), rlog = log(lamr);
+  // quirk Q2: the CURRENT step's rate multiplies ALL earlier branches (vcsmc.py:380-383)
+  const double LLr = (F + topo) + (-laml * cl + (double)(r + 1) * llog) + (-lamr * cr + (double)(r + 1) * rlog);
+  // quirk Q3: q = 1/C(n,2) is subtracted raw (vcsmc.py:298,392)
+  const double lw = LLr - a.ll_tilde[k] - (llog - laml * bl + rlog - lamr * br) + log((double)vm) - a.q;
+  a.LL[k] = LLr;
+  a.lw[k] = lw;
+  a.vminus[k] = vm;
+}
+
+// ELBO (vcsmc.py:276) and log_likelihood_R (vcsmc.py:254-268, incl. quirk Q4)
+__global__ void finalize_kernel(int N, int64_t K, const double* __restrict__ stats, const double* __restrict__ LL_last,
+                                const double* __restrict__ b_l, const double* __restrict__ b_r,
+                                const double* __restrict__ lam_l, const double* __restrict__ lam_r, double ldf_root,
+                                double* __restrict__ llR, double* __restrict__ elbo, double* __restrict__ logz,
+                                double* __restrict__ ess) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0) {
+    double s = 0.0;
+    const double lk = log((double)K);
+    for (int r = 0; r < N - 1; ++r) {
+      const double z = stats[r * 4] - lk;
+      logz[r] = z;
+      ess[r] = stats[r * 4 + 2];
+      s += z;
+    }
+    elbo[0] = s;
+  }
+  if (k >= K) return;
+  double lp = 0.0, rp = 0.0;
+  for (int r = 0; r < N - 1; ++r) {
+    const double ll = log(lam_l[r]);
+    lp += ll - b_l[(int64_t)r * K + k] * lam_l[r];
+    rp += ll - b_r[(int64_t)r * K + k] * lam_r[r];  // log(LEFT param): vcsmc.py:262
+  }
+  llR[k] = LL_last[k] + ldf_root - lp - rp;
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward kernels (scalar tables)
+// ---------------------------------------------------------------------------------------------
+__global__ void mark_consumed_kernel(const int32_t* __restrict__ lref, const int32_t* __restrict__ rref, int64_t n, int N,
+                                     int32_t* __restrict__ consumed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (lref[i] >= N) consumed[lref[i] - N] = 1;
+  if (rref[i] >= N) consumed[rref[i] - N] = 1;
+}
+
+__global__ void bwd_src_kernel(const int32_t* __restrict__ lref, const int32_t* __restrict__ rref,
+                               const int32_t* __restrict__ consumed, int64_t n, int N, int32_t* __restrict__ lsrc,
+                               int32_t* __restrict__ rsrc, int32_t* __restrict__ gsrc, int32_t* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = lref[i], r = rref[i];
+  lsrc[i] = l < N ? -(l + 1) : l - N;
+  rsrc[i] = r < N ? -(r + 1) : r - N;
+  const int c = consumed[i];
+  gsrc[i] = c ? (int32_t)i : -1;
+  dst[i] = c ? (int32_t)i : -1;
+}
+
+struct CoefArgs {
+  int r, n, N;
+  int64_t K;
+  double grad;
+  double share;  // fraction of the site-independent gradient terms this rank owns (site sharding)
+  const double* lw;
+  const double* stats;  // row r: lse
+  const int32_t* anc;
+  const uint8_t* rempos;
+  const double* childsum_cur;
+  double* childsum_next;
+  const double* Dacc_cur;
+  double* Dacc_next;
+  double* cnew;
+  const double* lam_l;
+  const double* lam_r;
+  const double* b_l;
+  const double* b_r;
+  const double* cum_l;
+  const double* cum_r;
+  double* suf_l;
+  double* suf_r;
+  double* gB_l;  // [K] site-independent part of dELBO/d b_l[r][k]
+  double* gB_r;
+  double* dlam_l;  // [N-1]
+  double* dlam_r;
+};
+
+// Adjoint of the weight algebra for rank event r (vcsmc.py:376-395 reversed):
+//   W = softmax(lw_r) * grad;  a = dELBO/dLL_r[k] = W - sum_{children k' at r+1} W_{r+1}[k'];
+//   D[p] = a + (what the descendants' forests still hold of entry p);  c_new = D[last].
+__global__ void __launch_bounds__(256) bwd_coef_kernel(const CoefArgs a) {
+  __shared__ double red[8];
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = a.N, n = a.n, r = a.r;
+  double dl = 0.0, dr = 0.0;
+  if (k < a.K) {
+    const double W = exp(a.lw[k] - a.stats[r * 4]) * a.grad;
+    const double av = W - a.childsum_cur[k];
+    const int64_t A = r > 0 ? a.anc[k] : k;
+    const uint8_t* rp = a.rempos + k * (int64_t)(n - 2);
+    for (int p = 0; p < n - 2; ++p) {
+      const double D = av + a.Dacc_cur[k * N + p];
+      if (D != 0.0) atomicAdd(a.Dacc_next + A * N + rp[p], D);
+    }
+    a.cnew[k] = av + a.Dacc_cur[k * N + n - 2];
+    if (r > 0 && W != 0.0) atomicAdd(a.childsum_next + A, W);
+    const double laml = a.lam_l[r], lamr = a.lam_r[r];
+    const double sl = a.suf_l[k] + av * laml, sr = a.suf_r[k] + av * lamr;  // sum_{r' >= r} a_{r'}[k] lam_{r'}
+    a.suf_l[k] = sl;
+    a.suf_r[k] = sr;
+    a.gB_l[k] = a.share * (W * laml - sl);
+    a.gB_r[k] = a.share * (W * lamr - sr);
+    dl = a.share * (av * (-a.cum_l[k] + (double)(r + 1) / laml) + W * (a.b_l[k] - 1.0 / laml));
+    dr = a.share * (av * (-a.cum_r[k] + (double)(r + 1) / lamr) + W * (a.b_r[k] - 1.0 / lamr));
+  }
+  const double tl = block_sum<256>(dl, red);
+  const double tr = block_sum<256>(dr, red);
+  if (threadIdx.x == 0) {
+    if (tl != 0.0) atomicAdd(a.dlam_l + r, tl);
+    if (tr != 0.0) atomicAdd(a.dlam_r + r, tr);
+  }
+}
+
+__global__ void zero_consumed_kernel(const int32_t* __restrict__ consumed, int64_t slot_sites, int n_sites,
+                                     double* __restrict__ gpool) {
+  const int64_t e = blockIdx.y;
+  if (!consumed[e]) return;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_sites) return;
+  d4 z;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) z.v[j] = 0.0;
+  st_site(gpool + (e * slot_sites + s) * 4, z);
+}
+
+// db -> dlam through b = -log(U)/lam, and accumulation of the per-matrix dQ (vcsmc.py:353-358 reversed)
+__global__ void __launch_bounds__(256) bwd_branch_kernel(int r, int64_t K, int jc, const double* __restrict__ dt,
+                                                         const double* __restrict__ dQ_each, const double* __restrict__ gB_l,
+                                                         const double* __restrict__ gB_r, const double* __restrict__ b_l,
+                                                         const double* __restrict__ b_r, const double* __restrict__ lam_l,
+                                                         const double* __restrict__ lam_r, double* __restrict__ dQ_acc,
+                                                         double* __restrict__ dlam_l, double* __restrict__ dlam_r) {
+  __shared__ double red[8];
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double dl = 0.0, dr = 0.0;
+  if (k < K) {
+    const double gl = dt[2 * k] + gB_l[k], gr = dt[2 * k + 1] + gB_r[k];
+    dl = gl * (-b_l[k] / lam_l[r]);
+    dr = gr * (-b_r[k] / lam_r[r]);
+    if (!jc) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) dQ_acc[k * 16 + e] += dQ_each[(2 * k) * 16 + e] + dQ_each[(2 * k + 1) * 16 + e];
+    }
+  }
+  const double tl = block_sum<256>(dl, red);
+  const double tr = block_sum<256>(dr, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(dlam_l + r, tl);
+    atomicAdd(dlam_r + r, tr);
+  }
+}
+
+// out[c] = sum_k in[k][c] (+ add[c]) in a fixed order: one CTA per column
+__global__ void __launch_bounds__(256) column_sum_kernel(const double* __restrict__ in, int64_t K, int C, int ld,
+                                                         double* __restrict__ out) {
+  __shared__ double red[8];
+  const int c = blockIdx.x;
+  double s = 0.0;
+  for (int64_t k = threadIdx.x; k < K; k += 256) s += in[k * ld + c];
+  const double t = block_sum<256>(s, red);
+  if (threadIdx.x == 0) out[c] += t;
+}
+
+// d/dpi of the leaves' sum_s log(pi . leaf[s]) weighted by c_leaf (column sums of the step-0 scatter)
+__global__ void __launch_bounds__(256) leaf_pi_grad_kernel(const uint8_t* __restrict__ codes, int64_t stride, int S,
+                                                           const double* __restrict__ pi, const double* __restrict__ cleaf,
+                                                           double* __restrict__ dpi) {
+  __shared__ double red[8];
+  const int leaf = blockIdx.x;
+  const double c = cleaf[leaf];
+  double p[4], acc[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) p[j] = pi[j];
+  for (int s = threadIdx.x; s < S; s += 256) {
+    const d4 L = leaf_site(codes[(int64_t)leaf * stride + s]);
+    double x = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x = fma(p[j], L.v[j], x);
+    const double inv = c / x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = fma(inv, L.v[j], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double t = block_sum<256>(acc[j], red);
+    if (threadIdx.x == 0) atomicAdd(dpi + j, t);
+  }
+}
+
+__global__ void zero_f64_kernel(double* p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.0;
+}
+
+}  // namespace
+}  // namespace vcsmc
+
+// ---------------------------------------------------------------------------------------------
+// host object
+// ---------------------------------------------------------------------------------------------
+using namespace vcsmc;
+
+struct vcsmc_sweep {
+  int N, S, jc, keep;
+  int64_t K;
+  char* ws;
+  int64_t ws_bytes;
+  // modes
+  bool fwd_gc;        // forward on the garbage-collected slot pool
+  bool retain;        // backward reuses the forward's nodes (no recompute)
+  int64_t pool_slots; // GC mode capacity
+  int chunk_sites;    // backward site-chunk size (== S when retain)
+  int tiles_max;
+  // offsets into ws
+  int64_t o_anc, o_lref, o_rref, o_nleaf, o_rempos, o_b_l, o_b_r, o_t2, o_cum_l, o_cum_r, o_lw, o_LL, o_lltilde, o_llR,
+      o_vminus, o_ell_node, o_stats, o_logz, o_ess, o_elbo, o_status, o_P, o_ids[2], o_cnt[2], o_slot[2], o_cdf,
+      o_u_pair, o_u_bl, o_u_br, o_u_res, o_ell_part, o_ell_new, o_lsrc, o_rsrc, o_dst, o_ldf, o_flags, o_childsum[2],
+      o_Dacc[2], o_cnew, o_consumed, o_bsrc_l, o_bsrc_r, o_bsrc_g, o_bdst, o_dP, o_dpi_each, o_dQ_acc, o_dQ_each, o_dt,
+      o_suf_l, o_suf_r, o_gB_l, o_gB_r, o_cleaf, o_pool;
+  int64_t pool_bytes;
+  std::vector<int64_t> rem_off;  // per step offset (bytes) into rempos
+  // uniform source
+  const float* x_pair = nullptr;
+  const double* x_bl = nullptr;
+  const double* x_br = nullptr;
+  const double* x_res = nullptr;
+  uint64_t seed = 0;
+  bool use_seed = true;
+  // hook
+  vcsmc_allreduce_fn allreduce = nullptr;
+  void* allreduce_user = nullptr;
+  double scalar_share = 1.0;
+  int skip_zero = 1;
+  // model pointers of the last forward (caller keeps them alive until backward)
+  const uint8_t* codes = nullptr;
+  const double* lam_l = nullptr;
+  const double* lam_r = nullptr;
+  const double* Q = nullptr;
+  const double* pi = nullptr;
+  bool forward_done = false;
+
+  template <typename T>
+  T* p(int64_t off) const { return reinterpret_cast<T*>(ws + off); }
+};
+
+namespace {
+
+int64_t full_pool_bytes(const vcsmc_sweep_config& c) {
+  return (int64_t)(c.n_taxa - 1) * c.n_particles * c.n_sites * 32;
+}
+
+// Carves the workspace.  pool_bytes < 0: only measure the table bytes.
+int64_t plan(vcsmc_sweep* h) {
+  const int N = h->N;
+  const int64_t K = h->K;
+  const int64_t E = (int64_t)(N - 1) * K;
+  Layout L;
+  h->o_status = L.take<int32_t>(8);
+  h->o_elbo = L.take<double>(1);
+  h->o_anc = L.take<int32_t>(E);
+  h->o_lref = L.take<int32_t>(E);
+  h->o_rref = L.take<int32_t>(E);
+  h->o_nleaf = L.take<int32_t>(E);
+  h->rem_off.assign(N - 1, 0);
+  int64_t rem_total = 0;
+  for (int r = 0; r < N - 1; ++r) {
+    h->rem_off[r] = rem_total;
+    rem_total += align_up(K * (int64_t)(N - r - 2), 16);
+  }
+  h->o_rempos = L.take<uint8_t>(rem_total + 16);
+  h->o_b_l = L.take<double>(E);
+  h->o_b_r = L.take<double>(E);
+  h->o_t2 = L.take<double>(2 * E);
+  h->o_cum_l = L.take<double>(E);
+  h->o_cum_r = L.take<double>(E);
+  h->o_lw = L.take<double>(E);
+  h->o_LL = L.take<double>(E);
+  h->o_lltilde = L.take<double>(K);
+  h->o_llR = L.take<double>(K);
+  h->o_vminus = L.take<int32_t>(K);
+  h->o_ell_node = L.take<double>(N + E);
+  h->o_stats = L.take<double>(4 * (int64_t)N);
+  h->o_logz = L.take<double>(N);
+  h->o_ess = L.take<double>(N);
+  h->o_P = L.take<double>(32 * E);
+  for (int i = 0; i < 2; ++i) {
+    h->o_ids[i] = L.take<int32_t>(K * N);
+    h->o_cnt[i] = L.take<int32_t>(K * N);
+    h->o_slot[i] = L.take<int32_t>(K * N);
+  }
+  h->o_cdf = L.take<double>(K);
+  h->o_u_pair = L.take<float>(K * N);
+  h->o_u_bl = L.take<double>(K);
+  h->o_u_br = L.take<double>(K);
+  h->o_u_res = L.take<double>(K);
+  h->tiles_max = merge_tiles(h->S);
+  h->o_ell_part = L.take<double>(K * h->tiles_max);
+  h->o_ell_new = L.take<double>(K);
+  h->o_lsrc = L.take<int32_t>(K);
+  h->o_rsrc = L.take<int32_t>(K);
+  h->o_dst = L.take<int32_t>(K);
+  h->o_ldf = L.take<double>(2 * (int64_t)N + 4);
+  if (h->keep) {
+    for (int i = 0; i < 2; ++i) {
+      h->o_childsum[i] = L.take<double>(K);
+      h->o_Dacc[i] = L.take<double>(K * N);
+    }
+    h->o_cnew = L.take<double>(E);
+    h->o_consumed = L.take<int32_t>(E);
+    h->o_bsrc_l = L.take<int32_t>(E);
+    h->o_bsrc_r = L.take<int32_t>(E);
+    h->o_bsrc_g = L.take<int32_t>(E);
+    h->o_bdst = L.take<int32_t>(E);
+    h->o_dP = L.take<double>(32 * E);
+    h->o_dpi_each = L.take<double>(4 * K);
+    h->o_dQ_acc = L.take<double>(16 * K);
+    h->o_dQ_each = L.take<double>(32 * K);
+    h->o_dt = L.take<double>(2 * K);
+    h->o_suf_l = L.take<double>(K);
+    h->o_suf_r = L.take<double>(K);
+    h->o_gB_l = L.take<double>(E);
+    h->o_gB_r = L.take<double>(E);
+    h->o_cleaf = L.take<double>(N);
+  }
+  return L.off;
+}
+
+int decide_modes(vcsmc_sweep* h, int64_t tables, int64_t ws_bytes, bool report) {
+  const int N = h->N, S = h->S;
+  const int64_t K = h->K;
+  const int64_t node_bytes = (int64_t)S * 32;
+  const int64_t full = (int64_t)(N - 1) * K * node_bytes;
+  const int64_t avail = ws_bytes - tables;
+  const int64_t need_retain = h->keep ? 2 * full : full;
+  if (avail >= need_retain) {
+    h->fwd_gc = false;
+    h->retain = true;
+    h->chunk_sites = S;
+    h->pool_slots = (int64_t)(N - 1) * K;
+    h->o_flags = tables;  // unused
+    h->o_pool = tables;
+    h->pool_bytes = need_retain;
+    return VCSMC_OK;
+  }
+  // GC forward: flags[P] + P slots
+  h->fwd_gc = true;
+  h->retain = false;
+  int64_t P = (avail - 4096) / (node_bytes + 4);
+  const int64_t Pmax = (int64_t)(N - 1) * K;
+  if (P > Pmax) P = Pmax;
+  if (P < 2 * K) {
+    if (report) set_error("workspace too small: GC pool would hold %lld slots, need >= %lld", (long long)P, (long long)(2 * K));
+    return VCSMC_ERR_ARG;
+  }
+  h->pool_slots = P;
+  h->o_flags = tables;
+  h->o_pool = align_up(tables + P * 4);
+  h->pool_bytes = ws_bytes - h->o_pool;
+  if (h->keep) {
+    int64_t Sc = (h->pool_bytes / 2) / ((int64_t)(N - 1) * K * 32);
+    Sc = Sc / 256 * 256;
+    if (Sc > S) Sc = S;
+    if (Sc < 256 && Sc < S) {
+      if (report) set_error("workspace too small for a 256-site backward chunk");
+      return VCSMC_ERR_ARG;
+    }
+    h->chunk_sites = (int)Sc;
+  } else {
+    h->chunk_sites = 0;
+  }
+  return VCSMC_OK;
+}
+
+int check_cfg(const vcsmc_sweep_config* c) {
+  if (!c) { set_error("null config"); return VCSMC_ERR_ARG; }
+  if (c->n_taxa < 2 || c->n_taxa > kMaxRoots) { set_error("n_taxa=%d out of range [2,%d]", c->n_taxa, kMaxRoots); return VCSMC_ERR_ARG; }
+  if (c->n_sites < 1) { set_error("n_sites must be >= 1"); return VCSMC_ERR_ARG; }
+  if (c->n_particles < 1) { set_error("n_particles must be >= 1"); return VCSMC_ERR_ARG; }
+  if ((int64_t)(c->n_taxa - 1) * c->n_particles + c->n_taxa > 2147483000LL) { set_error("too many nodes for int32 references"); return VCSMC_ERR_ARG; }
+  return VCSMC_OK;
+}
+
+double log_double_factorial_host(int m) {  // vcsmc.py:30-57
+  double r = 0.0;
+  for (int j = m; j >= 2; j -= 2) r += log((double)j);
+  return r;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vcsmc_sweep_query(const vcsmc_sweep_config* cfg, vcsmc_sweep_sizes* out) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (!out) { set_error("null out"); return VCSMC_ERR_ARG; }
+  vcsmc_sweep tmp;
+  tmp.N = cfg->n_taxa; tmp.S = cfg->n_sites; tmp.K = cfg->n_particles; tmp.jc = cfg->jc; tmp.keep = cfg->keep_for_backward;
+  const int64_t tables = plan(&tmp);
+  const int64_t full = full_pool_bytes(*cfg);
+  out->retain_bytes = tables + (cfg->keep_for_backward ? 2 * full : full);
+  const int64_t node = (int64_t)cfg->n_sites * 32;
+  const int64_t K = cfg->n_particles;
+  int64_t gc_min = 4096 + 2 * K * (node + 4) + 256;
+  if (cfg->keep_for_backward) {
+    const int64_t sc = cfg->n_sites < 256 ? cfg->n_sites : 256;
+    const int64_t chunk_min = 2 * (int64_t)(cfg->n_taxa - 1) * K * 32 * sc + 4 * 2 * K + 8192;
+    if (chunk_min > gc_min) gc_min = chunk_min;
+  }
+  out->min_bytes = tables + gc_min;
+  if (out->min_bytes > out->retain_bytes) out->min_bytes = out->retain_bytes;
+  return VCSMC_OK;
+}
+
+int vcsmc_sweep_create(const vcsmc_sweep_config* cfg, void* workspace, vcsmc_sweep_t** out) {
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (!workspace || !out) { set_error("null workspace/out"); return VCSMC_ERR_ARG; }
+  if (((uintptr_t)workspace & 255) != 0) { set_error("workspace must be 256-byte aligned"); return VCSMC_ERR_ARG; }
+  vcsmc_sweep* h = new (std::nothrow) vcsmc_sweep();
+  if (!h) { set_error("out of host memory"); return VCSMC_ERR_ARG; }
+  h->N = cfg->n_taxa; h->S = cfg->n_sites; h->K = cfg->n_particles; h->jc = cfg->jc; h->keep = cfg->keep_for_backward;
+  h->ws = (char*)workspace; h->ws_bytes = cfg->workspace_bytes;
+  const int64_t tables = plan(h);
+  rc = decide_modes(h, tables, cfg->workspace_bytes, true);
+  if (rc) { delete h; return rc; }
+  *out = h;
+  return VCSMC_OK;
+}
+
+void vcsmc_sweep_destroy(vcsmc_sweep_t* h) { delete h; }
+
+int vcsmc_sweep_set_allreduce(vcsmc_sweep_t* h, vcsmc_allreduce_fn fn, void* user) {
+  if (!h) return VCSMC_ERR_ARG;
+  h->allreduce = fn;
+  h->allreduce_user = user;
+  return VCSMC_OK;
+}
+
+int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value) {
+  if (!h || !name) return VCSMC_ERR_ARG;
+  if (!strcmp(name, "scalar_share")) h->scalar_share = value;
+  else if (!strcmp(name, "skip_zero")) h->skip_zero = value != 0.0;
+  else { set_error("unknown option %s", name); return VCSMC_ERR_ARG; }
+  return VCSMC_OK;
+}
+
+int vcsmc_sweep_set_uniforms(vcsmc_sweep_t* h, const float* u_pair, const double* u_bl, const double* u_br,
+                             const double* u_res) {
+  if (!h || !u_pair || !u_bl || !u_br || !u_res) { set_error("null uniforms"); return VCSMC_ERR_ARG; }
+  h->x_pair = u_pair; h->x_bl = u_bl; h->x_br = u_br; h->x_res = u_res;
+  h->use_seed = false;
+  return VCSMC_OK;
+}
+
+int vcsmc_sweep_set_seed(vcsmc_sweep_t* h, uint64_t seed) {
+  if (!h) return VCSMC_ERR_ARG;
+  h->seed = seed;
+  h->use_seed = true;
+  return VCSMC_OK;
+}
+
+int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* lam_l, const double* lam_r,
+                        const double* Q, const double* pi, void* stream) {
+  if (!h || !codes || !lam_l || !lam_r || !pi || (!h->jc && !Q)) { set_error("sweep_forward: null argument"); return VCSMC_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = h->N, S = h->S;
+  const int64_t K = h->K;
+  h->codes = codes; h->lam_l = lam_l; h->lam_r = lam_r; h->Q = Q; h->pi = pi;
+  h->forward_done = false;
+
+  // status + log-double-factorial table (host -> device, tiny)
+  VCSMC_CUDA(cudaMemsetAsync(h->p<int32_t>(h->o_status), 0, 8 * sizeof(int32_t), st));
+  {
+    std::vector<double> ldf(2 * N + 4, 0.0);
+    for (int m = 0; m < 2 * N + 4; ++m) ldf[m] = log_double_factorial_host(m);
+    VCSMC_CUDA(cudaMemcpyAsync(h->p<double>(h->o_ldf), ldf.data(), ldf.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    VCSMC_CUDA(cudaStreamSynchronize(st));  // ldf is a stack-lifetime host buffer
+  }
+  double* ell_node = h->p<double>(h->o_ell_node);
+  leaf_ell_kernel<<<N, 256, 0, st>>>(codes, S, S, pi, ell_node);
+  VCSMC_LAUNCH_CHECK("leaf_ell_kernel");
+  if (h->allreduce) {
+    int rc = h->allreduce(h->allreduce_user, ell_node, N, st);
+    if (rc) { set_error("allreduce hook failed (%d)", rc); return VCSMC_ERR_CUDA; }
+  }
+  double* pool = h->p<double>(h->o_pool);
+  int32_t* flags = h->p<int32_t>(h->o_flags);
+  int64_t pair_off = 0;
+
+  for (int r = 0; r < N - 1; ++r) {
+    const int n = N - r;
+    const int cur = r & 1, prev = cur ^ 1;
+    // uniforms of this rank event
+    const float* u_pair; const double *u_bl, *u_br, *u_res;
+    if (h->use_seed) {
+      int rc = launch_philox_step(h->seed, r, 0, K, n, h->p<float>(h->o_u_pair), h->p<double>(h->o_u_bl),
+                                  h->p<double>(h->o_u_br), h->p<double>(h->o_u_res), st);
+      if (rc) return rc;
+      u_pair = h->p<float>(h->o_u_pair); u_bl = h->p<double>(h->o_u_bl); u_br = h->p<double>(h->o_u_br); u_res = h->p<double>(h->o_u_res);
+    } else {
+      u_pair = h->x_pair + pair_off; u_bl = h->x_bl + (int64_t)r * K; u_br = h->x_br + (int64_t)r * K; u_res = h->x_res + (int64_t)r * K;
+      pair_off += K * n;
+    }
+    PrepArgs a;
+    a.r = r; a.n = n; a.N = N; a.gc = h->fwd_gc; a.K = K;
+    a.cdf = h->p<double>(h->o_cdf); a.u_res = u_res; a.u_pair = u_pair; a.u_bl = u_bl; a.u_br = u_br;
+    a.lam_l = lam_l; a.lam_r = lam_r;
+    a.ids_old = h->p<int32_t>(h->o_ids[prev]); a.cnt_old = h->p<int32_t>(h->o_cnt[prev]); a.slot_old = h->p<int32_t>(h->o_slot[prev]);
+    a.ids_new = h->p<int32_t>(h->o_ids[cur]); a.cnt_new = h->p<int32_t>(h->o_cnt[cur]); a.slot_new = h->p<int32_t>(h->o_slot[cur]);
+    a.LL_prev = r > 0 ? h->p<double>(h->o_LL) + (int64_t)(r - 1) * K : nullptr;
+    a.anc = h->p<int32_t>(h->o_anc) + (int64_t)r * K;
+    a.lref = h->p<int32_t>(h->o_lref) + (int64_t)r * K;
+    a.rref = h->p<int32_t>(h->o_rref) + (int64_t)r * K;
+    a.nleaf = h->p<int32_t>(h->o_nleaf) + (int64_t)r * K;
+    a.rempos = h->p<uint8_t>(h->o_rempos) + h->rem_off[r];
+    a.b_l = h->p<double>(h->o_b_l) + (int64_t)r * K;
+    a.b_r = h->p<double>(h->o_b_r) + (int64_t)r * K;
+    a.t2 = h->p<double>(h->o_t2) + (int64_t)r * 2 * K;
+    a.ll_tilde = h->p<double>(h->o_lltilde);
+    a.lsrc = h->p<int32_t>(h->o_lsrc); a.rsrc = h->p<int32_t>(h->o_rsrc); a.dst = h->p<int32_t>(h->o_dst);
+    step_prepare_kernel<<<(unsigned)((K + kPrepWarps - 1) / kPrepWarps), kPrepWarps * 32, (size_t)kPrepWarps * n * sizeof(float), st>>>(a);
+    VCSMC_LAUNCH_CHECK("step_prepare_kernel");
+
+    double* P = h->p<double>(h->o_P) + (int64_t)r * K * 32;
+    int rc = launch_transition_fwd(Q, a.t2, 2 * K, h->jc, P, st);
+    if (rc) return rc;
+
+    if (h->fwd_gc) {
+      VCSMC_CUDA(cudaMemsetAsync(flags, 0, (size_t)h->pool_slots * sizeof(int32_t), st));
+      count_launch();
+      gc_mark_kernel<<<(unsigned)((K * n + 255) / 256), 256, 0, st>>>(a.ids_new, a.slot_new, N, n, K, a.lsrc, a.rsrc, flags);
+      VCSMC_LAUNCH_CHECK("gc_mark_kernel");
+      gc_alloc_kernel<<<1, 1024, 0, st>>>(flags, h->pool_slots, K, N, n, a.dst, a.slot_new, h->p<int32_t>(h->o_status));
+      VCSMC_LAUNCH_CHECK("gc_alloc_kernel");
+    }
+    const int tiles = merge_tiles(S);
+    rc = launch_merge_fwd(codes, S, pool, S, a.lsrc, a.rsrc, a.dst, P, pi, K, S, h->jc, 0, h->p<double>(h->o_ell_part), st);
+    if (rc) return rc;
+
+    WeightArgs w;
+    w.r = r; w.n = n; w.N = N; w.tiles = tiles; w.K = K;
+    w.ell_part = h->p<double>(h->o_ell_part);
+    if (h->allreduce) {
+      rc = launch_ell_reduce(h->p<double>(h->o_ell_part), tiles, K, h->p<double>(h->o_ell_new), st);
+      if (rc) return rc;
+      rc = h->allreduce(h->allreduce_user, h->p<double>(h->o_ell_new), K, st);
+      if (rc) { set_error("allreduce hook failed (%d)", rc); return VCSMC_ERR_CUDA; }
+      w.ell_part = h->p<double>(h->o_ell_new);
+      w.tiles = 1;
+    }
+    w.ids_new = a.ids_new; w.cnt_new = a.cnt_new; w.ldf = h->p<double>(h->o_ldf);
+    w.lam_l = lam_l; w.lam_r = lam_r; w.b_l = a.b_l; w.b_r = a.b_r;
+    w.cum_l_prev = r > 0 ? h->p<double>(h->o_cum_l) + (int64_t)(r - 1) * K : nullptr;
+    w.cum_r_prev = r > 0 ? h->p<double>(h->o_cum_r) + (int64_t)(r - 1) * K : nullptr;
+    w.cum_l = h->p<double>(h->o_cum_l) + (int64_t)r * K;
+    w.cum_r = h->p<double>(h->o_cum_r) + (int64_t)r * K;
+    w.ll_tilde = a.ll_tilde; w.ell_node = ell_node;
+    w.lw = h->p<double>(h->o_lw) + (int64_t)r * K;
+    w.LL = h->p<double>(h->o_LL) + (int64_t)r * K;
+    w.vminus = h->p<int32_t>(h->o_vminus);
+    w.q = 1.0 / ((double)n * (double)(n - 1) / 2.0);
+    step_weights_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(w);
+    VCSMC_LAUNCH_CHECK("step_weights_kernel");
+
+    // log-sum-exp + CDF of this step's weights: logZ_r now, ancestors of the next rank event
+    rc = launch_resample_cdf(w.lw, K, h->p<double>(h->o_cdf), h->p<double>(h->o_stats) + r * 4, st);
+    if (rc) return rc;
+  }
+  finalize_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(
+      N, K, h->p<double>(h->o_stats), h->p<double>(h->o_LL) + (int64_t)(N - 2) * K, h->p<double>(h->o_b_l),
+      h->p<double>(h->o_b_r), lam_l, lam_r, log_double_factorial_host(2 * N - 3), h->p<double>(h->o_llR),
+      h->p<double>(h->o_elbo), h->p<double>(h->o_logz), h->p<double>(h->o_ess));
+  VCSMC_LAUNCH_CHECK("finalize_kernel");
+  h->forward_done = true;
+  return VCSMC_OK;
+}
+
+int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, double* dlam_r, double* dQ, double* dpi,
+                         void* stream) {
+  if (!h || !dlam_l || !dlam_r || !dpi || (!h->jc && !dQ)) { set_error("sweep_backward: null argument"); return VCSMC_ERR_ARG; }
+  if (!h->keep) { set_error("sweep was created with keep_for_backward = 0"); return VCSMC_ERR_STATE; }
+  if (!h->forward_done) { set_error("sweep_backward called before a successful sweep_forward"); return VCSMC_ERR_STATE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = h->N, S = h->S;
+  const int64_t K = h->K, E = (int64_t)(N - 1) * K;
+  int rc;
+
+  // ---- zero accumulators
+  VCSMC_CUDA(cudaMemsetAsync(dlam_l, 0, (N - 1) * sizeof(double), st));
+  VCSMC_CUDA(cudaMemsetAsync(dlam_r, 0, (N - 1) * sizeof(double), st));
+  if (dQ) VCSMC_CUDA(cudaMemsetAsync(dQ, 0, 16 * sizeof(double), st));
+  VCSMC_CUDA(cudaMemsetAsync(dpi, 0, 4 * sizeof(double), st));
+  VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_childsum[0]), 0, K * sizeof(double), st));
+  VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_childsum[1]), 0, K * sizeof(double), st));
+  VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_Dacc[0]), 0, K * N * sizeof(double), st));
+  VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_Dacc[1]), 0, K * N * sizeof(double), st));
+  VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_consumed), 0, E * sizeof(int32_t), st));
+  VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_dP), 0, 32 * E * sizeof(double), st));
+  VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_dpi_each), 0, 4 * K * sizeof(double), st));
+  VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_dQ_acc), 0, 16 * K * sizeof(double), st));
+  VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_suf_l), 0, K * sizeof(double), st));
+  VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_suf_r), 0, K * sizeof(double), st));
+  count_launch(14);
+
+  // ---- which nodes are ever consumed as a child; child/adjoint slots of every event
+  mark_consumed_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(h->p<int32_t>(h->o_lref), h->p<int32_t>(h->o_rref), E, N, h->p<int32_t>(h->o_consumed));
+  VCSMC_LAUNCH_CHECK("mark_consumed_kernel");
+  bwd_src_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(h->p<int32_t>(h->o_lref), h->p<int32_t>(h->o_rref), h->p<int32_t>(h->o_consumed), E, N,
+                                                              h->p<int32_t>(h->o_bsrc_l), h->p<int32_t>(h->o_bsrc_r), h->p<int32_t>(h->o_bsrc_g), h->p<int32_t>(h->o_bdst));
+  VCSMC_LAUNCH_CHECK("bwd_src_kernel");
+
+  // ---- scalar pass: coefficients of every node, site-independent gradient terms
+  for (int r = N - 2; r >= 0; --r) {
+    const int cur = r & 1, nxt = cur ^ 1;
+    CoefArgs a;
+    a.r = r; a.n = N - r; a.N = N; a.K = K; a.grad = grad_elbo; a.share = h->scalar_share;
+    a.lw = h->p<double>(h->o_lw) + (int64_t)r * K;
+    a.stats = h->p<double>(h->o_stats);
+    a.anc = h->p<int32_t>(h->o_anc) + (int64_t)r * K;
+    a.rempos = h->p<uint8_t>(h->o_rempos) + h->rem_off[r];
+    a.childsum_cur = h->p<double>(h->o_childsum[cur]); a.childsum_next = h->p<double>(h->o_childsum[nxt]);
+    a.Dacc_cur = h->p<double>(h->o_Dacc[cur]); a.Dacc_next = h->p<double>(h->o_Dacc[nxt]);
+    a.cnew = h->p<double>(h->o_cnew) + (int64_t)r * K;
+    a.lam_l = h->lam_l; a.lam_r = h->lam_r;
+    a.b_l = h->p<double>(h->o_b_l) + (int64_t)r * K; a.b_r = h->p<double>(h->o_b_r) + (int64_t)r * K;
+    a.cum_l = h->p<double>(h->o_cum_l) + (int64_t)r * K; a.cum_r = h->p<double>(h->o_cum_r) + (int64_t)r * K;
+    a.suf_l = h->p<double>(h->o_suf_l); a.suf_r = h->p<double>(h->o_suf_r);
+    a.gB_l = h->p<double>(h->o_gB_l) + (int64_t)r * K; a.gB_r = h->p<double>(h->o_gB_r) + (int64_t)r * K;
+    a.dlam_l = dlam_l; a.dlam_r = dlam_r;
+    bwd_coef_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(a);
+    VCSMC_LAUNCH_CHECK("bwd_coef_kernel");
+    // the buffers just consumed become the accumulation targets of step r-2
+    VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_childsum[cur]), 0, K * sizeof(double), st));
+    VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_Dacc[cur]), 0, K * N * sizeof(double), st));
+    count_launch(2);
+  }
+  // after r = 0 the scatter target was Dacc[(0&1)^1] = Dacc[1]: per-particle coefficients of the N leaves
+  VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_cleaf), 0, N * sizeof(double), st));
+  column_sum_kernel<<<N, 256, 0, st>>>(h->p<double>(h->o_Dacc[1]), K, N, N, h->p<double>(h->o_cleaf));
+  VCSMC_LAUNCH_CHECK("column_sum_kernel");
+  leaf_pi_grad_kernel<<<N, 256, 0, st>>>(h->codes, S, S, h->pi, h->p<double>(h->o_cleaf), dpi);
+  VCSMC_LAUNCH_CHECK("leaf_pi_grad_kernel");
+
+  // ---- per-site pass: reverse pruning, by site chunks
+  const int Sc = h->chunk_sites;
+  double* lpool;
+  double* gpool;
+  if (h->retain) {
+    lpool = h->p<double>(h->o_pool);
+    gpool = lpool + E * (int64_t)S * 4;
+  } else {
+    lpool = h->p<double>(h->o_pool);
+    gpool = lpool + E * (int64_t)Sc * 4;
+  }
+  int n_chunks = 0;
+  for (int s0 = 0; s0 < S; s0 += Sc, ++n_chunks) {
+    const int nc = (S - s0 < Sc) ? S - s0 : Sc;
+    const uint8_t* codes_c = h->codes + s0;
+    if (!h->retain) {
+      // recompute the forward for this chunk, materialising only nodes that are consumed later
+      for (int r = 0; r < N - 1; ++r) {
+        rc = launch_merge_fwd(codes_c, S, lpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
+                              h->p<int32_t>(h->o_bdst) + (int64_t)r * K, h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, K, nc,
+                              h->jc, 1, h->p<double>(h->o_ell_part), st);
+        if (rc) return rc;
+      }
+    }
+    // zero the adjoint slots of consumed nodes
+    for (int64_t e0 = 0; e0 < E; e0 += 65535) {
+      const int64_t ne = (E - e0 < 65535) ? E - e0 : 65535;
+      dim3 grid((nc + 255) / 256, (unsigned)ne, 1);
+      zero_consumed_kernel<<<grid, 256, 0, st>>>(h->p<int32_t>(h->o_consumed) + e0, Sc, nc, gpool + e0 * (int64_t)Sc * 4);
+      VCSMC_LAUNCH_CHECK("zero_consumed_kernel");
+    }
+    for (int r = N - 2; r >= 0; --r) {
+      rc = launch_merge_bwd(codes_c, S, lpool, gpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
+                            h->p<int32_t>(h->o_bsrc_g) + (int64_t)r * K, h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi,
+                            h->p<double>(h->o_cnew) + (int64_t)r * K, K, nc, h->jc, h->skip_zero, h->p<double>(h->o_dP) + (int64_t)r * K * 32,
+                            h->p<double>(h->o_dpi_each), st);
+      if (rc) return rc;
+    }
+  }
+  {
+    int32_t nch = n_chunks;
+    VCSMC_CUDA(cudaMemcpyAsync(h->p<int32_t>(h->o_status) + 2, &nch, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    VCSMC_CUDA(cudaStreamSynchronize(st));
+  }
+
+  // ---- dP -> (db, dQ) -> dlam
+  for (int r = 0; r < N - 1; ++r) {
+    rc = launch_transition_bwd(h->Q, h->p<double>(h->o_t2) + (int64_t)r * 2 * K, h->p<double>(h->o_dP) + (int64_t)r * K * 32, 2 * K, h->jc,
+                               h->p<double>(h->o_dt), h->jc ? nullptr : h->p<double>(h->o_dQ_each), st);
+    if (rc) return rc;
+    bwd_branch_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(
+        r, K, h->jc, h->p<double>(h->o_dt), h->p<double>(h->o_dQ_each), h->p<double>(h->o_gB_l) + (int64_t)r * K,
+        h->p<double>(h->o_gB_r) + (int64_t)r * K, h->p<double>(h->o_b_l) + (int64_t)r * K, h->p<double>(h->o_b_r) + (int64_t)r * K,
+        h->lam_l, h->lam_r, h->p<double>(h->o_dQ_acc), dlam_l, dlam_r);
+    VCSMC_LAUNCH_CHECK("bwd_branch_kernel");
+  }
+  if (!h->jc) {
+    column_sum_kernel<<<16, 256, 0, st>>>(h->p<double>(h->o_dQ_acc), K, 16, 16, dQ);
+    VCSMC_LAUNCH_CHECK("column_sum_kernel");
+  }
+  column_sum_kernel<<<4, 256, 0, st>>>(h->p<double>(h->o_dpi_each), K, 4, 4, dpi);
+  VCSMC_LAUNCH_CHECK("column_sum_kernel");
+  return VCSMC_OK;
+}
+
+void* vcsmc_sweep_output(vcsmc_sweep_t* h, const char* name) {
+  if (!h || !name) return nullptr;
+  struct { const char* n; int64_t off; } tab[] = {
+      {"elbo", h->o_elbo}, {"log_weights", h->o_lw}, {"log_likelihood", h->o_LL}, {"log_likelihood_tilde", h->o_lltilde},
+      {"log_likelihood_R", h->o_llR}, {"left_branches", h->o_b_l}, {"right_branches", h->o_b_r}, {"v_minus", h->o_vminus},
+      {"ancestors", h->o_anc}, {"left_ref", h->o_lref}, {"right_ref", h->o_rref}, {"leaf_counts", h->o_nleaf},
+      {"log_z", h->o_logz}, {"ess", h->o_ess}, {"status", h->o_status}, {"ell_node", h->o_ell_node}};
+  for (auto& t : tab)
+    if (!strcmp(t.n, name)) return h->ws + t.off;
+  if (h->keep && !strcmp(name, "node_coef")) return h->ws + h->o_cnew;
+  return nullptr;
+}
+
+}  // extern "C"

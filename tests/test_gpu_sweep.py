@@ -1,0 +1,216 @@
+"""GPU parity of the whole sweep (forward + reverse sweep) against the CPU oracle, through the C ABI."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vcsmc_oracle as O
+from vcsmc_test_helpers import gpu_uniforms, random_params, refs_from_oracle, synthetic_genome
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available()
+    from phylo_b200 import ops as _ops
+    return _ops
+
+
+def dev(x):
+    return torch.as_tensor(x).cuda().contiguous()
+
+
+def run_gpu(ops, genome, K, p, U, jc, workspace_bytes=None, grads=True, skip_zero=True):
+    N, S = genome.shape[0], genome.shape[1]
+    codes = ops.pack_alignment(dev(genome))
+    lam_l, lam_r, Q, pi = O.model_from_params(p)
+    sw = ops.Sweep(N, S, K, jc, keep_for_backward=grads, workspace_bytes=workspace_bytes)
+    sw.set_uniforms(*gpu_uniforms(U))
+    sw.set_option("skip_zero", 1.0 if skip_zero else 0.0)
+    elbo = sw.forward(codes, dev(lam_l), dev(lam_r), None if jc else dev(Q), dev(pi.reshape(-1)))
+    out = {k: sw.output(k).cpu().numpy().copy() for k in
+           ("log_weights", "log_likelihood", "log_likelihood_tilde", "log_likelihood_R", "left_branches",
+            "right_branches", "v_minus", "ancestors", "left_ref", "right_ref", "leaf_counts")}
+    out["elbo"] = float(elbo.item())
+    g = None
+    if grads:
+        g = [None if t is None else t.cpu().numpy() for t in sw.backward(1.0)]
+    out["info"] = sw.check_status()
+    return out, g, sw
+
+
+def oracle_param_grads(genome, K, p, U):
+    """Oracle gradients w.r.t. (lam_l, lam_r, Q, pi) -- the quantities the C ABI differentiates."""
+    lam_l, lam_r, Q, pi = [t.detach().clone().requires_grad_(True) for t in O.model_from_params(p)]
+    res = O.sweep(genome, K, lam_l, lam_r, Q, pi, U)
+    gs = torch.autograd.grad(res.elbo, [lam_l, lam_r, Q, pi], allow_unused=True)
+    return res, [None if g is None else g.numpy() for g in gs]
+
+
+def compare_forward(out, res, N, K):
+    anc = res.ancestors.copy()
+    np.testing.assert_array_equal(out["ancestors"][1:], anc[1:])                       # bit-exact ancestors
+    lref, rref = refs_from_oracle(res, N, K)
+    np.testing.assert_array_equal(out["left_ref"], lref)                                # bit-exact pair choices
+    np.testing.assert_array_equal(out["right_ref"], rref)
+    np.testing.assert_allclose(out["left_branches"], res.left_branches.detach().numpy(), rtol=1e-14)
+    np.testing.assert_allclose(out["log_weights"], res.log_weights.detach().numpy(), rtol=RTOL)
+    np.testing.assert_allclose(out["log_likelihood"], res.log_likelihood.detach().numpy(), rtol=RTOL)
+    np.testing.assert_allclose(out["log_likelihood_tilde"], res.log_likelihood_tilde.detach().numpy(), rtol=RTOL)
+    np.testing.assert_allclose(out["log_likelihood_R"], res.log_likelihood_R.detach().numpy(), rtol=RTOL)
+    np.testing.assert_array_equal(out["v_minus"], res.v_minus.numpy())
+    assert out["elbo"] == pytest.approx(float(res.elbo), rel=RTOL)
+
+
+def compare_grads(g, g_ref, jc):
+    names = ["dlam_l", "dlam_r", "dQ", "dpi"]
+    for name, a, b in zip(names, g, g_ref):
+        if jc and name in ("dQ",):
+            continue
+        scale = np.abs(b).max() + 1e-300
+        np.testing.assert_allclose(a, b, rtol=1e-7, atol=1e-9 * scale, err_msg=name)
+
+
+@pytest.mark.parametrize("jc", [True, False])
+@pytest.mark.parametrize("K", [1, 16, 64])
+def test_sweep_primate_subset(ops, primate_genome, jc, K):
+    g = primate_genome[:8, :300]
+    N = g.shape[0]
+    p = random_params(N, jc, seed=K)
+    U = O.Uniforms.draw(N, K, seed=100 + K)
+    res, g_ref = oracle_param_grads(g, K, p, U)
+    out, grads, sw = run_gpu(ops, g, K, p, U, jc)
+    assert sw.retained
+    compare_forward(out, res, N, K)
+    compare_grads(grads, g_ref, jc)
+
+
+@pytest.mark.parametrize("jc", [True, False])
+def test_sweep_primate_full(ops, primate_genome, jc):
+    """primate.p, all 12 taxa x 898 sites (BASELINE config 1/2 shape at an oracle-sized K)."""
+    g = primate_genome
+    N, K = g.shape[0], 32
+    p = O.Params.init(N, jc)           # the reference's initial parameters (vcsmc.py:119-131)
+    U = O.Uniforms.draw(N, K, seed=7)
+    res, g_ref = oracle_param_grads(g, K, p, U)
+    out, grads, _ = run_gpu(ops, g, K, p, U, jc)
+    compare_forward(out, res, N, K)
+    compare_grads(grads, g_ref, jc)
+    assert -7600 < out["elbo"] < -6500   # where the README figure's curves start
+
+
+@pytest.mark.parametrize("jc", [True, False])
+def test_sweep_flat_weights_many_lineages(ops, jc):
+    """Short alignment => flat weights => many distinct ancestors and shared nodes with several consumers."""
+    g = synthetic_genome(9, 5, seed=3, gaps=0.1)
+    N, K = 9, 128
+    p = random_params(N, jc, seed=5)
+    U = O.Uniforms.draw(N, K, seed=11)
+    res, g_ref = oracle_param_grads(g, K, p, U)
+    assert len(np.unique(res.ancestors[4])) > 10
+    out, grads, _ = run_gpu(ops, g, K, p, U, jc)
+    compare_forward(out, res, N, K)
+    compare_grads(grads, g_ref, jc)
+    # dense reverse sweep (no zero-adjoint skipping) gives the same gradients
+    _, grads_dense, _ = run_gpu(ops, g, K, p, U, jc, skip_zero=False)
+    compare_grads(grads_dense, g_ref, jc)
+
+
+@pytest.mark.parametrize("jc", [True, False])
+def test_sweep_gc_pool_and_chunked_backward(ops, primate_genome, jc):
+    """Smallest workspace: garbage-collected forward pool + site-chunked recompute backward == retained mode."""
+    g = primate_genome[:10]
+    N, K = g.shape[0], 48
+    p = random_params(N, jc, seed=2)
+    U = O.Uniforms.draw(N, K, seed=3)
+    res, g_ref = oracle_param_grads(g, K, p, U)
+    probe = ops.Sweep(N, g.shape[1], K, jc, workspace_bytes=None)
+    small = probe.min_bytes
+    assert small < probe.retain_bytes
+    del probe
+    out, grads, sw = run_gpu(ops, g, K, p, U, jc, workspace_bytes=small)
+    assert not sw.retained and out["info"]["backward_chunks"] >= 3
+    compare_forward(out, res, N, K)
+    compare_grads(grads, g_ref, jc)
+
+
+def test_sweep_pool_exhaustion_is_reported(ops):
+    """Flat weights keep many nodes alive; a 2K-slot pool must fail loudly, not silently corrupt."""
+    from phylo_b200._lib import VcsmcError
+    g = synthetic_genome(16, 3, seed=1)
+    N, K = 16, 256
+    p = O.Params.init(N, True)
+    U = O.Uniforms.draw(N, K, seed=1)
+    probe = ops.Sweep(N, 3, K, True, keep_for_backward=False)
+    small = probe.min_bytes
+    del probe
+    codes = ops.pack_alignment(dev(g))
+    lam_l, lam_r, Q, pi = O.model_from_params(p)
+    sw = ops.Sweep(N, 3, K, True, keep_for_backward=False, workspace_bytes=small)
+    sw.set_uniforms(*gpu_uniforms(U))
+    sw.forward(codes, dev(lam_l), dev(lam_r), None, dev(pi.reshape(-1)))
+    try:
+        info = sw.check_status()
+        assert info["peak_pool_slots"] <= 2 * K + 64   # it fitted: fine, and says how much it used
+    except VcsmcError as e:
+        assert e.code == -3
+
+
+def test_single_site_batch(ops, primate_genome):
+    """batch_size=1 (BASELINE config 1): the reference mis-shapes here (tf.squeeze, quirk Q9); intended semantics."""
+    g = primate_genome[:6, 17:18]
+    N, K = 6, 16
+    p = O.Params.init(N, True)
+    U = O.Uniforms.draw(N, K, seed=4)
+    res, g_ref = oracle_param_grads(g, K, p, U)
+    out, grads, _ = run_gpu(ops, g, K, p, U, True)
+    compare_forward(out, res, N, K)
+    compare_grads(grads, g_ref, True)
+
+
+def test_autograd_through_parameterisation(ops, primate_genome):
+    """sweep_elbo under torch autograd reproduces the oracle's gradients w.r.t. the reference's four variables."""
+    g = primate_genome[:7, :200]
+    N, K = 7, 32
+    p = random_params(N, False, seed=9)
+    U = O.Uniforms.draw(N, K, seed=10)
+    res, g_ref = O.elbo_and_grads(g, K, p, U)
+    codes = ops.pack_alignment(dev(g))
+    sw = ops.Sweep(N, g.shape[1], K, False)
+    sw.set_uniforms(*gpu_uniforms(U))
+    leaves = [dev(t).requires_grad_(True) for t in p.tensors()]
+    lam_l, lam_r = torch.exp(leaves[0]), torch.exp(leaves[1])
+    off = 1.0 - torch.eye(4, dtype=torch.float64, device="cuda")
+    e = torch.exp(leaves[2] * off) * off
+    qe = e / e.sum(dim=1, keepdim=True)
+    Q = qe - torch.diag(qe.sum(dim=1))
+    pi = torch.softmax(leaves[3], dim=0)
+    elbo = ops.sweep_elbo(sw, codes, lam_l, lam_r, Q, pi)
+    assert float(elbo) == pytest.approx(float(res.elbo), rel=RTOL)
+    (-elbo).backward()
+    for a, b in zip(leaves, g_ref):
+        scale = float(b.abs().max())
+        np.testing.assert_allclose(-a.grad.cpu().numpy(), b.numpy(), rtol=1e-7, atol=1e-9 * scale)
+
+
+def test_seeded_sweep_matches_oracle_fed_the_same_philox_uniforms(ops, primate_genome):
+    """Philox mode: dump the uniforms the sweep consumes, feed them to the oracle, compare."""
+    g = primate_genome[:9, :400]
+    N, K, seed = 9, 64, 20261018
+    p = O.Params.init(N, False)
+    pair, bl, br, rs = [], [], [], []
+    for r in range(N - 1):
+        a, b, c, d = ops.philox_step_uniforms(seed, r, 0, K, N - r)
+        pair.append(a.cpu().numpy()); bl.append(b.cpu().numpy()); br.append(c.cpu().numpy()); rs.append(d.cpu().numpy())
+    U = O.Uniforms(pair, np.stack(bl), np.stack(br), np.stack(rs))
+    lam_l, lam_r, Q, pi = O.model_from_params(p)
+    res = O.sweep(g, K, lam_l, lam_r, Q, pi, U)
+    codes = ops.pack_alignment(dev(g))
+    sw = ops.Sweep(N, g.shape[1], K, False, keep_for_backward=False)
+    sw.set_seed(seed)
+    elbo = sw.forward(codes, dev(lam_l), dev(lam_r), dev(Q), dev(pi.reshape(-1)))
+    assert float(elbo) == pytest.approx(float(res.elbo), rel=RTOL)
+    np.testing.assert_array_equal(sw.output("ancestors").cpu().numpy()[1:], res.ancestors[1:])
