@@ -70,6 +70,7 @@ def compare_grads(g, g_ref, jc):
     for name, a, b in zip(names, g, g_ref):
         if jc and name in ("dQ",):
             continue
+        b = np.asarray(b).reshape(np.asarray(a).shape)
         scale = np.abs(b).max() + 1e-300
         np.testing.assert_allclose(a, b, rtol=1e-7, atol=1e-9 * scale, err_msg=name)
 
