@@ -1,0 +1,314 @@
+"""Benchmark of the VCSMC hot path: fwd+grad sweeps on a synthetic alignment, particle.site merges/sec.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one ELBO-grad step (one forward SMC sweep + the reverse sweep, what sess.run([optimizer, cost])
+does at vcsmc.py:534) over the whole synthetic alignment.  A sweep performs K*S*(N-1) particle.site merges
+forward and the same number backward; `value` = K*S*(N-1) / seconds per step (fwd+grad), whole job.
+
+Workload (BASELINE.json configs[4], the one the metric's target is quoted on): 64 taxa x 10,000 sites x 65,536
+particles, i.i.d. uniform nucleotides (numpy PCG64 seed 0), reference initial parameters (rates 10, `GTR' logits
+1/4, uniform pi), float64.  N GPUs: the alignment's SITES are sharded (strong scaling).
+
+--impl reference times the restated reference (oracle/vcsmc_oracle.py: TensorFlow 1.15 cannot be installed
+in this image) on the host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+METRIC = "particle-site merges/sec (fwd+grad VCSMC sweep)"
+UNIT = "merges/s"
+BYTES_FWD, BYTES_BWD = 64.0, 128.0   # algorithmic bytes per merge, fp64 (SURVEY 8d / BASELINE.md section 3)
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="native", choices=["native", "reference"])
+    p.add_argument("--taxa", type=int, default=64)
+    p.add_argument("--sites", type=int, default=10000)
+    p.add_argument("--particles", type=int, default=65536)
+    p.add_argument("--model", default="gtr", choices=["gtr", "jc"])
+    p.add_argument("--dense", action="store_true", help="reverse sweep without zero-adjoint skipping")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-sample", default="64x1000x32", help="taxa x sites x particles of the CPU baseline sample")
+    return p.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the restated reference (oracle) on the host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_sample_run(sample: str, jc: bool, steps: int, warmup: int):
+    """Time fwd+grad sweeps of the oracle on a bounded sample; returns (merges/s, cores, description, s/step)."""
+    from oracle import vcsmc_oracle as O
+    from phylo_b200.loader import synthetic_alignment
+    n, s, k = [int(x) for x in sample.split("x")]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = synthetic_alignment(n, s)["genome"]
+    p = O.Params.init(n, jc)
+    times = []
+    for it in range(warmup + steps):
+        U = O.Uniforms.draw(n, k, seed=it)
+        t0 = time.perf_counter()
+        O.elbo_and_grads(g, k, p, U)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    per = float(np.mean(times))
+    desc = "%d taxa x %d sites x %d particles, %s, fwd+grad, restated reference (TensorFlow unavailable) in torch-CPU fp64" % (
+        n, s, k, "JC" if jc else "GTR")
+    return k * s * (n - 1) / per, cores, desc, per
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    jc = args.model == "jc"
+    n, s, k = [int(x) for x in args.cpu_sample.split("x")]
+    val, cores, desc, per = cpu_sample_run(args.cpu_sample, jc, max(args.steps, 1), args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "VCSMC %s fwd+grad sweep, 64 taxa x 10000 sites x 65536 particles (bounded sample: %s)" % (
+            args.model.upper(), desc)},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# native arm
+# ----------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch.distributed as dist
+    from phylo_b200 import _lib, ops
+    from phylo_b200.loader import synthetic_alignment
+    from phylo_b200.vcsmc import VCSMC
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, S, K = args.taxa, args.sites, args.particles
+    jc = args.model == "jc"
+
+    class A:  # the argparse namespace the reference's class reads (vcsmc.py:111-120)
+        M = 10; branch_prior = float(np.log(10)); jcmodel = jc; optimizer = "GradientDescentOptimizer"
+        dataset = "synthetic_%dx%d" % (N, S); nested = False; n_particles = K
+
+    datadict = synthetic_alignment(N, S, seed=0)
+    model = VCSMC(datadict, K, A, seed=0)
+    genome_host = torch.from_numpy(datadict["genome"]).pin_memory()
+    variables = model.trainable_variables()
+
+    def step(seed):
+        for v in variables:
+            v.grad = None
+        elbo = model.sample_phylogenies(need_grad=True, seed=seed)
+        (-elbo).backward()
+        model._allreduce_grads()
+        return elbo
+
+    def step_e2e(seed):
+        """Public-API step from HOST buffers: genome H2D + pack, parameters H2D, sweep fwd+grad, loss+grads D2H."""
+        model.codes = ops.pack_alignment(genome_host.to(model.device, non_blocking=True))
+        host_params = [v.detach().cpu() for v in variables]
+        for v, hp in zip(variables, host_params):
+            v.data.copy_(hp.pin_memory(), non_blocking=True)
+        elbo = step(seed)
+        out = [elbo.detach().cpu()] + [v.grad.cpu() for v in variables]
+        return out
+
+    sweep = None
+    for w in range(args.warmup):
+        step(1000 + w)
+    sweep = model._last
+    sweep.set_option("skip_zero", 0.0 if args.dense else 1.0)
+    if args.dense:
+        step(999)
+    info = sweep.check_status()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-timed region: inputs resident in HBM
+    sweep.set_option("profile", 1.0)
+    clocks = ClockSampler(local)
+    launches0 = _lib.launch_count()
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        elbo = step(i)
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    launches = _lib.launch_count() - launches0
+    ms = e0.elapsed_time(e1)
+    prof = sweep.profile()
+    sweep.set_option("profile", 0.0)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    merges = float(K) * S * (N - 1)
+    value = merges / (ms_step * 1e-3)
+
+    # ---- end-to-end region: host buffers in, loss + grads out, every step
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = merges / (float(te.item()) / args.steps)
+    nparam = sum(v.numel() for v in variables)
+    h2d = int(genome_host.numel() * 8 + nparam * 8)
+    d2h = int(8 + nparam * 8)
+
+    # ---- roofline of the dominant kernel (per-launch CUDA-event times recorded inside the timed region)
+    S_loc = len(model._local_sites(None))
+    alg = {"merge_fwd": BYTES_FWD * K * S_loc * (N - 1) * args.steps,
+           "merge_fwd_recompute": BYTES_FWD * K * S_loc * (N - 1) * args.steps,
+           "merge_bwd": BYTES_BWD * K * S_loc * (N - 1) * args.steps}
+    dom = max(prof, key=lambda k: prof[k][0])
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    dom_ms, dom_n = prof[dom]
+    achieved = alg[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom + ("_jc" if jc else "_gtr"))
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "launches": dom_n,
+                "avg_launch_ms": dom_ms / max(dom_n, 1),
+                "algorithmic_bytes_per_launch": alg[dom] / max(dom_n, 1),
+                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+                "note": "algorithmic bytes: 64 B/merge forward, 128 B/merge backward (fp64); with ESS~1 the children "
+                        "of a rank event are shared by all particles and are served from L2, so DRAM traffic is below "
+                        "the algorithmic figure (DESIGN.md section 5)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "VCSMC %s fwd+grad sweep, %d taxa x %d sites x %d particles, i.i.d. uniform nucleotides "
+                               "(PCG64 seed 0), reference initial parameters" % (args.model.upper(), N, S, K),
+                   "taxa": N, "sites": S, "particles": K, "model": args.model, "sharding": "sites/%d" % world,
+                   "l2": "inputs larger than L2 (node pool of %.1f GB streamed per sweep)" % (sweep.workspace.numel() / 1e9),
+                   "backward": "dense" if args.dense else "zero-adjoint events skipped (identical results)",
+                   "nodes_retained": bool(sweep.retained), "backward_chunks": info["backward_chunks"],
+                   "peak_pool_slots": info["peak_pool_slots"]},
+        "roofline": roofline,
+        "frac_of_fwdgrad_roofline": value * (BYTES_FWD + BYTES_BWD) / 1e9 / peak / world,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "elbo": float(elbo),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cval, cores, desc, per = cpu_sample_run(args.cpu_sample, jc, 1, 0)
+        line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": desc + " (1 sweep, %.1f s)" % per}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_native(a)

@@ -145,7 +145,8 @@ int vcsmc_sweep_set_allreduce(vcsmc_sweep_t* h, vcsmc_allreduce_fn fn, void* use
 /* Options: "scalar_share" (default 1): fraction of the site-independent gradient terms this rank contributes
  * (site sharding: 1 on rank 0, 0 elsewhere, then sum the gradients across ranks);
  * "skip_zero" (default 1): backward skips rank events whose adjoint is exactly zero (W underflowed to 0 and no
- * descendant uses the node) -- results are identical, set 0 to force the dense reverse sweep. */
+ * descendant uses the node) -- results are identical, set 0 to force the dense reverse sweep;
+ * "profile" (default 0): record CUDA events around every merge launch, read with vcsmc_sweep_profile. */
 int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value);
 
 /* Uniform source: explicit arrays (u_pair is the ragged concatenation over r of [K, N-r] float32;
@@ -161,11 +162,18 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
 int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, double* dlam_r, double* dQ,
                          double* dpi, void* stream);
 
+/* Per-kernel device time of the merge launches since the option "profile" was set to 1 (CUDA events on the
+ * launching stream): out_host[6] = {ms, launches} for the forward merge, the recompute merge of the chunked
+ * backward, and the backward merge.  Synchronises on the recorded events and resets the counters. */
+int vcsmc_sweep_profile(vcsmc_sweep_t* h, double* out_host);
+
 /* Device pointers into the workspace, valid after forward:
  *   "elbo"[1] "log_weights"[N-1,K] "log_likelihood"[N-1,K] "log_likelihood_tilde"[K]
  *   "log_likelihood_R"[K] "left_branches"[N-1,K] "right_branches"[N-1,K] (float64)
  *   "v_minus"[K] "ancestors"[N-1,K] "left_ref"[N-1,K] "right_ref"[N-1,K] "leaf_counts"[N-1,K] (int32)
- *   "log_z"[N-1] "ess"[N-1] (float64)   "status"[4] (int32: error, peak pool slots, chunks, skipped events)
+ *   "log_z"[N-1] "ess"[N-1] (float64)   "status"[8] (int32: error, peak pool slots, backward chunks, ...)
+ *   "rem_positions" (uint8, ragged: rank event r holds [K, N-r-2] at byte offset sum_{r'<r} align16(K (N-r'-2)):
+ *   the positions, in the ancestor's forest, of the subtrees a particle keeps, in the reference's order)
  * Returns NULL for an unknown name. */
 void* vcsmc_sweep_output(vcsmc_sweep_t* h, const char* name);
 

@@ -57,6 +57,7 @@ _SIGNATURES = {
     "vcsmc_sweep_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "vcsmc_sweep_backward": (C.c_int, [_P, C.c_double, _P, _P, _P, _P, _P]),
     "vcsmc_sweep_output": (_P, [_P, C.c_char_p]),
+    "vcsmc_sweep_profile": (C.c_int, [_P, C.POINTER(C.c_double)]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

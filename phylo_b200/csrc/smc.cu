@@ -112,8 +112,6 @@ __global__ void __launch_bounds__(kCdfThreads) resample_cdf_kernel(const double*
     off += exp((lw[i] - lse) - mlog);
     cdf[i] = off;
   }
-  // make the last entry exactly the reported total so that upper_bound(u*total) with u<1 always lands < K
-  if (e == K && b < e) cdf[K - 1] = fmax(cdf[K - 1], 0.0);
 }
 
 __global__ void resample_search_kernel(const double* __restrict__ cdf, const double* __restrict__ stats,
@@ -145,7 +143,14 @@ __global__ void philox_step_kernel(uint64_t seed, int r, int64_t k0, int64_t K, 
       philox4x32_10(p, s0, s1);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (j + q < n) u_pair[i * n + j + q] = u32_to_unit_f32(p[q]);
+        if (j + q < n) {
+          // 16 random bits + the 8-bit position: values inside one particle's row are pairwise DISTINCT.  Exact
+          // float32 ties make tf.nn.top_k keep one subtree twice and drop another (vcsmc.py:304-305, SURVEY Q-ties);
+          // at K = 65,536 that happens a few times per sweep and the truncated forest then wins every resampling.
+          // The proposal kernels keep the reference's tie semantics; this generator just never produces a tie.
+          const uint32_t bits = ((p[q] >> 8) & 0xFFFF00u) | (uint32_t)((j + q) & 0xFF);
+          u_pair[i * n + j + q] = (float)bits * 5.9604644775390625e-8f;
+        }
     }
   }
 }

@@ -513,6 +513,30 @@ struct vcsmc_sweep {
   const double* Q = nullptr;
   const double* pi = nullptr;
   bool forward_done = false;
+  // optional per-kernel timing of the merge launches (bench.py roofline): kind 0 = forward merge,
+  // 1 = recompute merge of the chunked backward, 2 = backward merge
+  bool profile = false;
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> ev_kind;
+  size_t ev_used = 0;
+  int prof_begin(int kind, cudaStream_t st) {
+    if (!profile) return 0;
+    if (ev_used + 2 > ev.size()) {
+      for (int i = 0; i < 256; ++i) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return -1;
+        ev.push_back(e);
+      }
+    }
+    ev_kind.push_back(kind);
+    return cudaEventRecord(ev[ev_used++], st) == cudaSuccess ? 0 : -1;
+  }
+  void prof_end(cudaStream_t st) {
+    if (profile) cudaEventRecord(ev[ev_used++], st);
+  }
+  ~vcsmc_sweep() {
+    for (auto e : ev) cudaEventDestroy(e);
+  }
 
   template <typename T>
   T* p(int64_t off) const { return reinterpret_cast<T*>(ws + off); }
@@ -716,6 +740,7 @@ int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value) {
   if (!h || !name) return VCSMC_ERR_ARG;
   if (!strcmp(name, "scalar_share")) h->scalar_share = value;
   else if (!strcmp(name, "skip_zero")) h->skip_zero = value != 0.0;
+  else if (!strcmp(name, "profile")) { h->profile = value != 0.0; h->ev_used = 0; h->ev_kind.clear(); }
   else { set_error("unknown option %s", name); return VCSMC_ERR_ARG; }
   return VCSMC_OK;
 }
@@ -810,7 +835,9 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
       VCSMC_LAUNCH_CHECK("gc_alloc_kernel");
     }
     const int tiles = merge_tiles(S);
+    h->prof_begin(0, st);
     rc = launch_merge_fwd(codes, S, pool, S, a.lsrc, a.rsrc, a.dst, P, pi, K, S, h->jc, 0, h->p<double>(h->o_ell_part), st);
+    h->prof_end(st);
     if (rc) return rc;
 
     WeightArgs w;
@@ -935,9 +962,11 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     if (!h->retain) {
       // recompute the forward for this chunk, materialising only nodes that are consumed later
       for (int r = 0; r < N - 1; ++r) {
+        h->prof_begin(1, st);
         rc = launch_merge_fwd(codes_c, S, lpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
                               h->p<int32_t>(h->o_bdst) + (int64_t)r * K, h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, K, nc,
                               h->jc, 1, h->p<double>(h->o_ell_part), st);
+        h->prof_end(st);
         if (rc) return rc;
       }
     }
@@ -949,10 +978,12 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
       VCSMC_LAUNCH_CHECK("zero_consumed_kernel");
     }
     for (int r = N - 2; r >= 0; --r) {
+      h->prof_begin(2, st);
       rc = launch_merge_bwd(codes_c, S, lpool, gpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
                             h->p<int32_t>(h->o_bsrc_g) + (int64_t)r * K, h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi,
                             h->p<double>(h->o_cnew) + (int64_t)r * K, K, nc, h->jc, h->skip_zero, h->p<double>(h->o_dP) + (int64_t)r * K * 32,
                             h->p<double>(h->o_dpi_each), st);
+      h->prof_end(st);
       if (rc) return rc;
     }
   }
@@ -982,13 +1013,31 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   return VCSMC_OK;
 }
 
+int vcsmc_sweep_profile(vcsmc_sweep_t* h, double* out_host) {
+  // out_host[6] = {ms, launches} for kind 0 (forward merge), 1 (recompute merge), 2 (backward merge); resets.
+  if (!h || !out_host) return VCSMC_ERR_ARG;
+  for (int i = 0; i < 6; ++i) out_host[i] = 0.0;
+  for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+    VCSMC_CUDA(cudaEventSynchronize(h->ev[i + 1]));
+    float ms = 0.f;
+    VCSMC_CUDA(cudaEventElapsedTime(&ms, h->ev[i], h->ev[i + 1]));
+    const int kind = h->ev_kind[i / 2];
+    out_host[2 * kind] += ms;
+    out_host[2 * kind + 1] += 1.0;
+  }
+  h->ev_used = 0;
+  h->ev_kind.clear();
+  return VCSMC_OK;
+}
+
 void* vcsmc_sweep_output(vcsmc_sweep_t* h, const char* name) {
   if (!h || !name) return nullptr;
   struct { const char* n; int64_t off; } tab[] = {
       {"elbo", h->o_elbo}, {"log_weights", h->o_lw}, {"log_likelihood", h->o_LL}, {"log_likelihood_tilde", h->o_lltilde},
       {"log_likelihood_R", h->o_llR}, {"left_branches", h->o_b_l}, {"right_branches", h->o_b_r}, {"v_minus", h->o_vminus},
       {"ancestors", h->o_anc}, {"left_ref", h->o_lref}, {"right_ref", h->o_rref}, {"leaf_counts", h->o_nleaf},
-      {"log_z", h->o_logz}, {"ess", h->o_ess}, {"status", h->o_status}, {"ell_node", h->o_ell_node}};
+      {"log_z", h->o_logz}, {"ess", h->o_ess}, {"status", h->o_status}, {"ell_node", h->o_ell_node},
+      {"rem_positions", h->o_rempos}};
   for (auto& t : tab)
     if (!strcmp(t.n, name)) return h->ws + t.off;
   if (h->keep && !strcmp(name, "node_coef")) return h->ws + h->o_cnew;

@@ -257,6 +257,23 @@ class Sweep:
         check(self._lib.vcsmc_sweep_backward(self._h, float(grad_elbo), _ptr(dl), _ptr(dr), _ptr(dQ), _ptr(dpi), _stream()))
         return dl, dr, dQ, dpi
 
+    def profile(self) -> Dict[str, Tuple[float, int]]:
+        """{kernel: (total ms, launches)} of the merge launches since set_option('profile', 1); resets."""
+        buf = (C.c_double * 6)()
+        check(self._lib.vcsmc_sweep_profile(self._h, buf))
+        return {"merge_fwd": (buf[0], int(buf[1])), "merge_fwd_recompute": (buf[2], int(buf[3])), "merge_bwd": (buf[4], int(buf[5]))}
+
+    def rem_positions(self):
+        """Per rank event r, the uint8 [K, N-r-2] table of kept forest positions (host numpy), see the header."""
+        ptr = self._lib.vcsmc_sweep_output(self._h, b"rem_positions")
+        base = ptr - self.workspace.data_ptr()
+        out, off = [], 0
+        for r in range(self.N - 1):
+            cnt = self.K * (self.N - r - 2)
+            out.append(self.workspace[base + off: base + off + cnt].cpu().numpy().reshape(self.K, self.N - r - 2))
+            off += (cnt + 15) // 16 * 16
+        return out
+
     def check_status(self) -> Dict[str, int]:
         """Synchronises; raises if the device-side status word reports an error (e.g. node pool exhausted)."""
         st = self.output("status").cpu().tolist()

@@ -1,0 +1,290 @@
+"""``VCSMC(datadict, K, args).train(...)``: the reference's class interface (vcsmc.py:103-645) over the CUDA sweep.
+
+Same constructor, same four trainable variables (vcsmc.py:119-124), same ``train`` protocol (site minibatches
+drawn once, last slice never trained on -- quirk Q8 --, per-epoch full-data evaluation, ``results.p`` /
+``run_parameters.txt`` with the reference's keys).  What differs, by design: no TensorFlow graph; the sweep and
+its gradient are hand-written sm_100a kernels (libvcsmc_b200.so); the alignment is packed once into device
+codes instead of being replicated K-fold on the host (vcsmc.py:479); randomness comes from a counter-based
+generator keyed by (seed, rank event, particle) because the reference seeds nothing.
+
+Multi-GPU: when torch.distributed is initialised the SITES of every (mini)batch are sharded across ranks; each
+rank holds all K particles for its sites, the only per-rank-event collective is an all-reduce of the K new
+log-likelihood sums, and every rank derives identical weights and ancestors ("site sharding").
+"""
+from __future__ import annotations
+
+import math
+import os
+import pickle
+import random
+from datetime import datetime
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+
+F64 = torch.float64
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+
+
+class VCSMC:
+    """
+    VCSMC takes as input a dictionary (datadict) with two keys:
+     taxa: a list of n strings denoting taxa
+     genome: a 3 tensor [N,S,A] of genomes for the n taxa one hot encoded (ambiguous = all ones)
+    """
+
+    def __init__(self, datadict, K, args=None, device: Optional[str] = None, seed: Optional[int] = None):
+        self.args = args
+        self.taxa = list(datadict["taxa"])
+        self.genome_NxSxA = np.asarray(datadict["genome"], dtype=np.float64)
+        self.K = int(K)
+        self.M = getattr(args, "M", 10)
+        self.N = len(self.genome_NxSxA)
+        self.S = len(self.genome_NxSxA[0])
+        self.A = len(self.genome_NxSxA[0, 0])
+        if self.A != 4:
+            raise NotImplementedError("phylo_b200 kernels are specialised for a 4-letter alphabet (got A=%d)" % self.A)
+        if not torch.cuda.is_available():
+            raise RuntimeError("phylo_b200 needs a CUDA device: there is no CPU fallback")
+        self.device = torch.device(device or ("cuda:%d" % torch.cuda.current_device()))
+        self.jcmodel = bool(getattr(args, "jcmodel", False))
+        branch_prior = float(getattr(args, "branch_prior", math.log(10.0)))
+        # the reference's variables (vcsmc.py:119-124); exp()/softmax parameterisations are applied in _model()
+        dev = self.device
+        self.left_branches_var = torch.full((self.N - 1,), branch_prior, dtype=F64, device=dev, requires_grad=True)
+        self.right_branches_var = torch.full((self.N - 1,), branch_prior, dtype=F64, device=dev, requires_grad=True)
+        if not self.jcmodel:
+            self.y_q = torch.full((self.A, self.A), 1.0 / self.A, dtype=F64, device=dev, requires_grad=True)
+            self.y_station = torch.full((self.A,), 1.0 / self.A, dtype=F64, device=dev, requires_grad=True)
+        else:
+            self.y_q = None
+            self.y_station = None
+        self.seed = int(seed if seed is not None else np.random.SeedSequence().entropy % (2 ** 63))
+        self._step_counter = 0
+        self._sweeps: Dict[tuple, ops.Sweep] = {}
+        dist = _dist()
+        self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+        # (a) pack the alignment ONCE into 4-bit device codes
+        self.codes = ops.pack_alignment(torch.from_numpy(self.genome_NxSxA).to(dev))
+
+    # -- parameters ---------------------------------------------------------------------------
+    def trainable_variables(self) -> List[torch.Tensor]:
+        v = [self.left_branches_var, self.right_branches_var]
+        if not self.jcmodel:
+            v += [self.y_q, self.y_station]
+        return v
+
+    def get_Q(self) -> torch.Tensor:
+        """vcsmc.py:138-148 (general) / :126-129 (JC)."""
+        eye = torch.eye(self.A, dtype=F64, device=self.device)
+        if self.jcmodel:
+            return torch.full((self.A, self.A), 1.0 / self.A, dtype=F64, device=self.device) - eye
+        off = 1.0 - eye
+        e = torch.exp(self.y_q * off) * off
+        q = e / e.sum(dim=1, keepdim=True)
+        return q - torch.diag(q.sum(dim=1))
+
+    def get_stationary_probs(self) -> torch.Tensor:
+        """vcsmc.py:133-136, shape [1,A]."""
+        if self.jcmodel:
+            return torch.full((1, self.A), 1.0 / self.A, dtype=F64, device=self.device)
+        return torch.softmax(self.y_station, dim=0).unsqueeze(0)
+
+    def _model(self):
+        return (torch.exp(self.left_branches_var), torch.exp(self.right_branches_var), self.get_Q(),
+                self.get_stationary_probs().reshape(-1))
+
+    # -- the sweep ----------------------------------------------------------------------------
+    def _local_sites(self, site_idx: Optional[np.ndarray]) -> np.ndarray:
+        idx = np.arange(self.S, dtype=np.int32) if site_idx is None else np.asarray(site_idx, dtype=np.int32)
+        if self.world > 1:
+            idx = np.array_split(idx, self.world)[self.rank]   # contiguous shards of the batch's site list
+        return idx
+
+    def _sweep_for(self, n_sites: int, need_grad: bool) -> ops.Sweep:
+        key = (n_sites, need_grad)
+        if key not in self._sweeps:
+            if need_grad and (n_sites, False) in self._sweeps:
+                del self._sweeps[(n_sites, False)]
+            sw = ops.Sweep(self.N, n_sites, self.K, self.jcmodel, keep_for_backward=need_grad, device=self.device)
+            if self.world > 1:
+                import torch.distributed as dist
+                sw.set_allreduce(lambda t: dist.all_reduce(t))
+                sw.set_option("scalar_share", 1.0 if self.rank == 0 else 0.0)
+            self._sweeps[key] = sw
+        return self._sweeps[key]
+
+    def sample_phylogenies(self, site_idx: Optional[np.ndarray] = None, need_grad: bool = True,
+                           seed: Optional[int] = None) -> torch.Tensor:
+        """Main sampling routine (vcsmc.py:406-451): one sweep over the given sites; returns the ELBO.
+
+        With ``need_grad`` the result is differentiable w.r.t. ``trainable_variables()`` (reverse sweep kernels).
+        """
+        local = self._local_sites(site_idx)
+        if len(local) == 0:
+            raise ValueError("a rank received zero sites: batch smaller than the number of GPUs")
+        if site_idx is None and self.world == 1:
+            codes = self.codes
+        else:
+            codes = ops.gather_sites(self.codes, torch.from_numpy(local).to(self.device))
+        sw = self._sweep_for(len(local), need_grad)
+        if seed is None:
+            self._step_counter += 1
+            seed = (self.seed + 0x9E3779B97F4A7C15 * self._step_counter) % (2 ** 64)
+        sw.set_seed(seed)
+        lam_l, lam_r, Q, pi = self._model()
+        self._last = sw
+        if need_grad:
+            elbo = ops.sweep_elbo(sw, codes, lam_l, lam_r, None if self.jcmodel else Q, pi)
+        else:
+            with torch.no_grad():
+                elbo = sw.forward(codes, lam_l.contiguous(), lam_r.contiguous(), None if self.jcmodel else Q.contiguous(),
+                                  pi.contiguous()).clone().reshape(())
+        self.elbo = elbo
+        self.cost = -elbo
+        return elbo
+
+    def _allreduce_grads(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            for v in self.trainable_variables():
+                if v.grad is not None:
+                    dist.all_reduce(v.grad)
+
+    def outputs(self) -> Dict[str, np.ndarray]:
+        """The tensors the reference evaluates per epoch (vcsmc.py:538-551), as numpy arrays."""
+        sw = self._last
+        sw.check_status()
+        names = ("log_weights", "log_likelihood", "log_likelihood_tilde", "log_likelihood_R", "left_branches",
+                 "right_branches", "v_minus", "ancestors", "left_ref", "right_ref")
+        return {n: sw.output(n).cpu().numpy().copy() for n in names}
+
+    def jump_chains(self, out: Optional[Dict[str, np.ndarray]] = None) -> np.ndarray:
+        """Taxa-label bookkeeping of vcsmc.py:306-313,:324,:424-425 rebuilt on the host from the integer tables.
+
+        Returns the [K, 1 + N + (N-1) + ... + 2] string array the reference calls ``jump_chains`` (first column '').
+        The labels are built correctly per particle; the reference's vcsmc.py reads particle 0's labels for every
+        particle (quirk Q6), which is not reproduced.
+        """
+        out = out or self.outputs()
+        sw = self._last
+        rem = sw.rem_positions()
+        N, K = self.N, self.K
+        label = {i: self.taxa[i] for i in range(N)}
+        forest = np.tile(np.arange(N, dtype=np.int64), (K, 1))
+        cols = [np.full((K, 1), "", dtype=object)]
+        for r in range(N - 1):
+            if r > 0:
+                forest = forest[out["ancestors"][r]]
+            cols.append(np.vectorize(label.get, otypes=[object])(forest))
+            for k in range(K):
+                label[N + r * K + k] = label[int(out["left_ref"][r, k])] + "+" + label[int(out["right_ref"][r, k])]
+            new_id = (N + r * K + np.arange(K, dtype=np.int64))[:, None]
+            forest = np.concatenate([np.take_along_axis(forest, rem[r].astype(np.int64), axis=1), new_id], axis=1)
+        self.final_trees = np.vectorize(label.get, otypes=[object])(forest[:, 0])
+        return np.concatenate(cols, axis=1)
+
+    # -- training driver (vcsmc.py:453-645) -----------------------------------------------------
+    def batch_slices(self, n_sites: int, batch_size: int):
+        """vcsmc.py:453-464: a fixed random partition of the sites, drawn once."""
+        sites_list = list(range(n_sites))
+        num_batches = n_sites // batch_size
+        slices = []
+        for _ in range(num_batches):
+            sampled = random.sample(sites_list, batch_size)
+            slices.append(sampled)
+            sites_list = list(set(sites_list) - set(sampled))
+        if len(sites_list) != 0:
+            slices.append(sites_list)
+        return slices
+
+    def train(self, epochs=100, batch_size=128, learning_rate=0.001, memory_optimization="on", save=True,
+              verbose=True):
+        """Run the train op and evaluate variables, like vcsmc.py:466-645 (``memory_optimization`` is accepted and
+        ignored: it toggles a TensorFlow Grappler pass, vcsmc.py:474-477)."""
+        K = self.K
+        self.lr = learning_rate
+        say = print if (verbose and self.rank == 0) else (lambda *a, **k: None)
+        slices = self.batch_slices(self.S, batch_size)
+        say("================= Dataset shape: KxNxSxA =================")
+        say((K, self.N, self.S, self.A))
+        say("==========================================================")
+        opt_name = getattr(self.args, "optimizer", "GradientDescentOptimizer")
+        if opt_name == "Adam":
+            self.optimizer = torch.optim.Adam(self.trainable_variables(), lr=self.lr, betas=(0.9, 0.999), eps=1e-8)
+        else:
+            self.optimizer = torch.optim.SGD(self.trainable_variables(), lr=self.lr)
+
+        init_elbo = float(self.sample_phylogenies(need_grad=False))
+        say("===================\nInitial evaluation of ELBO:", round(init_elbo, 3))
+        say("===================")
+        save_dir = None
+        if save and self.rank == 0:
+            tm = str(datetime.now())
+            root = "./results/" + str(getattr(self.args, "dataset", "dataset")) + "/" + str(getattr(self.args, "nested", False)) + \
+                "/" + str(getattr(self.args, "n_particles", K)) + "/"
+            save_dir = root + (tm[:10] + "-" + tm[11:13] + tm[14:16] + tm[17:19]) + "/"
+            os.makedirs(save_dir, exist_ok=True)
+            with open(save_dir + "run_parameters.txt", "w") as rp:
+                rp.write("Initial evaluation of ELBO : " + str(init_elbo) + "\n")
+                for k, v in (vars(self.args).items() if self.args is not None else []):
+                    rp.write(str(k) + " : " + str(v) + "\n")
+                rp.write(str(self.optimizer))
+
+        say("Training begins --")
+        elbos, Qmatrices, left_branches, right_branches, jump_chain_evolution = [], [], [], [], []
+        log_weights, ll, ll_tilde, ll_R = [], [], [], []
+        for i in range(epochs):
+            bt = datetime.now()
+            for j in range(len(slices) - 1):                       # quirk Q8: the last slice is never trained on
+                self.optimizer.zero_grad(set_to_none=True)
+                cost = -self.sample_phylogenies(np.asarray(slices[j], dtype=np.int32), need_grad=True)
+                cost.backward()
+                self._allreduce_grads()
+                self.optimizer.step()
+            cost = -float(self.sample_phylogenies(need_grad=False))  # per-epoch full-data evaluation, vcsmc.py:538-551
+            out = self.outputs()
+            stats = self.get_stationary_probs().detach().cpu().numpy()
+            Qs = self.get_Q().detach().cpu().numpy()
+            lb_param = torch.exp(self.left_branches_var).detach().cpu().numpy()
+            rb_param = torch.exp(self.right_branches_var).detach().cpu().numpy()
+            jc = self.jump_chains(out) if K * self.N <= 1 << 16 else None
+            say("Epoch", i + 1)
+            say("ELBO\n", round(-cost, 3))
+            say("Stationary probabilities\n", stats)
+            say("Q-matrix\n", Qs)
+            say("LB param:\n", lb_param)
+            say("RB param:\n", rb_param)
+            elbos.append(-cost)
+            Qmatrices.append(Qs)
+            left_branches.append(out["left_branches"])
+            right_branches.append(out["right_branches"])
+            ll.append(out["log_likelihood"])
+            ll_tilde.append(out["log_likelihood_tilde"])
+            ll_R.append(out["log_likelihood_R"])
+            log_weights.append(out["log_weights"])
+            jump_chain_evolution.append(jc)
+            say("Time spent\n", datetime.now() - bt, "\n-----------------------------------------")
+        say("Done training.")
+
+        best = int(np.argmax(elbos)) if elbos else 0
+        resultDict = {"cost": np.asarray(elbos), "nParticles": self.K, "nTaxa": self.N, "lr": self.lr,
+                      "log_weights": np.asarray(log_weights), "Qmatrices": np.asarray(Qmatrices),
+                      "left_branches": left_branches, "right_branches": right_branches, "log_lik": np.asarray(ll),
+                      "ll_tilde": np.asarray(ll_tilde), "log_lik_R": np.asarray(ll_R),
+                      "jump_chain_evolution": jump_chain_evolution, "best_epoch": best,
+                      "best_log_lik": np.asarray(ll_R)[best] if ll_R else None,
+                      "best_jump_chain": jump_chain_evolution[best] if jump_chain_evolution else None}
+        if save_dir is not None:
+            with open(save_dir + "results.p", "wb") as f:
+                pickle.dump(resultDict, f)
+        say("Finished...")
+        self.save_dir = save_dir
+        return resultDict
