@@ -2,8 +2,19 @@
 //
 // Forward replaces broadcast_conditional_likelihood_K (vcsmc.py:180-188) fused with the NEW node's term of
 // compute_forest_posterior (vcsmc.py:238-242).  Backward is the per-site part of what TF autodiff does to
-// those ops (vcsmc.py:488-491).  HBM-bound 4x4 contraction on CUDA cores: one 256-bit access per site
-// vector, per-particle P matrices in registers, fixed-order CTA reduction of the site log-likelihoods.
+// those ops (vcsmc.py:488-491).  A 4x4 contraction per site on CUDA cores (no tensor cores: 2 flop/B in fp64).
+//
+// Work decomposition (both directions): particles are visited in an order sorted by their (unordered) pair of
+// child nodes; one work item = a GROUP of up to R consecutive sorted particles x one TILE of 256*SPT sites.
+// A thread keeps its sites of the two children in registers (one 256-bit access per site vector) and only
+// reloads a child when the sorted order moves on to a different node.  After resampling most particles descend
+// from few ancestors and share children, so a child is read once per group instead of once per particle; with
+// all-distinct children the kernel degenerates to a plain streaming merge.  The per-particle P matrices of a
+// group are staged in shared memory with one cooperative load.  Backward additionally accumulates the adjoint
+// of a shared child in registers across the run and issues ONE set of fp64 atomics per run instead of one per
+// particle, and reduces the per-particle 4x4 adjoints with a halving-butterfly warp transpose.
+#include <limits.h>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -11,15 +22,19 @@ namespace vcsmc {
 
 namespace {
 
+constexpr int kRMax = 16;       // particles per group (shared-memory staging)
+constexpr int kWarps = kTileThreads / 32;
+constexpr int kNone = INT_MIN;  // "no child loaded"
+
 // P for one child.  General: 16 entries.  JC: P = o*1 1^T + (d-o) I, so lp_j = o*sum(L) + (d-o) L_j.
 template <bool JC>
 struct Trans;
 template <>
 struct Trans<false> {
   double p[16];
-  __device__ __forceinline__ void load(const double* __restrict__ P) {
+  __device__ __forceinline__ void load(const double* P) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) p[i] = __ldg(P + i);
+    for (int i = 0; i < 16; ++i) p[i] = P[i];
   }
   // row-vector convention (quirk Q5): out_j = sum_i L_i P[i][j]
   __device__ __forceinline__ d4 apply(const d4& L) const {
@@ -49,9 +64,9 @@ struct Trans<false> {
 template <>
 struct Trans<true> {
   double dmo, o;  // diag - off, off
-  __device__ __forceinline__ void load(const double* __restrict__ P) {
-    const double d = __ldg(P);
-    o = __ldg(P + 1);
+  __device__ __forceinline__ void load(const double* P) {
+    const double d = P[0];
+    o = P[1];
     dmo = d - o;
   }
   __device__ __forceinline__ d4 apply(const d4& L) const {
@@ -64,6 +79,43 @@ struct Trans<true> {
   __device__ __forceinline__ d4 apply_t(const d4& g) const { return apply(g); }  // symmetric
 };
 
+__device__ __forceinline__ d4 zero4() {
+  d4 z;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) z.v[j] = 0.0;
+  return z;
+}
+
+struct ChildRef {
+  const uint8_t* codes_row;
+  const double* node;
+};
+__device__ __forceinline__ ChildRef child_ref(int src, const uint8_t* codes, int64_t codes_stride, const double* pool,
+                                              int64_t slot_sites) {
+  ChildRef c;
+  c.codes_row = src < 0 ? codes + (int64_t)(-src - 1) * codes_stride : nullptr;
+  c.node = src < 0 ? nullptr : pool + (int64_t)src * slot_sites * 4;
+  return c;
+}
+__device__ __forceinline__ d4 load_child(const ChildRef& c, int s) {
+  return c.codes_row ? leaf_site(__ldg(c.codes_row + s)) : ld_site(c.node + (int64_t)s * 4);
+}
+
+// Sum of v[i] over the 32 lanes of a warp for 32 values at once: afterwards lane L holds the total of v[L]
+// in v[0].  Halving butterfly: 31 exchanges instead of 32 x 5.
+__device__ __forceinline__ void warp_transpose_sum32(double (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16, cnt = 16; s >= 1; s >>= 1, cnt >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < cnt; ++i) {
+      const double send = up ? v[i] : v[i + cnt];
+      const double keep = up ? v[i + cnt] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
 struct FwdArgs {
   const uint8_t* codes;
   int64_t codes_stride;
@@ -72,75 +124,125 @@ struct FwdArgs {
   const int32_t* lsrc;
   const int32_t* rsrc;
   const int32_t* dst;
+  const int32_t* order;  // sorted visiting order (null: identity)
+  const int32_t* count;  // number of leading entries of `order` to process (null: K)
   const double* P;
   const double* pi;
+  int64_t K;
   int n_sites;
   int tiles;
+  int R;
   int skip_unstored;  // re-forward of the chunked backward: nodes nobody consumes are not materialised
-  double* ell_part;
+  double* ell_part;   // [K][tiles][kWarps]
 };
 
-__device__ __forceinline__ d4 load_child(const uint8_t* __restrict__ codes_row, const double* __restrict__ node, int s) {
-  return codes_row ? leaf_site(__ldg(codes_row + s)) : ld_site(node + (int64_t)s * 4);
+// stage the group's particle descriptors and P matrices in shared memory (canonical child order a <= b)
+template <typename Extra>
+__device__ __forceinline__ void stage_group(const int32_t* order, const int32_t* lsrc, const int32_t* rsrc,
+                                            const double* P, int64_t j0, int nj, int* s_k, int* s_a, int* s_b,
+                                            double (*sP)[32], Extra&& extra) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  if (tid < nj) {
+    const int k = order ? order[j0 + tid] : (int)(j0 + tid);
+    const int ls = lsrc[k], rs = rsrc[k];
+    const bool sw = ls > rs;
+    s_a[tid] = sw ? rs : ls;
+    s_b[tid] = sw ? ls : rs;
+    s_k[tid] = sw ? ~k : k;  // swap flag in the sign
+    extra(tid, k);
+  }
+  __syncthreads();
+  for (int e = tid; e < nj * 32; e += kTileThreads) {
+    const int j = e >> 5, i = e & 31;
+    const int kk = s_k[j];
+    const bool sw = kk < 0;
+    const int k = sw ? ~kk : kk;
+    sP[j][i] = __ldg(P + (int64_t)k * 32 + (i ^ (sw ? 16 : 0)));
+  }
+  __syncthreads();
 }
 
-template <bool JC>
-__global__ void __launch_bounds__(kTileThreads) merge_fwd_kernel(const FwdArgs a) {
-  __shared__ double red[kTileThreads / 32];
-  const int64_t w = blockIdx.x;
-  const int64_t k = w / a.tiles;
-  const int tile = (int)(w - k * a.tiles);
-  const int ls = a.lsrc[k], rs = a.rsrc[k], ds = a.dst ? a.dst[k] : (int)k;
-  if (a.skip_unstored && ds < 0) return;
-
-  Trans<JC> Pl, Pr;
-  Pl.load(a.P + k * 32);
-  Pr.load(a.P + k * 32 + 16);
+template <bool JC, int SPT>
+__global__ void __launch_bounds__(kTileThreads, 2) merge_fwd_kernel(const FwdArgs a) {
+  __shared__ __align__(16) double sP[kRMax][32];
+  __shared__ int s_k[kRMax], s_a[kRMax], s_b[kRMax], s_dst[kRMax];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t count = a.count ? (int64_t)*a.count : a.K;
+  const int R = a.R;
+  const int64_t total = ((count + R - 1) / R) * a.tiles;
   double pi[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
-  const uint8_t* lcodes = ls < 0 ? a.codes + (int64_t)(-ls - 1) * a.codes_stride : nullptr;
-  const uint8_t* rcodes = rs < 0 ? a.codes + (int64_t)(-rs - 1) * a.codes_stride : nullptr;
-  const double* lnode = ls < 0 ? nullptr : a.pool + (int64_t)ls * a.slot_sites * 4;
-  const double* rnode = rs < 0 ? nullptr : a.pool + (int64_t)rs * a.slot_sites * 4;
-  double* out = ds < 0 ? nullptr : a.pool + (int64_t)ds * a.slot_sites * 4;
 
-  const int s0 = tile * kTileSites + threadIdx.x;
-  d4 Ll[kSitesPerThread], Lr[kSitesPerThread];
+  for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    const int64_t g = w / a.tiles;
+    const int t = (int)(w - g * a.tiles);
+    const int64_t j0 = g * R;
+    const int nj = (int)min((int64_t)R, count - j0);
+    stage_group(a.order, a.lsrc, a.rsrc, a.P, j0, nj, s_k, s_a, s_b, sP,
+                [&](int i, int k) { s_dst[i] = a.dst ? a.dst[k] : k; });
+    const int sbase = t * (kTileThreads * SPT) + tid;
+    int pa = kNone, pb = kNone;
+    d4 La[SPT], Lb[SPT];
+    for (int j = 0; j < nj; ++j) {
+      const int ds = s_dst[j];
+      if (a.skip_unstored && ds < 0) continue;
+      const int ca = s_a[j], cb = s_b[j];
+      if (ca != pa) {
+        const ChildRef c = child_ref(ca, a.codes, a.codes_stride, a.pool, a.slot_sites);
 #pragma unroll
-  for (int it = 0; it < kSitesPerThread; ++it) {
-    const int s = s0 + it * kTileThreads;
-    if (s < a.n_sites) {
-      Ll[it] = load_child(lcodes, lnode, s);
-      Lr[it] = load_child(rcodes, rnode, s);
-    }
-  }
-  double acc = 0.0;
-#pragma unroll
-  for (int it = 0; it < kSitesPerThread; ++it) {
-    const int s = s0 + it * kTileThreads;
-    if (s < a.n_sites) {
-      const d4 lp = Pl.apply(Ll[it]), rp = Pr.apply(Lr[it]);
-      d4 nw;
-      double x = 0.0;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        nw.v[j] = lp.v[j] * rp.v[j];
-        x = fma(pi[j], nw.v[j], x);
+        for (int q = 0; q < SPT; ++q) {
+          const int s = sbase + q * kTileThreads;
+          if (s < a.n_sites) La[q] = load_child(c, s);
+        }
+        pa = ca;
       }
-      if (out) st_site(out + (int64_t)s * 4, nw);
-      acc += log(x);
+      if (cb != pb) {
+        const ChildRef c = child_ref(cb, a.codes, a.codes_stride, a.pool, a.slot_sites);
+#pragma unroll
+        for (int q = 0; q < SPT; ++q) {
+          const int s = sbase + q * kTileThreads;
+          if (s < a.n_sites) Lb[q] = load_child(c, s);
+        }
+        pb = cb;
+      }
+      Trans<JC> Pa, Pb;
+      Pa.load(sP[j]);
+      Pb.load(sP[j] + 16);
+      double* out = ds < 0 ? nullptr : a.pool + (int64_t)ds * a.slot_sites * 4;
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < SPT; ++q) {
+        const int s = sbase + q * kTileThreads;
+        if (s < a.n_sites) {
+          const d4 lp = Pa.apply(La[q]), rp = Pb.apply(Lb[q]);
+          d4 nw;
+          double x = 0.0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            nw.v[i] = lp.v[i] * rp.v[i];
+            x = fma(pi[i], nw.v[i], x);
+          }
+          if (out) st_site(out + (int64_t)s * 4, nw);
+          acc += log(x);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const int kk = s_k[j];
+        const int64_t k = kk < 0 ? ~kk : kk;
+        a.ell_part[(k * a.tiles + t) * kWarps + wid] = acc;
+      }
     }
   }
-  const double t = block_sum<kTileThreads>(acc, red);
-  if (threadIdx.x == 0) a.ell_part[k * a.tiles + tile] = t;
 }
 
-__global__ void ell_reduce_kernel(const double* __restrict__ part, int tiles, int64_t K, double* __restrict__ ell) {
+__global__ void ell_reduce_kernel(const double* __restrict__ part, int n_part, int64_t K, double* __restrict__ ell) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   double s = 0.0;
-  for (int t = 0; t < tiles; ++t) s += part[k * tiles + t];
+  for (int t = 0; t < n_part; ++t) s += part[k * n_part + t];
   ell[k] = s;
 }
 
@@ -153,184 +255,247 @@ struct BwdArgs {
   const int32_t* lsrc;
   const int32_t* rsrc;
   const int32_t* gsrc;
+  const int32_t* order;
+  const int32_t* count;
   const double* P;
   const double* pi;
   const double* coef;
+  int64_t K;
   int n_sites;
   int tiles;
+  int R;
   double* dP;        // [K][32]
   double* dpi_each;  // [K][4] or null
   int skip_zero;
 };
 
-constexpr int kAccGeneral = 36;  // dP_l[16] dP_r[16] dpi[4]
-constexpr int kAccJC = 8;        // dPl_diag dPl_off dPr_diag dPr_off dpi[4]
+template <int SPT>
+__device__ __forceinline__ void flush_adjoint(int src, double* gpool, int64_t slot_sites, int sbase, int n_sites,
+                                              const d4 (&G)[SPT]) {
+  if (src < 0) return;  // leaves (and kNone) have no adjoint buffer
+  double* g = gpool + (int64_t)src * slot_sites * 4;
+#pragma unroll
+  for (int q = 0; q < SPT; ++q) {
+    const int s = sbase + q * kTileThreads;
+    if (s < n_sites) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(g + (int64_t)s * 4 + i, G[q].v[i]);
+    }
+  }
+}
 
-template <bool JC>
-__global__ void __launch_bounds__(kTileThreads) merge_bwd_kernel(const BwdArgs a) {
-  constexpr int NACC = JC ? kAccJC : kAccGeneral;
-  __shared__ double red[kTileThreads / 32][NACC];
-  const int64_t w = blockIdx.x;
-  const int64_t k = w / a.tiles;
-  const int tile = (int)(w - k * a.tiles);
-  const double c = a.coef[k];
-  const int gs = a.gsrc ? a.gsrc[k] : -1;
-  if (a.skip_zero && c == 0.0 && gs < 0) return;  // exact zero adjoint: nothing to propagate
-  const int ls = a.lsrc[k], rs = a.rsrc[k];
-
-  Trans<JC> Pl, Pr;
-  Pl.load(a.P + k * 32);
-  Pr.load(a.P + k * 32 + 16);
+template <bool JC, int SPT>
+__global__ void __launch_bounds__(kTileThreads, JC ? 2 : 1) merge_bwd_kernel(const BwdArgs a) {
+  __shared__ __align__(16) double sP[kRMax][32];
+  __shared__ double s_c[kRMax];
+  __shared__ int s_k[kRMax], s_a[kRMax], s_b[kRMax], s_g[kRMax];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t count = a.count ? (int64_t)*a.count : a.K;
+  const int R = a.R;
+  const int64_t total = ((count + R - 1) / R) * a.tiles;
   double pi[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
-  const uint8_t* lcodes = ls < 0 ? a.codes + (int64_t)(-ls - 1) * a.codes_stride : nullptr;
-  const uint8_t* rcodes = rs < 0 ? a.codes + (int64_t)(-rs - 1) * a.codes_stride : nullptr;
-  const double* lnode = ls < 0 ? nullptr : a.pool + (int64_t)ls * a.slot_sites * 4;
-  const double* rnode = rs < 0 ? nullptr : a.pool + (int64_t)rs * a.slot_sites * 4;
-  double* lg = ls < 0 ? nullptr : a.gpool + (int64_t)ls * a.slot_sites * 4;
-  double* rg = rs < 0 ? nullptr : a.gpool + (int64_t)rs * a.slot_sites * 4;
-  const double* gnew = gs < 0 ? nullptr : a.gpool + (int64_t)gs * a.slot_sites * 4;
 
-  double acc[NACC];
+  for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    const int64_t g = w / a.tiles;
+    const int t = (int)(w - g * a.tiles);
+    const int64_t j0 = g * R;
+    const int nj = (int)min((int64_t)R, count - j0);
+    stage_group(a.order, a.lsrc, a.rsrc, a.P, j0, nj, s_k, s_a, s_b, sP, [&](int i, int k) {
+      s_c[i] = a.coef[k];
+      s_g[i] = a.gsrc ? a.gsrc[k] : -1;
+    });
+    const int sbase = t * (kTileThreads * SPT) + tid;
+    int pa = kNone, pb = kNone;
+    d4 La[SPT], Lb[SPT], Ga[SPT], Gb[SPT];
+    for (int j = 0; j < nj; ++j) {
+      const double c = s_c[j];
+      const int gs = s_g[j];
+      if (a.skip_zero && c == 0.0 && gs < 0) continue;  // exact zero adjoint: nothing to propagate
+      const int ca = s_a[j], cb = s_b[j];
+      if (ca != pa) {
+        flush_adjoint<SPT>(pa, a.gpool, a.slot_sites, sbase, a.n_sites, Ga);
+        const ChildRef cr = child_ref(ca, a.codes, a.codes_stride, a.pool, a.slot_sites);
 #pragma unroll
-  for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
-
-  const int s0 = tile * kTileSites + threadIdx.x;
-#pragma unroll 2
-  for (int it = 0; it < kSitesPerThread; ++it) {
-    const int s = s0 + it * kTileThreads;
-    if (s >= a.n_sites) break;
-    const d4 Ll = load_child(lcodes, lnode, s), Lr = load_child(rcodes, rnode, s);
-    d4 g;
-    if (gnew) {
-      g = ld_site(gnew + (int64_t)s * 4);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) g.v[j] = 0.0;
-    }
-    const d4 lp = Pl.apply(Ll), rp = Pr.apply(Lr);
-    double nw[4], x = 0.0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      nw[j] = lp.v[j] * rp.v[j];
-      x = fma(pi[j], nw[j], x);
-    }
-    const double inv = c / x;
-    d4 gl, gr;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const double gj = fma(inv, pi[j], g.v[j]);
-      acc[NACC - 4 + j] = fma(inv, nw[j], acc[NACC - 4 + j]);  // d ell / d pi_j = new_j / x
-      gl.v[j] = gj * rp.v[j];
-      gr.v[j] = gj * lp.v[j];
-    }
-    if (lg) {
-      const d4 t = Pl.apply_t(gl);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(lg + (int64_t)s * 4 + i, t.v[i]);
-    }
-    if (rg) {
-      const d4 t = Pr.apply_t(gr);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) atomicAdd(rg + (int64_t)s * 4 + i, t.v[i]);
-    }
-    if (JC) {
-      // dP enters only through (sum_i dP_ii, sum_{i!=j} dP_ij): dP_ij = L_i gl_j
-      double dl = 0.0, dr = 0.0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        dl = fma(Ll.v[i], gl.v[i], dl);
-        dr = fma(Lr.v[i], gr.v[i], dr);
-      }
-      const double sl = ((Ll.v[0] + Ll.v[1]) + (Ll.v[2] + Ll.v[3])) * ((gl.v[0] + gl.v[1]) + (gl.v[2] + gl.v[3]));
-      const double sr = ((Lr.v[0] + Lr.v[1]) + (Lr.v[2] + Lr.v[3])) * ((gr.v[0] + gr.v[1]) + (gr.v[2] + gr.v[3]));
-      acc[0] += dl;
-      acc[1] += sl - dl;
-      acc[2] += dr;
-      acc[3] += sr - dr;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          acc[i * 4 + j] = fma(Ll.v[i], gl.v[j], acc[i * 4 + j]);
-          acc[16 + i * 4 + j] = fma(Lr.v[i], gr.v[j], acc[16 + i * 4 + j]);
+        for (int q = 0; q < SPT; ++q) {
+          const int s = sbase + q * kTileThreads;
+          if (s < a.n_sites) La[q] = load_child(cr, s);
+          Ga[q] = zero4();
         }
-    }
-  }
-  // CTA reduction of the accumulators, then one atomic per value (tiles of one particle race only here)
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int i = 0; i < NACC; ++i) {
-    const double t = warp_sum(acc[i]);
-    if (lane == 0) red[wid][i] = t;
-  }
-  __syncthreads();
-  if (threadIdx.x < NACC) {
-    double t = 0.0;
-#pragma unroll
-    for (int q = 0; q < kTileThreads / 32; ++q) t += red[q][threadIdx.x];
-    const int i = threadIdx.x;
-    if (JC) {
-      if (i < 4) {
-        // JC layout inside dP[k][32]: [0]=sum diag(dP_l), [1]=sum offdiag(dP_l), [16],[17] same for right
-        atomicAdd(a.dP + k * 32 + (i >> 1) * 16 + (i & 1), t);
-      } else if (a.dpi_each) {
-        atomicAdd(a.dpi_each + k * 4 + (i - 4), t);
+        pa = ca;
       }
-    } else {
-      if (i < 32) {
-        atomicAdd(a.dP + k * 32 + i, t);
-      } else if (a.dpi_each) {
-        atomicAdd(a.dpi_each + k * 4 + (i - 32), t);
+      if (cb != pb) {
+        flush_adjoint<SPT>(pb, a.gpool, a.slot_sites, sbase, a.n_sites, Gb);
+        const ChildRef cr = child_ref(cb, a.codes, a.codes_stride, a.pool, a.slot_sites);
+#pragma unroll
+        for (int q = 0; q < SPT; ++q) {
+          const int s = sbase + q * kTileThreads;
+          if (s < a.n_sites) Lb[q] = load_child(cr, s);
+          Gb[q] = zero4();
+        }
+        pb = cb;
+      }
+      Trans<JC> Pa, Pb;
+      Pa.load(sP[j]);
+      Pb.load(sP[j] + 16);
+      const double* gnew = gs < 0 ? nullptr : a.gpool + (int64_t)gs * a.slot_sites * 4;
+      const int kk = s_k[j];
+      const bool sw = kk < 0;
+      const int64_t k = sw ? ~kk : kk;
+
+      double dpi[4] = {0.0, 0.0, 0.0, 0.0};
+      double acc[JC ? 4 : 32];
+#pragma unroll
+      for (int i = 0; i < (JC ? 4 : 32); ++i) acc[i] = 0.0;
+#pragma unroll
+      for (int q = 0; q < SPT; ++q) {
+        const int s = sbase + q * kTileThreads;
+        if (s < a.n_sites) {
+          const d4 gin = gnew ? ld_site(gnew + (int64_t)s * 4) : zero4();
+          const d4 lp = Pa.apply(La[q]), rp = Pb.apply(Lb[q]);
+          double nw[4], x = 0.0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            nw[i] = lp.v[i] * rp.v[i];
+            x = fma(pi[i], nw[i], x);
+          }
+          const double inv = c / x;
+          d4 gl, gr;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const double gi = fma(inv, pi[i], gin.v[i]);
+            dpi[i] = fma(inv, nw[i], dpi[i]);  // d ell / d pi_i = new_i / x
+            gl.v[i] = gi * rp.v[i];
+            gr.v[i] = gi * lp.v[i];
+          }
+          if (ca >= 0) {
+            const d4 tt = Pa.apply_t(gl);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Ga[q].v[i] += tt.v[i];
+          }
+          if (cb >= 0) {
+            const d4 tt = Pb.apply_t(gr);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Gb[q].v[i] += tt.v[i];
+          }
+          if (JC) {
+            // dP enters only through (sum_i dP_ii, sum_{i!=j} dP_ij) with dP_ij = L_i g_j
+            double dl = 0.0, dr = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              dl = fma(La[q].v[i], gl.v[i], dl);
+              dr = fma(Lb[q].v[i], gr.v[i], dr);
+            }
+            const double sl = ((La[q].v[0] + La[q].v[1]) + (La[q].v[2] + La[q].v[3])) * ((gl.v[0] + gl.v[1]) + (gl.v[2] + gl.v[3]));
+            const double sr = ((Lb[q].v[0] + Lb[q].v[1]) + (Lb[q].v[2] + Lb[q].v[3])) * ((gr.v[0] + gr.v[1]) + (gr.v[2] + gr.v[3]));
+            acc[0] += dl;
+            acc[1] += sl - dl;
+            acc[2] += dr;
+            acc[3] += sr - dr;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                acc[i * 4 + jj] = fma(La[q].v[i], gl.v[jj], acc[i * 4 + jj]);
+                acc[16 + i * 4 + jj] = fma(Lb[q].v[i], gr.v[jj], acc[16 + i * 4 + jj]);
+              }
+          }
+        }
+      }
+      // per-particle reduction over the warp, one atomic per value per warp (a/b are in canonical order: undo swap)
+      if (JC) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = warp_sum(acc[i]);  // totals land in lane 0
+        if (lane == 0) {
+          // JC layout inside dP[k][32]: [0]=sum diag(dP_l), [1]=sum offdiag(dP_l), [16],[17] same for right
+          const int sa = sw ? 16 : 0, sb = sw ? 0 : 16;
+          atomicAdd(a.dP + k * 32 + sa, acc[0]);
+          atomicAdd(a.dP + k * 32 + sa + 1, acc[1]);
+          atomicAdd(a.dP + k * 32 + sb, acc[2]);
+          atomicAdd(a.dP + k * 32 + sb + 1, acc[3]);
+        }
+      } else {
+        double(&v32)[32] = *reinterpret_cast<double(*)[32]>(acc);
+        warp_transpose_sum32(v32, lane);
+        atomicAdd(a.dP + k * 32 + (lane ^ (sw ? 16 : 0)), v32[0]);
+      }
+      if (a.dpi_each) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dpi[i] = warp_sum(dpi[i]);
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) atomicAdd(a.dpi_each + k * 4 + i, dpi[i]);
+        }
       }
     }
+    flush_adjoint<SPT>(pa, a.gpool, a.slot_sites, sbase, a.n_sites, Ga);
+    flush_adjoint<SPT>(pb, a.gpool, a.slot_sites, sbase, a.n_sites, Gb);
   }
+}
+
+constexpr int kSptFwd = 2;
+constexpr int kSptBwdJC = 2;
+constexpr int kSptBwdGeneral = 1;
+
+int pick_group(int64_t K, int tiles) {
+  // enough work items to fill 148 SMs several times over; larger groups amortise shared children
+  int64_t R = (K * tiles) / (148 * 32);
+  if (R < 1) R = 1;
+  if (R > kRMax) R = kRMax;
+  return (int)R;
+}
+
+unsigned pick_grid(int64_t K, int R, int tiles) {
+  const int64_t total = ((K + R - 1) / R) * tiles;
+  const int64_t cap = 148 * 16;
+  return (unsigned)(total < cap ? (total > 0 ? total : 1) : cap);
 }
 
 }  // namespace
 
-int merge_tiles(int n_sites) { return (n_sites + kTileSites - 1) / kTileSites; }
+int merge_fwd_tiles(int n_sites) { return (n_sites + kTileThreads * kSptFwd - 1) / (kTileThreads * kSptFwd); }
+int merge_ell_parts(int n_sites) { return merge_fwd_tiles(n_sites) * kWarps; }
 
 int launch_merge_fwd(const uint8_t* codes, int64_t codes_stride, double* pool, int64_t slot_sites, const int32_t* lsrc,
-                     const int32_t* rsrc, const int32_t* dst, const double* P, const double* pi, int64_t K,
-                     int n_sites, int jc, int skip_unstored, double* ell_part, cudaStream_t st) {
+                     const int32_t* rsrc, const int32_t* dst, const int32_t* order, const int32_t* count,
+                     const double* P, const double* pi, int64_t K, int n_sites, int jc, int skip_unstored,
+                     double* ell_part, cudaStream_t st) {
   if (K <= 0 || n_sites <= 0) return VCSMC_OK;
   FwdArgs a;
   a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.slot_sites = slot_sites;
-  a.lsrc = lsrc; a.rsrc = rsrc; a.dst = dst; a.P = P;
-  a.pi = pi;
-  a.n_sites = n_sites; a.tiles = merge_tiles(n_sites); a.skip_unstored = skip_unstored; a.ell_part = ell_part;
-  const int64_t grid = K * a.tiles;
-  if (grid > 2147483647LL) { set_error("merge_fwd: grid too large"); return VCSMC_ERR_ARG; }
-  if (jc) merge_fwd_kernel<true><<<(unsigned)grid, kTileThreads, 0, st>>>(a);
-  else merge_fwd_kernel<false><<<(unsigned)grid, kTileThreads, 0, st>>>(a);
+  a.lsrc = lsrc; a.rsrc = rsrc; a.dst = dst; a.order = order; a.count = count; a.P = P; a.pi = pi; a.K = K;
+  a.n_sites = n_sites; a.tiles = merge_fwd_tiles(n_sites); a.R = pick_group(K, a.tiles);
+  a.skip_unstored = skip_unstored; a.ell_part = ell_part;
+  const unsigned grid = pick_grid(K, a.R, a.tiles);
+  if (jc) merge_fwd_kernel<true, kSptFwd><<<grid, kTileThreads, 0, st>>>(a);
+  else merge_fwd_kernel<false, kSptFwd><<<grid, kTileThreads, 0, st>>>(a);
   VCSMC_LAUNCH_CHECK("merge_fwd_kernel");
   return VCSMC_OK;
 }
 
-int launch_ell_reduce(const double* ell_part, int tiles, int64_t K, double* ell, cudaStream_t st) {
-  ell_reduce_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(ell_part, tiles, K, ell);
+int launch_ell_reduce(const double* ell_part, int n_part, int64_t K, double* ell, cudaStream_t st) {
+  ell_reduce_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(ell_part, n_part, K, ell);
   VCSMC_LAUNCH_CHECK("ell_reduce_kernel");
   return VCSMC_OK;
 }
 
 int launch_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* pool, double* gpool, int64_t slot_sites,
-                     const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc, const double* P,
-                     const double* pi, const double* coef, int64_t K, int n_sites, int jc, int skip_zero,
-                     double* dP, double* dpi_each, cudaStream_t st) {
+                     const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc, const int32_t* order,
+                     const int32_t* count, const double* P, const double* pi, const double* coef, int64_t K,
+                     int n_sites, int jc, int skip_zero, double* dP, double* dpi_each, cudaStream_t st) {
   if (K <= 0 || n_sites <= 0) return VCSMC_OK;
   BwdArgs a;
   a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.gpool = gpool; a.slot_sites = slot_sites;
-  a.lsrc = lsrc; a.rsrc = rsrc; a.gsrc = gsrc; a.P = P;
-  a.pi = pi;
-  a.coef = coef; a.n_sites = n_sites; a.tiles = merge_tiles(n_sites); a.dP = dP; a.dpi_each = dpi_each;
-  a.skip_zero = skip_zero;
-  const int64_t grid = K * a.tiles;
-  if (grid > 2147483647LL) { set_error("merge_bwd: grid too large"); return VCSMC_ERR_ARG; }
-  if (jc) merge_bwd_kernel<true><<<(unsigned)grid, kTileThreads, 0, st>>>(a);
-  else merge_bwd_kernel<false><<<(unsigned)grid, kTileThreads, 0, st>>>(a);
+  a.lsrc = lsrc; a.rsrc = rsrc; a.gsrc = gsrc; a.order = order; a.count = count; a.P = P; a.pi = pi;
+  a.coef = coef; a.K = K; a.n_sites = n_sites; a.dP = dP; a.dpi_each = dpi_each; a.skip_zero = skip_zero;
+  const int spt = jc ? kSptBwdJC : kSptBwdGeneral;
+  a.tiles = (n_sites + kTileThreads * spt - 1) / (kTileThreads * spt);
+  a.R = pick_group(K, a.tiles);
+  const unsigned grid = pick_grid(K, a.R, a.tiles);
+  if (jc) merge_bwd_kernel<true, kSptBwdJC><<<grid, kTileThreads, 0, st>>>(a);
+  else merge_bwd_kernel<false, kSptBwdGeneral><<<grid, kTileThreads, 0, st>>>(a);
   VCSMC_LAUNCH_CHECK("merge_bwd_kernel");
   return VCSMC_OK;
 }

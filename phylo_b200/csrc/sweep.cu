@@ -386,16 +386,26 @@ __global__ void __launch_bounds__(256) bwd_coef_kernel(const CoefArgs a) {
   }
 }
 
-__global__ void zero_consumed_kernel(const int32_t* __restrict__ consumed, int64_t slot_sites, int n_sites,
-                                     double* __restrict__ gpool) {
-  const int64_t e = blockIdx.y;
-  if (!consumed[e]) return;
+// which particles of rank event r the reverse sweep / the chunk recompute must visit
+__global__ void bwd_active_kernel(const double* __restrict__ cnew, const int32_t* __restrict__ consumed, int64_t K,
+                                  int skip_zero, int32_t* __restrict__ act_bwd, int32_t* __restrict__ act_rec) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const int c = consumed[k];
+  act_rec[k] = c;
+  act_bwd[k] = !(skip_zero && cnew[k] == 0.0 && !c);
+}
+
+// zero the adjoint slots of the consumed nodes of one rank event (the first *count entries of `order`)
+__global__ void zero_consumed_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ count, int64_t e0,
+                                     int64_t slot_sites, int n_sites, double* __restrict__ gpool) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sites) return;
+  const int n = *count;
   d4 z;
 #pragma unroll
   for (int j = 0; j < 4; ++j) z.v[j] = 0.0;
-  st_site(gpool + (e * slot_sites + s) * 4, z);
+  for (int j = blockIdx.y; j < n; j += gridDim.y) st_site(gpool + ((e0 + order[j]) * slot_sites + s) * 4, z);
 }
 
 // db -> dlam through b = -log(U)/lam, and accumulation of the per-matrix dQ (vcsmc.py:353-358 reversed)
@@ -491,7 +501,9 @@ struct vcsmc_sweep {
       o_vminus, o_ell_node, o_stats, o_logz, o_ess, o_elbo, o_status, o_P, o_ids[2], o_cnt[2], o_slot[2], o_cdf,
       o_u_pair, o_u_bl, o_u_br, o_u_res, o_ell_part, o_ell_new, o_lsrc, o_rsrc, o_dst, o_ldf, o_flags, o_childsum[2],
       o_Dacc[2], o_cnew, o_consumed, o_bsrc_l, o_bsrc_r, o_bsrc_g, o_bdst, o_dP, o_dpi_each, o_dQ_acc, o_dQ_each, o_dt,
-      o_suf_l, o_suf_r, o_gB_l, o_gB_r, o_cleaf, o_pool;
+      o_suf_l, o_suf_r, o_gB_l, o_gB_r, o_cleaf, o_pool, o_keys_in, o_keys_out, o_vals_in, o_order, o_count,
+      o_sort_temp, o_order_bwd, o_count_bwd, o_order_rec, o_count_rec, o_act_bwd, o_act_rec;
+  size_t sort_temp = 0;
   int64_t pool_bytes;
   std::vector<int64_t> rem_off;  // per step offset (bytes) into rempos
   // uniform source
@@ -592,13 +604,20 @@ int64_t plan(vcsmc_sweep* h) {
   h->o_u_bl = L.take<double>(K);
   h->o_u_br = L.take<double>(K);
   h->o_u_res = L.take<double>(K);
-  h->tiles_max = merge_tiles(h->S);
+  h->tiles_max = merge_ell_parts(h->S);
   h->o_ell_part = L.take<double>(K * h->tiles_max);
   h->o_ell_new = L.take<double>(K);
   h->o_lsrc = L.take<int32_t>(K);
   h->o_rsrc = L.take<int32_t>(K);
   h->o_dst = L.take<int32_t>(K);
   h->o_ldf = L.take<double>(2 * (int64_t)N + 4);
+  h->o_keys_in = L.take<uint64_t>(K);
+  h->o_keys_out = L.take<uint64_t>(K);
+  h->o_vals_in = L.take<int32_t>(K);
+  h->o_order = L.take<int32_t>(K);
+  h->o_count = L.take<int32_t>(4);
+  h->sort_temp = sort_temp_bytes(K);
+  h->o_sort_temp = L.take<char>((int64_t)h->sort_temp + 256);
   if (h->keep) {
     for (int i = 0; i < 2; ++i) {
       h->o_childsum[i] = L.take<double>(K);
@@ -620,6 +639,12 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_gB_l = L.take<double>(E);
     h->o_gB_r = L.take<double>(E);
     h->o_cleaf = L.take<double>(N);
+    h->o_order_bwd = L.take<int32_t>(E);
+    h->o_order_rec = L.take<int32_t>(E);
+    h->o_count_bwd = L.take<int32_t>(N);
+    h->o_count_rec = L.take<int32_t>(N);
+    h->o_act_bwd = L.take<int32_t>(K);
+    h->o_act_rec = L.take<int32_t>(K);
   }
   return L.off;
 }
@@ -834,9 +859,15 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
       gc_alloc_kernel<<<1, 1024, 0, st>>>(flags, h->pool_slots, K, N, n, a.dst, a.slot_new, h->p<int32_t>(h->o_status));
       VCSMC_LAUNCH_CHECK("gc_alloc_kernel");
     }
-    const int tiles = merge_tiles(S);
+    // visiting order: particles sorted by their pair of child nodes (shared children are read once per group)
+    rc = launch_sort_order(a.lsrc, a.rsrc, nullptr, K, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out),
+                           h->p<int32_t>(h->o_vals_in), h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count),
+                           h->p<char>(h->o_sort_temp), h->sort_temp, st);
+    if (rc) return rc;
+    const int tiles = merge_ell_parts(S);
     h->prof_begin(0, st);
-    rc = launch_merge_fwd(codes, S, pool, S, a.lsrc, a.rsrc, a.dst, P, pi, K, S, h->jc, 0, h->p<double>(h->o_ell_part), st);
+    rc = launch_merge_fwd(codes, S, pool, S, a.lsrc, a.rsrc, a.dst, h->p<int32_t>(h->o_order), nullptr, P, pi, K, S, h->jc, 0,
+                          h->p<double>(h->o_ell_part), st);
     h->prof_end(st);
     if (rc) return rc;
 
@@ -944,6 +975,21 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   leaf_pi_grad_kernel<<<N, 256, 0, st>>>(h->codes, S, S, h->pi, h->p<double>(h->o_cleaf), dpi);
   VCSMC_LAUNCH_CHECK("leaf_pi_grad_kernel");
 
+  // ---- visiting orders of every rank event (sorted by child pair; inactive particles last)
+  for (int r = 0; r < N - 1; ++r) {
+    bwd_active_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(h->p<double>(h->o_cnew) + (int64_t)r * K, h->p<int32_t>(h->o_consumed) + (int64_t)r * K,
+                                                                 K, h->skip_zero, h->p<int32_t>(h->o_act_bwd), h->p<int32_t>(h->o_act_rec));
+    VCSMC_LAUNCH_CHECK("bwd_active_kernel");
+    const int32_t* bl = h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K;
+    const int32_t* br = h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K;
+    rc = launch_sort_order(bl, br, h->p<int32_t>(h->o_act_bwd), K, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out), h->p<int32_t>(h->o_vals_in),
+                           h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r, h->p<char>(h->o_sort_temp), h->sort_temp, st);
+    if (rc) return rc;
+    rc = launch_sort_order(bl, br, h->p<int32_t>(h->o_act_rec), K, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out), h->p<int32_t>(h->o_vals_in),
+                           h->p<int32_t>(h->o_order_rec) + (int64_t)r * K, h->p<int32_t>(h->o_count_rec) + r, h->p<char>(h->o_sort_temp), h->sort_temp, st);
+    if (rc) return rc;
+  }
+
   // ---- per-site pass: reverse pruning, by site chunks
   const int Sc = h->chunk_sites;
   double* lpool;
@@ -964,25 +1010,24 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
       for (int r = 0; r < N - 1; ++r) {
         h->prof_begin(1, st);
         rc = launch_merge_fwd(codes_c, S, lpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
-                              h->p<int32_t>(h->o_bdst) + (int64_t)r * K, h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, K, nc,
-                              h->jc, 1, h->p<double>(h->o_ell_part), st);
+                              h->p<int32_t>(h->o_bdst) + (int64_t)r * K, h->p<int32_t>(h->o_order_rec) + (int64_t)r * K, h->p<int32_t>(h->o_count_rec) + r,
+                              h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, K, nc, h->jc, 1, h->p<double>(h->o_ell_part), st);
         h->prof_end(st);
         if (rc) return rc;
       }
     }
     // zero the adjoint slots of consumed nodes
-    for (int64_t e0 = 0; e0 < E; e0 += 65535) {
-      const int64_t ne = (E - e0 < 65535) ? E - e0 : 65535;
-      dim3 grid((nc + 255) / 256, (unsigned)ne, 1);
-      zero_consumed_kernel<<<grid, 256, 0, st>>>(h->p<int32_t>(h->o_consumed) + e0, Sc, nc, gpool + e0 * (int64_t)Sc * 4);
+    for (int r = 0; r < N - 1; ++r) {
+      dim3 grid((nc + 255) / 256, 32, 1);
+      zero_consumed_kernel<<<grid, 256, 0, st>>>(h->p<int32_t>(h->o_order_rec) + (int64_t)r * K, h->p<int32_t>(h->o_count_rec) + r, (int64_t)r * K, Sc, nc, gpool);
       VCSMC_LAUNCH_CHECK("zero_consumed_kernel");
     }
     for (int r = N - 2; r >= 0; --r) {
       h->prof_begin(2, st);
       rc = launch_merge_bwd(codes_c, S, lpool, gpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
-                            h->p<int32_t>(h->o_bsrc_g) + (int64_t)r * K, h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi,
-                            h->p<double>(h->o_cnew) + (int64_t)r * K, K, nc, h->jc, h->skip_zero, h->p<double>(h->o_dP) + (int64_t)r * K * 32,
-                            h->p<double>(h->o_dpi_each), st);
+                            h->p<int32_t>(h->o_bsrc_g) + (int64_t)r * K, h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r,
+                            h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, h->p<double>(h->o_cnew) + (int64_t)r * K, K, nc, h->jc, h->skip_zero,
+                            h->p<double>(h->o_dP) + (int64_t)r * K * 32, h->p<double>(h->o_dpi_each), st);
       h->prof_end(st);
       if (rc) return rc;
     }
