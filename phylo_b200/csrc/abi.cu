@@ -61,9 +61,10 @@ int vcsmc_merge_fwd(const uint8_t* codes, int64_t codes_stride, double* pool, in
                     const int32_t* rsrc, const int32_t* dst, const double* P, const double* pi, int64_t K, int n_sites,
                     int jc, double* ell_part, double* ell, void* stream) {
   if (!lsrc || !rsrc || !P || !pi || !ell_part || K < 0 || n_sites < 0 || slot_sites < n_sites) { set_error("merge_fwd: bad argument"); return VCSMC_ERR_ARG; }
-  int rc = launch_merge_fwd(codes, codes_stride, pool, slot_sites, lsrc, rsrc, dst, nullptr, nullptr, P, pi, K, n_sites, jc, 0, ell_part, (cudaStream_t)stream);
+  int n_parts = 0;
+  int rc = launch_merge_fwd(codes, codes_stride, pool, slot_sites, lsrc, rsrc, dst, nullptr, nullptr, P, pi, K, n_sites, jc, 0, ell_part, &n_parts, (cudaStream_t)stream);
   if (rc || !ell || K == 0 || n_sites == 0) return rc;
-  return launch_ell_reduce(ell_part, merge_ell_parts(n_sites), K, ell, (cudaStream_t)stream);
+  return launch_ell_reduce(ell_part, n_parts, K, ell, (cudaStream_t)stream);
 }
 
 int vcsmc_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* pool, double* gpool, int64_t slot_sites,

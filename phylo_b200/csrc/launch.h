@@ -7,11 +7,11 @@ namespace vcsmc {
 
 // merge.cu
 int merge_fwd_tiles(int n_sites);
-int merge_ell_parts(int n_sites);  // partial sums per particle written by launch_merge_fwd
+int merge_ell_parts(int n_sites);  // upper bound of the partial sums per particle written by launch_merge_fwd
 int launch_merge_fwd(const uint8_t* codes, int64_t codes_stride, double* pool, int64_t slot_sites, const int32_t* lsrc,
                      const int32_t* rsrc, const int32_t* dst, const int32_t* order, const int32_t* count,
                      const double* P, const double* pi, int64_t K, int n_sites, int jc, int skip_unstored,
-                     double* ell_part, cudaStream_t st);
+                     double* ell_part, int* n_parts, cudaStream_t st);
 int launch_ell_reduce(const double* ell_part, int n_part, int64_t K, double* ell, cudaStream_t st);
 int launch_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* pool, double* gpool, int64_t slot_sites,
                      const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc, const int32_t* order,

@@ -131,9 +131,11 @@ struct FwdArgs {
   int64_t K;
   int n_sites;
   int tiles;
+  int tiles_per_item;  // a work item = one group x tiles_per_item consecutive tiles (staging amortised)
+  int n_chunks;
   int R;
   int skip_unstored;  // re-forward of the chunked backward: nodes nobody consumes are not materialised
-  double* ell_part;   // [K][tiles][kWarps]
+  double* ell_part;   // [K][n_chunks][kWarps]
 };
 
 // stage the group's particle descriptors and P matrices in shared memory (canonical child order a <= b)
@@ -163,76 +165,114 @@ __device__ __forceinline__ void stage_group(const int32_t* order, const int32_t*
   __syncthreads();
 }
 
+// log(x) of a positive double split as (mantissa in [1,2), unbiased exponent): sum_s log x_s is then the log of a
+// running mantissa product plus ln2 times an integer sum -- ONE log per (thread, particle) instead of one per site.
+// Zero, subnormal, inf and NaN are passed through unsplit so that log() of the product still yields what
+// the reference's log(0) = -inf / NaN would.
+__device__ __forceinline__ void split_positive(double x, double& mant, int& ex) {
+  const int hi = __double2hiint(x);
+  const int e = (hi >> 20) & 0x7ff;
+  const bool normal = (e != 0) && (e != 0x7ff) && (hi >= 0);
+  mant = normal ? __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x)) : x;
+  ex = normal ? e - 1023 : 0;
+}
+
+constexpr int kFwdSmemBytes = kRMax * 32 * 8 + kRMax * kTileThreads * (8 + 4);
+
 template <bool JC, int SPT>
 __global__ void __launch_bounds__(kTileThreads, 2) merge_fwd_kernel(const FwdArgs a) {
-  __shared__ __align__(16) double sP[kRMax][32];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double(*sP)[32] = reinterpret_cast<double(*)[32]>(smem_raw);
+  double* s_prod = reinterpret_cast<double*>(smem_raw + kRMax * 32 * 8);   // [R][256] running mantissa products
+  int* s_exp = reinterpret_cast<int*>(s_prod + kRMax * kTileThreads);      // [R][256] running exponent sums
   __shared__ int s_k[kRMax], s_a[kRMax], s_b[kRMax], s_dst[kRMax];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int64_t count = a.count ? (int64_t)*a.count : a.K;
   const int R = a.R;
-  const int64_t total = ((count + R - 1) / R) * a.tiles;
+  const int64_t total = ((count + R - 1) / R) * a.n_chunks;
   double pi[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
 
   for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
-    const int64_t g = w / a.tiles;
-    const int t = (int)(w - g * a.tiles);
+    const int64_t g = w / a.n_chunks;
+    const int tc = (int)(w - g * a.n_chunks);
     const int64_t j0 = g * R;
     const int nj = (int)min((int64_t)R, count - j0);
     stage_group(a.order, a.lsrc, a.rsrc, a.P, j0, nj, s_k, s_a, s_b, sP,
                 [&](int i, int k) { s_dst[i] = a.dst ? a.dst[k] : k; });
-    const int sbase = t * (kTileThreads * SPT) + tid;
-    int pa = kNone, pb = kNone;
-    d4 La[SPT], Lb[SPT];
     for (int j = 0; j < nj; ++j) {
-      const int ds = s_dst[j];
-      if (a.skip_unstored && ds < 0) continue;
-      const int ca = s_a[j], cb = s_b[j];
-      if (ca != pa) {
-        const ChildRef c = child_ref(ca, a.codes, a.codes_stride, a.pool, a.slot_sites);
+      s_prod[j * kTileThreads + tid] = 1.0;
+      s_exp[j * kTileThreads + tid] = 0;
+    }
+    const int t_end = min(a.tiles, (tc + 1) * a.tiles_per_item);
+    for (int t = tc * a.tiles_per_item; t < t_end; ++t) {
+      const int sbase = t * (kTileThreads * SPT) + tid;
+      int pa = kNone, pb = kNone;
+      d4 La[SPT], Lb[SPT];
+      for (int j = 0; j < nj; ++j) {
+        const int ds = s_dst[j];
+        if (a.skip_unstored && ds < 0) continue;
+        const int ca = s_a[j], cb = s_b[j];
+        if (ca != pa) {
+          const ChildRef c = child_ref(ca, a.codes, a.codes_stride, a.pool, a.slot_sites);
 #pragma unroll
-        for (int q = 0; q < SPT; ++q) {
-          const int s = sbase + q * kTileThreads;
-          if (s < a.n_sites) La[q] = load_child(c, s);
-        }
-        pa = ca;
-      }
-      if (cb != pb) {
-        const ChildRef c = child_ref(cb, a.codes, a.codes_stride, a.pool, a.slot_sites);
-#pragma unroll
-        for (int q = 0; q < SPT; ++q) {
-          const int s = sbase + q * kTileThreads;
-          if (s < a.n_sites) Lb[q] = load_child(c, s);
-        }
-        pb = cb;
-      }
-      Trans<JC> Pa, Pb;
-      Pa.load(sP[j]);
-      Pb.load(sP[j] + 16);
-      double* out = ds < 0 ? nullptr : a.pool + (int64_t)ds * a.slot_sites * 4;
-      double acc = 0.0;
-#pragma unroll
-      for (int q = 0; q < SPT; ++q) {
-        const int s = sbase + q * kTileThreads;
-        if (s < a.n_sites) {
-          const d4 lp = Pa.apply(La[q]), rp = Pb.apply(Lb[q]);
-          d4 nw;
-          double x = 0.0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            nw.v[i] = lp.v[i] * rp.v[i];
-            x = fma(pi[i], nw.v[i], x);
+          for (int q = 0; q < SPT; ++q) {
+            const int s = sbase + q * kTileThreads;
+            if (s < a.n_sites) La[q] = load_child(c, s);
           }
-          if (out) st_site(out + (int64_t)s * 4, nw);
-          acc += log(x);
+          pa = ca;
         }
+        if (cb != pb) {
+          const ChildRef c = child_ref(cb, a.codes, a.codes_stride, a.pool, a.slot_sites);
+#pragma unroll
+          for (int q = 0; q < SPT; ++q) {
+            const int s = sbase + q * kTileThreads;
+            if (s < a.n_sites) Lb[q] = load_child(c, s);
+          }
+          pb = cb;
+        }
+        Trans<JC> Pa, Pb;
+        Pa.load(sP[j]);
+        Pb.load(sP[j] + 16);
+        double* out = ds < 0 ? nullptr : a.pool + (int64_t)ds * a.slot_sites * 4;
+        double pr = s_prod[j * kTileThreads + tid];
+        int ex = s_exp[j * kTileThreads + tid];
+#pragma unroll
+        for (int q = 0; q < SPT; ++q) {
+          const int s = sbase + q * kTileThreads;
+          if (s < a.n_sites) {
+            const d4 lp = Pa.apply(La[q]), rp = Pb.apply(Lb[q]);
+            d4 nw;
+            double x = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              nw.v[i] = lp.v[i] * rp.v[i];
+              x = fma(pi[i], nw.v[i], x);
+            }
+            if (out) st_site(out + (int64_t)s * 4, nw);
+            double m;
+            int e;
+            split_positive(x, m, e);
+            pr *= m;
+            ex += e;
+          }
+        }
+        s_prod[j * kTileThreads + tid] = pr;
+        s_exp[j * kTileThreads + tid] = ex;
       }
+    }
+    // one log per (thread, particle): sum_s log x_s = log(prod mantissas) + ln2 * sum exponents
+    for (int j = 0; j < nj; ++j) {
+      if (a.skip_unstored && s_dst[j] < 0) continue;
+      const double pr = s_prod[j * kTileThreads + tid];
+      const double ex = (double)s_exp[j * kTileThreads + tid];
+      double acc = fma(ex, 6.93147180369123816490e-01, fma(ex, 1.90821492927058770002e-10, log(pr)));  // ln2 hi + lo
       acc = warp_sum(acc);
       if (lane == 0) {
         const int kk = s_k[j];
         const int64_t k = kk < 0 ? ~kk : kk;
-        a.ell_part[(k * a.tiles + t) * kWarps + wid] = acc;
+        a.ell_part[(k * a.n_chunks + tc) * kWarps + wid] = acc;
       }
     }
   }
@@ -263,6 +303,8 @@ struct BwdArgs {
   int64_t K;
   int n_sites;
   int tiles;
+  int tiles_per_item;
+  int n_chunks;
   int R;
   double* dP;        // [K][32]
   double* dpi_each;  // [K][4] or null
@@ -292,20 +334,22 @@ __global__ void __launch_bounds__(kTileThreads, JC ? 2 : 1) merge_bwd_kernel(con
   const int tid = threadIdx.x, lane = tid & 31;
   const int64_t count = a.count ? (int64_t)*a.count : a.K;
   const int R = a.R;
-  const int64_t total = ((count + R - 1) / R) * a.tiles;
+  const int64_t total = ((count + R - 1) / R) * a.n_chunks;
   double pi[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
 
   for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
-    const int64_t g = w / a.tiles;
-    const int t = (int)(w - g * a.tiles);
+    const int64_t g = w / a.n_chunks;
+    const int tc = (int)(w - g * a.n_chunks);
     const int64_t j0 = g * R;
     const int nj = (int)min((int64_t)R, count - j0);
     stage_group(a.order, a.lsrc, a.rsrc, a.P, j0, nj, s_k, s_a, s_b, sP, [&](int i, int k) {
       s_c[i] = a.coef[k];
       s_g[i] = a.gsrc ? a.gsrc[k] : -1;
     });
+    const int t_end = min(a.tiles, (tc + 1) * a.tiles_per_item);
+    for (int t = tc * a.tiles_per_item; t < t_end; ++t) {
     const int sbase = t * (kTileThreads * SPT) + tid;
     int pa = kNone, pb = kNone;
     d4 La[SPT], Lb[SPT], Ga[SPT], Gb[SPT];
@@ -432,12 +476,15 @@ __global__ void __launch_bounds__(kTileThreads, JC ? 2 : 1) merge_bwd_kernel(con
     }
     flush_adjoint<SPT>(pa, a.gpool, a.slot_sites, sbase, a.n_sites, Ga);
     flush_adjoint<SPT>(pb, a.gpool, a.slot_sites, sbase, a.n_sites, Gb);
+    }
   }
 }
 
 constexpr int kSptFwd = 2;
 constexpr int kSptBwdJC = 2;
 constexpr int kSptBwdGeneral = 1;
+
+constexpr int64_t kTargetItems = 148 * 16;  // work items wanted per launch (persistent grid cap)
 
 int pick_group(int64_t K, int tiles) {
   // enough work items to fill 148 SMs several times over; larger groups amortise shared children
@@ -447,10 +494,20 @@ int pick_group(int64_t K, int tiles) {
   return (int)R;
 }
 
-unsigned pick_grid(int64_t K, int R, int tiles) {
-  const int64_t total = ((K + R - 1) / R) * tiles;
-  const int64_t cap = 148 * 16;
-  return (unsigned)(total < cap ? (total > 0 ? total : 1) : cap);
+// split the tiles of a group into n_chunks work items only when the groups alone cannot fill the machine
+void pick_chunks(int64_t K, int R, int tiles, int* tiles_per_item, int* n_chunks) {
+  const int64_t groups = (K + R - 1) / R;
+  int64_t nc = (kTargetItems + groups - 1) / groups;
+  if (nc < 1) nc = 1;
+  if (nc > tiles) nc = tiles;
+  const int tpi = (int)((tiles + nc - 1) / nc);
+  *tiles_per_item = tpi;
+  *n_chunks = (tiles + tpi - 1) / tpi;
+}
+
+unsigned pick_grid(int64_t K, int R, int n_chunks) {
+  const int64_t total = ((K + R - 1) / R) * n_chunks;
+  return (unsigned)(total < kTargetItems ? (total > 0 ? total : 1) : kTargetItems);
 }
 
 }  // namespace
@@ -461,16 +518,25 @@ int merge_ell_parts(int n_sites) { return merge_fwd_tiles(n_sites) * kWarps; }
 int launch_merge_fwd(const uint8_t* codes, int64_t codes_stride, double* pool, int64_t slot_sites, const int32_t* lsrc,
                      const int32_t* rsrc, const int32_t* dst, const int32_t* order, const int32_t* count,
                      const double* P, const double* pi, int64_t K, int n_sites, int jc, int skip_unstored,
-                     double* ell_part, cudaStream_t st) {
+                     double* ell_part, int* n_parts, cudaStream_t st) {
+  if (n_parts) *n_parts = 0;
   if (K <= 0 || n_sites <= 0) return VCSMC_OK;
+  static bool configured = false;
+  if (!configured) {
+    VCSMC_CUDA(cudaFuncSetAttribute(merge_fwd_kernel<true, kSptFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+    VCSMC_CUDA(cudaFuncSetAttribute(merge_fwd_kernel<false, kSptFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+    configured = true;
+  }
   FwdArgs a;
   a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.slot_sites = slot_sites;
   a.lsrc = lsrc; a.rsrc = rsrc; a.dst = dst; a.order = order; a.count = count; a.P = P; a.pi = pi; a.K = K;
   a.n_sites = n_sites; a.tiles = merge_fwd_tiles(n_sites); a.R = pick_group(K, a.tiles);
   a.skip_unstored = skip_unstored; a.ell_part = ell_part;
-  const unsigned grid = pick_grid(K, a.R, a.tiles);
-  if (jc) merge_fwd_kernel<true, kSptFwd><<<grid, kTileThreads, 0, st>>>(a);
-  else merge_fwd_kernel<false, kSptFwd><<<grid, kTileThreads, 0, st>>>(a);
+  pick_chunks(K, a.R, a.tiles, &a.tiles_per_item, &a.n_chunks);
+  if (n_parts) *n_parts = a.n_chunks * kWarps;
+  const unsigned grid = pick_grid(K, a.R, a.n_chunks);
+  if (jc) merge_fwd_kernel<true, kSptFwd><<<grid, kTileThreads, kFwdSmemBytes, st>>>(a);
+  else merge_fwd_kernel<false, kSptFwd><<<grid, kTileThreads, kFwdSmemBytes, st>>>(a);
   VCSMC_LAUNCH_CHECK("merge_fwd_kernel");
   return VCSMC_OK;
 }
@@ -493,7 +559,8 @@ int launch_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* p
   const int spt = jc ? kSptBwdJC : kSptBwdGeneral;
   a.tiles = (n_sites + kTileThreads * spt - 1) / (kTileThreads * spt);
   a.R = pick_group(K, a.tiles);
-  const unsigned grid = pick_grid(K, a.R, a.tiles);
+  pick_chunks(K, a.R, a.tiles, &a.tiles_per_item, &a.n_chunks);
+  const unsigned grid = pick_grid(K, a.R, a.n_chunks);
   if (jc) merge_bwd_kernel<true, kSptBwdJC><<<grid, kTileThreads, 0, st>>>(a);
   else merge_bwd_kernel<false, kSptBwdGeneral><<<grid, kTileThreads, 0, st>>>(a);
   VCSMC_LAUNCH_CHECK("merge_bwd_kernel");

@@ -864,10 +864,10 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
                            h->p<int32_t>(h->o_vals_in), h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count),
                            h->p<char>(h->o_sort_temp), h->sort_temp, st);
     if (rc) return rc;
-    const int tiles = merge_ell_parts(S);
+    int tiles = 0;  // partial sums per particle written by the merge
     h->prof_begin(0, st);
     rc = launch_merge_fwd(codes, S, pool, S, a.lsrc, a.rsrc, a.dst, h->p<int32_t>(h->o_order), nullptr, P, pi, K, S, h->jc, 0,
-                          h->p<double>(h->o_ell_part), st);
+                          h->p<double>(h->o_ell_part), &tiles, st);
     h->prof_end(st);
     if (rc) return rc;
 
@@ -1011,7 +1011,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
         h->prof_begin(1, st);
         rc = launch_merge_fwd(codes_c, S, lpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
                               h->p<int32_t>(h->o_bdst) + (int64_t)r * K, h->p<int32_t>(h->o_order_rec) + (int64_t)r * K, h->p<int32_t>(h->o_count_rec) + r,
-                              h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, K, nc, h->jc, 1, h->p<double>(h->o_ell_part), st);
+                              h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, K, nc, h->jc, 1, h->p<double>(h->o_ell_part), nullptr, st);
         h->prof_end(st);
         if (rc) return rc;
       }
