@@ -175,10 +175,29 @@ def gather_across(a: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return a[torch.arange(K).unsqueeze(1), idx]
 
 
-def compute_forest_posterior(core, leafnode_num_record, pi):
-    """vcsmc.py:231-245: sum_x sum_s log(pi . core[k,x,s,:]) - sum_x log (2 max(n_x,2) - 3)!!."""
+class _AllReduceSum(torch.autograd.Function):
+    """Sum across ranks; the adjoint of a sum of per-rank terms w.r.t. each term is the identity."""
+
+    @staticmethod
+    def forward(ctx, x, fn):
+        y = x.detach().clone()
+        fn(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def compute_forest_posterior(core, leafnode_num_record, pi, allreduce=None):
+    """vcsmc.py:231-245: sum_x sum_s log(pi . core[k,x,s,:]) - sum_x log (2 max(n_x,2) - 3)!!.
+
+    ``allreduce`` (site sharding): the site sum is completed across ranks before the weights.
+    """
     forest_lik = torch.matmul(core, pi.reshape(-1, 1)).squeeze(-1)      # [K,X,S]
     forest_loglik = torch.log(forest_lik).sum(dim=(1, 2))
+    if allreduce is not None:
+        forest_loglik = _AllReduceSum.apply(forest_loglik, allreduce)
     forest_logprior = (-log_double_factorial(2 * torch.clamp(leafnode_num_record, min=2) - 3)).sum(dim=1)
     return forest_loglik + forest_logprior
 
@@ -240,13 +259,20 @@ class SweepResult:
 
 def sweep(genome: np.ndarray, K: int, lam_l: torch.Tensor, lam_r: torch.Tensor, Q: torch.Tensor,
           pi: torch.Tensor, U: Uniforms, keep_nodes: bool = False,
-          site_idx: Optional[np.ndarray] = None) -> SweepResult:
+          site_idx: Optional[np.ndarray] = None, allreduce=None, scalar_share: float = 1.0) -> SweepResult:
     """One forward SMC sweep: vcsmc.py:406-451 driving body_rank_update vcsmc.py:332-400.
 
     ``lam_l``/``lam_r`` are the rates exp(variable) [N-1]; ``Q`` [4,4]; ``pi`` [1,4] or [4].
     ``site_idx`` selects a site minibatch exactly like np.take(data, slice, axis=2) (vcsmc.py:533).
     Node ids in ``forests``: leaf i -> i; the node created at event (r,k) -> N + r*K + k.
+    ``allreduce`` / ``scalar_share`` restate the site-sharding protocol of the product:
+    each rank holds a slice of the sites, the forest log-likelihood is summed across ranks, and the gradient of
+    the site-INDEPENDENT terms (branch priors, proposal density) is scaled by ``scalar_share`` so that the sum of
+    the per-rank gradients is the full gradient (share 1 on one rank, 0 on the others).
     """
+    def shared(t):
+        return t if scalar_share == 1.0 else scalar_share * t + (1.0 - scalar_share) * t.detach()
+
     g = np.asarray(genome, dtype=np.float64)
     if site_idx is not None:
         g = np.take(g, site_idx, axis=1)
@@ -300,13 +326,14 @@ def sweep(genome: np.ndarray, K: int, lam_l: torch.Tensor, lam_r: torch.Tensor, 
         if keep_nodes:
             new_nodes.append(new.detach().clone())
         # -- weights (vcsmc.py:376-395)
-        ll_r = compute_forest_posterior(core, record, pi)
+        ll_r = compute_forest_posterior(core, record, pi, allreduce)
         lsel = left_branches[1:r + 2]
         rsel = right_branches[1:r + 2]
-        ll_r = ll_r + (-lam_l[r] * lsel + torch.log(lam_l[r])).sum(dim=0) \
-                    + (-lam_r[r] * rsel + torch.log(lam_r[r])).sum(dim=0)
+        ll_r = ll_r + shared((-lam_l[r] * lsel + torch.log(lam_l[r])).sum(dim=0)
+                             + (-lam_r[r] * rsel + torch.log(lam_r[r])).sum(dim=0))
         v_minus = overcounting_correct(record)
-        lw_r = ll_r - ll_tilde - (torch.log(lam_l[r]) - lam_l[r] * b_l + torch.log(lam_r[r]) - lam_r[r] * b_r) \
+        lw_r = ll_r - ll_tilde \
+            - shared(torch.log(lam_l[r]) - lam_l[r] * b_l + torch.log(lam_r[r]) - lam_r[r] * b_r) \
             + torch.log(v_minus.to(F64)) - q
         log_weights = torch.cat([log_weights, lw_r.unsqueeze(0)], dim=0)
         log_likelihood = torch.cat([log_likelihood, ll_r.unsqueeze(0)], dim=0)

@@ -24,6 +24,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .sharding import local_sites, scalar_share
 
 F64 = torch.float64
 
@@ -104,9 +105,7 @@ class VCSMC:
     # -- the sweep ----------------------------------------------------------------------------
     def _local_sites(self, site_idx: Optional[np.ndarray]) -> np.ndarray:
         idx = np.arange(self.S, dtype=np.int32) if site_idx is None else np.asarray(site_idx, dtype=np.int32)
-        if self.world > 1:
-            idx = np.array_split(idx, self.world)[self.rank]   # contiguous shards of the batch's site list
-        return idx
+        return local_sites(idx, self.rank, self.world)
 
     def _sweep_for(self, n_sites: int, need_grad: bool) -> ops.Sweep:
         key = (n_sites, need_grad)
@@ -117,7 +116,7 @@ class VCSMC:
             if self.world > 1:
                 import torch.distributed as dist
                 sw.set_allreduce(lambda t: dist.all_reduce(t))
-                sw.set_option("scalar_share", 1.0 if self.rank == 0 else 0.0)
+                sw.set_option("scalar_share", scalar_share(self.rank, self.world))
             self._sweeps[key] = sw
         return self._sweeps[key]
 
