@@ -146,6 +146,7 @@ int vcsmc_sweep_set_allreduce(vcsmc_sweep_t* h, vcsmc_allreduce_fn fn, void* use
  * (site sharding: 1 on rank 0, 0 elsewhere, then sum the gradients across ranks);
  * "skip_zero" (default 1): backward skips rank events whose adjoint is exactly zero (W underflowed to 0 and no
  * descendant uses the node) -- results are identical, set 0 to force the dense reverse sweep;
+ * "max_chunk_sites" (default 0 = unlimited): cap on the site chunk of the recompute backward (testing aid);
  * "profile" (default 0): record CUDA events around every merge launch, read with vcsmc_sweep_profile. */
 int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value);
 

@@ -62,7 +62,7 @@ int vcsmc_merge_fwd(const uint8_t* codes, int64_t codes_stride, double* pool, in
                     int jc, double* ell_part, double* ell, void* stream) {
   if (!lsrc || !rsrc || !P || !pi || !ell_part || K < 0 || n_sites < 0 || slot_sites < n_sites) { set_error("merge_fwd: bad argument"); return VCSMC_ERR_ARG; }
   int n_parts = 0;
-  int rc = launch_merge_fwd(codes, codes_stride, pool, slot_sites, lsrc, rsrc, dst, nullptr, nullptr, P, pi, K, n_sites, jc, 0, ell_part, &n_parts, (cudaStream_t)stream);
+  int rc = launch_merge_fwd(codes, codes_stride, pool, slot_sites, lsrc, rsrc, dst, nullptr, nullptr, P, pi, K, -1, n_sites, jc, 0, ell_part, &n_parts, (cudaStream_t)stream);
   if (rc || !ell || K == 0 || n_sites == 0) return rc;
   return launch_ell_reduce(ell_part, n_parts, K, ell, (cudaStream_t)stream);
 }
@@ -71,7 +71,7 @@ int vcsmc_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* po
                     const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc, const double* P, const double* pi,
                     const double* coef, int64_t K, int n_sites, int jc, double* dP, double* dpi_each, void* stream) {
   if (!lsrc || !rsrc || !P || !pi || !coef || !dP || K < 0 || n_sites < 0 || slot_sites < n_sites) { set_error("merge_bwd: bad argument"); return VCSMC_ERR_ARG; }
-  return launch_merge_bwd(codes, codes_stride, pool, gpool, slot_sites, lsrc, rsrc, gsrc, nullptr, nullptr, P, pi, coef, K, n_sites, jc, 0, dP, dpi_each, (cudaStream_t)stream);
+  return launch_merge_bwd(codes, codes_stride, pool, gpool, slot_sites, lsrc, rsrc, gsrc, nullptr, nullptr, P, pi, coef, K, -1, n_sites, jc, 0, dP, dpi_each, (cudaStream_t)stream);
 }
 
 int vcsmc_propose_pairs(const float* u, int64_t K, int n, int32_t* coal, int32_t* rem, void* stream) {

@@ -10,17 +10,19 @@ int merge_fwd_tiles(int n_sites);
 int merge_ell_parts(int n_sites);  // upper bound of the partial sums per particle written by launch_merge_fwd
 int launch_merge_fwd(const uint8_t* codes, int64_t codes_stride, double* pool, int64_t slot_sites, const int32_t* lsrc,
                      const int32_t* rsrc, const int32_t* dst, const int32_t* order, const int32_t* count,
-                     const double* P, const double* pi, int64_t K, int n_sites, int jc, int skip_unstored,
-                     double* ell_part, int* n_parts, cudaStream_t st);
+                     const double* P, const double* pi, int64_t K, int64_t n_active, int n_sites, int jc,
+                     int skip_unstored, double* ell_part, int* n_parts, cudaStream_t st);
 int launch_ell_reduce(const double* ell_part, int n_part, int64_t K, double* ell, cudaStream_t st);
 int launch_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* pool, double* gpool, int64_t slot_sites,
                      const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc, const int32_t* order,
                      const int32_t* count, const double* P, const double* pi, const double* coef, int64_t K,
-                     int n_sites, int jc, int skip_zero, double* dP, double* dpi_each, cudaStream_t st);
+                     int64_t n_active, int n_sites, int jc, int skip_zero, double* dP, double* dpi_each, cudaStream_t st);
 
 // sort.cu
 size_t sort_temp_bytes(int64_t K);
-int launch_sort_order(const int32_t* lsrc, const int32_t* rsrc, const int32_t* active, int64_t K, uint64_t* keys_in,
+size_t scan_temp_bytes(int64_t n);
+int launch_exclusive_scan_i32(const int32_t* in, int32_t* out, int64_t n, void* temp, size_t temp_bytes, cudaStream_t st);
+int launch_sort_order(const int32_t* lsrc, const int32_t* rsrc, const int32_t* active, int64_t K, int64_t max_slot, uint64_t* keys_in,
                       uint64_t* keys_out, int32_t* vals_in, int32_t* order_out, int32_t* count_out, void* temp,
                       size_t temp_bytes, cudaStream_t st);
 

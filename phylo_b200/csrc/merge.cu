@@ -517,10 +517,12 @@ int merge_ell_parts(int n_sites) { return merge_fwd_tiles(n_sites) * kWarps; }
 
 int launch_merge_fwd(const uint8_t* codes, int64_t codes_stride, double* pool, int64_t slot_sites, const int32_t* lsrc,
                      const int32_t* rsrc, const int32_t* dst, const int32_t* order, const int32_t* count,
-                     const double* P, const double* pi, int64_t K, int n_sites, int jc, int skip_unstored,
-                     double* ell_part, int* n_parts, cudaStream_t st) {
+                     const double* P, const double* pi, int64_t K, int64_t n_active, int n_sites, int jc,
+                     int skip_unstored, double* ell_part, int* n_parts, cudaStream_t st) {
+  // n_active: host-side knowledge of *count (exact), or < 0 when only the device knows (then K bounds the grid)
   if (n_parts) *n_parts = 0;
-  if (K <= 0 || n_sites <= 0) return VCSMC_OK;
+  if (K <= 0 || n_sites <= 0 || n_active == 0) return VCSMC_OK;
+  const int64_t Kw = n_active > 0 ? n_active : K;
   static bool configured = false;
   if (!configured) {
     VCSMC_CUDA(cudaFuncSetAttribute(merge_fwd_kernel<true, kSptFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
@@ -530,11 +532,11 @@ int launch_merge_fwd(const uint8_t* codes, int64_t codes_stride, double* pool, i
   FwdArgs a;
   a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.slot_sites = slot_sites;
   a.lsrc = lsrc; a.rsrc = rsrc; a.dst = dst; a.order = order; a.count = count; a.P = P; a.pi = pi; a.K = K;
-  a.n_sites = n_sites; a.tiles = merge_fwd_tiles(n_sites); a.R = pick_group(K, a.tiles);
+  a.n_sites = n_sites; a.tiles = merge_fwd_tiles(n_sites); a.R = pick_group(Kw, a.tiles);
   a.skip_unstored = skip_unstored; a.ell_part = ell_part;
-  pick_chunks(K, a.R, a.tiles, &a.tiles_per_item, &a.n_chunks);
+  pick_chunks(Kw, a.R, a.tiles, &a.tiles_per_item, &a.n_chunks);
   if (n_parts) *n_parts = a.n_chunks * kWarps;
-  const unsigned grid = pick_grid(K, a.R, a.n_chunks);
+  const unsigned grid = pick_grid(Kw, a.R, a.n_chunks);
   if (jc) merge_fwd_kernel<true, kSptFwd><<<grid, kTileThreads, kFwdSmemBytes, st>>>(a);
   else merge_fwd_kernel<false, kSptFwd><<<grid, kTileThreads, kFwdSmemBytes, st>>>(a);
   VCSMC_LAUNCH_CHECK("merge_fwd_kernel");
@@ -550,17 +552,18 @@ int launch_ell_reduce(const double* ell_part, int n_part, int64_t K, double* ell
 int launch_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* pool, double* gpool, int64_t slot_sites,
                      const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc, const int32_t* order,
                      const int32_t* count, const double* P, const double* pi, const double* coef, int64_t K,
-                     int n_sites, int jc, int skip_zero, double* dP, double* dpi_each, cudaStream_t st) {
-  if (K <= 0 || n_sites <= 0) return VCSMC_OK;
+                     int64_t n_active, int n_sites, int jc, int skip_zero, double* dP, double* dpi_each, cudaStream_t st) {
+  if (K <= 0 || n_sites <= 0 || n_active == 0) return VCSMC_OK;
+  const int64_t Kw = n_active > 0 ? n_active : K;
   BwdArgs a;
   a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.gpool = gpool; a.slot_sites = slot_sites;
   a.lsrc = lsrc; a.rsrc = rsrc; a.gsrc = gsrc; a.order = order; a.count = count; a.P = P; a.pi = pi;
   a.coef = coef; a.K = K; a.n_sites = n_sites; a.dP = dP; a.dpi_each = dpi_each; a.skip_zero = skip_zero;
   const int spt = jc ? kSptBwdJC : kSptBwdGeneral;
   a.tiles = (n_sites + kTileThreads * spt - 1) / (kTileThreads * spt);
-  a.R = pick_group(K, a.tiles);
-  pick_chunks(K, a.R, a.tiles, &a.tiles_per_item, &a.n_chunks);
-  const unsigned grid = pick_grid(K, a.R, a.n_chunks);
+  a.R = pick_group(Kw, a.tiles);
+  pick_chunks(Kw, a.R, a.tiles, &a.tiles_per_item, &a.n_chunks);
+  const unsigned grid = pick_grid(Kw, a.R, a.n_chunks);
   if (jc) merge_bwd_kernel<true, kSptBwdJC><<<grid, kTileThreads, 0, st>>>(a);
   else merge_bwd_kernel<false, kSptBwdGeneral><<<grid, kTileThreads, 0, st>>>(a);
   VCSMC_LAUNCH_CHECK("merge_bwd_kernel");

@@ -35,69 +35,70 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) propose_pairs_kernel(const 
 constexpr int kCdfThreads = 1024;
 
 // stats[0] = logsumexp(lw), stats[1] = total = cdf[K-1], stats[2] = ESS, stats[3] = max(lw)
+// One CTA, fixed order: warp w owns the contiguous segment [w*seg, (w+1)*seg) and walks it 32 elements at a time
+// (coalesced); the running sum inside a segment is a warp shuffle scan plus a carried offset.
 __global__ void __launch_bounds__(kCdfThreads) resample_cdf_kernel(const double* __restrict__ lw, int64_t K,
                                                                    double* __restrict__ cdf,
                                                                    double* __restrict__ stats) {
-  __shared__ double sm[kCdfThreads / 32];
-  __shared__ double sm2[kCdfThreads / 32];
+  constexpr int NW = kCdfThreads / 32;
+  __shared__ double sm[NW];
+  __shared__ double sm2[NW];
   __shared__ double bc[2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int64_t chunk = (K + kCdfThreads - 1) / kCdfThreads;
-  const int64_t b = min((int64_t)tid * chunk, K), e = min(b + chunk, K);
+  const int64_t seg = ((K + NW - 1) / NW + 31) / 32 * 32;
+  const int64_t b = min((int64_t)wid * seg, K), e = min(b + seg, K);
 
   // max
   double m = -INFINITY;
-  for (int64_t i = b; i < e; ++i) m = fmax(m, lw[i]);
-  m = warp_max(m);
+  for (int64_t i = b + lane; i < e; i += 32) m = fmax(m, lw[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   if (lane == 0) sm[wid] = m;
   __syncthreads();
   if (tid == 0) {
     double t = sm[0];
-    for (int i = 1; i < kCdfThreads / 32; ++i) t = fmax(t, sm[i]);
+    for (int i = 1; i < NW; ++i) t = fmax(t, sm[i]);
     bc[0] = t;
   }
   __syncthreads();
   const double M = bc[0];
 
-  // logsumexp
+  // logsumexp (fixed order: lane-strided partial sums, shuffle tree, then warps in order)
   double s = 0.0;
-  for (int64_t i = b; i < e; ++i) s += exp(lw[i] - M);
+  for (int64_t i = b + lane; i < e; i += 32) s += exp(lw[i] - M);
   s = warp_sum(s);
   __syncthreads();
   if (lane == 0) sm[wid] = s;
   __syncthreads();
   if (tid == 0) {
     double t = 0.0;
-    for (int i = 0; i < kCdfThreads / 32; ++i) t += sm[i];
+    for (int i = 0; i < NW; ++i) t += sm[i];
     bc[1] = M + log(t);
   }
   __syncthreads();
   const double lse = bc[1];
   const double mlog = M - lse;  // max of the normalised logits (vcsmc.py:284)
 
-  // running sum of exp(logit - max): thread-local totals, CTA exclusive scan, then the prefix itself
+  // segment totals of w = exp(logit - max) and of w^2
   double run = 0.0, sq = 0.0;
-  for (int64_t i = b; i < e; ++i) {
+  for (int64_t i = b + lane; i < e; i += 32) {
     const double w = exp((lw[i] - lse) - mlog);
     run += w;
     sq = fma(w, w, sq);
   }
-  double incl = run;  // inclusive warp scan
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  const double sqw = warp_sum(sq);
+  run = warp_sum(run);
+  sq = warp_sum(sq);
   __syncthreads();
-  if (lane == 31) sm[wid] = incl;
-  if (lane == 0) sm2[wid] = sqw;
+  if (lane == 0) {
+    sm[wid] = run;
+    sm2[wid] = sq;
+  }
   __syncthreads();
   if (tid == 0) {
     double t = 0.0, q = 0.0;
-    for (int i = 0; i < kCdfThreads / 32; ++i) {
+    for (int i = 0; i < NW; ++i) {
       const double v = sm[i];
-      sm[i] = t;  // exclusive offset of warp i
+      sm[i] = t;  // exclusive offset of segment i
       t += v;
       q += sm2[i];
     }
@@ -107,10 +108,18 @@ __global__ void __launch_bounds__(kCdfThreads) resample_cdf_kernel(const double*
     stats[3] = M;
   }
   __syncthreads();
-  double off = sm[wid] + (incl - run);
-  for (int64_t i = b; i < e; ++i) {
-    off += exp((lw[i] - lse) - mlog);
-    cdf[i] = off;
+  // running sum inside the segment
+  double carry = sm[wid];
+  for (int64_t i0 = b; i0 < e; i0 += 32) {
+    const int64_t i = i0 + lane;
+    double w = i < e ? exp((lw[i] - lse) - mlog) : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
+    }
+    if (i < e) cdf[i] = carry + w;
+    carry += __shfl_sync(0xffffffffu, w, 31);
   }
 }
 

@@ -165,30 +165,31 @@ __global__ void gc_mark_kernel(const int32_t* __restrict__ ids_new, const int32_
   }
 }
 
-// The K lowest free slots, in order, go to particles 0..K-1.  Single CTA, fixed order.
+// The K lowest free slots, in order, go to particles 0..K-1.  Single CTA, fixed order.  Each warp owns a contiguous
+// segment of the flag array and walks it 32 flags at a time (coalesced), compacting with ballot/popc.
 __global__ void __launch_bounds__(1024) gc_alloc_kernel(const int32_t* __restrict__ flags, int64_t P, int64_t K, int N, int n,
                                                         int32_t* __restrict__ dst, int32_t* __restrict__ slot_new,
                                                         int32_t* __restrict__ status) {
-  __shared__ int64_t warp_tot[32];
+  __shared__ int64_t warp_off[33];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int64_t chunk = (P + 1023) / 1024;
-  const int64_t b = min((int64_t)tid * chunk, P), e = min(b + chunk, P);
-  int64_t cnt = 0;
-  for (int64_t i = b; i < e; ++i) cnt += flags[i] == 0;
-  int64_t incl = cnt;
+  // Lowest-free-first allocation keeps every slot ever used below the running peak (live + K), and the live slots of
+  // this event are a subset of last event's (live + new) <= previous peak: the K lowest free slots are < peak + K.
+  const int64_t Pfull = P;
+  P = min(Pfull, (int64_t)status[1] + K);
+  const int64_t seg = ((P + 31) / 32 + 31) / 32 * 32;  // per-warp segment length, multiple of 32
+  const int64_t b = min((int64_t)wid * seg, P), e = min(b + seg, P);
+  int cnt = 0;
+  for (int64_t i = b + lane; i < e; i += 32) cnt += flags[i] == 0;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int64_t t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) warp_tot[wid] = incl;
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) warp_off[wid + 1] = cnt;
   __syncthreads();
   if (tid == 0) {
     int64_t t = 0;
-    for (int i = 0; i < 32; ++i) {
-      const int64_t v = warp_tot[i];
-      warp_tot[i] = t;
-      t += v;
+    warp_off[0] = 0;
+    for (int i = 1; i <= 32; ++i) {
+      t += warp_off[i];
+      warp_off[i] = t;
     }
     if (t < K) status[0] = VCSMC_ERR_POOL;
     const int64_t used = P - t + (t < K ? t : K);
@@ -199,13 +200,17 @@ __global__ void __launch_bounds__(1024) gc_alloc_kernel(const int32_t* __restric
     }
   }
   __syncthreads();
-  int64_t j = warp_tot[wid] + (incl - cnt);
-  for (int64_t i = b; i < e && j < K; ++i) {
-    if (flags[i] == 0) {
-      dst[j] = (int32_t)i;
-      slot_new[j * N + (n - 2)] = (int32_t)i;
-      ++j;
+  int64_t j = warp_off[wid];
+  for (int64_t i0 = b; i0 < e && j < K; i0 += 32) {
+    const int64_t i = i0 + lane;
+    const bool is_free = i < e && flags[i] == 0;
+    const unsigned m = __ballot_sync(0xffffffffu, is_free);
+    const int64_t mine = j + __popc(m & ((1u << lane) - 1));
+    if (is_free && mine < K) {
+      dst[mine] = (int32_t)i;
+      slot_new[mine * N + (n - 2)] = (int32_t)i;
     }
+    j += __popc(m);
   }
 }
 
@@ -309,17 +314,21 @@ __global__ void mark_consumed_kernel(const int32_t* __restrict__ lref, const int
   if (rref[i] >= N) consumed[rref[i] - N] = 1;
 }
 
+// child / adjoint / output slots of every event for the reverse sweep.  slot_of == null: direct map (slot = event
+// index, nodes retained from the forward); otherwise the compact numbering of the consumed nodes (chunked mode).
 __global__ void bwd_src_kernel(const int32_t* __restrict__ lref, const int32_t* __restrict__ rref,
-                               const int32_t* __restrict__ consumed, int64_t n, int N, int32_t* __restrict__ lsrc,
-                               int32_t* __restrict__ rsrc, int32_t* __restrict__ gsrc, int32_t* __restrict__ dst) {
+                               const int32_t* __restrict__ consumed, const int32_t* __restrict__ slot_of, int64_t n, int N,
+                               int32_t* __restrict__ lsrc, int32_t* __restrict__ rsrc, int32_t* __restrict__ gsrc,
+                               int32_t* __restrict__ dst) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int l = lref[i], r = rref[i];
-  lsrc[i] = l < N ? -(l + 1) : l - N;
-  rsrc[i] = r < N ? -(r + 1) : r - N;
+  lsrc[i] = l < N ? -(l + 1) : (slot_of ? slot_of[l - N] : l - N);
+  rsrc[i] = r < N ? -(r + 1) : (slot_of ? slot_of[r - N] : r - N);
   const int c = consumed[i];
-  gsrc[i] = c ? (int32_t)i : -1;
-  dst[i] = c ? (int32_t)i : -1;
+  const int mine = slot_of ? slot_of[i] : (int32_t)i;
+  gsrc[i] = c ? mine : -1;
+  dst[i] = c ? mine : -1;
 }
 
 struct CoefArgs {
@@ -397,15 +406,16 @@ __global__ void bwd_active_kernel(const double* __restrict__ cnew, const int32_t
 }
 
 // zero the adjoint slots of the consumed nodes of one rank event (the first *count entries of `order`)
-__global__ void zero_consumed_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ count, int64_t e0,
-                                     int64_t slot_sites, int n_sites, double* __restrict__ gpool) {
+__global__ void zero_consumed_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ count,
+                                     const int32_t* __restrict__ gsrc, int64_t slot_sites, int n_sites,
+                                     double* __restrict__ gpool) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sites) return;
   const int n = *count;
   d4 z;
 #pragma unroll
   for (int j = 0; j < 4; ++j) z.v[j] = 0.0;
-  for (int j = blockIdx.y; j < n; j += gridDim.y) st_site(gpool + ((e0 + order[j]) * slot_sites + s) * 4, z);
+  for (int j = blockIdx.y; j < n; j += gridDim.y) st_site(gpool + ((int64_t)gsrc[order[j]] * slot_sites + s) * 4, z);
 }
 
 // db -> dlam through b = -log(U)/lam, and accumulation of the per-matrix dQ (vcsmc.py:353-358 reversed)
@@ -502,7 +512,7 @@ struct vcsmc_sweep {
       o_u_pair, o_u_bl, o_u_br, o_u_res, o_ell_part, o_ell_new, o_lsrc, o_rsrc, o_dst, o_ldf, o_flags, o_childsum[2],
       o_Dacc[2], o_cnew, o_consumed, o_bsrc_l, o_bsrc_r, o_bsrc_g, o_bdst, o_dP, o_dpi_each, o_dQ_acc, o_dQ_each, o_dt,
       o_suf_l, o_suf_r, o_gB_l, o_gB_r, o_cleaf, o_pool, o_keys_in, o_keys_out, o_vals_in, o_order, o_count,
-      o_sort_temp, o_order_bwd, o_count_bwd, o_order_rec, o_count_rec, o_act_bwd, o_act_rec;
+      o_sort_temp, o_order_bwd, o_count_bwd, o_order_rec, o_count_rec, o_act_bwd, o_act_rec, o_cslot;
   size_t sort_temp = 0;
   int64_t pool_bytes;
   std::vector<int64_t> rem_off;  // per step offset (bytes) into rempos
@@ -518,6 +528,7 @@ struct vcsmc_sweep {
   void* allreduce_user = nullptr;
   double scalar_share = 1.0;
   int skip_zero = 1;
+  int max_chunk_sites = 0;  // testing aid: cap the backward site chunk (0 = as large as memory allows)
   // model pointers of the last forward (caller keeps them alive until backward)
   const uint8_t* codes = nullptr;
   const double* lam_l = nullptr;
@@ -617,6 +628,7 @@ int64_t plan(vcsmc_sweep* h) {
   h->o_order = L.take<int32_t>(K);
   h->o_count = L.take<int32_t>(4);
   h->sort_temp = sort_temp_bytes(K);
+  if (h->keep) { const size_t sc = scan_temp_bytes(E); if (sc > h->sort_temp) h->sort_temp = sc; }
   h->o_sort_temp = L.take<char>((int64_t)h->sort_temp + 256);
   if (h->keep) {
     for (int i = 0; i < 2; ++i) {
@@ -645,6 +657,7 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_count_rec = L.take<int32_t>(N);
     h->o_act_bwd = L.take<int32_t>(K);
     h->o_act_rec = L.take<int32_t>(K);
+    h->o_cslot = L.take<int32_t>(E + 1);
   }
   return L.off;
 }
@@ -765,6 +778,7 @@ int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value) {
   if (!h || !name) return VCSMC_ERR_ARG;
   if (!strcmp(name, "scalar_share")) h->scalar_share = value;
   else if (!strcmp(name, "skip_zero")) h->skip_zero = value != 0.0;
+  else if (!strcmp(name, "max_chunk_sites")) h->max_chunk_sites = (int)value;
   else if (!strcmp(name, "profile")) { h->profile = value != 0.0; h->ev_used = 0; h->ev_kind.clear(); }
   else { set_error("unknown option %s", name); return VCSMC_ERR_ARG; }
   return VCSMC_OK;
@@ -860,13 +874,13 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
       VCSMC_LAUNCH_CHECK("gc_alloc_kernel");
     }
     // visiting order: particles sorted by their pair of child nodes (shared children are read once per group)
-    rc = launch_sort_order(a.lsrc, a.rsrc, nullptr, K, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out),
+    rc = launch_sort_order(a.lsrc, a.rsrc, nullptr, K, h->pool_slots, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out),
                            h->p<int32_t>(h->o_vals_in), h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count),
                            h->p<char>(h->o_sort_temp), h->sort_temp, st);
     if (rc) return rc;
     int tiles = 0;  // partial sums per particle written by the merge
     h->prof_begin(0, st);
-    rc = launch_merge_fwd(codes, S, pool, S, a.lsrc, a.rsrc, a.dst, h->p<int32_t>(h->o_order), nullptr, P, pi, K, S, h->jc, 0,
+    rc = launch_merge_fwd(codes, S, pool, S, a.lsrc, a.rsrc, a.dst, h->p<int32_t>(h->o_order), nullptr, P, pi, K, -1, S, h->jc, 0,
                           h->p<double>(h->o_ell_part), &tiles, st);
     h->prof_end(st);
     if (rc) return rc;
@@ -939,7 +953,13 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   // ---- which nodes are ever consumed as a child; child/adjoint slots of every event
   mark_consumed_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(h->p<int32_t>(h->o_lref), h->p<int32_t>(h->o_rref), E, N, h->p<int32_t>(h->o_consumed));
   VCSMC_LAUNCH_CHECK("mark_consumed_kernel");
-  bwd_src_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(h->p<int32_t>(h->o_lref), h->p<int32_t>(h->o_rref), h->p<int32_t>(h->o_consumed), E, N,
+  const int32_t* slot_of = nullptr;
+  if (!h->retain) {
+    rc = launch_exclusive_scan_i32(h->p<int32_t>(h->o_consumed), h->p<int32_t>(h->o_cslot), E, h->p<char>(h->o_sort_temp), h->sort_temp, st);
+    if (rc) return rc;
+    slot_of = h->p<int32_t>(h->o_cslot);
+  }
+  bwd_src_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(h->p<int32_t>(h->o_lref), h->p<int32_t>(h->o_rref), h->p<int32_t>(h->o_consumed), slot_of, E, N,
                                                               h->p<int32_t>(h->o_bsrc_l), h->p<int32_t>(h->o_bsrc_r), h->p<int32_t>(h->o_bsrc_g), h->p<int32_t>(h->o_bdst));
   VCSMC_LAUNCH_CHECK("bwd_src_kernel");
 
@@ -982,24 +1002,46 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     VCSMC_LAUNCH_CHECK("bwd_active_kernel");
     const int32_t* bl = h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K;
     const int32_t* br = h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K;
-    rc = launch_sort_order(bl, br, h->p<int32_t>(h->o_act_bwd), K, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out), h->p<int32_t>(h->o_vals_in),
+    rc = launch_sort_order(bl, br, h->p<int32_t>(h->o_act_bwd), K, E, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out), h->p<int32_t>(h->o_vals_in),
                            h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r, h->p<char>(h->o_sort_temp), h->sort_temp, st);
     if (rc) return rc;
-    rc = launch_sort_order(bl, br, h->p<int32_t>(h->o_act_rec), K, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out), h->p<int32_t>(h->o_vals_in),
+    rc = launch_sort_order(bl, br, h->p<int32_t>(h->o_act_rec), K, E, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out), h->p<int32_t>(h->o_vals_in),
                            h->p<int32_t>(h->o_order_rec) + (int64_t)r * K, h->p<int32_t>(h->o_count_rec) + r, h->p<char>(h->o_sort_temp), h->sort_temp, st);
     if (rc) return rc;
   }
 
+  // one small D2H + sync: the host learns how many particles each rank event really has to visit, so that empty
+  // launches are skipped and grids are sized exactly (with ESS ~ 1 almost every reverse event is empty)
+  std::vector<int32_t> cnt_bwd(N, 0), cnt_rec(N, 0);
+  VCSMC_CUDA(cudaMemcpyAsync(cnt_bwd.data(), h->p<int32_t>(h->o_count_bwd), (N - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  VCSMC_CUDA(cudaMemcpyAsync(cnt_rec.data(), h->p<int32_t>(h->o_count_rec), (N - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  VCSMC_CUDA(cudaStreamSynchronize(st));
+  {
+    int64_t visited = 0;
+    for (int r = 0; r < N - 1; ++r) visited += cnt_bwd[r];
+    int32_t v = (int32_t)(visited > 2147483647LL ? 2147483647LL : visited);
+    VCSMC_CUDA(cudaMemcpyAsync(h->p<int32_t>(h->o_status) + 3, &v, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    VCSMC_CUDA(cudaStreamSynchronize(st));
+  }
+
   // ---- per-site pass: reverse pruning, by site chunks
-  const int Sc = h->chunk_sites;
-  double* lpool;
+  int Sc = h->chunk_sites;
+  double* lpool = h->p<double>(h->o_pool);
   double* gpool;
   if (h->retain) {
-    lpool = h->p<double>(h->o_pool);
     gpool = lpool + E * (int64_t)S * 4;
   } else {
-    lpool = h->p<double>(h->o_pool);
-    gpool = lpool + E * (int64_t)Sc * 4;
+    // only nodes that a later merge consumes are materialised: the chunk is as long as their count allows
+    int64_t n_cons = 0;
+    for (int r = 0; r < N - 1; ++r) n_cons += cnt_rec[r];
+    if (n_cons < 1) n_cons = 1;
+    int64_t sc = (h->pool_bytes / 2) / (n_cons * 32);
+    if (h->max_chunk_sites > 0 && sc > h->max_chunk_sites) sc = h->max_chunk_sites;
+    sc = sc / 256 * 256;
+    if (sc > S) sc = S;
+    if (sc < 256 && sc < S) { set_error("workspace too small for a 256-site backward chunk"); return VCSMC_ERR_ARG; }
+    Sc = (int)sc;
+    gpool = lpool + n_cons * (int64_t)Sc * 4;
   }
   int n_chunks = 0;
   for (int s0 = 0; s0 < S; s0 += Sc, ++n_chunks) {
@@ -1008,25 +1050,29 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     if (!h->retain) {
       // recompute the forward for this chunk, materialising only nodes that are consumed later
       for (int r = 0; r < N - 1; ++r) {
+        if (cnt_rec[r] == 0) continue;
         h->prof_begin(1, st);
         rc = launch_merge_fwd(codes_c, S, lpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
                               h->p<int32_t>(h->o_bdst) + (int64_t)r * K, h->p<int32_t>(h->o_order_rec) + (int64_t)r * K, h->p<int32_t>(h->o_count_rec) + r,
-                              h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, K, nc, h->jc, 1, h->p<double>(h->o_ell_part), nullptr, st);
+                              h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, K, cnt_rec[r], nc, h->jc, 1, h->p<double>(h->o_ell_part), nullptr, st);
         h->prof_end(st);
         if (rc) return rc;
       }
     }
     // zero the adjoint slots of consumed nodes
     for (int r = 0; r < N - 1; ++r) {
-      dim3 grid((nc + 255) / 256, 32, 1);
-      zero_consumed_kernel<<<grid, 256, 0, st>>>(h->p<int32_t>(h->o_order_rec) + (int64_t)r * K, h->p<int32_t>(h->o_count_rec) + r, (int64_t)r * K, Sc, nc, gpool);
+      if (cnt_rec[r] == 0) continue;
+      dim3 grid((nc + 255) / 256, cnt_rec[r] < 32 ? cnt_rec[r] : 32, 1);
+      zero_consumed_kernel<<<grid, 256, 0, st>>>(h->p<int32_t>(h->o_order_rec) + (int64_t)r * K, h->p<int32_t>(h->o_count_rec) + r,
+                                                 h->p<int32_t>(h->o_bsrc_g) + (int64_t)r * K, Sc, nc, gpool);
       VCSMC_LAUNCH_CHECK("zero_consumed_kernel");
     }
     for (int r = N - 2; r >= 0; --r) {
+      if (cnt_bwd[r] == 0) continue;
       h->prof_begin(2, st);
       rc = launch_merge_bwd(codes_c, S, lpool, gpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
                             h->p<int32_t>(h->o_bsrc_g) + (int64_t)r * K, h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r,
-                            h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, h->p<double>(h->o_cnew) + (int64_t)r * K, K, nc, h->jc, h->skip_zero,
+                            h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, h->p<double>(h->o_cnew) + (int64_t)r * K, K, cnt_bwd[r], nc, h->jc, h->skip_zero,
                             h->p<double>(h->o_dP) + (int64_t)r * K * 32, h->p<double>(h->o_dpi_each), st);
       h->prof_end(st);
       if (rc) return rc;

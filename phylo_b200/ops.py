@@ -280,7 +280,7 @@ class Sweep:
         if st[0] != 0:
             raise _lib.VcsmcError(st[0], "device-side failure during the sweep (status=%s); pool exhausted means the "
                                   "workspace is too small for the number of live nodes" % st)
-        return {"peak_pool_slots": st[1], "backward_chunks": st[2]}
+        return {"peak_pool_slots": st[1], "backward_chunks": st[2], "backward_events_visited": st[3]}
 
     def output(self, name: str) -> torch.Tensor:
         """A view (no copy) of a result table inside the workspace; valid until the next forward()."""

@@ -23,13 +23,14 @@ def dev(x):
     return torch.as_tensor(x).cuda().contiguous()
 
 
-def run_gpu(ops, genome, K, p, U, jc, workspace_bytes=None, grads=True, skip_zero=True):
+def run_gpu(ops, genome, K, p, U, jc, workspace_bytes=None, grads=True, skip_zero=True, max_chunk_sites=0):
     N, S = genome.shape[0], genome.shape[1]
     codes = ops.pack_alignment(dev(genome))
     lam_l, lam_r, Q, pi = O.model_from_params(p)
     sw = ops.Sweep(N, S, K, jc, keep_for_backward=grads, workspace_bytes=workspace_bytes)
     sw.set_uniforms(*gpu_uniforms(U))
     sw.set_option("skip_zero", 1.0 if skip_zero else 0.0)
+    sw.set_option("max_chunk_sites", float(max_chunk_sites))
     elbo = sw.forward(codes, dev(lam_l), dev(lam_r), None if jc else dev(Q), dev(pi.reshape(-1)))
     out = {k: sw.output(k).cpu().numpy().copy() for k in
            ("log_weights", "log_likelihood", "log_likelihood_tilde", "log_likelihood_R", "left_branches",
@@ -133,8 +134,12 @@ def test_sweep_gc_pool_and_chunked_backward(ops, primate_genome, jc):
     assert small < probe.retain_bytes
     del probe
     out, grads, sw = run_gpu(ops, g, K, p, U, jc, workspace_bytes=small)
-    assert not sw.retained and out["info"]["backward_chunks"] >= 3
+    assert not sw.retained and out["info"]["backward_chunks"] >= 1 and out["info"]["peak_pool_slots"] >= K
     compare_forward(out, res, N, K)
+    compare_grads(grads, g_ref, jc)
+    # several site chunks (ragged last chunk: 898 = 3 x 256 + 130), dense reverse sweep
+    out, grads, sw = run_gpu(ops, g, K, p, U, jc, workspace_bytes=small, max_chunk_sites=256, skip_zero=False)
+    assert out["info"]["backward_chunks"] == 4
     compare_grads(grads, g_ref, jc)
 
 
