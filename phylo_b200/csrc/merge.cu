@@ -14,6 +14,7 @@
 // of a shared child in registers across the run and issues ONE set of fp64 atomics per run instead of one per
 // particle, and reduces the per-particle 4x4 adjoints with a halving-butterfly warp transpose.
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "launch.h"
@@ -179,8 +180,8 @@ __device__ __forceinline__ void split_positive(double x, double& mant, int& ex) 
 
 constexpr int kFwdSmemBytes = kRMax * 32 * 8 + kRMax * kTileThreads * (8 + 4);
 
-template <bool JC, int SPT>
-__global__ void __launch_bounds__(kTileThreads, 2) merge_fwd_kernel(const FwdArgs a) {
+template <bool JC, int SPT, int MINB>
+__global__ void __launch_bounds__(kTileThreads, MINB) merge_fwd_kernel(const FwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double(*sP)[32] = reinterpret_cast<double(*)[32]>(smem_raw);
   double* s_prod = reinterpret_cast<double*>(smem_raw + kRMax * 32 * 8);   // [R][256] running mantissa products
@@ -512,7 +513,7 @@ unsigned pick_grid(int64_t K, int R, int n_chunks) {
 
 }  // namespace
 
-int merge_fwd_tiles(int n_sites) { return (n_sites + kTileThreads * kSptFwd - 1) / (kTileThreads * kSptFwd); }
+int merge_fwd_tiles(int n_sites) { return (n_sites + kTileThreads - 1) / kTileThreads; }  // upper bound (SPT = 1)
 int merge_ell_parts(int n_sites) { return merge_fwd_tiles(n_sites) * kWarps; }
 
 int launch_merge_fwd(const uint8_t* codes, int64_t codes_stride, double* pool, int64_t slot_sites, const int32_t* lsrc,
@@ -523,22 +524,45 @@ int launch_merge_fwd(const uint8_t* codes, int64_t codes_stride, double* pool, i
   if (n_parts) *n_parts = 0;
   if (K <= 0 || n_sites <= 0 || n_active == 0) return VCSMC_OK;
   const int64_t Kw = n_active > 0 ? n_active : K;
-  static bool configured = false;
-  if (!configured) {
-    VCSMC_CUDA(cudaFuncSetAttribute(merge_fwd_kernel<true, kSptFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
-    VCSMC_CUDA(cudaFuncSetAttribute(merge_fwd_kernel<false, kSptFwd>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
-    configured = true;
+  // Measured on B200 at 64 x 10k x 65,536 (ms per sweep of merge_fwd): general Q 265 (SPT 2, 2 CTAs/SM), 266 (SPT 1, 3),
+  // 264 (SPT 1, 4), 283 (SPT 1, 2); JC 208 / 213 / 214 / 211 -- occupancy is not the limiter.  Default: general -> SPT 1
+  // with 4 CTAs/SM (also best at 27 x 1949 x 8192), JC -> SPT 2 with 2 CTAs/SM.  VCSMC_FWD_VARIANT=0..3 overrides.
+  static int forced = -2;
+  if (forced == -2) {
+    const char* e = getenv("VCSMC_FWD_VARIANT");
+    forced = e ? atoi(e) : -1;
+    if (forced < -1 || forced > 3) forced = -1;
+    VCSMC_CUDA(cudaFuncSetAttribute(merge_fwd_kernel<true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+    VCSMC_CUDA(cudaFuncSetAttribute(merge_fwd_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+    VCSMC_CUDA(cudaFuncSetAttribute(merge_fwd_kernel<true, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+    VCSMC_CUDA(cudaFuncSetAttribute(merge_fwd_kernel<false, 1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+    VCSMC_CUDA(cudaFuncSetAttribute(merge_fwd_kernel<true, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+    VCSMC_CUDA(cudaFuncSetAttribute(merge_fwd_kernel<false, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+    VCSMC_CUDA(cudaFuncSetAttribute(merge_fwd_kernel<true, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+    VCSMC_CUDA(cudaFuncSetAttribute(merge_fwd_kernel<false, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
   }
+  const int variant = forced >= 0 ? forced : (jc ? 0 : 2);
+  const int spt = variant >= 1 ? 1 : 2;
   FwdArgs a;
   a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.slot_sites = slot_sites;
   a.lsrc = lsrc; a.rsrc = rsrc; a.dst = dst; a.order = order; a.count = count; a.P = P; a.pi = pi; a.K = K;
-  a.n_sites = n_sites; a.tiles = merge_fwd_tiles(n_sites); a.R = pick_group(Kw, a.tiles);
+  a.n_sites = n_sites; a.tiles = (n_sites + kTileThreads * spt - 1) / (kTileThreads * spt); a.R = pick_group(Kw, a.tiles);
   a.skip_unstored = skip_unstored; a.ell_part = ell_part;
   pick_chunks(Kw, a.R, a.tiles, &a.tiles_per_item, &a.n_chunks);
   if (n_parts) *n_parts = a.n_chunks * kWarps;
   const unsigned grid = pick_grid(Kw, a.R, a.n_chunks);
-  if (jc) merge_fwd_kernel<true, kSptFwd><<<grid, kTileThreads, kFwdSmemBytes, st>>>(a);
-  else merge_fwd_kernel<false, kSptFwd><<<grid, kTileThreads, kFwdSmemBytes, st>>>(a);
+#define VCSMC_FWD_LAUNCH(SPT, MINB)                                                                       \
+  do {                                                                                                    \
+    if (jc) merge_fwd_kernel<true, SPT, MINB><<<grid, kTileThreads, kFwdSmemBytes, st>>>(a);              \
+    else merge_fwd_kernel<false, SPT, MINB><<<grid, kTileThreads, kFwdSmemBytes, st>>>(a);                \
+  } while (0)
+  switch (variant) {
+    case 1: VCSMC_FWD_LAUNCH(1, 3); break;
+    case 2: VCSMC_FWD_LAUNCH(1, 4); break;
+    case 3: VCSMC_FWD_LAUNCH(1, 2); break;
+    default: VCSMC_FWD_LAUNCH(2, 2); break;
+  }
+#undef VCSMC_FWD_LAUNCH
   VCSMC_LAUNCH_CHECK("merge_fwd_kernel");
   return VCSMC_OK;
 }
