@@ -128,6 +128,8 @@ typedef struct {
   int32_t jc;            /* 1 = JC closed form, 0 = general Q */
   int32_t keep_for_backward; /* 0 = forward only (nodes freed when dead) */
   int64_t workspace_bytes;   /* size of the workspace the caller will pass (0 = ask for the minimum) */
+  int32_t n_sub;             /* 0 = VCSMC (vcsmc.py); M > 0 = VNCSMC nested look-ahead with M sub-samples (vncsmc.py, --M) */
+  int32_t reserved;
 } vcsmc_sweep_config;
 
 typedef struct {
@@ -155,6 +157,11 @@ int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value);
 int vcsmc_sweep_set_uniforms(vcsmc_sweep_t* h, const float* u_pair, const double* u_bl, const double* u_br,
                              const double* u_res);
 int vcsmc_sweep_set_seed(vcsmc_sweep_t* h, uint64_t seed);
+/* VNCSMC explicit uniforms: look_bl / look_br are the ragged concatenation over r of [C(N-r,2)][M*K] float64 in
+ * [tiny,1) (pair t in r1-major order, column m*K + k, as vncsmc.py:346-353 lays them out); cat and res are [N-1,K]
+ * float64 in [0,1): the categorical draw over the C*M options (vncsmc.py:298) and the resampling draw. */
+int vcsmc_sweep_set_uniforms_nested(vcsmc_sweep_t* h, const double* look_bl, const double* look_br, const double* cat,
+                                    const double* res);
 
 /* codes [N,S] (row stride = S); lam_l, lam_r [N-1] rates; Q [16]; pi [4]. */
 int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* lam_l, const double* lam_r,
@@ -173,6 +180,7 @@ int vcsmc_sweep_profile(vcsmc_sweep_t* h, double* out_host);
  *   "log_likelihood_R"[K] "left_branches"[N-1,K] "right_branches"[N-1,K] (float64)
  *   "v_minus"[K] "ancestors"[N-1,K] "left_ref"[N-1,K] "right_ref"[N-1,K] "leaf_counts"[N-1,K] (int32)
  *   "log_z"[N-1] "ess"[N-1] (float64)   "status"[8] (int32: error, peak pool slots, backward chunks, ...)
+ *   "choice"[N-1,K] (int32, VNCSMC only: the chosen option t*M+m of vncsmc.py:298)
  *   "rem_positions" (uint8, ragged: rank event r holds [K, N-r-2] at byte offset sum_{r'<r} align16(K (N-r'-2)):
  *   the positions, in the ancestor's forest, of the subtrees a particle keeps, in the reference's order)
  * Returns NULL for an unknown name. */

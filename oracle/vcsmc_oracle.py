@@ -419,3 +419,158 @@ def pruning_loglik(genome: np.ndarray, merges, Q: torch.Tensor, pi: torch.Tensor
         nodes[nid] = (nodes[l] @ P_l) * (nodes[r] @ P_r)
         nid += 1
     return float(torch.log(nodes[nid - 1] @ pi.reshape(-1)).sum())
+
+
+# ----------------------------------------------------------------------------------------
+# VNCSMC: nested look-ahead proposal (vncsmc.py:295-499); everything else is shared with VCSMC
+# ----------------------------------------------------------------------------------------
+@dataclass
+class UniformsNested:
+    """Randomness of one VNCSMC sweep.
+
+    look_bl[r], look_br[r]  float64 [C(N-r,2), M*K] in [tiny,1): branch samples of pair t (r1-major enumeration,
+                            vncsmc.py:324-377), sub-particle m, particle k at column m*K + k  (vncsmc.py:350-353)
+    cat   float64 [N-1, K]  in [0,1): the categorical draw over the C*M options of each particle (vncsmc.py:298)
+    res   float64 [N-1, K]  in [0,1): resampling (row 0 unused)
+    """
+    look_bl: List[np.ndarray]
+    look_br: List[np.ndarray]
+    cat: np.ndarray
+    res: np.ndarray
+
+    @staticmethod
+    def draw(N: int, K: int, M: int, seed: int = 0) -> "UniformsNested":
+        rng = np.random.Generator(np.random.PCG64(seed))
+        tiny = np.finfo(np.float64).tiny
+        bl = [np.maximum(rng.random((int(ncr(N - r, 2)), M * K)), tiny) for r in range(N - 1)]
+        br = [np.maximum(rng.random((int(ncr(N - r, 2)), M * K)), tiny) for r in range(N - 1)]
+        return UniformsNested(bl, br, rng.random((N - 1, K)), rng.random((N - 1, K)))
+
+
+def categorical_rows(logits: np.ndarray, u: np.ndarray) -> np.ndarray:
+    """tf.random.categorical(logits [K,C], 1) (vncsmc.py:298), one injected uniform per row: per row the running
+    fp64 sum of exp(logit - rowmax) in column order, then upper_bound(u * total), clamped."""
+    lg = np.asarray(logits, dtype=np.float64)
+    w = np.exp(lg - lg.max(axis=1, keepdims=True))
+    cdf = np.cumsum(w, axis=1)
+    t = np.asarray(u, dtype=np.float64) * cdf[:, -1]
+    idx = (cdf <= t[:, None]).sum(axis=1)
+    return np.minimum(idx, lg.shape[1] - 1).astype(np.int64)
+
+
+def tree_posterior_K(data, leaf_counts, pi):
+    """vncsmc.py:217-233 (MK variant included: one leaf-count column): sum_s log(pi . data[k,s,:]) - log (2 max(c,2)-3)!!."""
+    lik = torch.matmul(data, pi.reshape(-1, 1)).squeeze(-1)
+    return torch.log(lik).sum(dim=1) - log_double_factorial(2 * torch.clamp(leaf_counts, min=2) - 3)
+
+
+def compute_potentials(core, record, lam_l_r, lam_r_r, Q, pi, M, u_bl, u_br):
+    """vncsmc.py:324-416: log-softmaxed look-ahead potentials [K, C*M] (column t*M+m) and the branch samples."""
+    K, n = core.shape[0], core.shape[1]
+    pots, lbs, rbs, pairs = [], [], [], []
+    t = 0
+    for r1 in range(n - 1):
+        for r2 in range(r1 + 1, n):
+            L_l, L_r = core[:, r1], core[:, r2]
+            L_l_MK, L_r_MK = L_l.repeat(M, 1, 1), L_r.repeat(M, 1, 1)              # index m*K + k  (:346-347)
+            b_l = -torch.log(torch.from_numpy(u_bl[t])) / lam_l_r                    # (:350-353)
+            b_r = -torch.log(torch.from_numpy(u_br[t])) / lam_r_r
+            merged = merge(L_l_MK, L_r_MK, b_l, b_r, Q)
+            c_l, c_r = record[:, r1].repeat(M), record[:, r2].repeat(M)
+            joint = tree_posterior_K(merged, c_l + c_r, pi) - tree_posterior_K(L_l_MK, c_l, pi) \
+                - tree_posterior_K(L_r_MK, c_r, pi)                                  # (:363-365)
+            pots.append(joint); lbs.append(b_l); rbs.append(b_r); pairs.append((r1, r2))
+            t += 1
+    C = len(pairs)
+    pot = torch.stack(pots).reshape(C * M, K).t()                                    # (:404-406)
+    pot = pot - torch.logsumexp(pot, dim=1, keepdim=True)                            # (:407)
+    l_br = torch.stack(lbs).reshape(C * M, K).t()
+    r_br = torch.stack(rbs).reshape(C * M, K).t()
+    return pot, np.array(pairs, dtype=np.int64), l_br, r_br
+
+
+def sweep_nested(genome: np.ndarray, K: int, M: int, lam_l, lam_r, Q, pi, U: UniformsNested,
+                 site_idx: Optional[np.ndarray] = None) -> SweepResult:
+    """One forward VNCSMC sweep: vncsmc.py:511-555 driving body_rank_update vncsmc.py:432-499."""
+    g = np.asarray(genome, dtype=np.float64)
+    if site_idx is not None:
+        g = np.take(g, site_idx, axis=1)
+    N, S, A = g.shape
+    pi = pi.reshape(-1)
+    core = torch.from_numpy(np.array([g] * K))
+    record = torch.ones((K, N), dtype=torch.int64)
+    left_branches = torch.zeros((1, K), dtype=F64)
+    right_branches = torch.zeros((1, K), dtype=F64)
+    log_weights = torch.zeros((1, K), dtype=F64)
+    log_likelihood = torch.zeros((1, K), dtype=F64)
+    ll_tilde = torch.full((K,), math.log(1.0 / K), dtype=F64)
+    ids = np.tile(np.arange(N, dtype=np.int64), (K, 1))
+    ancestors = np.tile(np.arange(K, dtype=np.int64), (N - 1, 1))
+    coal_hist, rem_hist, forests, choices = [], [], [], []
+    v_minus = torch.ones((K,), dtype=torch.int64)
+    ar = torch.arange(K)
+
+    for r in range(N - 1):
+        n = N - r
+        if r > 0:                                                            # vncsmc.py:440-446
+            idx_np = resample_indices(log_weights[r].detach().numpy(), U.res[r])
+            idx = torch.from_numpy(idx_np)
+            core, record, ids = core[idx], record[idx], ids[idx_np]
+            ll_tilde = log_likelihood[r][idx]
+            ancestors[r] = idx_np
+        # twist the proposal (vncsmc.py:449) and extend (vncsmc.py:295-322)
+        pot, pairs, l_all, r_all = compute_potentials(core, record, lam_l[r], lam_r[r], Q, pi, M, U.look_bl[r], U.look_br[r])
+        choice = categorical_rows(pot.detach().numpy(), U.cat[r])            # :298
+        choices.append(choice)
+        pair_idx = choice // M                                               # :299
+        coal_np = pairs[pair_idx].astype(np.int32)                           # :301  (r1 < r2)
+        rem_np = np.stack([np.array([i for i in range(n - 1, -1, -1) if i not in (c[0], c[1])], dtype=np.int32)
+                           for c in coal_np]).reshape(K, n - 2)              # :302-305 descending index order
+        ch = torch.from_numpy(choice)
+        q_log = pot[ar, ch]                                                  # :315-316 (a true log here)
+        b_l, b_r = l_all[ar, ch], r_all[ar, ch]                              # :317-320
+        coal, rem = torch.from_numpy(coal_np.astype(np.int64)), torch.from_numpy(rem_np.astype(np.int64))
+        coal_hist.append(coal_np); rem_hist.append(rem_np)
+        left_branches = torch.cat([left_branches, b_l.unsqueeze(0)], dim=0)
+        right_branches = torch.cat([right_branches, b_r.unsqueeze(0)], dim=0)
+        # the chosen merge is recomputed (vncsmc.py:458-465)
+        remaining_core = gather_across(core, rem)
+        L_l = gather_across(core, coal[:, 0:1]).squeeze(1)
+        L_r = gather_across(core, coal[:, 1:2]).squeeze(1)
+        new = merge(L_l, L_r, b_l, b_r, Q)
+        core = torch.cat([remaining_core, new.unsqueeze(1)], dim=1)
+        record = torch.cat([gather_across(record, rem), gather_across(record, coal).sum(dim=1, keepdim=True)], dim=1)
+        new_id = (N + r * K + np.arange(K, dtype=np.int64))[:, None]
+        ids = np.concatenate([np.take_along_axis(ids, rem_np.astype(np.int64), axis=1), new_id], axis=1)
+        forests.append(ids.copy())
+        # weights (vncsmc.py:472-491): identical to VCSMC except that q_log_proposal is a log-probability
+        ll_r = compute_forest_posterior(core, record, pi)
+        ll_r = ll_r + (-lam_l[r] * left_branches[1:r + 2] + torch.log(lam_l[r])).sum(dim=0) \
+                    + (-lam_r[r] * right_branches[1:r + 2] + torch.log(lam_r[r])).sum(dim=0)
+        v_minus = overcounting_correct(record)
+        lw_r = ll_r - ll_tilde - (torch.log(lam_l[r]) - lam_l[r] * b_l + torch.log(lam_r[r]) - lam_r[r] * b_r) \
+            + torch.log(v_minus.to(F64)) - q_log
+        log_weights = torch.cat([log_weights, lw_r.unsqueeze(0)], dim=0)
+        log_likelihood = torch.cat([log_likelihood, ll_r.unsqueeze(0)], dim=0)
+
+    elbo = compute_log_ZSMC(log_weights, K)
+    lb, rb = left_branches[1:], right_branches[1:]
+    l_prior = (torch.log(lam_l).unsqueeze(0) - lb.t() * lam_l.unsqueeze(0)).sum(dim=1)
+    r_prior = (torch.log(lam_l).unsqueeze(0) - rb.t() * lam_r.unsqueeze(0)).sum(dim=1)      # quirk Q4 as in vcsmc.py
+    ll_R = log_likelihood[N - 1] + log_double_factorial(torch.tensor(2.0 * N - 3)) - l_prior - r_prior
+    res = SweepResult(elbo=elbo, log_weights=log_weights[1:], log_likelihood=log_likelihood[1:],
+                      log_likelihood_tilde=ll_tilde, log_likelihood_R=ll_R, left_branches=lb, right_branches=rb,
+                      v_minus=v_minus, ancestors=ancestors, coal=coal_hist, rem=rem_hist, new_nodes=None,
+                      forests=forests, leaf_counts=record.numpy())
+    res.choices = choices
+    return res
+
+
+def elbo_and_grads_nested(genome, K, M, p: Params, U: UniformsNested, site_idx=None):
+    """VNCSMC ELBO and d(ELBO)/d(variables): autograd flows through the chosen potential AND the log-softmax
+    normaliser, i.e. through every look-ahead merge."""
+    leaves = [t.detach().clone().requires_grad_(True) for t in p.tensors()]
+    q = Params(leaves[0], leaves[1], None, None) if p.y_q is None else Params(*leaves)
+    lam_l, lam_r, Q, pi = model_from_params(q)
+    res = sweep_nested(genome, K, M, lam_l, lam_r, Q, pi, U, site_idx=site_idx)
+    return res, torch.autograd.grad(res.elbo, leaves)

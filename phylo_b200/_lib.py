@@ -23,7 +23,7 @@ class VcsmcError(RuntimeError):
 
 class SweepConfig(C.Structure):
     _fields_ = [("n_taxa", C.c_int32), ("n_sites", C.c_int32), ("n_particles", C.c_int64), ("jc", C.c_int32),
-                ("keep_for_backward", C.c_int32), ("workspace_bytes", C.c_int64)]
+                ("keep_for_backward", C.c_int32), ("workspace_bytes", C.c_int64), ("n_sub", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SweepSizes(C.Structure):
@@ -54,6 +54,7 @@ _SIGNATURES = {
     "vcsmc_sweep_set_option": (C.c_int, [_P, C.c_char_p, C.c_double]),
     "vcsmc_sweep_set_uniforms": (C.c_int, [_P, _P, _P, _P, _P]),
     "vcsmc_sweep_set_seed": (C.c_int, [_P, C.c_uint64]),
+    "vcsmc_sweep_set_uniforms_nested": (C.c_int, [_P, _P, _P, _P, _P]),
     "vcsmc_sweep_forward": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "vcsmc_sweep_backward": (C.c_int, [_P, C.c_double, _P, _P, _P, _P, _P]),
     "vcsmc_sweep_output": (_P, [_P, C.c_char_p]),

@@ -94,7 +94,7 @@ int vcsmc_resample(const double* lw, const double* u, int64_t K, int32_t* idx, d
 
 int vcsmc_philox_step_uniforms(uint64_t seed, int r, int64_t k0, int64_t K, int n, float* u_pair, double* u_bl, double* u_br, double* u_res, void* stream) {
   if (K < 0 || n < 0 || r < 0) { set_error("philox: bad argument"); return VCSMC_ERR_ARG; }
-  return launch_philox_step(seed, r, k0, K, n, u_pair, u_bl, u_br, u_res, (cudaStream_t)stream);
+  return launch_philox_step(seed, r, k0, K, n, u_pair, u_bl, u_br, u_res, nullptr, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -41,6 +41,34 @@ int launch_propose_pairs(const float* u, int64_t K, int n, int32_t* coal, int32_
 int launch_resample_cdf(const double* lw, int64_t K, double* cdf, double* stats /*[4]: lse,total,ess,max*/, cudaStream_t st);
 int launch_resample_search(const double* cdf, const double* stats, const double* u, int64_t K, int32_t* idx, cudaStream_t st);
 int launch_philox_step(uint64_t seed, int r, int64_t k0, int64_t K, int n, float* u_pair, double* u_bl, double* u_br,
-                       double* u_res, cudaStream_t st);
+                       double* u_res, double* u_cat, cudaStream_t st);
+
+// nested.cu (VNCSMC look-ahead)
+int nested_max_roots();
+int launch_nested_inherit(int r, int n, int N, int64_t K, const double* cdf, const double* u_res, const int32_t* ids_prev,
+                          const int32_t* cnt_prev, const int32_t* slot_prev, int32_t* ids, int32_t* cnt, int32_t* slot,
+                          int32_t* rows_all, const double* LL_prev, int32_t* anc, double* ll_tilde, cudaStream_t st);
+int launch_lookahead(int r, int n, int N, int M, int jc, int gc, int S, int64_t K, const int32_t* ids, const int32_t* cnt,
+                     const int32_t* slot, const uint8_t* codes, int64_t codes_stride, const double* pool, int64_t slot_sites,
+                     const double* ell_node, const double* ldf, const double* Q, const double* pi, const double* lam_l,
+                     const double* lam_r, const double* u_bl, const double* u_br, uint64_t seed, double* pot,
+                     cudaStream_t st);
+int launch_nested_choose(int r, int n, int N, int M, int gc, int64_t K, double* pot, const double* u_cat, const double* u_bl,
+                         const double* u_br, uint64_t seed, const double* lam_l, const double* lam_r, const int32_t* ids,
+                         const int32_t* cnt, const int32_t* slot, int32_t* ids_new, int32_t* cnt_new, int32_t* slot_new,
+                         int32_t* lref, int32_t* rref, int32_t* nleaf, uint8_t* rempos, int32_t* choice, double* b_l,
+                         double* b_r, double* t2, double* qlog, int32_t* lsrc, int32_t* rsrc, int32_t* dst, cudaStream_t st);
+int launch_nested_active(int r, int64_t K, int skip_zero, const double* lw, const double* stats, int32_t* active, cudaStream_t st);
+int launch_nested_mark_roots(int n, int N, int64_t K, const int32_t* active, const int32_t* rows, int32_t* consumed, cudaStream_t st);
+int launch_nested_coef(int r, int n, int N, int M, int64_t K, double grad, const double* lw, const double* stats,
+                       const double* pot, const int32_t* choice, const int32_t* anc, double* Dacc_next, cudaStream_t st);
+int launch_nested_virtual(int r, int n, int N, int M, int64_t K, double grad, const double* lw, const double* stats,
+                          const double* pot, const int32_t* choice, const int32_t* active, const int32_t* base,
+                          const int32_t* rows, const int32_t* slot_of, const double* u_bl, const double* u_br, uint64_t seed,
+                          const double* lam_l, const double* lam_r, int64_t v0, int64_t v1, int32_t* v_lsrc, int32_t* v_rsrc,
+                          double* v_coef, double* v_t2, cudaStream_t st);
+int launch_nested_reduce(int r, int64_t V, int jc, const double* dt, const double* dQ_each, const double* t2,
+                         const double* lam_l, const double* lam_r, double* dlam_l, double* dlam_r, double* dQ,
+                         cudaStream_t st);
 
 }  // namespace vcsmc

@@ -131,7 +131,8 @@ __global__ void resample_search_kernel(const double* __restrict__ cdf, const dou
 }
 
 __global__ void philox_step_kernel(uint64_t seed, int r, int64_t k0, int64_t K, int n, float* __restrict__ u_pair,
-                                   double* __restrict__ u_bl, double* __restrict__ u_br, double* __restrict__ u_res) {
+                                   double* __restrict__ u_bl, double* __restrict__ u_br, double* __restrict__ u_res,
+                                   double* __restrict__ u_cat) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K) return;
   const uint64_t k = (uint64_t)(k0 + i);  // LOGICAL particle index: identical streams for any GPU count
@@ -141,10 +142,11 @@ __global__ void philox_step_kernel(uint64_t seed, int r, int64_t k0, int64_t K, 
   const double tiny = 2.2250738585072014e-308;
   if (u_bl) u_bl[i] = fmax(u64_to_unit_f64(c[0], c[1]), tiny);   // tfp Exponential: U in [tiny, 1)
   if (u_br) u_br[i] = fmax(u64_to_unit_f64(c[2], c[3]), tiny);
-  if (u_res) {
+  if (u_res || u_cat) {
     uint32_t d[4] = {(uint32_t)k, (uint32_t)(k >> 32) | ((uint32_t)r << 8), 1u, 0u};
     philox4x32_10(d, s0, s1);
-    u_res[i] = u64_to_unit_f64(d[0], d[1]);
+    if (u_res) u_res[i] = u64_to_unit_f64(d[0], d[1]);
+    if (u_cat) u_cat[i] = u64_to_unit_f64(d[2], d[3]);
   }
   if (u_pair) {
     for (int j = 0; j < n; j += 4) {
@@ -191,9 +193,9 @@ int launch_resample_search(const double* cdf, const double* stats, const double*
 }
 
 int launch_philox_step(uint64_t seed, int r, int64_t k0, int64_t K, int n, float* u_pair, double* u_bl, double* u_br,
-                       double* u_res, cudaStream_t st) {
+                       double* u_res, double* u_cat, cudaStream_t st) {
   if (K <= 0) return VCSMC_OK;
-  philox_step_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(seed, r, k0, K, n, u_pair, u_bl, u_br, u_res);
+  philox_step_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(seed, r, k0, K, n, u_pair, u_bl, u_br, u_res, u_cat);
   VCSMC_LAUNCH_CHECK("philox_step_kernel");
   return VCSMC_OK;
 }

@@ -235,6 +235,7 @@ struct WeightArgs {
   double* LL;
   int32_t* vminus;
   double q;
+  const double* qlog;  // VNCSMC: per-particle log-probability of the chosen option (vncsmc.py:315-316), else null
 };
 
 // compute_forest_posterior with cached per-node scalars + branch priors + v^- + weight (vcsmc.py:376-395)
@@ -269,7 +270,7 @@ __global__ void step_weights_kernel(const WeightArgs a) {
   // quirk Q2: the CURRENT step's rate multiplies ALL earlier branches (vcsmc.py:380-383)
   const double LLr = (F + topo) + (-laml * cl + (double)(r + 1) * llog) + (-lamr * cr + (double)(r + 1) * rlog);
   // quirk Q3: q = 1/C(n,2) is subtracted raw (vcsmc.py:298,392)
-  const double lw = LLr - a.ll_tilde[k] - (llog - laml * bl + rlog - lamr * br) + log((double)vm) - a.q;
+  const double lw = LLr - a.ll_tilde[k] - (llog - laml * bl + rlog - lamr * br) + log((double)vm) - (a.qlog ? a.qlog[k] : a.q);
   a.LL[k] = LLr;
   a.lw[k] = lw;
   a.vminus[k] = vm;
@@ -497,6 +498,7 @@ using namespace vcsmc;
 
 struct vcsmc_sweep {
   int N, S, jc, keep;
+  int M = 0;  // VNCSMC sub-samples (0 = VCSMC)
   int64_t K;
   char* ws;
   int64_t ws_bytes;
@@ -512,7 +514,15 @@ struct vcsmc_sweep {
       o_u_pair, o_u_bl, o_u_br, o_u_res, o_ell_part, o_ell_new, o_lsrc, o_rsrc, o_dst, o_ldf, o_flags, o_childsum[2],
       o_Dacc[2], o_cnew, o_consumed, o_bsrc_l, o_bsrc_r, o_bsrc_g, o_bdst, o_dP, o_dpi_each, o_dQ_acc, o_dQ_each, o_dt,
       o_suf_l, o_suf_r, o_gB_l, o_gB_r, o_cleaf, o_pool, o_keys_in, o_keys_out, o_vals_in, o_order, o_count,
-      o_sort_temp, o_order_bwd, o_count_bwd, o_order_rec, o_count_rec, o_act_bwd, o_act_rec, o_cslot;
+      o_sort_temp, o_order_bwd, o_count_bwd, o_order_rec, o_count_rec, o_act_bwd, o_act_rec, o_cslot,
+      o_inh_ids, o_inh_cnt, o_inh_slot, o_pot, o_choice, o_qlog, o_u_cat, o_rows_all, o_nact, o_nbase, o_v_lsrc, o_v_rsrc,
+      o_v_coef, o_v_t2, o_v_P, o_v_dP, o_v_dt, o_v_dQ, o_v_dpi, o_v_order, o_v_keys_in, o_v_keys_out, o_v_vals, o_v_count, o_v_temp;
+  std::vector<int64_t> pot_off;  // per rank event, offset (doubles) into the potentials
+  int64_t v_batch = 0;           // virtual events per batch in the nested reverse sweep
+  size_t v_temp = 0;
+  const double* x_look_bl = nullptr;
+  const double* x_look_br = nullptr;
+  const double* x_cat = nullptr;
   size_t sort_temp = 0;
   int64_t pool_bytes;
   std::vector<int64_t> rem_off;  // per step offset (bytes) into rempos
@@ -622,6 +632,21 @@ int64_t plan(vcsmc_sweep* h) {
   h->o_rsrc = L.take<int32_t>(K);
   h->o_dst = L.take<int32_t>(K);
   h->o_ldf = L.take<double>(2 * (int64_t)N + 4);
+  if (h->M > 0) {
+    h->o_inh_ids = L.take<int32_t>(K * N);
+    h->o_inh_cnt = L.take<int32_t>(K * N);
+    h->o_inh_slot = L.take<int32_t>(K * N);
+    h->pot_off.assign(N, 0);
+    int64_t tot = 0;
+    for (int r = 0; r < N - 1; ++r) {
+      h->pot_off[r] = tot;
+      tot += K * (int64_t)((N - r) * (N - r - 1) / 2) * h->M;
+    }
+    h->o_pot = L.take<double>(tot + 1);
+    h->o_choice = L.take<int32_t>(E);
+    h->o_qlog = L.take<double>(K);
+    h->o_u_cat = L.take<double>(K);
+  }
   h->o_keys_in = L.take<uint64_t>(K);
   h->o_keys_out = L.take<uint64_t>(K);
   h->o_vals_in = L.take<int32_t>(K);
@@ -658,6 +683,30 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_act_bwd = L.take<int32_t>(K);
     h->o_act_rec = L.take<int32_t>(K);
     h->o_cslot = L.take<int32_t>(E + 1);
+    if (h->M > 0) {
+      h->o_rows_all = L.take<int32_t>(E * N);
+      h->o_nact = L.take<int32_t>(K);
+      h->o_nbase = L.take<int32_t>(K + 1);
+      const int64_t all = K * (int64_t)(N * (N - 1) / 2) * h->M;
+      h->v_batch = all < (1 << 20) ? all : (1 << 20);
+      const int64_t V = h->v_batch;
+      h->o_v_lsrc = L.take<int32_t>(V);
+      h->o_v_rsrc = L.take<int32_t>(V);
+      h->o_v_coef = L.take<double>(V);
+      h->o_v_t2 = L.take<double>(2 * V);
+      h->o_v_P = L.take<double>(32 * V);
+      h->o_v_dP = L.take<double>(32 * V);
+      h->o_v_dt = L.take<double>(2 * V);
+      h->o_v_dQ = L.take<double>(32 * V);
+      h->o_v_dpi = L.take<double>(4 * V);
+      h->o_v_order = L.take<int32_t>(V);
+      h->o_v_keys_in = L.take<uint64_t>(V);
+      h->o_v_keys_out = L.take<uint64_t>(V);
+      h->o_v_vals = L.take<int32_t>(V);
+      h->o_v_count = L.take<int32_t>(4);
+      h->v_temp = sort_temp_bytes(V);
+      h->o_v_temp = L.take<char>((int64_t)h->v_temp + 256);
+    }
   }
   return L.off;
 }
@@ -713,6 +762,8 @@ int check_cfg(const vcsmc_sweep_config* c) {
   if (c->n_taxa < 2 || c->n_taxa > kMaxRoots) { set_error("n_taxa=%d out of range [2,%d]", c->n_taxa, kMaxRoots); return VCSMC_ERR_ARG; }
   if (c->n_sites < 1) { set_error("n_sites must be >= 1"); return VCSMC_ERR_ARG; }
   if (c->n_particles < 1) { set_error("n_particles must be >= 1"); return VCSMC_ERR_ARG; }
+  if (c->n_sub < 0) { set_error("n_sub must be >= 0"); return VCSMC_ERR_ARG; }
+  if (c->n_sub > 0 && c->n_taxa > nested_max_roots()) { set_error("nested look-ahead supports at most %d taxa (got %d)", nested_max_roots(), c->n_taxa); return VCSMC_ERR_ARG; }
   if ((int64_t)(c->n_taxa - 1) * c->n_particles + c->n_taxa > 2147483000LL) { set_error("too many nodes for int32 references"); return VCSMC_ERR_ARG; }
   return VCSMC_OK;
 }
@@ -732,7 +783,7 @@ int vcsmc_sweep_query(const vcsmc_sweep_config* cfg, vcsmc_sweep_sizes* out) {
   if (rc) return rc;
   if (!out) { set_error("null out"); return VCSMC_ERR_ARG; }
   vcsmc_sweep tmp;
-  tmp.N = cfg->n_taxa; tmp.S = cfg->n_sites; tmp.K = cfg->n_particles; tmp.jc = cfg->jc; tmp.keep = cfg->keep_for_backward;
+  tmp.N = cfg->n_taxa; tmp.S = cfg->n_sites; tmp.K = cfg->n_particles; tmp.jc = cfg->jc; tmp.keep = cfg->keep_for_backward; tmp.M = cfg->n_sub;
   const int64_t tables = plan(&tmp);
   const int64_t full = full_pool_bytes(*cfg);
   out->retain_bytes = tables + (cfg->keep_for_backward ? 2 * full : full);
@@ -757,6 +808,7 @@ int vcsmc_sweep_create(const vcsmc_sweep_config* cfg, void* workspace, vcsmc_swe
   vcsmc_sweep* h = new (std::nothrow) vcsmc_sweep();
   if (!h) { set_error("out of host memory"); return VCSMC_ERR_ARG; }
   h->N = cfg->n_taxa; h->S = cfg->n_sites; h->K = cfg->n_particles; h->jc = cfg->jc; h->keep = cfg->keep_for_backward;
+  h->M = cfg->n_sub;
   h->ws = (char*)workspace; h->ws_bytes = cfg->workspace_bytes;
   const int64_t tables = plan(h);
   rc = decide_modes(h, tables, cfg->workspace_bytes, true);
@@ -788,6 +840,15 @@ int vcsmc_sweep_set_uniforms(vcsmc_sweep_t* h, const float* u_pair, const double
                              const double* u_res) {
   if (!h || !u_pair || !u_bl || !u_br || !u_res) { set_error("null uniforms"); return VCSMC_ERR_ARG; }
   h->x_pair = u_pair; h->x_bl = u_bl; h->x_br = u_br; h->x_res = u_res;
+  h->use_seed = false;
+  return VCSMC_OK;
+}
+
+int vcsmc_sweep_set_uniforms_nested(vcsmc_sweep_t* h, const double* look_bl, const double* look_br, const double* cat,
+                                    const double* res) {
+  if (!h || !look_bl || !look_br || !cat || !res) { set_error("null uniforms"); return VCSMC_ERR_ARG; }
+  if (h->M <= 0) { set_error("set_uniforms_nested on a sweep created with n_sub = 0"); return VCSMC_ERR_STATE; }
+  h->x_look_bl = look_bl; h->x_look_br = look_br; h->x_cat = cat; h->x_res = res;
   h->use_seed = false;
   return VCSMC_OK;
 }
@@ -825,16 +886,28 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
   }
   double* pool = h->p<double>(h->o_pool);
   int32_t* flags = h->p<int32_t>(h->o_flags);
-  int64_t pair_off = 0;
+  int64_t pair_off = 0, look_off = 0;
+  if (!h->use_seed && ((h->M > 0) != (h->x_look_bl != nullptr))) { set_error("uniforms were set for the other proposal (nested vs plain)"); return VCSMC_ERR_STATE; }
 
   for (int r = 0; r < N - 1; ++r) {
     const int n = N - r;
     const int cur = r & 1, prev = cur ^ 1;
     // uniforms of this rank event
-    const float* u_pair; const double *u_bl, *u_br, *u_res;
-    if (h->use_seed) {
+    const float* u_pair = nullptr; const double *u_bl = nullptr, *u_br = nullptr, *u_res = nullptr, *u_cat = nullptr;
+    const double *lk_bl = nullptr, *lk_br = nullptr;
+    if (h->M > 0) {
+      if (h->use_seed) {
+        int rc = launch_philox_step(h->seed, r, 0, K, 0, nullptr, nullptr, nullptr, h->p<double>(h->o_u_res), h->p<double>(h->o_u_cat), st);
+        if (rc) return rc;
+        u_res = h->p<double>(h->o_u_res); u_cat = h->p<double>(h->o_u_cat);
+      } else {
+        lk_bl = h->x_look_bl + look_off; lk_br = h->x_look_br + look_off;
+        look_off += (int64_t)(n * (n - 1) / 2) * h->M * K;
+        u_cat = h->x_cat + (int64_t)r * K; u_res = h->x_res + (int64_t)r * K;
+      }
+    } else if (h->use_seed) {
       int rc = launch_philox_step(h->seed, r, 0, K, n, h->p<float>(h->o_u_pair), h->p<double>(h->o_u_bl),
-                                  h->p<double>(h->o_u_br), h->p<double>(h->o_u_res), st);
+                                  h->p<double>(h->o_u_br), h->p<double>(h->o_u_res), nullptr, st);
       if (rc) return rc;
       u_pair = h->p<float>(h->o_u_pair); u_bl = h->p<double>(h->o_u_bl); u_br = h->p<double>(h->o_u_br); u_res = h->p<double>(h->o_u_res);
     } else {
@@ -858,11 +931,31 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
     a.t2 = h->p<double>(h->o_t2) + (int64_t)r * 2 * K;
     a.ll_tilde = h->p<double>(h->o_lltilde);
     a.lsrc = h->p<int32_t>(h->o_lsrc); a.rsrc = h->p<int32_t>(h->o_rsrc); a.dst = h->p<int32_t>(h->o_dst);
-    step_prepare_kernel<<<(unsigned)((K + kPrepWarps - 1) / kPrepWarps), kPrepWarps * 32, (size_t)kPrepWarps * n * sizeof(float), st>>>(a);
-    VCSMC_LAUNCH_CHECK("step_prepare_kernel");
+    int rc;
+    if (h->M > 0) {
+      // VNCSMC: inherit the ancestor's forest, score every (pair, sub-sample), draw one option per particle
+      int32_t* inh_ids = h->p<int32_t>(h->o_inh_ids);
+      int32_t* inh_cnt = h->p<int32_t>(h->o_inh_cnt);
+      int32_t* inh_slot = h->p<int32_t>(h->o_inh_slot);
+      rc = launch_nested_inherit(r, n, N, K, a.cdf, u_res, a.ids_old, a.cnt_old, a.slot_old, inh_ids, inh_cnt, inh_slot,
+                                 h->keep ? h->p<int32_t>(h->o_rows_all) + (int64_t)r * K * N : nullptr, a.LL_prev, a.anc, a.ll_tilde, st);
+      if (rc) return rc;
+      double* pot = h->p<double>(h->o_pot) + h->pot_off[r];
+      rc = launch_lookahead(r, n, N, h->M, h->jc, h->fwd_gc, S, K, inh_ids, inh_cnt, inh_slot, codes, S, pool, S, ell_node,
+                            h->p<double>(h->o_ldf), Q, pi, lam_l, lam_r, lk_bl, lk_br, h->seed, pot, st);
+      if (rc) return rc;
+      rc = launch_nested_choose(r, n, N, h->M, h->fwd_gc, K, pot, u_cat, lk_bl, lk_br, h->seed, lam_l, lam_r, inh_ids, inh_cnt,
+                                inh_slot, a.ids_new, a.cnt_new, a.slot_new, a.lref, a.rref, a.nleaf, a.rempos,
+                                h->p<int32_t>(h->o_choice) + (int64_t)r * K, a.b_l, a.b_r, a.t2, h->p<double>(h->o_qlog),
+                                a.lsrc, a.rsrc, a.dst, st);
+      if (rc) return rc;
+    } else {
+      step_prepare_kernel<<<(unsigned)((K + kPrepWarps - 1) / kPrepWarps), kPrepWarps * 32, (size_t)kPrepWarps * n * sizeof(float), st>>>(a);
+      VCSMC_LAUNCH_CHECK("step_prepare_kernel");
+    }
 
     double* P = h->p<double>(h->o_P) + (int64_t)r * K * 32;
-    int rc = launch_transition_fwd(Q, a.t2, 2 * K, h->jc, P, st);
+    rc = launch_transition_fwd(Q, a.t2, 2 * K, h->jc, P, st);
     if (rc) return rc;
 
     if (h->fwd_gc) {
@@ -907,6 +1000,7 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
     w.LL = h->p<double>(h->o_LL) + (int64_t)r * K;
     w.vminus = h->p<int32_t>(h->o_vminus);
     w.q = 1.0 / ((double)n * (double)(n - 1) / 2.0);
+    w.qlog = h->M > 0 ? h->p<double>(h->o_qlog) : nullptr;
     step_weights_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(w);
     VCSMC_LAUNCH_CHECK("step_weights_kernel");
 
@@ -953,6 +1047,23 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   // ---- which nodes are ever consumed as a child; child/adjoint slots of every event
   mark_consumed_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(h->p<int32_t>(h->o_lref), h->p<int32_t>(h->o_rref), E, N, h->p<int32_t>(h->o_consumed));
   VCSMC_LAUNCH_CHECK("mark_consumed_kernel");
+  std::vector<int64_t> n_act(N, 0);
+  if (h->M > 0) {
+    // VNCSMC: the look-ahead of every active particle reads (and sends adjoints to) ALL roots of its inherited forest
+    std::vector<int32_t> last_base(N, 0), last_flag(N, 0);
+    for (int r = 0; r < N - 1; ++r) {
+      rc = launch_nested_active(r, K, h->skip_zero, h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats), h->p<int32_t>(h->o_nact), st);
+      if (rc) return rc;
+      rc = launch_nested_mark_roots(N - r, N, K, h->p<int32_t>(h->o_nact), h->p<int32_t>(h->o_rows_all) + (int64_t)r * K * N, h->p<int32_t>(h->o_consumed), st);
+      if (rc) return rc;
+      rc = launch_exclusive_scan_i32(h->p<int32_t>(h->o_nact), h->p<int32_t>(h->o_nbase), K, h->p<char>(h->o_sort_temp), h->sort_temp, st);
+      if (rc) return rc;
+      VCSMC_CUDA(cudaMemcpyAsync(&last_base[r], h->p<int32_t>(h->o_nbase) + (K - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      VCSMC_CUDA(cudaMemcpyAsync(&last_flag[r], h->p<int32_t>(h->o_nact) + (K - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    VCSMC_CUDA(cudaStreamSynchronize(st));
+    for (int r = 0; r < N - 1; ++r) n_act[r] = (int64_t)last_base[r] + last_flag[r];
+  }
   const int32_t* slot_of = nullptr;
   if (!h->retain) {
     rc = launch_exclusive_scan_i32(h->p<int32_t>(h->o_consumed), h->p<int32_t>(h->o_cslot), E, h->p<char>(h->o_sort_temp), h->sort_temp, st);
@@ -983,6 +1094,11 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     a.dlam_l = dlam_l; a.dlam_r = dlam_r;
     bwd_coef_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(a);
     VCSMC_LAUNCH_CHECK("bwd_coef_kernel");
+    if (h->M > 0) {
+      rc = launch_nested_coef(r, N - r, N, h->M, K, grad_elbo, a.lw, a.stats, h->p<double>(h->o_pot) + h->pot_off[r],
+                              h->p<int32_t>(h->o_choice) + (int64_t)r * K, a.anc, a.Dacc_next, st);
+      if (rc) return rc;
+    }
     // the buffers just consumed become the accumulation targets of step r-2
     VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_childsum[cur]), 0, K * sizeof(double), st));
     VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_Dacc[cur]), 0, K * N * sizeof(double), st));
@@ -1068,6 +1184,51 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
       VCSMC_LAUNCH_CHECK("zero_consumed_kernel");
     }
     for (int r = N - 2; r >= 0; --r) {
+      if (h->M > 0 && n_act[r] > 0) {
+        // VNCSMC: every (active particle, pair, sub-sample) of this rank event as a virtual merge event
+        const int n = N - r;
+        const int64_t combos = (int64_t)(n * (n - 1) / 2) * h->M;
+        const int64_t V = n_act[r] * combos;
+        rc = launch_nested_active(r, K, h->skip_zero, h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats), h->p<int32_t>(h->o_nact), st);
+        if (rc) return rc;
+        rc = launch_exclusive_scan_i32(h->p<int32_t>(h->o_nact), h->p<int32_t>(h->o_nbase), K, h->p<char>(h->o_sort_temp), h->sort_temp, st);
+        if (rc) return rc;
+        const double *lk_bl = nullptr, *lk_br = nullptr;
+        if (!h->use_seed) {
+          int64_t off = 0;
+          for (int q = 0; q < r; ++q) off += (int64_t)((N - q) * (N - q - 1) / 2) * h->M * K;
+          lk_bl = h->x_look_bl + off; lk_br = h->x_look_br + off;
+        }
+        for (int64_t v0 = 0; v0 < V; v0 += h->v_batch) {
+          const int64_t Vb = (V - v0 < h->v_batch) ? V - v0 : h->v_batch;
+          rc = launch_nested_virtual(r, n, N, h->M, K, grad_elbo, h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats),
+                                     h->p<double>(h->o_pot) + h->pot_off[r], h->p<int32_t>(h->o_choice) + (int64_t)r * K,
+                                     h->p<int32_t>(h->o_nact), h->p<int32_t>(h->o_nbase), h->p<int32_t>(h->o_rows_all) + (int64_t)r * K * N,
+                                     slot_of, lk_bl, lk_br, h->seed, h->lam_l, h->lam_r, v0, v0 + Vb, h->p<int32_t>(h->o_v_lsrc),
+                                     h->p<int32_t>(h->o_v_rsrc), h->p<double>(h->o_v_coef), h->p<double>(h->o_v_t2), st);
+          if (rc) return rc;
+          rc = launch_transition_fwd(h->Q, h->p<double>(h->o_v_t2), 2 * Vb, h->jc, h->p<double>(h->o_v_P), st);
+          if (rc) return rc;
+          VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_v_dP), 0, 32 * Vb * sizeof(double), st));
+          VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_v_dpi), 0, 4 * Vb * sizeof(double), st));
+          rc = launch_sort_order(h->p<int32_t>(h->o_v_lsrc), h->p<int32_t>(h->o_v_rsrc), nullptr, Vb, E, h->p<uint64_t>(h->o_v_keys_in),
+                                 h->p<uint64_t>(h->o_v_keys_out), h->p<int32_t>(h->o_v_vals), h->p<int32_t>(h->o_v_order),
+                                 h->p<int32_t>(h->o_v_count), h->p<char>(h->o_v_temp), h->v_temp, st);
+          if (rc) return rc;
+          rc = launch_merge_bwd(codes_c, S, lpool, gpool, Sc, h->p<int32_t>(h->o_v_lsrc), h->p<int32_t>(h->o_v_rsrc), nullptr,
+                                h->p<int32_t>(h->o_v_order), nullptr, h->p<double>(h->o_v_P), h->pi, h->p<double>(h->o_v_coef), Vb, Vb, nc,
+                                h->jc, 1, h->p<double>(h->o_v_dP), h->p<double>(h->o_v_dpi), st);
+          if (rc) return rc;
+          rc = launch_transition_bwd(h->Q, h->p<double>(h->o_v_t2), h->p<double>(h->o_v_dP), 2 * Vb, h->jc, h->p<double>(h->o_v_dt),
+                                     h->jc ? nullptr : h->p<double>(h->o_v_dQ), st);
+          if (rc) return rc;
+          rc = launch_nested_reduce(r, Vb, h->jc, h->p<double>(h->o_v_dt), h->p<double>(h->o_v_dQ), h->p<double>(h->o_v_t2), h->lam_l,
+                                    h->lam_r, dlam_l, dlam_r, dQ, st);
+          if (rc) return rc;
+          column_sum_kernel<<<4, 256, 0, st>>>(h->p<double>(h->o_v_dpi), Vb, 4, 4, dpi);
+          VCSMC_LAUNCH_CHECK("column_sum_kernel");
+        }
+      }
       if (cnt_bwd[r] == 0) continue;
       h->prof_begin(2, st);
       rc = launch_merge_bwd(codes_c, S, lpool, gpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
@@ -1129,6 +1290,7 @@ void* vcsmc_sweep_output(vcsmc_sweep_t* h, const char* name) {
       {"ancestors", h->o_anc}, {"left_ref", h->o_lref}, {"right_ref", h->o_rref}, {"leaf_counts", h->o_nleaf},
       {"log_z", h->o_logz}, {"ess", h->o_ess}, {"status", h->o_status}, {"ell_node", h->o_ell_node},
       {"rem_positions", h->o_rempos}};
+  if (h->M > 0 && !strcmp(name, "choice")) return h->ws + h->o_choice;
   for (auto& t : tab)
     if (!strcmp(t.n, name)) return h->ws + t.off;
   if (h->keep && !strcmp(name, "node_coef")) return h->ws + h->o_cnew;

@@ -157,7 +157,8 @@ def philox_step_uniforms(seed: int, r: int, k0: int, K: int, n: int, device="cud
 _F64_OUT = {"elbo": (1,), "log_weights": None, "log_likelihood": None, "log_likelihood_tilde": "K",
             "log_likelihood_R": "K", "left_branches": None, "right_branches": None, "log_z": "N1", "ess": "N1",
             "node_coef": None}
-_I32_OUT = {"v_minus": "K", "ancestors": None, "left_ref": None, "right_ref": None, "leaf_counts": None, "status": (8,)}
+_I32_OUT = {"v_minus": "K", "ancestors": None, "left_ref": None, "right_ref": None, "leaf_counts": None, "status": (8,),
+            "choice": None}
 
 
 class Sweep:
@@ -170,11 +171,12 @@ class Sweep:
     """
 
     def __init__(self, n_taxa: int, n_sites: int, n_particles: int, jc: bool, keep_for_backward: bool = True,
-                 workspace_bytes: Optional[int] = None, device="cuda", mem_fraction: float = 0.85):
+                 workspace_bytes: Optional[int] = None, device="cuda", mem_fraction: float = 0.85, n_sub: int = 0):
         lib = _lib.load()
         self.N, self.S, self.K, self.jc, self.keep = int(n_taxa), int(n_sites), int(n_particles), bool(jc), bool(keep_for_backward)
         self.device = torch.device(device)
-        cfg = _lib.SweepConfig(self.N, self.S, self.K, int(self.jc), int(self.keep), 0)
+        self.M = int(n_sub)   # 0: VCSMC (vcsmc.py); M > 0: VNCSMC look-ahead with M sub-samples (vncsmc.py)
+        cfg = _lib.SweepConfig(self.N, self.S, self.K, int(self.jc), int(self.keep), 0, self.M, 0)
         sizes = _lib.SweepSizes()
         check(lib.vcsmc_sweep_query(C.byref(cfg), C.byref(sizes)))
         self.min_bytes, self.retain_bytes = int(sizes.min_bytes), int(sizes.retain_bytes)
@@ -210,6 +212,16 @@ class Sweep:
             raise ValueError("uniform arrays have the wrong size")
         self._uniforms = (u_pair, u_bl, u_br, u_res)
         check(self._lib.vcsmc_sweep_set_uniforms(self._h, _ptr(u_pair), _ptr(u_bl), _ptr(u_br), _ptr(u_res)))
+
+    def set_uniforms_nested(self, look_bl: torch.Tensor, look_br: torch.Tensor, cat: torch.Tensor, res: torch.Tensor) -> None:
+        """VNCSMC: look_bl/look_br flat ragged concat over r of [C(N-r,2), M*K]; cat/res [N-1,K] (all float64)."""
+        for t, nm in ((look_bl, "look_bl"), (look_br, "look_br"), (cat, "cat"), (res, "res")):
+            _chk(t, F64, nm)
+        need = self.K * self.M * sum((self.N - r) * (self.N - r - 1) // 2 for r in range(self.N - 1))
+        if look_bl.numel() != need or look_br.numel() != need or cat.numel() != (self.N - 1) * self.K:
+            raise ValueError("uniform arrays have the wrong size")
+        self._uniforms = (look_bl, look_br, cat, res)
+        check(self._lib.vcsmc_sweep_set_uniforms_nested(self._h, _ptr(look_bl), _ptr(look_br), _ptr(cat), _ptr(res)))
 
     def set_option(self, name: str, value: float) -> None:
         check(self._lib.vcsmc_sweep_set_option(self._h, name.encode(), float(value)))

@@ -53,9 +53,7 @@ def main(argv=None):
         dist.init_process_group("nccl")
     from .loader import load_dataset
     datadict = load_dataset(args.dataset, args.data_dir)
-    if args.nested:
-        raise NotImplementedError("--nested/--twisting (vncsmc.py look-ahead proposal) is not built yet in phylo_b200; "
-                                  "see DESIGN.md 'out of scope this round'")
+    # runner.py:197-206: --nested=true imports vncsmc (same class name); here one class with args.nested
     from . import vcsmc
     model = vcsmc.VCSMC(datadict, K=args.n_particles, args=args, seed=args.seed)
     return model.train(epochs=args.num_epoch, batch_size=args.batch_size, learning_rate=args.learning_rate,

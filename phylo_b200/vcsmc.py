@@ -56,6 +56,8 @@ class VCSMC:
             raise RuntimeError("phylo_b200 needs a CUDA device: there is no CPU fallback")
         self.device = torch.device(device or ("cuda:%d" % torch.cuda.current_device()))
         self.jcmodel = bool(getattr(args, "jcmodel", False))
+        # --nested=true selects the look-ahead proposal of vncsmc.py (same class name and signatures there)
+        self.nested = bool(getattr(args, "nested", False))
         branch_prior = float(getattr(args, "branch_prior", math.log(10.0)))
         # the reference's variables (vcsmc.py:119-124); exp()/softmax parameterisations are applied in _model()
         dev = self.device
@@ -112,7 +114,8 @@ class VCSMC:
         if key not in self._sweeps:
             if need_grad and (n_sites, False) in self._sweeps:
                 del self._sweeps[(n_sites, False)]
-            sw = ops.Sweep(self.N, n_sites, self.K, self.jcmodel, keep_for_backward=need_grad, device=self.device)
+            sw = ops.Sweep(self.N, n_sites, self.K, self.jcmodel, keep_for_backward=need_grad, device=self.device,
+                           n_sub=self.M if self.nested else 0)
             if self.world > 1:
                 import torch.distributed as dist
                 sw.set_allreduce(lambda t: dist.all_reduce(t))
