@@ -37,7 +37,7 @@ def test_arguments_are_validated_without_a_gpu():
     assert lib.vcsmc_sweep_query(C.byref(cfg), C.byref(sizes)) == 0
     full = 11 * 2048 * 898 * 32
     assert sizes.retain_bytes > 2 * full and sizes.min_bytes < sizes.retain_bytes
-    assert lib.vcsmc_merge_tiles(898) == 16 and lib.vcsmc_merge_tiles(10000) == 160
+    assert lib.vcsmc_merge_tiles(898) == 32 and lib.vcsmc_merge_tiles(10000) == 320   # upper bound of ell partials per particle
     with pytest.raises(_lib.VcsmcError):
         _lib.check(lib.vcsmc_transition_fwd(None, None, 4, 0, None, None))
 
