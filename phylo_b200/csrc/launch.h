@@ -62,11 +62,13 @@ int launch_nested_active(int r, int64_t K, int skip_zero, const double* lw, cons
 int launch_nested_mark_roots(int n, int N, int64_t K, const int32_t* active, const int32_t* rows, int32_t* consumed, cudaStream_t st);
 int launch_nested_coef(int r, int n, int N, int M, int64_t K, double grad, const double* lw, const double* stats,
                        const double* pot, const int32_t* choice, const int32_t* anc, double* Dacc_next, cudaStream_t st);
-int launch_nested_virtual(int r, int n, int N, int M, int64_t K, double grad, const double* lw, const double* stats,
-                          const double* pot, const int32_t* choice, const int32_t* active, const int32_t* base,
-                          const int32_t* rows, const int32_t* slot_of, const double* u_bl, const double* u_br, uint64_t seed,
-                          const double* lam_l, const double* lam_r, int64_t v0, int64_t v1, int32_t* v_lsrc, int32_t* v_rsrc,
-                          double* v_coef, double* v_t2, cudaStream_t st);
+int launch_nested_keep(int r, int n, int M, int64_t K, double grad, int dense, const double* lw, const double* stats,
+                       const double* pot, const int32_t* choice, int32_t* keep, cudaStream_t st);
+int launch_nested_virtual(int r, int n, int N, int M, int64_t K, double grad, int dense, const double* lw, const double* stats,
+                          const double* pot, const int32_t* choice, const int32_t* index, const int32_t* rows,
+                          const int32_t* slot_of, const double* u_bl, const double* u_br, uint64_t seed, const double* lam_l,
+                          const double* lam_r, int64_t v0, int64_t v1, int32_t* v_lsrc, int32_t* v_rsrc, double* v_coef,
+                          double* v_t2, cudaStream_t st);
 int launch_nested_reduce(int r, int64_t V, int jc, const double* dt, const double* dQ_each, const double* t2,
                          const double* lam_l, const double* lam_r, double* dlam_l, double* dlam_r, double* dQ,
                          cudaStream_t st);

@@ -198,6 +198,13 @@ __global__ void __launch_bounds__(kLookThreads) lookahead_kernel(const LookArgs 
           pr *= normal ? __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x)) : x;
           ex += normal ? e - 1023 : 0;
         }
+        // a thread multiplies up to 128 mantissas in [1,2) per tile: fold the product's exponent back once per tile
+        const int hi = __double2hiint(pr);
+        const int e = (hi >> 20) & 0x7ff;
+        if (e != 0 && e != 0x7ff && hi >= 0) {
+          pr = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(pr));
+          ex += e - 1023;
+        }
       }
     }
     double val = 0.0;
@@ -356,12 +363,12 @@ struct VirtArgs {
   int r, n, N, M;
   int64_t K;
   double grad;
+  int dense;               // 1: keep combinations whose adjoint is exactly zero too
   const double* lw;
   const double* stats;
   const double* pot;       // [K][combos] log-softmax
   const int32_t* choice;
-  const int32_t* active;   // [K] 0/1
-  const int32_t* base;     // [K] exclusive scan of active
+  const int32_t* index;    // [K*combos] exclusive scan of the keep flags
   const int32_t* rows;     // [K][N] inherited forest (node ids)
   const int32_t* slot_of;  // compact slot of a consumed node (or null: direct)
   const double* u_bl;
@@ -376,17 +383,35 @@ struct VirtArgs {
   double* v_t2;
 };
 
+__device__ __forceinline__ double kappa_of(const double* lw, const double* stats, const double* pot, const int32_t* choice,
+                                           int r, int64_t k, int combos, int c, double grad) {
+  const double W = exp(lw[k] - stats[r * 4]) * grad;
+  return W * (exp(pot[k * combos + c]) - (c == choice[k] ? 1.0 : 0.0));
+}
+
+// keep[k*combos + c] = 1 when the virtual event has to be visited (exact-zero adjoints are dropped unless dense)
+__global__ void nested_keep_kernel(int r, int n, int M, int64_t K, double grad, int dense, const double* __restrict__ lw,
+                                   const double* __restrict__ stats, const double* __restrict__ pot,
+                                   const int32_t* __restrict__ choice, int32_t* __restrict__ keep) {
+  const int combos = n * (n - 1) / 2 * M;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * combos) return;
+  const int64_t k = i / combos;
+  const int c = (int)(i - k * combos);
+  keep[i] = dense ? 1 : (kappa_of(lw, stats, pot, choice, r, k, combos, c, grad) != 0.0);
+}
+
 __global__ void nested_virtual_kernel(const VirtArgs a) {
   const int combos = a.n * (a.n - 1) / 2 * a.M;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.K * combos) return;
   const int64_t k = i / combos;
   const int c = (int)(i - k * combos);
-  if (k >= a.K || !a.active[k]) return;
-  const int64_t v = (int64_t)a.base[k] * combos + c;
+  const double kappa = kappa_of(a.lw, a.stats, a.pot, a.choice, a.r, k, combos, c, a.grad);
+  if (!a.dense && kappa == 0.0) return;
+  const int64_t v = a.index[i];
   if (v < a.v0 || v >= a.v1) return;
   const int64_t o = v - a.v0;
-  const double W = exp(a.lw[k] - a.stats[a.r * 4]) * a.grad;
-  const double kappa = W * (exp(a.pot[k * combos + c]) - (c == a.choice[k] ? 1.0 : 0.0));
   int r1, r2;
   pair_of(c / a.M, a.n, r1, r2);
   const int id1 = a.rows[k * a.N + r1], id2 = a.rows[k * a.N + r2];
@@ -537,12 +562,20 @@ int launch_nested_coef(int r, int n, int N, int M, int64_t K, double grad, const
   return VCSMC_OK;
 }
 
-int launch_nested_virtual(int r, int n, int N, int M, int64_t K, double grad, const double* lw, const double* stats,
-                          const double* pot, const int32_t* choice, const int32_t* active, const int32_t* base,
-                          const int32_t* rows, const int32_t* slot_of, const double* u_bl, const double* u_br, uint64_t seed,
-                          const double* lam_l, const double* lam_r, int64_t v0, int64_t v1, int32_t* v_lsrc, int32_t* v_rsrc,
-                          double* v_coef, double* v_t2, cudaStream_t st) {
-  VirtArgs a{r, n, N, M, K, grad, lw, stats, pot, choice, active, base, rows, slot_of, u_bl, u_br, seed, lam_l, lam_r,
+int launch_nested_keep(int r, int n, int M, int64_t K, double grad, int dense, const double* lw, const double* stats,
+                       const double* pot, const int32_t* choice, int32_t* keep, cudaStream_t st) {
+  const int64_t total = K * (int64_t)(n * (n - 1) / 2 * M);
+  nested_keep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r, n, M, K, grad, dense, lw, stats, pot, choice, keep);
+  VCSMC_LAUNCH_CHECK("nested_keep_kernel");
+  return VCSMC_OK;
+}
+
+int launch_nested_virtual(int r, int n, int N, int M, int64_t K, double grad, int dense, const double* lw, const double* stats,
+                          const double* pot, const int32_t* choice, const int32_t* index, const int32_t* rows,
+                          const int32_t* slot_of, const double* u_bl, const double* u_br, uint64_t seed, const double* lam_l,
+                          const double* lam_r, int64_t v0, int64_t v1, int32_t* v_lsrc, int32_t* v_rsrc, double* v_coef,
+                          double* v_t2, cudaStream_t st) {
+  VirtArgs a{r, n, N, M, K, grad, dense, lw, stats, pot, choice, index, rows, slot_of, u_bl, u_br, seed, lam_l, lam_r,
              v0, v1, v_lsrc, v_rsrc, v_coef, v_t2};
   const int64_t total = K * (int64_t)(n * (n - 1) / 2 * M);
   nested_virtual_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);

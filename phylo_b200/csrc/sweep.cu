@@ -516,7 +516,8 @@ struct vcsmc_sweep {
       o_suf_l, o_suf_r, o_gB_l, o_gB_r, o_cleaf, o_pool, o_keys_in, o_keys_out, o_vals_in, o_order, o_count,
       o_sort_temp, o_order_bwd, o_count_bwd, o_order_rec, o_count_rec, o_act_bwd, o_act_rec, o_cslot,
       o_inh_ids, o_inh_cnt, o_inh_slot, o_pot, o_choice, o_qlog, o_u_cat, o_rows_all, o_nact, o_nbase, o_v_lsrc, o_v_rsrc,
-      o_v_coef, o_v_t2, o_v_P, o_v_dP, o_v_dt, o_v_dQ, o_v_dpi, o_v_order, o_v_keys_in, o_v_keys_out, o_v_vals, o_v_count, o_v_temp;
+      o_v_coef, o_v_t2, o_v_P, o_v_dP, o_v_dt, o_v_dQ, o_v_dpi, o_v_order, o_v_keys_in, o_v_keys_out, o_v_vals, o_v_count, o_v_temp, o_v_keep, o_v_index, o_v_scan;
+  size_t v_scan = 0;
   std::vector<int64_t> pot_off;  // per rank event, offset (doubles) into the potentials
   int64_t v_batch = 0;           // virtual events per batch in the nested reverse sweep
   size_t v_temp = 0;
@@ -706,6 +707,10 @@ int64_t plan(vcsmc_sweep* h) {
       h->o_v_count = L.take<int32_t>(4);
       h->v_temp = sort_temp_bytes(V);
       h->o_v_temp = L.take<char>((int64_t)h->v_temp + 256);
+      h->o_v_keep = L.take<int32_t>(all + 1);
+      h->o_v_index = L.take<int32_t>(all + 1);
+      h->v_scan = scan_temp_bytes(all);
+      h->o_v_scan = L.take<char>((int64_t)h->v_scan + 256);
     }
   }
   return L.off;
@@ -1052,17 +1057,22 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     // VNCSMC: the look-ahead of every active particle reads (and sends adjoints to) ALL roots of its inherited forest
     std::vector<int32_t> last_base(N, 0), last_flag(N, 0);
     for (int r = 0; r < N - 1; ++r) {
+      const int n = N - r;
+      const int64_t tot = K * (int64_t)(n * (n - 1) / 2) * h->M;
       rc = launch_nested_active(r, K, h->skip_zero, h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats), h->p<int32_t>(h->o_nact), st);
       if (rc) return rc;
-      rc = launch_nested_mark_roots(N - r, N, K, h->p<int32_t>(h->o_nact), h->p<int32_t>(h->o_rows_all) + (int64_t)r * K * N, h->p<int32_t>(h->o_consumed), st);
+      rc = launch_nested_mark_roots(n, N, K, h->p<int32_t>(h->o_nact), h->p<int32_t>(h->o_rows_all) + (int64_t)r * K * N, h->p<int32_t>(h->o_consumed), st);
       if (rc) return rc;
-      rc = launch_exclusive_scan_i32(h->p<int32_t>(h->o_nact), h->p<int32_t>(h->o_nbase), K, h->p<char>(h->o_sort_temp), h->sort_temp, st);
+      rc = launch_nested_keep(r, n, h->M, K, grad_elbo, !h->skip_zero, h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats),
+                              h->p<double>(h->o_pot) + h->pot_off[r], h->p<int32_t>(h->o_choice) + (int64_t)r * K, h->p<int32_t>(h->o_v_keep), st);
       if (rc) return rc;
-      VCSMC_CUDA(cudaMemcpyAsync(&last_base[r], h->p<int32_t>(h->o_nbase) + (K - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-      VCSMC_CUDA(cudaMemcpyAsync(&last_flag[r], h->p<int32_t>(h->o_nact) + (K - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      rc = launch_exclusive_scan_i32(h->p<int32_t>(h->o_v_keep), h->p<int32_t>(h->o_v_index), tot, h->p<char>(h->o_v_scan), h->v_scan, st);
+      if (rc) return rc;
+      VCSMC_CUDA(cudaMemcpyAsync(&last_base[r], h->p<int32_t>(h->o_v_index) + (tot - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      VCSMC_CUDA(cudaMemcpyAsync(&last_flag[r], h->p<int32_t>(h->o_v_keep) + (tot - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     }
     VCSMC_CUDA(cudaStreamSynchronize(st));
-    for (int r = 0; r < N - 1; ++r) n_act[r] = (int64_t)last_base[r] + last_flag[r];
+    for (int r = 0; r < N - 1; ++r) n_act[r] = (int64_t)last_base[r] + last_flag[r];   // virtual events to visit
   }
   const int32_t* slot_of = nullptr;
   if (!h->retain) {
@@ -1187,11 +1197,12 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
       if (h->M > 0 && n_act[r] > 0) {
         // VNCSMC: every (active particle, pair, sub-sample) of this rank event as a virtual merge event
         const int n = N - r;
-        const int64_t combos = (int64_t)(n * (n - 1) / 2) * h->M;
-        const int64_t V = n_act[r] * combos;
-        rc = launch_nested_active(r, K, h->skip_zero, h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats), h->p<int32_t>(h->o_nact), st);
+        const int64_t tot = K * (int64_t)(n * (n - 1) / 2) * h->M;
+        const int64_t V = n_act[r];
+        rc = launch_nested_keep(r, n, h->M, K, grad_elbo, !h->skip_zero, h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats),
+                                h->p<double>(h->o_pot) + h->pot_off[r], h->p<int32_t>(h->o_choice) + (int64_t)r * K, h->p<int32_t>(h->o_v_keep), st);
         if (rc) return rc;
-        rc = launch_exclusive_scan_i32(h->p<int32_t>(h->o_nact), h->p<int32_t>(h->o_nbase), K, h->p<char>(h->o_sort_temp), h->sort_temp, st);
+        rc = launch_exclusive_scan_i32(h->p<int32_t>(h->o_v_keep), h->p<int32_t>(h->o_v_index), tot, h->p<char>(h->o_v_scan), h->v_scan, st);
         if (rc) return rc;
         const double *lk_bl = nullptr, *lk_br = nullptr;
         if (!h->use_seed) {
@@ -1201,9 +1212,9 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
         }
         for (int64_t v0 = 0; v0 < V; v0 += h->v_batch) {
           const int64_t Vb = (V - v0 < h->v_batch) ? V - v0 : h->v_batch;
-          rc = launch_nested_virtual(r, n, N, h->M, K, grad_elbo, h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats),
+          rc = launch_nested_virtual(r, n, N, h->M, K, grad_elbo, !h->skip_zero, h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats),
                                      h->p<double>(h->o_pot) + h->pot_off[r], h->p<int32_t>(h->o_choice) + (int64_t)r * K,
-                                     h->p<int32_t>(h->o_nact), h->p<int32_t>(h->o_nbase), h->p<int32_t>(h->o_rows_all) + (int64_t)r * K * N,
+                                     h->p<int32_t>(h->o_v_index), h->p<int32_t>(h->o_rows_all) + (int64_t)r * K * N,
                                      slot_of, lk_bl, lk_br, h->seed, h->lam_l, h->lam_r, v0, v0 + Vb, h->p<int32_t>(h->o_v_lsrc),
                                      h->p<int32_t>(h->o_v_rsrc), h->p<double>(h->o_v_coef), h->p<double>(h->o_v_t2), st);
           if (rc) return rc;

@@ -1,4 +1,4 @@
-"""Quick device-side timing of one sweep shape (not the bench): python scripts/perf_probe.py N S K jc [dense] [ws_gb]"""
+"""Quick device-side timing of one sweep shape (not the bench): python scripts/perf_probe.py N S K jc [dense|skip] [ws_gb|0] [M]"""
 import sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
@@ -7,7 +7,8 @@ from phylo_b200.loader import synthetic_alignment
 
 N, S, K, jc = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), bool(int(sys.argv[4]))
 dense = len(sys.argv) > 5 and sys.argv[5] == "dense"
-ws_gb = float(sys.argv[6]) if len(sys.argv) > 6 else None
+ws_gb = float(sys.argv[6]) if len(sys.argv) > 6 and float(sys.argv[6]) > 0 else None
+M = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 g = synthetic_alignment(N, S)["genome"]
 codes = ops.pack_alignment(torch.from_numpy(g).cuda())
 lam = torch.full((N - 1,), 10.0, dtype=torch.float64, device="cuda")
@@ -15,7 +16,10 @@ off = 1 - torch.eye(4, dtype=torch.float64, device="cuda")
 Q = (off / 3 - torch.eye(4, dtype=torch.float64, device="cuda")).contiguous()
 pi = torch.full((4,), 0.25, dtype=torch.float64, device="cuda")
 t0 = time.time()
-sw = ops.Sweep(N, S, K, jc, workspace_bytes=None if ws_gb is None else int(ws_gb * 2**30))
+sw = ops.Sweep(N, S, K, jc, workspace_bytes=None if ws_gb is None else int(ws_gb * 2**30), n_sub=M)
+if M:
+    look = K * S * M * sum((N - r) * (N - r - 1) // 2 for r in range(N - 1))
+    print("look-ahead merges per sweep: %.3e (+ %.3e main)" % (look, K * S * (N - 1)), flush=True)
 print("workspace GB %.2f retained=%s min GB %.2f retain GB %.2f" % (sw.workspace.numel() / 2**30, sw.retained, sw.min_bytes / 2**30, sw.retain_bytes / 2**30), flush=True)
 sw.set_seed(0)
 sw.set_option("skip_zero", 0.0 if dense else 1.0)
