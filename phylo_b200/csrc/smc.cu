@@ -48,9 +48,15 @@ __global__ void __launch_bounds__(kCdfThreads) resample_cdf_kernel(const double*
   const int64_t seg = ((K + NW - 1) / NW + 31) / 32 * 32;
   const int64_t b = min((int64_t)wid * seg, K), e = min(b + seg, K);
 
-  // max
+  // max  (4 independent loads in flight per lane: a single CTA is latency-bound, not bandwidth-bound)
   double m = -INFINITY;
-  for (int64_t i = b + lane; i < e; i += 32) m = fmax(m, lw[i]);
+  for (int64_t i0 = b + lane; i0 < e; i0 += 128) {
+    double v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = (i0 + 32 * q < e) ? lw[i0 + 32 * q] : -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) m = fmax(m, v[q]);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
   if (lane == 0) sm[wid] = m;
@@ -65,7 +71,13 @@ __global__ void __launch_bounds__(kCdfThreads) resample_cdf_kernel(const double*
 
   // logsumexp (fixed order: lane-strided partial sums, shuffle tree, then warps in order)
   double s = 0.0;
-  for (int64_t i = b + lane; i < e; i += 32) s += exp(lw[i] - M);
+  for (int64_t i0 = b + lane; i0 < e; i0 += 128) {
+    double v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = (i0 + 32 * q < e) ? lw[i0 + 32 * q] : -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s += exp(v[q] - M);   // exp(-inf) = 0 for the padding
+  }
   s = warp_sum(s);
   __syncthreads();
   if (lane == 0) sm[wid] = s;
@@ -81,10 +93,16 @@ __global__ void __launch_bounds__(kCdfThreads) resample_cdf_kernel(const double*
 
   // segment totals of w = exp(logit - max) and of w^2
   double run = 0.0, sq = 0.0;
-  for (int64_t i = b + lane; i < e; i += 32) {
-    const double w = exp((lw[i] - lse) - mlog);
-    run += w;
-    sq = fma(w, w, sq);
+  for (int64_t i0 = b + lane; i0 < e; i0 += 128) {
+    double v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = (i0 + 32 * q < e) ? lw[i0 + 32 * q] : -INFINITY;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double w = exp((v[q] - lse) - mlog);
+      run += w;
+      sq = fma(w, w, sq);
+    }
   }
   run = warp_sum(run);
   sq = warp_sum(sq);
@@ -110,16 +128,25 @@ __global__ void __launch_bounds__(kCdfThreads) resample_cdf_kernel(const double*
   __syncthreads();
   // running sum inside the segment
   double carry = sm[wid];
-  for (int64_t i0 = b; i0 < e; i0 += 32) {
-    const int64_t i = i0 + lane;
-    double w = i < e ? exp((lw[i] - lse) - mlog) : 0.0;
+  for (int64_t i0 = b; i0 < e; i0 += 128) {
+    double v[4];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double t = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += t;
+    for (int q = 0; q < 4; ++q) {
+      const int64_t i = i0 + 32 * q + lane;
+      v[q] = i < e ? exp((lw[i] - lse) - mlog) : 0.0;
     }
-    if (i < e) cdf[i] = carry + w;
-    carry += __shfl_sync(0xffffffffu, w, 31);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t i = i0 + 32 * q + lane;
+      double w = v[q];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      if (i < e) cdf[i] = carry + w;
+      carry += __shfl_sync(0xffffffffu, w, 31);
+    }
   }
 }
 

@@ -179,7 +179,13 @@ __global__ void __launch_bounds__(1024) gc_alloc_kernel(const int32_t* __restric
   const int64_t seg = ((P + 31) / 32 + 31) / 32 * 32;  // per-warp segment length, multiple of 32
   const int64_t b = min((int64_t)wid * seg, P), e = min(b + seg, P);
   int cnt = 0;
-  for (int64_t i = b + lane; i < e; i += 32) cnt += flags[i] == 0;
+  for (int64_t i0 = b + lane; i0 < e; i0 += 128) {
+    int f[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f[q] = (i0 + 32 * q < e) ? flags[i0 + 32 * q] : 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cnt += f[q] == 0;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
   if (lane == 0) warp_off[wid + 1] = cnt;
@@ -201,16 +207,22 @@ __global__ void __launch_bounds__(1024) gc_alloc_kernel(const int32_t* __restric
   }
   __syncthreads();
   int64_t j = warp_off[wid];
-  for (int64_t i0 = b; i0 < e && j < K; i0 += 32) {
-    const int64_t i = i0 + lane;
-    const bool is_free = i < e && flags[i] == 0;
-    const unsigned m = __ballot_sync(0xffffffffu, is_free);
-    const int64_t mine = j + __popc(m & ((1u << lane) - 1));
-    if (is_free && mine < K) {
-      dst[mine] = (int32_t)i;
-      slot_new[mine * N + (n - 2)] = (int32_t)i;
+  for (int64_t i0 = b; i0 < e && j < K; i0 += 128) {
+    int f[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f[q] = (i0 + 32 * q + lane < e) ? flags[i0 + 32 * q + lane] : 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t i = i0 + 32 * q + lane;
+      const bool is_free = f[q] == 0;
+      const unsigned m = __ballot_sync(0xffffffffu, is_free);
+      const int64_t mine = j + __popc(m & ((1u << lane) - 1));
+      if (is_free && mine < K) {
+        dst[mine] = (int32_t)i;
+        slot_new[mine * N + (n - 2)] = (int32_t)i;
+      }
+      j += __popc(m);
     }
-    j += __popc(m);
   }
 }
 
@@ -403,7 +415,7 @@ __global__ void bwd_active_kernel(const double* __restrict__ cnew, const int32_t
   if (k >= K) return;
   const int c = consumed[k];
   act_rec[k] = c;
-  act_bwd[k] = !(skip_zero && cnew[k] == 0.0 && !c);
+  act_bwd[k] = c || !(skip_zero && cnew[k] == 0.0);  // one visiting order serves the recompute and the reverse sweep
 }
 
 // zero the adjoint slots of the consumed nodes of one rank event (the first *count entries of `order`)
@@ -416,7 +428,10 @@ __global__ void zero_consumed_kernel(const int32_t* __restrict__ order, const in
   d4 z;
 #pragma unroll
   for (int j = 0; j < 4; ++j) z.v[j] = 0.0;
-  for (int j = blockIdx.y; j < n; j += gridDim.y) st_site(gpool + ((int64_t)gsrc[order[j]] * slot_sites + s) * 4, z);
+  for (int j = blockIdx.y; j < n; j += gridDim.y) {
+    const int g = gsrc[order[j]];
+    if (g >= 0) st_site(gpool + ((int64_t)g * slot_sites + s) * 4, z);
+  }
 }
 
 // db -> dlam through b = -log(U)/lam, and accumulation of the per-matrix dQ (vcsmc.py:353-358 reversed)
@@ -1131,16 +1146,13 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     rc = launch_sort_order(bl, br, h->p<int32_t>(h->o_act_bwd), K, E, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out), h->p<int32_t>(h->o_vals_in),
                            h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r, h->p<char>(h->o_sort_temp), h->sort_temp, st);
     if (rc) return rc;
-    rc = launch_sort_order(bl, br, h->p<int32_t>(h->o_act_rec), K, E, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out), h->p<int32_t>(h->o_vals_in),
-                           h->p<int32_t>(h->o_order_rec) + (int64_t)r * K, h->p<int32_t>(h->o_count_rec) + r, h->p<char>(h->o_sort_temp), h->sort_temp, st);
-    if (rc) return rc;
   }
 
   // one small D2H + sync: the host learns how many particles each rank event really has to visit, so that empty
   // launches are skipped and grids are sized exactly (with ESS ~ 1 almost every reverse event is empty)
   std::vector<int32_t> cnt_bwd(N, 0), cnt_rec(N, 0);
   VCSMC_CUDA(cudaMemcpyAsync(cnt_bwd.data(), h->p<int32_t>(h->o_count_bwd), (N - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  VCSMC_CUDA(cudaMemcpyAsync(cnt_rec.data(), h->p<int32_t>(h->o_count_rec), (N - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  VCSMC_CUDA(cudaMemcpyAsync(cnt_rec.data(), h->p<int32_t>(h->o_count_bwd), (N - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   VCSMC_CUDA(cudaStreamSynchronize(st));
   {
     int64_t visited = 0;
@@ -1158,8 +1170,11 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     gpool = lpool + E * (int64_t)S * 4;
   } else {
     // only nodes that a later merge consumes are materialised: the chunk is as long as their count allows
-    int64_t n_cons = 0;
-    for (int r = 0; r < N - 1; ++r) n_cons += cnt_rec[r];
+    int32_t last_slot = 0, last_flag = 0;  // number of consumed nodes = exclusive scan's last entry + last flag
+    VCSMC_CUDA(cudaMemcpyAsync(&last_slot, h->p<int32_t>(h->o_cslot) + (E - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    VCSMC_CUDA(cudaMemcpyAsync(&last_flag, h->p<int32_t>(h->o_consumed) + (E - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    VCSMC_CUDA(cudaStreamSynchronize(st));
+    int64_t n_cons = (int64_t)last_slot + last_flag;
     if (n_cons < 1) n_cons = 1;
     int64_t sc = (h->pool_bytes / 2) / (n_cons * 32);
     if (h->max_chunk_sites > 0 && sc > h->max_chunk_sites) sc = h->max_chunk_sites;
@@ -1179,7 +1194,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
         if (cnt_rec[r] == 0) continue;
         h->prof_begin(1, st);
         rc = launch_merge_fwd(codes_c, S, lpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
-                              h->p<int32_t>(h->o_bdst) + (int64_t)r * K, h->p<int32_t>(h->o_order_rec) + (int64_t)r * K, h->p<int32_t>(h->o_count_rec) + r,
+                              h->p<int32_t>(h->o_bdst) + (int64_t)r * K, h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r,
                               h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, K, cnt_rec[r], nc, h->jc, 1, h->p<double>(h->o_ell_part), nullptr, st);
         h->prof_end(st);
         if (rc) return rc;
@@ -1189,7 +1204,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     for (int r = 0; r < N - 1; ++r) {
       if (cnt_rec[r] == 0) continue;
       dim3 grid((nc + 255) / 256, cnt_rec[r] < 32 ? cnt_rec[r] : 32, 1);
-      zero_consumed_kernel<<<grid, 256, 0, st>>>(h->p<int32_t>(h->o_order_rec) + (int64_t)r * K, h->p<int32_t>(h->o_count_rec) + r,
+      zero_consumed_kernel<<<grid, 256, 0, st>>>(h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r,
                                                  h->p<int32_t>(h->o_bsrc_g) + (int64_t)r * K, Sc, nc, gpool);
       VCSMC_LAUNCH_CHECK("zero_consumed_kernel");
     }
