@@ -81,7 +81,7 @@ int vcsmc_transition_bwd(const double* Q, const double* t, const double* dP, int
  *     bwd (reverse pruning, the per-site part of TF autodiff through the while-loop):
  *        given coef[k] = dELBO/d ell[k] and (optionally) the adjoint G_new of the new node,
  *        accumulates the children's adjoints into gpool (atomic, same slot numbering as pool),
- *        dP[k][32] += per-particle 4x4 adjoints, dpi_each[k][4] += adjoint of pi.
+ *        dP[k][32] += per-particle 4x4 adjoints, dpi[4] += adjoint of pi (summed over all particles).
  *     jc != 0 selects the JC-specialised kernels: P must be the JC closed form (only P[0], P[1] of each
  *     matrix are read) and dP is COMPRESSED: dP[k][0] += sum_i dP_l[i][i], dP[k][1] += sum_{i!=j} dP_l[i][j],
  *     dP[k][16], dP[k][17] likewise for the right child -- the layout vcsmc_transition_bwd(jc=1) consumes.
@@ -93,7 +93,7 @@ int vcsmc_merge_fwd(const uint8_t* codes, int64_t codes_stride, double* pool, in
 int vcsmc_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* pool, double* gpool,
                     int64_t slot_sites, const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc,
                     const double* P, const double* pi, const double* coef, int64_t K, int n_sites, int jc,
-                    double* dP, double* dpi_each, void* stream);
+                    double* dP, double* dpi, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (d) proposal + resampling.

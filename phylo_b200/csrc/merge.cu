@@ -308,7 +308,7 @@ struct BwdArgs {
   int n_chunks;
   int R;
   double* dP;        // [K][32]
-  double* dpi_each;  // [K][4] or null
+  double* dpi_acc;   // [4] accumulated over all particles, or null
   int skip_zero;
 };
 
@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(kTileThreads, JC ? 2 : 1) merge_bwd_kernel(con
 #pragma unroll
   for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
 
+  double dpi[4] = {0.0, 0.0, 0.0, 0.0};  // d/dpi is a sum over ALL particles: reduced once per CTA, not per particle
   for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
     const int64_t g = w / a.n_chunks;
     const int tc = (int)(w - g * a.n_chunks);
@@ -389,7 +390,6 @@ __global__ void __launch_bounds__(kTileThreads, JC ? 2 : 1) merge_bwd_kernel(con
       const bool sw = kk < 0;
       const int64_t k = sw ? ~kk : kk;
 
-      double dpi[4] = {0.0, 0.0, 0.0, 0.0};
       double acc[JC ? 4 : 32];
 #pragma unroll
       for (int i = 0; i < (JC ? 4 : 32); ++i) acc[i] = 0.0;
@@ -466,24 +466,25 @@ __global__ void __launch_bounds__(kTileThreads, JC ? 2 : 1) merge_bwd_kernel(con
         warp_transpose_sum32(v32, lane);
         atomicAdd(a.dP + k * 32 + (lane ^ (sw ? 16 : 0)), v32[0]);
       }
-      if (a.dpi_each) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dpi[i] = warp_sum(dpi[i]);
-        if (lane == 0) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) atomicAdd(a.dpi_each + k * 4 + i, dpi[i]);
-        }
-      }
     }
     flush_adjoint<SPT>(pa, a.gpool, a.slot_sites, sbase, a.n_sites, Ga);
     flush_adjoint<SPT>(pb, a.gpool, a.slot_sites, sbase, a.n_sites, Gb);
+    }
+  }
+  if (a.dpi_acc) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dpi[i] = warp_sum(dpi[i]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (dpi[i] != 0.0) atomicAdd(a.dpi_acc + i, dpi[i]);
     }
   }
 }
 
 constexpr int kSptFwd = 2;
 constexpr int kSptBwdJC = 2;
-constexpr int kSptBwdGeneral = 1;
+constexpr int kSptBwdGeneral = 2;  // measured at 64x10kx65,536 dense: 1078 ms (SPT 2) vs 1278 ms (SPT 1)
 
 constexpr int64_t kTargetItems = 148 * 16;  // work items wanted per launch (persistent grid cap)
 
@@ -576,20 +577,27 @@ int launch_ell_reduce(const double* ell_part, int n_part, int64_t K, double* ell
 int launch_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* pool, double* gpool, int64_t slot_sites,
                      const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc, const int32_t* order,
                      const int32_t* count, const double* P, const double* pi, const double* coef, int64_t K,
-                     int64_t n_active, int n_sites, int jc, int skip_zero, double* dP, double* dpi_each, cudaStream_t st) {
+                     int64_t n_active, int n_sites, int jc, int skip_zero, double* dP, double* dpi_acc, cudaStream_t st) {
   if (K <= 0 || n_sites <= 0 || n_active == 0) return VCSMC_OK;
   const int64_t Kw = n_active > 0 ? n_active : K;
   BwdArgs a;
   a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.gpool = gpool; a.slot_sites = slot_sites;
   a.lsrc = lsrc; a.rsrc = rsrc; a.gsrc = gsrc; a.order = order; a.count = count; a.P = P; a.pi = pi;
-  a.coef = coef; a.K = K; a.n_sites = n_sites; a.dP = dP; a.dpi_each = dpi_each; a.skip_zero = skip_zero;
-  const int spt = jc ? kSptBwdJC : kSptBwdGeneral;
+  a.coef = coef; a.K = K; a.n_sites = n_sites; a.dP = dP; a.dpi_acc = dpi_acc; a.skip_zero = skip_zero;
+  static int gspt = -1;  // tuning knob (debug): VCSMC_BWD_SPT = 1 | 2 sites per thread in the general-Q reverse merge
+  if (gspt < 0) {
+    const char* e = getenv("VCSMC_BWD_SPT");
+    gspt = e ? atoi(e) : kSptBwdGeneral;
+    if (gspt != 1 && gspt != 2) gspt = kSptBwdGeneral;
+  }
+  const int spt = jc ? kSptBwdJC : gspt;
   a.tiles = (n_sites + kTileThreads * spt - 1) / (kTileThreads * spt);
   a.R = pick_group(Kw, a.tiles);
   pick_chunks(Kw, a.R, a.tiles, &a.tiles_per_item, &a.n_chunks);
   const unsigned grid = pick_grid(Kw, a.R, a.n_chunks);
   if (jc) merge_bwd_kernel<true, kSptBwdJC><<<grid, kTileThreads, 0, st>>>(a);
-  else merge_bwd_kernel<false, kSptBwdGeneral><<<grid, kTileThreads, 0, st>>>(a);
+  else if (spt == 2) merge_bwd_kernel<false, 2><<<grid, kTileThreads, 0, st>>>(a);
+  else merge_bwd_kernel<false, 1><<<grid, kTileThreads, 0, st>>>(a);
   VCSMC_LAUNCH_CHECK("merge_bwd_kernel");
   return VCSMC_OK;
 }

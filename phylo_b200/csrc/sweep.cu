@@ -1058,7 +1058,6 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_Dacc[1]), 0, K * N * sizeof(double), st));
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_consumed), 0, E * sizeof(int32_t), st));
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_dP), 0, 32 * E * sizeof(double), st));
-  VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_dpi_each), 0, 4 * K * sizeof(double), st));
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_dQ_acc), 0, 16 * K * sizeof(double), st));
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_suf_l), 0, K * sizeof(double), st));
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_suf_r), 0, K * sizeof(double), st));
@@ -1236,14 +1235,13 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
           rc = launch_transition_fwd(h->Q, h->p<double>(h->o_v_t2), 2 * Vb, h->jc, h->p<double>(h->o_v_P), st);
           if (rc) return rc;
           VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_v_dP), 0, 32 * Vb * sizeof(double), st));
-          VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_v_dpi), 0, 4 * Vb * sizeof(double), st));
           rc = launch_sort_order(h->p<int32_t>(h->o_v_lsrc), h->p<int32_t>(h->o_v_rsrc), nullptr, Vb, E, h->p<uint64_t>(h->o_v_keys_in),
                                  h->p<uint64_t>(h->o_v_keys_out), h->p<int32_t>(h->o_v_vals), h->p<int32_t>(h->o_v_order),
                                  h->p<int32_t>(h->o_v_count), h->p<char>(h->o_v_temp), h->v_temp, st);
           if (rc) return rc;
           rc = launch_merge_bwd(codes_c, S, lpool, gpool, Sc, h->p<int32_t>(h->o_v_lsrc), h->p<int32_t>(h->o_v_rsrc), nullptr,
                                 h->p<int32_t>(h->o_v_order), nullptr, h->p<double>(h->o_v_P), h->pi, h->p<double>(h->o_v_coef), Vb, Vb, nc,
-                                h->jc, 1, h->p<double>(h->o_v_dP), h->p<double>(h->o_v_dpi), st);
+                                h->jc, 1, h->p<double>(h->o_v_dP), dpi, st);
           if (rc) return rc;
           rc = launch_transition_bwd(h->Q, h->p<double>(h->o_v_t2), h->p<double>(h->o_v_dP), 2 * Vb, h->jc, h->p<double>(h->o_v_dt),
                                      h->jc ? nullptr : h->p<double>(h->o_v_dQ), st);
@@ -1251,8 +1249,6 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
           rc = launch_nested_reduce(r, Vb, h->jc, h->p<double>(h->o_v_dt), h->p<double>(h->o_v_dQ), h->p<double>(h->o_v_t2), h->lam_l,
                                     h->lam_r, dlam_l, dlam_r, dQ, st);
           if (rc) return rc;
-          column_sum_kernel<<<4, 256, 0, st>>>(h->p<double>(h->o_v_dpi), Vb, 4, 4, dpi);
-          VCSMC_LAUNCH_CHECK("column_sum_kernel");
         }
       }
       if (cnt_bwd[r] == 0) continue;
@@ -1260,7 +1256,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
       rc = launch_merge_bwd(codes_c, S, lpool, gpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
                             h->p<int32_t>(h->o_bsrc_g) + (int64_t)r * K, h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r,
                             h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, h->p<double>(h->o_cnew) + (int64_t)r * K, K, cnt_bwd[r], nc, h->jc, h->skip_zero,
-                            h->p<double>(h->o_dP) + (int64_t)r * K * 32, h->p<double>(h->o_dpi_each), st);
+                            h->p<double>(h->o_dP) + (int64_t)r * K * 32, dpi, st);
       h->prof_end(st);
       if (rc) return rc;
     }
@@ -1286,8 +1282,6 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     column_sum_kernel<<<16, 256, 0, st>>>(h->p<double>(h->o_dQ_acc), K, 16, 16, dQ);
     VCSMC_LAUNCH_CHECK("column_sum_kernel");
   }
-  column_sum_kernel<<<4, 256, 0, st>>>(h->p<double>(h->o_dpi_each), K, 4, 4, dpi);
-  VCSMC_LAUNCH_CHECK("column_sum_kernel");
   return VCSMC_OK;
 }
 

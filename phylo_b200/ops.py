@@ -109,13 +109,13 @@ def merge_fwd(codes: Optional[torch.Tensor], pool: torch.Tensor, lsrc: torch.Ten
 
 
 def merge_bwd(codes: Optional[torch.Tensor], pool: torch.Tensor, gpool: torch.Tensor, lsrc, rsrc, gsrc, P, pi, coef,
-              n_sites: int, jc: bool, dP: torch.Tensor, dpi_each: Optional[torch.Tensor]) -> None:
-    """Accumulates into gpool, dP [K,32], dpi_each [K,4]."""
+              n_sites: int, jc: bool, dP: torch.Tensor, dpi: Optional[torch.Tensor]) -> None:
+    """Accumulates into gpool, dP [K,32], dpi [4] (summed over particles)."""
     K = lsrc.numel()
     stride = codes.shape[1] if codes is not None else 0
     check(_lib.load().vcsmc_merge_bwd(_ptr(codes), stride, _ptr(pool), _ptr(gpool), pool.shape[1], _ptr(lsrc), _ptr(rsrc),
                                       _ptr(gsrc), _ptr(P), _ptr(pi), _ptr(coef), K, n_sites, int(jc), _ptr(dP),
-                                      _ptr(dpi_each), _stream()))
+                                      _ptr(dpi), _stream()))
 
 
 # ------------------------------------------------------------------------------------------
@@ -421,9 +421,9 @@ def _register():
         P = torch.cat([P_l.reshape(K, 16), P_r.reshape(K, 16)], dim=1).contiguous()
         coef = (g_ell if g_ell is not None else torch.zeros(K, dtype=F64, device=dev)).contiguous()
         dP = torch.zeros((K, 32), dtype=F64, device=dev)
-        dpi = torch.zeros((K, 4), dtype=F64, device=dev)
+        dpi = torch.zeros(4, dtype=F64, device=dev)
         merge_bwd(None, pool, gpool, ar, ar + K, ar + 2 * K, P, pi.contiguous(), coef, S, False, dP, dpi)
-        return gpool[:K], gpool[K:2 * K], dP[:, :16].reshape(K, 4, 4), dP[:, 16:].reshape(K, 4, 4), dpi.sum(dim=0)
+        return gpool[:K], gpool[K:2 * K], dP[:, :16].reshape(K, 4, 4), dP[:, 16:].reshape(K, 4, 4), dpi
 
     merge.register_autograd(_merge_bwd, setup_context=_merge_setup)
 
