@@ -47,6 +47,7 @@ def parse():
     p.add_argument("--particles", type=int, default=65536)
     p.add_argument("--model", default="gtr", choices=["gtr", "jc"])
     p.add_argument("--dense", action="store_true", help="reverse sweep without zero-adjoint skipping")
+    p.add_argument("--nested", type=int, default=0, help="M > 0: VNCSMC look-ahead proposal with M sub-samples (config 4)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample", default="64x1000x32", help="taxa x sites x particles of the CPU baseline sample")
     return p.parse_args()
@@ -173,8 +174,8 @@ def run_native(args):
     jc = args.model == "jc"
 
     class A:  # the argparse namespace the reference's class reads (vcsmc.py:111-120)
-        M = 10; branch_prior = float(np.log(10)); jcmodel = jc; optimizer = "GradientDescentOptimizer"
-        dataset = "synthetic_%dx%d" % (N, S); nested = False; n_particles = K
+        M = max(args.nested, 1); branch_prior = float(np.log(10)); jcmodel = jc; optimizer = "GradientDescentOptimizer"
+        dataset = "synthetic_%dx%d" % (N, S); nested = args.nested > 0; n_particles = K
 
     datadict = synthetic_alignment(N, S, seed=0)
     model = VCSMC(datadict, K, A, seed=0)
@@ -236,6 +237,8 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     merges = float(K) * S * (N - 1)
+    if args.nested:   # every (pair, sub-sample) of the look-ahead is a particle-site merge too
+        merges += float(K) * S * args.nested * sum((N - r) * (N - r - 1) // 2 for r in range(N - 1))
     value = merges / (ms_step * 1e-3)
 
     # ---- end-to-end region: host buffers in, loss + grads out, every step
@@ -282,8 +285,9 @@ def run_native(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "VCSMC %s fwd+grad sweep, %d taxa x %d sites x %d particles, i.i.d. uniform nucleotides "
-                               "(PCG64 seed 0), reference initial parameters" % (args.model.upper(), N, S, K),
+        "config": {"workload": "%s %s fwd+grad sweep, %d taxa x %d sites x %d particles, i.i.d. uniform nucleotides "
+                               "(PCG64 seed 0), reference initial parameters" % (
+                                   "VNCSMC(M=%d)" % args.nested if args.nested else "VCSMC", args.model.upper(), N, S, K),
                    "taxa": N, "sites": S, "particles": K, "model": args.model, "sharding": "sites/%d" % world,
                    "l2": "inputs larger than L2 (node pool of %.1f GB streamed per sweep)" % (sweep.workspace.numel() / 1e9),
                    "backward": "dense" if args.dense else "zero-adjoint events skipped (identical results)",

@@ -419,17 +419,17 @@ __global__ void bwd_active_kernel(const double* __restrict__ cnew, const int32_t
 }
 
 // zero the adjoint slots of the consumed nodes of one rank event (the first *count entries of `order`)
-__global__ void zero_consumed_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ count,
+__global__ void zero_consumed_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ count, int K,
                                      const int32_t* __restrict__ gsrc, int64_t slot_sites, int n_sites,
                                      double* __restrict__ gpool) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_sites) return;
-  const int n = *count;
+  const int n = count ? *count : K;
   d4 z;
 #pragma unroll
   for (int j = 0; j < 4; ++j) z.v[j] = 0.0;
   for (int j = blockIdx.y; j < n; j += gridDim.y) {
-    const int g = gsrc[order[j]];
+    const int g = gsrc[order ? order[j] : j];
     if (g >= 0) st_site(gpool + ((int64_t)g * slot_sites + s) * 4, z);
   }
 }
@@ -777,6 +777,13 @@ int decide_modes(vcsmc_sweep* h, int64_t tables, int64_t ws_bytes, bool report) 
   return VCSMC_OK;
 }
 
+// Sorting the particles by child pair only pays when groups of several particles are formed (see pick_group in
+// merge.cu: R = K * tiles / 4736); below that the visiting order is the identity and ~9 launches per event are saved.
+bool use_sorted_order(int64_t K, int n_sites) {
+  const int64_t tiles = (n_sites + 511) / 512;
+  return K * tiles >= 2 * 148 * 32;
+}
+
 int check_cfg(const vcsmc_sweep_config* c) {
   if (!c) { set_error("null config"); return VCSMC_ERR_ARG; }
   if (c->n_taxa < 2 || c->n_taxa > kMaxRoots) { set_error("n_taxa=%d out of range [2,%d]", c->n_taxa, kMaxRoots); return VCSMC_ERR_ARG; }
@@ -987,13 +994,16 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
       VCSMC_LAUNCH_CHECK("gc_alloc_kernel");
     }
     // visiting order: particles sorted by their pair of child nodes (shared children are read once per group)
-    rc = launch_sort_order(a.lsrc, a.rsrc, nullptr, K, h->pool_slots, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out),
-                           h->p<int32_t>(h->o_vals_in), h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count),
-                           h->p<char>(h->o_sort_temp), h->sort_temp, st);
-    if (rc) return rc;
+    const bool sorted = use_sorted_order(K, S);
+    if (sorted) {
+      rc = launch_sort_order(a.lsrc, a.rsrc, nullptr, K, h->pool_slots, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out),
+                             h->p<int32_t>(h->o_vals_in), h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count),
+                             h->p<char>(h->o_sort_temp), h->sort_temp, st);
+      if (rc) return rc;
+    }
     int tiles = 0;  // partial sums per particle written by the merge
     h->prof_begin(0, st);
-    rc = launch_merge_fwd(codes, S, pool, S, a.lsrc, a.rsrc, a.dst, h->p<int32_t>(h->o_order), nullptr, P, pi, K, -1, S, h->jc, 0,
+    rc = launch_merge_fwd(codes, S, pool, S, a.lsrc, a.rsrc, a.dst, sorted ? h->p<int32_t>(h->o_order) : nullptr, nullptr, P, pi, K, -1, S, h->jc, 0,
                           h->p<double>(h->o_ell_part), &tiles, st);
     h->prof_end(st);
     if (rc) return rc;
@@ -1136,23 +1146,25 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   VCSMC_LAUNCH_CHECK("leaf_pi_grad_kernel");
 
   // ---- visiting orders of every rank event (sorted by child pair; inactive particles last)
-  for (int r = 0; r < N - 1; ++r) {
-    bwd_active_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(h->p<double>(h->o_cnew) + (int64_t)r * K, h->p<int32_t>(h->o_consumed) + (int64_t)r * K,
-                                                                 K, h->skip_zero, h->p<int32_t>(h->o_act_bwd), h->p<int32_t>(h->o_act_rec));
-    VCSMC_LAUNCH_CHECK("bwd_active_kernel");
-    const int32_t* bl = h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K;
-    const int32_t* br = h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K;
-    rc = launch_sort_order(bl, br, h->p<int32_t>(h->o_act_bwd), K, E, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out), h->p<int32_t>(h->o_vals_in),
-                           h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r, h->p<char>(h->o_sort_temp), h->sort_temp, st);
-    if (rc) return rc;
+  const bool sorted_b = use_sorted_order(K, S);
+  std::vector<int32_t> cnt_bwd(N, (int32_t)K), cnt_rec(N, (int32_t)K);
+  if (sorted_b) {
+    for (int r = 0; r < N - 1; ++r) {
+      bwd_active_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(h->p<double>(h->o_cnew) + (int64_t)r * K, h->p<int32_t>(h->o_consumed) + (int64_t)r * K,
+                                                                   K, h->skip_zero, h->p<int32_t>(h->o_act_bwd), h->p<int32_t>(h->o_act_rec));
+      VCSMC_LAUNCH_CHECK("bwd_active_kernel");
+      const int32_t* bl = h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K;
+      const int32_t* br = h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K;
+      rc = launch_sort_order(bl, br, h->p<int32_t>(h->o_act_bwd), K, E, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out), h->p<int32_t>(h->o_vals_in),
+                             h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r, h->p<char>(h->o_sort_temp), h->sort_temp, st);
+      if (rc) return rc;
+    }
+    // one small D2H + sync: the host learns how many particles each rank event really has to visit, so that empty
+    // launches are skipped and grids are sized exactly (with ESS ~ 1 almost every reverse event is empty)
+    VCSMC_CUDA(cudaMemcpyAsync(cnt_bwd.data(), h->p<int32_t>(h->o_count_bwd), (N - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    VCSMC_CUDA(cudaStreamSynchronize(st));
+    cnt_rec = cnt_bwd;
   }
-
-  // one small D2H + sync: the host learns how many particles each rank event really has to visit, so that empty
-  // launches are skipped and grids are sized exactly (with ESS ~ 1 almost every reverse event is empty)
-  std::vector<int32_t> cnt_bwd(N, 0), cnt_rec(N, 0);
-  VCSMC_CUDA(cudaMemcpyAsync(cnt_bwd.data(), h->p<int32_t>(h->o_count_bwd), (N - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  VCSMC_CUDA(cudaMemcpyAsync(cnt_rec.data(), h->p<int32_t>(h->o_count_bwd), (N - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  VCSMC_CUDA(cudaStreamSynchronize(st));
   {
     int64_t visited = 0;
     for (int r = 0; r < N - 1; ++r) visited += cnt_bwd[r];
@@ -1193,7 +1205,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
         if (cnt_rec[r] == 0) continue;
         h->prof_begin(1, st);
         rc = launch_merge_fwd(codes_c, S, lpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
-                              h->p<int32_t>(h->o_bdst) + (int64_t)r * K, h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r,
+                              h->p<int32_t>(h->o_bdst) + (int64_t)r * K, sorted_b ? h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K : nullptr, sorted_b ? h->p<int32_t>(h->o_count_bwd) + r : nullptr,
                               h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, K, cnt_rec[r], nc, h->jc, 1, h->p<double>(h->o_ell_part), nullptr, st);
         h->prof_end(st);
         if (rc) return rc;
@@ -1203,7 +1215,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     for (int r = 0; r < N - 1; ++r) {
       if (cnt_rec[r] == 0) continue;
       dim3 grid((nc + 255) / 256, cnt_rec[r] < 32 ? cnt_rec[r] : 32, 1);
-      zero_consumed_kernel<<<grid, 256, 0, st>>>(h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r,
+      zero_consumed_kernel<<<grid, 256, 0, st>>>(sorted_b ? h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K : nullptr, sorted_b ? h->p<int32_t>(h->o_count_bwd) + r : nullptr, (int)K,
                                                  h->p<int32_t>(h->o_bsrc_g) + (int64_t)r * K, Sc, nc, gpool);
       VCSMC_LAUNCH_CHECK("zero_consumed_kernel");
     }
@@ -1254,7 +1266,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
       if (cnt_bwd[r] == 0) continue;
       h->prof_begin(2, st);
       rc = launch_merge_bwd(codes_c, S, lpool, gpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
-                            h->p<int32_t>(h->o_bsrc_g) + (int64_t)r * K, h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r,
+                            h->p<int32_t>(h->o_bsrc_g) + (int64_t)r * K, sorted_b ? h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K : nullptr, sorted_b ? h->p<int32_t>(h->o_count_bwd) + r : nullptr,
                             h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, h->p<double>(h->o_cnew) + (int64_t)r * K, K, cnt_bwd[r], nc, h->jc, h->skip_zero,
                             h->p<double>(h->o_dP) + (int64_t)r * K * 32, dpi, st);
       h->prof_end(st);
