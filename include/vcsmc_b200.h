@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VCSMC_ABI_VERSION 1
+#define VCSMC_ABI_VERSION 2
 
 #define VCSMC_OK 0
 #define VCSMC_ERR_ARG (-1)      /* bad argument */
@@ -140,15 +140,47 @@ typedef struct {
 /* Optional cross-rank hook (site sharding): sum `count` doubles in place across ranks, stream-ordered. */
 typedef int (*vcsmc_allreduce_fn)(void* user, double* buf, int64_t count, void* stream);
 
+/* Cross-rank hook of PARTICLE sharding (north_star: each GPU holds K/G particles).  The library asks the caller
+ * (torch.distributed / NCCL) for the three collectives the protocol needs, all stream-ordered on `stream`:
+ *   VCSMC_COMM_ALLGATHER  buf holds world chunks of `bytes` bytes, chunk g belongs to rank g; in place
+ *   VCSMC_COMM_BARRIER    every rank's earlier work on `stream` is complete before any rank's later work starts
+ *   VCSMC_COMM_ALLREDUCE  sum bytes/8 doubles in place
+ * Everything else -- reading a remote ancestor's forest row, copying the nodes a rank lacks -- is done by the library's
+ * own kernels through peer pointers (vcsmc_sweep_set_comm's peer_ws). */
+#define VCSMC_COMM_ALLGATHER 1
+#define VCSMC_COMM_BARRIER 2
+#define VCSMC_COMM_ALLREDUCE 3
+typedef int (*vcsmc_comm_fn)(void* user, int op, void* buf, int64_t bytes, void* stream);
+
+/* Peer mapping of a device allocation (CUDA IPC), so that every rank can address every rank's workspace:
+ * export: handle_host[64] and the byte offset of dev_ptr inside its allocation; open: maps a peer's allocation into
+ * this process and returns its base (add the exporter's offset); close: unmaps. */
+int vcsmc_ipc_export(void* dev_ptr, void* handle_host, int64_t* offset_host);
+int vcsmc_ipc_open(const void* handle_host, void** base_out);
+int vcsmc_ipc_close(void* base);
+
 int vcsmc_sweep_query(const vcsmc_sweep_config* cfg, vcsmc_sweep_sizes* out);
 int vcsmc_sweep_create(const vcsmc_sweep_config* cfg, void* workspace, vcsmc_sweep_t** out);
 void vcsmc_sweep_destroy(vcsmc_sweep_t* h);
 int vcsmc_sweep_set_allreduce(vcsmc_sweep_t* h, vcsmc_allreduce_fn fn, void* user);
+/* Particle sharding over `world` <= 8 ranks of one NVLink domain: this rank owns logical particles
+ * [rank K/world, (rank+1) K/world) (K must be divisible); peer_ws_host[g] is the address, in THIS process, of rank g's
+ * workspace (its own for g == rank); all ranks create the sweep with the same config and workspace size.  Forward:
+ * every rank scores its particles on all sites; per rank event one all-gather of the step record (weights, branch
+ * lengths, child references), identical ancestors on every rank, owners materialise the survivors, ranks that drew a
+ * remote ancestor pull the nodes they lack over NVLink.  Backward: sharded by SITE on the gathered tables
+ * (options "site_begin"/"site_end"), gradients are summed by the caller.  VCSMC proposal only (n_sub == 0). */
+int vcsmc_sweep_set_comm(vcsmc_sweep_t* h, int rank, int world, vcsmc_comm_fn fn, void* user, void* const* peer_ws_host);
 /* Options: "scalar_share" (default 1): fraction of the site-independent gradient terms this rank contributes
  * (site sharding: 1 on rank 0, 0 elsewhere, then sum the gradients across ranks);
  * "skip_zero" (default 1): backward skips rank events whose adjoint is exactly zero (W underflowed to 0 and no
  * descendant uses the node) -- results are identical, set 0 to force the dense reverse sweep;
  * "max_chunk_sites" (default 0 = unlimited): cap on the site chunk of the recompute backward (testing aid);
+ * "lazy" (default 1; VCSMC proposal only): the forward scores every particle without storing its node and materialises
+ * only the particles that the next resampling draws as an ancestor; 0 = eager (every node stored as it is computed) --
+ * results are identical;
+ * "force_gc" (default 0): use the garbage-collected pool and the recompute backward even when every node fits (testing aid);
+ * "site_begin", "site_end" (default 0, n_sites): the site slice this rank's reverse sweep covers;
  * "profile" (default 0): record CUDA events around every merge launch, read with vcsmc_sweep_profile. */
 int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value);
 
@@ -171,8 +203,9 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
                          double* dpi, void* stream);
 
 /* Per-kernel device time of the merge launches since the option "profile" was set to 1 (CUDA events on the
- * launching stream): out_host[6] = {ms, launches} for the forward merge, the recompute merge of the chunked
- * backward, and the backward merge.  Synchronises on the recorded events and resets the counters. */
+ * launching stream): out_host[8] = {ms, launches} for the forward merge (eager) or scoring kernel (lazy), the recompute
+ * merge of the chunked backward, the backward merge, and the survivor materialisation + peer pulls.  Synchronises on the
+ * recorded events and resets the counters. */
 int vcsmc_sweep_profile(vcsmc_sweep_t* h, double* out_host);
 
 /* Device pointers into the workspace, valid after forward:

@@ -31,6 +31,8 @@ class SweepSizes(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+COMM_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p)
+COMM_ALLGATHER, COMM_BARRIER, COMM_ALLREDUCE = 1, 2, 3
 
 _P = C.c_void_p
 _SIGNATURES = {
@@ -51,6 +53,10 @@ _SIGNATURES = {
     "vcsmc_sweep_create": (C.c_int, [C.POINTER(SweepConfig), _P, C.POINTER(_P)]),
     "vcsmc_sweep_destroy": (None, [_P]),
     "vcsmc_sweep_set_allreduce": (C.c_int, [_P, ALLREDUCE_FN, _P]),
+    "vcsmc_sweep_set_comm": (C.c_int, [_P, C.c_int, C.c_int, COMM_FN, _P, C.POINTER(C.c_void_p)]),
+    "vcsmc_ipc_export": (C.c_int, [_P, _P, C.POINTER(C.c_int64)]),
+    "vcsmc_ipc_open": (C.c_int, [_P, C.POINTER(_P)]),
+    "vcsmc_ipc_close": (C.c_int, [_P]),
     "vcsmc_sweep_set_option": (C.c_int, [_P, C.c_char_p, C.c_double]),
     "vcsmc_sweep_set_uniforms": (C.c_int, [_P, _P, _P, _P, _P]),
     "vcsmc_sweep_set_seed": (C.c_int, [_P, C.c_uint64]),
@@ -79,7 +85,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.vcsmc_abi_version() != 1:
+    if lib.vcsmc_abi_version() != 2:
         raise ImportError("libvcsmc_b200 ABI version mismatch")
     _lib = lib
     return lib

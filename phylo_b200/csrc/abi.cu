@@ -1,6 +1,7 @@
 // extern "C" surface of libvcsmc_b200 (kernel-level entry points) + error plumbing.  See include/vcsmc_b200.h.
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -89,6 +90,38 @@ int vcsmc_resample(const double* lw, const double* u, int64_t K, int32_t* idx, d
   if (rc) return rc;
   if (lse) VCSMC_CUDA(cudaMemcpyAsync(lse, stats, sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   if (ess) VCSMC_CUDA(cudaMemcpyAsync(ess, stats + 2, sizeof(double), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return VCSMC_OK;
+}
+
+int vcsmc_ipc_export(void* dev_ptr, void* handle_host, int64_t* offset_host) {
+  if (!dev_ptr || !handle_host || !offset_host) { set_error("ipc_export: null argument"); return VCSMC_ERR_ARG; }
+  cudaIpcMemHandle_t hd;
+  VCSMC_CUDA(cudaIpcGetMemHandle(&hd, dev_ptr));
+  memcpy(handle_host, &hd, sizeof(hd));
+  // the handle names the whole allocation dev_ptr lies in: report where inside it dev_ptr is
+  typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  VCSMC_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+  if (!fn || qr != cudaDriverEntryPointSuccess) { set_error("ipc_export: cuMemGetAddressRange unavailable"); return VCSMC_ERR_CUDA; }
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (((range_fn)fn)(&base, &size, (unsigned long long)(uintptr_t)dev_ptr) != 0) { set_error("ipc_export: cuMemGetAddressRange failed"); return VCSMC_ERR_CUDA; }
+  *offset_host = (int64_t)((unsigned long long)(uintptr_t)dev_ptr - base);
+  return VCSMC_OK;
+}
+
+int vcsmc_ipc_open(const void* handle_host, void** base_out) {
+  if (!handle_host || !base_out) { set_error("ipc_open: null argument"); return VCSMC_ERR_ARG; }
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle_host, sizeof(hd));
+  VCSMC_CUDA(cudaIpcOpenMemHandle(base_out, hd, cudaIpcMemLazyEnablePeerAccess));
+  return VCSMC_OK;
+}
+
+int vcsmc_ipc_close(void* base) {
+  if (!base) return VCSMC_OK;
+  VCSMC_CUDA(cudaIpcCloseMemHandle(base));
   return VCSMC_OK;
 }
 

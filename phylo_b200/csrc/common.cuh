@@ -25,6 +25,7 @@ int check_cuda(cudaError_t e, const char* what);
     if (_rc != 0) return _rc;                             \
   } while (0)
 
+constexpr int kMaxPeers = 8;         // ranks of one NVLink domain a sweep can address (particle sharding)
 constexpr int kTileThreads = 256;    // threads per merge CTA
 constexpr int kSitesPerThread = 4;   // sites per thread per tile
 constexpr int kTileSites = kTileThreads * kSitesPerThread;  // 1024 sites per (particle, tile) work item

@@ -18,6 +18,17 @@ int launch_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* p
                      const int32_t* count, const double* P, const double* pi, const double* coef, int64_t K,
                      int64_t n_active, int n_sites, int jc, int skip_zero, double* dP, double* dpi_acc, cudaStream_t st);
 
+// score.cu (lazy forward: likelihood-only scoring, survivor materialisation, peer pulls)
+int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double* pool, int64_t slot_sites,
+                       const int32_t* lsrc, const int32_t* rsrc, const int32_t* order, const double* P, const double* pi,
+                       int64_t K, int n_sites, int jc, double* ell_part, int* n_parts, cudaStream_t st);
+int launch_materialise(const uint8_t* codes, int64_t codes_stride, double* pool, int64_t slot_sites, const int32_t* lsrc,
+                       const int32_t* rsrc, const int32_t* list, const int32_t* count, int64_t max_count, const int32_t* loc,
+                       int64_t e_base, const double* P, int n_sites, int jc, cudaStream_t st);
+int launch_pull(const int32_t* fetch_e, const int32_t* fetch_src, const int32_t* count, int64_t max_count, const int32_t* loc,
+                double* pool, int64_t slot_sites, int n_sites, int world, const int32_t* const* peer_loc,
+                const double* const* peer_pool, cudaStream_t st);
+
 // sort.cu
 size_t sort_temp_bytes(int64_t K);
 size_t scan_temp_bytes(int64_t n);

@@ -1,0 +1,577 @@
+// The lazy forward sweep, and particle sharding across the GPUs of one NVLink domain.
+//
+// Same outputs as the eager forward of sweep.cu (sample_phylogenies / body_rank_update, vcsmc.py:332-451), different
+// schedule.  Rank event r scores every particle WITHOUT storing its node (merge_score_kernel, score.cu); once the
+// weights are known and the next event has drawn its ancestors, only the particles that were drawn at least once
+// ("survivors") get their node written.  With ESS ~ 1 that is one or two nodes per rank event instead of K.
+//
+// Particle sharding (north_star): rank g owns the logical particles [g K/G, (g+1) K/G) and a private node
+// pool.  Nodes are named by a global index e = r*K + k; `loc[e]` maps a node to its local pool slot (valid iff
+// slot_id[loc[e]] == e), so a pool is a cache of the nodes this rank's particles reference.  Per rank event:
+//   1. every rank builds the same CDF from the all-gathered weights and draws ALL K ancestors (same uniforms);
+//   2. the owner of each survivor materialises it into its own pool;
+//   3. every rank copies the forest ROW (node ids, leaf counts) of each of its particles' ancestors -- a peer read when
+//      the ancestor lives on another GPU -- and lists the nodes of those rows it holds no copy of;
+//   4. the slot allocator (free = not referenced by any surviving row of this rank) serves both lists;
+//   5. barrier; missing nodes are pulled out of the owners' pools over NVLink (pull_kernel);
+//   6. pair proposal, branch lengths, transition matrices, scoring, weights for the rank's own particles;
+//   7. ONE all-gather of the step record (weights, likelihoods, branch lengths, child references, kept positions):
+//      the tables every rank needs for the next CDF, for the outputs, and for the reverse sweep.
+// The reverse sweep is sharded by SITE on the gathered tables (sweep.cu, options site_begin/site_end): the gradient is
+// a sum over sites and the recompute backward needs nothing but those tables.
+#include <string.h>
+
+#include "sweep_state.h"
+
+namespace vcsmc {
+namespace {
+
+__global__ void lz_ancestors_kernel(int first, int64_t K, const double* __restrict__ cdf, const double* __restrict__ u_res,
+                                    int32_t* __restrict__ anc, int32_t* __restrict__ surv) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  if (first) {
+    anc[k] = (int32_t)k;
+    return;
+  }
+  const int idx = upper_bound_cdf(cdf, K, u_res[k] * cdf[K - 1]);  // resample, vcsmc.py:284-285
+  anc[k] = idx;
+  surv[idx] = 1;
+}
+
+struct SurvArgs {
+  int n, N, gc;
+  int64_t Kl, k0;
+  const int32_t* surv;
+  const int32_t* ids_prev;
+  const int32_t* lsrc_prev;
+  const int32_t* rsrc_prev;
+  const int32_t* loc;
+  int32_t* flags;
+  int32_t* mat_list;
+  int32_t* counts;
+};
+
+// survivors of this rank: list them for materialisation; keep their forest rows and their children alive
+__global__ void lz_survivors_kernel(const SurvArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = a.n + 2;
+  const int64_t kl = i / w;
+  const int p = (int)(i - kl * w);
+  if (kl >= a.Kl || !a.surv[a.k0 + kl]) return;
+  if (p < a.n) {
+    if (a.gc) {
+      const int id = a.ids_prev[kl * a.N + p];
+      if (id >= a.N) {
+        const int s = a.loc[id - a.N];
+        if (s >= 0) a.flags[s] = 1;  // (the row's newest node has no slot yet)
+      }
+    }
+  } else if (p == a.n) {
+    a.mat_list[atomicAdd(a.counts, 1)] = (int32_t)kl;
+    if (a.gc && a.lsrc_prev[kl] >= 0) a.flags[a.lsrc_prev[kl]] = 1;
+  } else {
+    if (a.gc && a.rsrc_prev[kl] >= 0) a.flags[a.rsrc_prev[kl]] = 1;
+  }
+}
+
+struct InhArgs {
+  int r, n, N, gc, rank;
+  int64_t K, Kl, k0, fetch_cap;
+  const int32_t* anc;
+  const int32_t* peer_ids[kMaxPeers];
+  const int32_t* peer_cnt[kMaxPeers];
+  int32_t* inh_ids;
+  int32_t* inh_cnt;
+  const int32_t* loc;
+  const int32_t* slot_id;
+  int32_t* flags;
+  int32_t* pend;
+  int32_t* fetch_e;
+  int32_t* fetch_src;
+  int32_t* counts;
+  const double* LL_prev;
+  double* ll_tilde;
+  int32_t* status;
+};
+
+constexpr int kInhWarps = 8;
+
+// one warp per own particle: copy the ancestor's forest row (peer read when it lives on another GPU), keep cached
+// nodes alive, list the nodes this rank holds no copy of
+__global__ void __launch_bounds__(kInhWarps * 32) lz_inherit_kernel(const InhArgs a) {
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t kl = (int64_t)blockIdx.x * kInhWarps + wid;
+  if (kl >= a.Kl) return;
+  const int64_t anc = a.anc[a.k0 + kl];
+  const int g = (int)(anc / a.Kl);
+  const int64_t al = anc - (int64_t)g * a.Kl;
+  const int32_t* src_ids = a.peer_ids[g] + al * a.N;
+  const int32_t* src_cnt = a.peer_cnt[g] + al * a.N;
+  const int64_t newest = (int64_t)(a.r - 1) * a.K + anc;  // the ancestor's own node: materialised by its owner
+  for (int p = lane; p < a.n; p += 32) {
+    const int id = src_ids[p];
+    a.inh_ids[kl * a.N + p] = id;
+    a.inh_cnt[kl * a.N + p] = src_cnt[p];
+    if (id < a.N) continue;
+    const int e = id - a.N;
+    bool have;
+    int s = -1;
+    if (e == newest) {
+      have = (g == a.rank);  // gets its slot from the allocator below, via the survivor list
+    } else {
+      s = a.loc[e];
+      have = !a.gc || (s >= 0 && a.slot_id[s] == e);
+      if (have && a.gc) a.flags[s] = 1;
+    }
+    if (!have && atomicExch(a.pend + e, a.r) != a.r) {  // first claim of this node in this rank event
+      const int pos = atomicAdd(a.counts + 1, 1);
+      if (pos < a.fetch_cap) {
+        a.fetch_e[pos] = e;
+        a.fetch_src[pos] = g;
+      } else {
+        a.status[0] = VCSMC_ERR_POOL;
+      }
+    }
+  }
+  if (lane == 0) a.ll_tilde[kl] = a.LL_prev[anc];
+}
+
+// Free slots (flag == 0), lowest first, go to the survivors to materialise and then to the nodes to pull.
+// Single CTA, fixed order; each warp owns a contiguous segment of the flag array.
+__global__ void __launch_bounds__(1024) lz_alloc_kernel(const int32_t* __restrict__ flags, int64_t P, const int32_t* __restrict__ counts,
+                                                        int64_t fetch_cap, const int32_t* __restrict__ mat_list, int64_t e_base_prev,
+                                                        const int32_t* __restrict__ fetch_e, int32_t* __restrict__ loc,
+                                                        int32_t* __restrict__ slot_id, int32_t* __restrict__ status) {
+  __shared__ int64_t warp_off[33];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int64_t n_mat = counts[0];
+  const int64_t n_fetch = counts[1] < fetch_cap ? counts[1] : fetch_cap;
+  const int64_t Kn = n_mat + n_fetch;
+  if (Kn == 0) return;
+  // every live slot lies below the running peak, so the Kn lowest free slots are below peak + Kn
+  const int64_t peak = status[1];
+  if (peak + Kn < P) P = peak + Kn;
+  const int64_t seg = ((P + 31) / 32 + 31) / 32 * 32;
+  const int64_t b = min((int64_t)wid * seg, P), e = min(b + seg, P);
+  int cnt = 0;
+  for (int64_t i0 = b + lane; i0 < e; i0 += 128) {
+    int f[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f[q] = (i0 + 32 * q < e) ? flags[i0 + 32 * q] : 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cnt += f[q] == 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if (lane == 0) warp_off[wid + 1] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    int64_t t = 0;
+    warp_off[0] = 0;
+    for (int i = 1; i <= 32; ++i) {
+      t += warp_off[i];
+      warp_off[i] = t;
+    }
+    if (t < Kn) {
+      status[0] = VCSMC_ERR_POOL;
+      for (int64_t j = t; j < Kn; ++j) loc[j < n_mat ? e_base_prev + mat_list[j] : fetch_e[j - n_mat]] = -1;
+    }
+  }
+  __syncthreads();
+  int64_t j = warp_off[wid];
+  int top = 0;
+  for (int64_t i0 = b; i0 < e && j < Kn; i0 += 128) {
+    int f[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f[q] = (i0 + 32 * q + lane < e) ? flags[i0 + 32 * q + lane] : 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t i = i0 + 32 * q + lane;
+      const bool is_free = f[q] == 0;
+      const unsigned m = __ballot_sync(0xffffffffu, is_free);
+      const int64_t mine = j + __popc(m & ((1u << lane) - 1));
+      if (is_free && mine < Kn) {
+        const int64_t node = mine < n_mat ? e_base_prev + mat_list[mine] : fetch_e[mine - n_mat];
+        loc[node] = (int32_t)i;
+        slot_id[i] = (int32_t)node;
+        top = (int)i + 1;
+      }
+      j += __popc(m);
+    }
+  }
+  if (top) atomicMax(status + 1, top);
+}
+
+struct LzPrepArgs {
+  int r, n, N;
+  int64_t K, Kl, k0;
+  const float* u_pair;  // [Kl][n]
+  const double* u_bl;   // [Kl]
+  const double* u_br;
+  const double* lam_l;
+  const double* lam_r;
+  const int32_t* inh_ids;  // [Kl][N]
+  const int32_t* inh_cnt;
+  int32_t* ids_new;
+  int32_t* cnt_new;
+  const int32_t* loc;
+  int32_t* lref;  // row r of the [N-1][K] tables
+  int32_t* rref;
+  int32_t* nleaf;
+  uint8_t* rempos;
+  double* b_l;
+  double* b_r;
+  double* t2;
+  double* ll_tilde;  // [Kl]
+  int32_t* lsrc;     // [Kl]
+  int32_t* rsrc;
+};
+
+constexpr int kLzPrepWarps = 8;
+
+// One warp per own particle: pair proposal on the inherited row, forest-row update, branch lengths.
+// (extend_partial_state vcsmc.py:298-305; Exponential sample :351-358; state update :361-373)
+__global__ void __launch_bounds__(kLzPrepWarps * 32) lz_prepare_kernel(const LzPrepArgs a) {
+  extern __shared__ float su_all[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t kl = (int64_t)blockIdx.x * kLzPrepWarps + wid;
+  if (kl >= a.Kl) return;
+  const int n = a.n, N = a.N, r = a.r;
+  const int64_t k = a.k0 + kl;
+  float* su = su_all + wid * n;
+  for (int i = lane; i < n; i += 32) su[i] = a.u_pair[kl * n + i];
+  __syncwarp();
+  const int32_t* io = a.inh_ids + kl * N;
+  const int32_t* co = a.inh_cnt + kl * N;
+  int32_t* in_ = a.ids_new + kl * N;
+  int32_t* cn = a.cnt_new + kl * N;
+  uint8_t* rp = a.rempos + k * (int64_t)(n - 2);
+  const bool first = (r == 0);  // initial forest = the N leaves, one each (vcsmc.py:414-415)
+  int c0, c1;
+  rank_pairs_warp(su, n, lane, c0, c1, [&](int pos, int i) {
+    rp[pos] = (uint8_t)i;
+    in_[pos] = first ? i : io[i];
+    cn[pos] = first ? 1 : co[i];
+  });
+  if (lane == 0) {
+    const int lid = first ? c0 : io[c0], rid = first ? c1 : io[c1];
+    in_[n - 2] = (int32_t)(N + (int64_t)r * a.K + k);
+    const int nl = (first ? 1 : co[c0]) + (first ? 1 : co[c1]);
+    cn[n - 2] = nl;
+    a.nleaf[k] = nl;
+    a.lref[k] = lid;
+    a.rref[k] = rid;
+    a.lsrc[kl] = lid < N ? -(lid + 1) : a.loc[lid - N];
+    a.rsrc[kl] = rid < N ? -(rid + 1) : a.loc[rid - N];
+    const double bl = -log(a.u_bl[kl]) / a.lam_l[r];
+    const double br = -log(a.u_br[kl]) / a.lam_r[r];
+    a.b_l[k] = bl;
+    a.b_r[k] = br;
+    a.t2[2 * k] = bl;
+    a.t2[2 * k + 1] = br;
+    if (first) a.ll_tilde[kl] = log(1.0 / (double)a.K);
+  }
+}
+
+// ---- the per-event record that is all-gathered across ranks (field-major inside a rank's chunk)
+struct RecArgs {
+  int n, rank;
+  int64_t Kl, k0, K, stride;
+  char* rec;
+  double* lw;
+  double* LL;
+  double* ell;  // ell_node + N + r*K
+  double* b_l;
+  double* b_r;
+  double* cum_l;
+  double* cum_r;
+  double* t2;
+  int32_t* lref;
+  int32_t* rref;
+  int32_t* nleaf;
+  int32_t* vminus;
+  uint8_t* rempos;
+};
+
+__global__ void lz_pack_kernel(const RecArgs a) {
+  const int64_t kl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (kl >= a.Kl) return;
+  const int64_t k = a.k0 + kl;
+  char* base = a.rec + (int64_t)a.rank * a.stride;
+  double* d = reinterpret_cast<double*>(base);
+  d[0 * a.Kl + kl] = a.lw[k];
+  d[1 * a.Kl + kl] = a.LL[k];
+  d[2 * a.Kl + kl] = a.ell[k];
+  d[3 * a.Kl + kl] = a.b_l[k];
+  d[4 * a.Kl + kl] = a.b_r[k];
+  d[5 * a.Kl + kl] = a.cum_l[k];
+  d[6 * a.Kl + kl] = a.cum_r[k];
+  int32_t* q = reinterpret_cast<int32_t*>(base + 56 * a.Kl);
+  q[0 * a.Kl + kl] = a.lref[k];
+  q[1 * a.Kl + kl] = a.rref[k];
+  q[2 * a.Kl + kl] = a.nleaf[k];
+  q[3 * a.Kl + kl] = a.vminus[k];
+  uint8_t* b = reinterpret_cast<uint8_t*>(base + 72 * a.Kl);
+  const int m = a.n - 2;
+  for (int p = 0; p < m; ++p) b[kl * m + p] = a.rempos[k * m + p];
+}
+
+__global__ void lz_unpack_kernel(const RecArgs a) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.K) return;
+  const int g = (int)(k / a.Kl);
+  if (g == a.rank) return;
+  const int64_t kl = k - (int64_t)g * a.Kl;
+  const char* base = a.rec + (int64_t)g * a.stride;
+  const double* d = reinterpret_cast<const double*>(base);
+  a.lw[k] = d[0 * a.Kl + kl];
+  a.LL[k] = d[1 * a.Kl + kl];
+  a.ell[k] = d[2 * a.Kl + kl];
+  const double bl = d[3 * a.Kl + kl], br = d[4 * a.Kl + kl];
+  a.b_l[k] = bl;
+  a.b_r[k] = br;
+  a.t2[2 * k] = bl;
+  a.t2[2 * k + 1] = br;
+  a.cum_l[k] = d[5 * a.Kl + kl];
+  a.cum_r[k] = d[6 * a.Kl + kl];
+  const int32_t* q = reinterpret_cast<const int32_t*>(base + 56 * a.Kl);
+  a.lref[k] = q[0 * a.Kl + kl];
+  a.rref[k] = q[1 * a.Kl + kl];
+  a.nleaf[k] = q[2 * a.Kl + kl];
+  a.vminus[k] = q[3 * a.Kl + kl];
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(base + 72 * a.Kl);
+  const int m = a.n - 2;
+  for (int p = 0; p < m; ++p) a.rempos[k * m + p] = b[kl * m + p];
+}
+
+__global__ void lz_lltilde_kernel(int64_t K, int N, const double* __restrict__ LL, const int32_t* __restrict__ anc,
+                                  double* __restrict__ ll_tilde) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  ll_tilde[k] = N >= 3 ? LL[(int64_t)(N - 3) * K + anc[(int64_t)(N - 2) * K + k]] : log(1.0 / (double)K);
+}
+
+__global__ void lz_iota_kernel(int32_t* p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int32_t)i;
+}
+
+}  // namespace
+
+int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l, const double* lam_r, const double* Q,
+                       const double* pi, cudaStream_t st) {
+  const int N = h->N, S = h->S, G = h->world;
+  const int64_t K = h->K, Kl = h->Kl, k0 = h->k0, E = (int64_t)(N - 1) * K;
+  const bool gc = h->fwd_gc;
+  int rc;
+  if (G > 1 && !gc) { set_error("particle sharding runs on the garbage-collected pool"); return VCSMC_ERR_STATE; }
+  if (!h->use_seed && h->x_look_bl != nullptr) { set_error("uniforms were set for the other proposal (nested vs plain)"); return VCSMC_ERR_STATE; }
+
+  int32_t* status = h->p<int32_t>(h->o_status);
+  VCSMC_CUDA(cudaMemsetAsync(status, 0, 8 * sizeof(int32_t), st));
+  {
+    std::vector<double> ldf(2 * N + 4, 0.0);
+    for (int m = 0; m < 2 * N + 4; ++m) ldf[m] = log_double_factorial_host(m);
+    VCSMC_CUDA(cudaMemcpyAsync(h->p<double>(h->o_ldf), ldf.data(), ldf.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    VCSMC_CUDA(cudaStreamSynchronize(st));  // ldf is a stack-lifetime host buffer
+  }
+  double* ell_node = h->p<double>(h->o_ell_node);
+  rc = launch_leaf_ell(codes, S, N, S, pi, ell_node, st);
+  if (rc) return rc;
+  if (h->allreduce) {  // site sharding: every rank holds a slice of the sites
+    if (h->allreduce(h->allreduce_user, ell_node, N, st)) { set_error("allreduce hook failed"); return VCSMC_ERR_CUDA; }
+  }
+  double* pool = h->p<double>(h->o_pool);
+  int32_t* flags = h->p<int32_t>(h->o_flags);
+  int32_t* loc = h->p<int32_t>(h->o_loc);
+  int32_t* slot_id = gc ? h->p<int32_t>(h->o_slot_id) : nullptr;
+  int32_t* pend = h->p<int32_t>(h->o_pend);
+  int32_t* surv = h->p<int32_t>(h->o_surv);
+  int32_t* counts = h->p<int32_t>(h->o_counts);
+  int32_t* mat_list = h->p<int32_t>(h->o_mat_list);
+  int32_t* fetch_e = h->p<int32_t>(h->o_fetch_e);
+  int32_t* fetch_src = h->p<int32_t>(h->o_fetch_src);
+  int32_t* inh_ids = h->p<int32_t>(h->o_lz_ids);
+  int32_t* inh_cnt = h->p<int32_t>(h->o_lz_cnt);
+  int32_t* lsrc = h->p<int32_t>(h->o_lsrc);
+  int32_t* rsrc = h->p<int32_t>(h->o_rsrc);
+  double* ll_tilde = h->p<double>(h->o_lltilde);
+  if (gc) {
+    VCSMC_CUDA(cudaMemsetAsync(loc, 0xFF, E * sizeof(int32_t), st));
+    VCSMC_CUDA(cudaMemsetAsync(slot_id, 0xFF, (size_t)h->pool_slots * sizeof(int32_t), st));
+    count_launch(2);
+  } else {
+    lz_iota_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(loc, E);  // direct map: node e lives in slot e
+    VCSMC_LAUNCH_CHECK("lz_iota_kernel");
+  }
+  if (G > 1) {
+    VCSMC_CUDA(cudaMemsetAsync(pend, 0xFF, E * sizeof(int32_t), st));
+    count_launch();
+  }
+  const bool sorted = use_sorted_order(Kl, S);
+  int64_t pair_off = 0;
+
+  for (int r = 0; r < N - 1; ++r) {
+    const int n = N - r;
+    const int cur = r & 1, prev = cur ^ 1;
+    // ---- uniforms: pair / branch draws of the rank's own particles, resampling draws of ALL particles
+    const float* u_pair;
+    const double *u_bl, *u_br, *u_res_all;
+    if (h->use_seed) {
+      rc = launch_philox_step(h->seed, r, k0, Kl, n, h->p<float>(h->o_u_pair), h->p<double>(h->o_u_bl), h->p<double>(h->o_u_br),
+                              nullptr, nullptr, st);
+      if (rc) return rc;
+      if (r > 0) {
+        rc = launch_philox_step(h->seed, r, 0, K, 0, nullptr, nullptr, nullptr, h->p<double>(h->o_u_res_all), nullptr, st);
+        if (rc) return rc;
+      }
+      u_pair = h->p<float>(h->o_u_pair); u_bl = h->p<double>(h->o_u_bl); u_br = h->p<double>(h->o_u_br);
+      u_res_all = h->p<double>(h->o_u_res_all);
+    } else {
+      u_pair = h->x_pair + pair_off + k0 * n; u_bl = h->x_bl + (int64_t)r * K + k0; u_br = h->x_br + (int64_t)r * K + k0;
+      u_res_all = h->x_res + (int64_t)r * K;
+      pair_off += K * n;
+    }
+    int32_t* anc_row = h->p<int32_t>(h->o_anc) + (int64_t)r * K;
+    int32_t* ids_prev = h->p<int32_t>(h->o_ids[prev]);
+    int32_t* ids_cur = h->p<int32_t>(h->o_ids[cur]);
+    int32_t* cnt_cur = h->p<int32_t>(h->o_cnt[cur]);
+
+    if (r > 0) {
+      VCSMC_CUDA(cudaMemsetAsync(surv, 0, K * sizeof(int32_t), st));
+      VCSMC_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(int32_t), st));
+      if (gc) VCSMC_CUDA(cudaMemsetAsync(flags, 0, (size_t)h->pool_slots * sizeof(int32_t), st));
+      count_launch(3);
+    }
+    lz_ancestors_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(r == 0, K, h->p<double>(h->o_cdf), u_res_all, anc_row, surv);
+    VCSMC_LAUNCH_CHECK("lz_ancestors_kernel");
+    if (r > 0) {
+      const int64_t e_base_prev = (int64_t)(r - 1) * K + k0;
+      SurvArgs sa;
+      sa.n = n; sa.N = N; sa.gc = gc; sa.Kl = Kl; sa.k0 = k0; sa.surv = surv; sa.ids_prev = ids_prev; sa.lsrc_prev = lsrc;
+      sa.rsrc_prev = rsrc; sa.loc = loc; sa.flags = flags; sa.mat_list = mat_list; sa.counts = counts;
+      lz_survivors_kernel<<<(unsigned)((Kl * (n + 2) + 255) / 256), 256, 0, st>>>(sa);
+      VCSMC_LAUNCH_CHECK("lz_survivors_kernel");
+      InhArgs ia;
+      ia.r = r; ia.n = n; ia.N = N; ia.gc = gc; ia.rank = h->rank; ia.K = K; ia.Kl = Kl; ia.k0 = k0; ia.fetch_cap = h->fetch_cap;
+      ia.anc = anc_row;
+      for (int g = 0; g < kMaxPeers; ++g) {
+        ia.peer_ids[g] = g < G ? reinterpret_cast<const int32_t*>(h->peer_ws[g] + h->o_ids[prev]) : nullptr;
+        ia.peer_cnt[g] = g < G ? reinterpret_cast<const int32_t*>(h->peer_ws[g] + h->o_cnt[prev]) : nullptr;
+      }
+      ia.inh_ids = inh_ids; ia.inh_cnt = inh_cnt; ia.loc = loc; ia.slot_id = slot_id; ia.flags = flags; ia.pend = pend;
+      ia.fetch_e = fetch_e; ia.fetch_src = fetch_src; ia.counts = counts;
+      ia.LL_prev = h->p<double>(h->o_LL) + (int64_t)(r - 1) * K; ia.ll_tilde = ll_tilde; ia.status = status;
+      lz_inherit_kernel<<<(unsigned)((Kl + kInhWarps - 1) / kInhWarps), kInhWarps * 32, 0, st>>>(ia);
+      VCSMC_LAUNCH_CHECK("lz_inherit_kernel");
+      if (gc) {
+        lz_alloc_kernel<<<1, 1024, 0, st>>>(flags, h->pool_slots, counts, h->fetch_cap, mat_list, e_base_prev, fetch_e, loc, slot_id, status);
+        VCSMC_LAUNCH_CHECK("lz_alloc_kernel");
+      }
+      // the survivors' nodes: children, P and slots of rank event r-1 are still in place
+      h->prof_begin(3, st);
+      rc = launch_materialise(codes, S, pool, S, lsrc, rsrc, mat_list, counts, Kl, loc, e_base_prev,
+                              h->p<double>(h->o_P) + ((int64_t)(r - 1) * K + k0) * 32, S, h->jc, st);
+      if (rc) return rc;
+      if (G > 1) {
+        if (h->comm(h->comm_user, VCSMC_COMM_BARRIER, nullptr, 0, st)) { set_error("comm hook failed (barrier)"); return VCSMC_ERR_CUDA; }
+        const int32_t* peer_loc[kMaxPeers];
+        const double* peer_pool[kMaxPeers];
+        for (int g = 0; g < G; ++g) {
+          peer_loc[g] = reinterpret_cast<const int32_t*>(h->peer_ws[g] + h->o_loc);
+          peer_pool[g] = reinterpret_cast<const double*>(h->peer_ws[g] + h->o_pool);
+        }
+        rc = launch_pull(fetch_e, fetch_src, counts + 1, h->fetch_cap < Kl * n ? h->fetch_cap : Kl * n, loc, pool, S, S, G,
+                         peer_loc, peer_pool, st);
+        if (rc) return rc;
+      }
+      h->prof_end(st);
+    }
+
+    // ---- proposal for the rank's own particles
+    LzPrepArgs a;
+    a.r = r; a.n = n; a.N = N; a.K = K; a.Kl = Kl; a.k0 = k0;
+    a.u_pair = u_pair; a.u_bl = u_bl; a.u_br = u_br; a.lam_l = lam_l; a.lam_r = lam_r;
+    a.inh_ids = inh_ids; a.inh_cnt = inh_cnt; a.ids_new = ids_cur; a.cnt_new = cnt_cur; a.loc = loc;
+    a.lref = h->p<int32_t>(h->o_lref) + (int64_t)r * K;
+    a.rref = h->p<int32_t>(h->o_rref) + (int64_t)r * K;
+    a.nleaf = h->p<int32_t>(h->o_nleaf) + (int64_t)r * K;
+    a.rempos = h->p<uint8_t>(h->o_rempos) + h->rem_off[r];
+    a.b_l = h->p<double>(h->o_b_l) + (int64_t)r * K;
+    a.b_r = h->p<double>(h->o_b_r) + (int64_t)r * K;
+    a.t2 = h->p<double>(h->o_t2) + (int64_t)r * 2 * K;
+    a.ll_tilde = ll_tilde; a.lsrc = lsrc; a.rsrc = rsrc;
+    lz_prepare_kernel<<<(unsigned)((Kl + kLzPrepWarps - 1) / kLzPrepWarps), kLzPrepWarps * 32, (size_t)kLzPrepWarps * n * sizeof(float), st>>>(a);
+    VCSMC_LAUNCH_CHECK("lz_prepare_kernel");
+
+    double* P = h->p<double>(h->o_P) + ((int64_t)r * K + k0) * 32;
+    rc = launch_transition_fwd(Q, a.t2 + 2 * k0, 2 * Kl, h->jc, P, st);
+    if (rc) return rc;
+    if (sorted) {
+      rc = launch_sort_order(lsrc, rsrc, nullptr, Kl, gc ? h->pool_slots : E, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out),
+                             h->p<int32_t>(h->o_vals_in), h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count),
+                             h->p<char>(h->o_sort_temp), h->sort_temp, st);
+      if (rc) return rc;
+    }
+    int tiles = 0;
+    h->prof_begin(0, st);
+    rc = launch_merge_score(codes, S, pool, S, lsrc, rsrc, sorted ? h->p<int32_t>(h->o_order) : nullptr, P, pi, Kl, S, h->jc,
+                            h->p<double>(h->o_ell_part), &tiles, st);
+    h->prof_end(st);
+    if (rc) return rc;
+
+    WeightArgs w;
+    w.r = r; w.n = n; w.N = N; w.tiles = tiles; w.K = Kl;
+    w.ell_part = h->p<double>(h->o_ell_part);
+    if (h->allreduce) {
+      rc = launch_ell_reduce(h->p<double>(h->o_ell_part), tiles, Kl, h->p<double>(h->o_ell_new), st);
+      if (rc) return rc;
+      if (h->allreduce(h->allreduce_user, h->p<double>(h->o_ell_new), Kl, st)) { set_error("allreduce hook failed"); return VCSMC_ERR_CUDA; }
+      w.ell_part = h->p<double>(h->o_ell_new);
+      w.tiles = 1;
+    }
+    w.ids_new = ids_cur; w.cnt_new = cnt_cur; w.ldf = h->p<double>(h->o_ldf);
+    w.lam_l = lam_l; w.lam_r = lam_r; w.b_l = a.b_l + k0; w.b_r = a.b_r + k0;
+    w.cum_l_prev = r > 0 ? h->p<double>(h->o_cum_l) + (int64_t)(r - 1) * K + k0 : nullptr;
+    w.cum_r_prev = r > 0 ? h->p<double>(h->o_cum_r) + (int64_t)(r - 1) * K + k0 : nullptr;
+    w.cum_l = h->p<double>(h->o_cum_l) + (int64_t)r * K + k0;
+    w.cum_r = h->p<double>(h->o_cum_r) + (int64_t)r * K + k0;
+    w.ll_tilde = ll_tilde; w.ell_node = ell_node;
+    w.lw = h->p<double>(h->o_lw) + (int64_t)r * K + k0;
+    w.LL = h->p<double>(h->o_LL) + (int64_t)r * K + k0;
+    w.vminus = h->p<int32_t>(h->o_vminus) + k0;
+    w.q = 1.0 / ((double)n * (double)(n - 1) / 2.0);
+    w.e_off = N + (int64_t)r * K + k0;
+    w.qlog = nullptr;
+    rc = launch_step_weights(w, st);
+    if (rc) return rc;
+
+    if (G > 1) {
+      RecArgs ra;
+      ra.n = n; ra.rank = h->rank; ra.Kl = Kl; ra.k0 = k0; ra.K = K; ra.stride = h->rec_stride; ra.rec = h->p<char>(h->o_rec);
+      ra.lw = h->p<double>(h->o_lw) + (int64_t)r * K; ra.LL = h->p<double>(h->o_LL) + (int64_t)r * K;
+      ra.ell = ell_node + N + (int64_t)r * K; ra.b_l = a.b_l; ra.b_r = a.b_r;
+      ra.cum_l = h->p<double>(h->o_cum_l) + (int64_t)r * K; ra.cum_r = h->p<double>(h->o_cum_r) + (int64_t)r * K;
+      ra.t2 = a.t2; ra.lref = a.lref; ra.rref = a.rref; ra.nleaf = a.nleaf; ra.vminus = h->p<int32_t>(h->o_vminus);
+      ra.rempos = a.rempos;
+      lz_pack_kernel<<<(unsigned)((Kl + 127) / 128), 128, 0, st>>>(ra);
+      VCSMC_LAUNCH_CHECK("lz_pack_kernel");
+      if (h->comm(h->comm_user, VCSMC_COMM_ALLGATHER, ra.rec, h->rec_stride, st)) { set_error("comm hook failed (all-gather)"); return VCSMC_ERR_CUDA; }
+      lz_unpack_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(ra);
+      VCSMC_LAUNCH_CHECK("lz_unpack_kernel");
+    }
+    // log-sum-exp + CDF of this step's weights over ALL particles (every rank: same input, same fixed order)
+    rc = launch_resample_cdf(h->p<double>(h->o_lw) + (int64_t)r * K, K, h->p<double>(h->o_cdf), h->p<double>(h->o_stats) + r * 4, st);
+    if (rc) return rc;
+  }
+  if (G > 1) {
+    lz_lltilde_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(K, N, h->p<double>(h->o_LL), h->p<int32_t>(h->o_anc), ll_tilde);
+    VCSMC_LAUNCH_CHECK("lz_lltilde_kernel");
+  }
+  return launch_finalize(N, K, h->p<double>(h->o_stats), h->p<double>(h->o_LL) + (int64_t)(N - 2) * K, h->p<double>(h->o_b_l),
+                         h->p<double>(h->o_b_r), lam_l, lam_r, log_double_factorial_host(2 * N - 3), h->p<double>(h->o_llR),
+                         h->p<double>(h->o_elbo), h->p<double>(h->o_logz), h->p<double>(h->o_ess), st);
+}
+
+}  // namespace vcsmc

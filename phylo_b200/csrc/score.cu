@@ -1,0 +1,475 @@
+// Likelihood-only scoring of a rank event, materialisation of the survivors, and peer pulls.
+//
+// With >= ~1000 sites the weights of a rank event spread over hundreds of nats, the ESS is ~1 and almost every
+// node the eager forward writes (32 B per particle.site) is dead one resampling later.  The lazy forward therefore
+// splits broadcast_conditional_likelihood_K + compute_forest_posterior (vcsmc.py:180-188, :231-245) in two:
+//
+//   merge_score_kernel   ell[k] = sum_s log(pi . ((L_l P_l) * (L_r P_r))[s]) for EVERY particle, nothing stored.
+//                        The site likelihood is a bilinear form of the two children,
+//                            x[s] = sum_{j,m} L_a[s][j] L_b[s][m] M_k[j][m],   M_k[j][m] = sum_i pi_i P_a[j][i] P_b[m][i],
+//                        so a group of particles that share a child pair (a, b) shares the 16 site products
+//                        O[s] = L_a[s] (x) L_b[s] (registers) and each particle costs 16 DFMA per site (general Q) or
+//                        4 DFMA (JC: x = a1 sa sb + a2 sa pb + a3 pa sb + a4 pab) instead of ~41.  FP64-pipe bound,
+//                        children come from L2.
+//   materialise_kernel   after the next resampling, only particles that were drawn as an ancestor get their node
+//                        written (the plain merge formula; 32 B per site, streaming).
+//   pull_kernel          particle sharding: a rank that drew a remote ancestor copies the nodes it lacks straight out
+//                        of the owner's pool over NVLink (peer pointers, 256-bit loads), one CTA per (node, site tile).
+#include <stdlib.h>
+
+#include "launch.h"
+#include "merge_device.cuh"
+
+namespace vcsmc {
+namespace {
+
+constexpr int kRScore = 32;  // particles per scoring group
+
+struct ScoreArgs {
+  const uint8_t* codes;
+  int64_t codes_stride;
+  const double* pool;
+  int64_t slot_sites;
+  const int32_t* lsrc;
+  const int32_t* rsrc;
+  const int32_t* order;  // sorted visiting order (null: identity)
+  const double* P;       // [K][32]
+  const double* pi;
+  int64_t K;
+  int n_sites;
+  int tiles;
+  int tiles_per_item;
+  int n_chunks;
+  int R;
+  double* ell_part;  // [K][n_chunks][kWarps]
+};
+
+constexpr int kScoreSmemBytes = kRScore * 16 * 8 + kRScore * kTileThreads * (8 + 4);
+
+// site products of one child pair for the SPT sites of a thread: general Q -> the 16 products L_a[i] L_b[m];
+// JC -> (sa sb, sa (pi.L_b), (pi.L_a) sb, sum_i pi_i L_a[i] L_b[i]).  Sites past the end get zeros.
+struct ChildSpace {
+  const uint8_t* codes;
+  int64_t codes_stride;
+  const double* pool;
+  int64_t slot_sites;
+  int n_sites;
+};
+
+template <bool JC, int SPT, int NC>
+__device__ __forceinline__ void site_products(const ChildSpace& a, int ca, int cb, int sbase, const double (&pi)[4],
+                                              double (&C)[SPT][NC]) {
+  const ChildRef ra = child_ref(ca, a.codes, a.codes_stride, a.pool, a.slot_sites);
+  const ChildRef rb = child_ref(cb, a.codes, a.codes_stride, a.pool, a.slot_sites);
+#pragma unroll
+  for (int q = 0; q < SPT; ++q) {
+    const int s = sbase + q * kTileThreads;
+    if (s < a.n_sites) {
+      const d4 La = load_child(ra, s), Lb = load_child(rb, s);
+      if (JC) {
+        const double sa = (La.v[0] + La.v[1]) + (La.v[2] + La.v[3]);
+        const double sb = (Lb.v[0] + Lb.v[1]) + (Lb.v[2] + Lb.v[3]);
+        double qa = pi[0] * La.v[0], qb = pi[0] * Lb.v[0], qab = pi[0] * La.v[0] * Lb.v[0];
+#pragma unroll
+        for (int i = 1; i < 4; ++i) {
+          qa = fma(pi[i], La.v[i], qa);
+          qb = fma(pi[i], Lb.v[i], qb);
+          qab = fma(pi[i] * La.v[i], Lb.v[i], qab);
+        }
+        C[q][0] = sa * sb;
+        C[q][1] = sa * qb;
+        C[q][2] = qa * sb;
+        C[q][3] = qab;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int m = 0; m < 4; ++m) C[q][(i * 4 + m) % NC] = La.v[i] * Lb.v[m];
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) C[q][c] = 0.0;
+    }
+  }
+}
+
+// One tile of SPT*256 sites for the nj particles of a group.  The running product of the site likelihoods of
+// (thread, particle) is kept as (mantissa product, BIASED exponent sum) in shared memory.  The split is three integer
+// ops per site; a likelihood that is not a positive normal number (0, subnormal, inf, NaN, negative) poisons the
+// mantissa product with NaN and the particle is re-evaluated with one log per site afterwards (never on sane inputs).
+// Sites past the end of the alignment have zero site products and x0 = 1, i.e. x = 1.
+// NP particles (that share the current child pair) against the SPT sites of this thread: NP*SPT*2 independent FMA
+// chains (each site likelihood is accumulated in an even and an odd half) -- the FP64 pipe has a long dependent-issue
+// latency and only 4 warps per scheduler fit, so the instruction-level parallelism has to come from here.
+template <bool JC, int SPT, int NP>
+__device__ __forceinline__ void score_particles(int j, const double (&C)[SPT][JC ? 4 : 16], const double (&x0)[SPT], bool renorm,
+                                                const double* sC, double* my_prod, int* my_exp) {
+  constexpr int NC = JC ? 4 : 16;
+  double xe[NP][SPT], xo[NP][SPT];
+#pragma unroll
+  for (int p = 0; p < NP; ++p)
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) {
+      xe[p][q] = x0[q];
+      xo[p][q] = 0.0;
+    }
+#pragma unroll
+  for (int c = 0; c < NC; c += 2) {
+    double2 m[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) m[p] = *reinterpret_cast<const double2*>(sC + (j + p) * 16 + c);
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+#pragma unroll
+      for (int q = 0; q < SPT; ++q) {
+        xe[p][q] = fma(m[p].x, C[q][c], xe[p][q]);
+        xo[p][q] = fma(m[p].y, C[q][c + 1], xo[p][q]);
+      }
+  }
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    double pr = my_prod[(j + p) * kTileThreads];
+    int ex = my_exp[(j + p) * kTileThreads];
+    bool odd = false;
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) {
+      const double x = xe[p][q] + xo[p][q];
+      const int hi = __double2hiint(x);
+      const unsigned e = (unsigned)hi >> 20;  // biased exponent (sign bit included: negative values are "odd")
+      odd |= (e - 1u) >= 0x7feu;
+      ex += (int)e;
+      pr *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+    }
+    if (odd) pr = __longlong_as_double(0x7ff8000000000000ll);
+    if (renorm) {  // keep the mantissa product far from 2^1024 (NaN stays NaN)
+      const int hi = __double2hiint(pr);
+      ex += (int)(((unsigned)hi >> 20) & 0x7ffu) - 1023;
+      if ((((unsigned)hi >> 20) & 0x7ffu) != 0x7ffu) pr = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(pr));
+    }
+    my_prod[(j + p) * kTileThreads] = pr;
+    my_exp[(j + p) * kTileThreads] = ex;
+  }
+}
+
+// One tile of SPT*256 sites for the nj particles of a group.  The running product of the site likelihoods of
+// (thread, particle) is kept as (mantissa product, BIASED exponent sum) in shared memory.  The split is three integer
+// ops per site; a likelihood that is not a positive normal number (0, subnormal, inf, NaN, negative) poisons the
+// mantissa product with NaN and the particle is re-evaluated with one log per site afterwards (never on sane inputs).
+// Sites past the end of the alignment have zero site products and x0 = 1, i.e. x = 1.
+template <bool JC, int SPT>
+__device__ __forceinline__ void score_tile(const ChildSpace& a, int nj, int sbase, bool renorm, const double (&pi)[4],
+                                           const int* s_a, const int* s_b, const double* sC, double* my_prod, int* my_exp) {
+  constexpr int NC = JC ? 4 : 16;
+  int pa = kNone, pb = kNone;
+  double C[SPT][NC];
+  double x0[SPT];
+#pragma unroll
+  for (int q = 0; q < SPT; ++q) x0[q] = (sbase + q * kTileThreads < a.n_sites) ? 0.0 : 1.0;
+  int j = 0;
+  while (j < nj) {
+    const int ca = s_a[j], cb = s_b[j];
+    if (ca != pa || cb != pb) {
+      site_products<JC, SPT, NC>(a, ca, cb, sbase, pi, C);
+      pa = ca;
+      pb = cb;
+    }
+    if (j + 1 < nj && s_a[j + 1] == ca && s_b[j + 1] == cb) {
+      score_particles<JC, SPT, 2>(j, C, x0, renorm, sC, my_prod, my_exp);
+      j += 2;
+    } else {
+      score_particles<JC, SPT, 1>(j, C, x0, renorm, sC, my_prod, my_exp);
+      j += 1;
+    }
+  }
+}
+
+// exact fallback for a particle whose product was poisoned: one log per site
+template <bool JC>
+__device__ __noinline__ double score_slow(ChildSpace a, int ca, int cb, const double* cj, int s_begin, int s_end, double pi0,
+                                          double pi1, double pi2, double pi3) {
+  constexpr int NC = JC ? 4 : 16;
+  const double pi[4] = {pi0, pi1, pi2, pi3};
+  double acc = 0.0;
+  double C[1][NC], m[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) m[c] = cj[c];
+  for (int s = s_begin + threadIdx.x; s < s_end; s += kTileThreads) {
+    site_products<JC, 1, NC>(a, ca, cb, s, pi, C);
+    double x = m[0] * C[0][0];
+#pragma unroll
+    for (int c = 1; c < NC; ++c) x = fma(m[c], C[0][c], x);
+    acc += log(x);
+  }
+  return acc;
+}
+
+template <bool JC, int SPT>
+__global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_score_kernel(const ScoreArgs a) {
+  constexpr int NC = JC ? 4 : 16;  // coefficients per particle == site products per site
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sC = reinterpret_cast<double*>(smem_raw);                    // [R][16] per-particle coefficients
+  double* s_prod = sC + kRScore * 16;                                   // [R][256] running mantissa products
+  int* s_exp = reinterpret_cast<int*>(s_prod + kRScore * kTileThreads); // [R][256] running (biased) exponent sums
+  __shared__ int s_k[kRScore], s_a[kRScore], s_b[kRScore];
+  __shared__ unsigned s_odd;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int R = a.R;
+  const int64_t total = ((a.K + R - 1) / R) * a.n_chunks;
+  double pi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
+  double* my_prod = s_prod + tid;
+  int* my_exp = s_exp + tid;
+  const ChildSpace cs = {a.codes, a.codes_stride, a.pool, a.slot_sites, a.n_sites};
+
+  for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    const int64_t g = w / a.n_chunks;
+    const int tc = (int)(w - g * a.n_chunks);
+    const int64_t j0 = g * R;
+    const int nj = (int)min((int64_t)R, a.K - j0);
+    __syncthreads();
+    if (tid == 0) s_odd = 0u;
+    if (tid < nj) {
+      const int k = a.order ? a.order[j0 + tid] : (int)(j0 + tid);
+      const int ls = a.lsrc[k], rs = a.rsrc[k];
+      const bool sw = ls > rs;  // canonical child order a <= b; the swap flag rides in the sign of k
+      s_a[tid] = sw ? rs : ls;
+      s_b[tid] = sw ? ls : rs;
+      s_k[tid] = sw ? ~k : k;
+    }
+    __syncthreads();
+    if (JC) {
+      if (tid < nj) {
+        const int kk = s_k[tid];
+        const bool sw = kk < 0;
+        const int64_t k = sw ? ~kk : kk;
+        const double* Pa = a.P + k * 32 + (sw ? 16 : 0);
+        const double* Pb = a.P + k * 32 + (sw ? 0 : 16);
+        const double oa = __ldg(Pa + 1), da = __ldg(Pa) - oa, ob = __ldg(Pb + 1), db = __ldg(Pb) - ob;
+        sC[tid * 16 + 0] = oa * ob * ((pi[0] + pi[1]) + (pi[2] + pi[3]));
+        sC[tid * 16 + 1] = oa * db;
+        sC[tid * 16 + 2] = da * ob;
+        sC[tid * 16 + 3] = da * db;
+      }
+    } else {
+      for (int e = tid; e < nj * 16; e += kTileThreads) {
+        const int j = e >> 4, ai = (e >> 2) & 3, bi = e & 3;
+        const int kk = s_k[j];
+        const bool sw = kk < 0;
+        const int64_t k = sw ? ~kk : kk;
+        const double* Pa = a.P + k * 32 + (sw ? 16 : 0) + ai * 4;
+        const double* Pb = a.P + k * 32 + (sw ? 0 : 16) + bi * 4;
+        double m = pi[0] * __ldg(Pa) * __ldg(Pb);
+#pragma unroll
+        for (int i = 1; i < 4; ++i) m = fma(pi[i] * __ldg(Pa + i), __ldg(Pb + i), m);
+        sC[j * 16 + ai * 4 + bi] = m;
+      }
+    }
+    for (int j = 0; j < nj; ++j) {
+      my_prod[j * kTileThreads] = 1.0;
+      my_exp[j * kTileThreads] = 0;
+    }
+    __syncthreads();
+
+    const int t_begin = tc * a.tiles_per_item;
+    const int t_end = min(a.tiles, t_begin + a.tiles_per_item);
+    for (int t = t_begin; t < t_end; ++t) {
+      const int sbase = t * (kTileThreads * SPT) + tid;
+      const bool renorm = ((t - t_begin) & 127) == 127;
+      score_tile<JC, SPT>(cs, nj, sbase, renorm, pi, s_a, s_b, sC, my_prod, my_exp);
+    }
+    // one log per (thread, particle): sum_s log x_s = log(prod mantissas) + ln2 * sum (exponents - bias)
+    const int bias = 1023 * SPT * (t_end - t_begin);
+    unsigned odd_mask = 0u;
+    for (int j = 0; j < nj; ++j) {
+      const double pr = my_prod[j * kTileThreads];
+      if (pr != pr) odd_mask |= 1u << j;
+    }
+    if (odd_mask) atomicOr(&s_odd, odd_mask);
+    __syncthreads();
+    const unsigned odd_all = s_odd;
+    for (int j = 0; j < nj; ++j) {
+      double acc;
+      if (odd_all >> j & 1u) {
+        // some likelihood of this particle is 0 / subnormal / not finite: one log per site, like the reference
+        acc = score_slow<JC>(cs, s_a[j], s_b[j], sC + j * 16, t_begin * (kTileThreads * SPT),
+                             min(a.n_sites, t_end * (kTileThreads * SPT)), pi[0], pi[1], pi[2], pi[3]);
+      } else {
+        const double ex = (double)(my_exp[j * kTileThreads] - bias);
+        acc = fma(ex, 6.93147180369123816490e-01, fma(ex, 1.90821492927058770002e-10, log(my_prod[j * kTileThreads])));  // ln2 hi + lo
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const int kk = s_k[j];
+        const int64_t k = kk < 0 ? ~kk : kk;
+        a.ell_part[(k * a.n_chunks + tc) * kWarps + wid] = acc;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// survivors: the plain merge, stored
+// ---------------------------------------------------------------------------------------------
+struct MatArgs {
+  const uint8_t* codes;
+  int64_t codes_stride;
+  double* pool;
+  int64_t slot_sites;
+  const int32_t* lsrc;   // [Kl] child slots of the event being materialised
+  const int32_t* rsrc;
+  const int32_t* list;   // local particle indices to materialise
+  const int32_t* count;  // device: number of list entries
+  const int32_t* loc;    // node -> local slot
+  int64_t e_base;        // node index of local particle 0 of that event
+  const double* P;       // [Kl][32] of that event
+  int n_sites;
+  int tiles;
+};
+
+constexpr int kMatSpt = 2;
+
+template <bool JC>
+__global__ void __launch_bounds__(kTileThreads) materialise_kernel(const MatArgs a) {
+  const int64_t total = (int64_t)(*a.count) * a.tiles;
+  for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    const int64_t j = w / a.tiles;
+    const int t = (int)(w - j * a.tiles);
+    const int kl = a.list[j];
+    const int ds = a.loc[a.e_base + kl];
+    if (ds < 0) continue;  // pool exhausted (reported through the status word)
+    const ChildRef ra = child_ref(a.lsrc[kl], a.codes, a.codes_stride, a.pool, a.slot_sites);
+    const ChildRef rb = child_ref(a.rsrc[kl], a.codes, a.codes_stride, a.pool, a.slot_sites);
+    Trans<JC> Pl, Pr;
+    Pl.load(a.P + (int64_t)kl * 32);
+    Pr.load(a.P + (int64_t)kl * 32 + 16);
+    double* out = a.pool + (int64_t)ds * a.slot_sites * 4;
+#pragma unroll
+    for (int q = 0; q < kMatSpt; ++q) {
+      const int s = t * (kTileThreads * kMatSpt) + q * kTileThreads + threadIdx.x;
+      if (s < a.n_sites) {
+        const d4 lp = Pl.apply(load_child(ra, s)), rp = Pr.apply(load_child(rb, s));
+        d4 nw;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) nw.v[i] = lp.v[i] * rp.v[i];
+        st_site(out + (int64_t)s * 4, nw);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// particle sharding: copy missing nodes out of the owner's pool (peer memory over NVLink)
+// ---------------------------------------------------------------------------------------------
+struct PullArgs {
+  const int32_t* fetch_e;    // node indices to fetch
+  const int32_t* fetch_src;  // rank that holds a copy
+  const int32_t* count;      // device: number of entries
+  const int32_t* loc;        // local node -> slot (destination, assigned by the allocator)
+  double* pool;
+  int64_t slot_sites;
+  int n_sites;
+  int tiles;
+  const int32_t* peer_loc[kMaxPeers];
+  const double* peer_pool[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(kTileThreads) pull_kernel(const PullArgs a) {
+  const int64_t total = (int64_t)(*a.count) * a.tiles;
+  for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    const int64_t j = w / a.tiles;
+    const int t = (int)(w - j * a.tiles);
+    const int e = a.fetch_e[j], g = a.fetch_src[j];
+    const int ds = a.loc[e];
+    const int ss = a.peer_loc[g][e];
+    if (ds < 0 || ss < 0) continue;
+    const double* src = a.peer_pool[g] + (int64_t)ss * a.slot_sites * 4;
+    double* dst = a.pool + (int64_t)ds * a.slot_sites * 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int s = t * (kTileThreads * 4) + q * kTileThreads + threadIdx.x;
+      if (s < a.n_sites) st_site(dst + (int64_t)s * 4, ld_site(src + (int64_t)s * 4));
+    }
+  }
+}
+
+constexpr int64_t kScoreItems = 148 * 8;  // work items wanted per launch
+
+}  // namespace
+
+int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double* pool, int64_t slot_sites,
+                       const int32_t* lsrc, const int32_t* rsrc, const int32_t* order, const double* P, const double* pi,
+                       int64_t K, int n_sites, int jc, double* ell_part, int* n_parts, cudaStream_t st) {
+  if (n_parts) *n_parts = 0;
+  if (K <= 0 || n_sites <= 0) return VCSMC_OK;
+  static int spt_general = 0;
+  if (spt_general == 0) {
+    const char* e = getenv("VCSMC_SCORE_SPT");  // tuning knob: sites per thread of the general-Q scoring kernel
+    spt_general = e ? atoi(e) : 2;
+    if (spt_general != 2 && spt_general != 4) spt_general = 2;
+    VCSMC_CUDA(cudaFuncSetAttribute(merge_score_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoreSmemBytes));
+    VCSMC_CUDA(cudaFuncSetAttribute(merge_score_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoreSmemBytes));
+    VCSMC_CUDA(cudaFuncSetAttribute(merge_score_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoreSmemBytes));
+  }
+  const int spt = jc ? 4 : spt_general;
+  ScoreArgs a;
+  a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.slot_sites = slot_sites; a.lsrc = lsrc; a.rsrc = rsrc;
+  a.order = order; a.P = P; a.pi = pi; a.K = K; a.n_sites = n_sites; a.ell_part = ell_part;
+  a.tiles = (n_sites + kTileThreads * spt - 1) / (kTileThreads * spt);
+  // groups as large as the machine fill allows (shared children and site products are amortised over the group)
+  int64_t R = (K * a.tiles) / kScoreItems;
+  if (R < 1) R = 1;
+  if (R > kRScore) R = kRScore;
+  a.R = (int)R;
+  const int64_t groups = (K + R - 1) / R;
+  int64_t nc = (kScoreItems + groups - 1) / groups;  // split a group's tiles only when the groups cannot fill the SMs
+  if (nc < 1) nc = 1;
+  if (nc > a.tiles) nc = a.tiles;
+  a.tiles_per_item = (int)((a.tiles + nc - 1) / nc);
+  a.n_chunks = (a.tiles + a.tiles_per_item - 1) / a.tiles_per_item;
+  if (n_parts) *n_parts = a.n_chunks * kWarps;
+  const int64_t total = groups * a.n_chunks;
+  const int64_t cap = 148 * 2 * 8;
+  const unsigned grid = (unsigned)(total < cap ? total : cap);
+  if (jc) merge_score_kernel<true, 4><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
+  else if (spt == 4) merge_score_kernel<false, 4><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
+  else merge_score_kernel<false, 2><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
+  VCSMC_LAUNCH_CHECK("merge_score_kernel");
+  return VCSMC_OK;
+}
+
+int launch_materialise(const uint8_t* codes, int64_t codes_stride, double* pool, int64_t slot_sites, const int32_t* lsrc,
+                       const int32_t* rsrc, const int32_t* list, const int32_t* count, int64_t max_count, const int32_t* loc,
+                       int64_t e_base, const double* P, int n_sites, int jc, cudaStream_t st) {
+  if (max_count <= 0 || n_sites <= 0) return VCSMC_OK;
+  MatArgs a;
+  a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.slot_sites = slot_sites; a.lsrc = lsrc; a.rsrc = rsrc;
+  a.list = list; a.count = count; a.loc = loc; a.e_base = e_base; a.P = P; a.n_sites = n_sites;
+  a.tiles = (n_sites + kTileThreads * kMatSpt - 1) / (kTileThreads * kMatSpt);
+  const int64_t total = max_count * a.tiles, cap = 148 * 8;
+  const unsigned grid = (unsigned)(total < cap ? total : cap);
+  if (jc) materialise_kernel<true><<<grid, kTileThreads, 0, st>>>(a);
+  else materialise_kernel<false><<<grid, kTileThreads, 0, st>>>(a);
+  VCSMC_LAUNCH_CHECK("materialise_kernel");
+  return VCSMC_OK;
+}
+
+int launch_pull(const int32_t* fetch_e, const int32_t* fetch_src, const int32_t* count, int64_t max_count, const int32_t* loc,
+                double* pool, int64_t slot_sites, int n_sites, int world, const int32_t* const* peer_loc,
+                const double* const* peer_pool, cudaStream_t st) {
+  if (max_count <= 0 || n_sites <= 0) return VCSMC_OK;
+  PullArgs a;
+  a.fetch_e = fetch_e; a.fetch_src = fetch_src; a.count = count; a.loc = loc; a.pool = pool; a.slot_sites = slot_sites;
+  a.n_sites = n_sites; a.tiles = (n_sites + kTileThreads * 4 - 1) / (kTileThreads * 4);
+  for (int g = 0; g < kMaxPeers; ++g) {
+    a.peer_loc[g] = g < world ? peer_loc[g] : nullptr;
+    a.peer_pool[g] = g < world ? peer_pool[g] : nullptr;
+  }
+  const int64_t total = max_count * a.tiles, cap = 148 * 8;
+  const unsigned grid = (unsigned)(total < cap ? total : cap);
+  pull_kernel<<<grid, kTileThreads, 0, st>>>(a);
+  VCSMC_LAUNCH_CHECK("pull_kernel");
+  return VCSMC_OK;
+}
+
+}  // namespace vcsmc

@@ -18,23 +18,10 @@
 #include <new>
 #include <vector>
 
-#include "launch.h"
-#include "smc_device.cuh"
+#include "sweep_state.h"
 
 namespace vcsmc {
 namespace {
-
-inline int64_t align_up(int64_t x, int64_t a = 256) { return (x + a - 1) / a * a; }
-
-struct Layout {
-  int64_t off = 0;
-  template <typename T>
-  int64_t take(int64_t count) {
-    const int64_t o = off;
-    off = align_up(off + count * (int64_t)sizeof(T));
-    return o;
-  }
-};
 
 // ---------------------------------------------------------------------------------------------
 // forward kernels
@@ -226,29 +213,6 @@ __global__ void __launch_bounds__(1024) gc_alloc_kernel(const int32_t* __restric
   }
 }
 
-struct WeightArgs {
-  int r, n, N, tiles;
-  int64_t K;
-  const double* ell_part;
-  const int32_t* ids_new;
-  const int32_t* cnt_new;
-  const double* ldf;
-  const double* lam_l;
-  const double* lam_r;
-  const double* b_l;
-  const double* b_r;
-  const double* cum_l_prev;
-  const double* cum_r_prev;
-  double* cum_l;
-  double* cum_r;
-  const double* ll_tilde;
-  double* ell_node;
-  double* lw;
-  double* LL;
-  int32_t* vminus;
-  double q;
-  const double* qlog;  // VNCSMC: per-particle log-probability of the chosen option (vncsmc.py:315-316), else null
-};
 
 // compute_forest_posterior with cached per-node scalars + branch priors + v^- + weight (vcsmc.py:376-395)
 __global__ void step_weights_kernel(const WeightArgs a) {
@@ -257,7 +221,7 @@ __global__ void step_weights_kernel(const WeightArgs a) {
   const int N = a.N, n = a.n, r = a.r;
   double ell = 0.0;
   for (int t = 0; t < a.tiles; ++t) ell += a.ell_part[k * a.tiles + t];
-  a.ell_node[N + (int64_t)r * a.K + k] = ell;
+  a.ell_node[a.e_off + k] = ell;
   double F = 0.0, topo = 0.0;
   int vm = 0;
   for (int p = 0; p < n - 2; ++p) {
@@ -506,90 +470,50 @@ __global__ void zero_f64_kernel(double* p, int64_t n) {
 }  // namespace
 }  // namespace vcsmc
 
+
+namespace vcsmc {
+
+// Sorting the particles by child pair only pays when groups of several particles are formed (see pick_group in
+// merge.cu: R = K * tiles / 4736); below that the visiting order is the identity and ~9 launches per event are saved.
+bool use_sorted_order(int64_t K, int n_sites) {
+  const int64_t tiles = (n_sites + 511) / 512;
+  return K * tiles >= 2 * 148 * 32;
+}
+
+double log_double_factorial_host(int m) {  // vcsmc.py:30-57
+  double r = 0.0;
+  for (int j = m; j >= 2; j -= 2) r += log((double)j);
+  return r;
+}
+
+
+int launch_leaf_ell(const uint8_t* codes, int64_t stride, int N, int S, const double* pi, double* ell_node, cudaStream_t st) {
+  leaf_ell_kernel<<<N, 256, 0, st>>>(codes, stride, S, pi, ell_node);
+  VCSMC_LAUNCH_CHECK("leaf_ell_kernel");
+  return VCSMC_OK;
+}
+
+int launch_step_weights(const WeightArgs& w, cudaStream_t st) {
+  if (w.K <= 0) return VCSMC_OK;
+  step_weights_kernel<<<(unsigned)((w.K + 127) / 128), 128, 0, st>>>(w);
+  VCSMC_LAUNCH_CHECK("step_weights_kernel");
+  return VCSMC_OK;
+}
+
+int launch_finalize(int N, int64_t K, const double* stats, const double* LL_last, const double* b_l, const double* b_r,
+                    const double* lam_l, const double* lam_r, double ldf_root, double* llR, double* elbo, double* logz,
+                    double* ess, cudaStream_t st) {
+  finalize_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(N, K, stats, LL_last, b_l, b_r, lam_l, lam_r, ldf_root, llR, elbo, logz, ess);
+  VCSMC_LAUNCH_CHECK("finalize_kernel");
+  return VCSMC_OK;
+}
+
+}  // namespace vcsmc
+
 // ---------------------------------------------------------------------------------------------
 // host object
 // ---------------------------------------------------------------------------------------------
 using namespace vcsmc;
-
-struct vcsmc_sweep {
-  int N, S, jc, keep;
-  int M = 0;  // VNCSMC sub-samples (0 = VCSMC)
-  int64_t K;
-  char* ws;
-  int64_t ws_bytes;
-  // modes
-  bool fwd_gc;        // forward on the garbage-collected slot pool
-  bool retain;        // backward reuses the forward's nodes (no recompute)
-  int64_t pool_slots; // GC mode capacity
-  int chunk_sites;    // backward site-chunk size (== S when retain)
-  int tiles_max;
-  // offsets into ws
-  int64_t o_anc, o_lref, o_rref, o_nleaf, o_rempos, o_b_l, o_b_r, o_t2, o_cum_l, o_cum_r, o_lw, o_LL, o_lltilde, o_llR,
-      o_vminus, o_ell_node, o_stats, o_logz, o_ess, o_elbo, o_status, o_P, o_ids[2], o_cnt[2], o_slot[2], o_cdf,
-      o_u_pair, o_u_bl, o_u_br, o_u_res, o_ell_part, o_ell_new, o_lsrc, o_rsrc, o_dst, o_ldf, o_flags, o_childsum[2],
-      o_Dacc[2], o_cnew, o_consumed, o_bsrc_l, o_bsrc_r, o_bsrc_g, o_bdst, o_dP, o_dpi_each, o_dQ_acc, o_dQ_each, o_dt,
-      o_suf_l, o_suf_r, o_gB_l, o_gB_r, o_cleaf, o_pool, o_keys_in, o_keys_out, o_vals_in, o_order, o_count,
-      o_sort_temp, o_order_bwd, o_count_bwd, o_order_rec, o_count_rec, o_act_bwd, o_act_rec, o_cslot,
-      o_inh_ids, o_inh_cnt, o_inh_slot, o_pot, o_choice, o_qlog, o_u_cat, o_rows_all, o_nact, o_nbase, o_v_lsrc, o_v_rsrc,
-      o_v_coef, o_v_t2, o_v_P, o_v_dP, o_v_dt, o_v_dQ, o_v_dpi, o_v_order, o_v_keys_in, o_v_keys_out, o_v_vals, o_v_count, o_v_temp, o_v_keep, o_v_index, o_v_scan;
-  size_t v_scan = 0;
-  std::vector<int64_t> pot_off;  // per rank event, offset (doubles) into the potentials
-  int64_t v_batch = 0;           // virtual events per batch in the nested reverse sweep
-  size_t v_temp = 0;
-  const double* x_look_bl = nullptr;
-  const double* x_look_br = nullptr;
-  const double* x_cat = nullptr;
-  size_t sort_temp = 0;
-  int64_t pool_bytes;
-  std::vector<int64_t> rem_off;  // per step offset (bytes) into rempos
-  // uniform source
-  const float* x_pair = nullptr;
-  const double* x_bl = nullptr;
-  const double* x_br = nullptr;
-  const double* x_res = nullptr;
-  uint64_t seed = 0;
-  bool use_seed = true;
-  // hook
-  vcsmc_allreduce_fn allreduce = nullptr;
-  void* allreduce_user = nullptr;
-  double scalar_share = 1.0;
-  int skip_zero = 1;
-  int max_chunk_sites = 0;  // testing aid: cap the backward site chunk (0 = as large as memory allows)
-  // model pointers of the last forward (caller keeps them alive until backward)
-  const uint8_t* codes = nullptr;
-  const double* lam_l = nullptr;
-  const double* lam_r = nullptr;
-  const double* Q = nullptr;
-  const double* pi = nullptr;
-  bool forward_done = false;
-  // optional per-kernel timing of the merge launches (bench.py roofline): kind 0 = forward merge,
-  // 1 = recompute merge of the chunked backward, 2 = backward merge
-  bool profile = false;
-  std::vector<cudaEvent_t> ev;
-  std::vector<int> ev_kind;
-  size_t ev_used = 0;
-  int prof_begin(int kind, cudaStream_t st) {
-    if (!profile) return 0;
-    if (ev_used + 2 > ev.size()) {
-      for (int i = 0; i < 256; ++i) {
-        cudaEvent_t e;
-        if (cudaEventCreate(&e) != cudaSuccess) return -1;
-        ev.push_back(e);
-      }
-    }
-    ev_kind.push_back(kind);
-    return cudaEventRecord(ev[ev_used++], st) == cudaSuccess ? 0 : -1;
-  }
-  void prof_end(cudaStream_t st) {
-    if (profile) cudaEventRecord(ev[ev_used++], st);
-  }
-  ~vcsmc_sweep() {
-    for (auto e : ev) cudaEventDestroy(e);
-  }
-
-  template <typename T>
-  T* p(int64_t off) const { return reinterpret_cast<T*>(ws + off); }
-};
 
 namespace {
 
@@ -662,6 +586,23 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_choice = L.take<int32_t>(E);
     h->o_qlog = L.take<double>(K);
     h->o_u_cat = L.take<double>(K);
+  }
+  if (h->M == 0) {
+    // lazy forward / particle sharding (lazy.cu): node -> local slot map, survivor and fetch lists, inherited rows,
+    // the per-event record that is all-gathered across ranks
+    h->o_loc = L.take<int32_t>(E);
+    h->o_pend = L.take<int32_t>(E);
+    h->o_surv = L.take<int32_t>(K);
+    h->o_mat_list = L.take<int32_t>(K);
+    h->fetch_cap = K * (int64_t)N < E ? K * (int64_t)N : E;
+    h->o_fetch_e = L.take<int32_t>(h->fetch_cap);
+    h->o_fetch_src = L.take<int32_t>(h->fetch_cap);
+    h->o_counts = L.take<int32_t>(8);
+    h->o_lz_ids = L.take<int32_t>(K * N);
+    h->o_lz_cnt = L.take<int32_t>(K * N);
+    h->o_u_res_all = L.take<double>(K);
+    h->rec_stride = align_up((h->Kl > 0 ? h->Kl : K) * (int64_t)(72 + N), 16);
+    h->o_rec = L.take<char>(K * (int64_t)(72 + N) + 16 * kMaxPeers + 256);
   }
   h->o_keys_in = L.take<uint64_t>(K);
   h->o_keys_out = L.take<uint64_t>(K);
@@ -738,7 +679,7 @@ int decide_modes(vcsmc_sweep* h, int64_t tables, int64_t ws_bytes, bool report) 
   const int64_t full = (int64_t)(N - 1) * K * node_bytes;
   const int64_t avail = ws_bytes - tables;
   const int64_t need_retain = h->keep ? 2 * full : full;
-  if (avail >= need_retain) {
+  if (avail >= need_retain && h->world == 1 && !h->force_gc) {
     h->fwd_gc = false;
     h->retain = true;
     h->chunk_sites = S;
@@ -748,10 +689,10 @@ int decide_modes(vcsmc_sweep* h, int64_t tables, int64_t ws_bytes, bool report) 
     h->pool_bytes = need_retain;
     return VCSMC_OK;
   }
-  // GC forward: flags[P] + P slots
+  // GC forward: flags[P] + slot_id[P] + P slots
   h->fwd_gc = true;
   h->retain = false;
-  int64_t P = (avail - 4096) / (node_bytes + 4);
+  int64_t P = (avail - 8192) / (node_bytes + 8);
   const int64_t Pmax = (int64_t)(N - 1) * K;
   if (P > Pmax) P = Pmax;
   if (P < 2 * K) {
@@ -760,7 +701,8 @@ int decide_modes(vcsmc_sweep* h, int64_t tables, int64_t ws_bytes, bool report) 
   }
   h->pool_slots = P;
   h->o_flags = tables;
-  h->o_pool = align_up(tables + P * 4);
+  h->o_slot_id = align_up(tables + P * 4);
+  h->o_pool = align_up(h->o_slot_id + P * 4);
   h->pool_bytes = ws_bytes - h->o_pool;
   if (h->keep) {
     int64_t Sc = (h->pool_bytes / 2) / ((int64_t)(N - 1) * K * 32);
@@ -777,13 +719,6 @@ int decide_modes(vcsmc_sweep* h, int64_t tables, int64_t ws_bytes, bool report) 
   return VCSMC_OK;
 }
 
-// Sorting the particles by child pair only pays when groups of several particles are formed (see pick_group in
-// merge.cu: R = K * tiles / 4736); below that the visiting order is the identity and ~9 launches per event are saved.
-bool use_sorted_order(int64_t K, int n_sites) {
-  const int64_t tiles = (n_sites + 511) / 512;
-  return K * tiles >= 2 * 148 * 32;
-}
-
 int check_cfg(const vcsmc_sweep_config* c) {
   if (!c) { set_error("null config"); return VCSMC_ERR_ARG; }
   if (c->n_taxa < 2 || c->n_taxa > kMaxRoots) { set_error("n_taxa=%d out of range [2,%d]", c->n_taxa, kMaxRoots); return VCSMC_ERR_ARG; }
@@ -793,12 +728,6 @@ int check_cfg(const vcsmc_sweep_config* c) {
   if (c->n_sub > 0 && c->n_taxa > nested_max_roots()) { set_error("nested look-ahead supports at most %d taxa (got %d)", nested_max_roots(), c->n_taxa); return VCSMC_ERR_ARG; }
   if ((int64_t)(c->n_taxa - 1) * c->n_particles + c->n_taxa > 2147483000LL) { set_error("too many nodes for int32 references"); return VCSMC_ERR_ARG; }
   return VCSMC_OK;
-}
-
-double log_double_factorial_host(int m) {  // vcsmc.py:30-57
-  double r = 0.0;
-  for (int j = m; j >= 2; j -= 2) r += log((double)j);
-  return r;
 }
 
 }  // namespace
@@ -816,7 +745,7 @@ int vcsmc_sweep_query(const vcsmc_sweep_config* cfg, vcsmc_sweep_sizes* out) {
   out->retain_bytes = tables + (cfg->keep_for_backward ? 2 * full : full);
   const int64_t node = (int64_t)cfg->n_sites * 32;
   const int64_t K = cfg->n_particles;
-  int64_t gc_min = 4096 + 2 * K * (node + 4) + 256;
+  int64_t gc_min = 8192 + 2 * K * (node + 8) + 512;
   if (cfg->keep_for_backward) {
     const int64_t sc = cfg->n_sites < 256 ? cfg->n_sites : 256;
     const int64_t chunk_min = 2 * (int64_t)(cfg->n_taxa - 1) * K * 32 * sc + 4 * 2 * K + 8192;
@@ -837,6 +766,7 @@ int vcsmc_sweep_create(const vcsmc_sweep_config* cfg, void* workspace, vcsmc_swe
   h->N = cfg->n_taxa; h->S = cfg->n_sites; h->K = cfg->n_particles; h->jc = cfg->jc; h->keep = cfg->keep_for_backward;
   h->M = cfg->n_sub;
   h->ws = (char*)workspace; h->ws_bytes = cfg->workspace_bytes;
+  h->Kl = h->K; h->k0 = 0; h->peer_ws[0] = h->ws;
   const int64_t tables = plan(h);
   rc = decide_modes(h, tables, cfg->workspace_bytes, true);
   if (rc) { delete h; return rc; }
@@ -853,11 +783,40 @@ int vcsmc_sweep_set_allreduce(vcsmc_sweep_t* h, vcsmc_allreduce_fn fn, void* use
   return VCSMC_OK;
 }
 
+int vcsmc_sweep_set_comm(vcsmc_sweep_t* h, int rank, int world, vcsmc_comm_fn fn, void* user, void* const* peer_ws_host) {
+  if (!h) return VCSMC_ERR_ARG;
+  if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) { set_error("set_comm: rank %d / world %d out of range (max %d ranks)", rank, world, kMaxPeers); return VCSMC_ERR_ARG; }
+  if (h->M > 0 && world > 1) { set_error("particle sharding supports the VCSMC proposal only (n_sub == 0)"); return VCSMC_ERR_STATE; }
+  if (h->K % world != 0) { set_error("n_particles = %lld is not divisible by %d ranks", (long long)h->K, world); return VCSMC_ERR_ARG; }
+  if (world > 1 && (!fn || !peer_ws_host)) { set_error("set_comm: null hook / peer table"); return VCSMC_ERR_ARG; }
+  if (h->allreduce && world > 1) { set_error("site sharding (set_allreduce) and particle sharding (set_comm) are exclusive"); return VCSMC_ERR_STATE; }
+  h->rank = rank; h->world = world; h->comm = fn; h->comm_user = user;
+  h->Kl = h->K / world; h->k0 = h->Kl * rank;
+  for (int g = 0; g < kMaxPeers; ++g) h->peer_ws[g] = (world > 1 && g < world) ? (char*)peer_ws_host[g] : nullptr;
+  h->peer_ws[rank] = h->ws;
+  if (world > 1) h->lazy = 1;
+  h->forward_done = false;
+  const int64_t tables = plan(h);
+  return decide_modes(h, tables, h->ws_bytes, true);
+}
+
 int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value) {
   if (!h || !name) return VCSMC_ERR_ARG;
   if (!strcmp(name, "scalar_share")) h->scalar_share = value;
   else if (!strcmp(name, "skip_zero")) h->skip_zero = value != 0.0;
   else if (!strcmp(name, "max_chunk_sites")) h->max_chunk_sites = (int)value;
+  else if (!strcmp(name, "lazy")) {
+    if (value == 0.0 && h->world > 1) { set_error("particle sharding needs the lazy forward"); return VCSMC_ERR_STATE; }
+    h->lazy = value != 0.0;
+  }
+  else if (!strcmp(name, "force_gc")) {  // testing aid: garbage-collected pool + recompute backward even when every node would fit
+    h->force_gc = value != 0.0;
+    h->forward_done = false;
+    const int64_t tables = plan(h);
+    return decide_modes(h, tables, h->ws_bytes, true);
+  }
+  else if (!strcmp(name, "site_begin")) h->site_begin = (int)value;
+  else if (!strcmp(name, "site_end")) h->site_end = (int)value;
   else if (!strcmp(name, "profile")) { h->profile = value != 0.0; h->ev_used = 0; h->ev_kind.clear(); }
   else { set_error("unknown option %s", name); return VCSMC_ERR_ARG; }
   return VCSMC_OK;
@@ -895,6 +854,12 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
   const int64_t K = h->K;
   h->codes = codes; h->lam_l = lam_l; h->lam_r = lam_r; h->Q = Q; h->pi = pi;
   h->forward_done = false;
+  if (h->M == 0 && h->lazy) {
+    const int rc = sweep_forward_lazy(h, codes, lam_l, lam_r, Q, pi, st);
+    if (rc == VCSMC_OK) h->forward_done = true;
+    return rc;
+  }
+  if (h->world > 1) { set_error("particle sharding needs the lazy forward"); return VCSMC_ERR_STATE; }
 
   // status + log-double-factorial table (host -> device, tiny)
   VCSMC_CUDA(cudaMemsetAsync(h->p<int32_t>(h->o_status), 0, 8 * sizeof(int32_t), st));
@@ -1030,6 +995,7 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
     w.LL = h->p<double>(h->o_LL) + (int64_t)r * K;
     w.vminus = h->p<int32_t>(h->o_vminus);
     w.q = 1.0 / ((double)n * (double)(n - 1) / 2.0);
+    w.e_off = N + (int64_t)r * K;
     w.qlog = h->M > 0 ? h->p<double>(h->o_qlog) : nullptr;
     step_weights_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(w);
     VCSMC_LAUNCH_CHECK("step_weights_kernel");
@@ -1056,6 +1022,10 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   const int N = h->N, S = h->S;
   const int64_t K = h->K, E = (int64_t)(N - 1) * K;
   int rc;
+  // site slice of this rank's reverse sweep (particle-sharded runs gather the scalar tables and shard the backward by site)
+  const int sb = h->site_begin < 0 ? 0 : (h->site_begin > S ? S : h->site_begin);
+  const int se = (h->site_end < 0 || h->site_end > S) ? S : (h->site_end < sb ? sb : h->site_end);
+  if (h->retain && (sb != 0 || se != S)) { set_error("a site slice needs the recompute backward (nodes are not retained per site slice)"); return VCSMC_ERR_STATE; }
 
   // ---- zero accumulators
   VCSMC_CUDA(cudaMemsetAsync(dlam_l, 0, (N - 1) * sizeof(double), st));
@@ -1073,6 +1043,11 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_suf_r), 0, K * sizeof(double), st));
   count_launch(14);
 
+  if (h->world > 1) {
+    // the forward filled P only for this rank's particles: rebuild all of it from the gathered branch lengths
+    rc = launch_transition_fwd(h->Q, h->p<double>(h->o_t2), 2 * E, h->jc, h->p<double>(h->o_P), st);
+    if (rc) return rc;
+  }
   // ---- which nodes are ever consumed as a child; child/adjoint slots of every event
   mark_consumed_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(h->p<int32_t>(h->o_lref), h->p<int32_t>(h->o_rref), E, N, h->p<int32_t>(h->o_consumed));
   VCSMC_LAUNCH_CHECK("mark_consumed_kernel");
@@ -1142,8 +1117,10 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_cleaf), 0, N * sizeof(double), st));
   column_sum_kernel<<<N, 256, 0, st>>>(h->p<double>(h->o_Dacc[1]), K, N, N, h->p<double>(h->o_cleaf));
   VCSMC_LAUNCH_CHECK("column_sum_kernel");
-  leaf_pi_grad_kernel<<<N, 256, 0, st>>>(h->codes, S, S, h->pi, h->p<double>(h->o_cleaf), dpi);
-  VCSMC_LAUNCH_CHECK("leaf_pi_grad_kernel");
+  if (se > sb) {
+    leaf_pi_grad_kernel<<<N, 256, 0, st>>>(h->codes + sb, S, se - sb, h->pi, h->p<double>(h->o_cleaf), dpi);
+    VCSMC_LAUNCH_CHECK("leaf_pi_grad_kernel");
+  }
 
   // ---- visiting orders of every rank event (sorted by child pair; inactive particles last)
   const bool sorted_b = use_sorted_order(K, S);
@@ -1190,14 +1167,15 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     int64_t sc = (h->pool_bytes / 2) / (n_cons * 32);
     if (h->max_chunk_sites > 0 && sc > h->max_chunk_sites) sc = h->max_chunk_sites;
     sc = sc / 256 * 256;
-    if (sc > S) sc = S;
-    if (sc < 256 && sc < S) { set_error("workspace too small for a 256-site backward chunk"); return VCSMC_ERR_ARG; }
+    if (sc > se - sb) sc = se - sb;
+    if (sc < 256 && sc < se - sb) { set_error("workspace too small for a 256-site backward chunk"); return VCSMC_ERR_ARG; }
+    if (sc < 1) sc = 1;
     Sc = (int)sc;
     gpool = lpool + n_cons * (int64_t)Sc * 4;
   }
   int n_chunks = 0;
-  for (int s0 = 0; s0 < S; s0 += Sc, ++n_chunks) {
-    const int nc = (S - s0 < Sc) ? S - s0 : Sc;
+  for (int s0 = sb; s0 < se; s0 += Sc, ++n_chunks) {
+    const int nc = (se - s0 < Sc) ? se - s0 : Sc;
     const uint8_t* codes_c = h->codes + s0;
     if (!h->retain) {
       // recompute the forward for this chunk, materialising only nodes that are consumed later
@@ -1298,9 +1276,10 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
 }
 
 int vcsmc_sweep_profile(vcsmc_sweep_t* h, double* out_host) {
-  // out_host[6] = {ms, launches} for kind 0 (forward merge), 1 (recompute merge), 2 (backward merge); resets.
+  // out_host[8] = {ms, launches} for kind 0 (forward merge / scoring), 1 (recompute merge), 2 (backward merge),
+  // 3 (survivor materialisation + peer pulls); resets.
   if (!h || !out_host) return VCSMC_ERR_ARG;
-  for (int i = 0; i < 6; ++i) out_host[i] = 0.0;
+  for (int i = 0; i < 8; ++i) out_host[i] = 0.0;
   for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
     VCSMC_CUDA(cudaEventSynchronize(h->ev[i + 1]));
     float ms = 0.f;

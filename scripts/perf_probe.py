@@ -1,5 +1,5 @@
 """Quick device-side timing of one sweep shape (not the bench): python scripts/perf_probe.py N S K jc [dense|skip] [ws_gb|0] [M]"""
-import sys, time
+import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, ".")
 from phylo_b200 import ops
@@ -24,6 +24,7 @@ print("workspace GB %.2f retained=%s min GB %.2f retain GB %.2f" % (sw.workspace
 sw.set_seed(0)
 sw.set_option("skip_zero", 0.0 if dense else 1.0)
 sw.set_option("profile", 1.0)
+sw.set_option("lazy", float(os.environ.get("LAZY", "1")))
 merges = K * S * (N - 1)
 for it in range(3):
     e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]

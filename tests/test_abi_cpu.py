@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     src = open(os.path.join(ROOT, "include", "vcsmc_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(vcsmc_[a-z0-9_]+)\s*\(", src)) - {"vcsmc_allreduce_fn"})
+    return sorted(set(re.findall(r"\b(vcsmc_[a-z0-9_]+)\s*\(", src)) - {"vcsmc_allreduce_fn", "vcsmc_comm_fn"})
 
 
 def test_library_exports_every_declared_symbol():
@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libvcsmc_b200.so does not export %s" % name
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared
-    assert lib.vcsmc_abi_version() == 1
+    assert lib.vcsmc_abi_version() == 2
 
 
 def test_arguments_are_validated_without_a_gpu():

@@ -23,7 +23,8 @@ def dev(x):
     return torch.as_tensor(x).cuda().contiguous()
 
 
-def run_gpu(ops, genome, K, p, U, jc, workspace_bytes=None, grads=True, skip_zero=True, max_chunk_sites=0):
+def run_gpu(ops, genome, K, p, U, jc, workspace_bytes=None, grads=True, skip_zero=True, max_chunk_sites=0, lazy=True,
+            force_gc=False):
     N, S = genome.shape[0], genome.shape[1]
     codes = ops.pack_alignment(dev(genome))
     lam_l, lam_r, Q, pi = O.model_from_params(p)
@@ -31,6 +32,9 @@ def run_gpu(ops, genome, K, p, U, jc, workspace_bytes=None, grads=True, skip_zer
     sw.set_uniforms(*gpu_uniforms(U))
     sw.set_option("skip_zero", 1.0 if skip_zero else 0.0)
     sw.set_option("max_chunk_sites", float(max_chunk_sites))
+    sw.set_option("lazy", 1.0 if lazy else 0.0)
+    if force_gc:
+        sw.set_option("force_gc", 1.0)
     elbo = sw.forward(codes, dev(lam_l), dev(lam_r), None if jc else dev(Q), dev(pi.reshape(-1)))
     out = {k: sw.output(k).cpu().numpy().copy() for k in
            ("log_weights", "log_likelihood", "log_likelihood_tilde", "log_likelihood_R", "left_branches",
@@ -76,15 +80,16 @@ def compare_grads(g, g_ref, jc):
         np.testing.assert_allclose(a, b, rtol=1e-7, atol=1e-9 * scale, err_msg=name)
 
 
+@pytest.mark.parametrize("lazy", [True, False])
 @pytest.mark.parametrize("jc", [True, False])
 @pytest.mark.parametrize("K", [1, 16, 64])
-def test_sweep_primate_subset(ops, primate_genome, jc, K):
+def test_sweep_primate_subset(ops, primate_genome, jc, K, lazy):
     g = primate_genome[:8, :300]
     N = g.shape[0]
     p = random_params(N, jc, seed=K)
     U = O.Uniforms.draw(N, K, seed=100 + K)
     res, g_ref = oracle_param_grads(g, K, p, U)
-    out, grads, sw = run_gpu(ops, g, K, p, U, jc)
+    out, grads, sw = run_gpu(ops, g, K, p, U, jc, lazy=lazy)
     assert sw.retained
     compare_forward(out, res, N, K)
     compare_grads(grads, g_ref, jc)
@@ -104,8 +109,9 @@ def test_sweep_primate_full(ops, primate_genome, jc):
     assert -7600 < out["elbo"] < -6500   # where the README figure's curves start
 
 
+@pytest.mark.parametrize("lazy", [True, False])
 @pytest.mark.parametrize("jc", [True, False])
-def test_sweep_flat_weights_many_lineages(ops, jc):
+def test_sweep_flat_weights_many_lineages(ops, jc, lazy):
     """Short alignment => flat weights => many distinct ancestors and shared nodes with several consumers."""
     g = synthetic_genome(9, 5, seed=3, gaps=0.1)
     N, K = 9, 128
@@ -113,16 +119,17 @@ def test_sweep_flat_weights_many_lineages(ops, jc):
     U = O.Uniforms.draw(N, K, seed=11)
     res, g_ref = oracle_param_grads(g, K, p, U)
     assert len(np.unique(res.ancestors[4])) > 10
-    out, grads, _ = run_gpu(ops, g, K, p, U, jc)
+    out, grads, _ = run_gpu(ops, g, K, p, U, jc, lazy=lazy)
     compare_forward(out, res, N, K)
     compare_grads(grads, g_ref, jc)
     # dense reverse sweep (no zero-adjoint skipping) gives the same gradients
-    _, grads_dense, _ = run_gpu(ops, g, K, p, U, jc, skip_zero=False)
+    _, grads_dense, _ = run_gpu(ops, g, K, p, U, jc, skip_zero=False, lazy=lazy)
     compare_grads(grads_dense, g_ref, jc)
 
 
+@pytest.mark.parametrize("lazy", [True, False])
 @pytest.mark.parametrize("jc", [True, False])
-def test_sweep_gc_pool_and_chunked_backward(ops, primate_genome, jc):
+def test_sweep_gc_pool_and_chunked_backward(ops, primate_genome, jc, lazy):
     """Smallest workspace: garbage-collected forward pool + site-chunked recompute backward == retained mode."""
     g = primate_genome[:10]
     N, K = g.shape[0], 48
@@ -133,14 +140,38 @@ def test_sweep_gc_pool_and_chunked_backward(ops, primate_genome, jc):
     small = probe.min_bytes
     assert small < probe.retain_bytes
     del probe
-    out, grads, sw = run_gpu(ops, g, K, p, U, jc, workspace_bytes=small)
-    assert not sw.retained and out["info"]["backward_chunks"] >= 1 and out["info"]["peak_pool_slots"] >= K
+    out, grads, sw = run_gpu(ops, g, K, p, U, jc, workspace_bytes=small, lazy=lazy)
+    # eager: every event allocates K slots; lazy: only survivors are materialised
+    assert not sw.retained and out["info"]["backward_chunks"] >= 1 and out["info"]["peak_pool_slots"] >= (1 if lazy else K)
+    if lazy:
+        assert out["info"]["peak_pool_slots"] < K
     compare_forward(out, res, N, K)
     compare_grads(grads, g_ref, jc)
     # several site chunks (ragged last chunk: 898 = 3 x 256 + 130), dense reverse sweep
-    out, grads, sw = run_gpu(ops, g, K, p, U, jc, workspace_bytes=small, max_chunk_sites=256, skip_zero=False)
+    out, grads, sw = run_gpu(ops, g, K, p, U, jc, workspace_bytes=small, max_chunk_sites=256, skip_zero=False, lazy=lazy)
     assert out["info"]["backward_chunks"] == 4
     compare_grads(grads, g_ref, jc)
+
+
+@pytest.mark.parametrize("lazy", [True, False])
+@pytest.mark.parametrize("jc", [True, False])
+def test_sweep_flat_weights_gc_pool_sorted_order(ops, jc, lazy):
+    """Many particles on few sites: the visiting order is sorted by child pair, thousands of distinct survivors go
+    through the slot allocator of the garbage-collected pool, and the backward recomputes by chunk."""
+    g = synthetic_genome(6, 7, seed=12, gaps=0.1)
+    N, K = 6, 12288
+    p = random_params(N, jc, seed=6)
+    U = O.Uniforms.draw(N, K, seed=13)
+    res, g_ref = oracle_param_grads(g, K, p, U)
+    assert len(np.unique(res.ancestors[3])) > 1000
+    probe = ops.Sweep(N, g.shape[1], K, jc)
+    roomy = probe.retain_bytes + (32 << 20)   # the slot tables of the garbage-collected pool need a little extra room
+    del probe
+    for force_gc in (False, True):
+        out, grads, sw = run_gpu(ops, g, K, p, U, jc, lazy=lazy, force_gc=force_gc, workspace_bytes=roomy)
+        assert (out["info"]["peak_pool_slots"] > 1000) == force_gc
+        compare_forward(out, res, N, K)
+        compare_grads(grads, g_ref, jc)
 
 
 def test_sweep_pool_exhaustion_is_reported(ops):
