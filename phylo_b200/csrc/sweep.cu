@@ -706,8 +706,8 @@ int decide_modes(vcsmc_sweep* h, int64_t tables, int64_t ws_bytes, bool report) 
   h->pool_bytes = ws_bytes - h->o_pool;
   if (h->keep) {
     int64_t Sc = (h->pool_bytes / 2) / ((int64_t)(N - 1) * K * 32);
-    Sc = Sc / 256 * 256;
-    if (Sc > S) Sc = S;
+    if (Sc >= S) Sc = S;
+    else Sc = Sc / 256 * 256;
     if (Sc < 256 && Sc < S) {
       if (report) set_error("workspace too small for a 256-site backward chunk");
       return VCSMC_ERR_ARG;
@@ -1166,8 +1166,8 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     if (n_cons < 1) n_cons = 1;
     int64_t sc = (h->pool_bytes / 2) / (n_cons * 32);
     if (h->max_chunk_sites > 0 && sc > h->max_chunk_sites) sc = h->max_chunk_sites;
-    sc = sc / 256 * 256;
-    if (sc > se - sb) sc = se - sb;
+    if (sc >= se - sb) sc = se - sb;
+    else sc = sc / 256 * 256;
     if (sc < 256 && sc < se - sb) { set_error("workspace too small for a 256-site backward chunk"); return VCSMC_ERR_ARG; }
     if (sc < 1) sc = 1;
     Sc = (int)sc;

@@ -171,7 +171,8 @@ class Sweep:
     """
 
     def __init__(self, n_taxa: int, n_sites: int, n_particles: int, jc: bool, keep_for_backward: bool = True,
-                 workspace_bytes: Optional[int] = None, device="cuda", mem_fraction: float = 0.85, n_sub: int = 0):
+                 workspace_bytes: Optional[int] = None, device="cuda", mem_fraction: float = 0.85, n_sub: int = 0,
+                 comm=None):
         lib = _lib.load()
         self.N, self.S, self.K, self.jc, self.keep = int(n_taxa), int(n_sites), int(n_particles), bool(jc), bool(keep_for_backward)
         self.device = torch.device(device)
@@ -183,7 +184,12 @@ class Sweep:
         if workspace_bytes is None:
             free, _total = torch.cuda.mem_get_info(self.device)
             budget = int(free * mem_fraction)
-            workspace_bytes = self.retain_bytes if self.retain_bytes <= budget else max(budget, self.min_bytes)
+            if comm is not None and comm.world > 1:
+                # particle sharding: every rank carves the same layout, and nodes are never all retained
+                budget = comm.min_int(budget)
+                workspace_bytes = max(min(budget, self.retain_bytes + (64 << 20)), self.min_bytes)
+            else:
+                workspace_bytes = self.retain_bytes if self.retain_bytes <= budget else max(budget, self.min_bytes)
         workspace_bytes = (int(workspace_bytes) + 255) // 256 * 256
         self.workspace = torch.empty(workspace_bytes, dtype=U8, device=self.device)
         cfg.workspace_bytes = workspace_bytes
@@ -193,12 +199,19 @@ class Sweep:
         self._lib = lib
         self._keepalive = None
         self._hook = None
+        self._comm_hook = None
+        self._peers = None
         self.retained = workspace_bytes >= self.retain_bytes
+        if comm is not None and comm.world > 1:
+            self.set_comm(comm)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
             self._lib.vcsmc_sweep_destroy(h)
+        peers = getattr(self, "_peers", None)
+        if peers is not None:
+            peers.close()
 
     # -- configuration
     def set_seed(self, seed: int) -> None:
@@ -246,6 +259,40 @@ class Sweep:
 
         self._hook = _lib.ALLREDUCE_FN(_cb)
         check(self._lib.vcsmc_sweep_set_allreduce(self._h, self._hook, None))
+
+    def set_comm(self, comm) -> None:
+        """Particle sharding (``vcsmc_sweep_set_comm``): this rank owns K/world logical particles; ``comm`` (a
+        ``phylo_b200.comm.Comm``) provides the per-event all-gather and barrier, the workspaces of all ranks are
+        mapped into each other through CUDA IPC."""
+        from .comm import PeerMap
+        if self.K % comm.world != 0:
+            raise ValueError("n_particles=%d is not divisible by the %d ranks" % (self.K, comm.world))
+        base = self.workspace.data_ptr()
+        dev = self.device
+
+        def _cb(_user, op, buf, nbytes, _stream_):
+            try:
+                if op == _lib.COMM_BARRIER:
+                    comm.barrier(dev)
+                elif op == _lib.COMM_ALLGATHER:
+                    off = buf - base
+                    comm.all_gather_inplace(self.workspace[off:off + nbytes * comm.world], nbytes)
+                elif op == _lib.COMM_ALLREDUCE:
+                    off = buf - base
+                    comm.all_reduce(self.workspace[off:off + nbytes].view(F64))
+                else:
+                    return -1
+                return 0
+            except Exception:  # never let an exception cross the C boundary
+                import traceback
+                traceback.print_exc()
+                return -1
+
+        self._peers = PeerMap(comm, self.workspace)
+        self._comm_hook = _lib.COMM_FN(_cb)
+        self._comm = comm
+        check(self._lib.vcsmc_sweep_set_comm(self._h, comm.rank, comm.world, self._comm_hook, None, self._peers.as_array()))
+        self.retained = False
 
     # -- execution
     def forward(self, codes: torch.Tensor, lam_l: torch.Tensor, lam_r: torch.Tensor, Q: Optional[torch.Tensor],

@@ -1,7 +1,12 @@
-"""Host-side logic of site sharding, shared by VCSMC and by the CPU (gloo) tests.
+"""Host-side logic of the two multi-GPU layouts, shared by VCSMC and by the CPU (gloo) tests.
 
-Every rank holds all K particles for a contiguous slice of the (mini)batch's site list; the forest log-likelihood
-sums are all-reduced once per rank event; the site-independent gradient terms are contributed by rank 0 only.
+Particle sharding (the default, north_star): rank g owns the logical particles [g K/G, (g+1) K/G) on ALL sites; per
+rank event the step record is all-gathered, every rank derives identical ancestors, missing nodes are pulled from
+their owners.  The reverse sweep is sharded by SITE on the gathered tables (``site_slice``); the site-independent
+gradient terms are contributed by rank 0 only (``scalar_share``) and the parameter gradients are summed.
+
+Site sharding (``sharding="sites"``): every rank holds all K particles for a contiguous slice of the (mini)batch's
+site list; the forest log-likelihood sums are all-reduced once per rank event.
 """
 from __future__ import annotations
 
@@ -19,3 +24,34 @@ def local_sites(site_idx: np.ndarray, rank: int, world: int) -> np.ndarray:
 def scalar_share(rank: int, world: int) -> float:
     """Fraction of the site-independent gradient terms this rank contributes before the gradient all-reduce."""
     return 1.0 if (world <= 1 or rank == 0) else 0.0
+
+
+def particle_range(n_particles: int, rank: int, world: int):
+    """[k0, k1) of the logical particles ``rank`` owns; K must be divisible by the world size."""
+    if n_particles % world != 0:
+        raise ValueError("n_particles=%d is not divisible by %d ranks" % (n_particles, world))
+    kl = n_particles // world
+    return rank * kl, (rank + 1) * kl
+
+
+def owner_of(k, n_particles: int, world: int):
+    """Rank that owns logical particle(s) ``k``."""
+    return np.asarray(k) // (n_particles // world)
+
+
+def site_slice(n_sites: int, rank: int, world: int):
+    """[s0, s1) of the sites whose reverse sweep ``rank`` runs under particle sharding (contiguous, sizes differ by <= 1)."""
+    base, extra = divmod(int(n_sites), int(world))   # the first `extra` ranks get one more site (np.array_split's rule)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def choose_sharding(requested, n_particles: int, world: int, nested: bool) -> str:
+    """'particles' unless asked otherwise or impossible (nested proposal, K not divisible): then 'sites'."""
+    if world <= 1:
+        return "none"
+    if requested in ("sites", "particles"):
+        if requested == "particles" and (nested or n_particles % world != 0):
+            raise ValueError("particle sharding needs the VCSMC proposal and n_particles divisible by the number of ranks")
+        return requested
+    return "sites" if (nested or n_particles % world != 0) else "particles"

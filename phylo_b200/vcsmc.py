@@ -7,9 +7,11 @@ its gradient are hand-written sm_100a kernels (libvcsmc_b200.so); the alignment 
 codes instead of being replicated K-fold on the host (vcsmc.py:479); randomness comes from a counter-based
 generator keyed by (seed, rank event, particle) because the reference seeds nothing.
 
-Multi-GPU: when torch.distributed is initialised the SITES of every (mini)batch are sharded across ranks; each
-rank holds all K particles for its sites, the only per-rank-event collective is an all-reduce of the K new
-log-likelihood sums, and every rank derives identical weights and ancestors ("site sharding").
+Multi-GPU: when torch.distributed is initialised the PARTICLES are sharded across ranks (each GPU holds K/G particles
+on all sites; one all-gather of the step record per rank event; nodes of remote ancestors are pulled over NVLink;
+the reverse sweep is sharded by site on the gathered tables).  ``sharding="sites"`` (or VCSMC_SHARDING=sites, and
+always for the nested proposal) shards the sites of every (mini)batch instead: each rank holds all K particles for
+its sites and the only per-event collective is an all-reduce of the K new log-likelihood sums.
 """
 from __future__ import annotations
 
@@ -24,7 +26,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .sharding import local_sites, scalar_share
+from .sharding import choose_sharding, local_sites, scalar_share, site_slice
 
 F64 = torch.float64
 
@@ -41,7 +43,8 @@ class VCSMC:
      genome: a 3 tensor [N,S,A] of genomes for the n taxa one hot encoded (ambiguous = all ones)
     """
 
-    def __init__(self, datadict, K, args=None, device: Optional[str] = None, seed: Optional[int] = None):
+    def __init__(self, datadict, K, args=None, device: Optional[str] = None, seed: Optional[int] = None,
+                 sharding: Optional[str] = None):
         self.args = args
         self.taxa = list(datadict["taxa"])
         self.genome_NxSxA = np.asarray(datadict["genome"], dtype=np.float64)
@@ -74,6 +77,11 @@ class VCSMC:
         self._sweeps: Dict[tuple, ops.Sweep] = {}
         dist = _dist()
         self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
+        self.sharding = choose_sharding(sharding or os.environ.get("VCSMC_SHARDING"), self.K, self.world, self.nested)
+        self._comm = None
+        if self.sharding == "particles":
+            from .comm import Comm
+            self._comm = Comm()
         # (a) pack the alignment ONCE into 4-bit device codes
         self.codes = ops.pack_alignment(torch.from_numpy(self.genome_NxSxA).to(dev))
 
@@ -107,6 +115,8 @@ class VCSMC:
     # -- the sweep ----------------------------------------------------------------------------
     def _local_sites(self, site_idx: Optional[np.ndarray]) -> np.ndarray:
         idx = np.arange(self.S, dtype=np.int32) if site_idx is None else np.asarray(site_idx, dtype=np.int32)
+        if self.sharding != "sites":
+            return idx                       # particle sharding: every rank sweeps all sites for its own particles
         return local_sites(idx, self.rank, self.world)
 
     def _sweep_for(self, n_sites: int, need_grad: bool) -> ops.Sweep:
@@ -115,10 +125,15 @@ class VCSMC:
             if need_grad and (n_sites, False) in self._sweeps:
                 del self._sweeps[(n_sites, False)]
             sw = ops.Sweep(self.N, n_sites, self.K, self.jcmodel, keep_for_backward=need_grad, device=self.device,
-                           n_sub=self.M if self.nested else 0)
-            if self.world > 1:
+                           n_sub=self.M if self.nested else 0, comm=self._comm)
+            if self.sharding == "sites":
                 import torch.distributed as dist
                 sw.set_allreduce(lambda t: dist.all_reduce(t))
+                sw.set_option("scalar_share", scalar_share(self.rank, self.world))
+            elif self.sharding == "particles":
+                s0, s1 = site_slice(n_sites, self.rank, self.world)   # the reverse sweep is sharded by site
+                sw.set_option("site_begin", float(s0))
+                sw.set_option("site_end", float(s1))
                 sw.set_option("scalar_share", scalar_share(self.rank, self.world))
             self._sweeps[key] = sw
         return self._sweeps[key]
@@ -132,7 +147,7 @@ class VCSMC:
         local = self._local_sites(site_idx)
         if len(local) == 0:
             raise ValueError("a rank received zero sites: batch smaller than the number of GPUs")
-        if site_idx is None and self.world == 1:
+        if site_idx is None and self.sharding != "sites":
             codes = self.codes
         else:
             codes = ops.gather_sites(self.codes, torch.from_numpy(local).to(self.device))
@@ -156,9 +171,18 @@ class VCSMC:
     def _allreduce_grads(self):
         if self.world > 1:
             import torch.distributed as dist
-            for v in self.trainable_variables():
-                if v.grad is not None:
-                    dist.all_reduce(v.grad)
+            grads = [v.grad for v in self.trainable_variables() if v.grad is not None]
+            if not grads:
+                return
+            flat = torch.cat([g.reshape(-1) for g in grads])       # one collective for the <= 2(N-1)+20 doubles
+            if self._comm is not None:
+                self._comm.all_reduce(flat)
+            else:
+                dist.all_reduce(flat)
+            off = 0
+            for g in grads:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
 
     def outputs(self) -> Dict[str, np.ndarray]:
         """The tensors the reference evaluates per epoch (vcsmc.py:538-551), as numpy arrays."""
