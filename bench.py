@@ -9,7 +9,14 @@ forward and the same number backward; `value` = K*S*(N-1) / seconds per step (fw
 
 Workload (BASELINE.json configs[4], the one the metric's target is quoted on): 64 taxa x 10,000 sites x 65,536
 particles, i.i.d. uniform nucleotides (numpy PCG64 seed 0), reference initial parameters (rates 10, `GTR' logits
-1/4, uniform pi), float64.  N GPUs: the alignment's SITES are sharded (strong scaling).
+1/4, uniform pi), float64.  N GPUs: the PARTICLES are sharded, K/N per GPU (strong scaling: K and S stay fixed; per
+rank event one all-gather of the step record, nodes of remote ancestors pulled over NVLink, reverse sweep sharded by
+site).  --sharding sites selects the site-sharded layout instead.
+
+The default path is the production one: the forward scores every particle and materialises only the particles that the
+next resampling draws ("lazy"); the reverse sweep skips events whose adjoint is exactly zero.  Results are identical to
+the eager / dense schedule, which is also timed (N = 1) and reported under "eager_dense" with the HBM roofline
+fractions of its two streaming kernels.
 
 --impl reference times the restated reference (oracle/vcsmc_oracle.py: TensorFlow 1.15 cannot be installed
 in this image) on the host cores on a bounded sample of the same workload.
@@ -34,6 +41,8 @@ import torch
 METRIC = "particle-site merges/sec (fwd+grad VCSMC sweep)"
 UNIT = "merges/s"
 BYTES_FWD, BYTES_BWD = 64.0, 128.0   # algorithmic bytes per merge, fp64 (SURVEY 8d / BASELINE.md section 3)
+FP64_PEAK_TFMA = 18.2                # measured FP64 FMA rate of a B200 on this pool (scripts/microbench.cu), T op/s
+FP64_OPS_SCORE = {"gtr": 18.0, "jc": 6.0}   # FP64-pipe instructions per particle.site of the scoring kernel
 
 
 def parse():
@@ -46,7 +55,9 @@ def parse():
     p.add_argument("--sites", type=int, default=10000)
     p.add_argument("--particles", type=int, default=65536)
     p.add_argument("--model", default="gtr", choices=["gtr", "jc"])
-    p.add_argument("--dense", action="store_true", help="reverse sweep without zero-adjoint skipping")
+    p.add_argument("--dense", action="store_true", help="eager forward (every node stored) + reverse sweep without zero-adjoint skipping")
+    p.add_argument("--sharding", default=None, choices=["particles", "sites"], help="multi-GPU layout (default: particles)")
+    p.add_argument("--no-eager-dense", action="store_true", help="skip the extra eager/dense timing at N = 1")
     p.add_argument("--nested", type=int, default=0, help="M > 0: VNCSMC look-ahead proposal with M sub-samples (config 4)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample", default="64x1000x32", help="taxa x sites x particles of the CPU baseline sample")
@@ -160,6 +171,7 @@ def run_native(args):
     import torch.distributed as dist
     from phylo_b200 import _lib, ops
     from phylo_b200.loader import synthetic_alignment
+    from phylo_b200.sharding import site_slice
     from phylo_b200.vcsmc import VCSMC
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -178,7 +190,8 @@ def run_native(args):
         dataset = "synthetic_%dx%d" % (N, S); nested = args.nested > 0; n_particles = K
 
     datadict = synthetic_alignment(N, S, seed=0)
-    model = VCSMC(datadict, K, A, seed=0)
+    model = VCSMC(datadict, K, A, seed=0, sharding=args.sharding)
+    sharding = model.sharding
     genome_host = torch.from_numpy(datadict["genome"]).pin_memory()
     variables = model.trainable_variables()
 
@@ -200,13 +213,19 @@ def run_native(args):
         out = [elbo.detach().cpu()] + [v.grad.cpu() for v in variables]
         return out
 
-    sweep = None
-    for w in range(args.warmup):
-        step(1000 + w)
+    lazy_ok = not args.nested          # the nested proposal runs the eager forward
+
+    def configure(dense):
+        sw = model._last
+        sw.set_option("skip_zero", 0.0 if dense else 1.0)
+        if lazy_ok and world == 1:
+            sw.set_option("lazy", 0.0 if dense else 1.0)
+
+    step(1000)                          # creates the sweep engine
     sweep = model._last
-    sweep.set_option("skip_zero", 0.0 if args.dense else 1.0)
-    if args.dense:
-        step(999)
+    configure(args.dense)
+    for w in range(max(args.warmup - 1, 2)):
+        step(1001 + w)
     info = sweep.check_status()
 
     def barrier():
@@ -255,11 +274,18 @@ def run_native(args):
     h2d = int(genome_host.numel() * 8 + nparam * 8)
     d2h = int(8 + nparam * 8)
 
-    # ---- roofline of the dominant kernel (per-launch CUDA-event times recorded inside the timed region)
-    S_loc = len(model._local_sites(None))
-    alg = {"merge_fwd": BYTES_FWD * K * S_loc * (N - 1) * args.steps,
-           "merge_fwd_recompute": BYTES_FWD * K * S_loc * (N - 1) * args.steps,
-           "merge_bwd": BYTES_BWD * K * S_loc * (N - 1) * args.steps}
+    # ---- roofline of the dominant kernel (per-launch CUDA-event times recorded inside the timed region, this rank)
+    S_fwd = len(model._local_sites(None))                        # sites this rank's forward covers
+    K_fwd = K // world if sharding == "particles" else K         # particles this rank's forward covers
+    if sharding == "particles":
+        b0, b1 = site_slice(S, rank, world)
+        S_bwd = b1 - b0
+    else:
+        S_bwd = S_fwd
+    fwd_merges = float(K_fwd) * S_fwd * (N - 1) * args.steps
+    bwd_merges = float(K) * S_bwd * (N - 1) * args.steps
+    alg = {"merge_fwd": BYTES_FWD * fwd_merges, "merge_fwd_recompute": BYTES_FWD * bwd_merges,
+           "merge_bwd": BYTES_BWD * bwd_merges, "materialise": BYTES_FWD * fwd_merges}
     dom = max(prof, key=lambda k: prof[k][0])
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -268,18 +294,50 @@ def run_native(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     dom_ms, dom_n = prof[dom]
     achieved = alg[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    lazy_fwd = lazy_ok and not (args.dense and world == 1)
+    kname = "merge_score" if (dom == "merge_fwd" and lazy_fwd) else dom
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom + ("_jc" if jc else "_gtr"))
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        traffic = json.load(open(tpath)).get(kname + ("_jc" if jc else "_gtr"))
+    roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "launches": dom_n,
                 "avg_launch_ms": dom_ms / max(dom_n, 1),
                 "algorithmic_bytes_per_launch": alg[dom] / max(dom_n, 1),
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
-                "note": "algorithmic bytes: 64 B/merge forward, 128 B/merge backward (fp64); with ESS~1 the children "
-                        "of a rank event are shared by all particles and are served from L2, so DRAM traffic is below "
-                        "the algorithmic figure (DESIGN.md section 5)"}
+                "note": "achieved = algorithmic bytes (64 B/merge forward, 128 B/merge backward, fp64; SURVEY 8d) / kernel "
+                        "time.  The lazy forward does not move those bytes: merge_score stores nothing and reads the shared "
+                        "children from L2, so it is bounded by the FP64 pipe (see fp64), not by HBM; the HBM-bound schedule "
+                        "is timed under eager_dense"}
+    if kname == "merge_score" and dom_ms > 0:
+        tops = FP64_OPS_SCORE[args.model] * fwd_merges / (dom_ms * 1e-3) / 1e12
+        roofline["fp64"] = {"achieved": tops, "peak": FP64_PEAK_TFMA, "unit": "T FP64 op/s", "frac": tops / FP64_PEAK_TFMA,
+                            "ops_per_merge": FP64_OPS_SCORE[args.model],
+                            "peak_source": "scripts/microbench.cu on this pool's B200s (DFMA, 64 warps/SM)"}
+
+    # ---- the eager / dense schedule (every node stored, no zero-adjoint skipping): the HBM-bound kernels
+    eager = None
+    if world == 1 and lazy_ok and not args.dense and not args.no_eager_dense:
+        configure(True)
+        step(2000)
+        sweep.set_option("profile", 1.0)
+        barrier()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nd = 2
+        d0.record()
+        for i in range(nd):
+            step(i)
+        d1.record()
+        barrier()
+        pd = sweep.profile()
+        sweep.set_option("profile", 0.0)
+        dms = d0.elapsed_time(d1) / nd
+        m1 = float(K) * S * (N - 1) * nd
+        eager = {"ms_per_step": dms, "value": float(K) * S * (N - 1) / (dms * 1e-3), "unit": UNIT, "steps": nd,
+                 "kernel_ms_per_step": {k: v[0] / nd for k, v in pd.items()},
+                 "hbm_frac": {k: (b * m1 / (pd[k][0] * 1e-3) / 1e9 / peak if pd[k][0] > 0 else None)
+                              for k, b in (("merge_fwd", BYTES_FWD), ("merge_bwd", BYTES_BWD))}}
+        configure(False)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -288,9 +346,10 @@ def run_native(args):
         "config": {"workload": "%s %s fwd+grad sweep, %d taxa x %d sites x %d particles, i.i.d. uniform nucleotides "
                                "(PCG64 seed 0), reference initial parameters" % (
                                    "VNCSMC(M=%d)" % args.nested if args.nested else "VCSMC", args.model.upper(), N, S, K),
-                   "taxa": N, "sites": S, "particles": K, "model": args.model, "sharding": "sites/%d" % world,
-                   "l2": "inputs larger than L2 (node pool of %.1f GB streamed per sweep)" % (sweep.workspace.numel() / 1e9),
-                   "backward": "dense" if args.dense else "zero-adjoint events skipped (identical results)",
+                   "taxa": N, "sites": S, "particles": K, "model": args.model, "sharding": "%s/%d" % (sharding, world),
+                   "l2": "inputs larger than L2 (%.1f GB workspace; node pool and per-event tables streamed per sweep)" % (sweep.workspace.numel() / 1e9),
+                   "forward": "lazy: every particle scored, survivors of the next resampling materialised (identical results)" if lazy_fwd else "eager: every node stored",
+                   "backward": ("dense" if args.dense else "zero-adjoint events skipped (identical results)") + (", sharded by site" if sharding == "particles" else ""),
                    "nodes_retained": bool(sweep.retained), "backward_chunks": info["backward_chunks"],
                    "peak_pool_slots": info["peak_pool_slots"]},
         "roofline": roofline,
@@ -298,8 +357,10 @@ def run_native(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "elbo": float(elbo),
+        "elbo": float(elbo.detach()),
     }
+    if eager is not None:
+        line["eager_dense"] = eager
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cval, cores, desc, per = cpu_sample_run(args.cpu_sample, jc, 1, 0)
         line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port",
@@ -307,6 +368,10 @@ def run_native(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
+        del sweep
+        model._sweeps.clear()
+        model._last = None
+        dist.barrier()
         dist.destroy_process_group()
 
 
