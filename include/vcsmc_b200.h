@@ -103,9 +103,10 @@ int vcsmc_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* po
  *     rem[K,n-2] = the others in ascending order.
  *     resample replaces resample (vcsmc.py:284-285): idx[j] = first i with cdf[i] > u[j]*total over
  *     the fp64 running sum of exp(logit - max); also returns logsumexp(lw) and the ESS.
- *     work must hold K + 4 doubles.
+ *     work must hold vcsmc_resample_work_doubles(K) doubles (CDF, statistics, per-tile partials of the multi-CTA scan).
  * --------------------------------------------------------------------------------------------- */
 int vcsmc_propose_pairs(const float* u, int64_t K, int n, int32_t* coal, int32_t* rem, void* stream);
+int64_t vcsmc_resample_work_doubles(int64_t K);
 int vcsmc_resample(const double* lw, const double* u, int64_t K, int32_t* idx, double* lse, double* ess,
                    double* work, void* stream);
 

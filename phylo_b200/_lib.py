@@ -47,6 +47,7 @@ _SIGNATURES = {
     "vcsmc_merge_fwd": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P]),
     "vcsmc_merge_bwd": (C.c_int, [_P, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P]),
     "vcsmc_propose_pairs": (C.c_int, [_P, C.c_int64, C.c_int, _P, _P, _P]),
+    "vcsmc_resample_work_doubles": (C.c_int64, [C.c_int64]),
     "vcsmc_resample": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, _P, _P]),
     "vcsmc_philox_step_uniforms": (C.c_int, [C.c_uint64, C.c_int, C.c_int64, C.c_int64, C.c_int, _P, _P, _P, _P, _P]),
     "vcsmc_sweep_query": (C.c_int, [C.POINTER(SweepConfig), C.POINTER(SweepSizes)]),

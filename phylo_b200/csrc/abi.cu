@@ -57,6 +57,7 @@ int vcsmc_transition_bwd(const double* Q, const double* t, const double* dP, int
 }
 
 int vcsmc_merge_tiles(int n_sites) { return merge_ell_parts(n_sites); }
+int64_t vcsmc_resample_work_doubles(int64_t K) { return K + 4 + resample_scratch_doubles(K); }
 
 int vcsmc_merge_fwd(const uint8_t* codes, int64_t codes_stride, double* pool, int64_t slot_sites, const int32_t* lsrc,
                     const int32_t* rsrc, const int32_t* dst, const double* P, const double* pi, int64_t K, int n_sites,
@@ -82,9 +83,9 @@ int vcsmc_propose_pairs(const float* u, int64_t K, int n, int32_t* coal, int32_t
 
 int vcsmc_resample(const double* lw, const double* u, int64_t K, int32_t* idx, double* lse, double* ess, double* work, void* stream) {
   if (!lw || !u || !idx || !work || K < 1) { set_error("resample: bad argument"); return VCSMC_ERR_ARG; }
-  // work: K doubles of CDF followed by 4 doubles of statistics
+  // work: K doubles of CDF, 4 doubles of statistics, then the per-tile partials of the multi-CTA scan
   double* stats = work + K;
-  int rc = launch_resample_cdf(lw, K, work, stats, (cudaStream_t)stream);
+  int rc = launch_resample_cdf(lw, K, work, stats, stats + 4, (cudaStream_t)stream);
   if (rc) return rc;
   rc = launch_resample_search(work, stats, u, K, idx, (cudaStream_t)stream);
   if (rc) return rc;

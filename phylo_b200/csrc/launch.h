@@ -37,6 +37,11 @@ int launch_sort_order(const int32_t* lsrc, const int32_t* rsrc, const int32_t* a
                       uint64_t* keys_out, int32_t* vals_in, int32_t* order_out, int32_t* count_out, void* temp,
                       size_t temp_bytes, cudaStream_t st);
 
+int64_t group_table_entries(int64_t K);
+int launch_group_order(const int32_t* lsrc, const int32_t* rsrc, const int32_t* active, int64_t K, unsigned long long* tab,
+                       int32_t* cnt, int32_t* off, int32_t* gslot, int32_t* grank, int32_t* order_out, int32_t* count_out,
+                       void* temp, size_t temp_bytes, cudaStream_t st);
+
 // transition.cu
 int launch_transition_fwd(const double* Q, const double* t, int64_t n, int jc, double* P, cudaStream_t st);
 int launch_transition_bwd(const double* Q, const double* t, const double* dP, int64_t n, int jc, double* dt,
@@ -49,7 +54,8 @@ int launch_gather_sites(const uint8_t* codes, int N, int S, const int32_t* site_
 
 // smc.cu
 int launch_propose_pairs(const float* u, int64_t K, int n, int32_t* coal, int32_t* rem, cudaStream_t st);
-int launch_resample_cdf(const double* lw, int64_t K, double* cdf, double* stats /*[4]: lse,total,ess,max*/, cudaStream_t st);
+int64_t resample_scratch_doubles(int64_t K);
+int launch_resample_cdf(const double* lw, int64_t K, double* cdf, double* stats /*[4]: lse,total,ess,max*/, double* scratch, cudaStream_t st);
 int launch_resample_search(const double* cdf, const double* stats, const double* u, int64_t K, int32_t* idx, cudaStream_t st);
 int launch_philox_step(uint64_t seed, int r, int64_t k0, int64_t K, int n, float* u_pair, double* u_bl, double* u_br,
                        double* u_res, double* u_cat, cudaStream_t st);

@@ -509,9 +509,7 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
     rc = launch_transition_fwd(Q, a.t2 + 2 * k0, 2 * Kl, h->jc, P, st);
     if (rc) return rc;
     if (sorted) {
-      rc = launch_sort_order(lsrc, rsrc, nullptr, Kl, gc ? h->pool_slots : E, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out),
-                             h->p<int32_t>(h->o_vals_in), h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count),
-                             h->p<char>(h->o_sort_temp), h->sort_temp, st);
+      rc = group_particles(h, lsrc, rsrc, nullptr, Kl, h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count), st);
       if (rc) return rc;
     }
     int tiles = 0;
@@ -562,7 +560,8 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
       VCSMC_LAUNCH_CHECK("lz_unpack_kernel");
     }
     // log-sum-exp + CDF of this step's weights over ALL particles (every rank: same input, same fixed order)
-    rc = launch_resample_cdf(h->p<double>(h->o_lw) + (int64_t)r * K, K, h->p<double>(h->o_cdf), h->p<double>(h->o_stats) + r * 4, st);
+    rc = launch_resample_cdf(h->p<double>(h->o_lw) + (int64_t)r * K, K, h->p<double>(h->o_cdf), h->p<double>(h->o_stats) + r * 4,
+                             h->p<double>(h->o_cdf_scratch), st);
     if (rc) return rc;
   }
   if (G > 1) {

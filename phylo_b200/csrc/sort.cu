@@ -28,7 +28,80 @@ __global__ void __launch_bounds__(256) build_keys_kernel(const int32_t* __restri
   if (threadIdx.x == 0 && n) atomicAdd(count, n);
 }
 
+// ---- grouping without a sort.  The merge kernels only need particles with the same (unordered) child pair to be
+// ADJACENT; which group comes first is irrelevant (every particle's result is independent of its neighbours).  A hash
+// table keyed by the pair hands out group slots, a warp-aggregated counter hands out ranks inside a group, one scan
+// turns the counts into offsets: 4 short launches instead of the ~13 of a 40-bit radix sort.
+__global__ void __launch_bounds__(256) group_insert_kernel(const int32_t* __restrict__ lsrc, const int32_t* __restrict__ rsrc,
+                                                           const int32_t* __restrict__ active, int64_t K, int log2T,
+                                                           unsigned long long* __restrict__ tab, int32_t* __restrict__ cnt,
+                                                           int32_t* __restrict__ gslot, int32_t* __restrict__ grank) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool on = k < K && (active ? active[k] != 0 : true);
+  int slot = -1 - lane;  // inactive lanes never match anybody
+  if (on) {
+    const int ls = lsrc[k], rs = rsrc[k];
+    const unsigned long long key = (((unsigned long long)(unsigned)(min(ls, rs) + 256)) << 32 | (unsigned)(max(ls, rs) + 256)) + 1ull;
+    const unsigned mask = (1u << log2T) - 1u;
+    unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> (64 - log2T));
+    while (true) {
+      const unsigned long long old = atomicCAS(tab + h, 0ull, key);
+      if (old == 0ull || old == key) break;
+      h = (h + 1) & mask;
+    }
+    slot = (int)h;
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, slot);
+  if (on) {
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(cnt + slot, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    gslot[k] = slot;
+    grank[k] = base + __popc(peers & ((1u << lane) - 1));
+  } else if (k < K) {
+    gslot[k] = -1;
+  }
+}
+
+__global__ void __launch_bounds__(256) group_scatter_kernel(int64_t K, int64_t T, const int32_t* __restrict__ cnt,
+                                                            const int32_t* __restrict__ off, const int32_t* __restrict__ gslot,
+                                                            const int32_t* __restrict__ grank, int32_t* __restrict__ order,
+                                                            int32_t* __restrict__ count_out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k == 0 && count_out) count_out[0] = off[T - 1] + cnt[T - 1];
+  if (k >= K) return;
+  const int s = gslot[k];
+  if (s >= 0) order[off[s] + grank[k]] = (int32_t)k;
+}
+
 }  // namespace
+
+int64_t group_table_entries(int64_t K) {
+  int64_t T = 1024;
+  while (T < 2 * K) T <<= 1;
+  return T;
+}
+
+int launch_group_order(const int32_t* lsrc, const int32_t* rsrc, const int32_t* active, int64_t K, unsigned long long* tab,
+                       int32_t* cnt, int32_t* off, int32_t* gslot, int32_t* grank, int32_t* order_out, int32_t* count_out,
+                       void* temp, size_t temp_bytes, cudaStream_t st) {
+  if (K <= 0) return VCSMC_OK;
+  const int64_t T = group_table_entries(K);
+  int log2T = 0;
+  while (((int64_t)1 << log2T) < T) ++log2T;
+  VCSMC_CUDA(cudaMemsetAsync(tab, 0, (size_t)T * sizeof(unsigned long long), st));
+  VCSMC_CUDA(cudaMemsetAsync(cnt, 0, (size_t)T * sizeof(int32_t), st));
+  count_launch(2);
+  group_insert_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(lsrc, rsrc, active, K, log2T, tab, cnt, gslot, grank);
+  VCSMC_LAUNCH_CHECK("group_insert_kernel");
+  VCSMC_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, cnt, off, (int)T, st));
+  count_launch(2);
+  group_scatter_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(K, T, cnt, off, gslot, grank, order_out, count_out);
+  VCSMC_LAUNCH_CHECK("group_scatter_kernel");
+  return VCSMC_OK;
+}
 
 size_t sort_temp_bytes(int64_t K) {
   size_t bytes = 0;

@@ -487,6 +487,13 @@ double log_double_factorial_host(int m) {  // vcsmc.py:30-57
 }
 
 
+int group_particles(vcsmc_sweep* h, const int32_t* lsrc, const int32_t* rsrc, const int32_t* active, int64_t K,
+                    int32_t* order_out, int32_t* count_out, cudaStream_t st) {
+  return launch_group_order(lsrc, rsrc, active, K, h->p<unsigned long long>(h->o_gtab), h->p<int32_t>(h->o_gcnt), h->p<int32_t>(h->o_goff),
+                            h->p<int32_t>(h->o_gslot), h->p<int32_t>(h->o_grank), order_out, count_out, h->p<char>(h->o_sort_temp),
+                            h->sort_temp, st);
+}
+
 int launch_leaf_ell(const uint8_t* codes, int64_t stride, int N, int S, const double* pi, double* ell_node, cudaStream_t st) {
   leaf_ell_kernel<<<N, 256, 0, st>>>(codes, stride, S, pi, ell_node);
   VCSMC_LAUNCH_CHECK("leaf_ell_kernel");
@@ -561,6 +568,7 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_slot[i] = L.take<int32_t>(K * N);
   }
   h->o_cdf = L.take<double>(K);
+  h->o_cdf_scratch = L.take<double>(resample_scratch_doubles(K));
   h->o_u_pair = L.take<float>(K * N);
   h->o_u_bl = L.take<double>(K);
   h->o_u_br = L.take<double>(K);
@@ -609,7 +617,16 @@ int64_t plan(vcsmc_sweep* h) {
   h->o_vals_in = L.take<int32_t>(K);
   h->o_order = L.take<int32_t>(K);
   h->o_count = L.take<int32_t>(4);
+  {
+    const int64_t T = group_table_entries(K);
+    h->o_gtab = L.take<unsigned long long>(T);
+    h->o_gcnt = L.take<int32_t>(T);
+    h->o_goff = L.take<int32_t>(T);
+    h->o_gslot = L.take<int32_t>(K);
+    h->o_grank = L.take<int32_t>(K);
+  }
   h->sort_temp = sort_temp_bytes(K);
+  { const size_t sc = scan_temp_bytes(group_table_entries(K)); if (sc > h->sort_temp) h->sort_temp = sc; }
   if (h->keep) { const size_t sc = scan_temp_bytes(E); if (sc > h->sort_temp) h->sort_temp = sc; }
   h->o_sort_temp = L.take<char>((int64_t)h->sort_temp + 256);
   if (h->keep) {
@@ -961,6 +978,7 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
     // visiting order: particles sorted by their pair of child nodes (shared children are read once per group)
     const bool sorted = use_sorted_order(K, S);
     if (sorted) {
+      // (a full sort, not just grouping: consecutive groups then also share their first child)
       rc = launch_sort_order(a.lsrc, a.rsrc, nullptr, K, h->pool_slots, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out),
                              h->p<int32_t>(h->o_vals_in), h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count),
                              h->p<char>(h->o_sort_temp), h->sort_temp, st);
@@ -1001,7 +1019,7 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
     VCSMC_LAUNCH_CHECK("step_weights_kernel");
 
     // log-sum-exp + CDF of this step's weights: logZ_r now, ancestors of the next rank event
-    rc = launch_resample_cdf(w.lw, K, h->p<double>(h->o_cdf), h->p<double>(h->o_stats) + r * 4, st);
+    rc = launch_resample_cdf(w.lw, K, h->p<double>(h->o_cdf), h->p<double>(h->o_stats) + r * 4, h->p<double>(h->o_cdf_scratch), st);
     if (rc) return rc;
   }
   finalize_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(
@@ -1132,8 +1150,13 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
       VCSMC_LAUNCH_CHECK("bwd_active_kernel");
       const int32_t* bl = h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K;
       const int32_t* br = h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K;
-      rc = launch_sort_order(bl, br, h->p<int32_t>(h->o_act_bwd), K, E, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out), h->p<int32_t>(h->o_vals_in),
-                             h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r, h->p<char>(h->o_sort_temp), h->sort_temp, st);
+      // sparse reverse sweep: grouping by child pair is enough; dense: a full sort keeps runs of the first child together
+      // (one flush of its adjoint per run instead of one per pair)
+      if (h->skip_zero)
+        rc = group_particles(h, bl, br, h->p<int32_t>(h->o_act_bwd), K, h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r, st);
+      else
+        rc = launch_sort_order(bl, br, h->p<int32_t>(h->o_act_bwd), K, E, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out), h->p<int32_t>(h->o_vals_in),
+                               h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r, h->p<char>(h->o_sort_temp), h->sort_temp, st);
       if (rc) return rc;
     }
     // one small D2H + sync: the host learns how many particles each rank event really has to visit, so that empty

@@ -47,6 +47,8 @@ struct WeightArgs {
   const double* qlog;  // VNCSMC: per-particle log-probability of the chosen option (vncsmc.py:315-316), else null
 };
 
+int group_particles(vcsmc_sweep* h, const int32_t* lsrc, const int32_t* rsrc, const int32_t* active, int64_t K,
+                    int32_t* order_out, int32_t* count_out, cudaStream_t st);
 int launch_leaf_ell(const uint8_t* codes, int64_t stride, int N, int S, const double* pi, double* ell_node, cudaStream_t st);
 int launch_step_weights(const WeightArgs& w, cudaStream_t st);
 int launch_finalize(int N, int64_t K, const double* stats, const double* LL_last, const double* b_l, const double* b_r,
@@ -107,7 +109,7 @@ struct vcsmc_sweep {
   void* comm_user = nullptr;
   int site_begin = 0, site_end = -1;   // site slice of the reverse sweep (particle-sharded runs shard the backward by site)
   int64_t o_loc = 0, o_slot_id = 0, o_pend = 0, o_surv = 0, o_mat_list = 0, o_fetch_e = 0, o_fetch_src = 0, o_counts = 0,
-          o_lz_ids = 0, o_lz_cnt = 0, o_u_res_all = 0, o_rec = 0;
+          o_lz_ids = 0, o_lz_cnt = 0, o_u_res_all = 0, o_rec = 0, o_cdf_scratch = 0, o_gtab = 0, o_gcnt = 0, o_goff = 0, o_gslot = 0, o_grank = 0;
   int64_t rec_stride = 0;              // bytes of one rank's chunk of the per-event record
   int64_t fetch_cap = 0;
   // hook

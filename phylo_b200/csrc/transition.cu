@@ -46,6 +46,20 @@ __global__ void transition_bwd_kernel(const double* __restrict__ Q, const double
     dt[i] = e * (0.25 * G[1] - 0.75 * G[0]);
     return;
   }
+  {
+    // a zero adjoint (the rule with ESS ~ 1: almost no particle of a rank event carries weight) needs no series
+    double any = 0.0;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) any += fabs(G[e]);
+    if (any == 0.0) {
+      dt[i] = 0.0;
+      if (dQ_each) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dQ_each[i * 16 + e] = 0.0;
+      }
+      return;
+    }
+  }
   M4 At, E, X, Y;
 #pragma unroll
   for (int r = 0; r < 4; ++r)

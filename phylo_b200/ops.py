@@ -136,7 +136,7 @@ def resample(lw: torch.Tensor, u: torch.Tensor):
     K = lw.numel()
     idx = torch.empty(K, dtype=I32, device=lw.device)
     out = torch.empty(2, dtype=F64, device=lw.device)
-    work = torch.empty(K + 4, dtype=F64, device=lw.device)
+    work = torch.empty(int(_lib.load().vcsmc_resample_work_doubles(K)), dtype=F64, device=lw.device)
     check(_lib.load().vcsmc_resample(_ptr(lw), _ptr(u), K, _ptr(idx), out.data_ptr(), out.data_ptr() + 8, _ptr(work), _stream()))
     return idx, out[0], out[1]
 
