@@ -180,6 +180,8 @@ int vcsmc_sweep_set_comm(vcsmc_sweep_t* h, int rank, int world, vcsmc_comm_fn fn
  * "lazy" (default 1; VCSMC proposal only): the forward scores every particle without storing its node and materialises
  * only the particles that the next resampling draws as an ancestor; 0 = eager (every node stored as it is computed) --
  * results are identical;
+ * "leaf_patterns" (default 1; lazy forward): merges of two leaves are scored from the site-pattern counts of the leaf
+ * pair (tabulated once per sweep) instead of site by site -- same sum, different summation order;
  * "force_gc" (default 0): use the garbage-collected pool and the recompute backward even when every node fits (testing aid);
  * "site_begin", "site_end" (default 0, n_sites): the site slice this rank's reverse sweep covers;
  * "profile" (default 0): record CUDA events around every merge launch, read with vcsmc_sweep_profile. */

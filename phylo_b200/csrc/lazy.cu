@@ -382,6 +382,12 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
   if (h->allreduce) {  // site sharding: every rank holds a slice of the sites
     if (h->allreduce(h->allreduce_user, ell_node, N, st)) { set_error("allreduce hook failed"); return VCSMC_ERR_CUDA; }
   }
+  const int32_t* leaf_hist = nullptr;
+  if (h->leaf_patterns) {  // site patterns of every leaf pair, once per sweep: cherries are scored from these counts
+    rc = launch_leaf_pair_hist(codes, S, N, S, h->p<int32_t>(h->o_leaf_hist), st);
+    if (rc) return rc;
+    leaf_hist = h->p<int32_t>(h->o_leaf_hist);
+  }
   double* pool = h->p<double>(h->o_pool);
   int32_t* flags = h->p<int32_t>(h->o_flags);
   int32_t* loc = h->p<int32_t>(h->o_loc);
@@ -515,7 +521,7 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
     int tiles = 0;
     h->prof_begin(0, st);
     rc = launch_merge_score(codes, S, pool, S, lsrc, rsrc, sorted ? h->p<int32_t>(h->o_order) : nullptr, P, pi, Kl, S, h->jc,
-                            h->p<double>(h->o_ell_part), &tiles, st);
+                            leaf_hist, N, h->p<double>(h->o_ell_part), &tiles, st);
     h->prof_end(st);
     if (rc) return rc;
 

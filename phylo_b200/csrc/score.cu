@@ -41,6 +41,7 @@ struct ScoreArgs {
   int tiles_per_item;
   int n_chunks;
   int R;
+  int skip_leaf_pairs;  // particles whose children are both leaves are scored from the pattern histogram instead
   double* ell_part;  // [K][n_chunks][kWarps]
 };
 
@@ -54,6 +55,7 @@ struct ChildSpace {
   const double* pool;
   int64_t slot_sites;
   int n_sites;
+  int skip_leaf_pairs;
 };
 
 template <bool JC, int SPT, int NC>
@@ -168,6 +170,10 @@ __device__ __forceinline__ void score_tile(const ChildSpace& a, int nj, int sbas
   int j = 0;
   while (j < nj) {
     const int ca = s_a[j], cb = s_b[j];
+    if (a.skip_leaf_pairs && cb < 0) {  // canonical order a <= b: both children are leaves
+      ++j;
+      continue;
+    }
     if (ca != pa || cb != pb) {
       site_products<JC, SPT, NC>(a, ca, cb, sbase, pi, C);
       pa = ca;
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
   for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
   double* my_prod = s_prod + tid;
   int* my_exp = s_exp + tid;
-  const ChildSpace cs = {a.codes, a.codes_stride, a.pool, a.slot_sites, a.n_sites};
+  const ChildSpace cs = {a.codes, a.codes_stride, a.pool, a.slot_sites, a.n_sites, a.skip_leaf_pairs};
 
   for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
     const int64_t g = w / a.n_chunks;
@@ -289,6 +295,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
     __syncthreads();
     const unsigned odd_all = s_odd;
     for (int j = 0; j < nj; ++j) {
+      if (a.skip_leaf_pairs && s_b[j] < 0) continue;  // written by score_leaf_pairs_kernel
       double acc;
       if (odd_all >> j & 1u) {
         // some likelihood of this particle is 0 / subnormal / not finite: one log per site, like the reference
@@ -393,13 +400,99 @@ __global__ void __launch_bounds__(kTileThreads) pull_kernel(const PullArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// leaf-leaf merges: site patterns instead of sites
+// ---------------------------------------------------------------------------------------------
+// When both children are leaves the site likelihood depends on the site only through the two 4-bit state masks:
+//   x(ca, cb) = sum_i pi_i (sum_{j in ca} P_a[j][i]) (sum_{m in cb} P_b[m][i]),
+// so sum_s log x[s] = sum over the <= 256 patterns of count(ca, cb) * log x(ca, cb).  The counts of every leaf pair are
+// tabulated once per sweep (site-pattern compression, the standard trick of likelihood codes, applied per cherry); a
+// cherry then costs a few dozen logs per particle instead of S site evaluations.  About a third of all merges of a
+// sweep join two leaves.
+__device__ __forceinline__ int64_t leaf_pair_index(int a, int b, int N) {  // a < b
+  return (int64_t)a * (2 * N - a - 1) / 2 + (b - a - 1);
+}
+
+__global__ void __launch_bounds__(256) leaf_pair_hist_kernel(const uint8_t* __restrict__ codes, int64_t stride, int N, int S,
+                                                             int32_t* __restrict__ hist) {
+  __shared__ int sh[256];
+  // blockIdx.x enumerates the pairs a < b in leaf_pair_index order
+  int a = 0;
+  int64_t rem = blockIdx.x;
+  while (rem >= N - 1 - a) {
+    rem -= N - 1 - a;
+    ++a;
+  }
+  const int b = a + 1 + (int)rem;
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const uint8_t* ra = codes + (int64_t)a * stride;
+  const uint8_t* rb = codes + (int64_t)b * stride;
+  for (int s = threadIdx.x; s < S; s += 256) atomicAdd(&sh[(ra[s] & 15) * 16 + (rb[s] & 15)], 1);
+  __syncthreads();
+  hist[(int64_t)blockIdx.x * 256 + threadIdx.x] = sh[threadIdx.x];
+}
+
+// one warp per particle; lanes share the 256 patterns
+__global__ void __launch_bounds__(256) score_leaf_pairs_kernel(const int32_t* __restrict__ lsrc, const int32_t* __restrict__ rsrc,
+                                                               const double* __restrict__ P, const double* __restrict__ pi_,
+                                                               int64_t K, int N, const int32_t* __restrict__ hist,
+                                                               int n_parts, double* __restrict__ ell_part) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (k >= K) return;
+  const int ls = lsrc[k], rs = rsrc[k];
+  if (ls >= 0 || rs >= 0) return;
+  const int la = -ls - 1, lb = -rs - 1;  // leaf indices of the left / right child
+  const bool sw = la > lb;
+  const int32_t* h = hist + leaf_pair_index(sw ? lb : la, sw ? la : lb, N) * 256;
+  const double* Pl = P + k * 32;
+  const double* Pr = Pl + 16;
+  double pi[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pi[i] = __ldg(pi_ + i);
+  double acc = 0.0;
+  for (int bin = lane; bin < 256; bin += 32) {
+    const int c = h[bin];
+    if (c == 0) continue;
+    // the histogram is indexed (code of the lower leaf, code of the higher leaf)
+    const int c_lo = bin >> 4, c_hi = bin & 15;
+    const int cl = sw ? c_hi : c_lo, cr = sw ? c_lo : c_hi;
+    double x = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double A = 0.0, B = 0.0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (cl >> j & 1) A += __ldg(Pl + j * 4 + i);
+        if (cr >> j & 1) B += __ldg(Pr + j * 4 + i);
+      }
+      x = fma(pi[i] * A, B, x);
+    }
+    acc = fma((double)c, log(x), acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) ell_part[k * n_parts] = acc;
+  for (int t = 1 + lane; t < n_parts; t += 32) ell_part[k * n_parts + t] = 0.0;
+}
+
 constexpr int64_t kScoreItems = 148 * 8;  // work items wanted per launch
 
 }  // namespace
 
+int64_t leaf_pair_hist_ints(int N) { return (int64_t)N * (N - 1) / 2 * 256; }
+
+int launch_leaf_pair_hist(const uint8_t* codes, int64_t stride, int N, int S, int32_t* hist, cudaStream_t st) {
+  if (N < 2 || S <= 0) return VCSMC_OK;
+  leaf_pair_hist_kernel<<<(unsigned)((int64_t)N * (N - 1) / 2), 256, 0, st>>>(codes, stride, N, S, hist);
+  VCSMC_LAUNCH_CHECK("leaf_pair_hist_kernel");
+  return VCSMC_OK;
+}
+
 int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double* pool, int64_t slot_sites,
                        const int32_t* lsrc, const int32_t* rsrc, const int32_t* order, const double* P, const double* pi,
-                       int64_t K, int n_sites, int jc, double* ell_part, int* n_parts, cudaStream_t st) {
+                       int64_t K, int n_sites, int jc, const int32_t* leaf_hist, int n_taxa, double* ell_part, int* n_parts,
+                       cudaStream_t st) {
   if (n_parts) *n_parts = 0;
   if (K <= 0 || n_sites <= 0) return VCSMC_OK;
   static int spt_general = 0;
@@ -415,6 +508,7 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
   ScoreArgs a;
   a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.slot_sites = slot_sites; a.lsrc = lsrc; a.rsrc = rsrc;
   a.order = order; a.P = P; a.pi = pi; a.K = K; a.n_sites = n_sites; a.ell_part = ell_part;
+  a.skip_leaf_pairs = leaf_hist != nullptr;
   a.tiles = (n_sites + kTileThreads * spt - 1) / (kTileThreads * spt);
   // groups as large as the machine fill allows (shared children and site products are amortised over the group)
   int64_t R = (K * a.tiles) / kScoreItems;
@@ -435,6 +529,10 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
   else if (spt == 4) merge_score_kernel<false, 4><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
   else merge_score_kernel<false, 2><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
   VCSMC_LAUNCH_CHECK("merge_score_kernel");
+  if (leaf_hist) {
+    score_leaf_pairs_kernel<<<(unsigned)((K + 7) / 8), 256, 0, st>>>(lsrc, rsrc, P, pi, K, n_taxa, leaf_hist, a.n_chunks * kWarps, ell_part);
+    VCSMC_LAUNCH_CHECK("score_leaf_pairs_kernel");
+  }
   return VCSMC_OK;
 }
 

@@ -609,6 +609,7 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_lz_ids = L.take<int32_t>(K * N);
     h->o_lz_cnt = L.take<int32_t>(K * N);
     h->o_u_res_all = L.take<double>(K);
+    h->o_leaf_hist = L.take<int32_t>(leaf_pair_hist_ints(N));
     h->rec_stride = align_up((h->Kl > 0 ? h->Kl : K) * (int64_t)(72 + N), 16);
     h->o_rec = L.take<char>(K * (int64_t)(72 + N) + 16 * kMaxPeers + 256);
   }
@@ -832,6 +833,7 @@ int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value) {
     const int64_t tables = plan(h);
     return decide_modes(h, tables, h->ws_bytes, true);
   }
+  else if (!strcmp(name, "leaf_patterns")) h->leaf_patterns = value != 0.0;
   else if (!strcmp(name, "site_begin")) h->site_begin = (int)value;
   else if (!strcmp(name, "site_end")) h->site_end = (int)value;
   else if (!strcmp(name, "profile")) { h->profile = value != 0.0; h->ev_used = 0; h->ev_kind.clear(); }
