@@ -53,7 +53,7 @@ int vcsmc_transition_fwd(const double* Q, const double* t, int64_t n, int jc, do
 
 int vcsmc_transition_bwd(const double* Q, const double* t, const double* dP, int64_t n, int jc, double* dt, double* dQ_each, void* stream) {
   if ((!jc && !Q) || !t || !dP || !dt || n < 0) { set_error("transition_bwd: bad argument"); return VCSMC_ERR_ARG; }
-  return launch_transition_bwd(Q, t, dP, n, jc, dt, dQ_each, (cudaStream_t)stream);
+  return launch_transition_bwd(Q, t, dP, n, jc, nullptr, dt, dQ_each, (cudaStream_t)stream);
 }
 
 int vcsmc_merge_tiles(int n_sites) { return merge_ell_parts(n_sites); }

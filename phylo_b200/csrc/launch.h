@@ -47,8 +47,8 @@ int launch_group_order(const int32_t* lsrc, const int32_t* rsrc, const int32_t* 
 
 // transition.cu
 int launch_transition_fwd(const double* Q, const double* t, int64_t n, int jc, double* P, cudaStream_t st);
-int launch_transition_bwd(const double* Q, const double* t, const double* dP, int64_t n, int jc, double* dt,
-                          double* dQ_each, cudaStream_t st);
+int launch_transition_bwd(const double* Q, const double* t, const double* dP, int64_t n, int jc, const int32_t* list,
+                          double* dt, double* dQ_each, cudaStream_t st);
 
 // loader.cu
 int launch_pack_alignment(const double* genome, int N, int S, uint8_t* codes, int* status, cudaStream_t st);

@@ -433,43 +433,46 @@ __global__ void __launch_bounds__(256) leaf_pair_hist_kernel(const uint8_t* __re
   hist[(int64_t)blockIdx.x * 256 + threadIdx.x] = sh[threadIdx.x];
 }
 
-// one warp per particle; lanes share the 256 patterns
+// one warp per particle: 16 lanes build M[j][m] = sum_i pi_i P_l[j][i] P_r[m][i] (the likelihood of the one-hot pattern
+// (j, m)), then the lanes share the 256 patterns; a pattern with ambiguity masks sums the M entries its masks cover
 __global__ void __launch_bounds__(256) score_leaf_pairs_kernel(const int32_t* __restrict__ lsrc, const int32_t* __restrict__ rsrc,
                                                                const double* __restrict__ P, const double* __restrict__ pi_,
                                                                int64_t K, int N, const int32_t* __restrict__ hist,
                                                                int n_parts, double* __restrict__ ell_part) {
-  const int lane = threadIdx.x & 31;
-  const int64_t k = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  __shared__ double sM[8][16];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t k = (int64_t)blockIdx.x * 8 + wid;
   if (k >= K) return;
   const int ls = lsrc[k], rs = rsrc[k];
-  if (ls >= 0 || rs >= 0) return;
+  if (ls >= 0 || rs >= 0) return;  // (whole warp)
   const int la = -ls - 1, lb = -rs - 1;  // leaf indices of the left / right child
   const bool sw = la > lb;
   const int32_t* h = hist + leaf_pair_index(sw ? lb : la, sw ? la : lb, N) * 256;
-  const double* Pl = P + k * 32;
-  const double* Pr = Pl + 16;
-  double pi[4];
+  int c[8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) pi[i] = __ldg(pi_ + i);
+  for (int q = 0; q < 8; ++q) c[q] = __ldg(h + lane + 32 * q);
+  if (lane < 16) {
+    // rows of M follow the LOWER leaf (the histogram's first code), columns the higher one
+    const double* Pa = P + k * 32 + (sw ? 16 : 0) + (lane >> 2) * 4;
+    const double* Pb = P + k * 32 + (sw ? 0 : 16) + (lane & 3) * 4;
+    double m = __ldg(pi_) * __ldg(Pa) * __ldg(Pb);
+#pragma unroll
+    for (int i = 1; i < 4; ++i) m = fma(__ldg(pi_ + i) * __ldg(Pa + i), __ldg(Pb + i), m);
+    sM[wid][lane] = m;
+  }
+  __syncwarp();
   double acc = 0.0;
-  for (int bin = lane; bin < 256; bin += 32) {
-    const int c = h[bin];
-    if (c == 0) continue;
-    // the histogram is indexed (code of the lower leaf, code of the higher leaf)
-    const int c_lo = bin >> 4, c_hi = bin & 15;
-    const int cl = sw ? c_hi : c_lo, cr = sw ? c_lo : c_hi;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (c[q] == 0) continue;
+    const int bin = lane + 32 * q, ca = bin >> 4, cb = bin & 15;
     double x = 0.0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      double A = 0.0, B = 0.0;
+    for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (cl >> j & 1) A += __ldg(Pl + j * 4 + i);
-        if (cr >> j & 1) B += __ldg(Pr + j * 4 + i);
-      }
-      x = fma(pi[i] * A, B, x);
-    }
-    acc = fma((double)c, log(x), acc);
+      for (int mm = 0; mm < 4; ++mm)
+        if ((ca >> jj & 1) && (cb >> mm & 1)) x += sM[wid][jj * 4 + mm];
+    acc = fma((double)c[q], log(x), acc);
   }
   acc = warp_sum(acc);
   if (lane == 0) ell_part[k * n_parts] = acc;

@@ -330,8 +330,6 @@ struct CoefArgs {
   const double* cum_r;
   double* suf_l;
   double* suf_r;
-  double* gB_l;  // [K] site-independent part of dELBO/d b_l[r][k]
-  double* gB_r;
   double* dlam_l;  // [N-1]
   double* dlam_r;
 };
@@ -359,10 +357,10 @@ __global__ void __launch_bounds__(256) bwd_coef_kernel(const CoefArgs a) {
     const double sl = a.suf_l[k] + av * laml, sr = a.suf_r[k] + av * lamr;  // sum_{r' >= r} a_{r'}[k] lam_{r'}
     a.suf_l[k] = sl;
     a.suf_r[k] = sr;
-    a.gB_l[k] = a.share * (W * laml - sl);
-    a.gB_r[k] = a.share * (W * lamr - sr);
-    dl = a.share * (av * (-a.cum_l[k] + (double)(r + 1) / laml) + W * (a.b_l[k] - 1.0 / laml));
-    dr = a.share * (av * (-a.cum_r[k] + (double)(r + 1) / lamr) + W * (a.b_r[k] - 1.0 / lamr));
+    // site-independent part of dELBO/d b[r][k] (priors and proposal density), pushed through b = -log(U)/lam at once
+    const double gBl = W * laml - sl, gBr = W * lamr - sr;
+    dl = a.share * (av * (-a.cum_l[k] + (double)(r + 1) / laml) + W * (a.b_l[k] - 1.0 / laml) + gBl * (-a.b_l[k] / laml));
+    dr = a.share * (av * (-a.cum_r[k] + (double)(r + 1) / lamr) + W * (a.b_r[k] - 1.0 / lamr) + gBr * (-a.b_r[k] / lamr));
   }
   const double tl = block_sum<256>(dl, red);
   const double tr = block_sum<256>(dr, red);
@@ -398,30 +396,32 @@ __global__ void zero_consumed_kernel(const int32_t* __restrict__ order, const in
   }
 }
 
-// db -> dlam through b = -log(U)/lam, and accumulation of the per-matrix dQ (vcsmc.py:353-358 reversed)
-__global__ void __launch_bounds__(256) bwd_branch_kernel(int r, int64_t K, int jc, const double* __restrict__ dt,
-                                                         const double* __restrict__ dQ_each, const double* __restrict__ gB_l,
-                                                         const double* __restrict__ gB_r, const double* __restrict__ b_l,
-                                                         const double* __restrict__ b_r, const double* __restrict__ lam_l,
-                                                         const double* __restrict__ lam_r, double* __restrict__ dQ_acc,
-                                                         double* __restrict__ dlam_l, double* __restrict__ dlam_r) {
+// per-site part of db -> dlam through b = -log(U)/lam, and accumulation of the per-matrix dQ (vcsmc.py:353-358 reversed).
+// Visits the `count` particles of `list` (null: all K) -- only particles the reverse merge visited carry a dP.
+__global__ void __launch_bounds__(256) bwd_branch_kernel(int r, int64_t count, const int32_t* __restrict__ list, int jc,
+                                                         const double* __restrict__ dt, const double* __restrict__ dQ_each,
+                                                         const double* __restrict__ b_l, const double* __restrict__ b_r,
+                                                         const double* __restrict__ lam_l, const double* __restrict__ lam_r,
+                                                         double* __restrict__ dQ_acc, double* __restrict__ dlam_l,
+                                                         double* __restrict__ dlam_r) {
   __shared__ double red[8];
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double dl = 0.0, dr = 0.0;
-  if (k < K) {
-    const double gl = dt[2 * k] + gB_l[k], gr = dt[2 * k + 1] + gB_r[k];
-    dl = gl * (-b_l[k] / lam_l[r]);
-    dr = gr * (-b_r[k] / lam_r[r]);
+  if (i < count) {
+    const int64_t k = list ? list[i] : i;
+    const int64_t m = list ? 2 * i : 2 * k;   // a listed run keeps its per-matrix results compact
+    dl = dt[m] * (-b_l[k] / lam_l[r]);
+    dr = dt[m + 1] * (-b_r[k] / lam_r[r]);
     if (!jc) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) dQ_acc[k * 16 + e] += dQ_each[(2 * k) * 16 + e] + dQ_each[(2 * k + 1) * 16 + e];
+      for (int e = 0; e < 16; ++e) dQ_acc[k * 16 + e] += dQ_each[m * 16 + e] + dQ_each[(m + 1) * 16 + e];
     }
   }
   const double tl = block_sum<256>(dl, red);
   const double tr = block_sum<256>(dr, red);
   if (threadIdx.x == 0) {
-    atomicAdd(dlam_l + r, tl);
-    atomicAdd(dlam_r + r, tr);
+    if (tl != 0.0) atomicAdd(dlam_l + r, tl);
+    if (tr != 0.0) atomicAdd(dlam_r + r, tr);
   }
 }
 
@@ -648,8 +648,6 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_dt = L.take<double>(2 * K);
     h->o_suf_l = L.take<double>(K);
     h->o_suf_r = L.take<double>(K);
-    h->o_gB_l = L.take<double>(E);
-    h->o_gB_r = L.take<double>(E);
     h->o_cleaf = L.take<double>(N);
     h->o_order_bwd = L.take<int32_t>(E);
     h->o_order_rec = L.take<int32_t>(E);
@@ -1119,7 +1117,6 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     a.b_l = h->p<double>(h->o_b_l) + (int64_t)r * K; a.b_r = h->p<double>(h->o_b_r) + (int64_t)r * K;
     a.cum_l = h->p<double>(h->o_cum_l) + (int64_t)r * K; a.cum_r = h->p<double>(h->o_cum_r) + (int64_t)r * K;
     a.suf_l = h->p<double>(h->o_suf_l); a.suf_r = h->p<double>(h->o_suf_r);
-    a.gB_l = h->p<double>(h->o_gB_l) + (int64_t)r * K; a.gB_r = h->p<double>(h->o_gB_r) + (int64_t)r * K;
     a.dlam_l = dlam_l; a.dlam_r = dlam_r;
     bwd_coef_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(a);
     VCSMC_LAUNCH_CHECK("bwd_coef_kernel");
@@ -1258,7 +1255,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
                                 h->p<int32_t>(h->o_v_order), nullptr, h->p<double>(h->o_v_P), h->pi, h->p<double>(h->o_v_coef), Vb, Vb, nc,
                                 h->jc, 1, h->p<double>(h->o_v_dP), dpi, st);
           if (rc) return rc;
-          rc = launch_transition_bwd(h->Q, h->p<double>(h->o_v_t2), h->p<double>(h->o_v_dP), 2 * Vb, h->jc, h->p<double>(h->o_v_dt),
+          rc = launch_transition_bwd(h->Q, h->p<double>(h->o_v_t2), h->p<double>(h->o_v_dP), 2 * Vb, h->jc, nullptr, h->p<double>(h->o_v_dt),
                                      h->jc ? nullptr : h->p<double>(h->o_v_dQ), st);
           if (rc) return rc;
           rc = launch_nested_reduce(r, Vb, h->jc, h->p<double>(h->o_v_dt), h->p<double>(h->o_v_dQ), h->p<double>(h->o_v_t2), h->lam_l,
@@ -1282,15 +1279,17 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     VCSMC_CUDA(cudaStreamSynchronize(st));
   }
 
-  // ---- dP -> (db, dQ) -> dlam
+  // ---- dP -> (db, dQ) -> dlam, for the particles the reverse merge visited
   for (int r = 0; r < N - 1; ++r) {
-    rc = launch_transition_bwd(h->Q, h->p<double>(h->o_t2) + (int64_t)r * 2 * K, h->p<double>(h->o_dP) + (int64_t)r * K * 32, 2 * K, h->jc,
-                               h->p<double>(h->o_dt), h->jc ? nullptr : h->p<double>(h->o_dQ_each), st);
+    const int64_t cnt = cnt_bwd[r];
+    if (cnt == 0) continue;
+    const int32_t* list = sorted_b ? h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K : nullptr;
+    rc = launch_transition_bwd(h->Q, h->p<double>(h->o_t2) + (int64_t)r * 2 * K, h->p<double>(h->o_dP) + (int64_t)r * K * 32, 2 * cnt, h->jc,
+                               list, h->p<double>(h->o_dt), h->jc ? nullptr : h->p<double>(h->o_dQ_each), st);
     if (rc) return rc;
-    bwd_branch_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(
-        r, K, h->jc, h->p<double>(h->o_dt), h->p<double>(h->o_dQ_each), h->p<double>(h->o_gB_l) + (int64_t)r * K,
-        h->p<double>(h->o_gB_r) + (int64_t)r * K, h->p<double>(h->o_b_l) + (int64_t)r * K, h->p<double>(h->o_b_r) + (int64_t)r * K,
-        h->lam_l, h->lam_r, h->p<double>(h->o_dQ_acc), dlam_l, dlam_r);
+    bwd_branch_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(
+        r, cnt, list, h->jc, h->p<double>(h->o_dt), h->p<double>(h->o_dQ_each), h->p<double>(h->o_b_l) + (int64_t)r * K,
+        h->p<double>(h->o_b_r) + (int64_t)r * K, h->lam_l, h->lam_r, h->p<double>(h->o_dQ_acc), dlam_l, dlam_r);
     VCSMC_LAUNCH_CHECK("bwd_branch_kernel");
   }
   if (!h->jc) {

@@ -33,13 +33,16 @@ __global__ void transition_fwd_kernel(const double* __restrict__ Q, const double
   for (int e = 0; e < 16; ++e) out[e] = X.a[e];
 }
 
+// `list` (optional): matrix i of the launch is matrix 2*list[i/2] + (i&1) of t / dP (the two matrices of a listed
+// particle); results are written compactly at i.
 __global__ void transition_bwd_kernel(const double* __restrict__ Q, const double* __restrict__ t,
-                                      const double* __restrict__ dP, int64_t n, int jc, double* __restrict__ dt,
-                                      double* __restrict__ dQ_each) {
+                                      const double* __restrict__ dP, int64_t n, int jc, const int32_t* __restrict__ list,
+                                      double* __restrict__ dt, double* __restrict__ dQ_each) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const double ti = t[i];
-  const double* G = dP + i * 16;
+  const int64_t src = list ? 2 * (int64_t)list[i >> 1] + (i & 1) : i;
+  const double ti = t[src];
+  const double* G = dP + src * 16;
   if (jc) {
     // compressed adjoint: G[0] = sum_i dP_ii, G[1] = sum_{i!=j} dP_ij;  d' = -3/4 e^-t, o' = 1/4 e^-t
     const double e = exp(-ti);
@@ -87,10 +90,10 @@ int launch_transition_fwd(const double* Q, const double* t, int64_t n, int jc, d
   return VCSMC_OK;
 }
 
-int launch_transition_bwd(const double* Q, const double* t, const double* dP, int64_t n, int jc, double* dt,
-                          double* dQ_each, cudaStream_t st) {
+int launch_transition_bwd(const double* Q, const double* t, const double* dP, int64_t n, int jc, const int32_t* list,
+                          double* dt, double* dQ_each, cudaStream_t st) {
   if (n <= 0) return VCSMC_OK;
-  transition_bwd_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(Q, t, dP, n, jc, dt, dQ_each);
+  transition_bwd_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(Q, t, dP, n, jc, list, dt, dQ_each);
   VCSMC_LAUNCH_CHECK("transition_bwd_kernel");
   return VCSMC_OK;
 }
