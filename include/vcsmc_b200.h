@@ -176,6 +176,9 @@ int vcsmc_sweep_set_comm(vcsmc_sweep_t* h, int rank, int world, vcsmc_comm_fn fn
  * (site sharding: 1 on rank 0, 0 elsewhere, then sum the gradients across ranks);
  * "skip_zero" (default 1): backward skips rank events whose adjoint is exactly zero (W underflowed to 0 and no
  * descendant uses the node) -- results are identical, set 0 to force the dense reverse sweep;
+ * "skip_below" (default 2^-64): with skip_zero, an adjoint coefficient dELBO/d ell of magnitude <= skip_below * |grad_elbo|
+ * counts as zero (softmax weights of 1e-200 are representable in fp64 but cannot change any digit of the gradient:
+ * the event's coefficients sum to O(1)); 0 restores "exactly zero only" -- gradients agree to ~1e-15 relative;
  * "max_chunk_sites" (default 0 = unlimited): cap on the site chunk of the recompute backward (testing aid);
  * "lazy" (default 1; VCSMC proposal only): the forward scores every particle without storing its node and materialises
  * only the particles that the next resampling draws as an ancestor; 0 = eager (every node stored as it is computed) --

@@ -73,7 +73,7 @@ int vcsmc_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* po
                     const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc, const double* P, const double* pi,
                     const double* coef, int64_t K, int n_sites, int jc, double* dP, double* dpi, void* stream) {
   if (!lsrc || !rsrc || !P || !pi || !coef || !dP || K < 0 || n_sites < 0 || slot_sites < n_sites) { set_error("merge_bwd: bad argument"); return VCSMC_ERR_ARG; }
-  return launch_merge_bwd(codes, codes_stride, pool, gpool, slot_sites, lsrc, rsrc, gsrc, nullptr, nullptr, P, pi, coef, K, -1, n_sites, jc, 0, dP, dpi, (cudaStream_t)stream);
+  return launch_merge_bwd(codes, codes_stride, pool, gpool, slot_sites, lsrc, rsrc, gsrc, nullptr, nullptr, P, pi, coef, K, -1, n_sites, jc, 0, 0.0, dP, dpi, (cudaStream_t)stream);
 }
 
 int vcsmc_propose_pairs(const float* u, int64_t K, int n, int32_t* coal, int32_t* rem, void* stream) {

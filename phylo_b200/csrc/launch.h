@@ -16,7 +16,7 @@ int launch_ell_reduce(const double* ell_part, int n_part, int64_t K, double* ell
 int launch_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* pool, double* gpool, int64_t slot_sites,
                      const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc, const int32_t* order,
                      const int32_t* count, const double* P, const double* pi, const double* coef, int64_t K,
-                     int64_t n_active, int n_sites, int jc, int skip_zero, double* dP, double* dpi_acc, cudaStream_t st);
+                     int64_t n_active, int n_sites, int jc, int skip_zero, double skip_below, double* dP, double* dpi_acc, cudaStream_t st);
 
 // score.cu (lazy forward: likelihood-only scoring, survivor materialisation, peer pulls)
 int64_t leaf_pair_hist_ints(int N);

@@ -26,15 +26,25 @@
 namespace vcsmc {
 namespace {
 
+// u_res == null: the resampling uniform of logical particle k at rank event r comes straight from the counter-based
+// generator (the same value philox_step_kernel would write: counter (k, r, 1, 0), first two words)
 __global__ void lz_ancestors_kernel(int first, int64_t K, const double* __restrict__ cdf, const double* __restrict__ u_res,
-                                    int32_t* __restrict__ anc, int32_t* __restrict__ surv) {
+                                    uint64_t seed, int r, int32_t* __restrict__ anc, int32_t* __restrict__ surv) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   if (first) {
     anc[k] = (int32_t)k;
     return;
   }
-  const int idx = upper_bound_cdf(cdf, K, u_res[k] * cdf[K - 1]);  // resample, vcsmc.py:284-285
+  double u;
+  if (u_res) {
+    u = u_res[k];
+  } else {
+    uint32_t d[4] = {(uint32_t)k, (uint32_t)((uint64_t)k >> 32) | ((uint32_t)r << 8), 1u, 0u};
+    philox4x32_10(d, (uint32_t)seed, (uint32_t)(seed >> 32));
+    u = u64_to_unit_f64(d[0], d[1]);
+  }
+  const int idx = upper_bound_cdf(cdf, K, u * cdf[K - 1]);  // resample, vcsmc.py:284-285
   anc[k] = idx;
   surv[idx] = 1;
 }
@@ -428,12 +438,8 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
       rc = launch_philox_step(h->seed, r, k0, Kl, n, h->p<float>(h->o_u_pair), h->p<double>(h->o_u_bl), h->p<double>(h->o_u_br),
                               nullptr, nullptr, st);
       if (rc) return rc;
-      if (r > 0) {
-        rc = launch_philox_step(h->seed, r, 0, K, 0, nullptr, nullptr, nullptr, h->p<double>(h->o_u_res_all), nullptr, st);
-        if (rc) return rc;
-      }
       u_pair = h->p<float>(h->o_u_pair); u_bl = h->p<double>(h->o_u_bl); u_br = h->p<double>(h->o_u_br);
-      u_res_all = h->p<double>(h->o_u_res_all);
+      u_res_all = nullptr;   // drawn inside lz_ancestors_kernel
     } else {
       u_pair = h->x_pair + pair_off + k0 * n; u_bl = h->x_bl + (int64_t)r * K + k0; u_br = h->x_br + (int64_t)r * K + k0;
       u_res_all = h->x_res + (int64_t)r * K;
@@ -450,7 +456,7 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
       if (gc) VCSMC_CUDA(cudaMemsetAsync(flags, 0, (size_t)h->pool_slots * sizeof(int32_t), st));
       count_launch(3);
     }
-    lz_ancestors_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(r == 0, K, h->p<double>(h->o_cdf), u_res_all, anc_row, surv);
+    lz_ancestors_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(r == 0, K, h->p<double>(h->o_cdf), u_res_all, h->seed, r, anc_row, surv);
     VCSMC_LAUNCH_CHECK("lz_ancestors_kernel");
     if (r > 0) {
       const int64_t e_base_prev = (int64_t)(r - 1) * K + k0;

@@ -219,6 +219,7 @@ struct BwdArgs {
   double* dP;        // [K][32]
   double* dpi_acc;   // [4] accumulated over all particles, or null
   int skip_zero;
+  double skip_below;  // |coefficient| at or below this counts as zero (0: exact zeros only)
 };
 
 template <int SPT>
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(kTileThreads, JC ? 2 : 1) merge_bwd_kernel(con
     for (int j = 0; j < nj; ++j) {
       const double c = s_c[j];
       const int gs = s_g[j];
-      if (a.skip_zero && c == 0.0 && gs < 0) continue;  // exact zero adjoint: nothing to propagate
+      if (a.skip_zero && fabs(c) <= a.skip_below && gs < 0) continue;  // (numerically) zero adjoint: nothing to propagate
       const int ca = s_a[j], cb = s_b[j];
       if (ca != pa) {
         flush_adjoint<SPT>(pa, a.gpool, a.slot_sites, sbase, a.n_sites, Ga);
@@ -486,13 +487,13 @@ int launch_ell_reduce(const double* ell_part, int n_part, int64_t K, double* ell
 int launch_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* pool, double* gpool, int64_t slot_sites,
                      const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc, const int32_t* order,
                      const int32_t* count, const double* P, const double* pi, const double* coef, int64_t K,
-                     int64_t n_active, int n_sites, int jc, int skip_zero, double* dP, double* dpi_acc, cudaStream_t st) {
+                     int64_t n_active, int n_sites, int jc, int skip_zero, double skip_below, double* dP, double* dpi_acc, cudaStream_t st) {
   if (K <= 0 || n_sites <= 0 || n_active == 0) return VCSMC_OK;
   const int64_t Kw = n_active > 0 ? n_active : K;
   BwdArgs a;
   a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.gpool = gpool; a.slot_sites = slot_sites;
   a.lsrc = lsrc; a.rsrc = rsrc; a.gsrc = gsrc; a.order = order; a.count = count; a.P = P; a.pi = pi;
-  a.coef = coef; a.K = K; a.n_sites = n_sites; a.dP = dP; a.dpi_acc = dpi_acc; a.skip_zero = skip_zero;
+  a.coef = coef; a.K = K; a.n_sites = n_sites; a.dP = dP; a.dpi_acc = dpi_acc; a.skip_zero = skip_zero; a.skip_below = skip_below;
   static int gspt = -1;  // tuning knob (debug): VCSMC_BWD_SPT = 1 | 2 sites per thread in the general-Q reverse merge
   if (gspt < 0) {
     const char* e = getenv("VCSMC_BWD_SPT");

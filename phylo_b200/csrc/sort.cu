@@ -65,12 +65,20 @@ __global__ void __launch_bounds__(256) group_insert_kernel(const int32_t* __rest
   }
 }
 
+// group order is irrelevant, so offsets need no scan: every occupied table slot reserves its range with one atomic
+__global__ void __launch_bounds__(256) group_offsets_kernel(int64_t T, const int32_t* __restrict__ cnt, int32_t* __restrict__ off,
+                                                            int32_t* __restrict__ cursor) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  const int c = cnt[i];
+  if (c > 0) off[i] = atomicAdd(cursor, c);
+}
+
 __global__ void __launch_bounds__(256) group_scatter_kernel(int64_t K, int64_t T, const int32_t* __restrict__ cnt,
                                                             const int32_t* __restrict__ off, const int32_t* __restrict__ gslot,
                                                             const int32_t* __restrict__ grank, int32_t* __restrict__ order,
                                                             int32_t* __restrict__ count_out) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k == 0 && count_out) count_out[0] = off[T - 1] + cnt[T - 1];
   if (k >= K) return;
   const int s = gslot[k];
   if (s >= 0) order[off[s] + grank[k]] = (int32_t)k;
@@ -91,13 +99,14 @@ int launch_group_order(const int32_t* lsrc, const int32_t* rsrc, const int32_t* 
   const int64_t T = group_table_entries(K);
   int log2T = 0;
   while (((int64_t)1 << log2T) < T) ++log2T;
-  VCSMC_CUDA(cudaMemsetAsync(tab, 0, (size_t)T * sizeof(unsigned long long), st));
-  VCSMC_CUDA(cudaMemsetAsync(cnt, 0, (size_t)T * sizeof(int32_t), st));
+  // tab [T] u64 and cnt [T] i32 are carved back to back: one memset; count_out doubles as the range cursor
+  VCSMC_CUDA(cudaMemsetAsync(tab, 0, (size_t)T * (sizeof(unsigned long long) + sizeof(int32_t)), st));
+  VCSMC_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int32_t), st));
   count_launch(2);
   group_insert_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(lsrc, rsrc, active, K, log2T, tab, cnt, gslot, grank);
   VCSMC_LAUNCH_CHECK("group_insert_kernel");
-  VCSMC_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, cnt, off, (int)T, st));
-  count_launch(2);
+  group_offsets_kernel<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(T, cnt, off, count_out);
+  VCSMC_LAUNCH_CHECK("group_offsets_kernel");
   group_scatter_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(K, T, cnt, off, gslot, grank, order_out, count_out);
   VCSMC_LAUNCH_CHECK("group_scatter_kernel");
   return VCSMC_OK;

@@ -372,12 +372,12 @@ __global__ void __launch_bounds__(256) bwd_coef_kernel(const CoefArgs a) {
 
 // which particles of rank event r the reverse sweep / the chunk recompute must visit
 __global__ void bwd_active_kernel(const double* __restrict__ cnew, const int32_t* __restrict__ consumed, int64_t K,
-                                  int skip_zero, int32_t* __restrict__ act_bwd, int32_t* __restrict__ act_rec) {
+                                  int skip_zero, double skip_below, int32_t* __restrict__ act_bwd, int32_t* __restrict__ act_rec) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   const int c = consumed[k];
   act_rec[k] = c;
-  act_bwd[k] = c || !(skip_zero && cnew[k] == 0.0);  // one visiting order serves the recompute and the reverse sweep
+  act_bwd[k] = c || !(skip_zero && fabs(cnew[k]) <= skip_below);  // one visiting order serves the recompute and the reverse sweep
 }
 
 // zero the adjoint slots of the consumed nodes of one rank event (the first *count entries of `order`)
@@ -620,8 +620,8 @@ int64_t plan(vcsmc_sweep* h) {
   h->o_count = L.take<int32_t>(4);
   {
     const int64_t T = group_table_entries(K);
-    h->o_gtab = L.take<unsigned long long>(T);
-    h->o_gcnt = L.take<int32_t>(T);
+    h->o_gtab = L.take<unsigned long long>(T + T / 2);   // hash keys [T] u64 immediately followed by the counts [T] i32
+    h->o_gcnt = h->o_gtab + T * (int64_t)sizeof(unsigned long long);
     h->o_goff = L.take<int32_t>(T);
     h->o_gslot = L.take<int32_t>(K);
     h->o_grank = L.take<int32_t>(K);
@@ -820,6 +820,7 @@ int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value) {
   if (!h || !name) return VCSMC_ERR_ARG;
   if (!strcmp(name, "scalar_share")) h->scalar_share = value;
   else if (!strcmp(name, "skip_zero")) h->skip_zero = value != 0.0;
+  else if (!strcmp(name, "skip_below")) h->skip_below = value < 0.0 ? 0.0 : value;
   else if (!strcmp(name, "max_chunk_sites")) h->max_chunk_sites = (int)value;
   else if (!strcmp(name, "lazy")) {
     if (value == 0.0 && h->world > 1) { set_error("particle sharding needs the lazy forward"); return VCSMC_ERR_STATE; }
@@ -1145,7 +1146,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   if (sorted_b) {
     for (int r = 0; r < N - 1; ++r) {
       bwd_active_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(h->p<double>(h->o_cnew) + (int64_t)r * K, h->p<int32_t>(h->o_consumed) + (int64_t)r * K,
-                                                                   K, h->skip_zero, h->p<int32_t>(h->o_act_bwd), h->p<int32_t>(h->o_act_rec));
+                                                                   K, h->skip_zero, h->skip_below * fabs(grad_elbo), h->p<int32_t>(h->o_act_bwd), h->p<int32_t>(h->o_act_rec));
       VCSMC_LAUNCH_CHECK("bwd_active_kernel");
       const int32_t* bl = h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K;
       const int32_t* br = h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K;
@@ -1253,7 +1254,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
           if (rc) return rc;
           rc = launch_merge_bwd(codes_c, S, lpool, gpool, Sc, h->p<int32_t>(h->o_v_lsrc), h->p<int32_t>(h->o_v_rsrc), nullptr,
                                 h->p<int32_t>(h->o_v_order), nullptr, h->p<double>(h->o_v_P), h->pi, h->p<double>(h->o_v_coef), Vb, Vb, nc,
-                                h->jc, 1, h->p<double>(h->o_v_dP), dpi, st);
+                                h->jc, 1, 0.0, h->p<double>(h->o_v_dP), dpi, st);
           if (rc) return rc;
           rc = launch_transition_bwd(h->Q, h->p<double>(h->o_v_t2), h->p<double>(h->o_v_dP), 2 * Vb, h->jc, nullptr, h->p<double>(h->o_v_dt),
                                      h->jc ? nullptr : h->p<double>(h->o_v_dQ), st);
@@ -1267,7 +1268,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
       h->prof_begin(2, st);
       rc = launch_merge_bwd(codes_c, S, lpool, gpool, Sc, h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K, h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K,
                             h->p<int32_t>(h->o_bsrc_g) + (int64_t)r * K, sorted_b ? h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K : nullptr, sorted_b ? h->p<int32_t>(h->o_count_bwd) + r : nullptr,
-                            h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, h->p<double>(h->o_cnew) + (int64_t)r * K, K, cnt_bwd[r], nc, h->jc, h->skip_zero,
+                            h->p<double>(h->o_P) + (int64_t)r * K * 32, h->pi, h->p<double>(h->o_cnew) + (int64_t)r * K, K, cnt_bwd[r], nc, h->jc, h->skip_zero, h->skip_below * fabs(grad_elbo),
                             h->p<double>(h->o_dP) + (int64_t)r * K * 32, dpi, st);
       h->prof_end(st);
       if (rc) return rc;

@@ -118,6 +118,7 @@ struct vcsmc_sweep {
   void* allreduce_user = nullptr;
   double scalar_share = 1.0;
   int skip_zero = 1;
+  double skip_below = 5.421010862427522e-20;  // 2^-64: adjoint coefficients this small (relative to dELBO = 1) are treated as zero
   int max_chunk_sites = 0;  // testing aid: cap the backward site chunk (0 = as large as memory allows)
   // model pointers of the last forward (caller keeps them alive until backward)
   const uint8_t* codes = nullptr;

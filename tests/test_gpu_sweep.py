@@ -24,7 +24,7 @@ def dev(x):
 
 
 def run_gpu(ops, genome, K, p, U, jc, workspace_bytes=None, grads=True, skip_zero=True, max_chunk_sites=0, lazy=True,
-            force_gc=False):
+            force_gc=False, skip_below=None):
     N, S = genome.shape[0], genome.shape[1]
     codes = ops.pack_alignment(dev(genome))
     lam_l, lam_r, Q, pi = O.model_from_params(p)
@@ -35,6 +35,8 @@ def run_gpu(ops, genome, K, p, U, jc, workspace_bytes=None, grads=True, skip_zer
     sw.set_option("lazy", 1.0 if lazy else 0.0)
     if force_gc:
         sw.set_option("force_gc", 1.0)
+    if skip_below is not None:
+        sw.set_option("skip_below", float(skip_below))
     elbo = sw.forward(codes, dev(lam_l), dev(lam_r), None if jc else dev(Q), dev(pi.reshape(-1)))
     out = {k: sw.output(k).cpu().numpy().copy() for k in
            ("log_weights", "log_likelihood", "log_likelihood_tilde", "log_likelihood_R", "left_branches",
@@ -107,6 +109,13 @@ def test_sweep_primate_full(ops, primate_genome, jc):
     compare_forward(out, res, N, K)
     compare_grads(grads, g_ref, jc)
     assert -7600 < out["elbo"] < -6500   # where the README figure's curves start
+    # adjoint coefficients below 2^-64 are skipped by default; "exact zeros only" visits more events, same gradients
+    out0, grads0, _ = run_gpu(ops, g, K, p, U, jc, skip_below=0.0)
+    assert out0["info"]["backward_events_visited"] >= out["info"]["backward_events_visited"]
+    for a, b in zip(grads, grads0):
+        if a is not None:
+            np.testing.assert_allclose(a, b, rtol=1e-11, atol=1e-13 * np.abs(b).max())
+    compare_grads(grads0, g_ref, jc)
 
 
 @pytest.mark.parametrize("lazy", [True, False])
