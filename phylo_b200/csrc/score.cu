@@ -24,6 +24,7 @@ namespace vcsmc {
 namespace {
 
 constexpr int kRScore = 32;  // particles per scoring group
+constexpr int kCoef = 20;    // doubles per particle in shared memory: M[4][4] (or the 4 JC coefficients) + the column sums of M
 
 struct ScoreArgs {
   const uint8_t* codes;
@@ -45,7 +46,7 @@ struct ScoreArgs {
   double* ell_part;  // [K][n_chunks][kWarps]
 };
 
-constexpr int kScoreSmemBytes = kRScore * 16 * 8 + kRScore * kTileThreads * (8 + 4);
+constexpr int kScoreSmemBytes = kRScore * kCoef * 8 + kRScore * kTileThreads * (8 + 4);
 
 // site products of one child pair for the SPT sites of a thread: general Q -> the 16 products L_a[i] L_b[m];
 // JC -> (sa sb, sa (pi.L_b), (pi.L_a) sb, sum_i pi_i L_a[i] L_b[i]).  Sites past the end get zeros.
@@ -95,11 +96,30 @@ __device__ __forceinline__ void site_products(const ChildSpace& a, int ca, int c
   }
 }
 
-// One tile of SPT*256 sites for the nj particles of a group.  The running product of the site likelihoods of
-// (thread, particle) is kept as (mantissa product, BIASED exponent sum) in shared memory.  The split is three integer
-// ops per site; a likelihood that is not a positive normal number (0, subnormal, inf, NaN, negative) poisons the
-// mantissa product with NaN and the particle is re-evaluated with one log per site afterwards (never on sane inputs).
-// Sites past the end of the alignment have zero site products and x0 = 1, i.e. x = 1.
+// fold the SPT site likelihoods x[] of one particle into its running (mantissa product, biased exponent sum)
+template <int SPT>
+__device__ __forceinline__ void fold_sites(const double (&x)[SPT], bool renorm, double* prod, int* expo) {
+  double pr = *prod;
+  int ex = *expo;
+  bool odd = false;
+#pragma unroll
+  for (int q = 0; q < SPT; ++q) {
+    const int hi = __double2hiint(x[q]);
+    const unsigned e = (unsigned)hi >> 20;  // biased exponent (sign bit included: negative values are "odd")
+    odd |= (e - 1u) >= 0x7feu;
+    ex += (int)e;
+    pr *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x[q]));
+  }
+  if (odd) pr = __longlong_as_double(0x7ff8000000000000ll);
+  if (renorm) {  // keep the mantissa product far from 2^1024 (NaN stays NaN)
+    const int hi = __double2hiint(pr);
+    ex += (int)(((unsigned)hi >> 20) & 0x7ffu) - 1023;
+    if ((((unsigned)hi >> 20) & 0x7ffu) != 0x7ffu) pr = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(pr));
+  }
+  *prod = pr;
+  *expo = ex;
+}
+
 // NP particles (that share the current child pair) against the SPT sites of this thread: NP*SPT*2 independent FMA
 // chains (each site likelihood is accumulated in an even and an odd half) -- the FP64 pipe has a long dependent-issue
 // latency and only 4 warps per scheduler fit, so the instruction-level parallelism has to come from here.
@@ -119,7 +139,7 @@ __device__ __forceinline__ void score_particles(int j, const double (&C)[SPT][JC
   for (int c = 0; c < NC; c += 2) {
     double2 m[NP];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) m[p] = *reinterpret_cast<const double2*>(sC + (j + p) * 16 + c);
+    for (int p = 0; p < NP; ++p) m[p] = *reinterpret_cast<const double2*>(sC + (j + p) * kCoef + c);
 #pragma unroll
     for (int p = 0; p < NP; ++p)
 #pragma unroll
@@ -130,26 +150,32 @@ __device__ __forceinline__ void score_particles(int j, const double (&C)[SPT][JC
   }
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
-    double pr = my_prod[(j + p) * kTileThreads];
-    int ex = my_exp[(j + p) * kTileThreads];
-    bool odd = false;
+    double x[SPT];
+#pragma unroll
+    for (int q = 0; q < SPT; ++q) x[q] = xe[p][q] + xo[p][q];
+    fold_sites<SPT>(x, renorm, my_prod + (j + p) * kTileThreads, my_exp + (j + p) * kTileThreads);
+  }
+}
+
+// The same when child a is a LEAF with a one-hot (or all-ones) state mask at every site of this thread: the site
+// likelihood is row `state` of M (or the column sums of M) dotted with L_b -- 4 DFMA per site instead of 16.  The row is
+// fetched from shared memory per lane (offset roff = 4 * state, or 16 for a gap).
+template <int SPT, int NP>
+__device__ __forceinline__ void score_particles_leaf(int j, const double (&Lb)[SPT][16], const int (&roff)[SPT],
+                                                     const double (&x0)[SPT], bool renorm, const double* sC, double* my_prod,
+                                                     int* my_exp) {
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    double x[SPT];
 #pragma unroll
     for (int q = 0; q < SPT; ++q) {
-      const double x = xe[p][q] + xo[p][q];
-      const int hi = __double2hiint(x);
-      const unsigned e = (unsigned)hi >> 20;  // biased exponent (sign bit included: negative values are "odd")
-      odd |= (e - 1u) >= 0x7feu;
-      ex += (int)e;
-      pr *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+      const double2* row = reinterpret_cast<const double2*>(sC + (j + p) * kCoef + roff[q]);
+      const double2 r0 = row[0], r1 = row[1];
+      const double xe = fma(r0.y, Lb[q][1], fma(r0.x, Lb[q][0], x0[q]));
+      const double xo = fma(r1.y, Lb[q][3], r1.x * Lb[q][2]);
+      x[q] = xe + xo;
     }
-    if (odd) pr = __longlong_as_double(0x7ff8000000000000ll);
-    if (renorm) {  // keep the mantissa product far from 2^1024 (NaN stays NaN)
-      const int hi = __double2hiint(pr);
-      ex += (int)(((unsigned)hi >> 20) & 0x7ffu) - 1023;
-      if ((((unsigned)hi >> 20) & 0x7ffu) != 0x7ffu) pr = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(pr));
-    }
-    my_prod[(j + p) * kTileThreads] = pr;
-    my_exp[(j + p) * kTileThreads] = ex;
+    fold_sites<SPT>(x, renorm, my_prod + (j + p) * kTileThreads, my_exp + (j + p) * kTileThreads);
   }
 }
 
@@ -165,8 +191,13 @@ __device__ __forceinline__ void score_tile(const ChildSpace& a, int nj, int sbas
   int pa = kNone, pb = kNone;
   double C[SPT][NC];
   double x0[SPT];
+  int roff[SPT];
+  bool leaf_rows = false;  // current pair = (leaf with one-hot / gap masks, internal node): use the 4-DFMA path
 #pragma unroll
-  for (int q = 0; q < SPT; ++q) x0[q] = (sbase + q * kTileThreads < a.n_sites) ? 0.0 : 1.0;
+  for (int q = 0; q < SPT; ++q) {
+    x0[q] = (sbase + q * kTileThreads < a.n_sites) ? 0.0 : 1.0;
+    roff[q] = 0;
+  }
   int j = 0;
   while (j < nj) {
     const int ca = s_a[j], cb = s_b[j];
@@ -175,17 +206,43 @@ __device__ __forceinline__ void score_tile(const ChildSpace& a, int nj, int sbas
       continue;
     }
     if (ca != pa || cb != pb) {
-      site_products<JC, SPT, NC>(a, ca, cb, sbase, pi, C);
+      leaf_rows = false;
+      if (!JC && ca < 0 && cb >= 0) {
+        // leaf + internal node: try the row path (every site of this warp must have a one-hot or all-ones mask)
+        const uint8_t* crow = a.codes + (int64_t)(-ca - 1) * a.codes_stride;
+        const double* node = a.pool + (int64_t)cb * a.slot_sites * 4;
+        bool ok = true;
+#pragma unroll
+        for (int q = 0; q < SPT; ++q) {
+          const int s = sbase + q * kTileThreads;
+          if (s < a.n_sites) {
+            const int code = __ldg(crow + s) & 15;
+            const d4 L = ld_site(node + (int64_t)s * 4);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) C[q][m % NC] = L.v[m];
+            roff[q] = code == 15 ? 16 : 4 * (__ffs(code) - 1);
+            ok = ok && (code == 15 || (code & (code - 1)) == 0);
+          } else {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) C[q][m % NC] = 0.0;
+            roff[q] = 0;
+          }
+        }
+        leaf_rows = __all_sync(0xffffffffu, ok);
+      }
+      if (!leaf_rows) site_products<JC, SPT, NC>(a, ca, cb, sbase, pi, C);
       pa = ca;
       pb = cb;
     }
-    if (j + 1 < nj && s_a[j + 1] == ca && s_b[j + 1] == cb) {
-      score_particles<JC, SPT, 2>(j, C, x0, renorm, sC, my_prod, my_exp);
-      j += 2;
+    const bool two = j + 1 < nj && s_a[j + 1] == ca && s_b[j + 1] == cb;
+    if (!JC && leaf_rows) {
+      if (two) score_particles_leaf<SPT, 2>(j, reinterpret_cast<const double(&)[SPT][16]>(C), roff, x0, renorm, sC, my_prod, my_exp);
+      else score_particles_leaf<SPT, 1>(j, reinterpret_cast<const double(&)[SPT][16]>(C), roff, x0, renorm, sC, my_prod, my_exp);
     } else {
-      score_particles<JC, SPT, 1>(j, C, x0, renorm, sC, my_prod, my_exp);
-      j += 1;
+      if (two) score_particles<JC, SPT, 2>(j, C, x0, renorm, sC, my_prod, my_exp);
+      else score_particles<JC, SPT, 1>(j, C, x0, renorm, sC, my_prod, my_exp);
     }
+    j += two ? 2 : 1;
   }
 }
 
@@ -214,7 +271,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
   constexpr int NC = JC ? 4 : 16;  // coefficients per particle == site products per site
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sC = reinterpret_cast<double*>(smem_raw);                    // [R][16] per-particle coefficients
-  double* s_prod = sC + kRScore * 16;                                   // [R][256] running mantissa products
+  double* s_prod = sC + kRScore * kCoef;                                 // [R][256] running mantissa products
   int* s_exp = reinterpret_cast<int*>(s_prod + kRScore * kTileThreads); // [R][256] running (biased) exponent sums
   __shared__ int s_k[kRScore], s_a[kRScore], s_b[kRScore];
   __shared__ unsigned s_odd;
@@ -252,10 +309,10 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
         const double* Pa = a.P + k * 32 + (sw ? 16 : 0);
         const double* Pb = a.P + k * 32 + (sw ? 0 : 16);
         const double oa = __ldg(Pa + 1), da = __ldg(Pa) - oa, ob = __ldg(Pb + 1), db = __ldg(Pb) - ob;
-        sC[tid * 16 + 0] = oa * ob * ((pi[0] + pi[1]) + (pi[2] + pi[3]));
-        sC[tid * 16 + 1] = oa * db;
-        sC[tid * 16 + 2] = da * ob;
-        sC[tid * 16 + 3] = da * db;
+        sC[tid * kCoef + 0] = oa * ob * ((pi[0] + pi[1]) + (pi[2] + pi[3]));
+        sC[tid * kCoef + 1] = oa * db;
+        sC[tid * kCoef + 2] = da * ob;
+        sC[tid * kCoef + 3] = da * db;
       }
     } else {
       for (int e = tid; e < nj * 16; e += kTileThreads) {
@@ -268,7 +325,12 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
         double m = pi[0] * __ldg(Pa) * __ldg(Pb);
 #pragma unroll
         for (int i = 1; i < 4; ++i) m = fma(pi[i] * __ldg(Pa + i), __ldg(Pb + i), m);
-        sC[j * 16 + ai * 4 + bi] = m;
+        sC[j * kCoef + ai * 4 + bi] = m;
+      }
+      __syncthreads();
+      for (int e = tid; e < nj * 4; e += kTileThreads) {  // column sums: the likelihood row of a gap in child a
+        const int j = e >> 2, m = e & 3;
+        sC[j * kCoef + 16 + m] = (sC[j * kCoef + m] + sC[j * kCoef + 4 + m]) + (sC[j * kCoef + 8 + m] + sC[j * kCoef + 12 + m]);
       }
     }
     for (int j = 0; j < nj; ++j) {
@@ -299,7 +361,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
       double acc;
       if (odd_all >> j & 1u) {
         // some likelihood of this particle is 0 / subnormal / not finite: one log per site, like the reference
-        acc = score_slow<JC>(cs, s_a[j], s_b[j], sC + j * 16, t_begin * (kTileThreads * SPT),
+        acc = score_slow<JC>(cs, s_a[j], s_b[j], sC + j * kCoef, t_begin * (kTileThreads * SPT),
                              min(a.n_sites, t_end * (kTileThreads * SPT)), pi[0], pi[1], pi[2], pi[3]);
       } else {
         const double ex = (double)(my_exp[j * kTileThreads] - bias);
