@@ -170,7 +170,10 @@ int vcsmc_sweep_set_allreduce(vcsmc_sweep_t* h, vcsmc_allreduce_fn fn, void* use
  * every rank scores its particles on all sites; per rank event one all-gather of the step record (weights, branch
  * lengths, child references), identical ancestors on every rank, owners materialise the survivors, ranks that drew a
  * remote ancestor pull the nodes they lack over NVLink.  Backward: sharded by SITE on the gathered tables
- * (options "site_begin"/"site_end"), gradients are summed by the caller.  VCSMC proposal only (n_sub == 0). */
+ * (options "site_begin"/"site_end"), gradients are summed by the caller.  VCSMC proposal only (n_sub == 0).
+ * `fn` may be NULL: by default (option "peer_sync") the synchronisations and the record exchange of the forward run
+ * over peer memory and nothing goes through the hook.  The caller must synchronise the ranks (any barrier) between
+ * this call and the first forward. */
 int vcsmc_sweep_set_comm(vcsmc_sweep_t* h, int rank, int world, vcsmc_comm_fn fn, void* user, void* const* peer_ws_host);
 /* Options: "scalar_share" (default 1): fraction of the site-independent gradient terms this rank contributes
  * (site sharding: 1 on rank 0, 0 elsewhere, then sum the gradients across ranks);
@@ -185,6 +188,9 @@ int vcsmc_sweep_set_comm(vcsmc_sweep_t* h, int rank, int world, vcsmc_comm_fn fn
  * results are identical;
  * "leaf_patterns" (default 1; lazy forward): merges of two leaves are scored from the site-pattern counts of the leaf
  * pair (tabulated once per sweep) instead of site by site -- same sum, different summation order;
+ * "peer_sync" (default 1; particle sharding): the two synchronisations of a rank event and the exchange of the step
+ * record run over peer memory (flag barrier kernel, peer loads) with no host involvement; 0 routes them through the
+ * collective hook (VCSMC_COMM_BARRIER / VCSMC_COMM_ALLGATHER) instead;
  * "force_gc" (default 0): use the garbage-collected pool and the recompute backward even when every node fits (testing aid);
  * "site_begin", "site_end" (default 0, n_sites): the site slice this rank's reverse sweep covers;
  * "profile" (default 0): record CUDA events around every merge launch, read with vcsmc_sweep_profile. */

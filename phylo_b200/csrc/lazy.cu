@@ -289,6 +289,7 @@ struct RecArgs {
   int n, rank;
   int64_t Kl, k0, K, stride;
   char* rec;
+  const char* peer_rec[kMaxPeers];  // null: every chunk has been gathered into `rec` (collective hook); else read chunk g from peer g
   double* lw;
   double* LL;
   double* ell;  // ell_node + N + r*K
@@ -303,6 +304,35 @@ struct RecArgs {
   int32_t* vminus;
   uint8_t* rempos;
 };
+
+// Cross-GPU barrier without the host: lane g stores this rank's epoch into peer g's flag array (peer store over
+// NVLink, system scope) and then spins until peer g's epoch has arrived in this rank's own array.  Every GPU runs
+// its own stream, so the store a lane waits for never depends on this kernel.  A timeout (~4 s) turns a lost peer
+// into a reported error instead of a hang.
+struct SigArgs {
+  int32_t* peer_sig[kMaxPeers];  // peer g's flag array (own array at index rank)
+  int rank, world, epoch;
+  int32_t* status;
+};
+
+__global__ void lz_barrier_kernel(const SigArgs a) {
+  const int g = threadIdx.x;
+  if (g >= a.world) return;
+  __threadfence_system();
+  volatile int32_t* out = a.peer_sig[g] + a.rank;
+  *out = a.epoch;
+  __threadfence_system();
+  volatile int32_t* in = a.peer_sig[a.rank] + g;
+  const long long t0 = clock64();
+  while (*in - a.epoch < 0) {
+    if (clock64() - t0 > 8000000000ll) {
+      a.status[0] = VCSMC_ERR_STATE;
+      break;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
 
 __global__ void lz_pack_kernel(const RecArgs a) {
   const int64_t kl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -333,7 +363,7 @@ __global__ void lz_unpack_kernel(const RecArgs a) {
   const int g = (int)(k / a.Kl);
   if (g == a.rank) return;
   const int64_t kl = k - (int64_t)g * a.Kl;
-  const char* base = a.rec + (int64_t)g * a.stride;
+  const char* base = (a.peer_rec[g] ? a.peer_rec[g] : a.rec) + (int64_t)g * a.stride;
   const double* d = reinterpret_cast<const double*>(base);
   a.lw[k] = d[0 * a.Kl + kl];
   a.LL[k] = d[1 * a.Kl + kl];
@@ -367,6 +397,22 @@ __global__ void lz_iota_kernel(int32_t* p, int64_t n) {
   if (i < n) p[i] = (int32_t)i;
 }
 
+}  // namespace
+
+namespace {
+// all ranks' earlier work on `st` is complete (and visible to peers) before any rank's later work starts
+int cross_rank_barrier(vcsmc_sweep* h, cudaStream_t st) {
+  if (!h->peer_sync) {
+    if (h->comm(h->comm_user, VCSMC_COMM_BARRIER, nullptr, 0, st)) { set_error("comm hook failed (barrier)"); return VCSMC_ERR_CUDA; }
+    return VCSMC_OK;
+  }
+  SigArgs a;
+  for (int g = 0; g < kMaxPeers; ++g) a.peer_sig[g] = g < h->world ? reinterpret_cast<int32_t*>(h->peer_ws[g] + h->o_sig) : nullptr;
+  a.rank = h->rank; a.world = h->world; a.epoch = ++h->epoch; a.status = h->p<int32_t>(h->o_status);
+  lz_barrier_kernel<<<1, 32, 0, st>>>(a);
+  VCSMC_LAUNCH_CHECK("lz_barrier_kernel");
+  return VCSMC_OK;
+}
 }  // namespace
 
 int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l, const double* lam_r, const double* Q,
@@ -487,7 +533,8 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
                               h->p<double>(h->o_P) + ((int64_t)(r - 1) * K + k0) * 32, S, h->jc, st);
       if (rc) return rc;
       if (G > 1) {
-        if (h->comm(h->comm_user, VCSMC_COMM_BARRIER, nullptr, 0, st)) { set_error("comm hook failed (barrier)"); return VCSMC_ERR_CUDA; }
+        rc = cross_rank_barrier(h, st);
+        if (rc) return rc;
         const int32_t* peer_loc[kMaxPeers];
         const double* peer_pool[kMaxPeers];
         for (int g = 0; g < G; ++g) {
@@ -560,6 +607,7 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
     if (G > 1) {
       RecArgs ra;
       ra.n = n; ra.rank = h->rank; ra.Kl = Kl; ra.k0 = k0; ra.K = K; ra.stride = h->rec_stride; ra.rec = h->p<char>(h->o_rec);
+      for (int g = 0; g < kMaxPeers; ++g) ra.peer_rec[g] = nullptr;
       ra.lw = h->p<double>(h->o_lw) + (int64_t)r * K; ra.LL = h->p<double>(h->o_LL) + (int64_t)r * K;
       ra.ell = ell_node + N + (int64_t)r * K; ra.b_l = a.b_l; ra.b_r = a.b_r;
       ra.cum_l = h->p<double>(h->o_cum_l) + (int64_t)r * K; ra.cum_r = h->p<double>(h->o_cum_r) + (int64_t)r * K;
@@ -567,7 +615,14 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
       ra.rempos = a.rempos;
       lz_pack_kernel<<<(unsigned)((Kl + 127) / 128), 128, 0, st>>>(ra);
       VCSMC_LAUNCH_CHECK("lz_pack_kernel");
-      if (h->comm(h->comm_user, VCSMC_COMM_ALLGATHER, ra.rec, h->rec_stride, st)) { set_error("comm hook failed (all-gather)"); return VCSMC_ERR_CUDA; }
+      if (h->peer_sync) {
+        // every rank has packed its chunk: read the other chunks straight out of the peers' record buffers
+        rc = cross_rank_barrier(h, st);
+        if (rc) return rc;
+        for (int g = 0; g < kMaxPeers; ++g) ra.peer_rec[g] = g < G ? h->peer_ws[g] + h->o_rec : nullptr;
+      } else {
+        if (h->comm(h->comm_user, VCSMC_COMM_ALLGATHER, ra.rec, h->rec_stride, st)) { set_error("comm hook failed (all-gather)"); return VCSMC_ERR_CUDA; }
+      }
       lz_unpack_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(ra);
       VCSMC_LAUNCH_CHECK("lz_unpack_kernel");
     }

@@ -535,6 +535,7 @@ int64_t plan(vcsmc_sweep* h) {
   const int64_t E = (int64_t)(N - 1) * K;
   Layout L;
   h->o_status = L.take<int32_t>(8);
+  h->o_sig = L.take<int32_t>(64);
   h->o_elbo = L.take<double>(1);
   h->o_anc = L.take<int32_t>(E);
   h->o_lref = L.take<int32_t>(E);
@@ -804,7 +805,8 @@ int vcsmc_sweep_set_comm(vcsmc_sweep_t* h, int rank, int world, vcsmc_comm_fn fn
   if (world < 1 || world > kMaxPeers || rank < 0 || rank >= world) { set_error("set_comm: rank %d / world %d out of range (max %d ranks)", rank, world, kMaxPeers); return VCSMC_ERR_ARG; }
   if (h->M > 0 && world > 1) { set_error("particle sharding supports the VCSMC proposal only (n_sub == 0)"); return VCSMC_ERR_STATE; }
   if (h->K % world != 0) { set_error("n_particles = %lld is not divisible by %d ranks", (long long)h->K, world); return VCSMC_ERR_ARG; }
-  if (world > 1 && (!fn || !peer_ws_host)) { set_error("set_comm: null hook / peer table"); return VCSMC_ERR_ARG; }
+  if (world > 1 && !peer_ws_host) { set_error("set_comm: null peer table"); return VCSMC_ERR_ARG; }
+  if (world > 1 && !fn) h->peer_sync = 1;
   if (h->allreduce && world > 1) { set_error("site sharding (set_allreduce) and particle sharding (set_comm) are exclusive"); return VCSMC_ERR_STATE; }
   h->rank = rank; h->world = world; h->comm = fn; h->comm_user = user;
   h->Kl = h->K / world; h->k0 = h->Kl * rank;
@@ -813,7 +815,12 @@ int vcsmc_sweep_set_comm(vcsmc_sweep_t* h, int rank, int world, vcsmc_comm_fn fn
   if (world > 1) h->lazy = 1;
   h->forward_done = false;
   const int64_t tables = plan(h);
-  return decide_modes(h, tables, h->ws_bytes, true);
+  const int rc = decide_modes(h, tables, h->ws_bytes, true);
+  if (rc) return rc;
+  // flag array of the peer barrier: zero before anybody signals (the caller synchronises the ranks after this call)
+  h->epoch = 0;
+  VCSMC_CUDA(cudaMemset(h->ws + h->o_sig, 0, 64 * sizeof(int32_t)));
+  return VCSMC_OK;
 }
 
 int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value) {
@@ -833,6 +840,10 @@ int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value) {
     return decide_modes(h, tables, h->ws_bytes, true);
   }
   else if (!strcmp(name, "leaf_patterns")) h->leaf_patterns = value != 0.0;
+  else if (!strcmp(name, "peer_sync")) {
+    if (value == 0.0 && !h->comm && h->world > 1) { set_error("peer_sync = 0 needs the collective hook"); return VCSMC_ERR_STATE; }
+    h->peer_sync = value != 0.0;
+  }
   else if (!strcmp(name, "site_begin")) h->site_begin = (int)value;
   else if (!strcmp(name, "site_end")) h->site_end = (int)value;
   else if (!strcmp(name, "profile")) { h->profile = value != 0.0; h->ev_used = 0; h->ev_kind.clear(); }

@@ -113,6 +113,9 @@ struct vcsmc_sweep {
   int leaf_patterns = 1;               // score leaf-leaf merges from the site-pattern histogram (option "leaf_patterns")
   int64_t rec_stride = 0;              // bytes of one rank's chunk of the per-event record
   int64_t fetch_cap = 0;
+  int64_t o_sig = 0;                   // int32[kMaxPeers]: epochs the peers have signalled (flag barrier over peer memory)
+  int peer_sync = 1;                   // 1: barriers and the record exchange run over peer memory; 0: through the collective hook
+  int epoch = 0;
   // hook
   vcsmc_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;

@@ -292,6 +292,8 @@ class Sweep:
         self._comm_hook = _lib.COMM_FN(_cb)
         self._comm = comm
         check(self._lib.vcsmc_sweep_set_comm(self._h, comm.rank, comm.world, self._comm_hook, None, self._peers.as_array()))
+        comm.barrier(dev)   # every rank has zeroed its flag array before anybody signals
+        torch.cuda.synchronize(dev)
         self.retained = False
 
     # -- execution
