@@ -191,6 +191,8 @@ int vcsmc_sweep_set_comm(vcsmc_sweep_t* h, int rank, int world, vcsmc_comm_fn fn
  * "peer_sync" (default 1; particle sharding): the two synchronisations of a rank event and the exchange of the step
  * record run over peer memory (flag barrier kernel, peer loads) with no host involvement; 0 routes them through the
  * collective hook (VCSMC_COMM_BARRIER / VCSMC_COMM_ALLGATHER) instead;
+ * "graph" (default 1; lazy forward): from the second forward on, the launch sequence of the forward sweep (no host
+ * synchronisation, seed and model read from the workspace) is captured once into a CUDA graph and replayed;
  * "force_gc" (default 0): use the garbage-collected pool and the recompute backward even when every node fits (testing aid);
  * "site_begin", "site_end" (default 0, n_sites): the site slice this rank's reverse sweep covers;
  * "profile" (default 0): record CUDA events around every merge launch, read with vcsmc_sweep_profile. */

@@ -61,7 +61,7 @@ int64_t resample_scratch_doubles(int64_t K);
 int launch_resample_cdf(const double* lw, int64_t K, double* cdf, double* stats /*[4]: lse,total,ess,max*/, double* scratch, cudaStream_t st);
 int launch_resample_search(const double* cdf, const double* stats, const double* u, int64_t K, int32_t* idx, cudaStream_t st);
 int launch_philox_step(uint64_t seed, int r, int64_t k0, int64_t K, int n, float* u_pair, double* u_bl, double* u_br,
-                       double* u_res, double* u_cat, cudaStream_t st);
+                       double* u_res, double* u_cat, cudaStream_t st, const uint64_t* seed_dev = nullptr);
 
 // nested.cu (VNCSMC look-ahead)
 int nested_max_roots();

@@ -29,7 +29,7 @@ namespace {
 // u_res == null: the resampling uniform of logical particle k at rank event r comes straight from the counter-based
 // generator (the same value philox_step_kernel would write: counter (k, r, 1, 0), first two words)
 __global__ void lz_ancestors_kernel(int first, int64_t K, const double* __restrict__ cdf, const double* __restrict__ u_res,
-                                    uint64_t seed, int r, int32_t* __restrict__ anc, int32_t* __restrict__ surv) {
+                                    const uint64_t* __restrict__ seed_dev, int r, int32_t* __restrict__ anc, int32_t* __restrict__ surv) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   if (first) {
@@ -41,6 +41,7 @@ __global__ void lz_ancestors_kernel(int first, int64_t K, const double* __restri
     u = u_res[k];
   } else {
     uint32_t d[4] = {(uint32_t)k, (uint32_t)((uint64_t)k >> 32) | ((uint32_t)r << 8), 1u, 0u};
+    const uint64_t seed = *seed_dev;
     philox4x32_10(d, (uint32_t)seed, (uint32_t)(seed >> 32));
     u = u64_to_unit_f64(d[0], d[1]);
   }
@@ -311,20 +312,22 @@ struct RecArgs {
 // into a reported error instead of a hang.
 struct SigArgs {
   int32_t* peer_sig[kMaxPeers];  // peer g's flag array (own array at index rank)
-  int rank, world, epoch;
+  int rank, world, index;        // this is the index-th barrier since the epoch base was last advanced
+  const int32_t* epoch_base;     // device-resident, advanced at the end of every forward (a replayed graph stays monotonic)
   int32_t* status;
 };
 
 __global__ void lz_barrier_kernel(const SigArgs a) {
   const int g = threadIdx.x;
   if (g >= a.world) return;
+  const int epoch = *a.epoch_base + a.index;
   __threadfence_system();
   volatile int32_t* out = a.peer_sig[g] + a.rank;
-  *out = a.epoch;
+  *out = epoch;
   __threadfence_system();
   volatile int32_t* in = a.peer_sig[a.rank] + g;
   const long long t0 = clock64();
-  while (*in - a.epoch < 0) {
+  while (*in - epoch < 0) {
     if (clock64() - t0 > 8000000000ll) {
       a.status[0] = VCSMC_ERR_STATE;
       break;
@@ -333,6 +336,9 @@ __global__ void lz_barrier_kernel(const SigArgs a) {
   }
   __threadfence_system();
 }
+
+__global__ void lz_advance_kernel(int32_t* epoch_base, int n) { *epoch_base += n; }
+__global__ void lz_set_seed_kernel(uint64_t* seed_dev, uint64_t seed) { *seed_dev = seed; }
 
 __global__ void lz_pack_kernel(const RecArgs a) {
   const int64_t kl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -401,23 +407,27 @@ __global__ void lz_iota_kernel(int32_t* p, int64_t n) {
 
 namespace {
 // all ranks' earlier work on `st` is complete (and visible to peers) before any rank's later work starts
-int cross_rank_barrier(vcsmc_sweep* h, cudaStream_t st) {
+int cross_rank_barrier(vcsmc_sweep* h, int* n_barriers, cudaStream_t st) {
   if (!h->peer_sync) {
     if (h->comm(h->comm_user, VCSMC_COMM_BARRIER, nullptr, 0, st)) { set_error("comm hook failed (barrier)"); return VCSMC_ERR_CUDA; }
     return VCSMC_OK;
   }
   SigArgs a;
   for (int g = 0; g < kMaxPeers; ++g) a.peer_sig[g] = g < h->world ? reinterpret_cast<int32_t*>(h->peer_ws[g] + h->o_sig) : nullptr;
-  a.rank = h->rank; a.world = h->world; a.epoch = ++h->epoch; a.status = h->p<int32_t>(h->o_status);
+  a.rank = h->rank; a.world = h->world; a.index = ++*n_barriers; a.epoch_base = h->p<int32_t>(h->o_epoch_dev);
+  a.status = h->p<int32_t>(h->o_status);
   lz_barrier_kernel<<<1, 32, 0, st>>>(a);
   VCSMC_LAUNCH_CHECK("lz_barrier_kernel");
   return VCSMC_OK;
 }
 }  // namespace
 
-int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l, const double* lam_r, const double* Q,
-                       const double* pi, cudaStream_t st) {
+namespace {
+// the launch sequence of one forward sweep: no host synchronisation, no host-dependent argument -- capturable
+int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l, const double* lam_r, const double* Q,
+                      const double* pi, cudaStream_t st) {
   const int N = h->N, S = h->S, G = h->world;
+  int n_barriers = 0;
   const int64_t K = h->K, Kl = h->Kl, k0 = h->k0, E = (int64_t)(N - 1) * K;
   const bool gc = h->fwd_gc;
   int rc;
@@ -426,12 +436,6 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
 
   int32_t* status = h->p<int32_t>(h->o_status);
   VCSMC_CUDA(cudaMemsetAsync(status, 0, 8 * sizeof(int32_t), st));
-  {
-    std::vector<double> ldf(2 * N + 4, 0.0);
-    for (int m = 0; m < 2 * N + 4; ++m) ldf[m] = log_double_factorial_host(m);
-    VCSMC_CUDA(cudaMemcpyAsync(h->p<double>(h->o_ldf), ldf.data(), ldf.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    VCSMC_CUDA(cudaStreamSynchronize(st));  // ldf is a stack-lifetime host buffer
-  }
   double* ell_node = h->p<double>(h->o_ell_node);
   rc = launch_leaf_ell(codes, S, N, S, pi, ell_node, st);
   if (rc) return rc;
@@ -481,8 +485,8 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
     const float* u_pair;
     const double *u_bl, *u_br, *u_res_all;
     if (h->use_seed) {
-      rc = launch_philox_step(h->seed, r, k0, Kl, n, h->p<float>(h->o_u_pair), h->p<double>(h->o_u_bl), h->p<double>(h->o_u_br),
-                              nullptr, nullptr, st);
+      rc = launch_philox_step(0, r, k0, Kl, n, h->p<float>(h->o_u_pair), h->p<double>(h->o_u_bl), h->p<double>(h->o_u_br),
+                              nullptr, nullptr, st, h->p<uint64_t>(h->o_seed_dev));
       if (rc) return rc;
       u_pair = h->p<float>(h->o_u_pair); u_bl = h->p<double>(h->o_u_bl); u_br = h->p<double>(h->o_u_br);
       u_res_all = nullptr;   // drawn inside lz_ancestors_kernel
@@ -502,7 +506,7 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
       if (gc) VCSMC_CUDA(cudaMemsetAsync(flags, 0, (size_t)h->pool_slots * sizeof(int32_t), st));
       count_launch(3);
     }
-    lz_ancestors_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(r == 0, K, h->p<double>(h->o_cdf), u_res_all, h->seed, r, anc_row, surv);
+    lz_ancestors_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(r == 0, K, h->p<double>(h->o_cdf), u_res_all, h->p<uint64_t>(h->o_seed_dev), r, anc_row, surv);
     VCSMC_LAUNCH_CHECK("lz_ancestors_kernel");
     if (r > 0) {
       const int64_t e_base_prev = (int64_t)(r - 1) * K + k0;
@@ -533,7 +537,7 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
                               h->p<double>(h->o_P) + ((int64_t)(r - 1) * K + k0) * 32, S, h->jc, st);
       if (rc) return rc;
       if (G > 1) {
-        rc = cross_rank_barrier(h, st);
+        rc = cross_rank_barrier(h, &n_barriers, st);
         if (rc) return rc;
         const int32_t* peer_loc[kMaxPeers];
         const double* peer_pool[kMaxPeers];
@@ -617,7 +621,7 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
       VCSMC_LAUNCH_CHECK("lz_pack_kernel");
       if (h->peer_sync) {
         // every rank has packed its chunk: read the other chunks straight out of the peers' record buffers
-        rc = cross_rank_barrier(h, st);
+        rc = cross_rank_barrier(h, &n_barriers, st);
         if (rc) return rc;
         for (int g = 0; g < kMaxPeers; ++g) ra.peer_rec[g] = g < G ? h->peer_ws[g] + h->o_rec : nullptr;
       } else {
@@ -635,9 +639,73 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
     lz_lltilde_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(K, N, h->p<double>(h->o_LL), h->p<int32_t>(h->o_anc), ll_tilde);
     VCSMC_LAUNCH_CHECK("lz_lltilde_kernel");
   }
+  if (n_barriers > 0) {
+    lz_advance_kernel<<<1, 1, 0, st>>>(h->p<int32_t>(h->o_epoch_dev), n_barriers);
+    VCSMC_LAUNCH_CHECK("lz_advance_kernel");
+  }
   return launch_finalize(N, K, h->p<double>(h->o_stats), h->p<double>(h->o_LL) + (int64_t)(N - 2) * K, h->p<double>(h->o_b_l),
                          h->p<double>(h->o_b_r), lam_l, lam_r, log_double_factorial_host(2 * N - 3), h->p<double>(h->o_llR),
                          h->p<double>(h->o_elbo), h->p<double>(h->o_logz), h->p<double>(h->o_ess), st);
+}
+}  // namespace
+
+int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l_in, const double* lam_r_in, const double* Q_in,
+                       const double* pi_in, cudaStream_t st) {
+  const int N = h->N;
+  if (!h->ldf_ready) {  // log-double-factorial table: once per sweep object
+    std::vector<double> ldf(2 * N + 4, 0.0);
+    for (int m = 0; m < 2 * N + 4; ++m) ldf[m] = log_double_factorial_host(m);
+    VCSMC_CUDA(cudaMemcpy(h->p<double>(h->o_ldf), ldf.data(), ldf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    h->ldf_ready = true;
+  }
+  // the model lives in the workspace from here on (the reverse sweep reads it too): the caller's tensors may move
+  double* m = h->p<double>(h->o_model);
+  double *lam_l = m, *lam_r = m + (N - 1), *Q = m + 2 * (N - 1), *pi = m + 2 * (N - 1) + 16;
+  VCSMC_CUDA(cudaMemcpyAsync(lam_l, lam_l_in, (N - 1) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  VCSMC_CUDA(cudaMemcpyAsync(lam_r, lam_r_in, (N - 1) * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (Q_in) VCSMC_CUDA(cudaMemcpyAsync(Q, Q_in, 16 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  VCSMC_CUDA(cudaMemcpyAsync(pi, pi_in, 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  lz_set_seed_kernel<<<1, 1, 0, st>>>(h->p<uint64_t>(h->o_seed_dev), h->seed);
+  VCSMC_LAUNCH_CHECK("lz_set_seed_kernel");
+  count_launch(4);
+  h->lam_l = lam_l; h->lam_r = lam_r; h->Q = Q_in ? Q : nullptr; h->pi = pi;
+  const double* Qm = Q_in ? Q : nullptr;
+  ++h->forwards;
+
+  // a sequence that involves the host (collective hooks, per-launch timing) cannot be captured
+  const bool capturable = h->use_graph && !h->profile && !h->allreduce && (h->world == 1 || h->peer_sync);
+  if (!capturable || h->forwards < 2)   // (the first forward also runs the one-time function-attribute setup)
+    return lazy_forward_body(h, codes, lam_l, lam_r, Qm, pi, st);
+  const void* key[6] = {codes, h->use_seed ? nullptr : (const void*)h->x_pair, h->use_seed ? nullptr : (const void*)h->x_bl,
+                        h->use_seed ? nullptr : (const void*)h->x_br, h->use_seed ? nullptr : (const void*)h->x_res,
+                        (const void*)(uintptr_t)(h->use_seed ? 1 : 2)};
+  if (h->fwd_graph && memcmp(key, h->graph_key, sizeof(key)) != 0) {
+    cudaGraphExecDestroy(h->fwd_graph);
+    h->fwd_graph = nullptr;
+  }
+  if (!h->fwd_graph) {
+    // captured on a private stream (the caller's may be the legacy default stream, which cannot capture); replayed on `st`
+    if (!h->cap_stream) VCSMC_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    const uint64_t before = vcsmc_launch_count();
+    VCSMC_CUDA(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed));
+    const int rc = lazy_forward_body(h, codes, lam_l, lam_r, Qm, pi, h->cap_stream);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+    if (rc != VCSMC_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    VCSMC_CUDA(ce);
+    h->graph_launches = vcsmc_launch_count() - before;
+    const cudaError_t ie = cudaGraphInstantiate(&h->fwd_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    VCSMC_CUDA(ie);
+    memcpy(h->graph_key, key, sizeof(key));
+  } else {
+    count_launch((int)h->graph_launches);
+  }
+  VCSMC_CUDA(cudaGraphLaunch(h->fwd_graph, st));
+  return VCSMC_OK;
 }
 
 }  // namespace vcsmc

@@ -276,11 +276,12 @@ __global__ void resample_search_kernel(const double* __restrict__ cdf, const dou
   idx[j] = upper_bound_cdf(cdf, K, u[j] * cdf[K - 1]);
 }
 
-__global__ void philox_step_kernel(uint64_t seed, int r, int64_t k0, int64_t K, int n, float* __restrict__ u_pair,
-                                   double* __restrict__ u_bl, double* __restrict__ u_br, double* __restrict__ u_res,
-                                   double* __restrict__ u_cat) {
+__global__ void philox_step_kernel(uint64_t seed, const uint64_t* __restrict__ seed_dev, int r, int64_t k0, int64_t K, int n,
+                                   float* __restrict__ u_pair, double* __restrict__ u_bl, double* __restrict__ u_br,
+                                   double* __restrict__ u_res, double* __restrict__ u_cat) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= K) return;
+  if (seed_dev) seed = *seed_dev;  // device-resident seed: a captured launch sequence can be replayed with a new seed
   const uint64_t k = (uint64_t)(k0 + i);  // LOGICAL particle index: identical streams for any GPU count
   const uint32_t s0 = (uint32_t)seed, s1 = (uint32_t)(seed >> 32);
   uint32_t c[4] = {(uint32_t)k, (uint32_t)(k >> 32) | ((uint32_t)r << 8), 0u, 0u};
@@ -354,9 +355,9 @@ int launch_resample_search(const double* cdf, const double* stats, const double*
 }
 
 int launch_philox_step(uint64_t seed, int r, int64_t k0, int64_t K, int n, float* u_pair, double* u_bl, double* u_br,
-                       double* u_res, double* u_cat, cudaStream_t st) {
+                       double* u_res, double* u_cat, cudaStream_t st, const uint64_t* seed_dev) {
   if (K <= 0) return VCSMC_OK;
-  philox_step_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(seed, r, k0, K, n, u_pair, u_bl, u_br, u_res, u_cat);
+  philox_step_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(seed, seed_dev, r, k0, K, n, u_pair, u_bl, u_br, u_res, u_cat);
   VCSMC_LAUNCH_CHECK("philox_step_kernel");
   return VCSMC_OK;
 }

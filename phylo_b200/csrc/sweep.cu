@@ -536,6 +536,9 @@ int64_t plan(vcsmc_sweep* h) {
   Layout L;
   h->o_status = L.take<int32_t>(8);
   h->o_sig = L.take<int32_t>(64);
+  h->o_epoch_dev = L.take<int32_t>(4);
+  h->o_seed_dev = L.take<uint64_t>(2);
+  h->o_model = L.take<double>(2 * (int64_t)N + 24);
   h->o_elbo = L.take<double>(1);
   h->o_anc = L.take<int32_t>(E);
   h->o_lref = L.take<int32_t>(E);
@@ -787,6 +790,7 @@ int vcsmc_sweep_create(const vcsmc_sweep_config* cfg, void* workspace, vcsmc_swe
   const int64_t tables = plan(h);
   rc = decide_modes(h, tables, cfg->workspace_bytes, true);
   if (rc) { delete h; return rc; }
+  if (cudaMemset(h->ws + h->o_epoch_dev, 0, 4 * sizeof(int32_t)) != cudaSuccess) cudaGetLastError();  // (no device: entry points fail later)
   *out = h;
   return VCSMC_OK;
 }
@@ -818,8 +822,9 @@ int vcsmc_sweep_set_comm(vcsmc_sweep_t* h, int rank, int world, vcsmc_comm_fn fn
   const int rc = decide_modes(h, tables, h->ws_bytes, true);
   if (rc) return rc;
   // flag array of the peer barrier: zero before anybody signals (the caller synchronises the ranks after this call)
-  h->epoch = 0;
   VCSMC_CUDA(cudaMemset(h->ws + h->o_sig, 0, 64 * sizeof(int32_t)));
+  VCSMC_CUDA(cudaMemset(h->ws + h->o_epoch_dev, 0, 4 * sizeof(int32_t)));
+  if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; }
   return VCSMC_OK;
 }
 
@@ -836,13 +841,16 @@ int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value) {
   else if (!strcmp(name, "force_gc")) {  // testing aid: garbage-collected pool + recompute backward even when every node would fit
     h->force_gc = value != 0.0;
     h->forward_done = false;
+    if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; }
     const int64_t tables = plan(h);
     return decide_modes(h, tables, h->ws_bytes, true);
   }
-  else if (!strcmp(name, "leaf_patterns")) h->leaf_patterns = value != 0.0;
+  else if (!strcmp(name, "leaf_patterns")) { h->leaf_patterns = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
+  else if (!strcmp(name, "graph")) h->use_graph = value != 0.0;
   else if (!strcmp(name, "peer_sync")) {
     if (value == 0.0 && !h->comm && h->world > 1) { set_error("peer_sync = 0 needs the collective hook"); return VCSMC_ERR_STATE; }
     h->peer_sync = value != 0.0;
+    if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; }
   }
   else if (!strcmp(name, "site_begin")) h->site_begin = (int)value;
   else if (!strcmp(name, "site_end")) h->site_end = (int)value;

@@ -115,7 +115,15 @@ struct vcsmc_sweep {
   int64_t fetch_cap = 0;
   int64_t o_sig = 0;                   // int32[kMaxPeers]: epochs the peers have signalled (flag barrier over peer memory)
   int peer_sync = 1;                   // 1: barriers and the record exchange run over peer memory; 0: through the collective hook
-  int epoch = 0;
+  int64_t o_epoch_dev = 0, o_seed_dev = 0, o_model = 0;   // device-resident barrier epoch base, seed, copy of (lam_l, lam_r, Q, pi)
+  bool ldf_ready = false;
+  // the lazy forward as a CUDA graph: captured on the second forward of a given (codes, uniform source), replayed after
+  int use_graph = 1;
+  int64_t forwards = 0;
+  cudaGraphExec_t fwd_graph = nullptr;
+  cudaStream_t cap_stream = nullptr;
+  const void* graph_key[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  uint64_t graph_launches = 0;         // kernels + memsets one replay stands for (bench's launch count)
   // hook
   vcsmc_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
@@ -153,6 +161,8 @@ struct vcsmc_sweep {
   }
   ~vcsmc_sweep() {
     for (auto e : ev) cudaEventDestroy(e);
+    if (fwd_graph) cudaGraphExecDestroy(fwd_graph);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
   }
 
   template <typename T>

@@ -183,6 +183,46 @@ def test_sweep_flat_weights_gc_pool_sorted_order(ops, jc, lazy):
         compare_grads(grads, g_ref, jc)
 
 
+@pytest.mark.parametrize("jc", [True, False])
+@pytest.mark.parametrize("force_gc", [False, True])
+def test_repeated_forward_replays_a_cuda_graph(ops, primate_genome, jc, force_gc):
+    """From the second forward on the launch sequence is a captured CUDA graph: new seeds / parameters must take effect
+    (they live in the workspace), and results must equal those of a fresh sweep object."""
+    g = primate_genome[:9, :500]
+    N, S, K = 9, 500, 96
+    codes = ops.pack_alignment(dev(g))
+    probe = ops.Sweep(N, S, K, jc)
+    roomy = probe.retain_bytes + (32 << 20)
+    del probe
+
+    def fresh(seed, p):
+        lam_l, lam_r, Q, pi = O.model_from_params(p)
+        sw = ops.Sweep(N, S, K, jc, workspace_bytes=roomy)
+        if force_gc:
+            sw.set_option("force_gc", 1.0)
+        sw.set_option("graph", 0.0)
+        sw.set_seed(seed)
+        e = float(sw.forward(codes, dev(lam_l), dev(lam_r), None if jc else dev(Q), dev(pi.reshape(-1))).item())
+        return e, sw.output("ancestors").cpu().numpy().copy(), [None if t is None else t.cpu().numpy() for t in sw.backward(1.0)]
+
+    sw = ops.Sweep(N, S, K, jc, workspace_bytes=roomy)
+    if force_gc:
+        sw.set_option("force_gc", 1.0)
+    for it, (seed, pseed) in enumerate([(11, 1), (12, 1), (13, 2), (11, 1)]):
+        p = random_params(N, jc, seed=pseed)
+        lam_l, lam_r, Q, pi = O.model_from_params(p)
+        sw.set_seed(seed)
+        e = float(sw.forward(codes, dev(lam_l), dev(lam_r), None if jc else dev(Q), dev(pi.reshape(-1))).item())
+        anc = sw.output("ancestors").cpu().numpy().copy()
+        grads = [None if t is None else t.cpu().numpy() for t in sw.backward(1.0)]
+        e0, anc0, grads0 = fresh(seed, p)
+        assert e == pytest.approx(e0, rel=1e-13), it
+        np.testing.assert_array_equal(anc, anc0)
+        for a, b in zip(grads, grads0):
+            if a is not None:
+                np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12 * np.abs(b).max())
+
+
 def test_sweep_pool_exhaustion_is_reported(ops):
     """Flat weights keep many nodes alive; a 2K-slot pool must fail loudly, not silently corrupt."""
     from phylo_b200._lib import VcsmcError
