@@ -195,12 +195,23 @@ def run_native(args):
     genome_host = torch.from_numpy(datadict["genome"]).pin_memory()
     variables = model.trainable_variables()
 
-    def step(seed):
+    split = []   # (forward ms, backward ms) of the steps run while `timing_split` is on
+
+    def step(seed, timing_split=False):
         for v in variables:
             v.grad = None
+        if timing_split:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            ev[0].record()
         elbo = model.sample_phylogenies(need_grad=True, seed=seed)
+        if timing_split:
+            ev[1].record()
         (-elbo).backward()
         model._allreduce_grads()
+        if timing_split:
+            ev[2].record()
+            torch.cuda.synchronize()
+            split.append((ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])))
         return elbo
 
     def step_e2e(seed):
@@ -276,6 +287,8 @@ def run_native(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = merges / (float(te.item()) / args.steps)
+    for i in range(2):   # forward / backward split of two more (graph-replayed) steps, device time
+        step(i, timing_split=True)
     nparam = sum(v.numel() for v in variables)
     h2d = int(genome_host.numel() * 8 + nparam * 8)
     d2h = int(8 + nparam * 8)
@@ -366,6 +379,7 @@ def run_native(args):
         "gpu_launches": int(launches),
         "clocks": clk,
         "elbo": float(elbo.detach()),
+        "fwd_bwd_ms": [round(float(np.mean([a for a, _ in split])), 3), round(float(np.mean([b for _, b in split])), 3)],
     }
     if eager is not None:
         line["eager_dense"] = eager

@@ -18,6 +18,8 @@
 #include <new>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "sweep_state.h"
 
 namespace vcsmc {
@@ -380,6 +382,205 @@ __global__ void bwd_active_kernel(const double* __restrict__ cnew, const int32_t
   act_bwd[k] = c || !(skip_zero && fabs(cnew[k]) <= skip_below);  // one visiting order serves the recompute and the reverse sweep
 }
 
+// ---------------------------------------------------------------------------------------------
+// The whole scalar pass of the reverse sweep in ONE cooperative launch (VCSMC proposal).  Rank events are strictly
+// sequential (the coefficients of event r need what event r+1 scattered), so the grid walks r = N-2 ... 0 with a grid
+// barrier between events instead of 5 launches + two 33 MB memsets per event.  Per event a thread does what
+// bwd_coef_kernel does for one particle, zeroes the accumulator entries it consumed (they are the scatter targets two
+// events later), decides whether the reverse merge has to visit the particle and appends it to the event's list.
+// ---------------------------------------------------------------------------------------------
+struct ScalarArgs {
+  int N, skip_zero;
+  int64_t K;
+  double grad, share, thresh;
+  const double* lw;
+  const double* stats;
+  const int32_t* anc;
+  const uint8_t* rempos;
+  double* childsum[2];
+  double* Dacc[2];
+  int32_t* dirty[2];   // [K]: accumulator row k of that buffer holds non-zeros
+  double* cnew;
+  const double* lam_l;
+  const double* lam_r;
+  const double* b_l;
+  const double* b_r;
+  const double* cum_l;
+  const double* cum_r;
+  double* suf_l;
+  double* suf_r;
+  double* dlam_l;
+  double* dlam_r;
+  const int32_t* consumed;
+  int32_t* act_all;    // [N-1][K]
+  int32_t* order_bwd;  // [N-1][K]: the particles the reverse merge of event r has to visit (in no particular order)
+  int32_t* count_bwd;  // [N-1]
+};
+
+__global__ void __launch_bounds__(256) bwd_scalar_kernel(const ScalarArgs a) {
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  __shared__ double red[8];
+  const int N = a.N, lane = threadIdx.x & 31;
+  const int64_t K = a.K;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  const int64_t Kround = (K + 31) / 32 * 32;
+  // byte offset of event r's block of kept positions: sum_{r' < r} align16(K (N - r' - 2))
+  int64_t rem_off = 0;
+  for (int q = 0; q < N - 2; ++q) rem_off += (K * (int64_t)(N - q - 2) + 15) / 16 * 16;
+  for (int r = N - 2; r >= 0; --r) {
+    const int n = N - r, cur = r & 1, nxt = cur ^ 1;
+    const double laml = a.lam_l[r], lamr = a.lam_r[r], lse = a.stats[r * 4];
+    double* Dcur = a.Dacc[cur];
+    double* Dnxt = a.Dacc[nxt];
+    double dl = 0.0, dr = 0.0;
+    for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < Kround; k += stride) {
+      bool act = false, need = false, is_dirty = false;
+      const bool valid = k < K;
+      const int64_t e = (int64_t)r * K + (valid ? k : 0);
+      double W = 0.0, av = 0.0, c = 0.0;
+      int A = 0;
+      if (valid) {
+        W = exp(a.lw[e] - lse) * a.grad;
+        av = W - a.childsum[cur][k];
+        a.childsum[cur][k] = 0.0;
+        A = r > 0 ? a.anc[e] : (int)k;
+        is_dirty = a.dirty[cur][k] != 0;   // somebody scattered into this particle's accumulator row two events ago
+        if (is_dirty) a.dirty[cur][k] = 0;
+        need = is_dirty || av != 0.0;
+        c = av;                            // clean row: D = av at every position
+      }
+      // rows that hold or produce something are walked by the whole warp (coalesced); with ESS ~ 1 that is a handful
+      unsigned todo = __ballot_sync(0xffffffffu, need);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int64_t kk = __shfl_sync(0xffffffffu, (int)k, src);
+        const double avv = __shfl_sync(0xffffffffu, av, src);
+        const int AA = __shfl_sync(0xffffffffu, A, src);
+        const bool dd = __shfl_sync(0xffffffffu, (int)is_dirty, src) != 0;
+        const uint8_t* rp = a.rempos + rem_off + kk * (int64_t)(n - 2);
+        double* row = Dcur + kk * N;
+        double last = 0.0;
+        bool wrote = false;
+        for (int p = lane; p < n - 1; p += 32) {
+          double d = 0.0;
+          if (dd) {
+            d = row[p];
+            row[p] = 0.0;
+          }
+          if (p < n - 2) {
+            const double D = avv + d;
+            if (D != 0.0) {
+              atomicAdd(Dnxt + (int64_t)AA * N + rp[p], D);
+              wrote = true;
+            }
+          } else {
+            last = d;
+          }
+        }
+        last = __shfl_sync(0xffffffffu, last, (n - 2) & 31);
+        if (lane == src) c = av + last;
+        if (__any_sync(0xffffffffu, wrote) && lane == 0) a.dirty[nxt][AA] = 1;
+      }
+      if (valid) {
+        a.cnew[e] = c;
+        if (r > 0 && W != 0.0) atomicAdd(a.childsum[nxt] + A, W);
+        const double sl = a.suf_l[k] + av * laml, sr = a.suf_r[k] + av * lamr;  // sum_{r' >= r} a_{r'}[k] lam_{r'}
+        a.suf_l[k] = sl;
+        a.suf_r[k] = sr;
+        const double bl = a.b_l[e], br = a.b_r[e];
+        const double gBl = W * laml - sl, gBr = W * lamr - sr;
+        dl += a.share * (av * (-a.cum_l[e] + (double)(r + 1) / laml) + W * (bl - 1.0 / laml) + gBl * (-bl / laml));
+        dr += a.share * (av * (-a.cum_r[e] + (double)(r + 1) / lamr) + W * (br - 1.0 / lamr) + gBr * (-br / lamr));
+        act = a.consumed[e] || !(a.skip_zero && fabs(c) <= a.thresh);
+        a.act_all[e] = act;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, act);
+      if (m) {
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(a.count_bwd + r, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (act) a.order_bwd[(int64_t)r * K + base + __popc(m & ((1u << lane) - 1))] = (int32_t)k;
+      }
+    }
+    const double tl = block_sum<256>(dl, red);
+    const double tr = block_sum<256>(dr, red);
+    if (threadIdx.x == 0) {
+      if (tl != 0.0) atomicAdd(a.dlam_l + r, tl);
+      if (tr != 0.0) atomicAdd(a.dlam_r + r, tr);
+    }
+    if (r > 0) rem_off -= (K * (int64_t)(N - (r - 1) - 2) + 15) / 16 * 16;
+    grid.sync();
+  }
+}
+
+// dP rows of the particles the reverse merge is going to visit (instead of clearing the whole [N-1][K][32] table)
+__global__ void __launch_bounds__(256) zero_dP_rows_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ count,
+                                                           int64_t K, double* __restrict__ dP) {
+  const int r = blockIdx.y;
+  const int64_t cnt = count[r];
+  for (int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < cnt; i += (int64_t)gridDim.x * 8)
+    dP[((int64_t)r * K + order[(int64_t)r * K + i]) * 32 + (threadIdx.x & 31)] = 0.0;
+}
+
+// dP -> (db, dQ) -> dlam for the visited particles of EVERY rank event in one launch: matrix i of event blockIdx.y is
+// child (i & 1) of particle order[r][i >> 1].  (vcsmc.py:353-358 and the expm of :183-184, reversed.)
+__global__ void __launch_bounds__(64) bwd_transition_all_kernel(const double* __restrict__ Q, const double* __restrict__ t2,
+                                                                const double* __restrict__ dP, const int32_t* __restrict__ order,
+                                                                const int32_t* __restrict__ count, int64_t K, int jc,
+                                                                const double* __restrict__ b_l, const double* __restrict__ b_r,
+                                                                const double* __restrict__ lam_l, const double* __restrict__ lam_r,
+                                                                double* __restrict__ dQ_acc, double* __restrict__ dlam_l,
+                                                                double* __restrict__ dlam_r) {
+  const int r = blockIdx.y;
+  const int64_t n = 2 * (int64_t)count[r];
+  for (int64_t i = (int64_t)blockIdx.x * 64 + threadIdx.x; i < (n + 63) / 64 * 64; i += (int64_t)gridDim.x * 64) {
+    double dt = 0.0;
+    int side = 0;
+    int64_t k = 0;
+    if (i < n) {
+      k = order[(int64_t)r * K + (i >> 1)];
+      side = (int)(i & 1);
+      const int64_t m = ((int64_t)r * K + k) * 2 + side;
+      const double ti = t2[m];
+      const double* G = dP + m * 16;
+      if (jc) {
+        const double e = exp(-ti);
+        dt = e * (0.25 * G[1] - 0.75 * G[0]);
+      } else {
+        double any = 0.0;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) any += fabs(G[e]);
+        if (any != 0.0) {
+          M4 At, E, X, Y;
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) At.a[rr * 4 + c] = __ldg(Q + c * 4 + rr) * ti;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) E.a[e] = G[e];
+          m4_expm_frechet(At, E, X, Y);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            dt = fma(Y.a[e], __ldg(Q + e), dt);
+            const double v = ti * Y.a[e];
+            if (v != 0.0) atomicAdd(dQ_acc + k * 16 + e, v);
+          }
+        }
+      }
+      dt *= side ? (-b_r[(int64_t)r * K + k] / lam_r[r]) : (-b_l[(int64_t)r * K + k] / lam_l[r]);
+    }
+    // lanes alternate left / right children: reduce the two parities separately
+    double vl = side ? 0.0 : dt, vr = side ? dt : 0.0;
+    vl = warp_sum(vl);
+    vr = warp_sum(vr);
+    if ((threadIdx.x & 31) == 0) {
+      if (vl != 0.0) atomicAdd(dlam_l + r, vl);
+      if (vr != 0.0) atomicAdd(dlam_r + r, vr);
+    }
+  }
+}
+
 // zero the adjoint slots of the consumed nodes of one rank event (the first *count entries of `order`)
 __global__ void zero_consumed_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ count, int K,
                                      const int32_t* __restrict__ gsrc, int64_t slot_sites, int n_sites,
@@ -657,6 +858,8 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_order_rec = L.take<int32_t>(E);
     h->o_count_bwd = L.take<int32_t>(N);
     h->o_count_rec = L.take<int32_t>(N);
+    h->o_act_all = L.take<int32_t>(h->M == 0 ? E : 1);
+    h->o_dirty = L.take<int32_t>(2 * K);
     h->o_act_bwd = L.take<int32_t>(K);
     h->o_act_rec = L.take<int32_t>(K);
     h->o_cslot = L.take<int32_t>(E + 1);
@@ -1075,7 +1278,8 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_Dacc[0]), 0, K * N * sizeof(double), st));
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_Dacc[1]), 0, K * N * sizeof(double), st));
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_consumed), 0, E * sizeof(int32_t), st));
-  VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_dP), 0, 32 * E * sizeof(double), st));
+  if (h->M > 0) VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_dP), 0, 32 * E * sizeof(double), st));  // (VCSMC: only the visited rows, below)
+  VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_count_bwd), 0, N * sizeof(int32_t), st));
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_dQ_acc), 0, 16 * K * sizeof(double), st));
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_suf_l), 0, K * sizeof(double), st));
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_suf_r), 0, K * sizeof(double), st));
@@ -1122,6 +1326,40 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   VCSMC_LAUNCH_CHECK("bwd_src_kernel");
 
   // ---- scalar pass: coefficients of every node, site-independent gradient terms
+  const bool fused = h->M == 0;
+  if (fused) {
+    ScalarArgs a;
+    a.N = N; a.skip_zero = h->skip_zero; a.K = K; a.grad = grad_elbo; a.share = h->scalar_share;
+    a.thresh = h->skip_below * fabs(grad_elbo);
+    a.lw = h->p<double>(h->o_lw); a.stats = h->p<double>(h->o_stats); a.anc = h->p<int32_t>(h->o_anc);
+    a.rempos = h->p<uint8_t>(h->o_rempos);
+    for (int i = 0; i < 2; ++i) {
+      a.childsum[i] = h->p<double>(h->o_childsum[i]); a.Dacc[i] = h->p<double>(h->o_Dacc[i]);
+      a.dirty[i] = h->p<int32_t>(h->o_dirty) + (int64_t)i * K;
+    }
+    VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_dirty), 0, 2 * K * sizeof(int32_t), st));
+    a.cnew = h->p<double>(h->o_cnew); a.lam_l = h->lam_l; a.lam_r = h->lam_r;
+    a.b_l = h->p<double>(h->o_b_l); a.b_r = h->p<double>(h->o_b_r);
+    a.cum_l = h->p<double>(h->o_cum_l); a.cum_r = h->p<double>(h->o_cum_r);
+    a.suf_l = h->p<double>(h->o_suf_l); a.suf_r = h->p<double>(h->o_suf_r);
+    a.dlam_l = dlam_l; a.dlam_r = dlam_r;
+    a.consumed = h->p<int32_t>(h->o_consumed); a.act_all = h->p<int32_t>(h->o_act_all);
+    a.order_bwd = h->p<int32_t>(h->o_order_bwd); a.count_bwd = h->p<int32_t>(h->o_count_bwd);
+    static int max_blocks = 0;
+    if (max_blocks == 0) {
+      int per_sm = 0, sms = 0, dev = 0;
+      VCSMC_CUDA(cudaGetDevice(&dev));
+      VCSMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      VCSMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bwd_scalar_kernel, 256, 0));
+      max_blocks = per_sm * sms;
+      if (max_blocks < 1) { set_error("bwd_scalar_kernel cannot be launched cooperatively"); return VCSMC_ERR_CUDA; }
+    }
+    int64_t blocks = (K + 255) / 256;
+    if (blocks > max_blocks) blocks = max_blocks;
+    void* kargs[] = {(void*)&a};
+    VCSMC_CUDA(cudaLaunchCooperativeKernel((const void*)bwd_scalar_kernel, dim3((unsigned)blocks), dim3(256), kargs, 0, st));
+    count_launch();
+  } else {
   for (int r = N - 2; r >= 0; --r) {
     const int cur = r & 1, nxt = cur ^ 1;
     CoefArgs a;
@@ -1150,6 +1388,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_Dacc[cur]), 0, K * N * sizeof(double), st));
     count_launch(2);
   }
+  }
   // after r = 0 the scatter target was Dacc[(0&1)^1] = Dacc[1]: per-particle coefficients of the N leaves
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_cleaf), 0, N * sizeof(double), st));
   column_sum_kernel<<<N, 256, 0, st>>>(h->p<double>(h->o_Dacc[1]), K, N, N, h->p<double>(h->o_cleaf));
@@ -1159,9 +1398,36 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     VCSMC_LAUNCH_CHECK("leaf_pi_grad_kernel");
   }
 
-  // ---- visiting orders of every rank event (sorted by child pair; inactive particles last)
-  const bool sorted_b = use_sorted_order(K, S);
+  // ---- visiting orders of every rank event
+  const bool sorted_b = fused || use_sorted_order(K, S);
   std::vector<int32_t> cnt_bwd(N, (int32_t)K), cnt_rec(N, (int32_t)K);
+  if (fused) {
+    // the scalar pass listed the particles to visit; one small D2H + sync tells the host how many per event
+    VCSMC_CUDA(cudaMemcpyAsync(cnt_bwd.data(), h->p<int32_t>(h->o_count_bwd), (N - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    VCSMC_CUDA(cudaStreamSynchronize(st));
+    for (int r = 0; r < N - 1; ++r) {
+      // long lists are worth arranging by child pair (shared children are then read once per run, adjoints flushed
+      // once per run); the dense reverse sweep gets the full sort, as before
+      if (h->skip_zero && cnt_bwd[r] < 1024) continue;
+      const int32_t* bl = h->p<int32_t>(h->o_bsrc_l) + (int64_t)r * K;
+      const int32_t* br = h->p<int32_t>(h->o_bsrc_r) + (int64_t)r * K;
+      const int32_t* act = h->p<int32_t>(h->o_act_all) + (int64_t)r * K;
+      if (h->skip_zero)
+        rc = group_particles(h, bl, br, act, K, h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r, st);
+      else
+        rc = launch_sort_order(bl, br, act, K, E, h->p<uint64_t>(h->o_keys_in), h->p<uint64_t>(h->o_keys_out), h->p<int32_t>(h->o_vals_in),
+                               h->p<int32_t>(h->o_order_bwd) + (int64_t)r * K, h->p<int32_t>(h->o_count_bwd) + r, h->p<char>(h->o_sort_temp), h->sort_temp, st);
+      if (rc) return rc;
+    }
+    cnt_rec = cnt_bwd;
+    int32_t max_cnt = 0;
+    for (int r = 0; r < N - 1; ++r) max_cnt = cnt_bwd[r] > max_cnt ? cnt_bwd[r] : max_cnt;
+    if (max_cnt > 0) {
+      const unsigned bx = (unsigned)((max_cnt + 7) / 8 < 2048 ? (max_cnt + 7) / 8 : 2048);
+      zero_dP_rows_kernel<<<dim3(bx, N - 1), 256, 0, st>>>(h->p<int32_t>(h->o_order_bwd), h->p<int32_t>(h->o_count_bwd), K, h->p<double>(h->o_dP));
+      VCSMC_LAUNCH_CHECK("zero_dP_rows_kernel");
+    }
+  } else
   if (sorted_b) {
     for (int r = 0; r < N - 1; ++r) {
       bwd_active_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(h->p<double>(h->o_cnew) + (int64_t)r * K, h->p<int32_t>(h->o_consumed) + (int64_t)r * K,
@@ -1300,6 +1566,17 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   }
 
   // ---- dP -> (db, dQ) -> dlam, for the particles the reverse merge visited
+  if (fused) {
+    int32_t max_cnt = 0;
+    for (int r = 0; r < N - 1; ++r) max_cnt = cnt_bwd[r] > max_cnt ? cnt_bwd[r] : max_cnt;
+    if (max_cnt > 0) {
+      const int64_t bx = (2 * (int64_t)max_cnt + 63) / 64;
+      bwd_transition_all_kernel<<<dim3((unsigned)(bx < 4096 ? bx : 4096), N - 1), 64, 0, st>>>(
+          h->Q, h->p<double>(h->o_t2), h->p<double>(h->o_dP), h->p<int32_t>(h->o_order_bwd), h->p<int32_t>(h->o_count_bwd), K, h->jc,
+          h->p<double>(h->o_b_l), h->p<double>(h->o_b_r), h->lam_l, h->lam_r, h->p<double>(h->o_dQ_acc), dlam_l, dlam_r);
+      VCSMC_LAUNCH_CHECK("bwd_transition_all_kernel");
+    }
+  } else
   for (int r = 0; r < N - 1; ++r) {
     const int64_t cnt = cnt_bwd[r];
     if (cnt == 0) continue;

@@ -79,7 +79,7 @@ struct vcsmc_sweep {
       o_u_pair, o_u_bl, o_u_br, o_u_res, o_ell_part, o_ell_new, o_lsrc, o_rsrc, o_dst, o_ldf, o_flags, o_childsum[2],
       o_Dacc[2], o_cnew, o_consumed, o_bsrc_l, o_bsrc_r, o_bsrc_g, o_bdst, o_dP, o_dpi_each, o_dQ_acc, o_dQ_each, o_dt,
       o_suf_l, o_suf_r, o_cleaf, o_pool, o_keys_in, o_keys_out, o_vals_in, o_order, o_count,
-      o_sort_temp, o_order_bwd, o_count_bwd, o_order_rec, o_count_rec, o_act_bwd, o_act_rec, o_cslot,
+      o_sort_temp, o_order_bwd, o_count_bwd, o_order_rec, o_count_rec, o_act_bwd, o_act_rec, o_act_all, o_dirty, o_cslot,
       o_inh_ids, o_inh_cnt, o_inh_slot, o_pot, o_choice, o_qlog, o_u_cat, o_rows_all, o_nact, o_nbase, o_v_lsrc, o_v_rsrc,
       o_v_coef, o_v_t2, o_v_P, o_v_dP, o_v_dt, o_v_dQ, o_v_dpi, o_v_order, o_v_keys_in, o_v_keys_out, o_v_vals, o_v_count, o_v_temp, o_v_keep, o_v_index, o_v_scan;
   size_t v_scan = 0;
