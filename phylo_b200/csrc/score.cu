@@ -43,6 +43,7 @@ struct ScoreArgs {
   int n_chunks;
   int R;
   int skip_leaf_pairs;  // particles whose children are both leaves are scored from the pattern histogram instead
+  int skip_octets;      // octets of particles that share one child pair are scored by merge_score_mma_kernel instead
   double* ell_part;  // [K][n_chunks][kWarps]
 };
 
@@ -57,6 +58,7 @@ struct ChildSpace {
   int64_t slot_sites;
   int n_sites;
   int skip_leaf_pairs;
+  int skip_octets;
 };
 
 template <bool JC, int SPT, int NC>
@@ -179,13 +181,23 @@ __device__ __forceinline__ void score_particles_leaf(int j, const double (&Lb)[S
   }
 }
 
+// particles j .. j+7 of the group exist and share one child pair (and are not a leaf-leaf pair when those are skipped)
+__device__ __forceinline__ bool octet_uniform(const int* s_a, const int* s_b, int j, int nj) {
+  if (j + 8 > nj) return false;
+  const int ca = s_a[j], cb = s_b[j];
+  bool u = true;
+#pragma unroll
+  for (int i = 1; i < 8; ++i) u = u && s_a[j + i] == ca && s_b[j + i] == cb;
+  return u;
+}
+
 // One tile of SPT*256 sites for the nj particles of a group.  The running product of the site likelihoods of
 // (thread, particle) is kept as (mantissa product, BIASED exponent sum) in shared memory.  The split is three integer
 // ops per site; a likelihood that is not a positive normal number (0, subnormal, inf, NaN, negative) poisons the
 // mantissa product with NaN and the particle is re-evaluated with one log per site afterwards (never on sane inputs).
 // Sites past the end of the alignment have zero site products and x0 = 1, i.e. x = 1.
 template <bool JC, int SPT>
-__device__ __forceinline__ void score_tile(const ChildSpace& a, int nj, int sbase, bool renorm, const double (&pi)[4],
+__device__ __forceinline__ void score_tile(const ChildSpace& a, int nj, unsigned skip, int sbase, bool renorm, const double (&pi)[4],
                                            const int* s_a, const int* s_b, const double* sC, double* my_prod, int* my_exp) {
   constexpr int NC = JC ? 4 : 16;
   int pa = kNone, pb = kNone;
@@ -201,7 +213,7 @@ __device__ __forceinline__ void score_tile(const ChildSpace& a, int nj, int sbas
   int j = 0;
   while (j < nj) {
     const int ca = s_a[j], cb = s_b[j];
-    if (a.skip_leaf_pairs && cb < 0) {  // canonical order a <= b: both children are leaves
+    if (skip >> j & 1u) {  // a leaf pair (scored from site patterns) or part of a uniform octet (tensor-core kernel)
       ++j;
       continue;
     }
@@ -234,7 +246,7 @@ __device__ __forceinline__ void score_tile(const ChildSpace& a, int nj, int sbas
       pa = ca;
       pb = cb;
     }
-    const bool two = j + 1 < nj && s_a[j + 1] == ca && s_b[j + 1] == cb;
+    const bool two = j + 1 < nj && !(skip >> (j + 1) & 1u) && s_a[j + 1] == ca && s_b[j + 1] == cb;
     if (!JC && leaf_rows) {
       if (two) score_particles_leaf<SPT, 2>(j, reinterpret_cast<const double(&)[SPT][16]>(C), roff, x0, renorm, sC, my_prod, my_exp);
       else score_particles_leaf<SPT, 1>(j, reinterpret_cast<const double(&)[SPT][16]>(C), roff, x0, renorm, sC, my_prod, my_exp);
@@ -274,7 +286,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
   double* s_prod = sC + kRScore * kCoef;                                 // [R][256] running mantissa products
   int* s_exp = reinterpret_cast<int*>(s_prod + kRScore * kTileThreads); // [R][256] running (biased) exponent sums
   __shared__ int s_k[kRScore], s_a[kRScore], s_b[kRScore];
-  __shared__ unsigned s_odd;
+  __shared__ unsigned s_odd, s_skip;   // s_skip: particles of the group some other kernel scores (leaf pairs, uniform octets)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int R = a.R;
   const int64_t total = ((a.K + R - 1) / R) * a.n_chunks;
@@ -283,7 +295,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
   for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
   double* my_prod = s_prod + tid;
   int* my_exp = s_exp + tid;
-  const ChildSpace cs = {a.codes, a.codes_stride, a.pool, a.slot_sites, a.n_sites, a.skip_leaf_pairs};
+  const ChildSpace cs = {a.codes, a.codes_stride, a.pool, a.slot_sites, a.n_sites, a.skip_leaf_pairs, a.skip_octets};
 
   for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
     const int64_t g = w / a.n_chunks;
@@ -301,6 +313,18 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
       s_k[tid] = sw ? ~k : k;
     }
     __syncthreads();
+    if (tid == 0) {
+      unsigned skip = 0u;
+      for (int j = 0; j < nj; ++j)
+        if (a.skip_leaf_pairs && s_b[j] < 0) skip |= 1u << j;
+      if (a.skip_octets)
+        for (int o = 0; o < 4; ++o)
+          if (octet_uniform(s_a, s_b, 8 * o, nj)) skip |= 0xffu << (8 * o);
+      s_skip = skip;
+    }
+    __syncthreads();
+    const unsigned skip = s_skip;
+    if ((skip | (nj < 32 ? ~0u << nj : 0u)) == ~0u) continue;   // nothing of this group is ours
     if (JC) {
       if (tid < nj) {
         const int kk = s_k[tid];
@@ -334,6 +358,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
       }
     }
     for (int j = 0; j < nj; ++j) {
+      if (skip >> j & 1u) continue;
       my_prod[j * kTileThreads] = 1.0;
       my_exp[j * kTileThreads] = 0;
     }
@@ -344,7 +369,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
     for (int t = t_begin; t < t_end; ++t) {
       const int sbase = t * (kTileThreads * SPT) + tid;
       const bool renorm = ((t - t_begin) & 127) == 127;
-      score_tile<JC, SPT>(cs, nj, sbase, renorm, pi, s_a, s_b, sC, my_prod, my_exp);
+      score_tile<JC, SPT>(cs, nj, skip, sbase, renorm, pi, s_a, s_b, sC, my_prod, my_exp);
     }
     // one log per (thread, particle): sum_s log x_s = log(prod mantissas) + ln2 * sum (exponents - bias)
     const int bias = 1023 * SPT * (t_end - t_begin);
@@ -357,7 +382,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
     __syncthreads();
     const unsigned odd_all = s_odd;
     for (int j = 0; j < nj; ++j) {
-      if (a.skip_leaf_pairs && s_b[j] < 0) continue;  // written by score_leaf_pairs_kernel
+      if (skip >> j & 1u) continue;  // written by score_leaf_pairs_kernel / merge_score_mma_kernel
       double acc;
       if (odd_all >> j & 1u) {
         // some likelihood of this particle is 0 / subnormal / not finite: one log per site, like the reference
@@ -372,6 +397,164 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
         const int kk = s_k[j];
         const int64_t k = kk < 0 ? ~kk : kk;
         a.ell_part[(k * a.n_chunks + tc) * kWarps + wid] = acc;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same scoring on the FP64 tensor cores, for octets of particles that share one child pair.
+//
+// x[particle][site] = sum_c M_particle[c] * O_site[c] is a GEMM with inner dimension 16.  One mma.sync.m8n8k4.f64
+// multiplies 8 particles (A: 8x4 coefficients, registers, loaded once per work item) by 8 sites (B: 4x8 site products,
+// 4 DMUL per lane per site block) -- 256 FMA per warp instruction instead of 32.  B200's DMMA rate equals its DFMA rate
+// (18.5 T FMA/s, scripts/microbench_dmma.cu): the gain is instruction issue, which is what bounds the vector kernel.
+// A warp owns 64 sites of every 512-site tile of the work item; a lane ends up with the likelihoods of ONE particle
+// (row lane/4) at two sites per block, folds them into a running (mantissa product, exponent sum) in registers, and the
+// four lanes of a row are combined at the end.  Same per-(particle, chunk, warp) partial sums as the vector kernel.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kTileThreads, 2) merge_score_mma_kernel(const ScoreArgs a) {
+  __shared__ __align__(16) double sC[kRScore * 16];
+  __shared__ int s_k[kRScore], s_a[kRScore], s_b[kRScore];
+  __shared__ unsigned s_odd, s_mine;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int row = lane >> 2, q4 = lane & 3;
+  const int R = a.R;
+  const int64_t total = ((a.K + R - 1) / R) * a.n_chunks;
+  double pi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
+  const ChildSpace cs = {a.codes, a.codes_stride, a.pool, a.slot_sites, a.n_sites, a.skip_leaf_pairs, 0};
+  constexpr int kTile = kTileThreads * 2;  // sites per tile (the vector kernel's tile with 2 sites per thread)
+
+  for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    const int64_t g = w / a.n_chunks;
+    const int tc = (int)(w - g * a.n_chunks);
+    const int64_t j0 = g * R;
+    const int nj = (int)min((int64_t)R, a.K - j0);
+    __syncthreads();
+    if (tid == 0) s_odd = 0u;
+    if (tid < nj) {
+      const int k = a.order ? a.order[j0 + tid] : (int)(j0 + tid);
+      const int ls = a.lsrc[k], rs = a.rsrc[k];
+      const bool sw = ls > rs;
+      s_a[tid] = sw ? rs : ls;
+      s_b[tid] = sw ? ls : rs;
+      s_k[tid] = sw ? ~k : k;
+    }
+    __syncthreads();
+    // which octets are mine (uniform pair, not a leaf pair)
+    if (tid == 0) {
+      unsigned m = 0u;
+      for (int o = 0; o < 4; ++o)
+        if (octet_uniform(s_a, s_b, 8 * o, nj) && !(a.skip_leaf_pairs && s_b[8 * o] < 0)) m |= 1u << o;
+      s_mine = m;
+    }
+    __syncthreads();
+    const unsigned mine = s_mine;
+    if (mine == 0u) continue;   // (uniform across the CTA)
+    for (int e = tid; e < nj * 16; e += kTileThreads) {
+      const int j = e >> 4, ai = (e >> 2) & 3, bi = e & 3;
+      const int kk = s_k[j];
+      const bool sw = kk < 0;
+      const int64_t k = sw ? ~kk : kk;
+      const double* Pa = a.P + k * 32 + (sw ? 16 : 0) + ai * 4;
+      const double* Pb = a.P + k * 32 + (sw ? 0 : 16) + bi * 4;
+      double m = pi[0] * __ldg(Pa) * __ldg(Pb);
+#pragma unroll
+      for (int i = 1; i < 4; ++i) m = fma(pi[i] * __ldg(Pa + i), __ldg(Pb + i), m);
+      sC[j * 16 + ai * 4 + bi] = m;
+    }
+    __syncthreads();
+    // A fragments: lane (row, q4) holds M_{particle 8 o + row}[4 ks + q4] for k-step ks
+    double A[4][4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) A[o][ks] = (mine >> o & 1u) ? sC[(8 * o + row) * 16 + 4 * ks + q4] : 0.0;
+    double pr[4] = {1.0, 1.0, 1.0, 1.0};
+    int ex[4] = {0, 0, 0, 0};
+
+    const int t_begin = tc * a.tiles_per_item;
+    const int t_end = min(a.tiles, t_begin + a.tiles_per_item);
+    int folded = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const bool renorm = ((t - t_begin) & 31) == 31;
+#pragma unroll 2
+      for (int blk = 0; blk < 8; ++blk) {
+        const int s0 = t * kTile + wid * 64 + blk * 8;   // the 8 sites of this block
+        const int sB = s0 + row;                          // B fragment: lane (q4, site row)
+        int pa = kNone, pb = kNone;
+        double B[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          if (!(mine >> o & 1u)) continue;
+          const int ca = s_a[8 * o], cb = s_b[8 * o];
+          if (ca != pa || cb != pb) {
+            // site products L_a[site][ks] * L_b[site][q4] for the four k-steps
+            if (sB < a.n_sites) {
+              const ChildRef ra = child_ref(ca, cs.codes, cs.codes_stride, cs.pool, cs.slot_sites);
+              const d4 La = load_child(ra, sB);
+              double lb;
+              if (cb < 0) lb = (__ldg(cs.codes + (int64_t)(-cb - 1) * cs.codes_stride + sB) >> q4 & 1) ? 1.0 : 0.0;
+              else lb = __ldg(cs.pool + ((int64_t)cb * cs.slot_sites + sB) * 4 + q4);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) B[ks] = La.v[ks] * lb;
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) B[ks] = 0.0;
+            }
+            pa = ca;
+            pb = cb;
+          }
+          double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) dmma8x8x4(c0, c1, A[o][ks], B[ks]);
+          // this lane: particle 8 o + row at sites s0 + 2 q4, s0 + 2 q4 + 1 (past the end: x = 1)
+          double x[2] = {s0 + 2 * q4 < a.n_sites ? c0 : 1.0, s0 + 2 * q4 + 1 < a.n_sites ? c1 : 1.0};
+          fold_sites<2>(x, renorm && blk == 7, &pr[o], &ex[o]);
+        }
+      }
+      folded += 16;   // site values folded per lane and octet in this tile
+    }
+    // poisoned products: the particle is re-evaluated with one log per site (never on sane inputs)
+    unsigned odd_mask = 0u;
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+      if ((mine >> o & 1u) && pr[o] != pr[o]) odd_mask |= 1u << (8 * o + row);
+    if (odd_mask) atomicOr(&s_odd, odd_mask);
+    __syncthreads();
+    const unsigned odd_all = s_odd;
+    const int bias = 1023 * folded;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      if (!(mine >> o & 1u)) continue;
+      const double e = (double)(ex[o] - bias);
+      double acc = fma(e, 6.93147180369123816490e-01, fma(e, 1.90821492927058770002e-10, log(pr[o])));
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      const int j = 8 * o + row;
+      if (q4 == 0 && !(odd_all >> j & 1u)) {
+        const int kk = s_k[j];
+        const int64_t k = kk < 0 ? ~kk : kk;
+        a.ell_part[(k * a.n_chunks + tc) * kWarps + wid] = acc;
+      }
+    }
+    if (odd_all) {
+      for (int j = 0; j < nj; ++j) {
+        if (!(odd_all >> j & 1u)) continue;
+        double acc = score_slow<false>(cs, s_a[j], s_b[j], sC + j * 16, t_begin * kTile, min(a.n_sites, t_end * kTile),
+                                       pi[0], pi[1], pi[2], pi[3]);
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          const int kk = s_k[j];
+          const int64_t k = kk < 0 ? ~kk : kk;
+          a.ell_part[(k * a.n_chunks + tc) * kWarps + wid] = acc;
+        }
       }
     }
   }
@@ -574,6 +757,15 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
   a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.slot_sites = slot_sites; a.lsrc = lsrc; a.rsrc = rsrc;
   a.order = order; a.P = P; a.pi = pi; a.K = K; a.n_sites = n_sites; a.ell_part = ell_part;
   a.skip_leaf_pairs = leaf_hist != nullptr;
+  static int use_mma = -1;
+  if (use_mma < 0) {
+    // VCSMC_SCORE_MMA=1 routes octets of particles that share a child pair to merge_score_mma_kernel (FP64 tensor cores).
+    // Measured at 64 x 10k x 65,536: 29.6 ms per sweep against 24.5 ms for the vector kernel alone -- DMMA and DFMA share
+    // one pipe on B200 (18.5 vs 18.2 T FMA/s) and the fold after each 8x8 block is the same work, so it stays off.
+    const char* e = getenv("VCSMC_SCORE_MMA");
+    use_mma = e ? atoi(e) != 0 : 0;
+  }
+  a.skip_octets = (!jc && spt == 2 && use_mma) ? 1 : 0;
   a.tiles = (n_sites + kTileThreads * spt - 1) / (kTileThreads * spt);
   // groups as large as the machine fill allows (shared children and site products are amortised over the group)
   int64_t R = (K * a.tiles) / kScoreItems;
@@ -594,6 +786,10 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
   else if (spt == 4) merge_score_kernel<false, 4><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
   else merge_score_kernel<false, 2><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
   VCSMC_LAUNCH_CHECK("merge_score_kernel");
+  if (a.skip_octets && a.R >= 8) {
+    merge_score_mma_kernel<<<grid, kTileThreads, 0, st>>>(a);
+    VCSMC_LAUNCH_CHECK("merge_score_mma_kernel");
+  }
   if (leaf_hist) {
     score_leaf_pairs_kernel<<<(unsigned)((K + 7) / 8), 256, 0, st>>>(lsrc, rsrc, P, pi, K, n_taxa, leaf_hist, a.n_chunks * kWarps, ell_part);
     VCSMC_LAUNCH_CHECK("score_leaf_pairs_kernel");
