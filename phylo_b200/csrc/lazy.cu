@@ -86,68 +86,6 @@ __global__ void lz_survivors_kernel(const SurvArgs a) {
   }
 }
 
-struct InhArgs {
-  int r, n, N, gc, rank;
-  int64_t K, Kl, k0, fetch_cap;
-  const int32_t* anc;
-  const int32_t* peer_ids[kMaxPeers];
-  const int32_t* peer_cnt[kMaxPeers];
-  int32_t* inh_ids;
-  int32_t* inh_cnt;
-  const int32_t* loc;
-  const int32_t* slot_id;
-  int32_t* flags;
-  int32_t* pend;
-  int32_t* fetch_e;
-  int32_t* fetch_src;
-  int32_t* counts;
-  const double* LL_prev;
-  double* ll_tilde;
-  int32_t* status;
-};
-
-constexpr int kInhWarps = 8;
-
-// one warp per own particle: copy the ancestor's forest row (peer read when it lives on another GPU), keep cached
-// nodes alive, list the nodes this rank holds no copy of
-__global__ void __launch_bounds__(kInhWarps * 32) lz_inherit_kernel(const InhArgs a) {
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t kl = (int64_t)blockIdx.x * kInhWarps + wid;
-  if (kl >= a.Kl) return;
-  const int64_t anc = a.anc[a.k0 + kl];
-  const int g = (int)(anc / a.Kl);
-  const int64_t al = anc - (int64_t)g * a.Kl;
-  const int32_t* src_ids = a.peer_ids[g] + al * a.N;
-  const int32_t* src_cnt = a.peer_cnt[g] + al * a.N;
-  const int64_t newest = (int64_t)(a.r - 1) * a.K + anc;  // the ancestor's own node: materialised by its owner
-  for (int p = lane; p < a.n; p += 32) {
-    const int id = src_ids[p];
-    a.inh_ids[kl * a.N + p] = id;
-    a.inh_cnt[kl * a.N + p] = src_cnt[p];
-    if (id < a.N) continue;
-    const int e = id - a.N;
-    bool have;
-    int s = -1;
-    if (e == newest) {
-      have = (g == a.rank);  // gets its slot from the allocator below, via the survivor list
-    } else {
-      s = a.loc[e];
-      have = !a.gc || (s >= 0 && a.slot_id[s] == e);
-      if (have && a.gc) a.flags[s] = 1;
-    }
-    if (!have && atomicExch(a.pend + e, a.r) != a.r) {  // first claim of this node in this rank event
-      const int pos = atomicAdd(a.counts + 1, 1);
-      if (pos < a.fetch_cap) {
-        a.fetch_e[pos] = e;
-        a.fetch_src[pos] = g;
-      } else {
-        a.status[0] = VCSMC_ERR_POOL;
-      }
-    }
-  }
-  if (lane == 0) a.ll_tilde[kl] = a.LL_prev[anc];
-}
-
 // Free slots (flag == 0), lowest first, go to the survivors to materialise and then to the nodes to pull.
 // Single CTA, fixed order; each warp owns a contiguous segment of the flag array.
 __global__ void __launch_bounds__(1024) lz_alloc_kernel(const int32_t* __restrict__ flags, int64_t P, const int32_t* __restrict__ counts,
@@ -214,75 +152,297 @@ __global__ void __launch_bounds__(1024) lz_alloc_kernel(const int32_t* __restric
   if (top) atomicMax(status + 1, top);
 }
 
-struct LzPrepArgs {
-  int r, n, N;
-  int64_t K, Kl, k0;
-  const float* u_pair;  // [Kl][n]
-  const double* u_bl;   // [Kl]
+// ---------------------------------------------------------------------------------------------
+// Inherit + propose in one pass (one warp per own particle): copy the ancestor's forest row (peer read when it lives on
+// another GPU), keep cached nodes alive / list missing ones, draw the pair and the two branch lengths, write the new
+// row.  The forest's scalars (sum of node log-likelihoods F, topology prior, v^-) travel with the particle and are
+// updated incrementally, so the weight step no longer walks the forest:
+//     F' = F_anc - ell[left] - ell[right] (+ ell[new], added once the merge has been scored).
+// resample vcsmc.py:284-289,318-325; extend_partial_state :298-305; Exponential sample :351-358; state update :361-373;
+// compute_forest_posterior :231-245 and overcounting_correct :247-252 as running sums.
+// ---------------------------------------------------------------------------------------------
+struct ProposeArgs {
+  int r, n, N, gc, rank, row_stride;
+  int64_t K, Kl, k0, fetch_cap;
+  const int32_t* anc;
+  const int32_t* peer_ids[kMaxPeers];
+  const int32_t* peer_cnt[kMaxPeers];
+  const double* peer_F[kMaxPeers];
+  const double* peer_topo[kMaxPeers];
+  const int32_t* peer_vm[kMaxPeers];
+  const int32_t* loc;
+  const int32_t* slot_id;
+  int32_t* flags;
+  int32_t* pend;
+  int32_t* fetch_e;
+  int32_t* fetch_src;
+  int32_t* counts;
+  int32_t* status;
+  const float* u_pair;   // explicit uniforms of the own particles ([Kl][n], [Kl], [Kl]) or null: counter-based generator
+  const double* u_bl;
   const double* u_br;
+  const uint64_t* seed_dev;
   const double* lam_l;
   const double* lam_r;
-  const int32_t* inh_ids;  // [Kl][N]
-  const int32_t* inh_cnt;
-  int32_t* ids_new;
+  const double* ell_node;
+  const double* ldf;
+  const double* LL_prev;
+  int32_t* ids_new;   // [Kl][N]
   int32_t* cnt_new;
-  const int32_t* loc;
-  int32_t* lref;  // row r of the [N-1][K] tables
+  double* F_new;      // [Kl] forest scalars after this event (F without the new node's term until the weight step)
+  double* topo_new;
+  int32_t* vm_new;
+  int32_t* lref;      // row r of the [N-1][K] tables
   int32_t* rref;
   int32_t* nleaf;
   uint8_t* rempos;
   double* b_l;
   double* b_r;
   double* t2;
-  double* ll_tilde;  // [Kl]
-  int32_t* lsrc;     // [Kl]
-  int32_t* rsrc;
+  double* ll_tilde;   // [Kl]
 };
 
-constexpr int kLzPrepWarps = 8;
+constexpr int kProposeWarps = 8;
 
-// One warp per own particle: pair proposal on the inherited row, forest-row update, branch lengths.
-// (extend_partial_state vcsmc.py:298-305; Exponential sample :351-358; state update :361-373)
-__global__ void __launch_bounds__(kLzPrepWarps * 32) lz_prepare_kernel(const LzPrepArgs a) {
-  extern __shared__ float su_all[];
+template <int NQ>
+__global__ void __launch_bounds__(kProposeWarps * 32) lz_propose_kernel(const ProposeArgs a) {
+  extern __shared__ __align__(16) float su_all[];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t kl = (int64_t)blockIdx.x * kLzPrepWarps + wid;
+  const int64_t kl = (int64_t)blockIdx.x * kProposeWarps + wid;
   if (kl >= a.Kl) return;
   const int n = a.n, N = a.N, r = a.r;
   const int64_t k = a.k0 + kl;
-  float* su = su_all + wid * n;
-  for (int i = lane; i < n; i += 32) su[i] = a.u_pair[kl * n + i];
+  const bool first = (r == 0);  // initial forest = the N leaves, one each (vcsmc.py:414-415)
+  float* su = su_all + wid * a.row_stride;
+
+  // ---- the ancestor's row
+  int64_t anc = k;
+  int g = a.rank;
+  int64_t al = kl;
+  if (!first) {
+    anc = a.anc[k];
+    g = (int)(anc / a.Kl);
+    al = anc - (int64_t)g * a.Kl;
+  }
+  const int32_t* src_ids = a.peer_ids[g] + al * N;
+  const int32_t* src_cnt = a.peer_cnt[g] + al * N;
+  const int64_t newest = (int64_t)(r - 1) * a.K + anc;  // the ancestor's own node: materialised by its owner
+  int my_id[NQ], my_cnt[NQ];
+  float my_u[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int i = lane + 32 * q;
+    my_id[q] = -1;
+    my_cnt[q] = 0;
+    my_u[q] = 0.f;
+    if (i >= n) continue;
+    if (first) {
+      my_id[q] = i;
+      my_cnt[q] = 1;
+    } else {
+      const int id = src_ids[i];
+      my_id[q] = id;
+      my_cnt[q] = src_cnt[i];
+      if (id >= N) {
+        const int e = id - N;
+        bool have;
+        if (e == newest) {
+          have = (g == a.rank);  // gets its slot from the allocator, via the survivor list
+        } else {
+          const int s = a.loc[e];
+          have = !a.gc || (s >= 0 && a.slot_id[s] == e);
+          if (have && a.gc) a.flags[s] = 1;
+        }
+        if (!have && atomicExch(a.pend + e, r) != r) {  // first claim of this node in this rank event
+          const int pos = atomicAdd(a.counts + 1, 1);
+          if (pos < a.fetch_cap) {
+            a.fetch_e[pos] = e;
+            a.fetch_src[pos] = g;
+          } else {
+            a.status[0] = VCSMC_ERR_POOL;
+          }
+        }
+      }
+    }
+    // ---- pair-proposal uniform of element i
+    float u;
+    if (a.u_pair) {
+      u = a.u_pair[kl * n + i];
+    } else {
+      uint32_t p[4] = {(uint32_t)k, (uint32_t)((uint64_t)k >> 32) | ((uint32_t)r << 8), 2u, (uint32_t)(i >> 2)};
+      const uint64_t seed = *a.seed_dev;
+      philox4x32_10(p, (uint32_t)seed, (uint32_t)(seed >> 32));
+      // 16 random bits + the 8-bit position: tie-free inside a row (see philox_step_kernel)
+      const uint32_t bits = ((p[i & 3] >> 8) & 0xFFFF00u) | (uint32_t)(i & 0xFF);
+      u = (float)bits * 5.9604644775390625e-8f;
+    }
+    my_u[q] = u;
+    su[i] = u;
+  }
+  for (int i = n + lane; i < ((n + 3) & ~3); i += 32) su[i] = INFINITY;   // padding of the float4 reads below
   __syncwarp();
-  const int32_t* io = a.inh_ids + kl * N;
-  const int32_t* co = a.inh_cnt + kl * N;
+
+  // ---- ranks.  z = -log(-log u) is increasing in u, so ranking u reproduces tf.nn.top_k (smc_device.cuh).  Without
+  // ties the ascending rank is #{u_j < u_i} and the descending rank its mirror image; rows with a tie (never produced
+  // by the generator above, possible with injected uniforms) take the exact all-pairs routine with the reference's
+  // tie rule.
+  int lt[NQ], eq[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) lt[q] = eq[q] = 0;
+  for (int j = 0; j < n; j += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(su + j);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      lt[q] += (v.x < my_u[q]) + (v.y < my_u[q]) + (v.z < my_u[q]) + (v.w < my_u[q]);
+      eq[q] += (v.x == my_u[q]) + (v.y == my_u[q]) + (v.z == my_u[q]) + (v.w == my_u[q]);
+    }
+  }
+  bool tie = false;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) tie = tie || (lane + 32 * q < n && eq[q] != 1);
   int32_t* in_ = a.ids_new + kl * N;
   int32_t* cn = a.cnt_new + kl * N;
   uint8_t* rp = a.rempos + k * (int64_t)(n - 2);
-  const bool first = (r == 0);  // initial forest = the N leaves, one each (vcsmc.py:414-415)
-  int c0, c1;
-  rank_pairs_warp(su, n, lane, c0, c1, [&](int pos, int i) {
-    rp[pos] = (uint8_t)i;
-    in_[pos] = first ? i : io[i];
-    cn[pos] = first ? 1 : co[i];
-  });
+  int lid = 0, rid = 0, cl = 0, cr = 0;   // (valid in lane 0 afterwards)
+  if (__any_sync(0xffffffffu, tie)) {
+    int c0, c1;
+    rank_pairs_warp(su, n, lane, c0, c1, [&](int pos, int i) {
+      rp[pos] = (uint8_t)i;
+      in_[pos] = first ? i : src_ids[i];
+      cn[pos] = first ? 1 : src_cnt[i];
+    });
+    lid = first ? c0 : src_ids[c0];
+    rid = first ? c1 : src_ids[c1];
+    cl = first ? 1 : src_cnt[c0];
+    cr = first ? 1 : src_cnt[c1];
+  } else {
+    int id0 = -1, ct0 = 0, id1 = -1, ct1 = 0;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int i = lane + 32 * q;
+      if (i >= n) continue;
+      const int ra = lt[q];
+      if (ra < n - 2) {
+        rp[ra] = (uint8_t)i;
+        in_[ra] = my_id[q];
+        cn[ra] = my_cnt[q];
+      } else if (ra == n - 1) {
+        id0 = my_id[q];
+        ct0 = my_cnt[q];
+      } else {
+        id1 = my_id[q];
+        ct1 = my_cnt[q];
+      }
+    }
+    const int s0 = __ffs(__ballot_sync(0xffffffffu, id0 >= 0)) - 1, s1 = __ffs(__ballot_sync(0xffffffffu, id1 >= 0)) - 1;
+    lid = __shfl_sync(0xffffffffu, id0, s0);
+    cl = __shfl_sync(0xffffffffu, ct0, s0);
+    rid = __shfl_sync(0xffffffffu, id1, s1);
+    cr = __shfl_sync(0xffffffffu, ct1, s1);
+  }
+  // ---- the forest's scalars before the merge
+  double F_anc = 0.0;
+  if (first) {
+    for (int i = lane; i < N; i += 32) F_anc += a.ell_node[i];
+    F_anc = warp_sum(F_anc);
+  }
   if (lane == 0) {
-    const int lid = first ? c0 : io[c0], rid = first ? c1 : io[c1];
+    double topo_anc = 0.0;   // -sum log (2 max(c,2) - 3)!! over the roots: 0 for N leaves
+    int vm_anc = 0;          // sum (c - [c == 1]) over the roots: 0 for N leaves
+    if (!first) {
+      F_anc = a.peer_F[g][al];
+      topo_anc = a.peer_topo[g][al];
+      vm_anc = a.peer_vm[g][al];
+    }
     in_[n - 2] = (int32_t)(N + (int64_t)r * a.K + k);
-    const int nl = (first ? 1 : co[c0]) + (first ? 1 : co[c1]);
+    const int nl = cl + cr;
     cn[n - 2] = nl;
     a.nleaf[k] = nl;
     a.lref[k] = lid;
     a.rref[k] = rid;
-    a.lsrc[kl] = lid < N ? -(lid + 1) : a.loc[lid - N];
-    a.rsrc[kl] = rid < N ? -(rid + 1) : a.loc[rid - N];
-    const double bl = -log(a.u_bl[kl]) / a.lam_l[r];
-    const double br = -log(a.u_br[kl]) / a.lam_r[r];
+    double ubl, ubr;
+    if (a.u_bl) {
+      ubl = a.u_bl[kl];
+      ubr = a.u_br[kl];
+    } else {
+      uint32_t c[4] = {(uint32_t)k, (uint32_t)((uint64_t)k >> 32) | ((uint32_t)r << 8), 0u, 0u};
+      const uint64_t seed = *a.seed_dev;
+      philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+      const double tiny = 2.2250738585072014e-308;
+      ubl = fmax(u64_to_unit_f64(c[0], c[1]), tiny);   // tfp Exponential: U in [tiny, 1)
+      ubr = fmax(u64_to_unit_f64(c[2], c[3]), tiny);
+    }
+    const double bl = -log(ubl) / a.lam_l[r];
+    const double br = -log(ubr) / a.lam_r[r];
     a.b_l[k] = bl;
     a.b_r[k] = br;
     a.t2[2 * k] = bl;
     a.t2[2 * k + 1] = br;
-    if (first) a.ll_tilde[kl] = log(1.0 / (double)a.K);
+    a.ll_tilde[kl] = first ? log(1.0 / (double)a.K) : a.LL_prev[anc];
+    a.F_new[kl] = F_anc - a.ell_node[lid] - a.ell_node[rid];
+    a.topo_new[kl] = topo_anc + a.ldf[2 * max(cl, 2) - 3] + a.ldf[2 * max(cr, 2) - 3] - a.ldf[2 * max(nl, 2) - 3];
+    a.vm_new[kl] = vm_anc - (cl - (cl == 1)) - (cr - (cr == 1)) + nl;
   }
+}
+
+// child slots of the own particles, once the allocator / the pulls have placed every node
+__global__ void lz_resolve_kernel(int64_t Kl, int N, const int32_t* __restrict__ lref, const int32_t* __restrict__ rref,
+                                  const int32_t* __restrict__ loc, int32_t* __restrict__ lsrc, int32_t* __restrict__ rsrc) {
+  const int64_t kl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (kl >= Kl) return;
+  const int l = lref[kl], r = rref[kl];
+  lsrc[kl] = l < N ? -(l + 1) : loc[l - N];
+  rsrc[kl] = r < N ? -(r + 1) : loc[r - N];
+}
+
+struct LzWeightArgs {
+  int r, n, tiles;
+  int64_t Kl;
+  const double* ell_part;
+  double* F;            // [Kl] in: forest sum without the new node; out: with it
+  const double* topo;   // [Kl]
+  const int32_t* vm;    // [Kl]
+  const double* lam_l;
+  const double* lam_r;
+  const double* b_l;    // own columns of row r
+  const double* b_r;
+  const double* cum_l_prev;
+  const double* cum_r_prev;
+  double* cum_l;
+  double* cum_r;
+  const double* ll_tilde;
+  double* ell_new;      // ell_node + N + r*K + k0
+  double* lw;
+  double* LL;
+  int32_t* vminus;
+  double q;
+};
+
+// forest posterior from the running sums + branch priors + v^- + weight (vcsmc.py:376-395), O(1) per particle
+__global__ void lz_weights_kernel(const LzWeightArgs a) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= a.Kl) return;
+  const int r = a.r;
+  double ell = 0.0;
+  for (int t = 0; t < a.tiles; ++t) ell += a.ell_part[k * a.tiles + t];
+  a.ell_new[k] = ell;
+  const double F = a.F[k] + ell;
+  a.F[k] = F;
+  const int vm = a.vm[k];
+  const double laml = a.lam_l[r], lamr = a.lam_r[r];
+  const double bl = a.b_l[k], br = a.b_r[k];
+  const double cl = (r > 0 ? a.cum_l_prev[k] : 0.0) + bl;   // quirk Q1: slot-wise, un-resampled histories
+  const double cr = (r > 0 ? a.cum_r_prev[k] : 0.0) + br;
+  a.cum_l[k] = cl;
+  a.cum_r[k] = cr;
+  const double llog = log(laml), rlog = log(lamr);
+  // quirk Q2: the CURRENT step's rate multiplies ALL earlier branches (vcsmc.py:380-383)
+  const double LLr = (F + a.topo[k]) + (-laml * cl + (double)(r + 1) * llog) + (-lamr * cr + (double)(r + 1) * rlog);
+  // quirk Q3: q = 1/C(n,2) is subtracted raw (vcsmc.py:298,392)
+  const double lw = LLr - a.ll_tilde[k] - (llog - laml * bl + rlog - lamr * br) + log((double)vm) - a.q;
+  a.LL[k] = LLr;
+  a.lw[k] = lw;
+  a.vminus[k] = vm;
 }
 
 // ---- the per-event record that is all-gathered across ranks (field-major inside a rank's chunk)
@@ -485,11 +645,8 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     const float* u_pair;
     const double *u_bl, *u_br, *u_res_all;
     if (h->use_seed) {
-      rc = launch_philox_step(0, r, k0, Kl, n, h->p<float>(h->o_u_pair), h->p<double>(h->o_u_bl), h->p<double>(h->o_u_br),
-                              nullptr, nullptr, st, h->p<uint64_t>(h->o_seed_dev));
-      if (rc) return rc;
-      u_pair = h->p<float>(h->o_u_pair); u_bl = h->p<double>(h->o_u_bl); u_br = h->p<double>(h->o_u_br);
-      u_res_all = nullptr;   // drawn inside lz_ancestors_kernel
+      u_pair = nullptr; u_bl = nullptr; u_br = nullptr;   // drawn inside lz_propose_kernel / lz_ancestors_kernel
+      u_res_all = nullptr;
     } else {
       u_pair = h->x_pair + pair_off + k0 * n; u_bl = h->x_bl + (int64_t)r * K + k0; u_br = h->x_br + (int64_t)r * K + k0;
       u_res_all = h->x_res + (int64_t)r * K;
@@ -499,6 +656,42 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     int32_t* ids_prev = h->p<int32_t>(h->o_ids[prev]);
     int32_t* ids_cur = h->p<int32_t>(h->o_ids[cur]);
     int32_t* cnt_cur = h->p<int32_t>(h->o_cnt[cur]);
+    int32_t* row_lref = h->p<int32_t>(h->o_lref) + (int64_t)r * K;
+    int32_t* row_rref = h->p<int32_t>(h->o_rref) + (int64_t)r * K;
+    int32_t* row_nleaf = h->p<int32_t>(h->o_nleaf) + (int64_t)r * K;
+    uint8_t* row_rempos = h->p<uint8_t>(h->o_rempos) + h->rem_off[r];
+    double* row_b_l = h->p<double>(h->o_b_l) + (int64_t)r * K;
+    double* row_b_r = h->p<double>(h->o_b_r) + (int64_t)r * K;
+    double* row_t2 = h->p<double>(h->o_t2) + (int64_t)r * 2 * K;
+    // inherit + propose for the rank's own particles (reads the rows and forest scalars event r-1 left behind)
+    auto launch_propose = [&]() -> int {
+      ProposeArgs a;
+      a.r = r; a.n = n; a.N = N; a.gc = gc; a.rank = h->rank; a.row_stride = (N + 3) & ~3;
+      a.K = K; a.Kl = Kl; a.k0 = k0; a.fetch_cap = h->fetch_cap; a.anc = anc_row;
+      for (int g = 0; g < kMaxPeers; ++g) {
+        const bool on = g < G;
+        a.peer_ids[g] = on ? reinterpret_cast<const int32_t*>(h->peer_ws[g] + h->o_ids[prev]) : nullptr;
+        a.peer_cnt[g] = on ? reinterpret_cast<const int32_t*>(h->peer_ws[g] + h->o_cnt[prev]) : nullptr;
+        a.peer_F[g] = on ? reinterpret_cast<const double*>(h->peer_ws[g] + h->o_F[prev]) : nullptr;
+        a.peer_topo[g] = on ? reinterpret_cast<const double*>(h->peer_ws[g] + h->o_topo[prev]) : nullptr;
+        a.peer_vm[g] = on ? reinterpret_cast<const int32_t*>(h->peer_ws[g] + h->o_vm[prev]) : nullptr;
+      }
+      a.loc = loc; a.slot_id = slot_id; a.flags = flags; a.pend = pend; a.fetch_e = fetch_e; a.fetch_src = fetch_src;
+      a.counts = counts; a.status = status;
+      a.u_pair = u_pair; a.u_bl = u_bl; a.u_br = u_br; a.seed_dev = h->p<uint64_t>(h->o_seed_dev);
+      a.lam_l = lam_l; a.lam_r = lam_r; a.ell_node = ell_node; a.ldf = h->p<double>(h->o_ldf);
+      a.LL_prev = r > 0 ? h->p<double>(h->o_LL) + (int64_t)(r - 1) * K : nullptr;
+      a.ids_new = ids_cur; a.cnt_new = cnt_cur;
+      a.F_new = h->p<double>(h->o_F[cur]); a.topo_new = h->p<double>(h->o_topo[cur]); a.vm_new = h->p<int32_t>(h->o_vm[cur]);
+      a.lref = row_lref; a.rref = row_rref; a.nleaf = row_nleaf; a.rempos = row_rempos;
+      a.b_l = row_b_l; a.b_r = row_b_r; a.t2 = row_t2; a.ll_tilde = ll_tilde;
+      const unsigned grid = (unsigned)((Kl + kProposeWarps - 1) / kProposeWarps);
+      const size_t smem = (size_t)kProposeWarps * a.row_stride * sizeof(float);
+      if (N <= 64) lz_propose_kernel<2><<<grid, kProposeWarps * 32, smem, st>>>(a);
+      else lz_propose_kernel<8><<<grid, kProposeWarps * 32, smem, st>>>(a);
+      VCSMC_LAUNCH_CHECK("lz_propose_kernel");
+      return VCSMC_OK;
+    };
 
     if (r > 0) {
       VCSMC_CUDA(cudaMemsetAsync(surv, 0, K * sizeof(int32_t), st));
@@ -515,18 +708,7 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
       sa.rsrc_prev = rsrc; sa.loc = loc; sa.flags = flags; sa.mat_list = mat_list; sa.counts = counts;
       lz_survivors_kernel<<<(unsigned)((Kl * (n + 2) + 255) / 256), 256, 0, st>>>(sa);
       VCSMC_LAUNCH_CHECK("lz_survivors_kernel");
-      InhArgs ia;
-      ia.r = r; ia.n = n; ia.N = N; ia.gc = gc; ia.rank = h->rank; ia.K = K; ia.Kl = Kl; ia.k0 = k0; ia.fetch_cap = h->fetch_cap;
-      ia.anc = anc_row;
-      for (int g = 0; g < kMaxPeers; ++g) {
-        ia.peer_ids[g] = g < G ? reinterpret_cast<const int32_t*>(h->peer_ws[g] + h->o_ids[prev]) : nullptr;
-        ia.peer_cnt[g] = g < G ? reinterpret_cast<const int32_t*>(h->peer_ws[g] + h->o_cnt[prev]) : nullptr;
-      }
-      ia.inh_ids = inh_ids; ia.inh_cnt = inh_cnt; ia.loc = loc; ia.slot_id = slot_id; ia.flags = flags; ia.pend = pend;
-      ia.fetch_e = fetch_e; ia.fetch_src = fetch_src; ia.counts = counts;
-      ia.LL_prev = h->p<double>(h->o_LL) + (int64_t)(r - 1) * K; ia.ll_tilde = ll_tilde; ia.status = status;
-      lz_inherit_kernel<<<(unsigned)((Kl + kInhWarps - 1) / kInhWarps), kInhWarps * 32, 0, st>>>(ia);
-      VCSMC_LAUNCH_CHECK("lz_inherit_kernel");
+      rc = launch_propose(); if (rc) return rc;
       if (gc) {
         lz_alloc_kernel<<<1, 1024, 0, st>>>(flags, h->pool_slots, counts, h->fetch_cap, mat_list, e_base_prev, fetch_e, loc, slot_id, status);
         VCSMC_LAUNCH_CHECK("lz_alloc_kernel");
@@ -552,24 +734,15 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
       h->prof_end(st);
     }
 
-    // ---- proposal for the rank's own particles
-    LzPrepArgs a;
-    a.r = r; a.n = n; a.N = N; a.K = K; a.Kl = Kl; a.k0 = k0;
-    a.u_pair = u_pair; a.u_bl = u_bl; a.u_br = u_br; a.lam_l = lam_l; a.lam_r = lam_r;
-    a.inh_ids = inh_ids; a.inh_cnt = inh_cnt; a.ids_new = ids_cur; a.cnt_new = cnt_cur; a.loc = loc;
-    a.lref = h->p<int32_t>(h->o_lref) + (int64_t)r * K;
-    a.rref = h->p<int32_t>(h->o_rref) + (int64_t)r * K;
-    a.nleaf = h->p<int32_t>(h->o_nleaf) + (int64_t)r * K;
-    a.rempos = h->p<uint8_t>(h->o_rempos) + h->rem_off[r];
-    a.b_l = h->p<double>(h->o_b_l) + (int64_t)r * K;
-    a.b_r = h->p<double>(h->o_b_r) + (int64_t)r * K;
-    a.t2 = h->p<double>(h->o_t2) + (int64_t)r * 2 * K;
-    a.ll_tilde = ll_tilde; a.lsrc = lsrc; a.rsrc = rsrc;
-    lz_prepare_kernel<<<(unsigned)((Kl + kLzPrepWarps - 1) / kLzPrepWarps), kLzPrepWarps * 32, (size_t)kLzPrepWarps * n * sizeof(float), st>>>(a);
-    VCSMC_LAUNCH_CHECK("lz_prepare_kernel");
+    if (r == 0) {
+      rc = launch_propose();
+      if (rc) return rc;
+    }
+    lz_resolve_kernel<<<(unsigned)((Kl + 255) / 256), 256, 0, st>>>(Kl, N, row_lref + k0, row_rref + k0, loc, lsrc, rsrc);
+    VCSMC_LAUNCH_CHECK("lz_resolve_kernel");
 
     double* P = h->p<double>(h->o_P) + ((int64_t)r * K + k0) * 32;
-    rc = launch_transition_fwd(Q, a.t2 + 2 * k0, 2 * Kl, h->jc, P, st);
+    rc = launch_transition_fwd(Q, row_t2 + 2 * k0, 2 * Kl, h->jc, P, st);
     if (rc) return rc;
     if (sorted) {
       rc = group_particles(h, lsrc, rsrc, nullptr, Kl, h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count), st);
@@ -582,8 +755,8 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     h->prof_end(st);
     if (rc) return rc;
 
-    WeightArgs w;
-    w.r = r; w.n = n; w.N = N; w.tiles = tiles; w.K = Kl;
+    LzWeightArgs w;
+    w.r = r; w.n = n; w.tiles = tiles; w.Kl = Kl;
     w.ell_part = h->p<double>(h->o_ell_part);
     if (h->allreduce) {
       rc = launch_ell_reduce(h->p<double>(h->o_ell_part), tiles, Kl, h->p<double>(h->o_ell_new), st);
@@ -592,31 +765,30 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
       w.ell_part = h->p<double>(h->o_ell_new);
       w.tiles = 1;
     }
-    w.ids_new = ids_cur; w.cnt_new = cnt_cur; w.ldf = h->p<double>(h->o_ldf);
-    w.lam_l = lam_l; w.lam_r = lam_r; w.b_l = a.b_l + k0; w.b_r = a.b_r + k0;
+    w.F = h->p<double>(h->o_F[cur]); w.topo = h->p<double>(h->o_topo[cur]); w.vm = h->p<int32_t>(h->o_vm[cur]);
+    w.lam_l = lam_l; w.lam_r = lam_r; w.b_l = row_b_l + k0; w.b_r = row_b_r + k0;
     w.cum_l_prev = r > 0 ? h->p<double>(h->o_cum_l) + (int64_t)(r - 1) * K + k0 : nullptr;
     w.cum_r_prev = r > 0 ? h->p<double>(h->o_cum_r) + (int64_t)(r - 1) * K + k0 : nullptr;
     w.cum_l = h->p<double>(h->o_cum_l) + (int64_t)r * K + k0;
     w.cum_r = h->p<double>(h->o_cum_r) + (int64_t)r * K + k0;
-    w.ll_tilde = ll_tilde; w.ell_node = ell_node;
+    w.ll_tilde = ll_tilde;
+    w.ell_new = ell_node + N + (int64_t)r * K + k0;
     w.lw = h->p<double>(h->o_lw) + (int64_t)r * K + k0;
     w.LL = h->p<double>(h->o_LL) + (int64_t)r * K + k0;
     w.vminus = h->p<int32_t>(h->o_vminus) + k0;
     w.q = 1.0 / ((double)n * (double)(n - 1) / 2.0);
-    w.e_off = N + (int64_t)r * K + k0;
-    w.qlog = nullptr;
-    rc = launch_step_weights(w, st);
-    if (rc) return rc;
+    lz_weights_kernel<<<(unsigned)((Kl + 127) / 128), 128, 0, st>>>(w);
+    VCSMC_LAUNCH_CHECK("lz_weights_kernel");
 
     if (G > 1) {
       RecArgs ra;
       ra.n = n; ra.rank = h->rank; ra.Kl = Kl; ra.k0 = k0; ra.K = K; ra.stride = h->rec_stride; ra.rec = h->p<char>(h->o_rec);
       for (int g = 0; g < kMaxPeers; ++g) ra.peer_rec[g] = nullptr;
       ra.lw = h->p<double>(h->o_lw) + (int64_t)r * K; ra.LL = h->p<double>(h->o_LL) + (int64_t)r * K;
-      ra.ell = ell_node + N + (int64_t)r * K; ra.b_l = a.b_l; ra.b_r = a.b_r;
+      ra.ell = ell_node + N + (int64_t)r * K; ra.b_l = row_b_l; ra.b_r = row_b_r;
       ra.cum_l = h->p<double>(h->o_cum_l) + (int64_t)r * K; ra.cum_r = h->p<double>(h->o_cum_r) + (int64_t)r * K;
-      ra.t2 = a.t2; ra.lref = a.lref; ra.rref = a.rref; ra.nleaf = a.nleaf; ra.vminus = h->p<int32_t>(h->o_vminus);
-      ra.rempos = a.rempos;
+      ra.t2 = row_t2; ra.lref = row_lref; ra.rref = row_rref; ra.nleaf = row_nleaf; ra.vminus = h->p<int32_t>(h->o_vminus);
+      ra.rempos = row_rempos;
       lz_pack_kernel<<<(unsigned)((Kl + 127) / 128), 128, 0, st>>>(ra);
       VCSMC_LAUNCH_CHECK("lz_pack_kernel");
       if (h->peer_sync) {

@@ -815,6 +815,11 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_lz_cnt = L.take<int32_t>(K * N);
     h->o_u_res_all = L.take<double>(K);
     h->o_leaf_hist = L.take<int32_t>(leaf_pair_hist_ints(N));
+    for (int i = 0; i < 2; ++i) {   // forest scalars that travel with a particle (lazy.cu)
+      h->o_F[i] = L.take<double>(K);
+      h->o_topo[i] = L.take<double>(K);
+      h->o_vm[i] = L.take<int32_t>(K);
+    }
     h->rec_stride = align_up((h->Kl > 0 ? h->Kl : K) * (int64_t)(72 + N), 16);
     h->o_rec = L.take<char>(K * (int64_t)(72 + N) + 16 * kMaxPeers + 256);
   }
