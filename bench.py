@@ -42,7 +42,9 @@ METRIC = "particle-site merges/sec (fwd+grad VCSMC sweep)"
 UNIT = "merges/s"
 BYTES_FWD, BYTES_BWD = 64.0, 128.0   # algorithmic bytes per merge, fp64 (SURVEY 8d / BASELINE.md section 3)
 FP64_PEAK_TFMA = 18.2                # measured FP64 FMA rate of a B200 on this pool (scripts/microbench.cu), T op/s
-FP64_OPS_SCORE = {"gtr": 18.0, "jc": 6.0}   # FP64-pipe instructions per particle.site of the scoring kernel
+# FP64-pipe operations per particle.site of the scoring path, by kind of merge: two internal children (16 DFMA + DADD +
+# the mantissa DMUL), leaf + internal (4 DFMA + DADD + DMUL), two leaves (site patterns: O(1) per particle, counted as 0)
+FP64_OPS_SCORE = {"gtr": (18.0, 6.0, 0.0), "jc": (6.0, 6.0, 0.0)}
 
 
 def parse():
@@ -331,9 +333,17 @@ def run_native(args):
                         "children from L2, so it is bounded by the FP64 pipe (see fp64), not by HBM; the HBM-bound schedule "
                         "is timed under eager_dense"}
     if kname == "merge_score" and dom_ms > 0:
-        tops = FP64_OPS_SCORE[args.model] * fwd_merges / (dom_ms * 1e-3) / 1e12
+        # what the scoring kernels really had to evaluate in the last sweep: classify its merges by kind of children
+        lr, rr = sweep.output("left_ref"), sweep.output("right_ref")
+        k_lo, k_hi = (rank * K_fwd, (rank + 1) * K_fwd) if sharding == "particles" else (0, K)
+        l_leaf, r_leaf = (lr[:, k_lo:k_hi] < N), (rr[:, k_lo:k_hi] < N)
+        n_ll = int((l_leaf & r_leaf).sum()); n_li = int((l_leaf ^ r_leaf).sum()); n_ii = int((~l_leaf & ~r_leaf).sum())
+        o_ii, o_li, o_ll = FP64_OPS_SCORE[args.model]
+        ops_per_sweep = float(S_fwd) * (o_ii * n_ii + o_li * n_li + o_ll * n_ll)
+        tops = ops_per_sweep * args.steps / (dom_ms * 1e-3) / 1e12
         roofline["fp64"] = {"achieved": tops, "peak": FP64_PEAK_TFMA, "unit": "T FP64 op/s", "frac": tops / FP64_PEAK_TFMA,
-                            "ops_per_merge": FP64_OPS_SCORE[args.model],
+                            "merges_by_children": {"internal+internal": n_ii, "leaf+internal": n_li, "leaf+leaf (site patterns)": n_ll},
+                            "ops_per_merge": {"internal+internal": o_ii, "leaf+internal": o_li, "leaf+leaf": o_ll},
                             "peak_source": "scripts/microbench.cu on this pool's B200s (DFMA, 64 warps/SM)"}
 
     # ---- the eager / dense schedule (every node stored, no zero-adjoint skipping): the HBM-bound kernels

@@ -153,13 +153,26 @@ __global__ void __launch_bounds__(kLookThreads) lookahead_kernel(const LookArgs 
     const int c = c0 + (G == 1 ? tid : tid % combos);
     const bool on = worker && c < combos;
     int r1 = 0, r2 = 1;
-    double Pl[16], Pr[16];
+    // The site likelihood of a merge is a bilinear form of the two children (score.cu):
+    //   x[s] = sum_{j,m} L1[s][j] L2[s][m] Mx[j][m],  Mx[j][m] = sum_i pi_i Pl[j][i] Pr[m][i]
+    // -- 20 DFMA per site (t = Mx L2, then L1 . t) instead of 36, and 16 registers instead of the two P matrices.
+    double Mx[16];
     if (on) {
       pair_of(c / M, n, r1, r2);
       double ul, ur;
       look_uniforms(a.u_bl, a.u_br, a.seed, a.r, k, a.K, M, c, ul, ur);
+      double Pl[16], Pr[16];
       transition_of(a.Q, -log(ul) / laml, JC, Pl);
       transition_of(a.Q, -log(ur) / lamr, JC, Pr);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          double v = pi[0] * Pl[j * 4] * Pr[m * 4];
+#pragma unroll
+          for (int i = 1; i < 4; ++i) v = fma(pi[i] * Pl[j * 4 + i], Pr[m * 4 + i], v);
+          Mx[j * 4 + m] = v;
+        }
     }
     double pr = 1.0;
     int ex = 0;
@@ -184,13 +197,10 @@ __global__ void __launch_bounds__(kLookThreads) lookahead_kernel(const LookArgs 
           double x = 0.0;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            double lp = L1.v[0] * Pl[j], rp = L2.v[0] * Pr[j];
+            double t = Mx[j * 4] * L2.v[0];
 #pragma unroll
-            for (int i = 1; i < 4; ++i) {
-              lp = fma(L1.v[i], Pl[i * 4 + j], lp);
-              rp = fma(L2.v[i], Pr[i * 4 + j], rp);
-            }
-            x = fma(pi[j], lp * rp, x);
+            for (int m = 1; m < 4; ++m) t = fma(Mx[j * 4 + m], L2.v[m], t);
+            x = fma(L1.v[j], t, x);
           }
           const int hi = __double2hiint(x);
           const int e = (hi >> 20) & 0x7ff;
