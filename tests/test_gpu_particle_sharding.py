@@ -143,3 +143,58 @@ def test_particle_sharding_seeded_equals_single_gpu():
         assert o["elbo"] == pytest.approx(elbo, rel=1e-12)
         np.testing.assert_array_equal(o["ancestors"][1:], anc[1:])
         np.testing.assert_allclose(o["grads"], grads, rtol=1e-7, atol=1e-9 * np.abs(grads).max())
+
+
+def _train_worker(rank, world, port, sharding, out):
+    """Two optimiser steps through the drop-in class under torch.distributed (the path runner.py takes under torchrun)."""
+    import argparse
+    import math
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    ndev = torch.cuda.device_count()
+    torch.cuda.set_device(rank % ndev)
+    if world > 1:
+        if ndev >= world:
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank % ndev))
+        else:
+            dist.init_process_group("gloo", rank=rank, world_size=world)
+    from phylo_b200.vcsmc import VCSMC
+    g = synthetic_genome(8, 300, seed=21, gaps=0.02)
+    args = argparse.Namespace(dataset="synthetic", n_particles=64, batch_size=128, learning_rate=0.01, num_epoch=1,
+                              optimizer="GradientDescentOptimizer", branch_prior=math.log(10.0), M=10, nested=False,
+                              jcmodel=False, memory_optimization="on")
+    m = VCSMC({"taxa": ["t%d" % i for i in range(8)], "genome": g}, 64, args, seed=3, sharding=sharding)
+    assert m.sharding == (sharding if world > 1 else "none")
+    opt = torch.optim.SGD(m.trainable_variables(), lr=0.01)
+    sites = np.random.default_rng(1).permutation(300)[:128].astype(np.int32)
+    elbos = []
+    for it in range(2):
+        opt.zero_grad(set_to_none=True)
+        cost = -m.sample_phylogenies(sites, need_grad=True, seed=500 + it)
+        cost.backward()
+        m._allreduce_grads()
+        opt.step()
+        elbos.append(float(-cost))
+    full = float(m.sample_phylogenies(need_grad=False, seed=900))
+    out[rank] = (elbos, full, [v.detach().cpu().numpy().copy() for v in m.trainable_variables()])
+    m._sweeps.clear()
+    m._last = None
+    if world > 1:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("sharding", ["particles", "sites"])
+def test_training_steps_agree_across_world_sizes(sharding):
+    """VCSMC(...).sample_phylogenies / backward / SGD under 1 and 2 ranks: same ELBOs, same updated variables."""
+    mgr = mp.Manager()
+    ref, two = mgr.dict(), mgr.dict()
+    mp.spawn(_train_worker, args=(1, 29800, sharding, ref), nprocs=1, join=True)
+    mp.spawn(_train_worker, args=(2, 29801 + (sharding == "sites"), sharding, two), nprocs=2, join=True)
+    e1, f1, v1 = ref[0]
+    for rank in (0, 1):
+        e2, f2, v2 = two[rank]
+        np.testing.assert_allclose(e2, e1, rtol=1e-10)
+        assert f2 == pytest.approx(f1, rel=1e-10)
+        for a, b in zip(v2, v1):
+            np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-10)
