@@ -264,21 +264,94 @@ __global__ void __launch_bounds__(kProposeWarps * 32) lz_propose_kernel(const Pr
         }
       }
     }
-    // ---- pair-proposal uniform of element i
-    float u;
-    if (a.u_pair) {
-      u = a.u_pair[kl * n + i];
-    } else {
-      uint32_t p[4] = {(uint32_t)k, (uint32_t)((uint64_t)k >> 32) | ((uint32_t)r << 8), 2u, (uint32_t)(i >> 2)};
-      const uint64_t seed = *a.seed_dev;
-      philox4x32_10(p, (uint32_t)seed, (uint32_t)(seed >> 32));
-      // 16 random bits + the 8-bit position: tie-free inside a row (see philox_step_kernel)
-      const uint32_t bits = ((p[i & 3] >> 8) & 0xFFFF00u) | (uint32_t)(i & 0xFF);
-      u = (float)bits * 5.9604644775390625e-8f;
+    if (a.u_pair) {   // injected uniforms: ranked by counting below
+      const float u = a.u_pair[kl * n + i];
+      my_u[q] = u;
+      su[i] = u;
     }
-    my_u[q] = u;
-    su[i] = u;
   }
+  int32_t* in_ = a.ids_new + kl * N;
+  int32_t* cn = a.cnt_new + kl * N;
+  uint8_t* rp = a.rempos + k * (int64_t)(n - 2);
+  int lid = 0, rid = 0, cl = 0, cr = 0;   // (valid in lane 0 afterwards)
+  if (!a.u_pair) {
+    // ---- counter-based uniforms: u_i = ((16 random bits) << 8 | i) 2^-24 (philox_step_kernel), so the integer key
+    // orders like u, is tie-free, and carries the element's index: ONE warp bitonic sort of the keys gives the kept
+    // order (ascending) and the merged pair (the two largest).  Lane b draws Philox block b (4 uniforms).
+    constexpr int NB = NQ >= 4 ? NQ / 4 : 1;
+    uint32_t blk[NB][4];
+    const uint64_t seed = *a.seed_dev;
+#pragma unroll
+    for (int t = 0; t < NB; ++t) {
+      blk[t][0] = (uint32_t)k;
+      blk[t][1] = (uint32_t)((uint64_t)k >> 32) | ((uint32_t)r << 8);
+      blk[t][2] = 2u;
+      blk[t][3] = (uint32_t)(lane + 32 * t);
+      philox4x32_10(blk[t], (uint32_t)seed, (uint32_t)(seed >> 32));
+    }
+    uint32_t key[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int i = lane + 32 * q;
+      const int src = (i >> 2) & 31;
+      uint32_t w = 0u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t x = __shfl_sync(0xffffffffu, blk[q >> 2][c], src);   // block (i >> 2) lives in lane src, slot q >> 2
+        if (c == (i & 3)) w = x;
+      }
+      key[q] = i < n ? ((w >> 8) & 0xFFFF00u) | (uint32_t)(i & 0xFF) : 0xFFFFFFFFu;
+    }
+    // bitonic sort of the 32*NQ keys, element index = lane + 32 q, ascending
+#pragma unroll
+    for (int k2 = 2; k2 <= 32 * NQ; k2 <<= 1) {
+#pragma unroll
+      for (int j = k2 >> 1; j > 0; j >>= 1) {
+        if (j >= 32) {
+          const int dq = j >> 5;
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            if ((q & dq) == 0) {
+              const bool asc = (((lane + 32 * q) & k2) == 0);
+              const uint32_t lo = min(key[q], key[q | dq]), hi = max(key[q], key[q | dq]);
+              key[q] = asc ? lo : hi;
+              key[q | dq] = asc ? hi : lo;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < NQ; ++q) {
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, key[q], j);
+            const bool asc = (((lane + 32 * q) & k2) == 0);
+            const bool lower = ((lane & j) == 0);
+            key[q] = (asc == lower) ? min(key[q], other) : max(key[q], other);
+          }
+        }
+      }
+    }
+    int i0 = -1, i1 = -1;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      const int pos = lane + 32 * q;
+      if (pos >= n) continue;
+      const int i = (int)(key[q] & 0xFFu);
+      if (pos < n - 2) {
+        rp[pos] = (uint8_t)i;
+        in_[pos] = first ? i : src_ids[i];
+        cn[pos] = first ? 1 : src_cnt[i];
+      } else if (pos == n - 1) {
+        i0 = i;
+      } else {
+        i1 = i;
+      }
+    }
+    // positions n-1 / n-2 live in lanes (n-1) & 31 / (n-2) & 31 (max over the lane's slots picks the one that was set)
+    const int c0 = __shfl_sync(0xffffffffu, i0, (n - 1) & 31), c1 = __shfl_sync(0xffffffffu, i1, (n - 2) & 31);
+    lid = first ? c0 : src_ids[c0];
+    rid = first ? c1 : src_ids[c1];
+    cl = first ? 1 : src_cnt[c0];
+    cr = first ? 1 : src_cnt[c1];
+  } else {
   for (int i = n + lane; i < ((n + 3) & ~3); i += 32) su[i] = INFINITY;   // padding of the float4 reads below
   __syncwarp();
 
@@ -300,10 +373,6 @@ __global__ void __launch_bounds__(kProposeWarps * 32) lz_propose_kernel(const Pr
   bool tie = false;
 #pragma unroll
   for (int q = 0; q < NQ; ++q) tie = tie || (lane + 32 * q < n && eq[q] != 1);
-  int32_t* in_ = a.ids_new + kl * N;
-  int32_t* cn = a.cnt_new + kl * N;
-  uint8_t* rp = a.rempos + k * (int64_t)(n - 2);
-  int lid = 0, rid = 0, cl = 0, cr = 0;   // (valid in lane 0 afterwards)
   if (__any_sync(0xffffffffu, tie)) {
     int c0, c1;
     rank_pairs_warp(su, n, lane, c0, c1, [&](int pos, int i) {
@@ -339,6 +408,7 @@ __global__ void __launch_bounds__(kProposeWarps * 32) lz_propose_kernel(const Pr
     cl = __shfl_sync(0xffffffffu, ct0, s0);
     rid = __shfl_sync(0xffffffffu, id1, s1);
     cr = __shfl_sync(0xffffffffu, ct1, s1);
+  }
   }
   // ---- the forest's scalars before the merge
   double F_anc = 0.0;
