@@ -23,8 +23,8 @@ int64_t leaf_pair_hist_ints(int N);
 int launch_leaf_pair_hist(const uint8_t* codes, int64_t stride, int N, int S, int32_t* hist, cudaStream_t st);
 int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double* pool, int64_t slot_sites,
                        const int32_t* lsrc, const int32_t* rsrc, const int32_t* order, const double* P, const double* pi,
-                       int64_t K, int n_sites, int jc, const int32_t* leaf_hist, int n_taxa, double* ell_part, int* n_parts,
-                       cudaStream_t st);
+                       int64_t K, const int32_t* count, int n_sites, int jc, const int32_t* leaf_hist, int n_taxa,
+                       double* ell_part, int* n_parts, cudaStream_t st);
 int launch_materialise(const uint8_t* codes, int64_t codes_stride, double* pool, int64_t slot_sites, const int32_t* lsrc,
                        const int32_t* rsrc, const int32_t* list, const int32_t* count, int64_t max_count, const int32_t* loc,
                        int64_t e_base, const double* P, int n_sites, int jc, cudaStream_t st);
@@ -41,7 +41,7 @@ int launch_sort_order(const int32_t* lsrc, const int32_t* rsrc, const int32_t* a
                       size_t temp_bytes, cudaStream_t st);
 
 int64_t group_table_entries(int64_t K);
-int launch_group_order(const int32_t* lsrc, const int32_t* rsrc, const int32_t* active, int64_t K, unsigned long long* tab,
+int launch_group_order(const int32_t* lsrc, const int32_t* rsrc, const int32_t* active, int skip_leaf_pairs, int64_t K, unsigned long long* tab,
                        int32_t* cnt, int32_t* off, int32_t* gslot, int32_t* grank, int32_t* order_out, int32_t* count_out,
                        void* temp, size_t temp_bytes, cudaStream_t st);
 

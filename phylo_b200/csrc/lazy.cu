@@ -815,12 +815,13 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     rc = launch_transition_fwd(Q, row_t2 + 2 * k0, 2 * Kl, h->jc, P, st);
     if (rc) return rc;
     if (sorted) {
-      rc = group_particles(h, lsrc, rsrc, nullptr, Kl, h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count), st);
+      rc = group_particles(h, lsrc, rsrc, nullptr, Kl, h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count), st, leaf_hist != nullptr);
       if (rc) return rc;
     }
     int tiles = 0;
     h->prof_begin(0, st);
-    rc = launch_merge_score(codes, S, pool, S, lsrc, rsrc, sorted ? h->p<int32_t>(h->o_order) : nullptr, P, pi, Kl, S, h->jc,
+    rc = launch_merge_score(codes, S, pool, S, lsrc, rsrc, sorted ? h->p<int32_t>(h->o_order) : nullptr, P, pi, Kl,
+                            sorted ? h->p<int32_t>(h->o_count) : nullptr, S, h->jc,
                             leaf_hist, N, h->p<double>(h->o_ell_part), &tiles, st);
     h->prof_end(st);
     if (rc) return rc;

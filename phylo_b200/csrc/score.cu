@@ -33,7 +33,8 @@ struct ScoreArgs {
   int64_t slot_sites;
   const int32_t* lsrc;
   const int32_t* rsrc;
-  const int32_t* order;  // sorted visiting order (null: identity)
+  const int32_t* order;  // grouped visiting order (null: identity)
+  const int32_t* count;  // device: number of leading entries of `order` to score (null: K)
   const double* P;       // [K][32]
   const double* pi;
   int64_t K;
@@ -289,7 +290,8 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
   __shared__ unsigned s_odd, s_skip;   // s_skip: particles of the group some other kernel scores (leaf pairs, uniform octets)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int R = a.R;
-  const int64_t total = ((a.K + R - 1) / R) * a.n_chunks;
+  const int64_t count = a.count ? (int64_t)*a.count : a.K;
+  const int64_t total = ((count + R - 1) / R) * a.n_chunks;
   double pi[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
     const int64_t g = w / a.n_chunks;
     const int tc = (int)(w - g * a.n_chunks);
     const int64_t j0 = g * R;
-    const int nj = (int)min((int64_t)R, a.K - j0);
+    const int nj = (int)min((int64_t)R, count - j0);
     __syncthreads();
     if (tid == 0) s_odd = 0u;
     if (tid < nj) {
@@ -424,7 +426,8 @@ __global__ void __launch_bounds__(kTileThreads, 2) merge_score_mma_kernel(const 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int row = lane >> 2, q4 = lane & 3;
   const int R = a.R;
-  const int64_t total = ((a.K + R - 1) / R) * a.n_chunks;
+  const int64_t count = a.count ? (int64_t)*a.count : a.K;
+  const int64_t total = ((count + R - 1) / R) * a.n_chunks;
   double pi[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
@@ -435,7 +438,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) merge_score_mma_kernel(const 
     const int64_t g = w / a.n_chunks;
     const int tc = (int)(w - g * a.n_chunks);
     const int64_t j0 = g * R;
-    const int nj = (int)min((int64_t)R, a.K - j0);
+    const int nj = (int)min((int64_t)R, count - j0);
     __syncthreads();
     if (tid == 0) s_odd = 0u;
     if (tid < nj) {
@@ -739,8 +742,8 @@ int launch_leaf_pair_hist(const uint8_t* codes, int64_t stride, int N, int S, in
 
 int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double* pool, int64_t slot_sites,
                        const int32_t* lsrc, const int32_t* rsrc, const int32_t* order, const double* P, const double* pi,
-                       int64_t K, int n_sites, int jc, const int32_t* leaf_hist, int n_taxa, double* ell_part, int* n_parts,
-                       cudaStream_t st) {
+                       int64_t K, const int32_t* count, int n_sites, int jc, const int32_t* leaf_hist, int n_taxa,
+                       double* ell_part, int* n_parts, cudaStream_t st) {
   if (n_parts) *n_parts = 0;
   if (K <= 0 || n_sites <= 0) return VCSMC_OK;
   static int spt_general = 0;
@@ -755,7 +758,7 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
   const int spt = jc ? 4 : spt_general;
   ScoreArgs a;
   a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.slot_sites = slot_sites; a.lsrc = lsrc; a.rsrc = rsrc;
-  a.order = order; a.P = P; a.pi = pi; a.K = K; a.n_sites = n_sites; a.ell_part = ell_part;
+  a.order = order; a.count = order ? count : nullptr; a.P = P; a.pi = pi; a.K = K; a.n_sites = n_sites; a.ell_part = ell_part;
   a.skip_leaf_pairs = leaf_hist != nullptr;
   static int use_mma = -1;
   if (use_mma < 0) {

@@ -33,12 +33,14 @@ __global__ void __launch_bounds__(256) build_keys_kernel(const int32_t* __restri
 // table keyed by the pair hands out group slots, a warp-aggregated counter hands out ranks inside a group, one scan
 // turns the counts into offsets: 4 short launches instead of the ~13 of a 40-bit radix sort.
 __global__ void __launch_bounds__(256) group_insert_kernel(const int32_t* __restrict__ lsrc, const int32_t* __restrict__ rsrc,
-                                                           const int32_t* __restrict__ active, int64_t K, int log2T,
-                                                           unsigned long long* __restrict__ tab, int32_t* __restrict__ cnt,
-                                                           int32_t* __restrict__ gslot, int32_t* __restrict__ grank) {
+                                                           const int32_t* __restrict__ active, int skip_leaf_pairs, int64_t K,
+                                                           int log2T, unsigned long long* __restrict__ tab,
+                                                           int32_t* __restrict__ cnt, int32_t* __restrict__ gslot,
+                                                           int32_t* __restrict__ grank) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
-  const bool on = k < K && (active ? active[k] != 0 : true);
+  bool on = k < K && (active ? active[k] != 0 : true);
+  if (on && skip_leaf_pairs && lsrc[k] < 0 && rsrc[k] < 0) on = false;   // two leaves: scored from site patterns, not listed
   int slot = -1 - lane;  // inactive lanes never match anybody
   if (on) {
     const int ls = lsrc[k], rs = rsrc[k];
@@ -92,7 +94,7 @@ int64_t group_table_entries(int64_t K) {
   return T;
 }
 
-int launch_group_order(const int32_t* lsrc, const int32_t* rsrc, const int32_t* active, int64_t K, unsigned long long* tab,
+int launch_group_order(const int32_t* lsrc, const int32_t* rsrc, const int32_t* active, int skip_leaf_pairs, int64_t K, unsigned long long* tab,
                        int32_t* cnt, int32_t* off, int32_t* gslot, int32_t* grank, int32_t* order_out, int32_t* count_out,
                        void* temp, size_t temp_bytes, cudaStream_t st) {
   if (K <= 0) return VCSMC_OK;
@@ -103,7 +105,7 @@ int launch_group_order(const int32_t* lsrc, const int32_t* rsrc, const int32_t* 
   VCSMC_CUDA(cudaMemsetAsync(tab, 0, (size_t)T * (sizeof(unsigned long long) + sizeof(int32_t)), st));
   VCSMC_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int32_t), st));
   count_launch(2);
-  group_insert_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(lsrc, rsrc, active, K, log2T, tab, cnt, gslot, grank);
+  group_insert_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(lsrc, rsrc, active, skip_leaf_pairs, K, log2T, tab, cnt, gslot, grank);
   VCSMC_LAUNCH_CHECK("group_insert_kernel");
   group_offsets_kernel<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(T, cnt, off, count_out);
   VCSMC_LAUNCH_CHECK("group_offsets_kernel");

@@ -689,8 +689,8 @@ double log_double_factorial_host(int m) {  // vcsmc.py:30-57
 
 
 int group_particles(vcsmc_sweep* h, const int32_t* lsrc, const int32_t* rsrc, const int32_t* active, int64_t K,
-                    int32_t* order_out, int32_t* count_out, cudaStream_t st) {
-  return launch_group_order(lsrc, rsrc, active, K, h->p<unsigned long long>(h->o_gtab), h->p<int32_t>(h->o_gcnt), h->p<int32_t>(h->o_goff),
+                    int32_t* order_out, int32_t* count_out, cudaStream_t st, int skip_leaf_pairs) {
+  return launch_group_order(lsrc, rsrc, active, skip_leaf_pairs, K, h->p<unsigned long long>(h->o_gtab), h->p<int32_t>(h->o_gcnt), h->p<int32_t>(h->o_goff),
                             h->p<int32_t>(h->o_gslot), h->p<int32_t>(h->o_grank), order_out, count_out, h->p<char>(h->o_sort_temp),
                             h->sort_temp, st);
 }
@@ -923,8 +923,9 @@ int decide_modes(vcsmc_sweep* h, int64_t tables, int64_t ws_bytes, bool report) 
   int64_t P = (avail - 8192) / (node_bytes + 8);
   const int64_t Pmax = (int64_t)(N - 1) * K;
   if (P > Pmax) P = Pmax;
-  if (P < 2 * K) {
-    if (report) set_error("workspace too small: GC pool would hold %lld slots, need >= %lld", (long long)P, (long long)(2 * K));
+  const int64_t P_need = 2 * K < Pmax ? 2 * K : Pmax;   // (a one-event sweep never holds more than its K nodes)
+  if (P < P_need) {
+    if (report) set_error("workspace too small: GC pool would hold %lld slots, need >= %lld", (long long)P, (long long)P_need);
     return VCSMC_ERR_ARG;
   }
   h->pool_slots = P;

@@ -48,7 +48,7 @@ struct WeightArgs {
 };
 
 int group_particles(vcsmc_sweep* h, const int32_t* lsrc, const int32_t* rsrc, const int32_t* active, int64_t K,
-                    int32_t* order_out, int32_t* count_out, cudaStream_t st);
+                    int32_t* order_out, int32_t* count_out, cudaStream_t st, int skip_leaf_pairs = 0);
 int launch_leaf_ell(const uint8_t* codes, int64_t stride, int N, int S, const double* pi, double* ell_node, cudaStream_t st);
 int launch_step_weights(const WeightArgs& w, cudaStream_t st);
 int launch_finalize(int N, int64_t K, const double* stats, const double* LL_last, const double* b_l, const double* b_r,

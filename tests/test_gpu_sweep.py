@@ -257,6 +257,24 @@ def test_single_site_batch(ops, primate_genome):
     compare_grads(grads, g_ref, True)
 
 
+@pytest.mark.parametrize("lazy", [True, False])
+@pytest.mark.parametrize("N,S,K", [(2, 40, 7), (3, 1, 5), (5, 513, 33), (4, 1025, 1)])
+def test_sweep_odd_shapes(ops, N, S, K, lazy):
+    """Smallest trees (one rank event), particle counts that are not a multiple of a warp, site counts around tile edges."""
+    g = synthetic_genome(N, S, seed=N + S, gaps=0.1)
+    for jc in (True, False):
+        p = random_params(N, jc, seed=K)
+        U = O.Uniforms.draw(N, K, seed=S)
+        res, g_ref = oracle_param_grads(g, K, p, U)
+        out, grads, _ = run_gpu(ops, g, K, p, U, jc, lazy=lazy)
+        compare_forward(out, res, N, K)
+        compare_grads(grads, g_ref, jc)
+        if lazy:   # and again on the replayed graph
+            out, grads, _ = run_gpu(ops, g, K, p, U, jc, lazy=lazy, force_gc=True, workspace_bytes=64 << 20)
+            compare_forward(out, res, N, K)
+            compare_grads(grads, g_ref, jc)
+
+
 def test_autograd_through_parameterisation(ops, primate_genome):
     """sweep_elbo under torch autograd reproduces the oracle's gradients w.r.t. the reference's four variables."""
     g = primate_genome[:7, :200]
