@@ -373,27 +373,44 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
       const bool renorm = ((t - t_begin) & 127) == 127;
       score_tile<JC, SPT>(cs, nj, skip, sbase, renorm, pi, s_a, s_b, sC, my_prod, my_exp);
     }
-    // one log per (thread, particle): sum_s log x_s = log(prod mantissas) + ln2 * sum (exponents - bias)
+    // sum_s log x_s = log(prod mantissas) + ln2 * sum (exponents - bias).  The 256 per-thread products of a particle are
+    // combined by ONE warp (8 entries per lane, renormalised after every multiply) before the log: 32 logs per particle
+    // instead of 256.
     const int bias = 1023 * SPT * (t_end - t_begin);
-    unsigned odd_mask = 0u;
-    for (int j = 0; j < nj; ++j) {
-      const double pr = my_prod[j * kTileThreads];
-      if (pr != pr) odd_mask |= 1u << j;
+    __syncthreads();
+    for (int j = wid; j < nj; j += kWarps) {
+      if (skip >> j & 1u) continue;  // written by score_leaf_pairs_kernel / merge_score_mma_kernel
+      double p = 1.0;
+      int e = 0;
+#pragma unroll
+      for (int i = 0; i < kTileThreads / 32; ++i) {
+        p *= s_prod[j * kTileThreads + lane + 32 * i];
+        e += s_exp[j * kTileThreads + lane + 32 * i] - bias;
+        const int hi = __double2hiint(p);
+        const int ee = (hi >> 20) & 0x7ff;
+        if (ee != 0x7ff) {   // (a poisoned product stays NaN)
+          p = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(p));
+          e += ee - 1023;
+        }
+      }
+      const double ef = (double)e;
+      double acc = fma(ef, 6.93147180369123816490e-01, fma(ef, 1.90821492927058770002e-10, log(p)));  // ln2 hi + lo
+      acc = warp_sum(acc);
+      if (__any_sync(0xffffffffu, p != p)) {
+        if (lane == 0) atomicOr(&s_odd, 1u << j);
+      } else if (lane < kWarps) {
+        const int kk = s_k[j];
+        const int64_t k = kk < 0 ? ~kk : kk;
+        a.ell_part[(k * a.n_chunks + tc) * kWarps + lane] = lane == 0 ? acc : 0.0;
+      }
     }
-    if (odd_mask) atomicOr(&s_odd, odd_mask);
     __syncthreads();
     const unsigned odd_all = s_odd;
-    for (int j = 0; j < nj; ++j) {
-      if (skip >> j & 1u) continue;  // written by score_leaf_pairs_kernel / merge_score_mma_kernel
-      double acc;
-      if (odd_all >> j & 1u) {
-        // some likelihood of this particle is 0 / subnormal / not finite: one log per site, like the reference
-        acc = score_slow<JC>(cs, s_a[j], s_b[j], sC + j * kCoef, t_begin * (kTileThreads * SPT),
-                             min(a.n_sites, t_end * (kTileThreads * SPT)), pi[0], pi[1], pi[2], pi[3]);
-      } else {
-        const double ex = (double)(my_exp[j * kTileThreads] - bias);
-        acc = fma(ex, 6.93147180369123816490e-01, fma(ex, 1.90821492927058770002e-10, log(my_prod[j * kTileThreads])));  // ln2 hi + lo
-      }
+    for (int j = 0; odd_all && j < nj; ++j) {
+      if (!(odd_all >> j & 1u)) continue;
+      // some likelihood of this particle is 0 / subnormal / not finite: one log per site, like the reference
+      double acc = score_slow<JC>(cs, s_a[j], s_b[j], sC + j * kCoef, t_begin * (kTileThreads * SPT),
+                                  min(a.n_sites, t_end * (kTileThreads * SPT)), pi[0], pi[1], pi[2], pi[3]);
       acc = warp_sum(acc);
       if (lane == 0) {
         const int kk = s_k[j];
