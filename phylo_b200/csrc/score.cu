@@ -744,7 +744,7 @@ __global__ void __launch_bounds__(256) score_leaf_pairs_kernel(const int32_t* __
   for (int t = 1 + lane; t < n_parts; t += 32) ell_part[k * n_parts + t] = 0.0;
 }
 
-constexpr int64_t kScoreItems = 148 * 8;  // work items wanted per launch
+constexpr int64_t kScoreItems = 148 * 32;  // work items wanted per launch (measured: 592 .. 18,944; work per item is uneven)
 
 }  // namespace
 
@@ -787,13 +787,19 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
   }
   a.skip_octets = (!jc && spt == 2 && use_mma) ? 1 : 0;
   a.tiles = (n_sites + kTileThreads * spt - 1) / (kTileThreads * spt);
+  static int64_t items = 0;
+  if (items == 0) {
+    const char* e = getenv("VCSMC_SCORE_ITEMS");   // tuning knob: work items wanted per launch
+    items = e ? atoll(e) : kScoreItems;
+    if (items < 1) items = kScoreItems;
+  }
   // groups as large as the machine fill allows (shared children and site products are amortised over the group)
-  int64_t R = (K * a.tiles) / kScoreItems;
+  int64_t R = (K * a.tiles) / items;
   if (R < 1) R = 1;
   if (R > kRScore) R = kRScore;
   a.R = (int)R;
   const int64_t groups = (K + R - 1) / R;
-  int64_t nc = (kScoreItems + groups - 1) / groups;  // split a group's tiles only when the groups cannot fill the SMs
+  int64_t nc = (items + groups - 1) / groups;  // split a group's tiles only when the groups cannot fill the SMs
   if (nc < 1) nc = 1;
   if (nc > a.tiles) nc = a.tiles;
   a.tiles_per_item = (int)((a.tiles + nc - 1) / nc);
