@@ -78,13 +78,13 @@ int launch_nested_choose(int r, int n, int N, int M, int gc, int64_t K, double* 
                          const int32_t* cnt, const int32_t* slot, int32_t* ids_new, int32_t* cnt_new, int32_t* slot_new,
                          int32_t* lref, int32_t* rref, int32_t* nleaf, uint8_t* rempos, int32_t* choice, double* b_l,
                          double* b_r, double* t2, double* qlog, int32_t* lsrc, int32_t* rsrc, int32_t* dst, cudaStream_t st);
-int launch_nested_active(int r, int64_t K, int skip_zero, const double* lw, const double* stats, int32_t* active, cudaStream_t st);
+int launch_nested_active(int r, int64_t K, int skip_zero, double rel, const double* lw, const double* stats, int32_t* active, cudaStream_t st);
 int launch_nested_mark_roots(int n, int N, int64_t K, const int32_t* active, const int32_t* rows, int32_t* consumed, cudaStream_t st);
 int launch_nested_coef(int r, int n, int N, int M, int64_t K, double grad, const double* lw, const double* stats,
                        const double* pot, const int32_t* choice, const int32_t* anc, double* Dacc_next, cudaStream_t st);
-int launch_nested_keep(int r, int n, int M, int64_t K, double grad, int dense, const double* lw, const double* stats,
+int launch_nested_keep(int r, int n, int M, int64_t K, double grad, int dense, double thresh, const double* lw, const double* stats,
                        const double* pot, const int32_t* choice, int32_t* keep, cudaStream_t st);
-int launch_nested_virtual(int r, int n, int N, int M, int64_t K, double grad, int dense, const double* lw, const double* stats,
+int launch_nested_virtual(int r, int n, int N, int M, int64_t K, double grad, int dense, double thresh, const double* lw, const double* stats,
                           const double* pot, const int32_t* choice, const int32_t* index, const int32_t* rows,
                           const int32_t* slot_of, const double* u_bl, const double* u_br, uint64_t seed, const double* lam_l,
                           const double* lam_r, int64_t v0, int64_t v1, int32_t* v_lsrc, int32_t* v_rsrc, double* v_coef,

@@ -538,7 +538,7 @@ struct RecArgs {
 
 // Cross-GPU barrier without the host: lane g stores this rank's epoch into peer g's flag array (peer store over
 // NVLink, system scope) and then spins until peer g's epoch has arrived in this rank's own array.  Every GPU runs
-// its own stream, so the store a lane waits for never depends on this kernel.  A timeout (~4 s) turns a lost peer
+// its own stream, so the store a lane waits for never depends on this kernel.  A timeout (~30 s) turns a lost peer
 // into a reported error instead of a hang.
 struct SigArgs {
   int32_t* peer_sig[kMaxPeers];  // peer g's flag array (own array at index rank)
@@ -558,7 +558,7 @@ __global__ void lz_barrier_kernel(const SigArgs a) {
   volatile int32_t* in = a.peer_sig[a.rank] + g;
   const long long t0 = clock64();
   while (*in - epoch < 0) {
-    if (clock64() - t0 > 8000000000ll) {
+    if (clock64() - t0 > 60000000000ll) {   // ~30 s at 1.9 GHz
       a.status[0] = VCSMC_ERR_STATE;
       break;
     }

@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(256) nested_choose_kernel(const ChooseArgs a) 
 // node coefficients of the roots.
 // ---------------------------------------------------------------------------------------------
 struct VirtArgs {
+  double thresh;
   int r, n, N, M;
   int64_t K;
   double grad;
@@ -394,13 +395,14 @@ struct VirtArgs {
 };
 
 __device__ __forceinline__ double kappa_of(const double* lw, const double* stats, const double* pot, const int32_t* choice,
-                                           int r, int64_t k, int combos, int c, double grad) {
+                                           int r, int64_t k, int combos, int c, double grad, double thresh) {
   const double W = exp(lw[k] - stats[r * 4]) * grad;
-  return W * (exp(pot[k * combos + c]) - (c == choice[k] ? 1.0 : 0.0));
+  const double kappa = W * (exp(pot[k * combos + c]) - (c == choice[k] ? 1.0 : 0.0));
+  return fabs(kappa) <= thresh ? 0.0 : kappa;   // thresh = skip_below * |dELBO| (0: exact zeros only)
 }
 
 // keep[k*combos + c] = 1 when the virtual event has to be visited (exact-zero adjoints are dropped unless dense)
-__global__ void nested_keep_kernel(int r, int n, int M, int64_t K, double grad, int dense, const double* __restrict__ lw,
+__global__ void nested_keep_kernel(int r, int n, int M, int64_t K, double grad, int dense, double thresh, const double* __restrict__ lw,
                                    const double* __restrict__ stats, const double* __restrict__ pot,
                                    const int32_t* __restrict__ choice, int32_t* __restrict__ keep) {
   const int combos = n * (n - 1) / 2 * M;
@@ -408,7 +410,7 @@ __global__ void nested_keep_kernel(int r, int n, int M, int64_t K, double grad, 
   if (i >= K * combos) return;
   const int64_t k = i / combos;
   const int c = (int)(i - k * combos);
-  keep[i] = dense ? 1 : (kappa_of(lw, stats, pot, choice, r, k, combos, c, grad) != 0.0);
+  keep[i] = dense ? 1 : (kappa_of(lw, stats, pot, choice, r, k, combos, c, grad, thresh) != 0.0);
 }
 
 __global__ void nested_virtual_kernel(const VirtArgs a) {
@@ -417,7 +419,7 @@ __global__ void nested_virtual_kernel(const VirtArgs a) {
   if (i >= a.K * combos) return;
   const int64_t k = i / combos;
   const int c = (int)(i - k * combos);
-  const double kappa = kappa_of(a.lw, a.stats, a.pot, a.choice, a.r, k, combos, c, a.grad);
+  const double kappa = kappa_of(a.lw, a.stats, a.pot, a.choice, a.r, k, combos, c, a.grad, a.dense ? 0.0 : a.thresh);
   if (!a.dense && kappa == 0.0) return;
   const int64_t v = a.index[i];
   if (v < a.v0 || v >= a.v1) return;
@@ -455,11 +457,11 @@ __global__ void nested_coef_kernel(int r, int n, int N, int M, int64_t K, double
   atomicAdd(Dacc_next + A * N + r2, -kappa);
 }
 
-__global__ void nested_active_kernel(int r, int64_t K, int skip_zero, const double* __restrict__ lw,
+__global__ void nested_active_kernel(int r, int64_t K, int skip_zero, double rel, const double* __restrict__ lw,
                                      const double* __restrict__ stats, int32_t* __restrict__ active) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
-  active[k] = skip_zero ? (exp(lw[k] - stats[r * 4]) != 0.0) : 1;
+  active[k] = skip_zero ? (exp(lw[k] - stats[r * 4]) > rel) : 1;   // |kappa| <= W: below the threshold nothing is kept
 }
 
 // roots of the active particles must be materialised (and own adjoint slots) in the reverse sweep
@@ -552,8 +554,8 @@ int launch_nested_choose(int r, int n, int N, int M, int gc, int64_t K, double* 
   return VCSMC_OK;
 }
 
-int launch_nested_active(int r, int64_t K, int skip_zero, const double* lw, const double* stats, int32_t* active, cudaStream_t st) {
-  nested_active_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(r, K, skip_zero, lw, stats, active);
+int launch_nested_active(int r, int64_t K, int skip_zero, double rel, const double* lw, const double* stats, int32_t* active, cudaStream_t st) {
+  nested_active_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(r, K, skip_zero, rel, lw, stats, active);
   VCSMC_LAUNCH_CHECK("nested_active_kernel");
   return VCSMC_OK;
 }
@@ -572,20 +574,20 @@ int launch_nested_coef(int r, int n, int N, int M, int64_t K, double grad, const
   return VCSMC_OK;
 }
 
-int launch_nested_keep(int r, int n, int M, int64_t K, double grad, int dense, const double* lw, const double* stats,
+int launch_nested_keep(int r, int n, int M, int64_t K, double grad, int dense, double thresh, const double* lw, const double* stats,
                        const double* pot, const int32_t* choice, int32_t* keep, cudaStream_t st) {
   const int64_t total = K * (int64_t)(n * (n - 1) / 2 * M);
-  nested_keep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r, n, M, K, grad, dense, lw, stats, pot, choice, keep);
+  nested_keep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(r, n, M, K, grad, dense, thresh, lw, stats, pot, choice, keep);
   VCSMC_LAUNCH_CHECK("nested_keep_kernel");
   return VCSMC_OK;
 }
 
-int launch_nested_virtual(int r, int n, int N, int M, int64_t K, double grad, int dense, const double* lw, const double* stats,
+int launch_nested_virtual(int r, int n, int N, int M, int64_t K, double grad, int dense, double thresh, const double* lw, const double* stats,
                           const double* pot, const int32_t* choice, const int32_t* index, const int32_t* rows,
                           const int32_t* slot_of, const double* u_bl, const double* u_br, uint64_t seed, const double* lam_l,
                           const double* lam_r, int64_t v0, int64_t v1, int32_t* v_lsrc, int32_t* v_rsrc, double* v_coef,
                           double* v_t2, cudaStream_t st) {
-  VirtArgs a{r, n, N, M, K, grad, dense, lw, stats, pot, choice, index, rows, slot_of, u_bl, u_br, seed, lam_l, lam_r,
+  VirtArgs a{thresh, r, n, N, M, K, grad, dense, lw, stats, pot, choice, index, rows, slot_of, u_bl, u_br, seed, lam_l, lam_r,
              v0, v1, v_lsrc, v_rsrc, v_coef, v_t2};
   const int64_t total = K * (int64_t)(n * (n - 1) / 2 * M);
   nested_virtual_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);

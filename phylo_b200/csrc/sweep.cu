@@ -1306,11 +1306,11 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     for (int r = 0; r < N - 1; ++r) {
       const int n = N - r;
       const int64_t tot = K * (int64_t)(n * (n - 1) / 2) * h->M;
-      rc = launch_nested_active(r, K, h->skip_zero, h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats), h->p<int32_t>(h->o_nact), st);
+      rc = launch_nested_active(r, K, h->skip_zero, h->skip_below, h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats), h->p<int32_t>(h->o_nact), st);
       if (rc) return rc;
       rc = launch_nested_mark_roots(n, N, K, h->p<int32_t>(h->o_nact), h->p<int32_t>(h->o_rows_all) + (int64_t)r * K * N, h->p<int32_t>(h->o_consumed), st);
       if (rc) return rc;
-      rc = launch_nested_keep(r, n, h->M, K, grad_elbo, !h->skip_zero, h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats),
+      rc = launch_nested_keep(r, n, h->M, K, grad_elbo, !h->skip_zero, h->skip_below * fabs(grad_elbo), h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats),
                               h->p<double>(h->o_pot) + h->pot_off[r], h->p<int32_t>(h->o_choice) + (int64_t)r * K, h->p<int32_t>(h->o_v_keep), st);
       if (rc) return rc;
       rc = launch_exclusive_scan_i32(h->p<int32_t>(h->o_v_keep), h->p<int32_t>(h->o_v_index), tot, h->p<char>(h->o_v_scan), h->v_scan, st);
@@ -1517,7 +1517,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
         const int n = N - r;
         const int64_t tot = K * (int64_t)(n * (n - 1) / 2) * h->M;
         const int64_t V = n_act[r];
-        rc = launch_nested_keep(r, n, h->M, K, grad_elbo, !h->skip_zero, h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats),
+        rc = launch_nested_keep(r, n, h->M, K, grad_elbo, !h->skip_zero, h->skip_below * fabs(grad_elbo), h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats),
                                 h->p<double>(h->o_pot) + h->pot_off[r], h->p<int32_t>(h->o_choice) + (int64_t)r * K, h->p<int32_t>(h->o_v_keep), st);
         if (rc) return rc;
         rc = launch_exclusive_scan_i32(h->p<int32_t>(h->o_v_keep), h->p<int32_t>(h->o_v_index), tot, h->p<char>(h->o_v_scan), h->v_scan, st);
@@ -1530,7 +1530,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
         }
         for (int64_t v0 = 0; v0 < V; v0 += h->v_batch) {
           const int64_t Vb = (V - v0 < h->v_batch) ? V - v0 : h->v_batch;
-          rc = launch_nested_virtual(r, n, N, h->M, K, grad_elbo, !h->skip_zero, h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats),
+          rc = launch_nested_virtual(r, n, N, h->M, K, grad_elbo, !h->skip_zero, h->skip_below * fabs(grad_elbo), h->p<double>(h->o_lw) + (int64_t)r * K, h->p<double>(h->o_stats),
                                      h->p<double>(h->o_pot) + h->pot_off[r], h->p<int32_t>(h->o_choice) + (int64_t)r * K,
                                      h->p<int32_t>(h->o_v_index), h->p<int32_t>(h->o_rows_all) + (int64_t)r * K * N,
                                      slot_of, lk_bl, lk_br, h->seed, h->lam_l, h->lam_r, v0, v0 + Vb, h->p<int32_t>(h->o_v_lsrc),
