@@ -7,10 +7,13 @@
 //   merge_score_kernel   ell[k] = sum_s log(pi . ((L_l P_l) * (L_r P_r))[s]) for EVERY particle, nothing stored.
 //                        The site likelihood is a bilinear form of the two children,
 //                            x[s] = sum_{j,m} L_a[s][j] L_b[s][m] M_k[j][m],   M_k[j][m] = sum_i pi_i P_a[j][i] P_b[m][i],
-//                        so a group of particles that share a child pair (a, b) shares the 16 site products
+//                        so a run of particles that share a child pair (a, b) shares the 16 site products
 //                        O[s] = L_a[s] (x) L_b[s] (registers) and each particle costs 16 DFMA per site (general Q) or
-//                        4 DFMA (JC: x = a1 sa sb + a2 sa pb + a3 pa sb + a4 pab) instead of ~41.  FP64-pipe bound,
-//                        children come from L2.
+//                        4 DFMA (JC: x = a1 sa sb + a2 sa pb + a3 pa sb + a4 pab) instead of ~41; when child a is a
+//                        leaf with one-hot / all-ones masks it is row `state` of M dotted with L_b (4 DFMA).
+//                        Children come from L2; bound by instruction issue around the FP64 pipe.
+//   score_leaf_pairs_kernel  particles whose children are both leaves: site patterns instead of sites.
+//   merge_score_mma_kernel   experiment: the same GEMM on the FP64 tensor cores (off by default, see the launcher).
 //   materialise_kernel   after the next resampling, only particles that were drawn as an ancestor get their node
 //                        written (the plain merge formula; 32 B per site, streaming).
 //   pull_kernel          particle sharding: a rank that drew a remote ancestor copies the nodes it lacks straight out

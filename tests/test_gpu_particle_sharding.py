@@ -28,6 +28,9 @@ def _case(name):
     if name == "flat":        # few sites: flat weights, hundreds of survivors, many nodes pulled per event
         g = synthetic_genome(9, 5, seed=3, gaps=0.1)
         return g, 128
+    if name == "flat_large":  # thousands of survivors per event: long fetch lists, every rank pulls from every rank
+        g = synthetic_genome(6, 7, seed=12, gaps=0.1)
+        return g, 4096
     raise KeyError(name)
 
 
@@ -123,6 +126,18 @@ def test_particle_sharding_matches_oracle(world, jc, name):
     for o in outs[1:]:
         assert o["elbo"] == outs[0]["elbo"]
         np.testing.assert_array_equal(o["log_weights"], outs[0]["log_weights"])
+
+
+def test_particle_sharding_many_pulls():
+    res, g_ref, N, K = _oracle(False, "flat_large")
+    assert len(np.unique(res.ancestors[3])) > 1000
+    outs = _run(4, False, "flat_large", 29760)
+    for o in outs:
+        np.testing.assert_array_equal(o["ancestors"][1:], res.ancestors[1:])
+        np.testing.assert_allclose(o["log_weights"], res.log_weights.detach().numpy(), rtol=RTOL)
+        assert o["elbo"] == pytest.approx(float(res.elbo), rel=RTOL)
+        np.testing.assert_allclose(o["grads"], g_ref, rtol=1e-7, atol=1e-9 * np.abs(g_ref).max())
+        assert o["info"]["peak_pool_slots"] > 500
 
 
 def test_particle_sharding_seeded_equals_single_gpu():

@@ -223,6 +223,39 @@ def test_repeated_forward_replays_a_cuda_graph(ops, primate_genome, jc, force_gc
                 np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-12 * np.abs(b).max())
 
 
+@pytest.mark.parametrize("jc", [True, False])
+def test_lazy_equals_eager_at_scale(ops, primate_genome, jc):
+    """K = 8192 on primate.p (too large for the CPU oracle): the lazy schedule -- grouped scoring with 32-particle groups
+    and several site chunks, leaf pairs from site patterns, leaf rows, survivors only, graph replay, thresholded reverse
+    sweep -- against the eager schedule with the dense reverse sweep, same seed."""
+    g = primate_genome
+    N, S, K = g.shape[0], g.shape[1], 8192
+    p = random_params(N, jc, seed=4)
+    lam_l, lam_r, Q, pi = O.model_from_params(p)
+    codes = ops.pack_alignment(dev(g))
+    args = (codes, dev(lam_l), dev(lam_r), None if jc else dev(Q), dev(pi.reshape(-1)))
+
+    def run(lazy, reps):
+        sw = ops.Sweep(N, S, K, jc)
+        sw.set_option("lazy", 1.0 if lazy else 0.0)
+        sw.set_option("skip_zero", 1.0 if lazy else 0.0)
+        sw.set_seed(77)
+        for _ in range(reps):
+            elbo = float(sw.forward(*args).item())
+            grads = [None if t is None else t.cpu().numpy() for t in sw.backward(1.0)]
+        sw.check_status()
+        return elbo, sw.output("ancestors").cpu().numpy().copy(), sw.output("log_weights").cpu().numpy().copy(), grads
+
+    e0, a0, w0, g0 = run(False, 1)
+    e1, a1, w1, g1 = run(True, 3)      # the third forward replays the captured graph
+    assert e1 == pytest.approx(e0, rel=1e-12)
+    np.testing.assert_array_equal(a1[1:], a0[1:])
+    np.testing.assert_allclose(w1, w0, rtol=1e-10)
+    for a, b in zip(g1, g0):
+        if a is not None:
+            np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-10 * np.abs(b).max())
+
+
 def test_sweep_pool_exhaustion_is_reported(ops):
     """Flat weights keep many nodes alive; a 2K-slot pool must fail loudly, not silently corrupt."""
     from phylo_b200._lib import VcsmcError
