@@ -1,6 +1,7 @@
 // extern "C" surface of libvcsmc_b200 (kernel-level entry points) + error plumbing.  See include/vcsmc_b200.h.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -18,6 +19,14 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+bool debug_sync() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("VCSMC_SYNC_CHECK");
+    on = (e && e[0] == '1') ? 1 : 0;
+  }
+  return on == 1;
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 int check_cuda(cudaError_t e, const char* what) {

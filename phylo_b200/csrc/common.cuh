@@ -18,11 +18,16 @@ int check_cuda(cudaError_t e, const char* what);
     int _rc = ::vcsmc::check_cuda((call), #call);         \
     if (_rc != 0) return _rc;                             \
   } while (0)
+bool debug_sync();  // VCSMC_SYNC_CHECK=1: synchronise after every launch so that a faulting kernel is named (debugging aid)
 #define VCSMC_LAUNCH_CHECK(name)                          \
   do {                                                    \
     ::vcsmc::count_launch();                              \
     int _rc = ::vcsmc::check_cuda(cudaGetLastError(), name); \
     if (_rc != 0) return _rc;                             \
+    if (::vcsmc::debug_sync()) {                          \
+      _rc = ::vcsmc::check_cuda(cudaDeviceSynchronize(), name); \
+      if (_rc != 0) return _rc;                           \
+    }                                                     \
   } while (0)
 
 constexpr int kMaxPeers = 8;         // ranks of one NVLink domain a sweep can address (particle sharding)

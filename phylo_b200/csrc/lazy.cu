@@ -19,6 +19,7 @@
 //      the tables every rank needs for the next CDF, for the outputs, and for the reverse sweep.
 // The reverse sweep is sharded by SITE on the gathered tables (sweep.cu, options site_begin/site_end): the gradient is
 // a sum over sites and the recompute backward needs nothing but those tables.
+#include <stdlib.h>
 #include <string.h>
 
 #include "sweep_state.h"
@@ -815,7 +816,7 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     rc = launch_transition_fwd(Q, row_t2 + 2 * k0, 2 * Kl, h->jc, P, st);
     if (rc) return rc;
     if (sorted) {
-      rc = group_particles(h, lsrc, rsrc, nullptr, Kl, h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count), st, leaf_hist != nullptr);
+      rc = group_particles(h, lsrc, rsrc, nullptr, Kl, h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count), st, leaf_hist != nullptr && !getenv("VCSMC_DEBUG_KEEP_LEAFPAIRS"));
       if (rc) return rc;
     }
     int tiles = 0;

@@ -101,10 +101,11 @@ int launch_group_order(const int32_t* lsrc, const int32_t* rsrc, const int32_t* 
   const int64_t T = group_table_entries(K);
   int log2T = 0;
   while (((int64_t)1 << log2T) < T) ++log2T;
-  // tab [T] u64 and cnt [T] i32 are carved back to back: one memset; count_out doubles as the range cursor
-  VCSMC_CUDA(cudaMemsetAsync(tab, 0, (size_t)T * (sizeof(unsigned long long) + sizeof(int32_t)), st));
-  VCSMC_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int32_t), st));
-  count_launch(2);
+  // (T depends on the K of THIS call -- a rank's share under particle sharding -- not on how the buffers were carved)
+  VCSMC_CUDA(cudaMemsetAsync(tab, 0, (size_t)T * sizeof(unsigned long long), st));
+  VCSMC_CUDA(cudaMemsetAsync(cnt, 0, (size_t)T * sizeof(int32_t), st));
+  VCSMC_CUDA(cudaMemsetAsync(count_out, 0, sizeof(int32_t), st));   // doubles as the range cursor
+  count_launch(3);
   group_insert_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(lsrc, rsrc, active, skip_leaf_pairs, K, log2T, tab, cnt, gslot, grank);
   VCSMC_LAUNCH_CHECK("group_insert_kernel");
   group_offsets_kernel<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(T, cnt, off, count_out);
