@@ -816,7 +816,7 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     rc = launch_transition_fwd(Q, row_t2 + 2 * k0, 2 * Kl, h->jc, P, st);
     if (rc) return rc;
     if (sorted) {
-      rc = group_particles(h, lsrc, rsrc, nullptr, Kl, h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count), st, leaf_hist != nullptr && !getenv("VCSMC_DEBUG_KEEP_LEAFPAIRS"));
+      rc = group_particles(h, lsrc, rsrc, nullptr, Kl, h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count), st, leaf_hist != nullptr);
       if (rc) return rc;
     }
     int tiles = 0;

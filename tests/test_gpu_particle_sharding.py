@@ -31,6 +31,9 @@ def _case(name):
     if name == "flat_large":  # thousands of survivors per event: long fetch lists, every rank pulls from every rank
         g = synthetic_genome(6, 7, seed=12, gaps=0.1)
         return g, 4096
+    if name == "flat_grouped":  # K/G large enough for the grouped visiting order of the scoring kernel (regression)
+        g = synthetic_genome(6, 7, seed=12, gaps=0.1)
+        return g, 32768
     raise KeyError(name)
 
 
