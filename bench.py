@@ -50,7 +50,7 @@ FP64_OPS_SCORE = {"gtr": (18.0, 6.0, 0.0), "jc": (6.0, 6.0, 0.0)}
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="native", choices=["native", "reference"])
     p.add_argument("--taxa", type=int, default=64)
