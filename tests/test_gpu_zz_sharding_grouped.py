@@ -17,3 +17,30 @@ def test_particle_sharding_grouped_order():
         np.testing.assert_allclose(o["log_weights"], res.log_weights.detach().numpy(), rtol=RTOL)
         assert o["elbo"] == pytest.approx(float(res.elbo), rel=RTOL)
         np.testing.assert_allclose(o["grads"], g_ref, rtol=1e-7, atol=1e-9 * np.abs(g_ref).max())
+
+
+def test_seeded_sweep_with_more_than_64_taxa():
+    """N = 70: forest rows no longer fit two entries per lane (the proposal kernel's 8-entries-per-lane instantiation,
+    two Philox blocks per lane, a 256-key bitonic sort); seeded mode against the oracle fed the same Philox uniforms."""
+    import torch
+    from oracle import vcsmc_oracle as O
+    from phylo_b200 import ops
+    from vcsmc_test_helpers import synthetic_genome
+    N, S, K, seed = 70, 24, 12, 424242
+    g = synthetic_genome(N, S, seed=9, gaps=0.05)
+    p = O.Params.init(N, False)
+    pair, bl, br, rs = [], [], [], []
+    for r in range(N - 1):
+        a, b, c, d = ops.philox_step_uniforms(seed, r, 0, K, N - r)
+        pair.append(a.cpu().numpy()); bl.append(b.cpu().numpy()); br.append(c.cpu().numpy()); rs.append(d.cpu().numpy())
+    U = O.Uniforms(pair, np.stack(bl), np.stack(br), np.stack(rs))
+    lam_l, lam_r, Q, pi = O.model_from_params(p)
+    res = O.sweep(g, K, lam_l, lam_r, Q, pi, U)
+    dev = lambda x: torch.as_tensor(x).cuda().contiguous()
+    sw = ops.Sweep(N, S, K, False, keep_for_backward=False)
+    sw.set_seed(seed)
+    for _ in range(2):   # the second forward replays the captured graph
+        elbo = sw.forward(ops.pack_alignment(dev(g)), dev(lam_l), dev(lam_r), dev(Q), dev(pi.reshape(-1)))
+        assert float(elbo) == pytest.approx(float(res.elbo), rel=RTOL)
+        np.testing.assert_array_equal(sw.output("ancestors").cpu().numpy()[1:], res.ancestors[1:])
+        np.testing.assert_allclose(sw.output("log_weights").cpu().numpy(), res.log_weights.detach().numpy(), rtol=RTOL)
