@@ -55,3 +55,46 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("# oracle", ""), f
+
+
+def test_sweep_object_argument_checks_without_a_gpu():
+    """Creating a sweep only carves a layout (no CUDA call that must succeed): the argument checks of the particle-
+    sharding entry points and of the option table can be exercised on a CPU-only machine."""
+    import ctypes as C
+    from phylo_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.SweepConfig(8, 100, 64, 0, 1, 0, 0, 0)
+    sizes = _lib.SweepSizes()
+    assert lib.vcsmc_sweep_query(C.byref(cfg), C.byref(sizes)) == 0
+    cfg.workspace_bytes = sizes.retain_bytes
+    h = C.c_void_p()
+    fake_ws = C.c_void_p(1 << 20)          # never dereferenced on the host
+    assert lib.vcsmc_sweep_create(C.byref(cfg), fake_ws, C.byref(h)) == 0
+    try:
+        peers = (C.c_void_p * 8)(*([1 << 20] * 8))
+        hook = _lib.COMM_FN(lambda *a: 0)
+        assert lib.vcsmc_sweep_set_comm(h, 0, 9, hook, None, peers) == _lib.ERR_ARG          # more than 8 ranks
+        assert lib.vcsmc_sweep_set_comm(h, 3, 3, hook, None, peers) == _lib.ERR_ARG          # rank out of range
+        assert lib.vcsmc_sweep_set_comm(h, 0, 3, hook, None, peers) == _lib.ERR_ARG          # 64 particles / 3 ranks
+        assert b"divisible" in lib.vcsmc_last_error()
+        assert lib.vcsmc_sweep_set_comm(h, 0, 2, hook, None, None) == _lib.ERR_ARG           # no peer table
+        assert lib.vcsmc_sweep_set_option(h, b"no_such_option", 1.0) == _lib.ERR_ARG
+        for name in (b"skip_zero", b"skip_below", b"lazy", b"leaf_patterns", b"graph", b"site_begin", b"site_end", b"scalar_share"):
+            assert lib.vcsmc_sweep_set_option(h, name, 1.0) == 0, name
+        assert lib.vcsmc_sweep_output(h, b"no_such_table") is None
+        assert lib.vcsmc_sweep_output(h, b"log_weights") is not None
+        # backward before forward is a state error, not a crash
+        assert lib.vcsmc_sweep_backward(h, 1.0, fake_ws, fake_ws, fake_ws, fake_ws, None) == _lib.ERR_STATE
+    finally:
+        lib.vcsmc_sweep_destroy(h)
+    # the nested proposal cannot be particle-sharded
+    cfg = _lib.SweepConfig(8, 100, 64, 0, 1, 0, 5, 0)
+    assert lib.vcsmc_sweep_query(C.byref(cfg), C.byref(sizes)) == 0
+    cfg.workspace_bytes = sizes.retain_bytes
+    h = C.c_void_p()
+    assert lib.vcsmc_sweep_create(C.byref(cfg), fake_ws, C.byref(h)) == 0
+    try:
+        peers = (C.c_void_p * 8)(*([1 << 20] * 8))
+        assert lib.vcsmc_sweep_set_comm(h, 0, 2, _lib.COMM_FN(lambda *a: 0), None, peers) == _lib.ERR_STATE
+    finally:
+        lib.vcsmc_sweep_destroy(h)
