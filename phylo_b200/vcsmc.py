@@ -75,6 +75,7 @@ class VCSMC:
         self.seed = int(seed if seed is not None else np.random.SeedSequence().entropy % (2 ** 63))
         self._step_counter = 0
         self._sweeps: Dict[tuple, ops.Sweep] = {}
+        self._code_bufs: Dict[int, torch.Tensor] = {}
         dist = _dist()
         self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
         self.sharding = choose_sharding(sharding or os.environ.get("VCSMC_SHARDING"), self.K, self.world, self.nested)
@@ -150,7 +151,14 @@ class VCSMC:
         if site_idx is None and self.sharding != "sites":
             codes = self.codes
         else:
-            codes = ops.gather_sites(self.codes, torch.from_numpy(local).to(self.device))
+            # gathered into a resident buffer per batch length: the sweep sees the same address every step, so its
+            # captured launch graph stays valid across minibatches
+            gathered = ops.gather_sites(self.codes, torch.from_numpy(local).to(self.device))
+            buf = self._code_bufs.get(gathered.shape[1])
+            if buf is None:
+                buf = self._code_bufs[gathered.shape[1]] = torch.empty_like(gathered)
+            buf.copy_(gathered)
+            codes = buf
         sw = self._sweep_for(len(local), need_grad)
         if seed is None:
             self._step_counter += 1
