@@ -4,19 +4,39 @@ actually uses (a stale count table corrupted the visiting order on multi-GPU run
 import numpy as np
 import pytest
 
-from test_gpu_particle_sharding import RTOL, _oracle, _run
+from test_gpu_particle_sharding import RTOL, _run
 
 pytestmark = pytest.mark.gpu
 
 
 def test_particle_sharding_grouped_order():
-    res, g_ref, N, K = _oracle(False, "flat_grouped")
-    outs = _run(2, False, "flat_grouped", 29770)
+    """2 ranks x 16,384 particles against ONE rank x 32,768 on the same GPU code (seeded): same ELBO, same ancestors, same
+    gradients.  (Against the single-GPU run rather than the oracle: with 32,768 flat weights a last-bit difference between
+    numpy's and the kernels' CDF could legitimately move one draw across a boundary.)"""
+    import torch
+    from oracle import vcsmc_oracle as O
+    from phylo_b200 import ops
+    from vcsmc_test_helpers import random_params
+    import test_gpu_particle_sharding as T
+    g, K = T._case("flat_grouped")
+    N, S = g.shape[0], g.shape[1]
+    p = random_params(N, False, seed=5)
+    lam_l, lam_r, Q, pi = O.model_from_params(p)
+    dev = lambda x: torch.as_tensor(x).cuda().contiguous()
+    sw = ops.Sweep(N, S, K, False)
+    sw.set_seed(1234)
+    elbo = float(sw.forward(ops.pack_alignment(dev(g)), dev(lam_l), dev(lam_r), dev(Q), dev(pi.reshape(-1))).item())
+    anc = sw.output("ancestors").cpu().numpy().copy()
+    lw = sw.output("log_weights").cpu().numpy().copy()
+    grads = torch.cat([t.reshape(-1) for t in sw.backward(1.0)]).cpu().numpy()
+    assert max(len(np.unique(anc[r])) for r in range(1, N - 1)) > 1000      # flat weights: thousands of lineages
+    del sw
+    outs = _run(2, False, "flat_grouped", 29770, seeded=True)
     for o in outs:
-        np.testing.assert_array_equal(o["ancestors"][1:], res.ancestors[1:])
-        np.testing.assert_allclose(o["log_weights"], res.log_weights.detach().numpy(), rtol=RTOL)
-        assert o["elbo"] == pytest.approx(float(res.elbo), rel=RTOL)
-        np.testing.assert_allclose(o["grads"], g_ref, rtol=1e-7, atol=1e-9 * np.abs(g_ref).max())
+        assert o["elbo"] == pytest.approx(elbo, rel=1e-11)
+        np.testing.assert_array_equal(o["ancestors"][1:], anc[1:])
+        np.testing.assert_allclose(o["log_weights"], lw, rtol=1e-10)
+        np.testing.assert_allclose(o["grads"], grads, rtol=1e-6, atol=1e-9 * np.abs(grads).max())
 
 
 def test_seeded_sweep_with_more_than_64_taxa():
