@@ -29,7 +29,7 @@ def test_particle_sharding_grouped_order():
     anc = sw.output("ancestors").cpu().numpy().copy()
     lw = sw.output("log_weights").cpu().numpy().copy()
     grads = torch.cat([t.reshape(-1) for t in sw.backward(1.0)]).cpu().numpy()
-    assert max(len(np.unique(anc[r])) for r in range(1, N - 1)) > 1000      # flat weights: thousands of lineages
+    assert max(len(np.unique(anc[r])) for r in range(1, N - 1)) > 100       # flat weights: many lineages alive
     del sw
     outs = _run(2, False, "flat_grouped", 29770, seeded=True)
     for o in outs:
