@@ -183,6 +183,8 @@ def run_native(args):
         raise SystemExit("bench.py --impl native needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL prints its version banner (NCCL_DEBUG=VERSION/INFO) to stdout by default: keep stdout for the ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N, S, K = args.taxa, args.sites, args.particles
     jc = args.model == "jc"
