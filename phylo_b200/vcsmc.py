@@ -225,6 +225,16 @@ class VCSMC:
         self.final_trees = np.vectorize(label.get, otypes=[object])(forest[:, 0])
         return np.concatenate(cols, axis=1)
 
+    def newick(self, k: Optional[int] = None, out: Optional[Dict[str, np.ndarray]] = None) -> str:
+        """Newick string (with the sampled branch lengths) of the tree particle slot ``k`` holds after the last sweep;
+        default: the particle with the largest ``log_likelihood_R``.  Rebuilt on the host from the integer tables
+        (phylo_b200/trees.py); the reference only carries '+'-joined label strings (vcsmc.py:306-313)."""
+        from . import trees
+        out = out or self.outputs()
+        if k is None:
+            k = int(np.argmax(out["log_likelihood_R"]))
+        return trees.final_tree_newick(k, self.taxa, out)
+
     # -- training driver (vcsmc.py:453-645) -----------------------------------------------------
     def batch_slices(self, n_sites: int, batch_size: int):
         """vcsmc.py:453-464: a fixed random partition of the sites, drawn once."""
