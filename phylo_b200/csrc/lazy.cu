@@ -275,6 +275,9 @@ __global__ void __launch_bounds__(kProposeWarps * 32) lz_propose_kernel(const Pr
   int32_t* cn = a.cnt_new + kl * N;
   uint8_t* rp = a.rempos + k * (int64_t)(n - 2);
   int lid = 0, rid = 0, cl = 0, cr = 0;   // (valid in lane 0 afterwards)
+  bool tie_row = false;
+  double tie_F = 0.0, tie_topo = 0.0;
+  int tie_vm = 0;
   if (!a.u_pair) {
     // ---- counter-based uniforms: u_i = ((16 random bits) << 8 | i) 2^-24 (philox_step_kernel), so the integer key
     // orders like u, is tie-free, and carries the element's index: ONE warp bitonic sort of the keys gives the kept
@@ -385,6 +388,23 @@ __global__ void __launch_bounds__(kProposeWarps * 32) lz_propose_kernel(const Pr
     rid = first ? c1 : src_ids[c1];
     cl = first ? 1 : src_cnt[c0];
     cr = first ? 1 : src_cnt[c1];
+    // tf.nn.top_k's tie rule can keep a merged subtree and drop another one (duplicate-on-tie quirk, vcsmc.py:304-305),
+    // so the kept set is not "all but the pair": the forest scalars of such a row are summed over the row itself
+    __syncwarp();
+    double fs = 0.0, ts = 0.0;
+    int vs = 0;
+    for (int pos = lane; pos < n - 2; pos += 32) {
+      const int c = cn[pos];
+      fs += a.ell_node[in_[pos]];
+      ts -= a.ldf[2 * max(c, 2) - 3];
+      vs += c - (c == 1);
+    }
+    tie_F = warp_sum(fs);
+    tie_topo = warp_sum(ts);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, o);
+    tie_vm = vs;
+    tie_row = true;
   } else {
     int id0 = -1, ct0 = 0, id1 = -1, ct1 = 0;
 #pragma unroll
@@ -450,9 +470,15 @@ __global__ void __launch_bounds__(kProposeWarps * 32) lz_propose_kernel(const Pr
     a.t2[2 * k] = bl;
     a.t2[2 * k + 1] = br;
     a.ll_tilde[kl] = first ? log(1.0 / (double)a.K) : a.LL_prev[anc];
-    a.F_new[kl] = F_anc - a.ell_node[lid] - a.ell_node[rid];
-    a.topo_new[kl] = topo_anc + a.ldf[2 * max(cl, 2) - 3] + a.ldf[2 * max(cr, 2) - 3] - a.ldf[2 * max(nl, 2) - 3];
-    a.vm_new[kl] = vm_anc - (cl - (cl == 1)) - (cr - (cr == 1)) + nl;
+    if (tie_row) {
+      a.F_new[kl] = tie_F;
+      a.topo_new[kl] = tie_topo - a.ldf[2 * max(nl, 2) - 3];
+      a.vm_new[kl] = tie_vm + nl;
+    } else {
+      a.F_new[kl] = F_anc - a.ell_node[lid] - a.ell_node[rid];
+      a.topo_new[kl] = topo_anc + a.ldf[2 * max(cl, 2) - 3] + a.ldf[2 * max(cr, 2) - 3] - a.ldf[2 * max(nl, 2) - 3];
+      a.vm_new[kl] = vm_anc - (cl - (cl == 1)) - (cr - (cr == 1)) + nl;
+    }
   }
 }
 

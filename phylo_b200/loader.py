@@ -79,22 +79,61 @@ DATASETS = ("primate_data", "corona_data", "hohna_data", "load_strings", "simula
     tuple("hohna_data_%d" % i for i in range(1, 12))
 
 
-def load_dataset(name: str, data_dir: str = "data") -> dict:
+def repair_datadict(d: dict) -> dict:
+    """The betacoronavirus pickles as shipped are not loadable by the reference's class: ``taxa`` is a 1-tuple holding
+    a 16-name list for 17 genome rows (betacorona1.p) and the genome key is misspelt ``gemome`` (betacorona2.p).
+    Returns a well-formed ``{'taxa': [N names], 'genome': [N,S,A]}``."""
+    genome = np.asarray(d["genome"] if "genome" in d else d["gemome"], dtype=np.float64)
+    taxa = d.get("taxa", [])
+    if isinstance(taxa, tuple) and len(taxa) == 1 and isinstance(taxa[0], (list, tuple)):
+        taxa = taxa[0]
+    taxa = [str(t) for t in taxa]
+    for i in range(len(taxa), genome.shape[0]):
+        taxa.append("S" + str(i))
+    return {"taxa": taxa[:genome.shape[0]], "genome": genome}
+
+
+def _corona(data_dir: str) -> dict:
+    """runner.py:159-160 reads data/coronavirus.p as a ready datadict.  That file is not in the reference repository
+    (.MISSING_LARGE_BLOBS); the closest shipped alignment is data/betacoronavirus/betacorona1.p (17 x 3260, 16.5 % gap
+    sites), which is used -- repaired -- when coronavirus.p is absent (a copy of its state masks ships in data/)."""
+    path = os.path.join(data_dir, "coronavirus.p")
+    if os.path.exists(path):
+        return repair_datadict(_read_pickle(path))
+    path = os.path.join(data_dir, "betacoronavirus", "betacorona1.p")
+    if os.path.exists(path):
+        return repair_datadict(_read_pickle(path))
+    path = os.path.join(data_dir, "betacorona1_codes.npz")
+    if os.path.exists(path):
+        codes = np.load(path)["codes"]
+        genome = ((codes[..., None] >> np.arange(4, dtype=np.uint8)) & 1).astype(np.float64)
+        return {"taxa": ["S" + str(i) for i in range(genome.shape[0])], "genome": genome}
+    raise FileNotFoundError(os.path.join(data_dir, "coronavirus.p"))
+
+
+def load_dataset(name: str, data_dir: str = "data", unknown_as_gap: bool = True) -> dict:
     """The ``exec(args.dataset + ' = True')`` switch of runner.py:81,117-184 by name.
 
-    Extra names: ``synthetic_NxS`` (e.g. synthetic_64x10000) for the benchmark shapes.
+    ``unknown_as_gap`` applies to every string dataset alike: characters outside the alphabet dict ('N' in DS7, '.', 'n'
+    in DS10/DS11) become the all-ones mask; with False they raise KeyError like the reference's ``alphabet_dir[ch]``
+    (runner.py:111).  Extra names: ``hohna_data_9`` .. ``_11``, ``fish_data``, ``synthetic_NxS`` (e.g.
+    synthetic_64x10000) for the benchmark shapes.
     """
+    def strings(d, alphabet):
+        return form_dataset_from_strings(list(d.values()), alphabet, unknown_as_gap=unknown_as_gap)
+
     if name in ("hohna_data", "hohna_data_1"):
-        return form_dataset_from_strings(list(_hohna(data_dir, 1).values()), ALPHABET_DIR_BLANK)
+        return strings(_hohna(data_dir, 1), ALPHABET_DIR_BLANK)
     if name.startswith("hohna_data_"):
-        n = int(name.rsplit("_", 1)[1])
-        return form_dataset_from_strings(list(_hohna(data_dir, n).values()), ALPHABET_DIR_BLANK, unknown_as_gap=n > 8)
+        return strings(_hohna(data_dir, int(name.rsplit("_", 1)[1])), ALPHABET_DIR_BLANK)
     if name == "corona_data":
-        return _read_pickle(os.path.join(data_dir, "coronavirus.p"))  # runner.py:159-160: already a datadict
+        return _corona(data_dir)
+    if name == "fish_data":      # data/fish.p (12 x 1047) ships with the reference but has no branch in runner.py
+        return strings(_read_pickle(os.path.join(data_dir, "fish.p")), ALPHABET_DIR_BLANK)
     if name == "primate_data":
-        return form_dataset_from_strings(list(_read_pickle(os.path.join(data_dir, "primate.p")).values()), ALPHABET_DIR_BLANK)
+        return strings(_read_pickle(os.path.join(data_dir, "primate.p")), ALPHABET_DIR_BLANK)
     if name == "primate_data_wang":
-        return form_dataset_from_strings(list(_read_pickle(os.path.join(data_dir, "primates_small.p")).values()), ALPHABET_DIR)
+        return strings(_read_pickle(os.path.join(data_dir, "primates_small.p")), ALPHABET_DIR)
     if name == "simulate_data":
         g = simulateDNA(3, 5)
         return {"taxa": ["S" + str(i) for i in range(g.shape[0])], "genome": g}

@@ -336,6 +336,15 @@ class Sweep:
             off += (cnt + 15) // 16 * 16
         return out
 
+    def rem_row(self, r: int, k: int):
+        """Kept forest positions of ONE particle slot at rank event r (uint8 [N-r-2], host numpy)."""
+        ptr = self._lib.vcsmc_sweep_output(self._h, b"rem_positions")
+        off = ptr - self.workspace.data_ptr()
+        for q in range(r):
+            off += (self.K * (self.N - q - 2) + 15) // 16 * 16
+        m = self.N - r - 2
+        return self.workspace[off + k * m: off + (k + 1) * m].cpu().numpy()
+
     def check_status(self) -> Dict[str, int]:
         """Synchronises; raises if the device-side status word reports an error (e.g. node pool exhausted)."""
         st = self.output("status").cpu().tolist()

@@ -6,7 +6,7 @@
 Same flags and defaults.  ``--twisting`` (README.md:27 / BASELINE.json) is accepted as an alias of ``--nested``
 (runner.py:46-48 only defines --nested).  The reference at HEAD imports a missing module ``vcsmc_jet`` and
 hard-codes ``ginkgo = True`` (runner.py:77,186-206); the working configuration -- ``import vcsmc`` with the
-chosen dataset -- is what this runner means.  Extra flags: --seed, --data_dir, --no_save.
+chosen dataset -- is what this runner means.  Extra flags: --seed, --data_dir, --no_save, --unknown_as_gap.
 """
 from __future__ import annotations
 
@@ -38,6 +38,8 @@ def parse_args(argv=None):
     p.add_argument("--seed", type=int, default=None, help="seed of the counter-based generator (reference: unseeded)")
     p.add_argument("--data_dir", default="data")
     p.add_argument("--no_save", action="store_true")
+    p.add_argument("--unknown_as_gap", default=True, type=_bool,
+                   help="characters outside the alphabet (N in DS7, . n in DS10/11) become all-ones; false: KeyError like the reference")
     args = p.parse_args(argv)
     if args.twisting is not None:
         args.nested = args.twisting
@@ -52,7 +54,7 @@ def main(argv=None):
         torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
         dist.init_process_group("nccl")
     from .loader import load_dataset
-    datadict = load_dataset(args.dataset, args.data_dir)
+    datadict = load_dataset(args.dataset, args.data_dir, unknown_as_gap=args.unknown_as_gap)
     # runner.py:197-206: --nested=true imports vncsmc (same class name); here one class with args.nested
     from . import vcsmc
     model = vcsmc.VCSMC(datadict, K=args.n_particles, args=args, seed=args.seed)

@@ -72,12 +72,19 @@ class VCSMC:
         else:
             self.y_q = None
             self.y_station = None
+        dist = _dist()
+        self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
         self.seed = int(seed if seed is not None else np.random.SeedSequence().entropy % (2 ** 63))
+        if dist:
+            # every rank must derive the same ancestors, pairs and branch lengths from the same counter-based uniforms
+            # and train on the same site minibatches: rank 0's seed (explicit or drawn) is the run's seed
+            box = [self.seed]
+            dist.broadcast_object_list(box, src=0)
+            self.seed = int(box[0])
+        self._slice_rng = random.Random(self.seed) if (dist or seed is not None) else random
         self._step_counter = 0
         self._sweeps: Dict[tuple, ops.Sweep] = {}
         self._code_bufs: Dict[int, torch.Tensor] = {}
-        dist = _dist()
-        self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
         self.sharding = choose_sharding(sharding or os.environ.get("VCSMC_SHARDING"), self.K, self.world, self.nested)
         self._comm = None
         if self.sharding == "particles":
@@ -145,9 +152,12 @@ class VCSMC:
 
         With ``need_grad`` the result is differentiable w.r.t. ``trainable_variables()`` (reverse sweep kernels).
         """
+        n_batch = self.S if site_idx is None else len(site_idx)
+        if self.sharding == "sites" and n_batch < self.world:
+            # decided from the batch length alone, so EVERY rank raises before any collective (no rank is left waiting)
+            raise ValueError("site sharding needs at least one site per rank: batch of %d sites on %d GPUs"
+                             % (n_batch, self.world))
         local = self._local_sites(site_idx)
-        if len(local) == 0:
-            raise ValueError("a rank received zero sites: batch smaller than the number of GPUs")
         if site_idx is None and self.sharding != "sites":
             codes = self.codes
         else:
@@ -225,6 +235,35 @@ class VCSMC:
         self.final_trees = np.vectorize(label.get, otypes=[object])(forest[:, 0])
         return np.concatenate(cols, axis=1)
 
+    def jump_chain_of(self, k: int, out: Optional[Dict[str, np.ndarray]] = None) -> np.ndarray:
+        """Row ``k`` of ``jump_chains()`` alone ([1, cols]), without building the labels of all K particles: what large
+        runs store (K*N > 65,536), where the full string array would take minutes and gigabytes on the host."""
+        out = out or self.outputs()
+        sw = self._last
+        N, K = self.N, self.K
+        anc, lref, rref = out["ancestors"], out["left_ref"], out["right_ref"]
+        after, label = {}, {i: self.taxa[i] for i in range(N)}
+
+        def forest_before(r, j):                 # slot j's forest at event r, after resampling (vcsmc.py:288)
+            return list(range(N)) if r == 0 else forest_after(r - 1, int(anc[r][j]))
+
+        def forest_after(r, j):                  # ... after the merge of event r (vcsmc.py:313)
+            if (r, j) not in after:
+                f = forest_before(r, j)
+                after[(r, j)] = [f[p] for p in sw.rem_row(r, j)] + [N + r * K + j]
+            return after[(r, j)]
+
+        def name(x):
+            if x not in label:
+                r, j = divmod(x - N, K)
+                label[x] = name(int(lref[r, j])) + "+" + name(int(rref[r, j]))
+            return label[x]
+
+        row = [""]
+        for r in range(N - 1):
+            row += [name(x) for x in forest_before(r, k)]
+        return np.array([row], dtype=object)
+
     def newick(self, k: Optional[int] = None, out: Optional[Dict[str, np.ndarray]] = None) -> str:
         """Newick string (with the sampled branch lengths) of the tree particle slot ``k`` holds after the last sweep;
         default: the particle with the largest ``log_likelihood_R``.  Rebuilt on the host from the integer tables
@@ -242,7 +281,7 @@ class VCSMC:
         num_batches = n_sites // batch_size
         slices = []
         for _ in range(num_batches):
-            sampled = random.sample(sites_list, batch_size)
+            sampled = self._slice_rng.sample(sites_list, batch_size)   # seeded (and identical on every rank) when a seed is known
             slices.append(sampled)
             sites_list = list(set(sites_list) - set(sampled))
         if len(sites_list) != 0:
@@ -268,6 +307,8 @@ class VCSMC:
 
         init_elbo = float(self.sample_phylogenies(need_grad=False))
         say("===================\nInitial evaluation of ELBO:", round(init_elbo, 3))
+        say("Initial jump chain:")                                   # vcsmc.py:498-499 (row 0)
+        say(self.jump_chain_of(0)[0])
         say("===================")
         save_dir = None
         if save and self.rank == 0:
@@ -299,7 +340,8 @@ class VCSMC:
             Qs = self.get_Q().detach().cpu().numpy()
             lb_param = torch.exp(self.left_branches_var).detach().cpu().numpy()
             rb_param = torch.exp(self.right_branches_var).detach().cpu().numpy()
-            jc = self.jump_chains(out) if K * self.N <= 1 << 16 else None
+            # the reference stores all K rows (vcsmc.py:550,:589); large runs keep the best particle's row only
+            jc = self.jump_chains(out) if K * self.N <= 1 << 16 else self.jump_chain_of(int(np.argmax(out["log_likelihood_R"])), out)
             say("Epoch", i + 1)
             say("ELBO\n", round(-cost, 3))
             say("Stationary probabilities\n", stats)
