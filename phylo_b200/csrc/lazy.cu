@@ -5,283 +5,280 @@
 // weights are known and the next event has drawn its ancestors, only the particles that were drawn at least once
 // ("survivors") get their node written.  With ESS ~ 1 that is one or two nodes per rank event instead of K.
 //
-// Particle sharding (north_star): rank g owns the logical particles [g K/G, (g+1) K/G) and a private node
-// pool.  Nodes are named by a global index e = r*K + k; `loc[e]` maps a node to its local pool slot (valid iff
-// slot_id[loc[e]] == e), so a pool is a cache of the nodes this rank's particles reference.  Per rank event:
-//   1. every rank builds the same CDF from the all-gathered weights and draws ALL K ancestors (same uniforms);
-//   2. the owner of each survivor materialises it into its own pool;
-//   3. every rank copies the forest ROW (node ids, leaf counts) of each of its particles' ancestors -- a peer read when
-//      the ancestor lives on another GPU -- and lists the nodes of those rows it holds no copy of;
-//   4. the slot allocator (free = not referenced by any surviving row of this rank) serves both lists;
-//   5. barrier; missing nodes are pulled out of the owners' pools over NVLink (pull_kernel);
-//   6. pair proposal, branch lengths, transition matrices, scoring, weights for the rank's own particles;
-//   7. ONE all-gather of the step record (weights, likelihoods, branch lengths, child references, kept positions):
-//      the tables every rank needs for the next CDF, for the outputs, and for the reverse sweep.
-// The reverse sweep is sharded by SITE on the gathered tables (sweep.cu, options site_begin/site_end): the gradient is
-// a sum over sites and the recompute backward needs nothing but those tables.
+// Everything of a rank event that is not scoring runs in ONE cooperative kernel (lz_event_kernel) whose phases are
+// separated by grid barriers instead of kernel boundaries -- a rank event used to be ~28 dependent launches, which at
+// 40 ms per sweep (and K/8 particles per GPU) is where the time went.  Launch r of the kernel finishes event r-1 and
+// prepares event r:
+//   1. weights of event r-1 for the rank's own particles (vcsmc.py:376-395) [particle sharding: packed into the step
+//      record, flag barrier over peer memory, the other ranks' chunks are read straight out of their record buffers];
+//   2-4. log-sum-exp, ESS and the categorical CDF over ALL K particles in a fixed tiled order (every rank derives
+//      bit-identical ancestors);
+//   5. ancestors of event r for all K particles (resample, vcsmc.py:284-285), and the forest ROWS of event r-1 -- but
+//      only for "live" particles, those whose normalised weight is not zero in double precision: nobody else can be
+//      drawn as an ancestor or carry a gradient.  A row (node ids, leaf counts, kept positions, and the forest's
+//      scalars: sum of node log-likelihoods, topology prior, v^-) is rebuilt from the ancestor's row and the particle's
+//      own uniforms, so every rank rebuilds every live row locally and no row ever crosses a GPU;
+//   6. survivors: the owner lists them for materialisation, rows keep their nodes alive in the garbage-collected pool,
+//      nodes a rank's particles descend from but does not hold are listed for a pull; the last CTA to finish runs the
+//      slot allocator;
+//   7. the survivors' nodes are written (plain merge), and ONE THREAD per own particle proposes event r: the pair is
+//      the top-2 of its uniforms (extend_partial_state, vcsmc.py:298-305: no sort is needed for that), two ids and two
+//      counts are read from the ancestor's row, the branch lengths are drawn (:351-358), both transition matrices
+//      computed (:181-184) and the particle is entered into the child-pair hash table of the scoring kernel
+//      [particle sharding: flag barrier, then missing nodes are pulled out of the owners' pools over NVLink];
+//   8. grouped visiting order for the scoring kernel.
+// The reverse sweep is sharded by SITE on the gathered tables (sweep.cu, options site_begin/site_end).
+#include <cooperative_groups.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include "merge_device.cuh"
 #include "sweep_state.h"
+
+namespace cg = cooperative_groups;
 
 namespace vcsmc {
 namespace {
 
-// u_res == null: the resampling uniform of logical particle k at rank event r comes straight from the counter-based
-// generator (the same value philox_step_kernel would write: counter (k, r, 1, 0), first two words)
-__global__ void lz_ancestors_kernel(int first, int64_t K, const double* __restrict__ cdf, const double* __restrict__ u_res,
-                                    const uint64_t* __restrict__ seed_dev, int r, int32_t* __restrict__ anc, int32_t* __restrict__ surv) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
-  if (first) {
-    anc[k] = (int32_t)k;
-    return;
-  }
-  double u;
-  if (u_res) {
-    u = u_res[k];
-  } else {
-    uint32_t d[4] = {(uint32_t)k, (uint32_t)((uint64_t)k >> 32) | ((uint32_t)r << 8), 1u, 0u};
-    const uint64_t seed = *seed_dev;
-    philox4x32_10(d, (uint32_t)seed, (uint32_t)(seed >> 32));
-    u = u64_to_unit_f64(d[0], d[1]);
-  }
-  const int idx = upper_bound_cdf(cdf, K, u * cdf[K - 1]);  // resample, vcsmc.py:284-285
-  anc[k] = idx;
-  surv[idx] = 1;
-}
+constexpr int kEvThreads = 256;
+constexpr int kEvWarps = kEvThreads / 32;
+constexpr int kMatSptEv = 2;
 
-struct SurvArgs {
-  int n, N, gc;
-  int64_t Kl, k0;
-  const int32_t* surv;
-  const int32_t* ids_prev;
-  const int32_t* lsrc_prev;
-  const int32_t* rsrc_prev;
-  const int32_t* loc;
-  int32_t* flags;
-  int32_t* mat_list;
-  int32_t* counts;
-};
-
-// survivors of this rank: list them for materialisation; keep their forest rows and their children alive
-__global__ void lz_survivors_kernel(const SurvArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int w = a.n + 2;
-  const int64_t kl = i / w;
-  const int p = (int)(i - kl * w);
-  if (kl >= a.Kl || !a.surv[a.k0 + kl]) return;
-  if (p < a.n) {
-    if (a.gc) {
-      const int id = a.ids_prev[kl * a.N + p];
-      if (id >= a.N) {
-        const int s = a.loc[id - a.N];
-        if (s >= 0) a.flags[s] = 1;  // (the row's newest node has no slot yet)
-      }
-    }
-  } else if (p == a.n) {
-    a.mat_list[atomicAdd(a.counts, 1)] = (int32_t)kl;
-    if (a.gc && a.lsrc_prev[kl] >= 0) a.flags[a.lsrc_prev[kl]] = 1;
-  } else {
-    if (a.gc && a.rsrc_prev[kl] >= 0) a.flags[a.rsrc_prev[kl]] = 1;
-  }
-}
-
-// Free slots (flag == 0), lowest first, go to the survivors to materialise and then to the nodes to pull.
-// Single CTA, fixed order; each warp owns a contiguous segment of the flag array.
-__global__ void __launch_bounds__(1024) lz_alloc_kernel(const int32_t* __restrict__ flags, int64_t P, const int32_t* __restrict__ counts,
-                                                        int64_t fetch_cap, const int32_t* __restrict__ mat_list, int64_t e_base_prev,
-                                                        const int32_t* __restrict__ fetch_e, int32_t* __restrict__ loc,
-                                                        int32_t* __restrict__ slot_id, int32_t* __restrict__ status) {
-  __shared__ int64_t warp_off[33];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int64_t n_mat = counts[0];
-  const int64_t n_fetch = counts[1] < fetch_cap ? counts[1] : fetch_cap;
-  const int64_t Kn = n_mat + n_fetch;
-  if (Kn == 0) return;
-  // every live slot lies below the running peak, so the Kn lowest free slots are below peak + Kn
-  const int64_t peak = status[1];
-  if (peak + Kn < P) P = peak + Kn;
-  const int64_t seg = ((P + 31) / 32 + 31) / 32 * 32;
-  const int64_t b = min((int64_t)wid * seg, P), e = min(b + seg, P);
-  int cnt = 0;
-  for (int64_t i0 = b + lane; i0 < e; i0 += 128) {
-    int f[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) f[q] = (i0 + 32 * q < e) ? flags[i0 + 32 * q] : 1;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) cnt += f[q] == 0;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  if (lane == 0) warp_off[wid + 1] = cnt;
-  __syncthreads();
-  if (tid == 0) {
-    int64_t t = 0;
-    warp_off[0] = 0;
-    for (int i = 1; i <= 32; ++i) {
-      t += warp_off[i];
-      warp_off[i] = t;
-    }
-    if (t < Kn) {
-      status[0] = VCSMC_ERR_POOL;
-      for (int64_t j = t; j < Kn; ++j) loc[j < n_mat ? e_base_prev + mat_list[j] : fetch_e[j - n_mat]] = -1;
-    }
-  }
-  __syncthreads();
-  int64_t j = warp_off[wid];
-  int top = 0;
-  for (int64_t i0 = b; i0 < e && j < Kn; i0 += 128) {
-    int f[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) f[q] = (i0 + 32 * q + lane < e) ? flags[i0 + 32 * q + lane] : 1;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int64_t i = i0 + 32 * q + lane;
-      const bool is_free = f[q] == 0;
-      const unsigned m = __ballot_sync(0xffffffffu, is_free);
-      const int64_t mine = j + __popc(m & ((1u << lane) - 1));
-      if (is_free && mine < Kn) {
-        const int64_t node = mine < n_mat ? e_base_prev + mat_list[mine] : fetch_e[mine - n_mat];
-        loc[node] = (int32_t)i;
-        slot_id[i] = (int32_t)node;
-        top = (int)i + 1;
-      }
-      j += __popc(m);
-    }
-  }
-  if (top) atomicMax(status + 1, top);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Inherit + propose in one pass (one warp per own particle): copy the ancestor's forest row (peer read when it lives on
-// another GPU), keep cached nodes alive / list missing ones, draw the pair and the two branch lengths, write the new
-// row.  The forest's scalars (sum of node log-likelihoods F, topology prior, v^-) travel with the particle and are
-// updated incrementally, so the weight step no longer walks the forest:
-//     F' = F_anc - ell[left] - ell[right] (+ ell[new], added once the merge has been scored).
-// resample vcsmc.py:284-289,318-325; extend_partial_state :298-305; Exponential sample :351-358; state update :361-373;
-// compute_forest_posterior :231-245 and overcounting_correct :247-252 as running sums.
-// ---------------------------------------------------------------------------------------------
-struct ProposeArgs {
-  int r, n, N, gc, rank, row_stride;
-  int64_t K, Kl, k0, fetch_cap;
-  const int32_t* anc;
-  const int32_t* peer_ids[kMaxPeers];
-  const int32_t* peer_cnt[kMaxPeers];
-  const double* peer_F[kMaxPeers];
-  const double* peer_topo[kMaxPeers];
-  const int32_t* peer_vm[kMaxPeers];
-  const int32_t* loc;
-  const int32_t* slot_id;
-  int32_t* flags;
-  int32_t* pend;
-  int32_t* fetch_e;
-  int32_t* fetch_src;
-  int32_t* counts;
-  int32_t* status;
-  const float* u_pair;   // explicit uniforms of the own particles ([Kl][n], [Kl], [Kl]) or null: counter-based generator
-  const double* u_bl;
-  const double* u_br;
-  const uint64_t* seed_dev;
+struct EvArgs {
+  int r;                 // launch index: finishes rank event r-1 (r > 0) and prepares rank event r (r < N-1)
+  int N, S, jc, gc, rank, world, sorted, skip_leaf_pairs, row_stride, log2T, tiles, bar_index, n_barriers_total;
+  int64_t K, Kl, k0, pool_slots, fetch_cap, slot_sites;
+  // model and uniforms (null uniforms: counter-based generator)
   const double* lam_l;
   const double* lam_r;
-  const double* ell_node;
+  const double* Q;
+  const double* pi;
   const double* ldf;
-  const double* LL_prev;
-  int32_t* ids_new;   // [Kl][N]
-  int32_t* cnt_new;
-  double* F_new;      // [Kl] forest scalars after this event (F without the new node's term until the weight step)
-  double* topo_new;
-  int32_t* vm_new;
-  int32_t* lref;      // row r of the [N-1][K] tables
+  const float* u_pair_prev;   // [K][N-r+1] of event r-1
+  const float* u_pair_cur;    // [K][N-r]   of event r
+  const double* u_bl;         // row r, all K
+  const double* u_br;
+  const double* u_res;        // row r, all K
+  const uint64_t* seed_dev;
+  const uint8_t* codes;
+  // [N-1][K] tables
+  int32_t* anc;
+  int32_t* lref;
   int32_t* rref;
   int32_t* nleaf;
-  uint8_t* rempos;
   double* b_l;
   double* b_r;
   double* t2;
-  double* ll_tilde;   // [Kl]
+  double* cum_l;
+  double* cum_r;
+  double* lw;
+  double* LL;
+  double* P;
+  double* ell_node;
+  uint8_t* rempos_prev;       // block of event r-1
+  double* stats;
+  // per-particle work arrays
+  const double* ell_part;     // [Kl][tiles] partial sums of event r-1's scoring
+  double* pF;                 // [Kl] forest sum without the new node
+  double* pT;                 // [Kl] topology prior of the forest after the merge
+  int32_t* pV;                // [Kl] v^- of the forest after the merge
+  double* pLLt;               // [Kl] log_likelihood_tilde
+  int32_t* vminus;            // [K] output
+  int32_t* lsrc[2];           // [Kl] child slots, by event parity
+  int32_t* rsrc[2];
+  // rows of live particles, by event parity, indexed by GLOBAL particle
+  int32_t* row_ids[2];
+  int32_t* row_cnt[2];
+  double* row_F[2];
+  double* row_T[2];
+  int32_t* row_V[2];
+  double* F0;                 // sum of the leaves' log-likelihoods
+  // resampling
+  double* cdf;
+  double* cdf_scratch;
+  int32_t* live;
+  int32_t* surv;
+  int32_t* haskid;
+  // node pool
+  double* pool;
+  int32_t* flags;
+  int32_t* loc;
+  int32_t* slot_id;
+  int32_t* pend;
+  int32_t* mat_list;
+  int32_t* fetch_e;
+  int32_t* fetch_src;
+  int32_t* counts;            // [0] survivors to materialise, [1] nodes to pull, [2] occupied hash slots, [3..4] last-CTA tickets
+  int32_t* status;
+  // grouping
+  unsigned long long* gtab;
+  int32_t* gcnt;
+  int32_t* goff;
+  int32_t* gslot;
+  int32_t* grank;
+  int32_t* gocc;
+  int32_t* order;
+  int32_t* gcount;
+  // outputs of the last launch
+  double* llR;
+  double* ll_tilde_out;
+  double* elbo;
+  double* logz;
+  double* ess;
+  double ldf_root;
+  // particle sharding
+  char* rec;
+  int64_t rec_stride;
+  const char* peer_rec[kMaxPeers];
+  int32_t* peer_sig[kMaxPeers];
+  const int32_t* peer_loc[kMaxPeers];
+  const double* peer_pool[kMaxPeers];
+  int32_t* epoch_base;
 };
 
-constexpr int kProposeWarps = 8;
-
-template <int NQ>
-__global__ void __launch_bounds__(kProposeWarps * 32) lz_propose_kernel(const ProposeArgs a) {
-  extern __shared__ __align__(16) float su_all[];
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t kl = (int64_t)blockIdx.x * kProposeWarps + wid;
-  if (kl >= a.Kl) return;
-  const int n = a.n, N = a.N, r = a.r;
-  const int64_t k = a.k0 + kl;
-  const bool first = (r == 0);  // initial forest = the N leaves, one each (vcsmc.py:414-415)
-  float* su = su_all + wid * a.row_stride;
-
-  // ---- the ancestor's row
-  int64_t anc = k;
-  int g = a.rank;
-  int64_t al = kl;
-  if (!first) {
-    anc = a.anc[k];
-    g = (int)(anc / a.Kl);
-    al = anc - (int64_t)g * a.Kl;
-  }
-  const int32_t* src_ids = a.peer_ids[g] + al * N;
-  const int32_t* src_cnt = a.peer_cnt[g] + al * N;
-  const int64_t newest = (int64_t)(r - 1) * a.K + anc;  // the ancestor's own node: materialised by its owner
-  int my_id[NQ], my_cnt[NQ];
-  float my_u[NQ];
+__device__ __forceinline__ int warp_sum_int(int v) {
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    const int i = lane + 32 * q;
-    my_id[q] = -1;
-    my_cnt[q] = 0;
-    my_u[q] = 0.f;
-    if (i >= n) continue;
-    if (first) {
-      my_id[q] = i;
-      my_cnt[q] = 1;
-    } else {
-      const int id = src_ids[i];
-      my_id[q] = id;
-      my_cnt[q] = src_cnt[i];
-      if (id >= N) {
-        const int e = id - N;
-        bool have;
-        if (e == newest) {
-          have = (g == a.rank);  // gets its slot from the allocator, via the survivor list
-        } else {
-          const int s = a.loc[e];
-          have = !a.gc || (s >= 0 && a.slot_id[s] == e);
-          if (have && a.gc) a.flags[s] = 1;
-        }
-        if (!have && atomicExch(a.pend + e, r) != r) {  // first claim of this node in this rank event
-          const int pos = atomicAdd(a.counts + 1, 1);
-          if (pos < a.fetch_cap) {
-            a.fetch_e[pos] = e;
-            a.fetch_src[pos] = g;
-          } else {
-            a.status[0] = VCSMC_ERR_POOL;
-          }
-        }
-      }
-    }
-    if (a.u_pair) {   // injected uniforms: ranked by counting below
-      const float u = a.u_pair[kl * n + i];
-      my_u[q] = u;
-      su[i] = u;
-    }
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// true in every thread of the LAST CTA to get here (all CTAs call it once per ticket); that CTA sees what the others wrote
+__device__ __forceinline__ bool last_cta(int32_t* ticket, int* s_flag) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(ticket, 1);
+    const int last = (t == (int)gridDim.x - 1);
+    if (last) *ticket = 0;
+    __threadfence();
+    *s_flag = last;
   }
-  int32_t* in_ = a.ids_new + kl * N;
-  int32_t* cn = a.cnt_new + kl * N;
-  uint8_t* rp = a.rempos + k * (int64_t)(n - 2);
-  int lid = 0, rid = 0, cl = 0, cr = 0;   // (valid in lane 0 afterwards)
-  bool tie_row = false;
-  double tie_F = 0.0, tie_topo = 0.0;
-  int tie_vm = 0;
-  if (!a.u_pair) {
-    // ---- counter-based uniforms: u_i = ((16 random bits) << 8 | i) 2^-24 (philox_step_kernel), so the integer key
-    // orders like u, is tie-free, and carries the element's index: ONE warp bitonic sort of the keys gives the kept
-    // order (ascending) and the merged pair (the two largest).  Lane b draws Philox block b (4 uniforms).
+  __syncthreads();
+  return *s_flag != 0;
+}
+
+// Cross-GPU barrier without the host: after a grid barrier CTA 0 stores this rank's epoch into every peer's flag array
+// (peer store over NVLink, system scope); every CTA then polls its own rank's array until all peers have arrived.
+// A timeout (~30 s) turns a lost peer into a reported error instead of a hang.
+__device__ __forceinline__ void cross_sync(const EvArgs& a, int index, cg::grid_group& grid) {
+  __threadfence_system();
+  grid.sync();
+  const int epoch = *a.epoch_base + index;
+  const int g = threadIdx.x;
+  if (blockIdx.x == 0 && g < a.world) {
+    volatile int32_t* out = a.peer_sig[g] + a.rank;
+    *out = epoch;
+    __threadfence_system();
+  }
+  if (g < a.world) {
+    volatile int32_t* in = a.peer_sig[a.rank] + g;
+    const long long t0 = clock64();
+    while (*in - epoch < 0) {
+      if (clock64() - t0 > 60000000000ll) {   // ~30 s at 1.9 GHz
+        a.status[0] = VCSMC_ERR_STATE;
+        break;
+      }
+      __nanosleep(100);
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 1: weights of event r-1 (forest posterior from the row scalars + branch priors + v^- + weight, vcsmc.py:376-395),
+// O(1) per particle; under particle sharding also the rank's chunk of the step record
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void particle_weight(const EvArgs& a, int64_t k) {
+  const int r = a.r - 1;
+  const int64_t kl = k - a.k0;
+  const int64_t e = (int64_t)r * a.K + k;
+  double ell = 0.0;
+  for (int t = 0; t < a.tiles; ++t) ell += a.ell_part[kl * a.tiles + t];
+  a.ell_node[a.N + e] = ell;
+  const double F = a.pF[kl] + ell;
+  const int vm = a.pV[kl];
+  const double laml = a.lam_l[r], lamr = a.lam_r[r];
+  const double bl = a.b_l[e], br = a.b_r[e];
+  const double cl = (r > 0 ? a.cum_l[e - a.K] : 0.0) + bl;   // quirk Q1: slot-wise, un-resampled histories
+  const double cr = (r > 0 ? a.cum_r[e - a.K] : 0.0) + br;
+  a.cum_l[e] = cl;
+  a.cum_r[e] = cr;
+  const double llog = log(laml), rlog = log(lamr);
+  // quirk Q2: the CURRENT step's rate multiplies ALL earlier branches (vcsmc.py:380-383)
+  const double LLr = (F + a.pT[kl]) + (-laml * cl + (double)(r + 1) * llog) + (-lamr * cr + (double)(r + 1) * rlog);
+  // quirk Q3: q = 1/C(n,2) is subtracted raw (vcsmc.py:298,392)
+  const int n = a.N - r;
+  const double q = 1.0 / ((double)n * (double)(n - 1) / 2.0);
+  const double lw = LLr - a.pLLt[kl] - (llog - laml * bl + rlog - lamr * br) + log((double)vm) - q;
+  a.LL[e] = LLr;
+  a.lw[e] = lw;
+  a.vminus[k] = vm;
+  if (a.world > 1) {   // the per-event record (field-major inside the rank's chunk)
+    char* base = a.rec + (int64_t)a.rank * a.rec_stride;
+    double* d = reinterpret_cast<double*>(base);
+    d[0 * a.Kl + kl] = lw;
+    d[1 * a.Kl + kl] = LLr;
+    d[2 * a.Kl + kl] = ell;
+    d[3 * a.Kl + kl] = bl;
+    d[4 * a.Kl + kl] = br;
+    d[5 * a.Kl + kl] = cl;
+    d[6 * a.Kl + kl] = cr;
+    int32_t* qi = reinterpret_cast<int32_t*>(base + 56 * a.Kl);
+    qi[0 * a.Kl + kl] = a.lref[e];
+    qi[1 * a.Kl + kl] = a.rref[e];
+    qi[2 * a.Kl + kl] = a.nleaf[e];
+    qi[3 * a.Kl + kl] = vm;
+  }
+}
+
+__device__ __forceinline__ void particle_unpack(const EvArgs& a, int64_t k) {
+  const int r = a.r - 1;
+  const int g = (int)(k / a.Kl);
+  const int64_t kl = k - (int64_t)g * a.Kl;
+  const int64_t e = (int64_t)r * a.K + k;
+  const char* base = a.peer_rec[g] + (int64_t)g * a.rec_stride;
+  const double* d = reinterpret_cast<const double*>(base);
+  a.lw[e] = d[0 * a.Kl + kl];
+  a.LL[e] = d[1 * a.Kl + kl];
+  a.ell_node[a.N + e] = d[2 * a.Kl + kl];
+  const double bl = d[3 * a.Kl + kl], br = d[4 * a.Kl + kl];
+  a.b_l[e] = bl;
+  a.b_r[e] = br;
+  a.t2[2 * e] = bl;
+  a.t2[2 * e + 1] = br;
+  a.cum_l[e] = d[5 * a.Kl + kl];
+  a.cum_r[e] = d[6 * a.Kl + kl];
+  const int32_t* qi = reinterpret_cast<const int32_t*>(base + 56 * a.Kl);
+  a.lref[e] = qi[0 * a.Kl + kl];
+  a.rref[e] = qi[1 * a.Kl + kl];
+  a.nleaf[e] = qi[2 * a.Kl + kl];
+  a.vminus[k] = qi[3 * a.Kl + kl];
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 5b: the forest row of a live particle of event r-1 (one warp): the ancestor's row, reordered by the ascending
+// rank of the particle's pair uniforms (the order tf.nn.top_k(-z) leaves the kept subtrees in, vcsmc.py:305), plus the
+// new node; and the row's scalars.  Ties (injected uniforms only) follow tf.nn.top_k's lower-index rule in both
+// rankings, including its keep-one-twice / drop-another consequence.
+// ---------------------------------------------------------------------------------------------
+template <int NQ>
+__device__ __forceinline__ void build_row(const EvArgs& a, int64_t k, float* su, int lane) {
+  const int r = a.r - 1;          // the event whose row this is
+  const int n = a.N - r, N = a.N;  // roots before the merge
+  const bool first = (r == 0);
+  const int pb = r & 1, pa = pb ^ 1;
+  const int64_t anc = first ? k : a.anc[(int64_t)r * a.K + k];
+  const int32_t* src_ids = a.row_ids[pa] + anc * N;
+  const int32_t* src_cnt = a.row_cnt[pa] + anc * N;
+  int32_t* in_ = a.row_ids[pb] + k * N;
+  int32_t* cn = a.row_cnt[pb] + k * N;
+  uint8_t* rp = a.rempos_prev + k * (int64_t)(n - 2);
+  int c0 = 0, c1 = 0;
+  if (!a.u_pair_prev) {
+    // counter-based uniforms: u_i = ((16 random bits) << 8 | i) 2^-24 (philox_step_kernel), so the integer key orders
+    // like u, is tie-free, and carries the element's index: ONE warp bitonic sort of the keys gives the kept order
+    // (ascending) and the merged pair (the two largest).  Lane b draws Philox block b (4 uniforms).
     constexpr int NB = NQ >= 4 ? NQ / 4 : 1;
     uint32_t blk[NB][4];
     const uint64_t seed = *a.seed_dev;
@@ -306,7 +303,6 @@ __global__ void __launch_bounds__(kProposeWarps * 32) lz_propose_kernel(const Pr
       }
       key[q] = i < n ? ((w >> 8) & 0xFFFF00u) | (uint32_t)(i & 0xFF) : 0xFFFFFFFFu;
     }
-    // bitonic sort of the 32*NQ keys, element index = lane + 32 q, ascending
 #pragma unroll
     for (int k2 = 2; k2 <= 32 * NQ; k2 <<= 1) {
 #pragma unroll
@@ -349,112 +345,230 @@ __global__ void __launch_bounds__(kProposeWarps * 32) lz_propose_kernel(const Pr
         i1 = i;
       }
     }
-    // positions n-1 / n-2 live in lanes (n-1) & 31 / (n-2) & 31 (max over the lane's slots picks the one that was set)
-    const int c0 = __shfl_sync(0xffffffffu, i0, (n - 1) & 31), c1 = __shfl_sync(0xffffffffu, i1, (n - 2) & 31);
-    lid = first ? c0 : src_ids[c0];
-    rid = first ? c1 : src_ids[c1];
-    cl = first ? 1 : src_cnt[c0];
-    cr = first ? 1 : src_cnt[c1];
-  } else {
-  for (int i = n + lane; i < ((n + 3) & ~3); i += 32) su[i] = INFINITY;   // padding of the float4 reads below
-  __syncwarp();
-
-  // ---- ranks.  z = -log(-log u) is increasing in u, so ranking u reproduces tf.nn.top_k (smc_device.cuh).  Without
-  // ties the ascending rank is #{u_j < u_i} and the descending rank its mirror image; rows with a tie (never produced
-  // by the generator above, possible with injected uniforms) take the exact all-pairs routine with the reference's
-  // tie rule.
-  int lt[NQ], eq[NQ];
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) lt[q] = eq[q] = 0;
-  for (int j = 0; j < n; j += 4) {
-    const float4 v = *reinterpret_cast<const float4*>(su + j);
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      lt[q] += (v.x < my_u[q]) + (v.y < my_u[q]) + (v.z < my_u[q]) + (v.w < my_u[q]);
-      eq[q] += (v.x == my_u[q]) + (v.y == my_u[q]) + (v.z == my_u[q]) + (v.w == my_u[q]);
+    for (int o = 16; o > 0; o >>= 1) {
+      i0 = max(i0, __shfl_xor_sync(0xffffffffu, i0, o));
+      i1 = max(i1, __shfl_xor_sync(0xffffffffu, i1, o));
     }
-  }
-  bool tie = false;
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) tie = tie || (lane + 32 * q < n && eq[q] != 1);
-  if (__any_sync(0xffffffffu, tie)) {
-    int c0, c1;
+    c0 = i0;
+    c1 = i1;
+  } else {
+    const float* u = a.u_pair_prev + k * n;
+    for (int i = lane; i < n; i += 32) su[i] = u[i];
+    __syncwarp();
     rank_pairs_warp(su, n, lane, c0, c1, [&](int pos, int i) {
       rp[pos] = (uint8_t)i;
       in_[pos] = first ? i : src_ids[i];
       cn[pos] = first ? 1 : src_cnt[i];
     });
-    lid = first ? c0 : src_ids[c0];
-    rid = first ? c1 : src_ids[c1];
-    cl = first ? 1 : src_cnt[c0];
-    cr = first ? 1 : src_cnt[c1];
-    // tf.nn.top_k's tie rule can keep a merged subtree and drop another one (duplicate-on-tie quirk, vcsmc.py:304-305),
-    // so the kept set is not "all but the pair": the forest scalars of such a row are summed over the row itself
     __syncwarp();
-    double fs = 0.0, ts = 0.0;
-    int vs = 0;
-    for (int pos = lane; pos < n - 2; pos += 32) {
-      const int c = cn[pos];
-      fs += a.ell_node[in_[pos]];
-      ts -= a.ldf[2 * max(c, 2) - 3];
-      vs += c - (c == 1);
-    }
-    tie_F = warp_sum(fs);
-    tie_topo = warp_sum(ts);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, o);
-    tie_vm = vs;
-    tie_row = true;
-  } else {
-    int id0 = -1, ct0 = 0, id1 = -1, ct1 = 0;
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const int i = lane + 32 * q;
-      if (i >= n) continue;
-      const int ra = lt[q];
-      if (ra < n - 2) {
-        rp[ra] = (uint8_t)i;
-        in_[ra] = my_id[q];
-        cn[ra] = my_cnt[q];
-      } else if (ra == n - 1) {
-        id0 = my_id[q];
-        ct0 = my_cnt[q];
-      } else {
-        id1 = my_id[q];
-        ct1 = my_cnt[q];
-      }
-    }
-    const int s0 = __ffs(__ballot_sync(0xffffffffu, id0 >= 0)) - 1, s1 = __ffs(__ballot_sync(0xffffffffu, id1 >= 0)) - 1;
-    lid = __shfl_sync(0xffffffffu, id0, s0);
-    cl = __shfl_sync(0xffffffffu, ct0, s0);
-    rid = __shfl_sync(0xffffffffu, id1, s1);
-    cr = __shfl_sync(0xffffffffu, ct1, s1);
-  }
-  }
-  // ---- the forest's scalars before the merge
-  double F_anc = 0.0;
-  if (first) {
-    for (int i = lane; i < N; i += 32) F_anc += a.ell_node[i];
-    F_anc = warp_sum(F_anc);
   }
   if (lane == 0) {
-    double topo_anc = 0.0;   // -sum log (2 max(c,2) - 3)!! over the roots: 0 for N leaves
-    int vm_anc = 0;          // sum (c - [c == 1]) over the roots: 0 for N leaves
-    if (!first) {
-      F_anc = a.peer_F[g][al];
-      topo_anc = a.peer_topo[g][al];
-      vm_anc = a.peer_vm[g][al];
-    }
     in_[n - 2] = (int32_t)(N + (int64_t)r * a.K + k);
+    cn[n - 2] = (first ? 1 : src_cnt[c0]) + (first ? 1 : src_cnt[c1]);
+  }
+  __syncwarp();
+  // the row's scalars: sum of node log-likelihoods (compute_forest_posterior, vcsmc.py:238-242), topology prior (:243),
+  // v^- (:247-252)
+  double fs = 0.0, ts = 0.0;
+  int vs = 0;
+  for (int pos = lane; pos < n - 1; pos += 32) {
+    const int c = cn[pos];
+    fs += a.ell_node[in_[pos]];
+    ts -= a.ldf[2 * max(c, 2) - 3];
+    vs += c - (c == 1);
+  }
+  fs = warp_sum(fs);
+  ts = warp_sum(ts);
+  vs = warp_sum_int(vs);
+  if (lane == 0) {
+    a.row_F[pb][k] = fs;
+    a.row_T[pb][k] = ts;
+    a.row_V[pb][k] = vs;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 6: a survivor of event r-1 (one warp): keep its row's nodes alive, list what has to be written or pulled
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void survivor_row(const EvArgs& a, int64_t k, int lane) {
+  const int r = a.r - 1;
+  const int N = a.N, m = N - r - 1;   // roots after the merge
+  const int g = (int)(k / a.Kl);
+  const bool own = (g == a.rank);
+  const bool kid = a.haskid[k] != 0;
+  if (!own && !kid) return;
+  const int32_t* ids = a.row_ids[r & 1] + k * N;
+  const int64_t newest = (int64_t)r * a.K + k;
+  for (int pos = lane; pos < m; pos += 32) {
+    const int id = ids[pos];
+    if (id < N) continue;
+    const int e = id - N;
+    bool have;
+    if (e == newest) {
+      have = own;                       // gets its slot from the allocator through the survivor list
+    } else {
+      const int s = a.loc[e];
+      have = !a.gc || (s >= 0 && a.slot_id[s] == e);
+      if (have && a.gc) a.flags[s] = 1;
+    }
+    if (!have && kid && atomicExch(a.pend + e, a.r) != a.r) {   // first claim of this node in this rank event
+      const int p = atomicAdd(a.counts + 1, 1);
+      if (p < a.fetch_cap) {
+        a.fetch_e[p] = e;
+        a.fetch_src[p] = g;
+      } else {
+        a.status[0] = VCSMC_ERR_POOL;
+      }
+    }
+  }
+  if (own && lane == 0) {
+    const int64_t kl = k - a.k0;
+    a.mat_list[atomicAdd(a.counts, 1)] = (int32_t)kl;
+    if (a.gc) {   // the children the node is about to be computed from
+      const int ls = a.lsrc[r & 1][kl], rs = a.rsrc[r & 1][kl];
+      if (ls >= 0) a.flags[ls] = 1;
+      if (rs >= 0) a.flags[rs] = 1;
+    }
+  }
+}
+
+// Free slots (flag == 0), lowest first, go to the survivors to materialise and then to the nodes to pull.
+// One CTA (the last one to finish phase 6), fixed order; each warp owns a contiguous segment of the flag array.
+__device__ void allocate_slots(const EvArgs& a, int64_t* warp_off) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  volatile int32_t* counts = a.counts;
+  const int64_t n_mat = counts[0];
+  const int64_t n_fetch = counts[1] < a.fetch_cap ? counts[1] : a.fetch_cap;
+  const int64_t Kn = n_mat + n_fetch;
+  if (Kn == 0) return;
+  const int64_t e_base_prev = (int64_t)(a.r - 1) * a.K + a.k0;
+  // every live slot lies below the running peak, so the Kn lowest free slots are below peak + Kn
+  int64_t P = a.pool_slots;
+  const int64_t peak = a.status[1];
+  if (peak + Kn < P) P = peak + Kn;
+  const int64_t seg = ((P + kEvWarps - 1) / kEvWarps + 31) / 32 * 32;
+  const int64_t b = min((int64_t)wid * seg, P), e = min(b + seg, P);
+  volatile const int32_t* flags = a.flags;
+  int cnt = 0;
+  for (int64_t i0 = b + lane; i0 < e; i0 += 128) {
+    int f[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f[q] = (i0 + 32 * q < e) ? flags[i0 + 32 * q] : 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cnt += f[q] == 0;
+  }
+  cnt = warp_sum_int(cnt);
+  if (lane == 0) warp_off[wid + 1] = cnt;
+  __syncthreads();
+  if (tid == 0) {
+    int64_t t = 0;
+    warp_off[0] = 0;
+    for (int i = 1; i <= kEvWarps; ++i) {
+      t += warp_off[i];
+      warp_off[i] = t;
+    }
+    if (t < Kn) {
+      a.status[0] = VCSMC_ERR_POOL;
+      for (int64_t j = t; j < Kn; ++j) a.loc[j < n_mat ? e_base_prev + a.mat_list[j] : a.fetch_e[j - n_mat]] = -1;
+    }
+  }
+  __syncthreads();
+  int64_t j = warp_off[wid];
+  int top = 0;
+  for (int64_t i0 = b; i0 < e && j < Kn; i0 += 128) {
+    int f[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) f[q] = (i0 + 32 * q + lane < e) ? flags[i0 + 32 * q + lane] : 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t i = i0 + 32 * q + lane;
+      const bool is_free = f[q] == 0;
+      const unsigned mm = __ballot_sync(0xffffffffu, is_free);
+      const int64_t mine = j + __popc(mm & ((1u << lane) - 1));
+      if (is_free && mine < Kn) {
+        const int64_t node = mine < n_mat ? e_base_prev + ((volatile int32_t*)a.mat_list)[mine] : ((volatile int32_t*)a.fetch_e)[mine - n_mat];
+        a.loc[node] = (int32_t)i;
+        a.slot_id[i] = (int32_t)node;
+        top = (int)i + 1;
+      }
+      j += __popc(mm);
+    }
+  }
+  if (top) atomicMax(a.status + 1, top);
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase 7b: proposal of event r for one own particle (one thread)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void propose_particle(const EvArgs& a, int64_t kl, bool on, int lane) {
+  const int r = a.r, N = a.N, n = N - r;
+  const int64_t K = a.K;
+  const int64_t k = a.k0 + kl;
+  const bool first = (r == 0);
+  int ls = 0, rs = 0;
+  if (on) {
+    const int64_t anc = first ? k : a.anc[(int64_t)r * K + k];
+    const int pa = (r & 1) ^ 1;
+    const int32_t* row_ids = a.row_ids[pa] + anc * N;
+    const int32_t* row_cnt = a.row_cnt[pa] + anc * N;
+    int c0 = 0, c1 = 1;
+    bool straddle = false;   // the 2nd and 3rd largest uniforms tie: tf.nn.top_k keeps a merged subtree and drops another
+    if (!a.u_pair_cur) {
+      uint32_t best = 0u, second = 0u;
+      const uint64_t seed = *a.seed_dev;
+      for (int j = 0; j < n; j += 4) {
+        uint32_t p[4] = {(uint32_t)k, (uint32_t)((uint64_t)k >> 32) | ((uint32_t)r << 8), 2u, (uint32_t)(j >> 2)};
+        philox4x32_10(p, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (j + q < n) {
+            const uint32_t key = (((p[q] >> 8) & 0xFFFF00u) | (uint32_t)((j + q) & 0xFF)) + 1u;   // > 0, tie-free
+            if (key > best) {
+              second = best;
+              best = key;
+            } else if (key > second) {
+              second = key;
+            }
+          }
+        }
+      }
+      c0 = (int)((best - 1u) & 0xFFu);
+      c1 = (int)((second - 1u) & 0xFFu);
+    } else {
+      const float* u = a.u_pair_cur + k * n;
+      float b0 = -1.f, b1 = -1.f, b2 = -1.f;   // uniforms are >= 0
+      int i0 = 0, i1 = 0;
+      for (int i = 0; i < n; ++i) {
+        const float v = u[i];
+        if (v > b0) {
+          b2 = b1;
+          b1 = b0; i1 = i0;
+          b0 = v; i0 = i;
+        } else if (v > b1) {
+          b2 = b1;
+          b1 = v; i1 = i;
+        } else if (v > b2) {
+          b2 = v;
+        }
+      }
+      c0 = i0;
+      c1 = i1;
+      straddle = (n > 2) && (b1 == b2);
+    }
+    const int lid = first ? c0 : row_ids[c0];
+    const int rid = first ? c1 : row_ids[c1];
+    const int cl = first ? 1 : row_cnt[c0];
+    const int cr = first ? 1 : row_cnt[c1];
     const int nl = cl + cr;
-    cn[n - 2] = nl;
-    a.nleaf[k] = nl;
-    a.lref[k] = lid;
-    a.rref[k] = rid;
+    const int64_t e = (int64_t)r * K + k;
+    a.nleaf[e] = nl;
+    a.lref[e] = lid;
+    a.rref[e] = rid;
     double ubl, ubr;
     if (a.u_bl) {
-      ubl = a.u_bl[kl];
-      ubr = a.u_br[kl];
+      ubl = a.u_bl[k];
+      ubr = a.u_br[k];
     } else {
       uint32_t c[4] = {(uint32_t)k, (uint32_t)((uint64_t)k >> 32) | ((uint32_t)r << 8), 0u, 0u};
       const uint64_t seed = *a.seed_dev;
@@ -465,230 +579,370 @@ __global__ void __launch_bounds__(kProposeWarps * 32) lz_propose_kernel(const Pr
     }
     const double bl = -log(ubl) / a.lam_l[r];
     const double br = -log(ubr) / a.lam_r[r];
-    a.b_l[k] = bl;
-    a.b_r[k] = br;
-    a.t2[2 * k] = bl;
-    a.t2[2 * k + 1] = br;
-    a.ll_tilde[kl] = first ? log(1.0 / (double)a.K) : a.LL_prev[anc];
-    if (tie_row) {
-      a.F_new[kl] = tie_F;
-      a.topo_new[kl] = tie_topo - a.ldf[2 * max(nl, 2) - 3];
-      a.vm_new[kl] = tie_vm + nl;
+    a.b_l[e] = bl;
+    a.b_r[e] = br;
+    a.t2[2 * e] = bl;
+    a.t2[2 * e + 1] = br;
+    a.pLLt[kl] = first ? log(1.0 / (double)K) : a.LL[(int64_t)(r - 1) * K + anc];
+    if (!straddle) {
+      const double F_anc = first ? *a.F0 : a.row_F[pa][anc];
+      const double T_anc = first ? 0.0 : a.row_T[pa][anc];
+      const int V_anc = first ? 0 : a.row_V[pa][anc];
+      a.pF[kl] = F_anc - a.ell_node[lid] - a.ell_node[rid];
+      a.pT[kl] = T_anc + a.ldf[2 * max(cl, 2) - 3] + a.ldf[2 * max(cr, 2) - 3] - a.ldf[2 * max(nl, 2) - 3];
+      a.pV[kl] = V_anc - (cl - (cl == 1)) - (cr - (cr == 1)) + nl;
     } else {
-      a.F_new[kl] = F_anc - a.ell_node[lid] - a.ell_node[rid];
-      a.topo_new[kl] = topo_anc + a.ldf[2 * max(cl, 2) - 3] + a.ldf[2 * max(cr, 2) - 3] - a.ldf[2 * max(nl, 2) - 3];
-      a.vm_new[kl] = vm_anc - (cl - (cl == 1)) - (cr - (cr == 1)) + nl;
+      // the kept set is "ascending rank < n-2" with tf.nn.top_k's tie rule, not "all but the pair": sum over it
+      const float* u = a.u_pair_cur + k * n;
+      double fs = 0.0, ts = 0.0;
+      int vs = 0;
+      for (int i = 0; i < n; ++i) {
+        const float ui = u[i];
+        int ra = 0;
+        for (int j = 0; j < n; ++j) ra += (u[j] < ui) || (u[j] == ui && j < i);
+        if (ra < n - 2) {
+          const int c = first ? 1 : row_cnt[i];
+          fs += a.ell_node[first ? i : row_ids[i]];
+          ts -= a.ldf[2 * max(c, 2) - 3];
+          vs += c - (c == 1);
+        }
+      }
+      a.pF[kl] = fs;
+      a.pT[kl] = ts - a.ldf[2 * max(nl, 2) - 3];
+      a.pV[kl] = vs + nl;
+    }
+    // child slots (the allocator / earlier pulls have placed every node of the ancestor's row)
+    ls = lid < N ? -(lid + 1) : a.loc[lid - N];
+    rs = rid < N ? -(rid + 1) : a.loc[rid - N];
+    a.lsrc[r & 1][kl] = ls;
+    a.rsrc[r & 1][kl] = rs;
+    // transition matrices (vcsmc.py:181-184)
+    double* Pout = a.P + e * 32;
+    if (a.jc) {
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const double ti = side ? br : bl;
+        const double o = -0.25 * expm1(-ti);
+        const double d = 0.25 + 0.75 * exp(-ti);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) Pout[side * 16 + q] = (q % 5 == 0) ? d : o;
+      }
+    } else {
+      for (int side = 0; side < 2; ++side) {
+        const double ti = side ? br : bl;
+        M4 A;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) A.a[q] = a.Q[q] * ti;
+        const M4 X = m4_expm(A);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) Pout[side * 16 + q] = X.a[q];
+      }
+    }
+  }
+  if (!a.sorted) return;
+  // ---- child-pair hash table of the scoring kernel: particles with the same (unordered) pair become adjacent
+  bool ins = on && !(a.skip_leaf_pairs && ls < 0 && rs < 0);   // two leaves: scored from site patterns, not listed
+  int slot = -1 - lane;  // lanes that insert nothing never match anybody
+  if (ins) {
+    const unsigned long long key = (((unsigned long long)(unsigned)(min(ls, rs) + 256)) << 32 | (unsigned)(max(ls, rs) + 256)) + 1ull;
+    const unsigned mask = (1u << a.log2T) - 1u;
+    unsigned h = (unsigned)((key * 0x9E3779B97F4A7C15ull) >> (64 - a.log2T));
+    while (true) {
+      const unsigned long long old = atomicCAS(a.gtab + h, 0ull, key);
+      if (old == 0ull) {
+        a.gocc[atomicAdd(a.counts + 2, 1)] = (int32_t)h;   // first particle of this pair: the slot is now occupied
+        break;
+      }
+      if (old == key) break;
+      h = (h + 1) & mask;
+    }
+    slot = (int)h;
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, slot);
+  if (ins) {
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(a.gcnt + slot, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    a.gslot[kl] = slot;
+    a.grank[kl] = base + __popc(peers & ((1u << lane) - 1));
+  } else if (on) {
+    a.gslot[kl] = -1;
+  }
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) float su_all[];
+  __shared__ double sm[8];
+  __shared__ double wsum[8];
+  __shared__ int64_t warp_off[kEvWarps + 1];
+  __shared__ int s_flag;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int r = a.r, N = a.N;
+  const int64_t K = a.K, Kl = a.Kl, k0 = a.k0;
+  const int nb = (int)((K + kCdfTile - 1) / kCdfTile);
+  const int64_t gthreads = (int64_t)gridDim.x * kEvThreads, gtid = (int64_t)blockIdx.x * kEvThreads + tid;
+  const int64_t gwarps = (int64_t)gridDim.x * kEvWarps, gwid = (int64_t)blockIdx.x * kEvWarps + wid;
+  float* su = su_all + wid * a.row_stride;
+
+  if (r > 0) {
+    const int64_t e_row = (int64_t)(r - 1) * K;
+    double* lw = a.lw + e_row;
+    double *pmax = a.cdf_scratch, *psum = pmax + nb, *pw = psum + nb, *pq = pw + nb;
+    // ---- phase 1: weights of event r-1 (own particles), tile by tile, and the tile maxima
+    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int64_t k = (int64_t)vb * kCdfTile + q * 256 + tid;
+        if (k >= k0 && k < k0 + Kl) particle_weight(a, k);
+      }
+      if (a.world == 1) cdf_stage_max(vb, lw, K, pmax, sm);   // (each thread reads back exactly what it wrote)
+    }
+    // scratch of the coming phases: survivor / child flags, slot flags below the running peak, the hash slots the
+    // previous event occupied
+    for (int64_t i = gtid; i < K; i += gthreads) {
+      a.surv[i] = 0;
+      a.haskid[i] = 0;
+    }
+    if (a.gc) {
+      const int64_t peak = a.status[1];
+      for (int64_t i = gtid; i < peak; i += gthreads) a.flags[i] = 0;
+    }
+    if (a.sorted) {
+      const int n_occ = a.counts[2];
+      for (int64_t i = gtid; i < n_occ; i += gthreads) {
+        const int s = a.gocc[i];
+        a.gtab[s] = 0ull;
+        a.gcnt[s] = 0;
+      }
+    }
+    if (a.world > 1) {
+      cross_sync(a, a.bar_index + 1, grid);
+      for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int64_t k = (int64_t)vb * kCdfTile + q * 256 + tid;
+          if (k < K && !(k >= k0 && k < k0 + Kl)) particle_unpack(a, k);
+        }
+        cdf_stage_max(vb, lw, K, pmax, sm);
+      }
+    }
+    grid.sync();
+    // ---- phases 2-4: log-sum-exp, normalised weights + live flags, CDF (resample, vcsmc.py:284-285)
+    if (gtid == 0) {
+      a.counts[0] = 0;
+      a.counts[1] = 0;
+      a.counts[2] = 0;
+      *a.gcount = 0;
+    }
+    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_sumexp(vb, lw, K, nb, pmax, psum, sm);
+    grid.sync();
+    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_weights(vb, lw, K, nb, pmax, psum, a.cdf, pw, pq, a.live, sm);
+    grid.sync();
+    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_scan(vb, K, nb, pmax, psum, pw, pq, a.cdf, a.stats + (r - 1) * 4, sm, wsum);
+    grid.sync();
+    if (r == N - 1) {
+      // ---- last launch: ELBO (vcsmc.py:276), log_likelihood_R (vcsmc.py:254-268, incl. quirk Q4), log_likelihood_tilde
+      if (gtid == 0) {
+        double s = 0.0;
+        const double lk = log((double)K);
+        for (int q = 0; q < N - 1; ++q) {
+          const double z = a.stats[q * 4] - lk;
+          a.logz[q] = z;
+          a.ess[q] = a.stats[q * 4 + 2];
+          s += z;
+        }
+        a.elbo[0] = s;
+      }
+      for (int64_t k = gtid; k < K; k += gthreads) {
+        double lp = 0.0, rp = 0.0;
+        for (int q = 0; q < N - 1; ++q) {
+          const double ll = log(a.lam_l[q]);
+          lp += ll - a.b_l[(int64_t)q * K + k] * a.lam_l[q];
+          rp += ll - a.b_r[(int64_t)q * K + k] * a.lam_r[q];  // log(LEFT param): vcsmc.py:262
+        }
+        a.llR[k] = a.LL[(int64_t)(N - 2) * K + k] + a.ldf_root - lp - rp;
+        a.ll_tilde_out[k] = N >= 3 ? a.LL[(int64_t)(N - 3) * K + a.anc[(int64_t)(N - 2) * K + k]] : log(1.0 / (double)K);
+      }
+      if (a.world > 1) {
+        // nobody starts the next sweep's record before everybody has read this one; then the epochs move on
+        cross_sync(a, a.bar_index + 2, grid);
+        grid.sync();
+        if (gtid == 0) *a.epoch_base += a.n_barriers_total;
+      }
+      return;
+    }
+  }
+
+  // ---- phase 5: ancestors of event r (all K), rows of the live particles of event r-1 (all K)
+  {
+    int32_t* anc_row = a.anc + (int64_t)r * K;
+    if (r == 0) {
+      for (int64_t k = gtid; k < K; k += gthreads) anc_row[k] = (int32_t)k;
+      if (blockIdx.x == 0 && wid == 0) {
+        double f = 0.0;
+        for (int i = lane; i < N; i += 32) f += a.ell_node[i];
+        f = warp_sum(f);
+        if (lane == 0) *a.F0 = f;
+      }
+    } else {
+      const double total = a.cdf[K - 1];
+      for (int64_t k = gtid; k < K; k += gthreads) {
+        double u;
+        if (a.u_res) {
+          u = a.u_res[k];
+        } else {
+          // the same value philox_step_kernel would write: counter (k, r, 1, 0), first two words
+          uint32_t d[4] = {(uint32_t)k, (uint32_t)((uint64_t)k >> 32) | ((uint32_t)r << 8), 1u, 0u};
+          const uint64_t seed = *a.seed_dev;
+          philox4x32_10(d, (uint32_t)seed, (uint32_t)(seed >> 32));
+          u = u64_to_unit_f64(d[0], d[1]);
+        }
+        const int idx = upper_bound_cdf(a.cdf, K, u * total);  // resample, vcsmc.py:284-285
+        anc_row[k] = idx;
+        a.surv[idx] = 1;
+        if (k >= k0 && k < k0 + Kl) a.haskid[idx] = 1;
+      }
+      for (int64_t k = gwid; k < K; k += gwarps)
+        if (a.live[k]) build_row<NQ>(a, k, su, lane);
+    }
+  }
+  grid.sync();
+  // ---- phase 6: survivors of event r-1; the last CTA to finish allocates the slots
+  if (r > 0) {
+    for (int64_t k = gwid; k < K; k += gwarps)
+      if (a.surv[k]) survivor_row(a, k, lane);
+    if (a.gc && last_cta(a.counts + 3, &s_flag)) allocate_slots(a, warp_off);
+  }
+  grid.sync();
+  // ---- phase 7: the survivors' nodes (plain merge, stored); proposal of event r for the own particles
+  if (r > 0) {
+    const int n_mat = a.counts[0];
+    const int tiles = (a.S + kEvThreads * kMatSptEv - 1) / (kEvThreads * kMatSptEv);
+    const int64_t e_base = (int64_t)(r - 1) * K + k0;
+    const int pp = (r - 1) & 1;
+    for (int64_t w = blockIdx.x; w < (int64_t)n_mat * tiles; w += gridDim.x) {
+      const int64_t j = w / tiles;
+      const int t = (int)(w - j * tiles);
+      const int kl = a.mat_list[j];
+      const int ds = a.loc[e_base + kl];
+      if (ds < 0) continue;  // pool exhausted (reported through the status word)
+      const ChildRef ra = child_ref(a.lsrc[pp][kl], a.codes, a.S, a.pool, a.slot_sites);
+      const ChildRef rb = child_ref(a.rsrc[pp][kl], a.codes, a.S, a.pool, a.slot_sites);
+      const double* Pk = a.P + (e_base + kl) * 32;
+      double* out = a.pool + (int64_t)ds * a.slot_sites * 4;
+      if (a.jc) {
+        Trans<true> Pl, Pr;
+        Pl.load(Pk);
+        Pr.load(Pk + 16);
+#pragma unroll
+        for (int q = 0; q < kMatSptEv; ++q) {
+          const int s = t * (kEvThreads * kMatSptEv) + q * kEvThreads + tid;
+          if (s < a.S) {
+            const d4 lp = Pl.apply(load_child(ra, s)), rp = Pr.apply(load_child(rb, s));
+            d4 nw;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) nw.v[i] = lp.v[i] * rp.v[i];
+            st_site(out + (int64_t)s * 4, nw);
+          }
+        }
+      } else {
+        Trans<false> Pl, Pr;
+        Pl.load(Pk);
+        Pr.load(Pk + 16);
+#pragma unroll
+        for (int q = 0; q < kMatSptEv; ++q) {
+          const int s = t * (kEvThreads * kMatSptEv) + q * kEvThreads + tid;
+          if (s < a.S) {
+            const d4 lp = Pl.apply(load_child(ra, s)), rp = Pr.apply(load_child(rb, s));
+            d4 nw;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) nw.v[i] = lp.v[i] * rp.v[i];
+            st_site(out + (int64_t)s * 4, nw);
+          }
+        }
+      }
+    }
+  }
+  for (int64_t base = (int64_t)blockIdx.x * kEvThreads; base < Kl; base += gthreads)
+    propose_particle(a, base + tid, base + tid < Kl, lane);
+  if (a.sorted && last_cta(a.counts + 4, &s_flag)) {
+    // group order is irrelevant, so offsets need no scan: every occupied slot reserves its range with one atomic
+    const int n_occ = ((volatile int32_t*)a.counts)[2];
+    for (int i = tid; i < n_occ; i += kEvThreads) {
+      const int s = ((volatile int32_t*)a.gocc)[i];
+      a.goff[s] = atomicAdd(a.gcount, ((volatile int32_t*)a.gcnt)[s]);
+    }
+  }
+  if (a.world > 1) cross_sync(a, a.bar_index + 2, grid);
+  else grid.sync();
+  // ---- phase 8: grouped visiting order; particle sharding: pull the missing nodes out of the owners' pools
+  if (a.sorted) {
+    for (int64_t kl = gtid; kl < Kl; kl += gthreads) {
+      const int s = a.gslot[kl];
+      if (s >= 0) a.order[a.goff[s] + a.grank[kl]] = (int32_t)kl;
+    }
+  }
+  if (a.world > 1 && r > 0) {
+    const int n_fetch = a.counts[1] < a.fetch_cap ? a.counts[1] : (int)a.fetch_cap;
+    const int tiles = (a.S + kEvThreads * 4 - 1) / (kEvThreads * 4);
+    for (int64_t w = blockIdx.x; w < (int64_t)n_fetch * tiles; w += gridDim.x) {
+      const int64_t j = w / tiles;
+      const int t = (int)(w - j * tiles);
+      const int e = a.fetch_e[j], g = a.fetch_src[j];
+      const int ds = a.loc[e];
+      const int ss = a.peer_loc[g][e];
+      if (ds < 0 || ss < 0) continue;
+      const double* src = a.peer_pool[g] + (int64_t)ss * a.slot_sites * 4;
+      double* dst = a.pool + (int64_t)ds * a.slot_sites * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int s = t * (kEvThreads * 4) + q * kEvThreads + tid;
+        if (s < a.S) st_site(dst + (int64_t)s * 4, ld_site(src + (int64_t)s * 4));
+      }
     }
   }
 }
 
-// child slots of the own particles, once the allocator / the pulls have placed every node
-__global__ void lz_resolve_kernel(int64_t Kl, int N, const int32_t* __restrict__ lref, const int32_t* __restrict__ rref,
-                                  const int32_t* __restrict__ loc, int32_t* __restrict__ lsrc, int32_t* __restrict__ rsrc) {
-  const int64_t kl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (kl >= Kl) return;
-  const int l = lref[kl], r = rref[kl];
-  lsrc[kl] = l < N ? -(l + 1) : loc[l - N];
-  rsrc[kl] = r < N ? -(r + 1) : loc[r - N];
-}
-
-struct LzWeightArgs {
-  int r, n, tiles;
-  int64_t Kl;
-  const double* ell_part;
-  double* F;            // [Kl] in: forest sum without the new node; out: with it
-  const double* topo;   // [Kl]
-  const int32_t* vm;    // [Kl]
-  const double* lam_l;
-  const double* lam_r;
-  const double* b_l;    // own columns of row r
-  const double* b_r;
-  const double* cum_l_prev;
-  const double* cum_r_prev;
-  double* cum_l;
-  double* cum_r;
-  const double* ll_tilde;
-  double* ell_new;      // ell_node + N + r*K + k0
-  double* lw;
-  double* LL;
-  int32_t* vminus;
-  double q;
-};
-
-// forest posterior from the running sums + branch priors + v^- + weight (vcsmc.py:376-395), O(1) per particle
-__global__ void lz_weights_kernel(const LzWeightArgs a) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= a.Kl) return;
-  const int r = a.r;
-  double ell = 0.0;
-  for (int t = 0; t < a.tiles; ++t) ell += a.ell_part[k * a.tiles + t];
-  a.ell_new[k] = ell;
-  const double F = a.F[k] + ell;
-  a.F[k] = F;
-  const int vm = a.vm[k];
-  const double laml = a.lam_l[r], lamr = a.lam_r[r];
-  const double bl = a.b_l[k], br = a.b_r[k];
-  const double cl = (r > 0 ? a.cum_l_prev[k] : 0.0) + bl;   // quirk Q1: slot-wise, un-resampled histories
-  const double cr = (r > 0 ? a.cum_r_prev[k] : 0.0) + br;
-  a.cum_l[k] = cl;
-  a.cum_r[k] = cr;
-  const double llog = log(laml), rlog = log(lamr);
-  // quirk Q2: the CURRENT step's rate multiplies ALL earlier branches (vcsmc.py:380-383)
-  const double LLr = (F + a.topo[k]) + (-laml * cl + (double)(r + 1) * llog) + (-lamr * cr + (double)(r + 1) * rlog);
-  // quirk Q3: q = 1/C(n,2) is subtracted raw (vcsmc.py:298,392)
-  const double lw = LLr - a.ll_tilde[k] - (llog - laml * bl + rlog - lamr * br) + log((double)vm) - a.q;
-  a.LL[k] = LLr;
-  a.lw[k] = lw;
-  a.vminus[k] = vm;
-}
-
-// ---- the per-event record that is all-gathered across ranks (field-major inside a rank's chunk)
-struct RecArgs {
-  int n, rank;
-  int64_t Kl, k0, K, stride;
-  char* rec;
-  const char* peer_rec[kMaxPeers];  // null: every chunk has been gathered into `rec` (collective hook); else read chunk g from peer g
-  double* lw;
-  double* LL;
-  double* ell;  // ell_node + N + r*K
-  double* b_l;
-  double* b_r;
-  double* cum_l;
-  double* cum_r;
-  double* t2;
-  int32_t* lref;
-  int32_t* rref;
-  int32_t* nleaf;
-  int32_t* vminus;
-  uint8_t* rempos;
-};
-
-// Cross-GPU barrier without the host: lane g stores this rank's epoch into peer g's flag array (peer store over
-// NVLink, system scope) and then spins until peer g's epoch has arrived in this rank's own array.  Every GPU runs
-// its own stream, so the store a lane waits for never depends on this kernel.  A timeout (~30 s) turns a lost peer
-// into a reported error instead of a hang.
-struct SigArgs {
-  int32_t* peer_sig[kMaxPeers];  // peer g's flag array (own array at index rank)
-  int rank, world, index;        // this is the index-th barrier since the epoch base was last advanced
-  const int32_t* epoch_base;     // device-resident, advanced at the end of every forward (a replayed graph stays monotonic)
-  int32_t* status;
-};
-
-__global__ void lz_barrier_kernel(const SigArgs a) {
-  const int g = threadIdx.x;
-  if (g >= a.world) return;
-  const int epoch = *a.epoch_base + a.index;
-  __threadfence_system();
-  volatile int32_t* out = a.peer_sig[g] + a.rank;
-  *out = epoch;
-  __threadfence_system();
-  volatile int32_t* in = a.peer_sig[a.rank] + g;
-  const long long t0 = clock64();
-  while (*in - epoch < 0) {
-    if (clock64() - t0 > 60000000000ll) {   // ~30 s at 1.9 GHz
-      a.status[0] = VCSMC_ERR_STATE;
-      break;
-    }
-    __nanosleep(200);
-  }
-  __threadfence_system();
-}
-
-__global__ void lz_advance_kernel(int32_t* epoch_base, int n) { *epoch_base += n; }
 __global__ void lz_set_seed_kernel(uint64_t* seed_dev, uint64_t seed) { *seed_dev = seed; }
-
-__global__ void lz_pack_kernel(const RecArgs a) {
-  const int64_t kl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (kl >= a.Kl) return;
-  const int64_t k = a.k0 + kl;
-  char* base = a.rec + (int64_t)a.rank * a.stride;
-  double* d = reinterpret_cast<double*>(base);
-  d[0 * a.Kl + kl] = a.lw[k];
-  d[1 * a.Kl + kl] = a.LL[k];
-  d[2 * a.Kl + kl] = a.ell[k];
-  d[3 * a.Kl + kl] = a.b_l[k];
-  d[4 * a.Kl + kl] = a.b_r[k];
-  d[5 * a.Kl + kl] = a.cum_l[k];
-  d[6 * a.Kl + kl] = a.cum_r[k];
-  int32_t* q = reinterpret_cast<int32_t*>(base + 56 * a.Kl);
-  q[0 * a.Kl + kl] = a.lref[k];
-  q[1 * a.Kl + kl] = a.rref[k];
-  q[2 * a.Kl + kl] = a.nleaf[k];
-  q[3 * a.Kl + kl] = a.vminus[k];
-  uint8_t* b = reinterpret_cast<uint8_t*>(base + 72 * a.Kl);
-  const int m = a.n - 2;
-  for (int p = 0; p < m; ++p) b[kl * m + p] = a.rempos[k * m + p];
-}
-
-__global__ void lz_unpack_kernel(const RecArgs a) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= a.K) return;
-  const int g = (int)(k / a.Kl);
-  if (g == a.rank) return;
-  const int64_t kl = k - (int64_t)g * a.Kl;
-  const char* base = (a.peer_rec[g] ? a.peer_rec[g] : a.rec) + (int64_t)g * a.stride;
-  const double* d = reinterpret_cast<const double*>(base);
-  a.lw[k] = d[0 * a.Kl + kl];
-  a.LL[k] = d[1 * a.Kl + kl];
-  a.ell[k] = d[2 * a.Kl + kl];
-  const double bl = d[3 * a.Kl + kl], br = d[4 * a.Kl + kl];
-  a.b_l[k] = bl;
-  a.b_r[k] = br;
-  a.t2[2 * k] = bl;
-  a.t2[2 * k + 1] = br;
-  a.cum_l[k] = d[5 * a.Kl + kl];
-  a.cum_r[k] = d[6 * a.Kl + kl];
-  const int32_t* q = reinterpret_cast<const int32_t*>(base + 56 * a.Kl);
-  a.lref[k] = q[0 * a.Kl + kl];
-  a.rref[k] = q[1 * a.Kl + kl];
-  a.nleaf[k] = q[2 * a.Kl + kl];
-  a.vminus[k] = q[3 * a.Kl + kl];
-  const uint8_t* b = reinterpret_cast<const uint8_t*>(base + 72 * a.Kl);
-  const int m = a.n - 2;
-  for (int p = 0; p < m; ++p) a.rempos[k * m + p] = b[kl * m + p];
-}
-
-__global__ void lz_lltilde_kernel(int64_t K, int N, const double* __restrict__ LL, const int32_t* __restrict__ anc,
-                                  double* __restrict__ ll_tilde) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
-  ll_tilde[k] = N >= 3 ? LL[(int64_t)(N - 3) * K + anc[(int64_t)(N - 2) * K + k]] : log(1.0 / (double)K);
-}
 
 __global__ void lz_iota_kernel(int32_t* p, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = (int32_t)i;
 }
 
-}  // namespace
-
-namespace {
-// all ranks' earlier work on `st` is complete (and visible to peers) before any rank's later work starts
-int cross_rank_barrier(vcsmc_sweep* h, int* n_barriers, cudaStream_t st) {
-  if (!h->peer_sync) {
-    if (h->comm(h->comm_user, VCSMC_COMM_BARRIER, nullptr, 0, st)) { set_error("comm hook failed (barrier)"); return VCSMC_ERR_CUDA; }
-    return VCSMC_OK;
-  }
-  SigArgs a;
-  for (int g = 0; g < kMaxPeers; ++g) a.peer_sig[g] = g < h->world ? reinterpret_cast<int32_t*>(h->peer_ws[g] + h->o_sig) : nullptr;
-  a.rank = h->rank; a.world = h->world; a.index = ++*n_barriers; a.epoch_base = h->p<int32_t>(h->o_epoch_dev);
-  a.status = h->p<int32_t>(h->o_status);
-  lz_barrier_kernel<<<1, 32, 0, st>>>(a);
-  VCSMC_LAUNCH_CHECK("lz_barrier_kernel");
+template <int NQ>
+int launch_event(const EvArgs& a, int blocks, size_t smem, cudaStream_t st) {
+  void* kargs[] = {(void*)&a};
+  VCSMC_CUDA(cudaLaunchCooperativeKernel((const void*)lz_event_kernel<NQ>, dim3((unsigned)blocks), dim3(kEvThreads), kargs, smem, st));
+  count_launch();
+  if (debug_sync()) VCSMC_CUDA(cudaDeviceSynchronize());
   return VCSMC_OK;
 }
-}  // namespace
 
-namespace {
+template <int NQ>
+int event_blocks(size_t smem, int* out) {
+  int per_sm = 0, sms = 0, dev = 0;
+  VCSMC_CUDA(cudaGetDevice(&dev));
+  VCSMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  VCSMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz_event_kernel<NQ>, kEvThreads, smem));
+  if (per_sm < 1) { set_error("lz_event_kernel cannot be launched cooperatively"); return VCSMC_ERR_CUDA; }
+  if (per_sm > 2) per_sm = 2;   // more CTAs only make the grid barriers slower
+  *out = per_sm * sms;
+  return VCSMC_OK;
+}
+
 // the launch sequence of one forward sweep: no host synchronisation, no host-dependent argument -- capturable
 int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l, const double* lam_r, const double* Q,
                       const double* pi, cudaStream_t st) {
   const int N = h->N, S = h->S, G = h->world;
-  int n_barriers = 0;
   const int64_t K = h->K, Kl = h->Kl, k0 = h->k0, E = (int64_t)(N - 1) * K;
   const bool gc = h->fwd_gc;
   int rc;
   if (G > 1 && !gc) { set_error("particle sharding runs on the garbage-collected pool"); return VCSMC_ERR_STATE; }
+  if (G > 1 && !h->peer_sync) { set_error("particle sharding synchronises over peer memory (peer_sync = 1)"); return VCSMC_ERR_STATE; }
   if (!h->use_seed && h->x_look_bl != nullptr) { set_error("uniforms were set for the other proposal (nested vs plain)"); return VCSMC_ERR_STATE; }
 
   int32_t* status = h->p<int32_t>(h->o_status);
@@ -705,217 +959,128 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     if (rc) return rc;
     leaf_hist = h->p<int32_t>(h->o_leaf_hist);
   }
-  double* pool = h->p<double>(h->o_pool);
-  int32_t* flags = h->p<int32_t>(h->o_flags);
-  int32_t* loc = h->p<int32_t>(h->o_loc);
-  int32_t* slot_id = gc ? h->p<int32_t>(h->o_slot_id) : nullptr;
-  int32_t* pend = h->p<int32_t>(h->o_pend);
-  int32_t* surv = h->p<int32_t>(h->o_surv);
-  int32_t* counts = h->p<int32_t>(h->o_counts);
-  int32_t* mat_list = h->p<int32_t>(h->o_mat_list);
-  int32_t* fetch_e = h->p<int32_t>(h->o_fetch_e);
-  int32_t* fetch_src = h->p<int32_t>(h->o_fetch_src);
-  int32_t* inh_ids = h->p<int32_t>(h->o_lz_ids);
-  int32_t* inh_cnt = h->p<int32_t>(h->o_lz_cnt);
-  int32_t* lsrc = h->p<int32_t>(h->o_lsrc);
-  int32_t* rsrc = h->p<int32_t>(h->o_rsrc);
-  double* ll_tilde = h->p<double>(h->o_lltilde);
+  const bool sorted = use_sorted_order(Kl, S);
+  const int64_t T = group_table_entries(Kl);
+  int log2T = 0;
+  while (((int64_t)1 << log2T) < T) ++log2T;
+
+  EvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.N = N; a.S = S; a.jc = h->jc; a.gc = gc; a.rank = h->rank; a.world = G; a.sorted = sorted;
+  a.skip_leaf_pairs = leaf_hist != nullptr; a.row_stride = (N + 3) & ~3; a.log2T = log2T;
+  a.K = K; a.Kl = Kl; a.k0 = k0; a.pool_slots = h->pool_slots; a.fetch_cap = h->fetch_cap; a.slot_sites = S;
+  a.lam_l = lam_l; a.lam_r = lam_r; a.Q = Q; a.pi = pi; a.ldf = h->p<double>(h->o_ldf);
+  a.seed_dev = h->p<uint64_t>(h->o_seed_dev); a.codes = codes;
+  a.anc = h->p<int32_t>(h->o_anc); a.lref = h->p<int32_t>(h->o_lref); a.rref = h->p<int32_t>(h->o_rref); a.nleaf = h->p<int32_t>(h->o_nleaf);
+  a.b_l = h->p<double>(h->o_b_l); a.b_r = h->p<double>(h->o_b_r); a.t2 = h->p<double>(h->o_t2);
+  a.cum_l = h->p<double>(h->o_cum_l); a.cum_r = h->p<double>(h->o_cum_r); a.lw = h->p<double>(h->o_lw); a.LL = h->p<double>(h->o_LL);
+  a.P = h->p<double>(h->o_P); a.ell_node = ell_node; a.stats = h->p<double>(h->o_stats);
+  a.pF = h->p<double>(h->o_pF); a.pT = h->p<double>(h->o_pT); a.pV = h->p<int32_t>(h->o_pV); a.pLLt = h->p<double>(h->o_pLLt);
+  a.vminus = h->p<int32_t>(h->o_vminus);
+  a.lsrc[0] = h->p<int32_t>(h->o_lsrc); a.rsrc[0] = h->p<int32_t>(h->o_rsrc);
+  a.lsrc[1] = h->p<int32_t>(h->o_lsrc2); a.rsrc[1] = h->p<int32_t>(h->o_rsrc2);
+  for (int i = 0; i < 2; ++i) {
+    a.row_ids[i] = h->p<int32_t>(h->o_ids[i]); a.row_cnt[i] = h->p<int32_t>(h->o_cnt[i]);
+    a.row_F[i] = h->p<double>(h->o_F[i]); a.row_T[i] = h->p<double>(h->o_topo[i]); a.row_V[i] = h->p<int32_t>(h->o_vm[i]);
+  }
+  a.F0 = h->p<double>(h->o_F0);
+  a.cdf = h->p<double>(h->o_cdf); a.cdf_scratch = h->p<double>(h->o_cdf_scratch);
+  a.live = h->p<int32_t>(h->o_live); a.surv = h->p<int32_t>(h->o_surv); a.haskid = h->p<int32_t>(h->o_haskid);
+  a.pool = h->p<double>(h->o_pool); a.flags = h->p<int32_t>(h->o_flags); a.loc = h->p<int32_t>(h->o_loc);
+  a.slot_id = gc ? h->p<int32_t>(h->o_slot_id) : nullptr; a.pend = h->p<int32_t>(h->o_pend);
+  a.mat_list = h->p<int32_t>(h->o_mat_list); a.fetch_e = h->p<int32_t>(h->o_fetch_e); a.fetch_src = h->p<int32_t>(h->o_fetch_src);
+  a.counts = h->p<int32_t>(h->o_counts); a.status = status;
+  a.gtab = h->p<unsigned long long>(h->o_gtab); a.gcnt = h->p<int32_t>(h->o_gcnt); a.goff = h->p<int32_t>(h->o_goff);
+  a.gslot = h->p<int32_t>(h->o_gslot); a.grank = h->p<int32_t>(h->o_grank); a.gocc = h->p<int32_t>(h->o_gocc);
+  a.order = h->p<int32_t>(h->o_order); a.gcount = h->p<int32_t>(h->o_count);
+  a.llR = h->p<double>(h->o_llR); a.ll_tilde_out = h->p<double>(h->o_lltilde); a.elbo = h->p<double>(h->o_elbo);
+  a.logz = h->p<double>(h->o_logz); a.ess = h->p<double>(h->o_ess); a.ldf_root = log_double_factorial_host(2 * N - 3);
+  a.rec = h->p<char>(h->o_rec); a.rec_stride = h->rec_stride; a.epoch_base = h->p<int32_t>(h->o_epoch_dev);
+  for (int g = 0; g < kMaxPeers; ++g) {
+    const bool on = g < G && G > 1;
+    a.peer_rec[g] = on ? h->peer_ws[g] + h->o_rec : nullptr;
+    a.peer_sig[g] = on ? reinterpret_cast<int32_t*>(h->peer_ws[g] + h->o_sig) : nullptr;
+    a.peer_loc[g] = on ? reinterpret_cast<const int32_t*>(h->peer_ws[g] + h->o_loc) : nullptr;
+    a.peer_pool[g] = on ? reinterpret_cast<const double*>(h->peer_ws[g] + h->o_pool) : nullptr;
+  }
+  a.n_barriers_total = 2 * N;   // every launch reserves two barrier indices
+
+  // scratch every launch relies on: the node -> slot map, the hash table, counters
   if (gc) {
-    VCSMC_CUDA(cudaMemsetAsync(loc, 0xFF, E * sizeof(int32_t), st));
-    VCSMC_CUDA(cudaMemsetAsync(slot_id, 0xFF, (size_t)h->pool_slots * sizeof(int32_t), st));
-    count_launch(2);
+    VCSMC_CUDA(cudaMemsetAsync(a.loc, 0xFF, E * sizeof(int32_t), st));
+    VCSMC_CUDA(cudaMemsetAsync(a.slot_id, 0xFF, (size_t)h->pool_slots * sizeof(int32_t), st));
+    VCSMC_CUDA(cudaMemsetAsync(a.flags, 0, (size_t)h->pool_slots * sizeof(int32_t), st));   // (the launches re-zero below the running peak only)
+    count_launch(3);
   } else {
-    lz_iota_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(loc, E);  // direct map: node e lives in slot e
+    lz_iota_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(a.loc, E);  // direct map: node e lives in slot e
     VCSMC_LAUNCH_CHECK("lz_iota_kernel");
   }
   if (G > 1) {
-    VCSMC_CUDA(cudaMemsetAsync(pend, 0xFF, E * sizeof(int32_t), st));
+    VCSMC_CUDA(cudaMemsetAsync(a.pend, 0xFF, E * sizeof(int32_t), st));
     count_launch();
   }
-  const bool sorted = use_sorted_order(Kl, S);
+  VCSMC_CUDA(cudaMemsetAsync(a.counts, 0, 8 * sizeof(int32_t), st));
+  VCSMC_CUDA(cudaMemsetAsync(a.gcount, 0, sizeof(int32_t), st));
+  if (sorted) {
+    VCSMC_CUDA(cudaMemsetAsync(a.gtab, 0, (size_t)T * sizeof(unsigned long long), st));
+    VCSMC_CUDA(cudaMemsetAsync(a.gcnt, 0, (size_t)T * sizeof(int32_t), st));
+  }
+  count_launch(4);
+
+  const int NQ = N <= 32 ? 1 : N <= 64 ? 2 : N <= 128 ? 4 : 8;
+  const size_t smem = (size_t)kEvWarps * a.row_stride * sizeof(float);
+  int blocks = 0;
+  rc = NQ == 1 ? event_blocks<1>(smem, &blocks) : NQ == 2 ? event_blocks<2>(smem, &blocks) : NQ == 4 ? event_blocks<4>(smem, &blocks) : event_blocks<8>(smem, &blocks);
+  if (rc) return rc;
+  {
+    // no more CTAs than there is work for the widest phase (a warp per particle), at least one
+    const int64_t want = (K + kEvWarps - 1) / kEvWarps;
+    if (want < blocks) blocks = (int)(want < 1 ? 1 : want);
+  }
+
   int64_t pair_off = 0;
-
-  for (int r = 0; r < N - 1; ++r) {
+  for (int r = 0; r <= N - 1; ++r) {
     const int n = N - r;
-    const int cur = r & 1, prev = cur ^ 1;
-    // ---- uniforms: pair / branch draws of the rank's own particles, resampling draws of ALL particles
-    const float* u_pair;
-    const double *u_bl, *u_br, *u_res_all;
+    a.r = r;
+    a.bar_index = 2 * r;
     if (h->use_seed) {
-      u_pair = nullptr; u_bl = nullptr; u_br = nullptr;   // drawn inside lz_propose_kernel / lz_ancestors_kernel
-      u_res_all = nullptr;
+      a.u_pair_prev = nullptr; a.u_pair_cur = nullptr; a.u_bl = nullptr; a.u_br = nullptr; a.u_res = nullptr;
     } else {
-      u_pair = h->x_pair + pair_off + k0 * n; u_bl = h->x_bl + (int64_t)r * K + k0; u_br = h->x_br + (int64_t)r * K + k0;
-      u_res_all = h->x_res + (int64_t)r * K;
-      pair_off += K * n;
+      a.u_pair_prev = r > 0 ? h->x_pair + (pair_off - K * (int64_t)(n + 1)) : nullptr;
+      a.u_pair_cur = r < N - 1 ? h->x_pair + pair_off : nullptr;
+      a.u_bl = r < N - 1 ? h->x_bl + (int64_t)r * K : nullptr;
+      a.u_br = r < N - 1 ? h->x_br + (int64_t)r * K : nullptr;
+      a.u_res = r < N - 1 ? h->x_res + (int64_t)r * K : nullptr;
+      pair_off += K * (int64_t)n;
     }
-    int32_t* anc_row = h->p<int32_t>(h->o_anc) + (int64_t)r * K;
-    int32_t* ids_prev = h->p<int32_t>(h->o_ids[prev]);
-    int32_t* ids_cur = h->p<int32_t>(h->o_ids[cur]);
-    int32_t* cnt_cur = h->p<int32_t>(h->o_cnt[cur]);
-    int32_t* row_lref = h->p<int32_t>(h->o_lref) + (int64_t)r * K;
-    int32_t* row_rref = h->p<int32_t>(h->o_rref) + (int64_t)r * K;
-    int32_t* row_nleaf = h->p<int32_t>(h->o_nleaf) + (int64_t)r * K;
-    uint8_t* row_rempos = h->p<uint8_t>(h->o_rempos) + h->rem_off[r];
-    double* row_b_l = h->p<double>(h->o_b_l) + (int64_t)r * K;
-    double* row_b_r = h->p<double>(h->o_b_r) + (int64_t)r * K;
-    double* row_t2 = h->p<double>(h->o_t2) + (int64_t)r * 2 * K;
-    // inherit + propose for the rank's own particles (reads the rows and forest scalars event r-1 left behind)
-    auto launch_propose = [&]() -> int {
-      ProposeArgs a;
-      a.r = r; a.n = n; a.N = N; a.gc = gc; a.rank = h->rank; a.row_stride = (N + 3) & ~3;
-      a.K = K; a.Kl = Kl; a.k0 = k0; a.fetch_cap = h->fetch_cap; a.anc = anc_row;
-      for (int g = 0; g < kMaxPeers; ++g) {
-        const bool on = g < G;
-        a.peer_ids[g] = on ? reinterpret_cast<const int32_t*>(h->peer_ws[g] + h->o_ids[prev]) : nullptr;
-        a.peer_cnt[g] = on ? reinterpret_cast<const int32_t*>(h->peer_ws[g] + h->o_cnt[prev]) : nullptr;
-        a.peer_F[g] = on ? reinterpret_cast<const double*>(h->peer_ws[g] + h->o_F[prev]) : nullptr;
-        a.peer_topo[g] = on ? reinterpret_cast<const double*>(h->peer_ws[g] + h->o_topo[prev]) : nullptr;
-        a.peer_vm[g] = on ? reinterpret_cast<const int32_t*>(h->peer_ws[g] + h->o_vm[prev]) : nullptr;
-      }
-      a.loc = loc; a.slot_id = slot_id; a.flags = flags; a.pend = pend; a.fetch_e = fetch_e; a.fetch_src = fetch_src;
-      a.counts = counts; a.status = status;
-      a.u_pair = u_pair; a.u_bl = u_bl; a.u_br = u_br; a.seed_dev = h->p<uint64_t>(h->o_seed_dev);
-      a.lam_l = lam_l; a.lam_r = lam_r; a.ell_node = ell_node; a.ldf = h->p<double>(h->o_ldf);
-      a.LL_prev = r > 0 ? h->p<double>(h->o_LL) + (int64_t)(r - 1) * K : nullptr;
-      a.ids_new = ids_cur; a.cnt_new = cnt_cur;
-      a.F_new = h->p<double>(h->o_F[cur]); a.topo_new = h->p<double>(h->o_topo[cur]); a.vm_new = h->p<int32_t>(h->o_vm[cur]);
-      a.lref = row_lref; a.rref = row_rref; a.nleaf = row_nleaf; a.rempos = row_rempos;
-      a.b_l = row_b_l; a.b_r = row_b_r; a.t2 = row_t2; a.ll_tilde = ll_tilde;
-      const unsigned grid = (unsigned)((Kl + kProposeWarps - 1) / kProposeWarps);
-      const size_t smem = (size_t)kProposeWarps * a.row_stride * sizeof(float);
-      if (N <= 64) lz_propose_kernel<2><<<grid, kProposeWarps * 32, smem, st>>>(a);
-      else lz_propose_kernel<8><<<grid, kProposeWarps * 32, smem, st>>>(a);
-      VCSMC_LAUNCH_CHECK("lz_propose_kernel");
-      return VCSMC_OK;
-    };
-
-    if (r > 0) {
-      VCSMC_CUDA(cudaMemsetAsync(surv, 0, K * sizeof(int32_t), st));
-      VCSMC_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(int32_t), st));
-      if (gc) VCSMC_CUDA(cudaMemsetAsync(flags, 0, (size_t)h->pool_slots * sizeof(int32_t), st));
-      count_launch(3);
-    }
-    lz_ancestors_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(r == 0, K, h->p<double>(h->o_cdf), u_res_all, h->p<uint64_t>(h->o_seed_dev), r, anc_row, surv);
-    VCSMC_LAUNCH_CHECK("lz_ancestors_kernel");
-    if (r > 0) {
-      const int64_t e_base_prev = (int64_t)(r - 1) * K + k0;
-      SurvArgs sa;
-      sa.n = n; sa.N = N; sa.gc = gc; sa.Kl = Kl; sa.k0 = k0; sa.surv = surv; sa.ids_prev = ids_prev; sa.lsrc_prev = lsrc;
-      sa.rsrc_prev = rsrc; sa.loc = loc; sa.flags = flags; sa.mat_list = mat_list; sa.counts = counts;
-      lz_survivors_kernel<<<(unsigned)((Kl * (n + 2) + 255) / 256), 256, 0, st>>>(sa);
-      VCSMC_LAUNCH_CHECK("lz_survivors_kernel");
-      rc = launch_propose(); if (rc) return rc;
-      if (gc) {
-        lz_alloc_kernel<<<1, 1024, 0, st>>>(flags, h->pool_slots, counts, h->fetch_cap, mat_list, e_base_prev, fetch_e, loc, slot_id, status);
-        VCSMC_LAUNCH_CHECK("lz_alloc_kernel");
-      }
-      // the survivors' nodes: children, P and slots of rank event r-1 are still in place
-      h->prof_begin(3, st);
-      rc = launch_materialise(codes, S, pool, S, lsrc, rsrc, mat_list, counts, Kl, loc, e_base_prev,
-                              h->p<double>(h->o_P) + ((int64_t)(r - 1) * K + k0) * 32, S, h->jc, st);
-      if (rc) return rc;
-      if (G > 1) {
-        rc = cross_rank_barrier(h, &n_barriers, st);
-        if (rc) return rc;
-        const int32_t* peer_loc[kMaxPeers];
-        const double* peer_pool[kMaxPeers];
-        for (int g = 0; g < G; ++g) {
-          peer_loc[g] = reinterpret_cast<const int32_t*>(h->peer_ws[g] + h->o_loc);
-          peer_pool[g] = reinterpret_cast<const double*>(h->peer_ws[g] + h->o_pool);
-        }
-        rc = launch_pull(fetch_e, fetch_src, counts + 1, h->fetch_cap < Kl * n ? h->fetch_cap : Kl * n, loc, pool, S, S, G,
-                         peer_loc, peer_pool, st);
-        if (rc) return rc;
-      }
-      h->prof_end(st);
-    }
-
-    if (r == 0) {
-      rc = launch_propose();
-      if (rc) return rc;
-    }
-    lz_resolve_kernel<<<(unsigned)((Kl + 255) / 256), 256, 0, st>>>(Kl, N, row_lref + k0, row_rref + k0, loc, lsrc, rsrc);
-    VCSMC_LAUNCH_CHECK("lz_resolve_kernel");
-
-    double* P = h->p<double>(h->o_P) + ((int64_t)r * K + k0) * 32;
-    rc = launch_transition_fwd(Q, row_t2 + 2 * k0, 2 * Kl, h->jc, P, st);
-    if (rc) return rc;
-    if (sorted) {
-      rc = group_particles(h, lsrc, rsrc, nullptr, Kl, h->p<int32_t>(h->o_order), h->p<int32_t>(h->o_count), st, leaf_hist != nullptr);
-      if (rc) return rc;
-    }
-    int tiles = 0;
-    h->prof_begin(0, st);
-    rc = launch_merge_score(codes, S, pool, S, lsrc, rsrc, sorted ? h->p<int32_t>(h->o_order) : nullptr, P, pi, Kl,
-                            sorted ? h->p<int32_t>(h->o_count) : nullptr, S, h->jc,
-                            leaf_hist, N, h->p<double>(h->o_ell_part), &tiles, st);
+    a.rempos_prev = r > 0 ? h->p<uint8_t>(h->o_rempos) + h->rem_off[r - 1] : nullptr;
+    h->prof_begin(3, st);
+    rc = NQ == 1 ? launch_event<1>(a, blocks, smem, st) : NQ == 2 ? launch_event<2>(a, blocks, smem, st)
+       : NQ == 4 ? launch_event<4>(a, blocks, smem, st) : launch_event<8>(a, blocks, smem, st);
     h->prof_end(st);
     if (rc) return rc;
+    if (r == N - 1) break;
 
-    LzWeightArgs w;
-    w.r = r; w.n = n; w.tiles = tiles; w.Kl = Kl;
-    w.ell_part = h->p<double>(h->o_ell_part);
+    // ---- scoring of event r: nothing stored
+    const int cur = r & 1;
+    const double* P = h->p<double>(h->o_P) + ((int64_t)r * K + k0) * 32;
+    int tiles = 0;
+    h->prof_begin(0, st);
+    rc = launch_merge_score(codes, S, h->p<double>(h->o_pool), S, a.lsrc[cur], a.rsrc[cur], sorted ? a.order : nullptr, P, pi, Kl,
+                            sorted ? a.gcount : nullptr, S, h->jc, leaf_hist, N, h->p<double>(h->o_ell_part), &tiles, st);
+    h->prof_end(st);
+    if (rc) return rc;
+    a.ell_part = h->p<double>(h->o_ell_part);
+    a.tiles = tiles;
     if (h->allreduce) {
       rc = launch_ell_reduce(h->p<double>(h->o_ell_part), tiles, Kl, h->p<double>(h->o_ell_new), st);
       if (rc) return rc;
       if (h->allreduce(h->allreduce_user, h->p<double>(h->o_ell_new), Kl, st)) { set_error("allreduce hook failed"); return VCSMC_ERR_CUDA; }
-      w.ell_part = h->p<double>(h->o_ell_new);
-      w.tiles = 1;
+      a.ell_part = h->p<double>(h->o_ell_new);
+      a.tiles = 1;
     }
-    w.F = h->p<double>(h->o_F[cur]); w.topo = h->p<double>(h->o_topo[cur]); w.vm = h->p<int32_t>(h->o_vm[cur]);
-    w.lam_l = lam_l; w.lam_r = lam_r; w.b_l = row_b_l + k0; w.b_r = row_b_r + k0;
-    w.cum_l_prev = r > 0 ? h->p<double>(h->o_cum_l) + (int64_t)(r - 1) * K + k0 : nullptr;
-    w.cum_r_prev = r > 0 ? h->p<double>(h->o_cum_r) + (int64_t)(r - 1) * K + k0 : nullptr;
-    w.cum_l = h->p<double>(h->o_cum_l) + (int64_t)r * K + k0;
-    w.cum_r = h->p<double>(h->o_cum_r) + (int64_t)r * K + k0;
-    w.ll_tilde = ll_tilde;
-    w.ell_new = ell_node + N + (int64_t)r * K + k0;
-    w.lw = h->p<double>(h->o_lw) + (int64_t)r * K + k0;
-    w.LL = h->p<double>(h->o_LL) + (int64_t)r * K + k0;
-    w.vminus = h->p<int32_t>(h->o_vminus) + k0;
-    w.q = 1.0 / ((double)n * (double)(n - 1) / 2.0);
-    lz_weights_kernel<<<(unsigned)((Kl + 127) / 128), 128, 0, st>>>(w);
-    VCSMC_LAUNCH_CHECK("lz_weights_kernel");
-
-    if (G > 1) {
-      RecArgs ra;
-      ra.n = n; ra.rank = h->rank; ra.Kl = Kl; ra.k0 = k0; ra.K = K; ra.stride = h->rec_stride; ra.rec = h->p<char>(h->o_rec);
-      for (int g = 0; g < kMaxPeers; ++g) ra.peer_rec[g] = nullptr;
-      ra.lw = h->p<double>(h->o_lw) + (int64_t)r * K; ra.LL = h->p<double>(h->o_LL) + (int64_t)r * K;
-      ra.ell = ell_node + N + (int64_t)r * K; ra.b_l = row_b_l; ra.b_r = row_b_r;
-      ra.cum_l = h->p<double>(h->o_cum_l) + (int64_t)r * K; ra.cum_r = h->p<double>(h->o_cum_r) + (int64_t)r * K;
-      ra.t2 = row_t2; ra.lref = row_lref; ra.rref = row_rref; ra.nleaf = row_nleaf; ra.vminus = h->p<int32_t>(h->o_vminus);
-      ra.rempos = row_rempos;
-      lz_pack_kernel<<<(unsigned)((Kl + 127) / 128), 128, 0, st>>>(ra);
-      VCSMC_LAUNCH_CHECK("lz_pack_kernel");
-      if (h->peer_sync) {
-        // every rank has packed its chunk: read the other chunks straight out of the peers' record buffers
-        rc = cross_rank_barrier(h, &n_barriers, st);
-        if (rc) return rc;
-        for (int g = 0; g < kMaxPeers; ++g) ra.peer_rec[g] = g < G ? h->peer_ws[g] + h->o_rec : nullptr;
-      } else {
-        if (h->comm(h->comm_user, VCSMC_COMM_ALLGATHER, ra.rec, h->rec_stride, st)) { set_error("comm hook failed (all-gather)"); return VCSMC_ERR_CUDA; }
-      }
-      lz_unpack_kernel<<<(unsigned)((K + 127) / 128), 128, 0, st>>>(ra);
-      VCSMC_LAUNCH_CHECK("lz_unpack_kernel");
-    }
-    // log-sum-exp + CDF of this step's weights over ALL particles (every rank: same input, same fixed order)
-    rc = launch_resample_cdf(h->p<double>(h->o_lw) + (int64_t)r * K, K, h->p<double>(h->o_cdf), h->p<double>(h->o_stats) + r * 4,
-                             h->p<double>(h->o_cdf_scratch), st);
-    if (rc) return rc;
   }
-  if (G > 1) {
-    lz_lltilde_kernel<<<(unsigned)((K + 255) / 256), 256, 0, st>>>(K, N, h->p<double>(h->o_LL), h->p<int32_t>(h->o_anc), ll_tilde);
-    VCSMC_LAUNCH_CHECK("lz_lltilde_kernel");
-  }
-  if (n_barriers > 0) {
-    lz_advance_kernel<<<1, 1, 0, st>>>(h->p<int32_t>(h->o_epoch_dev), n_barriers);
-    VCSMC_LAUNCH_CHECK("lz_advance_kernel");
-  }
-  return launch_finalize(N, K, h->p<double>(h->o_stats), h->p<double>(h->o_LL) + (int64_t)(N - 2) * K, h->p<double>(h->o_b_l),
-                         h->p<double>(h->o_b_r), lam_l, lam_r, log_double_factorial_host(2 * N - 3), h->p<double>(h->o_llR),
-                         h->p<double>(h->o_elbo), h->p<double>(h->o_logz), h->p<double>(h->o_ess), st);
+  return VCSMC_OK;
 }
 }  // namespace
 
@@ -926,6 +1091,8 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
     std::vector<double> ldf(2 * N + 4, 0.0);
     for (int m = 0; m < 2 * N + 4; ++m) ldf[m] = log_double_factorial_host(m);
     VCSMC_CUDA(cudaMemcpy(h->p<double>(h->o_ldf), ldf.data(), ldf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // kept positions of particles that are never rebuilt (weight exactly zero) must still be valid positions
+    VCSMC_CUDA(cudaMemset(h->p<uint8_t>(h->o_rempos), 0, (size_t)(h->rem_off[N - 2] + 16)));
     h->ldf_ready = true;
   }
   // the model lives in the workspace from here on (the reverse sweep reads it too): the caller's tensors may move
@@ -943,7 +1110,7 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
   ++h->forwards;
 
   // a sequence that involves the host (collective hooks, per-launch timing) cannot be captured
-  const bool capturable = h->use_graph && !h->profile && !h->allreduce && (h->world == 1 || h->peer_sync);
+  const bool capturable = h->use_graph && !h->profile && !h->allreduce;
   if (!capturable || h->forwards < 2)   // (the first forward also runs the one-time function-attribute setup)
     return lazy_forward_body(h, codes, lam_l, lam_r, Qm, pi, st);
   const void* key[6] = {codes, h->use_seed ? nullptr : (const void*)h->x_pair, h->use_seed ? nullptr : (const void*)h->x_bl,

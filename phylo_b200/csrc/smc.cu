@@ -151,50 +151,17 @@ __global__ void __launch_bounds__(kCdfThreads) resample_cdf_kernel(const double*
 }
 
 // ---- the same statistics and CDF with ceil(K / 2048) CTAs (four tiny launches instead of one 80 us single-CTA kernel
-// at K = 65,536).  Every reduction runs in a fixed order, so every GPU still derives bit-identical ancestors.
-constexpr int kCdfTile = 2048;  // elements per CTA: 256 threads x 8 consecutive elements
-
-__device__ __forceinline__ double block_reduce_array(const double* p, int n, bool is_max, double* sm) {
-  // every thread returns the same value: strided partials in thread order, then the block tree (fixed order)
-  double v = is_max ? -INFINITY : 0.0;
-  for (int i = threadIdx.x; i < n; i += 256) v = is_max ? fmax(v, p[i]) : v + p[i];
-  v = is_max ? warp_max(v) : warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double t = sm[0];
-#pragma unroll
-  for (int i = 1; i < 8; ++i) t = is_max ? fmax(t, sm[i]) : t + sm[i];
-  __syncthreads();
-  return t;
-}
-
+// at K = 65,536).  Every reduction runs in a fixed order (cdf_stage_* in smc_device.cuh, shared with the lazy forward's
+// event kernel), so every GPU -- and every schedule -- derives bit-identical ancestors.
 __global__ void __launch_bounds__(256) cdf_max_kernel(const double* __restrict__ lw, int64_t K, double* __restrict__ pmax) {
   __shared__ double sm[8];
-  const int64_t b = (int64_t)blockIdx.x * kCdfTile + threadIdx.x;
-  double m = -INFINITY;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) m = fmax(m, b + q * 256 < K ? lw[b + q * 256] : -INFINITY);
-  m = warp_max(m);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double t = sm[0];
-    for (int i = 1; i < 8; ++i) t = fmax(t, sm[i]);
-    pmax[blockIdx.x] = t;
-  }
+  cdf_stage_max((int)blockIdx.x, lw, K, pmax, sm);
 }
 
 __global__ void __launch_bounds__(256) cdf_sumexp_kernel(const double* __restrict__ lw, int64_t K, int nb,
                                                          const double* __restrict__ pmax, double* __restrict__ psum) {
   __shared__ double sm[8];
-  const double M = block_reduce_array(pmax, nb, true, sm);
-  const int64_t b = (int64_t)blockIdx.x * kCdfTile + threadIdx.x;
-  double s = 0.0;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) s += b + q * 256 < K ? exp(lw[b + q * 256] - M) : 0.0;
-  const double t = block_sum<256>(s, sm);
-  if (threadIdx.x == 0) psum[blockIdx.x] = t;
+  cdf_stage_sumexp((int)blockIdx.x, lw, K, nb, pmax, psum, sm);
 }
 
 __global__ void __launch_bounds__(256) cdf_weights_kernel(const double* __restrict__ lw, int64_t K, int nb,
@@ -202,26 +169,7 @@ __global__ void __launch_bounds__(256) cdf_weights_kernel(const double* __restri
                                                           double* __restrict__ w_out, double* __restrict__ pw,
                                                           double* __restrict__ pq) {
   __shared__ double sm[8];
-  const double M = block_reduce_array(pmax, nb, true, sm);
-  const double lse = M + log(block_reduce_array(psum, nb, false, sm));
-  const double mlog = M - lse;  // max of the normalised logits (vcsmc.py:284)
-  const int64_t b = (int64_t)blockIdx.x * kCdfTile + (int64_t)threadIdx.x * 8;   // 8 CONSECUTIVE elements per thread
-  double s = 0.0, q2 = 0.0;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    if (b + q < K) {
-      const double w = exp((lw[b + q] - lse) - mlog);
-      w_out[b + q] = w;
-      s += w;
-      q2 = fma(w, w, q2);
-    }
-  }
-  const double ts = block_sum<256>(s, sm);
-  const double tq = block_sum<256>(q2, sm);
-  if (threadIdx.x == 0) {
-    pw[blockIdx.x] = ts;
-    pq[blockIdx.x] = tq;
-  }
+  cdf_stage_weights((int)blockIdx.x, lw, K, nb, pmax, psum, w_out, pw, pq, nullptr, sm);
 }
 
 __global__ void __launch_bounds__(256) cdf_scan_kernel(int64_t K, int nb, const double* __restrict__ pmax,
@@ -230,43 +178,22 @@ __global__ void __launch_bounds__(256) cdf_scan_kernel(int64_t K, int nb, const 
                                                        double* __restrict__ stats) {
   __shared__ double sm[8];
   __shared__ double wsum[8];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const double offset = block_reduce_array(pw, (int)blockIdx.x, false, sm);   // sum of the tiles before this one
-  const int64_t b = (int64_t)blockIdx.x * kCdfTile + (int64_t)tid * 8;
-  double w[8], run = 0.0;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    w[q] = b + q < K ? cdf[b + q] : 0.0;
-    run += w[q];
-    w[q] = run;  // inclusive inside the thread
-  }
-  double incl = run;  // inclusive scan of the thread totals inside the warp
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) wsum[wid] = incl;
+  cdf_stage_scan((int)blockIdx.x, K, nb, pmax, psum, pw, pq, cdf, stats, sm, wsum);
+}
+
+// small K: the same four stages, tile after tile, by ONE CTA in one launch (identical arithmetic)
+__global__ void __launch_bounds__(256) cdf_one_cta_kernel(const double* __restrict__ lw, int64_t K, int nb, double* __restrict__ scratch,
+                                                          double* __restrict__ cdf, double* __restrict__ stats) {
+  __shared__ double sm[8];
+  __shared__ double wsum[8];
+  double *pmax = scratch, *psum = scratch + nb, *pw = scratch + 2 * nb, *pq = scratch + 3 * nb;
+  for (int vb = 0; vb < nb; ++vb) cdf_stage_max(vb, lw, K, pmax, sm);
   __syncthreads();
-  double wbase = 0.0;
-  for (int i = 0; i < wid; ++i) wbase += wsum[i];
-  const double base = offset + wbase + (incl - run);
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    if (b + q < K) cdf[b + q] = base + w[q];
-  if (blockIdx.x == 0) {
-    __syncthreads();
-    const double M = block_reduce_array(pmax, nb, true, sm);
-    const double lse = M + log(block_reduce_array(psum, nb, false, sm));
-    const double t = block_reduce_array(pw, nb, false, sm);
-    const double q = block_reduce_array(pq, nb, false, sm);
-    if (tid == 0) {
-      stats[0] = lse;
-      stats[1] = t;
-      stats[2] = t * t / q;
-      stats[3] = M;
-    }
-  }
+  for (int vb = 0; vb < nb; ++vb) cdf_stage_sumexp(vb, lw, K, nb, pmax, psum, sm);
+  __syncthreads();
+  for (int vb = 0; vb < nb; ++vb) cdf_stage_weights(vb, lw, K, nb, pmax, psum, cdf, pw, pq, nullptr, sm);
+  __syncthreads();
+  for (int vb = 0; vb < nb; ++vb) cdf_stage_scan(vb, K, nb, pmax, psum, pw, pq, cdf, stats, sm, wsum);
 }
 
 __global__ void resample_search_kernel(const double* __restrict__ cdf, const double* __restrict__ stats,
@@ -328,13 +255,18 @@ int64_t resample_scratch_doubles(int64_t K) { return 4 * ((K + kCdfTile - 1) / k
 
 int launch_resample_cdf(const double* lw, int64_t K, double* cdf, double* stats, double* scratch, cudaStream_t st) {
   if (K <= 0) return VCSMC_OK;
-  if (K <= 2 * kCdfTile || !scratch) {  // small K: one CTA does it all in one launch
+  if (!scratch) {  // no scratch for the tile partials: the single-CTA routine (its own fixed order)
     resample_cdf_kernel<<<1, kCdfThreads, 0, st>>>(lw, K, cdf, stats);
     VCSMC_LAUNCH_CHECK("resample_cdf_kernel");
     return VCSMC_OK;
   }
   const int nb = (int)((K + kCdfTile - 1) / kCdfTile);
   double *pmax = scratch, *psum = scratch + nb, *pw = scratch + 2 * nb, *pq = scratch + 3 * nb;
+  if (nb <= 2) {   // one launch; same arithmetic as the four-launch path and as the lazy forward's event kernel
+    cdf_one_cta_kernel<<<1, 256, 0, st>>>(lw, K, nb, scratch, cdf, stats);
+    VCSMC_LAUNCH_CHECK("cdf_one_cta_kernel");
+    return VCSMC_OK;
+  }
   cdf_max_kernel<<<nb, 256, 0, st>>>(lw, K, pmax);
   VCSMC_LAUNCH_CHECK("cdf_max_kernel");
   cdf_sumexp_kernel<<<nb, 256, 0, st>>>(lw, K, nb, pmax, psum);

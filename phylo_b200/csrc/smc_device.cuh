@@ -49,4 +49,128 @@ __device__ __forceinline__ int upper_bound_cdf(const double* __restrict__ cdf, i
   return (int)(lo < K ? lo : K - 1);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// log-sum-exp, ESS and the categorical CDF of K log-weights in tiles of 2048 elements (resample, vcsmc.py:284-285; also
+// compute_log_ZSMC's reduce_logsumexp, vcsmc.py:276).  Four stages, each needing the previous one's partials of ALL tiles;
+// `vb` is the tile a CTA of exactly 256 threads works on.  Every reduction has a fixed order that depends on K only, so
+// whoever runs the stages (four launches, one CTA, the lazy forward's cooperative event kernel; 1 or 8 GPUs) gets the
+// same bits, hence the same ancestors.
+//   stats[0] = logsumexp(lw), stats[1] = total = cdf[K-1], stats[2] = ESS, stats[3] = max(lw)
+// ---------------------------------------------------------------------------------------------
+constexpr int kCdfTile = 2048;  // elements per tile: 256 threads x 8
+
+__device__ __forceinline__ double block_reduce_array(const double* p, int n, bool is_max, double* sm) {
+  // every thread returns the same value: strided partials in thread order, then the block tree (fixed order)
+  double v = is_max ? -INFINITY : 0.0;
+  for (int i = threadIdx.x; i < n; i += 256) v = is_max ? fmax(v, p[i]) : v + p[i];
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = sm[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) t = is_max ? fmax(t, sm[i]) : t + sm[i];
+  __syncthreads();
+  return t;
+}
+
+__device__ __forceinline__ void cdf_stage_max(int vb, const double* lw, int64_t K, double* pmax, double* sm) {
+  const int64_t b = (int64_t)vb * kCdfTile + threadIdx.x;
+  double m = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) m = fmax(m, b + q * 256 < K ? lw[b + q * 256] : -INFINITY);
+  m = warp_max(m);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = sm[0];
+    for (int i = 1; i < 8; ++i) t = fmax(t, sm[i]);
+    pmax[vb] = t;
+  }
+}
+
+__device__ __forceinline__ void cdf_stage_sumexp(int vb, const double* lw, int64_t K, int nb, const double* pmax, double* psum,
+                                                 double* sm) {
+  const double M = block_reduce_array(pmax, nb, true, sm);
+  const int64_t b = (int64_t)vb * kCdfTile + threadIdx.x;
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s += b + q * 256 < K ? exp(lw[b + q * 256] - M) : 0.0;
+  const double t = block_sum<256>(s, sm);
+  if (threadIdx.x == 0) psum[vb] = t;
+}
+
+// live (optional): 1 where the normalised weight is not zero in double precision -- the particles that can be drawn by
+// the next resampling or carry a gradient
+__device__ __forceinline__ void cdf_stage_weights(int vb, const double* lw, int64_t K, int nb, const double* pmax,
+                                                  const double* psum, double* w_out, double* pw, double* pq, int32_t* live,
+                                                  double* sm) {
+  const double M = block_reduce_array(pmax, nb, true, sm);
+  const double lse = M + log(block_reduce_array(psum, nb, false, sm));
+  const double mlog = M - lse;  // max of the normalised logits (vcsmc.py:284)
+  const int64_t b = (int64_t)vb * kCdfTile + (int64_t)threadIdx.x * 8;   // 8 CONSECUTIVE elements per thread
+  double s = 0.0, q2 = 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (b + q < K) {
+      const double w = exp((lw[b + q] - lse) - mlog);
+      w_out[b + q] = w;
+      if (live) live[b + q] = w != 0.0;
+      s += w;
+      q2 = fma(w, w, q2);
+    }
+  }
+  const double ts = block_sum<256>(s, sm);
+  const double tq = block_sum<256>(q2, sm);
+  if (threadIdx.x == 0) {
+    pw[vb] = ts;
+    pq[vb] = tq;
+  }
+}
+
+__device__ __forceinline__ void cdf_stage_scan(int vb, int64_t K, int nb, const double* pmax, const double* psum,
+                                               const double* pw, const double* pq, double* cdf, double* stats, double* sm,
+                                               double* wsum) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const double offset = block_reduce_array(pw, vb, false, sm);   // sum of the tiles before this one
+  const int64_t b = (int64_t)vb * kCdfTile + (int64_t)tid * 8;
+  double w[8], run = 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    w[q] = b + q < K ? cdf[b + q] : 0.0;
+    run += w[q];
+    w[q] = run;  // inclusive inside the thread
+  }
+  double incl = run;  // inclusive scan of the thread totals inside the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  __syncthreads();
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  double wbase = 0.0;
+  for (int i = 0; i < wid; ++i) wbase += wsum[i];
+  const double base = offset + wbase + (incl - run);
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (b + q < K) cdf[b + q] = base + w[q];
+  if (vb == 0) {
+    __syncthreads();
+    const double M = block_reduce_array(pmax, nb, true, sm);
+    const double lse = M + log(block_reduce_array(psum, nb, false, sm));
+    const double t = block_reduce_array(pw, nb, false, sm);
+    const double q = block_reduce_array(pq, nb, false, sm);
+    if (tid == 0) {
+      stats[0] = lse;
+      stats[1] = t;
+      stats[2] = t * t / q;
+      stats[3] = M;
+    }
+  }
+}
+
 }  // namespace vcsmc

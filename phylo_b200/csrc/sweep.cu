@@ -811,9 +811,16 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_fetch_e = L.take<int32_t>(h->fetch_cap);
     h->o_fetch_src = L.take<int32_t>(h->fetch_cap);
     h->o_counts = L.take<int32_t>(8);
-    h->o_lz_ids = L.take<int32_t>(K * N);
-    h->o_lz_cnt = L.take<int32_t>(K * N);
-    h->o_u_res_all = L.take<double>(K);
+    h->o_pF = L.take<double>(K);      // per-particle work arrays of the event kernel (lazy.cu)
+    h->o_pT = L.take<double>(K);
+    h->o_pV = L.take<int32_t>(K);
+    h->o_pLLt = L.take<double>(K);
+    h->o_lsrc2 = L.take<int32_t>(K);
+    h->o_rsrc2 = L.take<int32_t>(K);
+    h->o_F0 = L.take<double>(2);
+    h->o_live = L.take<int32_t>(K);
+    h->o_haskid = L.take<int32_t>(K);
+    h->o_gocc = L.take<int32_t>(K);
     h->o_leaf_hist = L.take<int32_t>(leaf_pair_hist_ints(N));
     for (int i = 0; i < 2; ++i) {   // forest scalars that travel with a particle (lazy.cu)
       h->o_F[i] = L.take<double>(K);

@@ -216,3 +216,44 @@ def test_training_steps_agree_across_world_sizes(sharding):
         assert f2 == pytest.approx(f1, rel=1e-10)
         for a, b in zip(v2, v1):
             np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-10)
+
+
+def _unseeded_train_worker(rank, world, port, sharding, out):
+    """runner.py's default under torchrun: seed=None.  Every rank must end up with rank 0's seed and slices."""
+    import argparse
+    import math
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    ndev = torch.cuda.device_count()
+    torch.cuda.set_device(rank % ndev)
+    if ndev >= world:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank % ndev))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    from phylo_b200.vcsmc import VCSMC
+    g = synthetic_genome(8, 300, seed=21, gaps=0.02)
+    args = argparse.Namespace(dataset="synthetic", n_particles=64, batch_size=64, learning_rate=0.01, num_epoch=1,
+                              optimizer="GradientDescentOptimizer", branch_prior=math.log(10.0), M=10, nested=False,
+                              jcmodel=False, memory_optimization="on")
+    m = VCSMC({"taxa": ["t%d" % i for i in range(8)], "genome": g}, 64, args, seed=None, sharding=sharding)
+    slices = m.batch_slices(300, 64)
+    res = m.train(epochs=2, batch_size=64, learning_rate=0.01, save=False, verbose=False)
+    out[rank] = (m.seed, slices, res["cost"], [v.detach().cpu().numpy().copy() for v in m.trainable_variables()])
+    m._sweeps.clear()
+    m._last = None
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("sharding", ["particles", "sites"])
+def test_unseeded_training_is_consistent_across_ranks(sharding):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_unseeded_train_worker, args=(2, 29820 + (sharding == "sites"), sharding, out), nprocs=2, join=True)
+    s0, sl0, c0, v0 = out[0]
+    s1, sl1, c1, v1 = out[1]
+    assert s0 == s1 and sl0 == sl1
+    assert np.isfinite(c0).all() and -4000 < c0[0] < -1000
+    np.testing.assert_allclose(c1, c0, rtol=1e-10)
+    for a, b in zip(v1, v0):
+        np.testing.assert_allclose(a, b, rtol=1e-8, atol=1e-10)
