@@ -96,6 +96,7 @@ struct EvArgs {
   // resampling
   double* cdf;
   double* cdf_scratch;
+  long long* lw_max;          // running maximum of the event's log-weights (order-preserving integer image)
   int32_t* live;
   int32_t* surv;
   int32_t* haskid;
@@ -134,7 +135,16 @@ struct EvArgs {
   const int32_t* peer_loc[kMaxPeers];
   const double* peer_pool[kMaxPeers];
   int32_t* epoch_base;
+  unsigned long long* timing;   // optional [N][16] phase time stamps of CTA 0 (option "event_timing"), else null
 };
+
+__device__ __forceinline__ void stamp(const EvArgs& a, int i) {
+  if (a.timing && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.timing[a.r * 16 + i] = t;
+  }
+}
 
 __device__ __forceinline__ int warp_sum_int(int v) {
 #pragma unroll
@@ -189,12 +199,19 @@ __device__ __forceinline__ void cross_sync(const EvArgs& a, int index, cg::grid_
 // phase 1: weights of event r-1 (forest posterior from the row scalars + branch priors + v^- + weight, vcsmc.py:376-395),
 // O(1) per particle; under particle sharding also the rank's chunk of the step record
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void particle_weight(const EvArgs& a, int64_t k) {
+// doubles -> int64 with the same order (NaN aside): the running maximum of the log-weights is kept with atomicMax
+__device__ __forceinline__ long long ordered_bits(double x) {
+  const long long b = __double_as_longlong(x);
+  return b >= 0 ? b : (b ^ 0x7fffffffffffffffll);
+}
+__device__ __forceinline__ double from_ordered_bits(long long b) {
+  return __longlong_as_double(b >= 0 ? b : (b ^ 0x7fffffffffffffffll));
+}
+
+__device__ __forceinline__ double particle_weight(const EvArgs& a, int64_t k, double ell) {
   const int r = a.r - 1;
   const int64_t kl = k - a.k0;
   const int64_t e = (int64_t)r * a.K + k;
-  double ell = 0.0;
-  for (int t = 0; t < a.tiles; ++t) ell += a.ell_part[kl * a.tiles + t];
   a.ell_node[a.N + e] = ell;
   const double F = a.pF[kl] + ell;
   const int vm = a.pV[kl];
@@ -230,16 +247,18 @@ __device__ __forceinline__ void particle_weight(const EvArgs& a, int64_t k) {
     qi[2 * a.Kl + kl] = a.nleaf[e];
     qi[3 * a.Kl + kl] = vm;
   }
+  return lw;
 }
 
-__device__ __forceinline__ void particle_unpack(const EvArgs& a, int64_t k) {
+__device__ __forceinline__ double particle_unpack(const EvArgs& a, int64_t k) {
   const int r = a.r - 1;
   const int g = (int)(k / a.Kl);
   const int64_t kl = k - (int64_t)g * a.Kl;
   const int64_t e = (int64_t)r * a.K + k;
   const char* base = a.peer_rec[g] + (int64_t)g * a.rec_stride;
   const double* d = reinterpret_cast<const double*>(base);
-  a.lw[e] = d[0 * a.Kl + kl];
+  const double lw = d[0 * a.Kl + kl];
+  a.lw[e] = lw;
   a.LL[e] = d[1 * a.Kl + kl];
   a.ell_node[a.N + e] = d[2 * a.Kl + kl];
   const double bl = d[3 * a.Kl + kl], br = d[4 * a.Kl + kl];
@@ -254,6 +273,7 @@ __device__ __forceinline__ void particle_unpack(const EvArgs& a, int64_t k) {
   a.rref[e] = qi[1 * a.Kl + kl];
   a.nleaf[e] = qi[2 * a.Kl + kl];
   a.vminus[k] = qi[3 * a.Kl + kl];
+  return lw;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -690,15 +710,22 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
   if (r > 0) {
     const int64_t e_row = (int64_t)(r - 1) * K;
     double* lw = a.lw + e_row;
-    double *pmax = a.cdf_scratch, *psum = pmax + nb, *pw = psum + nb, *pq = pw + nb;
-    // ---- phase 1: weights of event r-1 (own particles), tile by tile, and the tile maxima
-    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int64_t k = (int64_t)vb * kCdfTile + q * 256 + tid;
-        if (k >= k0 && k < k0 + Kl) particle_weight(a, k);
+    double *psum = a.cdf_scratch + nb, *pw = psum + nb, *pq = pw + nb;
+    // ---- phase 1: weights of event r-1 for the own particles (one thread each; the few partial log-likelihoods of a
+    // particle are summed in a fixed order), and the maximum log-weight (exact in any order: an atomic max on the
+    // order-preserving integer image of the doubles)
+    stamp(a, 0);
+    {
+      double m = -INFINITY;
+      for (int64_t kl = gtid; kl < Kl; kl += gthreads) {
+        double ell = 0.0;
+        for (int t = 0; t < a.tiles; ++t) ell += a.ell_part[kl * a.tiles + t];
+        m = fmax(m, particle_weight(a, k0 + kl, ell));
       }
-      if (a.world == 1) cdf_stage_max(vb, lw, K, pmax, sm);   // (each thread reads back exactly what it wrote)
+      if (a.world == 1) {
+        m = warp_max(m);
+        if (lane == 0 && m > -INFINITY) atomicMax(a.lw_max, ordered_bits(m));
+      }
     }
     // scratch of the coming phases: survivor / child flags, slot flags below the running peak, the hash slots the
     // previous event occupied
@@ -719,17 +746,17 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
       }
     }
     if (a.world > 1) {
+      // the other ranks' chunks of the step record, straight out of their buffers; the own weights join the maximum here
       cross_sync(a, a.bar_index + 1, grid);
-      for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int64_t k = (int64_t)vb * kCdfTile + q * 256 + tid;
-          if (k < K && !(k >= k0 && k < k0 + Kl)) particle_unpack(a, k);
-        }
-        cdf_stage_max(vb, lw, K, pmax, sm);
-      }
+      double m = -INFINITY;
+      for (int64_t k = gtid; k < K; k += gthreads) m = fmax(m, (k >= k0 && k < k0 + Kl) ? lw[k] : particle_unpack(a, k));
+      m = warp_max(m);
+      if (lane == 0 && m > -INFINITY) atomicMax(a.lw_max, ordered_bits(m));
     }
     grid.sync();
+    stamp(a, 1);
+    const double M = from_ordered_bits(*(volatile long long*)a.lw_max);
+    stamp(a, 2);
     // ---- phases 2-4: log-sum-exp, normalised weights + live flags, CDF (resample, vcsmc.py:284-285)
     if (gtid == 0) {
       a.counts[0] = 0;
@@ -737,11 +764,13 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
       a.counts[2] = 0;
       *a.gcount = 0;
     }
-    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_sumexp(vb, lw, K, nb, pmax, psum, sm);
+    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_sumexp(vb, lw, K, M, psum, sm);
     grid.sync();
-    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_weights(vb, lw, K, nb, pmax, psum, a.cdf, pw, pq, a.live, sm);
+    stamp(a, 3);
+    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_weights(vb, lw, K, nb, M, psum, a.cdf, pw, pq, a.live, sm);
     grid.sync();
-    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_scan(vb, K, nb, pmax, psum, pw, pq, a.cdf, a.stats + (r - 1) * 4, sm, wsum);
+    stamp(a, 4);
+    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_scan(vb, K, nb, M, psum, pw, pq, a.cdf, a.stats + (r - 1) * 4, sm, wsum);
     grid.sync();
     if (r == N - 1) {
       // ---- last launch: ELBO (vcsmc.py:276), log_likelihood_R (vcsmc.py:254-268, incl. quirk Q4), log_likelihood_tilde
@@ -777,6 +806,8 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
   }
 
   // ---- phase 5: ancestors of event r (all K), rows of the live particles of event r-1 (all K)
+  stamp(a, 5);
+  if (gtid == 0) *a.lw_max = LLONG_MIN;   // (every CTA has read the previous maximum by now)
   {
     int32_t* anc_row = a.anc + (int64_t)r * K;
     if (r == 0) {
@@ -789,6 +820,15 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
       }
     } else {
       const double total = a.cdf[K - 1];
+      // the first levels of the search run on 256 pivots in shared memory (the last entries of 256 equal blocks of the
+      // CDF): same result as a binary search over the whole array, a third of the dependent global loads
+      const int64_t blk = (K + 255) / 256;
+      double* piv = reinterpret_cast<double*>(su_all);
+      {
+        const int64_t last = min((int64_t)(tid + 1) * blk, K) - 1;
+        piv[tid] = (int64_t)tid * blk < K ? a.cdf[last] : INFINITY;
+      }
+      __syncthreads();
       for (int64_t k = gtid; k < K; k += gthreads) {
         double u;
         if (a.u_res) {
@@ -800,23 +840,53 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
           philox4x32_10(d, (uint32_t)seed, (uint32_t)(seed >> 32));
           u = u64_to_unit_f64(d[0], d[1]);
         }
-        const int idx = upper_bound_cdf(a.cdf, K, u * total);  // resample, vcsmc.py:284-285
+        const double t = u * total;
+        int lo = 0, hi = 256;                // first pivot > t (the block that holds the answer)
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (piv[mid] > t) hi = mid;
+          else lo = mid + 1;
+        }
+        int idx;
+        if (lo >= 256 || (int64_t)lo * blk >= K) {
+          idx = (int)(K - 1);                // no entry exceeds t: clamp, like upper_bound_cdf
+        } else {
+          const int64_t b0 = (int64_t)lo * blk;
+          const int64_t n_in = min(blk, K - b0);
+          idx = (int)(b0 + upper_bound_cdf(a.cdf + b0, n_in, t));  // resample, vcsmc.py:284-285
+        }
         anc_row[k] = idx;
         a.surv[idx] = 1;
         if (k >= k0 && k < k0 + Kl) a.haskid[idx] = 1;
       }
-      for (int64_t k = gwid; k < K; k += gwarps)
-        if (a.live[k]) build_row<NQ>(a, k, su, lane);
+      __syncthreads();   // (the pivots share the rows' staging buffer)
+      // (a warp looks at 32 flags at a time)
+      for (int64_t kb = gwid * 32; kb < K; kb += gwarps * 32) {
+        unsigned todo = __ballot_sync(0xffffffffu, kb + lane < K && a.live[kb + lane] != 0);
+        while (todo) {
+          const int b = __ffs(todo) - 1;
+          todo &= todo - 1;
+          build_row<NQ>(a, kb + b, su, lane);
+        }
+      }
     }
   }
   grid.sync();
+  stamp(a, 6);
   // ---- phase 6: survivors of event r-1; the last CTA to finish allocates the slots
   if (r > 0) {
-    for (int64_t k = gwid; k < K; k += gwarps)
-      if (a.surv[k]) survivor_row(a, k, lane);
+    for (int64_t kb = gwid * 32; kb < K; kb += gwarps * 32) {
+      unsigned todo = __ballot_sync(0xffffffffu, kb + lane < K && a.surv[kb + lane] != 0);
+      while (todo) {
+        const int b = __ffs(todo) - 1;
+        todo &= todo - 1;
+        survivor_row(a, kb + b, lane);
+      }
+    }
     if (a.gc && last_cta(a.counts + 3, &s_flag)) allocate_slots(a, warp_off);
   }
   grid.sync();
+  stamp(a, 7);
   // ---- phase 7: the survivors' nodes (plain merge, stored); proposal of event r for the own particles
   if (r > 0) {
     const int n_mat = a.counts[0];
@@ -866,8 +936,14 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
       }
     }
   }
-  for (int64_t base = (int64_t)blockIdx.x * kEvThreads; base < Kl; base += gthreads)
-    propose_particle(a, base + tid, base + tid < Kl, lane);
+  stamp(a, 8);
+  {
+    // every CTA takes an equal share of the particles (two CTAs share an SM's FP64 pipe: an idle CTA next to a full one
+    // would make that SM the straggler)
+    const int64_t lo = Kl * blockIdx.x / gridDim.x, hi = Kl * (blockIdx.x + 1) / gridDim.x;
+    for (int64_t base = lo; base < hi; base += kEvThreads) propose_particle(a, base + tid, base + tid < hi, lane);
+  }
+  stamp(a, 9);
   if (a.sorted && last_cta(a.counts + 4, &s_flag)) {
     // group order is irrelevant, so offsets need no scan: every occupied slot reserves its range with one atomic
     const int n_occ = ((volatile int32_t*)a.counts)[2];
@@ -878,6 +954,7 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
   }
   if (a.world > 1) cross_sync(a, a.bar_index + 2, grid);
   else grid.sync();
+  stamp(a, 10);
   // ---- phase 8: grouped visiting order; particle sharding: pull the missing nodes out of the owners' pools
   if (a.sorted) {
     for (int64_t kl = gtid; kl < Kl; kl += gthreads) {
@@ -904,6 +981,7 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
       }
     }
   }
+  stamp(a, 11);
 }
 
 __global__ void lz_set_seed_kernel(uint64_t* seed_dev, uint64_t seed) { *seed_dev = seed; }
@@ -929,7 +1007,13 @@ int event_blocks(size_t smem, int* out) {
   VCSMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   VCSMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lz_event_kernel<NQ>, kEvThreads, smem));
   if (per_sm < 1) { set_error("lz_event_kernel cannot be launched cooperatively"); return VCSMC_ERR_CUDA; }
-  if (per_sm > 2) per_sm = 2;   // more CTAs only make the grid barriers slower
+  static int want_per_sm = 0;
+  if (want_per_sm == 0) {
+    const char* e = getenv("VCSMC_EVENT_CTAS_PER_SM");   // tuning knob
+    want_per_sm = e ? atoi(e) : 2;                      // more CTAs only make the grid barriers slower
+    if (want_per_sm < 1) want_per_sm = 1;
+  }
+  if (per_sm > want_per_sm) per_sm = want_per_sm;
   *out = per_sm * sms;
   return VCSMC_OK;
 }
@@ -983,7 +1067,7 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     a.row_ids[i] = h->p<int32_t>(h->o_ids[i]); a.row_cnt[i] = h->p<int32_t>(h->o_cnt[i]);
     a.row_F[i] = h->p<double>(h->o_F[i]); a.row_T[i] = h->p<double>(h->o_topo[i]); a.row_V[i] = h->p<int32_t>(h->o_vm[i]);
   }
-  a.F0 = h->p<double>(h->o_F0);
+  a.F0 = h->p<double>(h->o_F0); a.lw_max = reinterpret_cast<long long*>(h->p<double>(h->o_F0) + 1);
   a.cdf = h->p<double>(h->o_cdf); a.cdf_scratch = h->p<double>(h->o_cdf_scratch);
   a.live = h->p<int32_t>(h->o_live); a.surv = h->p<int32_t>(h->o_surv); a.haskid = h->p<int32_t>(h->o_haskid);
   a.pool = h->p<double>(h->o_pool); a.flags = h->p<int32_t>(h->o_flags); a.loc = h->p<int32_t>(h->o_loc);
@@ -1004,6 +1088,7 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     a.peer_pool[g] = on ? reinterpret_cast<const double*>(h->peer_ws[g] + h->o_pool) : nullptr;
   }
   a.n_barriers_total = 2 * N;   // every launch reserves two barrier indices
+  a.timing = h->event_timing ? h->p<unsigned long long>(h->o_ev_timing) : nullptr;
 
   // scratch every launch relies on: the node -> slot map, the hash table, counters
   if (gc) {
@@ -1028,7 +1113,8 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
   count_launch(4);
 
   const int NQ = N <= 32 ? 1 : N <= 64 ? 2 : N <= 128 ? 4 : 8;
-  const size_t smem = (size_t)kEvWarps * a.row_stride * sizeof(float);
+  size_t smem = (size_t)kEvWarps * a.row_stride * sizeof(float);   // rows' staging buffer, also the 256 CDF pivots
+  if (smem < 256 * sizeof(double)) smem = 256 * sizeof(double);
   int blocks = 0;
   rc = NQ == 1 ? event_blocks<1>(smem, &blocks) : NQ == 2 ? event_blocks<2>(smem, &blocks) : NQ == 4 ? event_blocks<4>(smem, &blocks) : event_blocks<8>(smem, &blocks);
   if (rc) return rc;

@@ -48,7 +48,8 @@ struct ScoreArgs {
   int R;
   int skip_leaf_pairs;  // particles whose children are both leaves are scored from the pattern histogram instead
   int skip_octets;      // octets of particles that share one child pair are scored by merge_score_mma_kernel instead
-  double* ell_part;  // [K][n_chunks][kWarps]
+  int part_stride;      // partial sums per (particle, chunk): 1, or kWarps when the tensor-core experiment shares the array
+  double* ell_part;  // [K][n_chunks][part_stride]
 };
 
 constexpr int kScoreSmemBytes = kRScore * kCoef * 8 + kRScore * kTileThreads * (8 + 4);
@@ -290,6 +291,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
   double* s_prod = sC + kRScore * kCoef;                                 // [R][256] running mantissa products
   int* s_exp = reinterpret_cast<int*>(s_prod + kRScore * kTileThreads); // [R][256] running (biased) exponent sums
   __shared__ int s_k[kRScore], s_a[kRScore], s_b[kRScore];
+  __shared__ double s_slow[kWarps];
   __shared__ unsigned s_odd, s_skip;   // s_skip: particles of the group some other kernel scores (leaf pairs, uniform octets)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int R = a.R;
@@ -401,10 +403,10 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
       acc = warp_sum(acc);
       if (__any_sync(0xffffffffu, p != p)) {
         if (lane == 0) atomicOr(&s_odd, 1u << j);
-      } else if (lane < kWarps) {
+      } else if (lane < a.part_stride) {
         const int kk = s_k[j];
         const int64_t k = kk < 0 ? ~kk : kk;
-        a.ell_part[(k * a.n_chunks + tc) * kWarps + lane] = lane == 0 ? acc : 0.0;
+        a.ell_part[(k * a.n_chunks + tc) * a.part_stride + lane] = lane == 0 ? acc : 0.0;
       }
     }
     __syncthreads();
@@ -415,10 +417,16 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
       double acc = score_slow<JC>(cs, s_a[j], s_b[j], sC + j * kCoef, t_begin * (kTileThreads * SPT),
                                   min(a.n_sites, t_end * (kTileThreads * SPT)), pi[0], pi[1], pi[2], pi[3]);
       acc = warp_sum(acc);
-      if (lane == 0) {
+      __syncthreads();
+      if (lane == 0) s_slow[wid] = acc;
+      __syncthreads();
+      if (tid < a.part_stride) {
         const int kk = s_k[j];
         const int64_t k = kk < 0 ? ~kk : kk;
-        a.ell_part[(k * a.n_chunks + tc) * kWarps + wid] = acc;
+        double t = s_slow[tid];
+        if (a.part_stride == 1)
+          for (int w2 = 1; w2 < kWarps; ++w2) t += s_slow[w2];
+        a.ell_part[(k * a.n_chunks + tc) * a.part_stride + tid] = t;
       }
     }
   }
@@ -807,7 +815,8 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
   if (nc > a.tiles) nc = a.tiles;
   a.tiles_per_item = (int)((a.tiles + nc - 1) / nc);
   a.n_chunks = (a.tiles + a.tiles_per_item - 1) / a.tiles_per_item;
-  if (n_parts) *n_parts = a.n_chunks * kWarps;
+  a.part_stride = a.skip_octets ? kWarps : 1;
+  if (n_parts) *n_parts = a.n_chunks * a.part_stride;
   const int64_t total = groups * a.n_chunks;
   const int64_t cap = 148 * 2 * 8;
   const unsigned grid = (unsigned)(total < cap ? total : cap);
@@ -820,7 +829,7 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
     VCSMC_LAUNCH_CHECK("merge_score_mma_kernel");
   }
   if (leaf_hist) {
-    score_leaf_pairs_kernel<<<(unsigned)((K + 7) / 8), 256, 0, st>>>(lsrc, rsrc, P, pi, K, n_taxa, leaf_hist, a.n_chunks * kWarps, ell_part);
+    score_leaf_pairs_kernel<<<(unsigned)((K + 7) / 8), 256, 0, st>>>(lsrc, rsrc, P, pi, K, n_taxa, leaf_hist, a.n_chunks * a.part_stride, ell_part);
     VCSMC_LAUNCH_CHECK("score_leaf_pairs_kernel");
   }
   return VCSMC_OK;

@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(256) cdf_max_kernel(const double* __restrict__
 __global__ void __launch_bounds__(256) cdf_sumexp_kernel(const double* __restrict__ lw, int64_t K, int nb,
                                                          const double* __restrict__ pmax, double* __restrict__ psum) {
   __shared__ double sm[8];
-  cdf_stage_sumexp((int)blockIdx.x, lw, K, nb, pmax, psum, sm);
+  const double M = block_reduce_array(pmax, nb, true, sm);
+  cdf_stage_sumexp((int)blockIdx.x, lw, K, M, psum, sm);
 }
 
 __global__ void __launch_bounds__(256) cdf_weights_kernel(const double* __restrict__ lw, int64_t K, int nb,
@@ -169,7 +170,8 @@ __global__ void __launch_bounds__(256) cdf_weights_kernel(const double* __restri
                                                           double* __restrict__ w_out, double* __restrict__ pw,
                                                           double* __restrict__ pq) {
   __shared__ double sm[8];
-  cdf_stage_weights((int)blockIdx.x, lw, K, nb, pmax, psum, w_out, pw, pq, nullptr, sm);
+  const double M = block_reduce_array(pmax, nb, true, sm);
+  cdf_stage_weights((int)blockIdx.x, lw, K, nb, M, psum, w_out, pw, pq, nullptr, sm);
 }
 
 __global__ void __launch_bounds__(256) cdf_scan_kernel(int64_t K, int nb, const double* __restrict__ pmax,
@@ -178,7 +180,8 @@ __global__ void __launch_bounds__(256) cdf_scan_kernel(int64_t K, int nb, const 
                                                        double* __restrict__ stats) {
   __shared__ double sm[8];
   __shared__ double wsum[8];
-  cdf_stage_scan((int)blockIdx.x, K, nb, pmax, psum, pw, pq, cdf, stats, sm, wsum);
+  const double M = block_reduce_array(pmax, nb, true, sm);
+  cdf_stage_scan((int)blockIdx.x, K, nb, M, psum, pw, pq, cdf, stats, sm, wsum);
 }
 
 // small K: the same four stages, tile after tile, by ONE CTA in one launch (identical arithmetic)
@@ -189,11 +192,12 @@ __global__ void __launch_bounds__(256) cdf_one_cta_kernel(const double* __restri
   double *pmax = scratch, *psum = scratch + nb, *pw = scratch + 2 * nb, *pq = scratch + 3 * nb;
   for (int vb = 0; vb < nb; ++vb) cdf_stage_max(vb, lw, K, pmax, sm);
   __syncthreads();
-  for (int vb = 0; vb < nb; ++vb) cdf_stage_sumexp(vb, lw, K, nb, pmax, psum, sm);
+  const double M = block_reduce_array(pmax, nb, true, sm);
+  for (int vb = 0; vb < nb; ++vb) cdf_stage_sumexp(vb, lw, K, M, psum, sm);
   __syncthreads();
-  for (int vb = 0; vb < nb; ++vb) cdf_stage_weights(vb, lw, K, nb, pmax, psum, cdf, pw, pq, nullptr, sm);
+  for (int vb = 0; vb < nb; ++vb) cdf_stage_weights(vb, lw, K, nb, M, psum, cdf, pw, pq, nullptr, sm);
   __syncthreads();
-  for (int vb = 0; vb < nb; ++vb) cdf_stage_scan(vb, K, nb, pmax, psum, pw, pq, cdf, stats, sm, wsum);
+  for (int vb = 0; vb < nb; ++vb) cdf_stage_scan(vb, K, nb, M, psum, pw, pq, cdf, stats, sm, wsum);
 }
 
 __global__ void resample_search_kernel(const double* __restrict__ cdf, const double* __restrict__ stats,

@@ -91,9 +91,8 @@ __device__ __forceinline__ void cdf_stage_max(int vb, const double* lw, int64_t 
   }
 }
 
-__device__ __forceinline__ void cdf_stage_sumexp(int vb, const double* lw, int64_t K, int nb, const double* pmax, double* psum,
-                                                 double* sm) {
-  const double M = block_reduce_array(pmax, nb, true, sm);
+// M: the maximum of all K log-weights (exact in any order: the tile maxima of stage 1 reduced, or an atomic max)
+__device__ __forceinline__ void cdf_stage_sumexp(int vb, const double* lw, int64_t K, double M, double* psum, double* sm) {
   const int64_t b = (int64_t)vb * kCdfTile + threadIdx.x;
   double s = 0.0;
 #pragma unroll
@@ -104,10 +103,9 @@ __device__ __forceinline__ void cdf_stage_sumexp(int vb, const double* lw, int64
 
 // live (optional): 1 where the normalised weight is not zero in double precision -- the particles that can be drawn by
 // the next resampling or carry a gradient
-__device__ __forceinline__ void cdf_stage_weights(int vb, const double* lw, int64_t K, int nb, const double* pmax,
+__device__ __forceinline__ void cdf_stage_weights(int vb, const double* lw, int64_t K, int nb, double M,
                                                   const double* psum, double* w_out, double* pw, double* pq, int32_t* live,
                                                   double* sm) {
-  const double M = block_reduce_array(pmax, nb, true, sm);
   const double lse = M + log(block_reduce_array(psum, nb, false, sm));
   const double mlog = M - lse;  // max of the normalised logits (vcsmc.py:284)
   const int64_t b = (int64_t)vb * kCdfTile + (int64_t)threadIdx.x * 8;   // 8 CONSECUTIVE elements per thread
@@ -130,7 +128,7 @@ __device__ __forceinline__ void cdf_stage_weights(int vb, const double* lw, int6
   }
 }
 
-__device__ __forceinline__ void cdf_stage_scan(int vb, int64_t K, int nb, const double* pmax, const double* psum,
+__device__ __forceinline__ void cdf_stage_scan(int vb, int64_t K, int nb, double M, const double* psum,
                                                const double* pw, const double* pq, double* cdf, double* stats, double* sm,
                                                double* wsum) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -160,7 +158,6 @@ __device__ __forceinline__ void cdf_stage_scan(int vb, int64_t K, int nb, const 
     if (b + q < K) cdf[b + q] = base + w[q];
   if (vb == 0) {
     __syncthreads();
-    const double M = block_reduce_array(pmax, nb, true, sm);
     const double lse = M + log(block_reduce_array(psum, nb, false, sm));
     const double t = block_reduce_array(pw, nb, false, sm);
     const double q = block_reduce_array(pq, nb, false, sm);

@@ -821,6 +821,7 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_live = L.take<int32_t>(K);
     h->o_haskid = L.take<int32_t>(K);
     h->o_gocc = L.take<int32_t>(K);
+    h->o_ev_timing = L.take<unsigned long long>(16 * (int64_t)N);
     h->o_leaf_hist = L.take<int32_t>(leaf_pair_hist_ints(N));
     for (int i = 0; i < 2; ++i) {   // forest scalars that travel with a particle (lazy.cu)
       h->o_F[i] = L.take<double>(K);
@@ -1063,6 +1064,7 @@ int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value) {
   }
   else if (!strcmp(name, "leaf_patterns")) { h->leaf_patterns = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
   else if (!strcmp(name, "graph")) h->use_graph = value != 0.0;
+  else if (!strcmp(name, "event_timing")) { h->event_timing = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
   else if (!strcmp(name, "peer_sync")) {
     if (value == 0.0 && !h->comm && h->world > 1) { set_error("peer_sync = 0 needs the collective hook"); return VCSMC_ERR_STATE; }
     h->peer_sync = value != 0.0;
@@ -1634,7 +1636,7 @@ void* vcsmc_sweep_output(vcsmc_sweep_t* h, const char* name) {
       {"log_likelihood_R", h->o_llR}, {"left_branches", h->o_b_l}, {"right_branches", h->o_b_r}, {"v_minus", h->o_vminus},
       {"ancestors", h->o_anc}, {"left_ref", h->o_lref}, {"right_ref", h->o_rref}, {"leaf_counts", h->o_nleaf},
       {"log_z", h->o_logz}, {"ess", h->o_ess}, {"status", h->o_status}, {"ell_node", h->o_ell_node},
-      {"rem_positions", h->o_rempos}};
+      {"rem_positions", h->o_rempos}, {"event_timing", h->o_ev_timing}};
   if (h->M > 0 && !strcmp(name, "choice")) return h->ws + h->o_choice;
   for (auto& t : tab)
     if (!strcmp(t.n, name)) return h->ws + t.off;

@@ -111,6 +111,8 @@ struct vcsmc_sweep {
   int64_t o_loc = 0, o_slot_id = 0, o_pend = 0, o_surv = 0, o_mat_list = 0, o_fetch_e = 0, o_fetch_src = 0, o_counts = 0,
           o_pF = 0, o_pT = 0, o_pV = 0, o_pLLt = 0, o_lsrc2 = 0, o_rsrc2 = 0, o_F0 = 0, o_live = 0, o_haskid = 0, o_gocc = 0,
           o_lz_ids = 0, o_lz_cnt = 0, o_u_res_all = 0, o_rec = 0, o_cdf_scratch = 0, o_gtab = 0, o_gcnt = 0, o_goff = 0, o_gslot = 0, o_grank = 0, o_leaf_hist = 0, o_F[2] = {0, 0}, o_topo[2] = {0, 0}, o_vm[2] = {0, 0};
+  int event_timing = 0;                // option "event_timing": CTA 0 of the event kernel stamps %globaltimer at every phase boundary
+  int64_t o_ev_timing = 0;
   int leaf_patterns = 1;               // score leaf-leaf merges from the site-pattern histogram (option "leaf_patterns")
   int64_t rec_stride = 0;              // bytes of one rank's chunk of the per-event record
   int64_t fetch_cap = 0;

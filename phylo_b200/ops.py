@@ -319,11 +319,12 @@ class Sweep:
         return dl, dr, dQ, dpi
 
     def profile(self) -> Dict[str, Tuple[float, int]]:
-        """{kernel: (total ms, launches)} of the merge launches since set_option('profile', 1); resets."""
+        """{kernel: (total ms, launches)} since set_option('profile', 1); resets.  merge_fwd = the forward's scoring /
+        merge kernels, event_kernel = the lazy forward's cooperative bookkeeping kernel (one launch per rank event)."""
         buf = (C.c_double * 8)()
         check(self._lib.vcsmc_sweep_profile(self._h, buf))
         return {"merge_fwd": (buf[0], int(buf[1])), "merge_fwd_recompute": (buf[2], int(buf[3])),
-                "merge_bwd": (buf[4], int(buf[5])), "materialise": (buf[6], int(buf[7]))}
+                "merge_bwd": (buf[4], int(buf[5])), "event_kernel": (buf[6], int(buf[7]))}
 
     def rem_positions(self):
         """Per rank event r, the uint8 [K, N-r-2] table of kept forest positions (host numpy), see the header."""
@@ -335,6 +336,13 @@ class Sweep:
             out.append(self.workspace[base + off: base + off + cnt].cpu().numpy().reshape(self.K, self.N - r - 2))
             off += (cnt + 15) // 16 * 16
         return out
+
+    def event_timing(self):
+        """[N,16] uint64 %globaltimer stamps (ns) of the lazy forward's event kernel, launch r in row r: entry i is taken
+        by CTA 0 at the start of phase i (needs set_option("event_timing", 1) before the forward)."""
+        ptr = self._lib.vcsmc_sweep_output(self._h, b"event_timing")
+        off = ptr - self.workspace.data_ptr()
+        return self.workspace[off:off + 8 * 16 * self.N].view(torch.int64).view(self.N, 16).cpu().numpy()
 
     def rem_row(self, r: int, k: int):
         """Kept forest positions of ONE particle slot at rank event r (uint8 [N-r-2], host numpy)."""
