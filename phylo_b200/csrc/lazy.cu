@@ -46,7 +46,7 @@ constexpr int kMatSptEv = 2;
 
 struct EvArgs {
   int r;                 // launch index: finishes rank event r-1 (r > 0) and prepares rank event r (r < N-1)
-  int N, S, jc, gc, rank, world, sorted, skip_leaf_pairs, row_stride, log2T, tiles, bar_index, n_barriers_total;
+  int N, S, jc, gc, rank, world, sorted, two_lists, skip_leaf_pairs, row_stride, log2T, tiles, bar_index, n_barriers_total;
   int64_t K, Kl, k0, pool_slots, fetch_cap, slot_sites;
   // model and uniforms (null uniforms: counter-based generator)
   const double* lam_l;
@@ -637,25 +637,27 @@ __device__ __forceinline__ void propose_particle(const EvArgs& a, int64_t kl, bo
     a.lsrc[r & 1][kl] = ls;
     a.rsrc[r & 1][kl] = rs;
     // transition matrices (vcsmc.py:181-184)
-    double* Pout = a.P + e * 32;
-    if (a.jc) {
-#pragma unroll
-      for (int side = 0; side < 2; ++side) {
-        const double ti = side ? br : bl;
+    double* Pout = a.P + e * 32;   // (256-byte aligned: whole 32-byte sectors per store)
+    for (int side = 0; side < 2; ++side) {
+      const double ti = side ? br : bl;
+      M4 X;
+      if (a.jc) {
         const double o = -0.25 * expm1(-ti);
         const double d = 0.25 + 0.75 * exp(-ti);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) Pout[side * 16 + q] = (q % 5 == 0) ? d : o;
-      }
-    } else {
-      for (int side = 0; side < 2; ++side) {
-        const double ti = side ? br : bl;
+        for (int q = 0; q < 16; ++q) X.a[q] = (q % 5 == 0) ? d : o;
+      } else {
         M4 A;
 #pragma unroll
         for (int q = 0; q < 16; ++q) A.a[q] = a.Q[q] * ti;
-        const M4 X = m4_expm(A);
+        X = m4_expm(A);
+      }
 #pragma unroll
-        for (int q = 0; q < 16; ++q) Pout[side * 16 + q] = X.a[q];
+      for (int q = 0; q < 4; ++q) {
+        d4 row;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) row.v[c] = X.a[q * 4 + c];
+        st_site(Pout + side * 16 + q * 4, row);
       }
     }
   }
@@ -762,7 +764,8 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
       a.counts[0] = 0;
       a.counts[1] = 0;
       a.counts[2] = 0;
-      *a.gcount = 0;
+      a.gcount[0] = 0;
+      a.gcount[1] = 0;
     }
     for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_sumexp(vb, lw, K, M, psum, sm);
     grid.sync();
@@ -945,11 +948,54 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
   }
   stamp(a, 9);
   if (a.sorted && last_cta(a.counts + 4, &s_flag)) {
-    // group order is irrelevant, so offsets need no scan: every occupied slot reserves its range with one atomic
+    // offsets of the groups, in the order the slots were occupied: every thread takes a contiguous stretch of the
+    // occupied list, one CTA-wide exclusive scan of the stretch totals (no chain of dependent atomics).  Two lists
+    // share the order array: pairs of a LEAF and an internal node from the front (rows kernel), pairs of two internal
+    // nodes from the back (generic kernel).
     const int n_occ = ((volatile int32_t*)a.counts)[2];
-    for (int i = tid; i < n_occ; i += kEvThreads) {
-      const int s = ((volatile int32_t*)a.gocc)[i];
-      a.goff[s] = atomicAdd(a.gcount, ((volatile int32_t*)a.gcnt)[s]);
+    const int per = (n_occ + kEvThreads - 1) / kEvThreads;
+    const int i0 = min(tid * per, n_occ), i1 = min(i0 + per, n_occ);
+    int mine[2] = {0, 0};
+    for (int i = i0; i < i1; ++i) {
+      const int sl = ((volatile int32_t*)a.gocc)[i];
+      const bool leafy = !a.two_lists || ((((volatile unsigned long long*)a.gtab)[sl] - 1ull) >> 32) < 256ull;   // the smaller reference is a leaf
+      mine[leafy ? 0 : 1] += ((volatile int32_t*)a.gcnt)[sl];
+    }
+    int incl[2] = {mine[0], mine[1]};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t0 = __shfl_up_sync(0xffffffffu, incl[0], o), t1 = __shfl_up_sync(0xffffffffu, incl[1], o);
+      if (lane >= o) {
+        incl[0] += t0;
+        incl[1] += t1;
+      }
+    }
+    int* wtot = reinterpret_cast<int*>(warp_off);
+    if (lane == 31) {
+      wtot[2 * wid] = incl[0];
+      wtot[2 * wid + 1] = incl[1];
+    }
+    __syncthreads();
+    int base[2] = {incl[0] - mine[0], incl[1] - mine[1]};
+    for (int w2 = 0; w2 < wid; ++w2) {
+      base[0] += wtot[2 * w2];
+      base[1] += wtot[2 * w2 + 1];
+    }
+    for (int i = i0; i < i1; ++i) {
+      const int sl = ((volatile int32_t*)a.gocc)[i];
+      const bool leafy = !a.two_lists || ((((volatile unsigned long long*)a.gtab)[sl] - 1ull) >> 32) < 256ull;
+      const int c = ((volatile int32_t*)a.gcnt)[sl];
+      if (leafy) {
+        a.goff[sl] = base[0];
+        base[0] += c;
+      } else {
+        base[1] += c;
+        a.goff[sl] = (int)Kl - base[1];
+      }
+    }
+    if (tid == kEvThreads - 1) {
+      a.gcount[0] = base[0];
+      a.gcount[1] = base[1];
     }
   }
   if (a.world > 1) cross_sync(a, a.bar_index + 2, grid);
@@ -1043,7 +1089,15 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     if (rc) return rc;
     leaf_hist = h->p<int32_t>(h->o_leaf_hist);
   }
-  const bool sorted = use_sorted_order(Kl, S);
+  const bool sorted = h->force_sorted || use_sorted_order(Kl, S);
+  const int32_t* leaf_perm = nullptr;
+  const uint8_t* leaf_tstate = nullptr;
+  if (sorted && h->leaf_rows) {  // every leaf's sites in state order, once per sweep: the rows kernel scores leaf + internal pairs on them
+    rc = launch_leaf_sort(codes, S, N, S, h->p<int32_t>(h->o_leaf_perm), h->p<uint8_t>(h->o_leaf_tstate), st);
+    if (rc) return rc;
+    leaf_perm = h->p<int32_t>(h->o_leaf_perm);
+    leaf_tstate = h->p<uint8_t>(h->o_leaf_tstate);
+  }
   const int64_t T = group_table_entries(Kl);
   int log2T = 0;
   while (((int64_t)1 << log2T) < T) ++log2T;
@@ -1051,7 +1105,7 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
   EvArgs a;
   memset(&a, 0, sizeof(a));
   a.N = N; a.S = S; a.jc = h->jc; a.gc = gc; a.rank = h->rank; a.world = G; a.sorted = sorted;
-  a.skip_leaf_pairs = leaf_hist != nullptr; a.row_stride = (N + 3) & ~3; a.log2T = log2T;
+  a.two_lists = leaf_perm != nullptr; a.skip_leaf_pairs = leaf_hist != nullptr; a.row_stride = (N + 3) & ~3; a.log2T = log2T;
   a.K = K; a.Kl = Kl; a.k0 = k0; a.pool_slots = h->pool_slots; a.fetch_cap = h->fetch_cap; a.slot_sites = S;
   a.lam_l = lam_l; a.lam_r = lam_r; a.Q = Q; a.pi = pi; a.ldf = h->p<double>(h->o_ldf);
   a.seed_dev = h->p<uint64_t>(h->o_seed_dev); a.codes = codes;
@@ -1105,7 +1159,7 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     count_launch();
   }
   VCSMC_CUDA(cudaMemsetAsync(a.counts, 0, 8 * sizeof(int32_t), st));
-  VCSMC_CUDA(cudaMemsetAsync(a.gcount, 0, sizeof(int32_t), st));
+  VCSMC_CUDA(cudaMemsetAsync(a.gcount, 0, 2 * sizeof(int32_t), st));
   if (sorted) {
     VCSMC_CUDA(cudaMemsetAsync(a.gtab, 0, (size_t)T * sizeof(unsigned long long), st));
     VCSMC_CUDA(cudaMemsetAsync(a.gcnt, 0, (size_t)T * sizeof(int32_t), st));
@@ -1153,7 +1207,7 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     int tiles = 0;
     h->prof_begin(0, st);
     rc = launch_merge_score(codes, S, h->p<double>(h->o_pool), S, a.lsrc[cur], a.rsrc[cur], sorted ? a.order : nullptr, P, pi, Kl,
-                            sorted ? a.gcount : nullptr, S, h->jc, leaf_hist, N, h->p<double>(h->o_ell_part), &tiles, st);
+                            sorted ? a.gcount : nullptr, S, h->jc, leaf_hist, N, leaf_perm, leaf_tstate, h->p<double>(h->o_ell_part), &tiles, st);
     h->prof_end(st);
     if (rc) return rc;
     a.ell_part = h->p<double>(h->o_ell_part);

@@ -13,12 +13,15 @@
 //                        leaf with one-hot / all-ones masks it is row `state` of M dotted with L_b (4 DFMA).
 //                        Children come from L2; bound by instruction issue around the FP64 pipe.
 //   score_leaf_pairs_kernel  particles whose children are both leaves: site patterns instead of sites.
-//   merge_score_mma_kernel   experiment: the same GEMM on the FP64 tensor cores (off by default, see the launcher).
+//   merge_score_rows_kernel  particles whose children are a LEAF and an internal node (most of the scored work on
+//                        leaf-rich forests): the sites are visited in the leaf's state order (leaf_sort_kernel, once per
+//                        sweep), so a 1024-site tile shares ONE row of M per particle and a site costs 4 DFMA + 1/4 fold.
 //   materialise_kernel   after the next resampling, only particles that were drawn as an ancestor get their node
 //                        written (the plain merge formula; 32 B per site, streaming).
 //   pull_kernel          particle sharding: a rank that drew a remote ancestor copies the nodes it lacks straight out
 //                        of the owner's pool over NVLink (peer pointers, 256-bit loads), one CTA per (node, site tile).
 #include <stdlib.h>
+#include <string.h>
 
 #include "launch.h"
 #include "merge_device.cuh"
@@ -47,9 +50,9 @@ struct ScoreArgs {
   int n_chunks;
   int R;
   int skip_leaf_pairs;  // particles whose children are both leaves are scored from the pattern histogram instead
-  int skip_octets;      // octets of particles that share one child pair are scored by merge_score_mma_kernel instead
-  int part_stride;      // partial sums per (particle, chunk): 1, or kWarps when the tensor-core experiment shares the array
-  double* ell_part;  // [K][n_chunks][part_stride]
+  int n_parts;          // partial sums per particle in ell_part (>= n_chunks; the tail is zero-filled)
+  int from_end;         // the `*count` entries to score are the LAST ones of order[0, K) (the generic list of the grouped order)
+  double* ell_part;  // [K][n_parts]
 };
 
 constexpr int kScoreSmemBytes = kRScore * kCoef * 8 + kRScore * kTileThreads * (8 + 4);
@@ -63,7 +66,6 @@ struct ChildSpace {
   int64_t slot_sites;
   int n_sites;
   int skip_leaf_pairs;
-  int skip_octets;
 };
 
 template <bool JC, int SPT, int NC>
@@ -186,16 +188,6 @@ __device__ __forceinline__ void score_particles_leaf(int j, const double (&Lb)[S
   }
 }
 
-// particles j .. j+7 of the group exist and share one child pair (and are not a leaf-leaf pair when those are skipped)
-__device__ __forceinline__ bool octet_uniform(const int* s_a, const int* s_b, int j, int nj) {
-  if (j + 8 > nj) return false;
-  const int ca = s_a[j], cb = s_b[j];
-  bool u = true;
-#pragma unroll
-  for (int i = 1; i < 8; ++i) u = u && s_a[j + i] == ca && s_b[j + i] == cb;
-  return u;
-}
-
 // One tile of SPT*256 sites for the nj particles of a group.  The running product of the site likelihoods of
 // (thread, particle) is kept as (mantissa product, BIASED exponent sum) in shared memory.  The split is three integer
 // ops per site; a likelihood that is not a positive normal number (0, subnormal, inf, NaN, negative) poisons the
@@ -218,7 +210,7 @@ __device__ __forceinline__ void score_tile(const ChildSpace& a, int nj, unsigned
   int j = 0;
   while (j < nj) {
     const int ca = s_a[j], cb = s_b[j];
-    if (skip >> j & 1u) {  // a leaf pair (scored from site patterns) or part of a uniform octet (tensor-core kernel)
+    if (skip >> j & 1u) {  // a leaf pair (scored from site patterns)
       ++j;
       continue;
     }
@@ -292,7 +284,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
   int* s_exp = reinterpret_cast<int*>(s_prod + kRScore * kTileThreads); // [R][256] running (biased) exponent sums
   __shared__ int s_k[kRScore], s_a[kRScore], s_b[kRScore];
   __shared__ double s_slow[kWarps];
-  __shared__ unsigned s_odd, s_skip;   // s_skip: particles of the group some other kernel scores (leaf pairs, uniform octets)
+  __shared__ unsigned s_odd, s_skip;   // s_skip: particles of the group some other kernel scores (leaf pairs)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int R = a.R;
   const int64_t count = a.count ? (int64_t)*a.count : a.K;
@@ -302,7 +294,8 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
   for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
   double* my_prod = s_prod + tid;
   int* my_exp = s_exp + tid;
-  const ChildSpace cs = {a.codes, a.codes_stride, a.pool, a.slot_sites, a.n_sites, a.skip_leaf_pairs, a.skip_octets};
+  const ChildSpace cs = {a.codes, a.codes_stride, a.pool, a.slot_sites, a.n_sites, a.skip_leaf_pairs};
+  const int64_t first = a.from_end ? a.K - count : 0;
 
   for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
     const int64_t g = w / a.n_chunks;
@@ -312,7 +305,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
     __syncthreads();
     if (tid == 0) s_odd = 0u;
     if (tid < nj) {
-      const int k = a.order ? a.order[j0 + tid] : (int)(j0 + tid);
+      const int k = a.order ? a.order[first + j0 + tid] : (int)(j0 + tid);
       const int ls = a.lsrc[k], rs = a.rsrc[k];
       const bool sw = ls > rs;  // canonical child order a <= b; the swap flag rides in the sign of k
       s_a[tid] = sw ? rs : ls;
@@ -324,9 +317,6 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
       unsigned skip = 0u;
       for (int j = 0; j < nj; ++j)
         if (a.skip_leaf_pairs && s_b[j] < 0) skip |= 1u << j;
-      if (a.skip_octets)
-        for (int o = 0; o < 4; ++o)
-          if (octet_uniform(s_a, s_b, 8 * o, nj)) skip |= 0xffu << (8 * o);
       s_skip = skip;
     }
     __syncthreads();
@@ -403,10 +393,12 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
       acc = warp_sum(acc);
       if (__any_sync(0xffffffffu, p != p)) {
         if (lane == 0) atomicOr(&s_odd, 1u << j);
-      } else if (lane < a.part_stride) {
+      } else {
         const int kk = s_k[j];
         const int64_t k = kk < 0 ? ~kk : kk;
-        a.ell_part[(k * a.n_chunks + tc) * a.part_stride + lane] = lane == 0 ? acc : 0.0;
+        if (lane == 0) a.ell_part[k * a.n_parts + tc] = acc;
+        if (tc == 0)   // the entries no chunk of this kernel writes
+          for (int t = a.n_chunks + lane; t < a.n_parts; t += 32) a.ell_part[k * a.n_parts + t] = 0.0;
       }
     }
     __syncthreads();
@@ -420,47 +412,146 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
       __syncthreads();
       if (lane == 0) s_slow[wid] = acc;
       __syncthreads();
-      if (tid < a.part_stride) {
+      if (tid == 0) {
         const int kk = s_k[j];
         const int64_t k = kk < 0 ? ~kk : kk;
-        double t = s_slow[tid];
-        if (a.part_stride == 1)
-          for (int w2 = 1; w2 < kWarps; ++w2) t += s_slow[w2];
-        a.ell_part[(k * a.n_chunks + tc) * a.part_stride + tid] = t;
+        double t = s_slow[0];
+        for (int w2 = 1; w2 < kWarps; ++w2) t += s_slow[w2];
+        a.ell_part[k * a.n_parts + tc] = t;
+        if (tc == 0)
+          for (int q = a.n_chunks; q < a.n_parts; ++q) a.ell_part[k * a.n_parts + q] = 0.0;
       }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// The same scoring on the FP64 tensor cores, for octets of particles that share one child pair.
-//
-// x[particle][site] = sum_c M_particle[c] * O_site[c] is a GEMM with inner dimension 16.  One mma.sync.m8n8k4.f64
-// multiplies 8 particles (A: 8x4 coefficients, registers, loaded once per work item) by 8 sites (B: 4x8 site products,
-// 4 DMUL per lane per site block) -- 256 FMA per warp instruction instead of 32.  B200's DMMA rate equals its DFMA rate
-// (18.5 T FMA/s, scripts/microbench_dmma.cu): the gain is instruction issue, which is what bounds the vector kernel.
-// A warp owns 64 sites of every 512-site tile of the work item; a lane ends up with the likelihoods of ONE particle
-// (row lane/4) at two sites per block, folds them into a running (mantissa product, exponent sum) in registers, and the
-// four lanes of a row are combined at the end.  Same per-(particle, chunk, warp) partial sums as the vector kernel.
+// leaf + internal node: sites in the leaf's state order
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
-  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+// When child a is a LEAF, L_a[s] is a 0/1 mask and the site likelihood is row `state` of M (the column sums of M for a
+// gap) dotted with L_b[s].  leaf_sort_kernel lists every leaf's sites by state class once per sweep (A, C, G, T, gap,
+// other ambiguity codes; every class padded to whole 1024-site tiles with -1), so that all 1024 sites of a tile use the
+// SAME row: it is fetched once per particle (a broadcast read), the four sites of a thread cost 16 DFMA, their product
+// is folded into the running (mantissa, exponent) with ONE split -- against a per-lane row fetch, 4 + 1 FP64 ops and
+// a split per site in the generic kernel's leaf path, which was bound by instruction issue, not by the FP64 pipe.
+// The internal child is read through the permutation (32 B per site: whole sectors, so the gather costs nothing extra).
+constexpr int kRowTile = 1024;            // sorted positions per tile: 256 threads x 4
+constexpr int kLeafClasses = 6;
+
+__device__ __forceinline__ int leaf_class(int code) {
+  code &= 15;
+  return code == 1 ? 0 : code == 2 ? 1 : code == 4 ? 2 : code == 8 ? 3 : code == 15 ? 4 : 5;
 }
 
-__global__ void __launch_bounds__(kTileThreads, 2) merge_score_mma_kernel(const ScoreArgs a) {
-  __shared__ __align__(16) double sC[kRScore * 16];
+// one CTA per leaf; stable (thread t owns a contiguous stretch of sites, classes are placed in thread order), so the
+// order -- and with it every floating-point sum over sites -- is reproducible
+__global__ void __launch_bounds__(256) leaf_sort_kernel(const uint8_t* __restrict__ codes, int64_t stride, int S, int Sp,
+                                                        int32_t* __restrict__ perm, uint8_t* __restrict__ tstate) {
+  __shared__ int cnt[256][kLeafClasses];
+  __shared__ int start[kLeafClasses + 1];
+  const int leaf = blockIdx.x, tid = threadIdx.x;
+  const uint8_t* row = codes + (int64_t)leaf * stride;
+  int32_t* out = perm + (int64_t)leaf * Sp;
+  const int per = (S + 255) / 256, s0 = min(tid * per, S), s1 = min(s0 + per, S);
+  int mine[kLeafClasses] = {0, 0, 0, 0, 0, 0};
+  for (int s = s0; s < s1; ++s) ++mine[leaf_class(row[s])];
+#pragma unroll
+  for (int c = 0; c < kLeafClasses; ++c) cnt[tid][c] = mine[c];
+  for (int p = tid; p < Sp; p += 256) out[p] = -1;
+  __syncthreads();
+  if (tid == 0) {
+    int at = 0;
+    for (int c = 0; c < kLeafClasses; ++c) {
+      int tot = 0;
+      for (int t = 0; t < 256; ++t) tot += cnt[t][c];
+      start[c] = at;
+      at += (tot + kRowTile - 1) / kRowTile * kRowTile;
+    }
+    start[kLeafClasses] = at;
+  }
+  __syncthreads();
+  int pos[kLeafClasses];
+#pragma unroll
+  for (int c = 0; c < kLeafClasses; ++c) {
+    int before = 0;
+    for (int t = 0; t < tid; ++t) before += cnt[t][c];
+    pos[c] = start[c] + before;
+  }
+  for (int s = s0; s < s1; ++s) {
+    const int c = leaf_class(row[s]);
+    int p = 0;
+#pragma unroll
+    for (int q = 0; q < kLeafClasses; ++q)
+      if (q == c) p = pos[q]++;
+    out[p] = s;
+  }
+  const int n_tiles = Sp / kRowTile;
+  for (int t = tid; t < n_tiles; t += 256) {
+    const int p = t * kRowTile;
+    int c = 255;   // no sites
+    for (int q = 0; q < kLeafClasses; ++q)
+      if (p >= start[q] && p < start[q + 1]) c = q;
+    tstate[(int64_t)leaf * n_tiles + t] = (uint8_t)c;
+  }
+}
+
+struct RowArgs {
+  const uint8_t* codes;
+  int64_t codes_stride;
+  const double* pool;
+  int64_t slot_sites;
+  const int32_t* lsrc;
+  const int32_t* rsrc;
+  const int32_t* order;   // the first *count entries: particles with one leaf child and one internal child, grouped by pair
+  const int32_t* count;
+  const double* P;
+  const double* pi;
+  const int32_t* perm;    // [N][Sp] sites of every leaf in state order (-1: padding)
+  const uint8_t* tstate;  // [N][tiles] state class of every tile (255: empty)
+  int Sp, tiles, tiles_per_item, n_chunks, R, n_parts;
+  double* ell_part;
+};
+
+// exact fallback for a particle whose product was poisoned: one log per site
+__device__ __noinline__ double rows_slow(const RowArgs a, int leaf, int cb, const double* M, int p_begin, int p_end) {
+  const uint8_t* crow = a.codes + (int64_t)leaf * a.codes_stride;
+  const double* node = a.pool + (int64_t)cb * a.slot_sites * 4;
+  const int32_t* pm = a.perm + (int64_t)leaf * a.Sp;
+  double acc = 0.0;
+  for (int p = p_begin + threadIdx.x; p < p_end; p += kTileThreads) {
+    const int s = pm[p];
+    if (s < 0) continue;
+    const d4 La = leaf_site(__ldg(crow + s)), Lb = ld_site(node + (int64_t)s * 4);
+    double x = 0.0;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      double d = M[jj * 4] * Lb.v[0];
+#pragma unroll
+      for (int m = 1; m < 4; ++m) d = fma(M[jj * 4 + m], Lb.v[m], d);
+      x = fma(La.v[jj], d, x);
+    }
+    acc += log(x);
+  }
+  return acc;
+}
+
+__global__ void __launch_bounds__(kTileThreads, 2) merge_score_rows_kernel(const RowArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sC = reinterpret_cast<double*>(smem_raw);                    // [R][20]: M[4][4] and its column sums
+  double* s_prod = sC + kRScore * kCoef;                                 // [R][256] running mantissa products
+  int* s_exp = reinterpret_cast<int*>(s_prod + kRScore * kTileThreads); // [R][256] running (biased) exponent sums
   __shared__ int s_k[kRScore], s_a[kRScore], s_b[kRScore];
-  __shared__ unsigned s_odd, s_mine;
+  __shared__ double s_slow[kWarps];
+  __shared__ unsigned s_odd;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int row = lane >> 2, q4 = lane & 3;
   const int R = a.R;
-  const int64_t count = a.count ? (int64_t)*a.count : a.K;
+  const int64_t count = (int64_t)*a.count;
   const int64_t total = ((count + R - 1) / R) * a.n_chunks;
   double pi[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
-  const ChildSpace cs = {a.codes, a.codes_stride, a.pool, a.slot_sites, a.n_sites, a.skip_leaf_pairs, 0};
-  constexpr int kTile = kTileThreads * 2;  // sites per tile (the vector kernel's tile with 2 sites per thread)
+  double* my_prod = s_prod + tid;
+  int* my_exp = s_exp + tid;
 
   for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
     const int64_t g = w / a.n_chunks;
@@ -470,25 +561,15 @@ __global__ void __launch_bounds__(kTileThreads, 2) merge_score_mma_kernel(const 
     __syncthreads();
     if (tid == 0) s_odd = 0u;
     if (tid < nj) {
-      const int k = a.order ? a.order[j0 + tid] : (int)(j0 + tid);
+      const int k = a.order[j0 + tid];
       const int ls = a.lsrc[k], rs = a.rsrc[k];
-      const bool sw = ls > rs;
-      s_a[tid] = sw ? rs : ls;
-      s_b[tid] = sw ? ls : rs;
+      const bool sw = ls > rs;          // the leaf (negative reference) comes first; the swap flag rides in the sign of k
+      s_a[tid] = -(sw ? rs : ls) - 1;   // leaf index
+      s_b[tid] = sw ? ls : rs;          // slot of the internal node
       s_k[tid] = sw ? ~k : k;
     }
     __syncthreads();
-    // which octets are mine (uniform pair, not a leaf pair)
-    if (tid == 0) {
-      unsigned m = 0u;
-      for (int o = 0; o < 4; ++o)
-        if (octet_uniform(s_a, s_b, 8 * o, nj) && !(a.skip_leaf_pairs && s_b[8 * o] < 0)) m |= 1u << o;
-      s_mine = m;
-    }
-    __syncthreads();
-    const unsigned mine = s_mine;
-    if (mine == 0u) continue;   // (uniform across the CTA)
-    for (int e = tid; e < nj * 16; e += kTileThreads) {
+    for (int e = tid; e < nj * 16; e += kTileThreads) {   // M[j][m] = sum_i pi_i P_leaf[j][i] P_node[m][i]
       const int j = e >> 4, ai = (e >> 2) & 3, bi = e & 3;
       const int kk = s_k[j];
       const bool sw = kk < 0;
@@ -498,94 +579,177 @@ __global__ void __launch_bounds__(kTileThreads, 2) merge_score_mma_kernel(const 
       double m = pi[0] * __ldg(Pa) * __ldg(Pb);
 #pragma unroll
       for (int i = 1; i < 4; ++i) m = fma(pi[i] * __ldg(Pa + i), __ldg(Pb + i), m);
-      sC[j * 16 + ai * 4 + bi] = m;
+      sC[j * kCoef + ai * 4 + bi] = m;
     }
     __syncthreads();
-    // A fragments: lane (row, q4) holds M_{particle 8 o + row}[4 ks + q4] for k-step ks
-    double A[4][4];
-#pragma unroll
-    for (int o = 0; o < 4; ++o)
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) A[o][ks] = (mine >> o & 1u) ? sC[(8 * o + row) * 16 + 4 * ks + q4] : 0.0;
-    double pr[4] = {1.0, 1.0, 1.0, 1.0};
-    int ex[4] = {0, 0, 0, 0};
+    for (int e = tid; e < nj * 4; e += kTileThreads) {  // column sums: the row of a gap
+      const int j = e >> 2, m = e & 3;
+      sC[j * kCoef + 16 + m] = (sC[j * kCoef + m] + sC[j * kCoef + 4 + m]) + (sC[j * kCoef + 8 + m] + sC[j * kCoef + 12 + m]);
+    }
+    for (int j = 0; j < nj; ++j) {
+      my_prod[j * kTileThreads] = 1.0;
+      my_exp[j * kTileThreads] = 0;
+    }
+    __syncthreads();
 
     const int t_begin = tc * a.tiles_per_item;
     const int t_end = min(a.tiles, t_begin + a.tiles_per_item);
-    int folded = 0;
     for (int t = t_begin; t < t_end; ++t) {
-      const bool renorm = ((t - t_begin) & 31) == 31;
-#pragma unroll 2
-      for (int blk = 0; blk < 8; ++blk) {
-        const int s0 = t * kTile + wid * 64 + blk * 8;   // the 8 sites of this block
-        const int sB = s0 + row;                          // B fragment: lane (q4, site row)
-        int pa = kNone, pb = kNone;
-        double B[4] = {0.0, 0.0, 0.0, 0.0};
+      const bool renorm = ((t - t_begin) & 127) == 127;
+      int pa = -1, pb = kNone, cls = 255;
+      double Lb[4][4], x0[4];
+      int code[4];
+      int j = 0;
+      while (j < nj) {
+        const int ca = s_a[j], cb = s_b[j];
+        if (ca != pa || cb != pb) {   // a new (leaf, node) pair: this thread's four sites of the leaf's tile t
+          cls = a.tstate[(int64_t)ca * a.tiles + t];
+          const int32_t* pm = a.perm + (int64_t)ca * a.Sp + (int64_t)t * kRowTile + tid;
+          const double* node = a.pool + (int64_t)cb * a.slot_sites * 4;
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-          if (!(mine >> o & 1u)) continue;
-          const int ca = s_a[8 * o], cb = s_b[8 * o];
-          if (ca != pa || cb != pb) {
-            // site products L_a[site][ks] * L_b[site][q4] for the four k-steps
-            if (sB < a.n_sites) {
-              const ChildRef ra = child_ref(ca, cs.codes, cs.codes_stride, cs.pool, cs.slot_sites);
-              const d4 La = load_child(ra, sB);
-              double lb;
-              if (cb < 0) lb = (__ldg(cs.codes + (int64_t)(-cb - 1) * cs.codes_stride + sB) >> q4 & 1) ? 1.0 : 0.0;
-              else lb = __ldg(cs.pool + ((int64_t)cb * cs.slot_sites + sB) * 4 + q4);
+          for (int q = 0; q < 4; ++q) {
+            const int s = cls != 255 ? __ldg(pm + q * kTileThreads) : -1;
+            code[q] = 0;
+            if (s >= 0) {
+              const d4 L = ld_site(node + (int64_t)s * 4);
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) B[ks] = La.v[ks] * lb;
+              for (int m = 0; m < 4; ++m) Lb[q][m] = L.v[m];
+              x0[q] = 0.0;
+              if (cls == 5) code[q] = __ldg(a.codes + (int64_t)ca * a.codes_stride + s) & 15;
             } else {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) B[ks] = 0.0;
+              for (int m = 0; m < 4; ++m) Lb[q][m] = 0.0;
+              x0[q] = 1.0;   // padding: the site likelihood of "no site" is 1
             }
-            pa = ca;
-            pb = cb;
           }
-          double c0 = 0.0, c1 = 0.0;
+          pa = ca;
+          pb = cb;
+        }
+        if (cls == 255) {   // nothing of this leaf in tile t
+          ++j;
+          continue;
+        }
+        const bool two = j + 1 < nj && s_a[j + 1] == ca && s_b[j + 1] == cb;
+        const int np = two ? 2 : 1;
+        double x[2][4];
+        if (cls < 5) {
+          // one row of M (or its column sums) for the whole tile: a broadcast read per particle
+          const int roff = cls == 4 ? 16 : 4 * cls;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) dmma8x8x4(c0, c1, A[o][ks], B[ks]);
-          // this lane: particle 8 o + row at sites s0 + 2 q4, s0 + 2 q4 + 1 (past the end: x = 1)
-          double x[2] = {s0 + 2 * q4 < a.n_sites ? c0 : 1.0, s0 + 2 * q4 + 1 < a.n_sites ? c1 : 1.0};
-          fold_sites<2>(x, renorm && blk == 7, &pr[o], &ex[o]);
+          for (int p = 0; p < 2; ++p) {
+            if (p < np) {
+              const double2* row = reinterpret_cast<const double2*>(sC + (j + p) * kCoef + roff);
+              const double2 r0 = row[0], r1 = row[1];
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                x[p][q] = fma(r1.y, Lb[q][3], fma(r1.x, Lb[q][2], fma(r0.y, Lb[q][1], fma(r0.x, Lb[q][0], x0[q]))));
+            }
+          }
+        } else {
+          // other ambiguity codes: the rows the mask covers, summed per site
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            if (p < np) {
+              const double* M = sC + (j + p) * kCoef;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                double acc = x0[q];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                  if (code[q] >> jj & 1) {
+                    double d = M[jj * 4] * Lb[q][0];
+#pragma unroll
+                    for (int m = 1; m < 4; ++m) d = fma(M[jj * 4 + m], Lb[q][m], d);
+                    acc += d;
+                  }
+                }
+                x[p][q] = acc;
+              }
+            }
+          }
+        }
+        // the product of the four site likelihoods is folded with ONE split into (mantissa, biased exponent); a product
+        // that is not a positive normal number poisons the running product and the particle is redone site by site
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          if (p < np) {
+            const double v = (x[p][0] * x[p][1]) * (x[p][2] * x[p][3]);
+            const int hi = __double2hiint(v);
+            const unsigned e = (unsigned)hi >> 20;
+            double pr = my_prod[(j + p) * kTileThreads];
+            int ex = my_exp[(j + p) * kTileThreads] + (int)e;
+            pr *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
+            if ((e - 1u) >= 0x7feu) pr = __longlong_as_double(0x7ff8000000000000ll);
+            if (renorm) {
+              const int h2 = __double2hiint(pr);
+              const unsigned e2 = ((unsigned)h2 >> 20) & 0x7ffu;
+              if (e2 != 0x7ffu) {
+                ex += (int)e2 - 1023;
+                pr = __hiloint2double((h2 & 0x000fffff) | 0x3ff00000, __double2loint(pr));
+              }
+            }
+            my_prod[(j + p) * kTileThreads] = pr;
+            my_exp[(j + p) * kTileThreads] = ex;
+          }
+        }
+        j += np;
+      }
+    }
+    // sum_s log x_s = log(prod mantissas) + ln2 * sum (exponents - bias): one fold (bias 1023) per thread and tile
+    const int bias = 1023 * (t_end - t_begin);
+    __syncthreads();
+    for (int j = wid; j < nj; j += kWarps) {
+      const int ca = s_a[j];
+      // tiles without sites of this leaf were skipped: their folds never happened
+      int folds = 0;
+      for (int t = t_begin + lane; t < t_end; t += 32) folds += a.tstate[(int64_t)ca * a.tiles + t] != 255;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) folds += __shfl_xor_sync(0xffffffffu, folds, o);
+      const int my_bias = 1023 * folds;
+      (void)bias;
+      double p = 1.0;
+      int e = 0;
+#pragma unroll
+      for (int i = 0; i < kTileThreads / 32; ++i) {
+        p *= s_prod[j * kTileThreads + lane + 32 * i];
+        e += s_exp[j * kTileThreads + lane + 32 * i] - my_bias;
+        const int hi = __double2hiint(p);
+        const int ee = (hi >> 20) & 0x7ff;
+        if (ee != 0x7ff) {   // (a poisoned product stays NaN)
+          p = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(p));
+          e += ee - 1023;
         }
       }
-      folded += 16;   // site values folded per lane and octet in this tile
-    }
-    // poisoned products: the particle is re-evaluated with one log per site (never on sane inputs)
-    unsigned odd_mask = 0u;
-#pragma unroll
-    for (int o = 0; o < 4; ++o)
-      if ((mine >> o & 1u) && pr[o] != pr[o]) odd_mask |= 1u << (8 * o + row);
-    if (odd_mask) atomicOr(&s_odd, odd_mask);
-    __syncthreads();
-    const unsigned odd_all = s_odd;
-    const int bias = 1023 * folded;
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      if (!(mine >> o & 1u)) continue;
-      const double e = (double)(ex[o] - bias);
-      double acc = fma(e, 6.93147180369123816490e-01, fma(e, 1.90821492927058770002e-10, log(pr[o])));
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      const int j = 8 * o + row;
-      if (q4 == 0 && !(odd_all >> j & 1u)) {
+      const double ef = (double)e;
+      double acc = fma(ef, 6.93147180369123816490e-01, fma(ef, 1.90821492927058770002e-10, log(p)));  // ln2 hi + lo
+      acc = warp_sum(acc);
+      if (__any_sync(0xffffffffu, p != p)) {
+        if (lane == 0) atomicOr(&s_odd, 1u << j);
+      } else {
         const int kk = s_k[j];
         const int64_t k = kk < 0 ? ~kk : kk;
-        a.ell_part[(k * a.n_chunks + tc) * kWarps + wid] = acc;
+        if (lane == 0) a.ell_part[k * a.n_parts + tc] = acc;
+        if (tc == 0)
+          for (int t = a.n_chunks + lane; t < a.n_parts; t += 32) a.ell_part[k * a.n_parts + t] = 0.0;
       }
     }
-    if (odd_all) {
-      for (int j = 0; j < nj; ++j) {
-        if (!(odd_all >> j & 1u)) continue;
-        double acc = score_slow<false>(cs, s_a[j], s_b[j], sC + j * 16, t_begin * kTile, min(a.n_sites, t_end * kTile),
-                                       pi[0], pi[1], pi[2], pi[3]);
-        acc = warp_sum(acc);
-        if (lane == 0) {
-          const int kk = s_k[j];
-          const int64_t k = kk < 0 ? ~kk : kk;
-          a.ell_part[(k * a.n_chunks + tc) * kWarps + wid] = acc;
-        }
+    __syncthreads();
+    const unsigned odd_all = s_odd;
+    for (int j = 0; odd_all && j < nj; ++j) {
+      if (!(odd_all >> j & 1u)) continue;
+      double acc = rows_slow(a, s_a[j], s_b[j], sC + j * kCoef, t_begin * kRowTile, t_end * kRowTile);
+      acc = warp_sum(acc);
+      __syncthreads();
+      if (lane == 0) s_slow[wid] = acc;
+      __syncthreads();
+      if (tid == 0) {
+        const int kk = s_k[j];
+        const int64_t k = kk < 0 ? ~kk : kk;
+        double t = s_slow[0];
+        for (int w2 = 1; w2 < kWarps; ++w2) t += s_slow[w2];
+        a.ell_part[k * a.n_parts + tc] = t;
+        if (tc == 0)
+          for (int q = a.n_chunks; q < a.n_parts; ++q) a.ell_part[k * a.n_parts + q] = 0.0;
       }
     }
   }
@@ -768,10 +932,41 @@ int launch_leaf_pair_hist(const uint8_t* codes, int64_t stride, int N, int S, in
   return VCSMC_OK;
 }
 
+int leaf_sort_stride(int n_sites) {   // padded length of a leaf's sorted site list: every class ends on a tile boundary
+  return (n_sites + kLeafClasses * kRowTile + kRowTile - 1) / kRowTile * kRowTile;
+}
+
+int launch_leaf_sort(const uint8_t* codes, int64_t stride, int N, int S, int32_t* perm, uint8_t* tstate, cudaStream_t st) {
+  if (N < 1 || S <= 0) return VCSMC_OK;
+  leaf_sort_kernel<<<N, 256, 0, st>>>(codes, stride, S, leaf_sort_stride(S), perm, tstate);
+  VCSMC_LAUNCH_CHECK("leaf_sort_kernel");
+  return VCSMC_OK;
+}
+
+namespace {
+// work items of one scoring launch: groups of R particles x chunks of tiles, about `items` of them
+void split_work(int64_t K, int tiles, int64_t items, int* R_out, int* tiles_per_item, int* n_chunks) {
+  int64_t R = (K * tiles) / items;   // groups as large as the machine fill allows (site data is amortised over the group)
+  if (R < 1) R = 1;
+  if (R > kRScore) R = kRScore;
+  const int64_t groups = (K + R - 1) / R;
+  int64_t nc = (items + groups - 1) / groups;  // split a group's tiles only when the groups cannot fill the SMs
+  if (nc < 1) nc = 1;
+  if (nc > tiles) nc = tiles;
+  *R_out = (int)R;
+  *tiles_per_item = (int)((tiles + nc - 1) / nc);
+  *n_chunks = (tiles + *tiles_per_item - 1) / *tiles_per_item;
+}
+}  // namespace
+
+// order == null: every particle in identity order through the generic kernel (its leaf path included).
+// order != null: the grouped order of the event kernel -- count[0] leaf + internal particles at the front (rows kernel,
+// needs leaf_perm / leaf_tstate), count[1] internal + internal particles at the end (generic kernel).
+// Particles with two leaf children are scored from the site-pattern histogram when leaf_hist is given.
 int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double* pool, int64_t slot_sites,
                        const int32_t* lsrc, const int32_t* rsrc, const int32_t* order, const double* P, const double* pi,
                        int64_t K, const int32_t* count, int n_sites, int jc, const int32_t* leaf_hist, int n_taxa,
-                       double* ell_part, int* n_parts, cudaStream_t st) {
+                       const int32_t* leaf_perm, const uint8_t* leaf_tstate, double* ell_part, int* n_parts, cudaStream_t st) {
   if (n_parts) *n_parts = 0;
   if (K <= 0 || n_sites <= 0) return VCSMC_OK;
   static int spt_general = 0;
@@ -782,54 +977,53 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
     VCSMC_CUDA(cudaFuncSetAttribute(merge_score_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoreSmemBytes));
     VCSMC_CUDA(cudaFuncSetAttribute(merge_score_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoreSmemBytes));
     VCSMC_CUDA(cudaFuncSetAttribute(merge_score_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoreSmemBytes));
+    VCSMC_CUDA(cudaFuncSetAttribute(merge_score_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScoreSmemBytes));
   }
-  const int spt = jc ? 4 : spt_general;
-  ScoreArgs a;
-  a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.slot_sites = slot_sites; a.lsrc = lsrc; a.rsrc = rsrc;
-  a.order = order; a.count = order ? count : nullptr; a.P = P; a.pi = pi; a.K = K; a.n_sites = n_sites; a.ell_part = ell_part;
-  a.skip_leaf_pairs = leaf_hist != nullptr;
-  static int use_mma = -1;
-  if (use_mma < 0) {
-    // VCSMC_SCORE_MMA=1 routes octets of particles that share a child pair to merge_score_mma_kernel (FP64 tensor cores).
-    // Measured at 64 x 10k x 65,536: 29.6 ms per sweep against 24.5 ms for the vector kernel alone -- DMMA and DFMA share
-    // one pipe on B200 (18.5 vs 18.2 T FMA/s) and the fold after each 8x8 block is the same work, so it stays off.
-    const char* e = getenv("VCSMC_SCORE_MMA");
-    use_mma = e ? atoi(e) != 0 : 0;
-  }
-  a.skip_octets = (!jc && spt == 2 && use_mma) ? 1 : 0;
-  a.tiles = (n_sites + kTileThreads * spt - 1) / (kTileThreads * spt);
   static int64_t items = 0;
   if (items == 0) {
     const char* e = getenv("VCSMC_SCORE_ITEMS");   // tuning knob: work items wanted per launch
     items = e ? atoll(e) : kScoreItems;
     if (items < 1) items = kScoreItems;
   }
-  // groups as large as the machine fill allows (shared children and site products are amortised over the group)
-  int64_t R = (K * a.tiles) / items;
-  if (R < 1) R = 1;
-  if (R > kRScore) R = kRScore;
-  a.R = (int)R;
-  const int64_t groups = (K + R - 1) / R;
-  int64_t nc = (items + groups - 1) / groups;  // split a group's tiles only when the groups cannot fill the SMs
-  if (nc < 1) nc = 1;
-  if (nc > a.tiles) nc = a.tiles;
-  a.tiles_per_item = (int)((a.tiles + nc - 1) / nc);
-  a.n_chunks = (a.tiles + a.tiles_per_item - 1) / a.tiles_per_item;
-  a.part_stride = a.skip_octets ? kWarps : 1;
-  if (n_parts) *n_parts = a.n_chunks * a.part_stride;
-  const int64_t total = groups * a.n_chunks;
+  const int spt = jc ? 4 : spt_general;
+  const bool rows = order != nullptr && leaf_perm != nullptr;
+  ScoreArgs a;
+  a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.slot_sites = slot_sites; a.lsrc = lsrc; a.rsrc = rsrc;
+  a.order = order; a.count = order ? (rows ? count + 1 : count) : nullptr; a.P = P; a.pi = pi; a.K = K; a.n_sites = n_sites; a.ell_part = ell_part;
+  a.skip_leaf_pairs = leaf_hist != nullptr;
+  a.from_end = rows ? 1 : 0;
+  a.tiles = (n_sites + kTileThreads * spt - 1) / (kTileThreads * spt);
+  split_work(K, a.tiles, items, &a.R, &a.tiles_per_item, &a.n_chunks);
+  RowArgs b;
+  memset(&b, 0, sizeof(b));
+  if (rows) {
+    b.codes = codes; b.codes_stride = codes_stride; b.pool = pool; b.slot_sites = slot_sites; b.lsrc = lsrc; b.rsrc = rsrc;
+    b.order = order; b.count = count; b.P = P; b.pi = pi; b.perm = leaf_perm; b.tstate = leaf_tstate; b.ell_part = ell_part;
+    b.Sp = leaf_sort_stride(n_sites);
+    b.tiles = b.Sp / kRowTile;
+    split_work(K, b.tiles, items, &b.R, &b.tiles_per_item, &b.n_chunks);
+  }
+  const int parts = rows && b.n_chunks > a.n_chunks ? b.n_chunks : a.n_chunks;
+  a.n_parts = parts;
+  b.n_parts = parts;
+  if (n_parts) *n_parts = parts;
   const int64_t cap = 148 * 2 * 8;
-  const unsigned grid = (unsigned)(total < cap ? total : cap);
-  if (jc) merge_score_kernel<true, 4><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
-  else if (spt == 4) merge_score_kernel<false, 4><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
-  else merge_score_kernel<false, 2><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
-  VCSMC_LAUNCH_CHECK("merge_score_kernel");
-  if (a.skip_octets && a.R >= 8) {
-    merge_score_mma_kernel<<<grid, kTileThreads, 0, st>>>(a);
-    VCSMC_LAUNCH_CHECK("merge_score_mma_kernel");
+  {
+    const int64_t total = ((K + a.R - 1) / a.R) * a.n_chunks;
+    const unsigned grid = (unsigned)(total < cap ? total : cap);
+    if (jc) merge_score_kernel<true, 4><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
+    else if (spt == 4) merge_score_kernel<false, 4><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
+    else merge_score_kernel<false, 2><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
+    VCSMC_LAUNCH_CHECK("merge_score_kernel");
+  }
+  if (rows) {
+    const int64_t total = ((K + b.R - 1) / b.R) * b.n_chunks;
+    const unsigned grid = (unsigned)(total < cap ? total : cap);
+    merge_score_rows_kernel<<<grid, kTileThreads, kScoreSmemBytes, st>>>(b);
+    VCSMC_LAUNCH_CHECK("merge_score_rows_kernel");
   }
   if (leaf_hist) {
-    score_leaf_pairs_kernel<<<(unsigned)((K + 7) / 8), 256, 0, st>>>(lsrc, rsrc, P, pi, K, n_taxa, leaf_hist, a.n_chunks * a.part_stride, ell_part);
+    score_leaf_pairs_kernel<<<(unsigned)((K + 7) / 8), 256, 0, st>>>(lsrc, rsrc, P, pi, K, n_taxa, leaf_hist, parts, ell_part);
     VCSMC_LAUNCH_CHECK("score_leaf_pairs_kernel");
   }
   return VCSMC_OK;

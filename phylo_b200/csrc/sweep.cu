@@ -822,6 +822,8 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_haskid = L.take<int32_t>(K);
     h->o_gocc = L.take<int32_t>(K);
     h->o_ev_timing = L.take<unsigned long long>(16 * (int64_t)N);
+    h->o_leaf_perm = L.take<int32_t>((int64_t)N * leaf_sort_stride(h->S));
+    h->o_leaf_tstate = L.take<uint8_t>((int64_t)N * (leaf_sort_stride(h->S) / 1024) + 16);
     h->o_leaf_hist = L.take<int32_t>(leaf_pair_hist_ints(N));
     for (int i = 0; i < 2; ++i) {   // forest scalars that travel with a particle (lazy.cu)
       h->o_F[i] = L.take<double>(K);
@@ -1063,6 +1065,8 @@ int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value) {
     return decide_modes(h, tables, h->ws_bytes, true);
   }
   else if (!strcmp(name, "leaf_patterns")) { h->leaf_patterns = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
+  else if (!strcmp(name, "force_sorted")) { h->force_sorted = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
+  else if (!strcmp(name, "leaf_rows")) { h->leaf_rows = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
   else if (!strcmp(name, "graph")) h->use_graph = value != 0.0;
   else if (!strcmp(name, "event_timing")) { h->event_timing = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
   else if (!strcmp(name, "peer_sync")) {

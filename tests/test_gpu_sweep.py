@@ -351,3 +351,37 @@ def test_seeded_sweep_matches_oracle_fed_the_same_philox_uniforms(ops, primate_g
     elbo = sw.forward(codes, dev(lam_l), dev(lam_r), dev(Q), dev(pi.reshape(-1)))
     assert float(elbo) == pytest.approx(float(res.elbo), rel=RTOL)
     np.testing.assert_array_equal(sw.output("ancestors").cpu().numpy()[1:], res.ancestors[1:])
+
+
+@pytest.mark.parametrize("leaf_rows", [True, False])
+@pytest.mark.parametrize("jc", [True, False])
+def test_grouped_scoring_kernels_against_oracle(ops, primate_genome, jc, leaf_rows):
+    """The grouped visiting order and its three scoring kernels (site patterns for two leaves, state-sorted rows for a
+    leaf + an internal node, the bilinear form for two internal nodes) are what large runs use; `force_sorted` puts a
+    small run on that path so that it can be checked against the oracle: gaps, ambiguity codes other than gaps (class
+    "other" of the leaf sort), more sites than one 1024-site tile, and a site count that is not a multiple of anything."""
+    g = np.concatenate([primate_genome[:9], primate_genome[:9, :403]], axis=1)   # 1301 sites
+    rng = np.random.default_rng(4)
+    amb = rng.random(g.shape[:2]) < 0.03
+    g[amb] = np.array([1.0, 0.0, 1.0, 0.0])          # R = A|G: neither one-hot nor a gap
+    g[rng.random(g.shape[:2]) < 0.03] = 1.0           # gaps
+    N, K = g.shape[0], 96
+    p = random_params(N, jc, seed=21)
+    U = O.Uniforms.draw(N, K, seed=31)
+    res, g_ref = oracle_param_grads(g, K, p, U)
+    codes = ops.pack_alignment(dev(g))
+    lam_l, lam_r, Q, pi = O.model_from_params(p)
+    sw = ops.Sweep(N, g.shape[1], K, jc)
+    sw.set_uniforms(*gpu_uniforms(U))
+    sw.set_option("force_sorted", 1.0)
+    sw.set_option("leaf_rows", 1.0 if leaf_rows else 0.0)
+    for it in range(2):   # the second sweep replays the captured graph
+        elbo = sw.forward(codes, dev(lam_l), dev(lam_r), None if jc else dev(Q), dev(pi.reshape(-1)))
+        out = {k: sw.output(k).cpu().numpy().copy() for k in
+               ("log_weights", "log_likelihood", "log_likelihood_tilde", "log_likelihood_R", "left_branches",
+                "right_branches", "v_minus", "ancestors", "left_ref", "right_ref", "leaf_counts")}
+        out["elbo"] = float(elbo.item())
+        grads = [None if t is None else t.cpu().numpy() for t in sw.backward(1.0)]
+        sw.check_status()
+        compare_forward(out, res, N, K)
+        compare_grads(grads, g_ref, jc)
