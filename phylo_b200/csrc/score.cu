@@ -430,12 +430,14 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
 // ---------------------------------------------------------------------------------------------
 // When child a is a LEAF, L_a[s] is a 0/1 mask and the site likelihood is row `state` of M (the column sums of M for a
 // gap) dotted with L_b[s].  leaf_sort_kernel lists every leaf's sites by state class once per sweep (A, C, G, T, gap,
-// other ambiguity codes; every class padded to whole 1024-site tiles with -1), so that all 1024 sites of a tile use the
-// SAME row: it is fetched once per particle (a broadcast read), the four sites of a thread cost 16 DFMA, their product
-// is folded into the running (mantissa, exponent) with ONE split -- against a per-lane row fetch, 4 + 1 FP64 ops and
-// a split per site in the generic kernel's leaf path, which was bound by instruction issue, not by the FP64 pipe.
-// The internal child is read through the permutation (32 B per site: whole sectors, so the gather costs nothing extra).
-constexpr int kRowTile = 1024;            // sorted positions per tile: 256 threads x 4
+// other ambiguity codes; every class padded to whole 256-site sub-tiles with -1), so that the 256 sites a CTA visits
+// together use the SAME row: it is fetched once per particle (a broadcast read), the four sites of a thread cost 16
+// DFMA, and their product is folded into the running (mantissa, exponent) with ONE split -- against a per-lane row
+// fetch, 4 + 1 FP64 ops and a split per site in the generic kernel's leaf path, which was bound by instruction issue,
+// not by the FP64 pipe.  The internal child is read through the permutation (32 B per site: whole sectors, so the
+// gather costs nothing extra).
+constexpr int kRowTile = 1024;            // sorted positions per tile: 256 threads x 4 sub-tiles
+constexpr int kRowSub = 256;              // positions per sub-tile (one state class each)
 constexpr int kLeafClasses = 6;
 
 __device__ __forceinline__ int leaf_class(int code) {
@@ -465,7 +467,7 @@ __global__ void __launch_bounds__(256) leaf_sort_kernel(const uint8_t* __restric
       int tot = 0;
       for (int t = 0; t < 256; ++t) tot += cnt[t][c];
       start[c] = at;
-      at += (tot + kRowTile - 1) / kRowTile * kRowTile;
+      at += (tot + kRowSub - 1) / kRowSub * kRowSub;
     }
     start[kLeafClasses] = at;
   }
@@ -485,13 +487,13 @@ __global__ void __launch_bounds__(256) leaf_sort_kernel(const uint8_t* __restric
       if (q == c) p = pos[q]++;
     out[p] = s;
   }
-  const int n_tiles = Sp / kRowTile;
-  for (int t = tid; t < n_tiles; t += 256) {
-    const int p = t * kRowTile;
+  const int n_sub = Sp / kRowSub;
+  for (int t = tid; t < n_sub; t += 256) {
+    const int p = t * kRowSub;
     int c = 255;   // no sites
     for (int q = 0; q < kLeafClasses; ++q)
       if (p >= start[q] && p < start[q + 1]) c = q;
-    tstate[(int64_t)leaf * n_tiles + t] = (uint8_t)c;
+    tstate[(int64_t)leaf * n_sub + t] = (uint8_t)c;
   }
 }
 
@@ -507,7 +509,7 @@ struct RowArgs {
   const double* P;
   const double* pi;
   const int32_t* perm;    // [N][Sp] sites of every leaf in state order (-1: padding)
-  const uint8_t* tstate;  // [N][tiles] state class of every tile (255: empty)
+  const uint8_t* tstate;  // [N][Sp / 256] state class of every sub-tile (255: empty)
   int Sp, tiles, tiles_per_item, n_chunks, R, n_parts;
   double* ell_part;
 };
@@ -535,18 +537,32 @@ __device__ __noinline__ double rows_slow(const RowArgs a, int leaf, int cb, cons
   return acc;
 }
 
+// fold the product v of a thread's four site likelihoods into a particle's running (mantissa product, biased exponent
+// sum): one split; a product that is not a positive normal number poisons the mantissa (the particle is redone site by site)
+__device__ __forceinline__ void fold_product(double v, double* pp, int* pe) {
+  const int hi = __double2hiint(v);
+  const unsigned e = (unsigned)hi >> 20;
+  double pr = *pp * __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
+  if ((e - 1u) >= 0x7feu) pr = __longlong_as_double(0x7ff8000000000000ll);
+  *pp = pr;
+  *pe += (int)e;
+}
+
 __global__ void __launch_bounds__(kTileThreads, 2) merge_score_rows_kernel(const RowArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sC = reinterpret_cast<double*>(smem_raw);                    // [R][20]: M[4][4] and its column sums
   double* s_prod = sC + kRScore * kCoef;                                 // [R][256] running mantissa products
   int* s_exp = reinterpret_cast<int*>(s_prod + kRScore * kTileThreads); // [R][256] running (biased) exponent sums
   __shared__ int s_k[kRScore], s_a[kRScore], s_b[kRScore];
+  __shared__ int s_run[kRScore + 1];   // first particle of every run of one (leaf, node) pair; s_run[n_runs] = nj
+  __shared__ int s_nruns;
   __shared__ double s_slow[kWarps];
   __shared__ unsigned s_odd;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int R = a.R;
   const int64_t count = (int64_t)*a.count;
   const int64_t total = ((count + R - 1) / R) * a.n_chunks;
+  const int n_sub = a.Sp / kRowSub;
   double pi[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
@@ -569,6 +585,13 @@ __global__ void __launch_bounds__(kTileThreads, 2) merge_score_rows_kernel(const
       s_k[tid] = sw ? ~k : k;
     }
     __syncthreads();
+    if (tid == 0) {
+      int nr = 0;
+      for (int j = 0; j < nj; ++j)
+        if (j == 0 || s_a[j] != s_a[j - 1] || s_b[j] != s_b[j - 1]) s_run[nr++] = j;
+      s_run[nr] = nj;
+      s_nruns = nr;
+    }
     for (int e = tid; e < nj * 16; e += kTileThreads) {   // M[j][m] = sum_i pi_i P_leaf[j][i] P_node[m][i]
       const int j = e >> 4, ai = (e >> 2) & 3, bi = e & 3;
       const int kk = s_k[j];
@@ -591,122 +614,114 @@ __global__ void __launch_bounds__(kTileThreads, 2) merge_score_rows_kernel(const
       my_exp[j * kTileThreads] = 0;
     }
     __syncthreads();
+    const int n_runs = s_nruns;
 
     const int t_begin = tc * a.tiles_per_item;
     const int t_end = min(a.tiles, t_begin + a.tiles_per_item);
     for (int t = t_begin; t < t_end; ++t) {
-      const bool renorm = ((t - t_begin) & 127) == 127;
-      int pa = -1, pb = kNone, cls = 255;
-      double Lb[4][4], x0[4];
-      int code[4];
-      int j = 0;
-      while (j < nj) {
-        const int ca = s_a[j], cb = s_b[j];
-        if (ca != pa || cb != pb) {   // a new (leaf, node) pair: this thread's four sites of the leaf's tile t
-          cls = a.tstate[(int64_t)ca * a.tiles + t];
-          const int32_t* pm = a.perm + (int64_t)ca * a.Sp + (int64_t)t * kRowTile + tid;
-          const double* node = a.pool + (int64_t)cb * a.slot_sites * 4;
+      for (int run = 0; run < n_runs; ++run) {
+        const int jb = s_run[run], je = s_run[run + 1];
+        const int ca = s_a[jb], cb = s_b[jb];
+        // the four sub-tiles of the leaf's tile t: state classes and this thread's four sites
+        const uchar4 c4 = *reinterpret_cast<const uchar4*>(a.tstate + (int64_t)ca * n_sub + (int64_t)t * 4);
+        if (c4.x == 255) continue;   // (classes are packed from the front: nothing of this leaf in tile t)
+        const int cls[4] = {c4.x, c4.y, c4.z, c4.w};
+        const int32_t* pm = a.perm + (int64_t)ca * a.Sp + (int64_t)t * kRowTile + tid;
+        const double* node = a.pool + (int64_t)cb * a.slot_sites * 4;
+        double Lb[4][4], x0[4];
+        int code[4];
+        bool other = false;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int s = cls != 255 ? __ldg(pm + q * kTileThreads) : -1;
-            code[q] = 0;
-            if (s >= 0) {
-              const d4 L = ld_site(node + (int64_t)s * 4);
+        for (int q = 0; q < 4; ++q) {
+          const int s = cls[q] != 255 ? __ldg(pm + q * kTileThreads) : -1;
+          code[q] = 0;
+          other = other || cls[q] == 5;
+          if (s >= 0) {
+            const d4 L = ld_site(node + (int64_t)s * 4);
 #pragma unroll
-              for (int m = 0; m < 4; ++m) Lb[q][m] = L.v[m];
-              x0[q] = 0.0;
-              if (cls == 5) code[q] = __ldg(a.codes + (int64_t)ca * a.codes_stride + s) & 15;
-            } else {
+            for (int m = 0; m < 4; ++m) Lb[q][m] = L.v[m];
+            x0[q] = 0.0;
+            if (cls[q] == 5) code[q] = __ldg(a.codes + (int64_t)ca * a.codes_stride + s) & 15;
+          } else {
 #pragma unroll
-              for (int m = 0; m < 4; ++m) Lb[q][m] = 0.0;
-              x0[q] = 1.0;   // padding: the site likelihood of "no site" is 1
-            }
+            for (int m = 0; m < 4; ++m) Lb[q][m] = 0.0;
+            x0[q] = 1.0;   // padding: the site likelihood of "no site" is 1
           }
-          pa = ca;
-          pb = cb;
         }
-        if (cls == 255) {   // nothing of this leaf in tile t
-          ++j;
-          continue;
-        }
-        const bool two = j + 1 < nj && s_a[j + 1] == ca && s_b[j + 1] == cb;
-        const int np = two ? 2 : 1;
-        double x[2][4];
-        if (cls < 5) {
-          // one row of M (or its column sums) for the whole tile: a broadcast read per particle
-          const int roff = cls == 4 ? 16 : 4 * cls;
+        double* pp = my_prod + jb * kTileThreads;
+        int* pe = my_exp + jb * kTileThreads;
+        const double* Mj = sC + jb * kCoef;
+        const int len = je - jb;
+        if (!other && c4.x == c4.y && c4.x == c4.z && c4.x == c4.w) {
+          // one row of M (or its column sums) for all four sub-tiles: a broadcast read per particle
+          const double* rowp = Mj + (c4.x == 4 ? 16 : 4 * c4.x);
+#pragma unroll 2
+          for (int i = 0; i < len; ++i, pp += kTileThreads, pe += kTileThreads, rowp += kCoef) {
+            const double2 r0 = *reinterpret_cast<const double2*>(rowp), r1 = *reinterpret_cast<const double2*>(rowp + 2);
+            double x[4];
 #pragma unroll
-          for (int p = 0; p < 2; ++p) {
-            if (p < np) {
-              const double2* row = reinterpret_cast<const double2*>(sC + (j + p) * kCoef + roff);
-              const double2 r0 = row[0], r1 = row[1];
+            for (int q = 0; q < 4; ++q)
+              x[q] = fma(r1.y, Lb[q][3], fma(r1.x, Lb[q][2], fma(r0.y, Lb[q][1], fma(r0.x, Lb[q][0], x0[q]))));
+            fold_product((x[0] * x[1]) * (x[2] * x[3]), pp, pe);
+          }
+        } else if (!other) {
+          // sub-tiles of different classes (a class boundary inside the tile): a row per sub-tile
+          int roff[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                x[p][q] = fma(r1.y, Lb[q][3], fma(r1.x, Lb[q][2], fma(r0.y, Lb[q][1], fma(r0.x, Lb[q][0], x0[q]))));
+          for (int q = 0; q < 4; ++q) roff[q] = cls[q] == 4 ? 16 : cls[q] == 255 ? 0 : 4 * cls[q];
+          for (int i = 0; i < len; ++i, pp += kTileThreads, pe += kTileThreads, Mj += kCoef) {
+            double x[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const double2 r0 = *reinterpret_cast<const double2*>(Mj + roff[q]), r1 = *reinterpret_cast<const double2*>(Mj + roff[q] + 2);
+              x[q] = fma(r1.y, Lb[q][3], fma(r1.x, Lb[q][2], fma(r0.y, Lb[q][1], fma(r0.x, Lb[q][0], x0[q]))));
             }
+            fold_product((x[0] * x[1]) * (x[2] * x[3]), pp, pe);
           }
         } else {
-          // other ambiguity codes: the rows the mask covers, summed per site
+          // other ambiguity codes somewhere in the tile: the rows each site's mask covers, summed per site
+          for (int i = 0; i < len; ++i, pp += kTileThreads, pe += kTileThreads, Mj += kCoef) {
+            double x[4];
 #pragma unroll
-          for (int p = 0; p < 2; ++p) {
-            if (p < np) {
-              const double* M = sC + (j + p) * kCoef;
+            for (int q = 0; q < 4; ++q) {
+              const int mask = cls[q] == 5 ? code[q] : cls[q] == 4 ? 15 : cls[q] == 255 ? 0 : 1 << cls[q];
+              double acc = x0[q];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                double acc = x0[q];
+              for (int jj = 0; jj < 4; ++jj) {
+                if (mask >> jj & 1) {
+                  double d = Mj[jj * 4] * Lb[q][0];
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                  if (code[q] >> jj & 1) {
-                    double d = M[jj * 4] * Lb[q][0];
-#pragma unroll
-                    for (int m = 1; m < 4; ++m) d = fma(M[jj * 4 + m], Lb[q][m], d);
-                    acc += d;
-                  }
+                  for (int m = 1; m < 4; ++m) d = fma(Mj[jj * 4 + m], Lb[q][m], d);
+                  acc += d;
                 }
-                x[p][q] = acc;
               }
+              x[q] = acc;
             }
+            fold_product((x[0] * x[1]) * (x[2] * x[3]), pp, pe);
           }
         }
-        // the product of the four site likelihoods is folded with ONE split into (mantissa, biased exponent); a product
-        // that is not a positive normal number poisons the running product and the particle is redone site by site
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          if (p < np) {
-            const double v = (x[p][0] * x[p][1]) * (x[p][2] * x[p][3]);
-            const int hi = __double2hiint(v);
-            const unsigned e = (unsigned)hi >> 20;
-            double pr = my_prod[(j + p) * kTileThreads];
-            int ex = my_exp[(j + p) * kTileThreads] + (int)e;
-            pr *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
-            if ((e - 1u) >= 0x7feu) pr = __longlong_as_double(0x7ff8000000000000ll);
-            if (renorm) {
-              const int h2 = __double2hiint(pr);
-              const unsigned e2 = ((unsigned)h2 >> 20) & 0x7ffu;
-              if (e2 != 0x7ffu) {
-                ex += (int)e2 - 1023;
-                pr = __hiloint2double((h2 & 0x000fffff) | 0x3ff00000, __double2loint(pr));
-              }
-            }
-            my_prod[(j + p) * kTileThreads] = pr;
-            my_exp[(j + p) * kTileThreads] = ex;
+      }
+      if (((t - t_begin) & 127) == 127) {   // keep the mantissa products far from 2^1024 (NaN stays NaN)
+        for (int j = 0; j < nj; ++j) {
+          const double pr = my_prod[j * kTileThreads];
+          const int h2 = __double2hiint(pr);
+          const unsigned e2 = ((unsigned)h2 >> 20) & 0x7ffu;
+          if (e2 != 0x7ffu) {
+            my_exp[j * kTileThreads] += (int)e2 - 1023;
+            my_prod[j * kTileThreads] = __hiloint2double((h2 & 0x000fffff) | 0x3ff00000, __double2loint(pr));
           }
         }
-        j += np;
       }
     }
-    // sum_s log x_s = log(prod mantissas) + ln2 * sum (exponents - bias): one fold (bias 1023) per thread and tile
-    const int bias = 1023 * (t_end - t_begin);
+    // sum_s log x_s = log(prod mantissas) + ln2 * sum (exponents - bias): one fold (bias 1023) per thread and non-empty tile
     __syncthreads();
     for (int j = wid; j < nj; j += kWarps) {
       const int ca = s_a[j];
-      // tiles without sites of this leaf were skipped: their folds never happened
       int folds = 0;
-      for (int t = t_begin + lane; t < t_end; t += 32) folds += a.tstate[(int64_t)ca * a.tiles + t] != 255;
+      for (int t = t_begin + lane; t < t_end; t += 32) folds += a.tstate[(int64_t)ca * n_sub + (int64_t)t * 4] != 255;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) folds += __shfl_xor_sync(0xffffffffu, folds, o);
       const int my_bias = 1023 * folds;
-      (void)bias;
       double p = 1.0;
       int e = 0;
 #pragma unroll
@@ -932,8 +947,8 @@ int launch_leaf_pair_hist(const uint8_t* codes, int64_t stride, int N, int S, in
   return VCSMC_OK;
 }
 
-int leaf_sort_stride(int n_sites) {   // padded length of a leaf's sorted site list: every class ends on a tile boundary
-  return (n_sites + kLeafClasses * kRowTile + kRowTile - 1) / kRowTile * kRowTile;
+int leaf_sort_stride(int n_sites) {   // padded length of a leaf's sorted site list: every class ends on a sub-tile boundary
+  return (n_sites + kLeafClasses * kRowSub + kRowTile - 1) / kRowTile * kRowTile;
 }
 
 int launch_leaf_sort(const uint8_t* codes, int64_t stride, int N, int S, int32_t* perm, uint8_t* tstate, cudaStream_t st) {
