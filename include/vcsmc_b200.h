@@ -177,20 +177,29 @@ int vcsmc_sweep_set_allreduce(vcsmc_sweep_t* h, vcsmc_allreduce_fn fn, void* use
 int vcsmc_sweep_set_comm(vcsmc_sweep_t* h, int rank, int world, vcsmc_comm_fn fn, void* user, void* const* peer_ws_host);
 /* Options: "scalar_share" (default 1): fraction of the site-independent gradient terms this rank contributes
  * (site sharding: 1 on rank 0, 0 elsewhere, then sum the gradients across ranks);
- * "skip_zero" (default 1): backward skips rank events whose adjoint is exactly zero (W underflowed to 0 and no
- * descendant uses the node) -- results are identical, set 0 to force the dense reverse sweep;
+ * "skip_zero" (default 1): backward skips rank events whose adjoint is zero (W underflowed to 0 and no descendant
+ * uses the node; see skip_below for what counts as zero), set 0 to force the dense reverse sweep;
  * "skip_below" (default 2^-64): with skip_zero, an adjoint coefficient dELBO/d ell of magnitude <= skip_below * |grad_elbo|
  * counts as zero (softmax weights of 1e-200 are representable in fp64 but cannot change any digit of the gradient:
- * the event's coefficients sum to O(1)); 0 restores "exactly zero only" -- gradients agree to ~1e-15 relative;
+ * the event's coefficients sum to O(1)); 0 restores "exactly zero only".  This is an APPROXIMATION of the gradient:
+ * the dropped terms are bounded by K * skip_below * max |d ell / d theta| per rank event; the two settings agree to
+ * 1e-11 relative on primate.p (tested);
  * "max_chunk_sites" (default 0 = unlimited): cap on the site chunk of the recompute backward (testing aid);
  * "lazy" (default 1; VCSMC proposal only): the forward scores every particle without storing its node and materialises
  * only the particles that the next resampling draws as an ancestor; 0 = eager (every node stored as it is computed) --
  * results are identical;
  * "leaf_patterns" (default 1; lazy forward): merges of two leaves are scored from the site-pattern counts of the leaf
  * pair (tabulated once per sweep) instead of site by site -- same sum, different summation order;
+ * "leaf_rows" (default 1; lazy forward, grouped order): merges of a leaf and an internal node are scored by the rows
+ * kernel on the leaf's state-sorted sites (one row of the bilinear form per 256-site sub-tile) -- same sum, different
+ * summation order; 0 leaves them to the generic scoring kernel;
+ * "force_sorted" (default 0): grouped visiting order even when K is too small for it to pay (testing aid);
+ * "event_timing" (default 0; lazy forward): CTA 0 of the event kernel stamps %globaltimer at every phase boundary
+ * (output "event_timing", uint64 [N][16]);
  * "peer_sync" (default 1; particle sharding): the two synchronisations of a rank event and the exchange of the step
- * record run over peer memory (flag barrier kernel, peer loads) with no host involvement; 0 routes them through the
- * collective hook (VCSMC_COMM_BARRIER / VCSMC_COMM_ALLGATHER) instead;
+ * record run over peer memory (flags polled inside the event kernel, peer loads) with no host involvement.  The
+ * collective-hook route (0) of the first round is gone: the forward is one cooperative kernel per rank event and
+ * cannot call back into the host between its phases;
  * "graph" (default 1; lazy forward): from the second forward on, the launch sequence of the forward sweep (no host
  * synchronisation, seed and model read from the workspace) is captured once into a CUDA graph and replayed;
  * "force_gc" (default 0): use the garbage-collected pool and the recompute backward even when every node fits (testing aid);
@@ -218,8 +227,9 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
 
 /* Per-kernel device time of the merge launches since the option "profile" was set to 1 (CUDA events on the
  * launching stream): out_host[8] = {ms, launches} for the forward merge (eager) or scoring kernel (lazy), the recompute
- * merge of the chunked backward, the backward merge, and the survivor materialisation + peer pulls.  Synchronises on the
- * recorded events and resets the counters. */
+ * merge of the chunked backward, the backward merge, and the lazy forward's cooperative event kernel (one launch per
+ * rank event: weights, CDF, ancestors, rows, survivors, proposal) or, with n_sub > 0, the look-ahead kernel.
+ * Synchronises on the recorded events and resets the counters. */
 int vcsmc_sweep_profile(vcsmc_sweep_t* h, double* out_host);
 
 /* Device pointers into the workspace, valid after forward:
@@ -229,7 +239,10 @@ int vcsmc_sweep_profile(vcsmc_sweep_t* h, double* out_host);
  *   "log_z"[N-1] "ess"[N-1] (float64)   "status"[8] (int32: error, peak pool slots, backward chunks, ...)
  *   "choice"[N-1,K] (int32, VNCSMC only: the chosen option t*M+m of vncsmc.py:298)
  *   "rem_positions" (uint8, ragged: rank event r holds [K, N-r-2] at byte offset sum_{r'<r} align16(K (N-r'-2)):
- *   the positions, in the ancestor's forest, of the subtrees a particle keeps, in the reference's order)
+ *   the positions, in the ancestor's forest, of the subtrees a particle keeps, in the reference's order.  The lazy
+ *   forward fills the rows of particles whose normalised weight is not zero in double precision -- the only ones that can
+ *   be resampled or carry a gradient -- and leaves the others at position 0)
+ *   "event_timing" (uint64 [N][16], lazy forward with option "event_timing")
  * Returns NULL for an unknown name. */
 void* vcsmc_sweep_output(vcsmc_sweep_t* h, const char* name);
 

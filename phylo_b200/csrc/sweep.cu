@@ -1192,8 +1192,10 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
                                  h->keep ? h->p<int32_t>(h->o_rows_all) + (int64_t)r * K * N : nullptr, a.LL_prev, a.anc, a.ll_tilde, st);
       if (rc) return rc;
       double* pot = h->p<double>(h->o_pot) + h->pot_off[r];
+      h->prof_begin(3, st);
       rc = launch_lookahead(r, n, N, h->M, h->jc, h->fwd_gc, S, K, inh_ids, inh_cnt, inh_slot, codes, S, pool, S, ell_node,
                             h->p<double>(h->o_ldf), Q, pi, lam_l, lam_r, lk_bl, lk_br, h->seed, pot, st);
+      h->prof_end(st);
       if (rc) return rc;
       rc = launch_nested_choose(r, n, N, h->M, h->fwd_gc, K, pot, u_cat, lk_bl, lk_br, h->seed, lam_l, lam_r, inh_ids, inh_cnt,
                                 inh_slot, a.ids_new, a.cnt_new, a.slot_new, a.lref, a.rref, a.nleaf, a.rempos,
@@ -1617,7 +1619,7 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
 
 int vcsmc_sweep_profile(vcsmc_sweep_t* h, double* out_host) {
   // out_host[8] = {ms, launches} for kind 0 (forward merge / scoring), 1 (recompute merge), 2 (backward merge),
-  // 3 (survivor materialisation + peer pulls); resets.
+  // 3 (lazy forward: the cooperative event kernel; nested proposal: the look-ahead kernel); resets.
   if (!h || !out_host) return VCSMC_ERR_ARG;
   for (int i = 0; i < 8; ++i) out_host[i] = 0.0;
   for (size_t i = 0; i + 1 < h->ev_used; i += 2) {

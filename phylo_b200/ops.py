@@ -324,7 +324,7 @@ class Sweep:
         buf = (C.c_double * 8)()
         check(self._lib.vcsmc_sweep_profile(self._h, buf))
         return {"merge_fwd": (buf[0], int(buf[1])), "merge_fwd_recompute": (buf[2], int(buf[3])),
-                "merge_bwd": (buf[4], int(buf[5])), "event_kernel": (buf[6], int(buf[7]))}
+                "merge_bwd": (buf[4], int(buf[5])), ("lookahead" if self.M else "event_kernel"): (buf[6], int(buf[7]))}
 
     def rem_positions(self):
         """Per rank event r, the uint8 [K, N-r-2] table of kept forest positions (host numpy), see the header."""
