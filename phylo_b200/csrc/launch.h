@@ -19,13 +19,14 @@ int launch_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* p
                      int64_t n_active, int n_sites, int jc, int skip_zero, double skip_below, double* dP, double* dpi_acc, cudaStream_t st);
 
 // score.cu (lazy forward: likelihood-only scoring, survivor materialisation, peer pulls)
+constexpr int kLeafPairInts = 512;   // ints per leaf pair in the site-pattern table (see leaf_pair_hist_kernel)
 int64_t leaf_pair_hist_ints(int N);
 int launch_leaf_pair_hist(const uint8_t* codes, int64_t stride, int N, int S, int32_t* hist, cudaStream_t st);
 int leaf_sort_stride(int n_sites);
 int launch_leaf_sort(const uint8_t* codes, int64_t stride, int N, int S, int32_t* perm, uint8_t* tstate, cudaStream_t st);
 int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double* pool, int64_t slot_sites,
                        const int32_t* lsrc, const int32_t* rsrc, const int32_t* order, const double* P, const double* pi,
-                       int64_t K, const int32_t* count, int n_sites, int jc, const int32_t* leaf_hist, int n_taxa,
+                       int64_t K, const int32_t* count, int n_sites, int jc, int skip_leaf_pairs,
                        const int32_t* leaf_perm, const uint8_t* leaf_tstate, double* ell_part, int* n_parts, cudaStream_t st);
 int launch_materialise(const uint8_t* codes, int64_t codes_stride, double* pool, int64_t slot_sites, const int32_t* lsrc,
                        const int32_t* rsrc, const int32_t* list, const int32_t* count, int64_t max_count, const int32_t* loc,

@@ -83,6 +83,9 @@ struct EvArgs {
   double* pT;                 // [Kl] topology prior of the forest after the merge
   int32_t* pV;                // [Kl] v^- of the forest after the merge
   double* pLLt;               // [Kl] log_likelihood_tilde
+  double* pEll;               // [Kl] log-likelihood of the new node when the proposing thread scored it (two leaves)
+  int32_t* pDirect;           // [Kl] 1: pEll is valid, the scoring kernels skipped the particle
+  const int32_t* leaf_tab;    // site-pattern table of every leaf pair (leaf_pair_hist_kernel), or null
   int32_t* vminus;            // [K] output
   int32_t* lsrc[2];           // [Kl] child slots, by event parity
   int32_t* rsrc[2];
@@ -661,6 +664,56 @@ __device__ __forceinline__ void propose_particle(const EvArgs& a, int64_t kl, bo
       }
     }
   }
+  // ---- two leaves: the site likelihood depends on the site only through the two state masks, so
+  //   sum_s log x[s] = sum over patterns of count(c_a, c_b) log x(c_a, c_b),  x = sum_{j in c_a, m in c_b} M[j][m],
+  //   M[j][m] = sum_i pi_i P_a[j][i] P_b[m][i]
+  // with the pattern counts of the leaf pair tabulated once per sweep (site-pattern compression, applied per cherry)
+  if (on) {
+    const bool cherry = a.leaf_tab != nullptr && ls < 0 && rs < 0;
+    a.pDirect[kl] = cherry;
+    if (cherry) {
+      const int la = -ls - 1, lb = -rs - 1;
+      const bool sw = la > lb;
+      const int lo = sw ? lb : la, hi = sw ? la : lb;
+      const int32_t* tab = a.leaf_tab + ((int64_t)lo * (2 * N - lo - 1) / 2 + (hi - lo - 1)) * kLeafPairInts;
+      const double* Pa = a.P + ((int64_t)r * K + k) * 32 + (sw ? 16 : 0);   // rows of M follow the LOWER leaf
+      const double* Pb = a.P + ((int64_t)r * K + k) * 32 + (sw ? 0 : 16);
+      double pi[4], M[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pi[i] = a.pi[i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const d4 ra = ld_site(Pa + 4 * j);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const d4 rb = ld_site(Pb + 4 * m);
+          double v = pi[0] * ra.v[0] * rb.v[0];
+#pragma unroll
+          for (int i = 1; i < 4; ++i) v = fma(pi[i] * ra.v[i], rb.v[i], v);
+          M[j * 4 + m] = v;
+        }
+      }
+      double acc = 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int c = tab[q];
+        if (c != 0) acc = fma((double)c, log(M[q]), acc);
+      }
+      const int n_amb = tab[16];
+      for (int t = 0; t < n_amb; ++t) {   // gaps and other ambiguity codes: the entries of M the two masks cover
+        const int bin = tab[17 + 2 * t], c = tab[18 + 2 * t];
+        const int ca = bin >> 4, cb = bin & 15;
+        double x = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+          for (int mm = 0; mm < 4; ++mm)
+            if ((ca >> jj & 1) && (cb >> mm & 1)) x += M[jj * 4 + mm];
+        acc = fma((double)c, log(x), acc);
+      }
+      a.pEll[kl] = acc;
+    }
+  }
   if (!a.sorted) return;
   // ---- child-pair hash table of the scoring kernel: particles with the same (unordered) pair become adjacent
   bool ins = on && !(a.skip_leaf_pairs && ls < 0 && rs < 0);   // two leaves: scored from site patterns, not listed
@@ -721,7 +774,9 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
       double m = -INFINITY;
       for (int64_t kl = gtid; kl < Kl; kl += gthreads) {
         double ell = 0.0;
-        for (int t = 0; t < a.tiles; ++t) ell += a.ell_part[kl * a.tiles + t];
+        if (a.pDirect[kl]) ell = a.pEll[kl];
+        else
+          for (int t = 0; t < a.tiles; ++t) ell += a.ell_part[kl * a.tiles + t];
         m = fmax(m, particle_weight(a, k0 + kl, ell));
       }
       if (a.world == 1) {
@@ -1114,6 +1169,7 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
   a.cum_l = h->p<double>(h->o_cum_l); a.cum_r = h->p<double>(h->o_cum_r); a.lw = h->p<double>(h->o_lw); a.LL = h->p<double>(h->o_LL);
   a.P = h->p<double>(h->o_P); a.ell_node = ell_node; a.stats = h->p<double>(h->o_stats);
   a.pF = h->p<double>(h->o_pF); a.pT = h->p<double>(h->o_pT); a.pV = h->p<int32_t>(h->o_pV); a.pLLt = h->p<double>(h->o_pLLt);
+  a.pEll = h->p<double>(h->o_pEll); a.pDirect = h->p<int32_t>(h->o_pDirect); a.leaf_tab = leaf_hist;
   a.vminus = h->p<int32_t>(h->o_vminus);
   a.lsrc[0] = h->p<int32_t>(h->o_lsrc); a.rsrc[0] = h->p<int32_t>(h->o_rsrc);
   a.lsrc[1] = h->p<int32_t>(h->o_lsrc2); a.rsrc[1] = h->p<int32_t>(h->o_rsrc2);
@@ -1207,7 +1263,7 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     int tiles = 0;
     h->prof_begin(0, st);
     rc = launch_merge_score(codes, S, h->p<double>(h->o_pool), S, a.lsrc[cur], a.rsrc[cur], sorted ? a.order : nullptr, P, pi, Kl,
-                            sorted ? a.gcount : nullptr, S, h->jc, leaf_hist, N, leaf_perm, leaf_tstate, h->p<double>(h->o_ell_part), &tiles, st);
+                            sorted ? a.gcount : nullptr, S, h->jc, leaf_hist != nullptr, leaf_perm, leaf_tstate, h->p<double>(h->o_ell_part), &tiles, st);
     h->prof_end(st);
     if (rc) return rc;
     a.ell_part = h->p<double>(h->o_ell_part);

@@ -12,7 +12,8 @@
 //                        4 DFMA (JC: x = a1 sa sb + a2 sa pb + a3 pa sb + a4 pab) instead of ~41; when child a is a
 //                        leaf with one-hot / all-ones masks it is row `state` of M dotted with L_b (4 DFMA).
 //                        Children come from L2; bound by instruction issue around the FP64 pipe.
-//   score_leaf_pairs_kernel  particles whose children are both leaves: site patterns instead of sites.
+//   (particles whose children are both leaves are scored from the pair's site-pattern counts by the proposing thread
+//   of the event kernel, lazy.cu: leaf_pair_hist_kernel tabulates the patterns of every leaf pair once per sweep)
 //   merge_score_rows_kernel  particles whose children are a LEAF and an internal node (most of the scored work on
 //                        leaf-rich forests): the sites are visited in the leaf's state order (leaf_sort_kernel, once per
 //                        sweep), so a 1024-site tile shares ONE row of M per particle and a site costs 4 DFMA + 1/4 fold.
@@ -864,12 +865,12 @@ __global__ void __launch_bounds__(kTileThreads) pull_kernel(const PullArgs a) {
 // tabulated once per sweep (site-pattern compression, the standard trick of likelihood codes, applied per cherry); a
 // cherry then costs a few dozen logs per particle instead of S site evaluations.  About a third of all merges of a
 // sweep join two leaves.
-__device__ __forceinline__ int64_t leaf_pair_index(int a, int b, int N) {  // a < b
-  return (int64_t)a * (2 * N - a - 1) / 2 + (b - a - 1);
-}
 
+// Pattern table of one leaf pair (kLeafPairInts ints): [0,16) counts of the one-hot x one-hot patterns (state j of the
+// lower leaf, state m of the higher one, at j*4+m); [16] number of other patterns with a nonzero count; then
+// (mask_a * 16 + mask_b, count) pairs for those.  The event kernel scores a cherry from it in the proposing thread.
 __global__ void __launch_bounds__(256) leaf_pair_hist_kernel(const uint8_t* __restrict__ codes, int64_t stride, int N, int S,
-                                                             int32_t* __restrict__ hist) {
+                                                             int32_t* __restrict__ table) {
   __shared__ int sh[256];
   // blockIdx.x enumerates the pairs a < b in leaf_pair_index order
   int a = 0;
@@ -885,60 +886,28 @@ __global__ void __launch_bounds__(256) leaf_pair_hist_kernel(const uint8_t* __re
   const uint8_t* rb = codes + (int64_t)b * stride;
   for (int s = threadIdx.x; s < S; s += 256) atomicAdd(&sh[(ra[s] & 15) * 16 + (rb[s] & 15)], 1);
   __syncthreads();
-  hist[(int64_t)blockIdx.x * 256 + threadIdx.x] = sh[threadIdx.x];
-}
-
-// one warp per particle: 16 lanes build M[j][m] = sum_i pi_i P_l[j][i] P_r[m][i] (the likelihood of the one-hot pattern
-// (j, m)), then the lanes share the 256 patterns; a pattern with ambiguity masks sums the M entries its masks cover
-__global__ void __launch_bounds__(256) score_leaf_pairs_kernel(const int32_t* __restrict__ lsrc, const int32_t* __restrict__ rsrc,
-                                                               const double* __restrict__ P, const double* __restrict__ pi_,
-                                                               int64_t K, int N, const int32_t* __restrict__ hist,
-                                                               int n_parts, double* __restrict__ ell_part) {
-  __shared__ double sM[8][16];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t k = (int64_t)blockIdx.x * 8 + wid;
-  if (k >= K) return;
-  const int ls = lsrc[k], rs = rsrc[k];
-  if (ls >= 0 || rs >= 0) return;  // (whole warp)
-  const int la = -ls - 1, lb = -rs - 1;  // leaf indices of the left / right child
-  const bool sw = la > lb;
-  const int32_t* h = hist + leaf_pair_index(sw ? lb : la, sw ? la : lb, N) * 256;
-  int c[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) c[q] = __ldg(h + lane + 32 * q);
-  if (lane < 16) {
-    // rows of M follow the LOWER leaf (the histogram's first code), columns the higher one
-    const double* Pa = P + k * 32 + (sw ? 16 : 0) + (lane >> 2) * 4;
-    const double* Pb = P + k * 32 + (sw ? 0 : 16) + (lane & 3) * 4;
-    double m = __ldg(pi_) * __ldg(Pa) * __ldg(Pb);
-#pragma unroll
-    for (int i = 1; i < 4; ++i) m = fma(__ldg(pi_ + i) * __ldg(Pa + i), __ldg(Pb + i), m);
-    sM[wid][lane] = m;
+  int32_t* out = table + (int64_t)blockIdx.x * kLeafPairInts;
+  if (threadIdx.x < 16) out[threadIdx.x] = sh[(1 << (threadIdx.x >> 2)) * 16 + (1 << (threadIdx.x & 3))];
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int bin = 0; bin < 256; ++bin) {
+      const int ca = bin >> 4, cb = bin & 15;
+      const bool onehot = ca != 0 && cb != 0 && (ca & (ca - 1)) == 0 && (cb & (cb - 1)) == 0;
+      if (!onehot && sh[bin] != 0) {
+        out[17 + 2 * n] = bin;
+        out[18 + 2 * n] = sh[bin];
+        ++n;
+      }
+    }
+    out[16] = n;
   }
-  __syncwarp();
-  double acc = 0.0;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    if (c[q] == 0) continue;
-    const int bin = lane + 32 * q, ca = bin >> 4, cb = bin & 15;
-    double x = 0.0;
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-      for (int mm = 0; mm < 4; ++mm)
-        if ((ca >> jj & 1) && (cb >> mm & 1)) x += sM[wid][jj * 4 + mm];
-    acc = fma((double)c[q], log(x), acc);
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) ell_part[k * n_parts] = acc;
-  for (int t = 1 + lane; t < n_parts; t += 32) ell_part[k * n_parts + t] = 0.0;
 }
 
 constexpr int64_t kScoreItems = 148 * 32;  // work items wanted per launch (measured: 592 .. 18,944; work per item is uneven)
 
 }  // namespace
 
-int64_t leaf_pair_hist_ints(int N) { return (int64_t)N * (N - 1) / 2 * 256; }
+int64_t leaf_pair_hist_ints(int N) { return (int64_t)N * (N - 1) / 2 * kLeafPairInts; }
 
 int launch_leaf_pair_hist(const uint8_t* codes, int64_t stride, int N, int S, int32_t* hist, cudaStream_t st) {
   if (N < 2 || S <= 0) return VCSMC_OK;
@@ -977,10 +946,10 @@ void split_work(int64_t K, int tiles, int64_t items, int* R_out, int* tiles_per_
 // order == null: every particle in identity order through the generic kernel (its leaf path included).
 // order != null: the grouped order of the event kernel -- count[0] leaf + internal particles at the front (rows kernel,
 // needs leaf_perm / leaf_tstate), count[1] internal + internal particles at the end (generic kernel).
-// Particles with two leaf children are scored from the site-pattern histogram when leaf_hist is given.
+// skip_leaf_pairs: particles with two leaf children have been scored from the pair's site patterns by the event kernel.
 int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double* pool, int64_t slot_sites,
                        const int32_t* lsrc, const int32_t* rsrc, const int32_t* order, const double* P, const double* pi,
-                       int64_t K, const int32_t* count, int n_sites, int jc, const int32_t* leaf_hist, int n_taxa,
+                       int64_t K, const int32_t* count, int n_sites, int jc, int skip_leaf_pairs,
                        const int32_t* leaf_perm, const uint8_t* leaf_tstate, double* ell_part, int* n_parts, cudaStream_t st) {
   if (n_parts) *n_parts = 0;
   if (K <= 0 || n_sites <= 0) return VCSMC_OK;
@@ -1005,7 +974,7 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
   ScoreArgs a;
   a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.slot_sites = slot_sites; a.lsrc = lsrc; a.rsrc = rsrc;
   a.order = order; a.count = order ? (rows ? count + 1 : count) : nullptr; a.P = P; a.pi = pi; a.K = K; a.n_sites = n_sites; a.ell_part = ell_part;
-  a.skip_leaf_pairs = leaf_hist != nullptr;
+  a.skip_leaf_pairs = skip_leaf_pairs;
   a.from_end = rows ? 1 : 0;
   a.tiles = (n_sites + kTileThreads * spt - 1) / (kTileThreads * spt);
   split_work(K, a.tiles, items, &a.R, &a.tiles_per_item, &a.n_chunks);
@@ -1036,10 +1005,6 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
     const unsigned grid = (unsigned)(total < cap ? total : cap);
     merge_score_rows_kernel<<<grid, kTileThreads, kScoreSmemBytes, st>>>(b);
     VCSMC_LAUNCH_CHECK("merge_score_rows_kernel");
-  }
-  if (leaf_hist) {
-    score_leaf_pairs_kernel<<<(unsigned)((K + 7) / 8), 256, 0, st>>>(lsrc, rsrc, P, pi, K, n_taxa, leaf_hist, parts, ell_part);
-    VCSMC_LAUNCH_CHECK("score_leaf_pairs_kernel");
   }
   return VCSMC_OK;
 }

@@ -815,6 +815,8 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_pT = L.take<double>(K);
     h->o_pV = L.take<int32_t>(K);
     h->o_pLLt = L.take<double>(K);
+    h->o_pEll = L.take<double>(K);
+    h->o_pDirect = L.take<int32_t>(K);
     h->o_lsrc2 = L.take<int32_t>(K);
     h->o_rsrc2 = L.take<int32_t>(K);
     h->o_F0 = L.take<double>(2);

@@ -188,8 +188,14 @@ class Sweep:
                 # particle sharding: every rank carves the same layout, and nodes are never all retained
                 budget = comm.min_int(budget)
                 workspace_bytes = max(min(budget, self.retain_bytes + (64 << 20)), self.min_bytes)
+            elif self.retain_bytes <= budget:
+                workspace_bytes = self.retain_bytes
+            elif not self.keep and self.M == 0:
+                # an evaluation-only lazy sweep stores the survivors' nodes and nothing else: the garbage-collected pool
+                # of min_bytes (2 K slots) is all it can ever use -- leave the rest of the device to the training sweep
+                workspace_bytes = self.min_bytes
             else:
-                workspace_bytes = self.retain_bytes if self.retain_bytes <= budget else max(budget, self.min_bytes)
+                workspace_bytes = max(budget, self.min_bytes)
         workspace_bytes = (int(workspace_bytes) + 255) // 256 * 256
         self.workspace = torch.empty(workspace_bytes, dtype=U8, device=self.device)
         cfg.workspace_bytes = workspace_bytes
@@ -245,12 +251,13 @@ class Sweep:
             self._hook = None
             check(self._lib.vcsmc_sweep_set_allreduce(self._h, _lib.ALLREDUCE_FN(0), None))
             return
-        base = self.workspace.data_ptr()
+        ws = self.workspace          # (the closure must not hold `self`: a cycle would delay freeing the workspace)
+        base = ws.data_ptr()
 
         def _cb(_user, buf, count, _stream_):
             try:
                 off = buf - base
-                fn(self.workspace[off:off + 8 * count].view(F64))
+                fn(ws[off:off + 8 * count].view(F64))
                 return 0
             except Exception:  # never let an exception cross the C boundary
                 import traceback
@@ -267,7 +274,8 @@ class Sweep:
         from .comm import PeerMap
         if self.K % comm.world != 0:
             raise ValueError("n_particles=%d is not divisible by the %d ranks" % (self.K, comm.world))
-        base = self.workspace.data_ptr()
+        ws = self.workspace          # (not `self`: see set_allreduce)
+        base = ws.data_ptr()
         dev = self.device
 
         def _cb(_user, op, buf, nbytes, _stream_):
@@ -276,10 +284,10 @@ class Sweep:
                     comm.barrier(dev)
                 elif op == _lib.COMM_ALLGATHER:
                     off = buf - base
-                    comm.all_gather_inplace(self.workspace[off:off + nbytes * comm.world], nbytes)
+                    comm.all_gather_inplace(ws[off:off + nbytes * comm.world], nbytes)
                 elif op == _lib.COMM_ALLREDUCE:
                     off = buf - base
-                    comm.all_reduce(self.workspace[off:off + nbytes].view(F64))
+                    comm.all_reduce(ws[off:off + nbytes].view(F64))
                 else:
                     return -1
                 return 0
