@@ -282,6 +282,8 @@ def run_native(args):
     launches = _lib.launch_count() - launches0
     ms = e0.elapsed_time(e1)
     info = sweep.check_status()
+    ws_gb = sweep.workspace.numel() / 1e9
+    retained = bool(sweep.retained)
     # what the last timed sweep did (seed args.steps - 1): integer tables for the accounting below and for the checksums
     anc, lr, rr = sweep.output("ancestors"), sweep.output("left_ref"), sweep.output("right_ref")
     crc = {"seed": args.steps - 1, "ancestors": crc_of(anc), "log_weights": crc_of(sweep.output("log_weights")),
@@ -291,10 +293,15 @@ def run_native(args):
     n_ll = int((l_leaf & r_leaf).sum()); n_li = int((l_leaf ^ r_leaf).sum()); n_ii = int((~l_leaf & ~r_leaf).sum())
     # ---- the same steps again with CUDA events around the launches (per-kernel times for the roofline; events cannot
     #      bracket kernels inside a graph, so this pass issues the launches one by one)
+    K_own = K // world if sharding == "particles" else K
+    k_lo = rank * K_own if sharding == "particles" else 0
+    own_counts = np.zeros(3)                 # (internal+internal, leaf+internal, leaf+leaf) scored by THIS rank in the profile pass
     sweep.set_option("profile", 1.0)
     barrier()
     for i in range(args.steps):
         step(i)
+        a_, b_ = (sweep.output("left_ref")[:, k_lo:k_lo + K_own] < N), (sweep.output("right_ref")[:, k_lo:k_lo + K_own] < N)
+        own_counts += np.array([int((~a_ & ~b_).sum()), int((a_ ^ b_).sum()), int((a_ & b_).sum())])
     barrier()
     prof = sweep.profile()
     sweep.set_option("profile", 0.0)
@@ -362,23 +369,21 @@ def run_native(args):
         # the scoring kernels evaluate the site likelihood of EVERY particle and store nothing; their children are the
         # one or two surviving forests' nodes (L2-resident): FP64-pipe work, not HBM traffic
         sc_ms, sc_n = prof["merge_fwd"]
-        k_lo, k_hi = (rank * K_fwd, (rank + 1) * K_fwd) if sharding == "particles" else (0, K)
-        ll_, rl_ = l_leaf[:, k_lo:k_hi], r_leaf[:, k_lo:k_hi]
-        m_ll = int((ll_ & rl_).sum()); m_li = int((ll_ ^ rl_).sum()); m_ii = int((~ll_ & ~rl_).sum())
+        m_ii, m_li, m_ll = [float(x) / args.steps for x in own_counts]     # per sweep, averaged over the profiled steps
         o_ii, o_li, o_ll = FP64_OPS_SCORE[args.model]
         fp_ops = float(S_fwd) * (o_ii * m_ii + o_li * m_li + o_ll * m_ll) * args.steps
         tops = fp_ops / (sc_ms * 1e-3) / 1e12 if sc_ms > 0 else 0.0
-        roofline = {"bound": "fp64", "kernel": "merge_score_rows_kernel + merge_score_kernel + score_leaf_pairs_kernel",
+        roofline = {"bound": "fp64", "kernel": "merge_score_rows_kernel + merge_score_kernel",
                     "achieved": tops, "peak": FP64_PEAK_TFMA, "unit": "T FP64 op/s", "frac": tops / FP64_PEAK_TFMA,
                     "traffic": traffic_file.get("merge_score_rows" + sfx),
                     "peak_source": "scripts/microbench.cu on this pool's B200s (DFMA, 64 warps/SM)", "launches": sc_n,
                     "avg_launch_ms": sc_ms / max(sc_n, 1),
                     "ops_per_merge": {"internal+internal": o_ii, "leaf+internal": o_li, "leaf+leaf (site patterns)": o_ll},
-                    "merges_scored_this_rank": {"internal+internal": m_ii, "leaf+internal": m_li, "leaf+leaf (site patterns)": m_ll},
+                    "merges_scored_per_sweep_this_rank": {"internal+internal": m_ii, "leaf+internal": m_li, "leaf+leaf (site patterns)": m_ll},
                     "kernel_ms_per_step": kms, "timing": timing_note,
                     "note": "achieved = FP64-pipe operations the scored merges need (per particle.site: 16 DFMA + DADD + "
-                            "DMUL with two internal children; 4 DFMA + 1 DMUL with a leaf; none for two leaves, which are "
-                            "scored from site-pattern counts) / time of the three scoring kernels of a rank event.  These "
+                            "DMUL with two internal children; 4 DFMA + 1 DMUL with a leaf; none for two leaves, which the "
+                            "event kernel scores from site-pattern counts) / time of the two scoring kernels of a rank event.  These "
                             "kernels move almost no HBM bytes (traffic = ncu dram bytes of one launch); the HBM-bound "
                             "kernels are measured under hbm_kernels and eager_dense"}
     else:
@@ -439,14 +444,18 @@ def run_native(args):
     # ---- multi-GPU: the sharded result against a single-GPU sweep of the same seed (integer tables bit for bit)
     single = None
     if world > 1 and not args.nested and not args.no_single_check:
-        lam_l, lam_r, Q, pi = [x.detach().contiguous() for x in model._model()]
+        lam_l, lam_r, Q, pi = [x.detach().contiguous().clone() for x in model._model()]
         codes_full = model.codes
+        elbo = elbo.detach().clone()          # (the autograd node of the last step holds the sweep object)
+        for v in variables:
+            v.grad = None
         del sweep, anc, lr, rr, l_leaf, r_leaf
-        model._sweeps.clear()
-        model._last = None
+        model.release()
         import gc
-        gc.collect()
-        torch.cuda.empty_cache()
+        gc.collect()                          # every rank unmaps its peers' workspaces (CUDA IPC) ...
+        torch.cuda.synchronize()
+        barrier()
+        torch.cuda.empty_cache()              # ... and only then can the workspaces be returned to the driver
         barrier()
         sw1 = ops.Sweep(N, S, K, jc, keep_for_backward=False, device=model.device)
         sw1.set_seed(crc["seed"])
@@ -469,12 +478,12 @@ def run_native(args):
                        "VNCSMC(M=%d)" % args.nested if args.nested else "VCSMC", args.model.upper(), data_desc, K),
                    "taxa": N, "sites": S, "particles": K, "model": args.model, "sharding": "%s/%d" % (sharding, world),
                    "l2": "inputs larger than L2 (%.1f GB workspace; per-event tables of %.1f GB streamed per sweep)" % (
-                       model._last.workspace.numel() / 1e9 if model._last is not None else 0.0, (N - 1) * K * 460 / 1e9),
+                       ws_gb, (N - 1) * K * 460 / 1e9),
                    "forward": ("lazy: every particle scored, survivors of the next resampling materialised (same ELBO to 1e-12, "
                                "same integer tables as the eager schedule)") if lazy_fwd else "eager: every node stored",
                    "backward": ("dense" if args.dense else "events whose adjoint coefficient is below 2^-64 of dELBO skipped "
                                 "(gradients within 1e-11 of the dense sweep)") + (", sharded by site" if sharding == "particles" else ""),
-                   "nodes_retained": bool(model._last.retained) if model._last is not None else False,
+                   "nodes_retained": retained,
                    "backward_chunks": info["backward_chunks"], "peak_pool_slots": info["peak_pool_slots"]},
         "value_counts": "nominal merges K*S*(N-1) per sweep (every particle's site likelihood is evaluated; merges of two "
                         "leaves through site-pattern counts)",
@@ -508,8 +517,7 @@ def run_native(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        model._sweeps.clear()
-        model._last = None
+        model.release()
         dist.barrier()
         dist.destroy_process_group()
 

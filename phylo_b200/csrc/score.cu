@@ -33,6 +33,21 @@ namespace {
 constexpr int kRScore = 32;  // particles per scoring group
 constexpr int kCoef = 20;    // doubles per particle in shared memory: M[4][4] (or the 4 JC coefficients) + the column sums of M
 
+// Work items of a scoring launch: groups of R particles x chunks of tiles.  `count` (how many particles the launch really
+// has to score) is only known on the device, so the kernel itself splits a group's tiles into as many chunks as it takes
+// to reach about `items` work items (at most n_parts: a particle has that many partial sums).
+__host__ __device__ __forceinline__ void chunking(int64_t count, int R, int tiles, int items, int n_parts, int* tiles_per_item,
+                                                  int* n_chunks) {
+  int64_t groups = (count + R - 1) / R;
+  if (groups < 1) groups = 1;
+  int64_t nc = (items + groups - 1) / groups;
+  if (nc > n_parts) nc = n_parts;
+  if (nc > tiles) nc = tiles;
+  if (nc < 1) nc = 1;
+  *tiles_per_item = (int)((tiles + nc - 1) / nc);
+  *n_chunks = (tiles + *tiles_per_item - 1) / *tiles_per_item;
+}
+
 struct ScoreArgs {
   const uint8_t* codes;
   int64_t codes_stride;
@@ -47,8 +62,7 @@ struct ScoreArgs {
   int64_t K;
   int n_sites;
   int tiles;
-  int tiles_per_item;
-  int n_chunks;
+  int items;            // work items wanted per launch (the kernel splits a group's tiles into chunks accordingly)
   int R;
   int skip_leaf_pairs;  // particles whose children are both leaves are scored from the pattern histogram instead
   int n_parts;          // partial sums per particle in ell_part (>= n_chunks; the tail is zero-filled)
@@ -289,7 +303,9 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int R = a.R;
   const int64_t count = a.count ? (int64_t)*a.count : a.K;
-  const int64_t total = ((count + R - 1) / R) * a.n_chunks;
+  int tiles_per_item, n_chunks;
+  chunking(count, R, a.tiles, a.items, a.n_parts, &tiles_per_item, &n_chunks);
+  const int64_t total = ((count + R - 1) / R) * n_chunks;
   double pi[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
@@ -299,8 +315,8 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
   const int64_t first = a.from_end ? a.K - count : 0;
 
   for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
-    const int64_t g = w / a.n_chunks;
-    const int tc = (int)(w - g * a.n_chunks);
+    const int64_t g = w / n_chunks;
+    const int tc = (int)(w - g * n_chunks);
     const int64_t j0 = g * R;
     const int nj = (int)min((int64_t)R, count - j0);
     __syncthreads();
@@ -362,8 +378,8 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
     }
     __syncthreads();
 
-    const int t_begin = tc * a.tiles_per_item;
-    const int t_end = min(a.tiles, t_begin + a.tiles_per_item);
+    const int t_begin = tc * tiles_per_item;
+    const int t_end = min(a.tiles, t_begin + tiles_per_item);
     for (int t = t_begin; t < t_end; ++t) {
       const int sbase = t * (kTileThreads * SPT) + tid;
       const bool renorm = ((t - t_begin) & 127) == 127;
@@ -399,7 +415,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
         const int64_t k = kk < 0 ? ~kk : kk;
         if (lane == 0) a.ell_part[k * a.n_parts + tc] = acc;
         if (tc == 0)   // the entries no chunk of this kernel writes
-          for (int t = a.n_chunks + lane; t < a.n_parts; t += 32) a.ell_part[k * a.n_parts + t] = 0.0;
+          for (int t = n_chunks + lane; t < a.n_parts; t += 32) a.ell_part[k * a.n_parts + t] = 0.0;
       }
     }
     __syncthreads();
@@ -420,7 +436,7 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
         for (int w2 = 1; w2 < kWarps; ++w2) t += s_slow[w2];
         a.ell_part[k * a.n_parts + tc] = t;
         if (tc == 0)
-          for (int q = a.n_chunks; q < a.n_parts; ++q) a.ell_part[k * a.n_parts + q] = 0.0;
+          for (int q = n_chunks; q < a.n_parts; ++q) a.ell_part[k * a.n_parts + q] = 0.0;
       }
     }
   }
@@ -511,7 +527,7 @@ struct RowArgs {
   const double* pi;
   const int32_t* perm;    // [N][Sp] sites of every leaf in state order (-1: padding)
   const uint8_t* tstate;  // [N][Sp / 256] state class of every sub-tile (255: empty)
-  int Sp, tiles, tiles_per_item, n_chunks, R, n_parts;
+  int Sp, tiles, items, R, n_parts;
   double* ell_part;
 };
 
@@ -562,7 +578,10 @@ __global__ void __launch_bounds__(kTileThreads, 2) merge_score_rows_kernel(const
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int R = a.R;
   const int64_t count = (int64_t)*a.count;
-  const int64_t total = ((count + R - 1) / R) * a.n_chunks;
+  // chunks of tiles per group of particles: as many as it takes to fill the machine with the particles there really are
+  int tiles_per_item, n_chunks;
+  chunking(count, R, a.tiles, a.items, a.n_parts, &tiles_per_item, &n_chunks);
+  const int64_t total = ((count + R - 1) / R) * n_chunks;
   const int n_sub = a.Sp / kRowSub;
   double pi[4];
 #pragma unroll
@@ -571,8 +590,8 @@ __global__ void __launch_bounds__(kTileThreads, 2) merge_score_rows_kernel(const
   int* my_exp = s_exp + tid;
 
   for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
-    const int64_t g = w / a.n_chunks;
-    const int tc = (int)(w - g * a.n_chunks);
+    const int64_t g = w / n_chunks;
+    const int tc = (int)(w - g * n_chunks);
     const int64_t j0 = g * R;
     const int nj = (int)min((int64_t)R, count - j0);
     __syncthreads();
@@ -617,8 +636,8 @@ __global__ void __launch_bounds__(kTileThreads, 2) merge_score_rows_kernel(const
     __syncthreads();
     const int n_runs = s_nruns;
 
-    const int t_begin = tc * a.tiles_per_item;
-    const int t_end = min(a.tiles, t_begin + a.tiles_per_item);
+    const int t_begin = tc * tiles_per_item;
+    const int t_end = min(a.tiles, t_begin + tiles_per_item);
     for (int t = t_begin; t < t_end; ++t) {
       for (int run = 0; run < n_runs; ++run) {
         const int jb = s_run[run], je = s_run[run + 1];
@@ -656,8 +675,48 @@ __global__ void __launch_bounds__(kTileThreads, 2) merge_score_rows_kernel(const
         if (!other && c4.x == c4.y && c4.x == c4.z && c4.x == c4.w) {
           // one row of M (or its column sums) for all four sub-tiles: a broadcast read per particle
           const double* rowp = Mj + (c4.x == 4 ? 16 : 4 * c4.x);
-#pragma unroll 2
-          for (int i = 0; i < len; ++i, pp += kTileThreads, pe += kTileThreads, rowp += kCoef) {
+          int i = 0;
+          // two particles per trip, loads first: the particles' accumulators are distinct shared-memory words, which the
+          // compiler cannot know, so the interleaving (two independent chains per site) is written out by hand
+          for (; i + 1 < len; i += 2, pp += 2 * kTileThreads, pe += 2 * kTileThreads, rowp += 2 * kCoef) {
+            const double2 a0 = *reinterpret_cast<const double2*>(rowp), a1 = *reinterpret_cast<const double2*>(rowp + 2);
+            const double2 b0 = *reinterpret_cast<const double2*>(rowp + kCoef), b1 = *reinterpret_cast<const double2*>(rowp + kCoef + 2);
+            const double pa = pp[0], pb = pp[kTileThreads];
+            const int ea = pe[0], eb = pe[kTileThreads];
+            double xa[4], xb[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              xa[q] = fma(a0.x, Lb[q][0], x0[q]);
+              xb[q] = fma(b0.x, Lb[q][0], x0[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              xa[q] = fma(a0.y, Lb[q][1], xa[q]);
+              xb[q] = fma(b0.y, Lb[q][1], xb[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              xa[q] = fma(a1.x, Lb[q][2], xa[q]);
+              xb[q] = fma(b1.x, Lb[q][2], xb[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              xa[q] = fma(a1.y, Lb[q][3], xa[q]);
+              xb[q] = fma(b1.y, Lb[q][3], xb[q]);
+            }
+            const double va = (xa[0] * xa[1]) * (xa[2] * xa[3]), vb = (xb[0] * xb[1]) * (xb[2] * xb[3]);
+            const int ha = __double2hiint(va), hb = __double2hiint(vb);
+            const unsigned sa = (unsigned)ha >> 20, sb = (unsigned)hb >> 20;
+            double na = pa * __hiloint2double((ha & 0x000fffff) | 0x3ff00000, __double2loint(va));
+            double nb = pb * __hiloint2double((hb & 0x000fffff) | 0x3ff00000, __double2loint(vb));
+            if ((sa - 1u) >= 0x7feu) na = __longlong_as_double(0x7ff8000000000000ll);
+            if ((sb - 1u) >= 0x7feu) nb = __longlong_as_double(0x7ff8000000000000ll);
+            pp[0] = na;
+            pp[kTileThreads] = nb;
+            pe[0] = ea + (int)sa;
+            pe[kTileThreads] = eb + (int)sb;
+          }
+          if (i < len) {
             const double2 r0 = *reinterpret_cast<const double2*>(rowp), r1 = *reinterpret_cast<const double2*>(rowp + 2);
             double x[4];
 #pragma unroll
@@ -746,7 +805,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) merge_score_rows_kernel(const
         const int64_t k = kk < 0 ? ~kk : kk;
         if (lane == 0) a.ell_part[k * a.n_parts + tc] = acc;
         if (tc == 0)
-          for (int t = a.n_chunks + lane; t < a.n_parts; t += 32) a.ell_part[k * a.n_parts + t] = 0.0;
+          for (int t = n_chunks + lane; t < a.n_parts; t += 32) a.ell_part[k * a.n_parts + t] = 0.0;
       }
     }
     __syncthreads();
@@ -765,7 +824,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) merge_score_rows_kernel(const
         for (int w2 = 1; w2 < kWarps; ++w2) t += s_slow[w2];
         a.ell_part[k * a.n_parts + tc] = t;
         if (tc == 0)
-          for (int q = a.n_chunks; q < a.n_parts; ++q) a.ell_part[k * a.n_parts + q] = 0.0;
+          for (int q = n_chunks; q < a.n_parts; ++q) a.ell_part[k * a.n_parts + q] = 0.0;
       }
     }
   }
@@ -903,7 +962,7 @@ __global__ void __launch_bounds__(256) leaf_pair_hist_kernel(const uint8_t* __re
   }
 }
 
-constexpr int64_t kScoreItems = 148 * 32;  // work items wanted per launch (measured: 592 .. 18,944; work per item is uneven)
+constexpr int64_t kScoreItems = 148 * 8;  // work items wanted per launch (for the particles a launch really scores)
 
 }  // namespace
 
@@ -927,21 +986,7 @@ int launch_leaf_sort(const uint8_t* codes, int64_t stride, int N, int S, int32_t
   return VCSMC_OK;
 }
 
-namespace {
-// work items of one scoring launch: groups of R particles x chunks of tiles, about `items` of them
-void split_work(int64_t K, int tiles, int64_t items, int* R_out, int* tiles_per_item, int* n_chunks) {
-  int64_t R = (K * tiles) / items;   // groups as large as the machine fill allows (site data is amortised over the group)
-  if (R < 1) R = 1;
-  if (R > kRScore) R = kRScore;
-  const int64_t groups = (K + R - 1) / R;
-  int64_t nc = (items + groups - 1) / groups;  // split a group's tiles only when the groups cannot fill the SMs
-  if (nc < 1) nc = 1;
-  if (nc > tiles) nc = tiles;
-  *R_out = (int)R;
-  *tiles_per_item = (int)((tiles + nc - 1) / nc);
-  *n_chunks = (tiles + *tiles_per_item - 1) / *tiles_per_item;
-}
-}  // namespace
+constexpr int kScoreParts = 8;   // partial sums per particle (upper bound of the chunks a group's tiles are split into)
 
 // order == null: every particle in identity order through the generic kernel (its leaf path included).
 // order != null: the grouped order of the event kernel -- count[0] leaf + internal particles at the front (rows kernel,
@@ -977,7 +1022,12 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
   a.skip_leaf_pairs = skip_leaf_pairs;
   a.from_end = rows ? 1 : 0;
   a.tiles = (n_sites + kTileThreads * spt - 1) / (kTileThreads * spt);
-  split_work(K, a.tiles, items, &a.R, &a.tiles_per_item, &a.n_chunks);
+  a.items = (int)items;
+  // groups as large as the machine fill allows (site data is amortised over the group); K bounds the particles of a launch
+  {
+    int64_t R = (K * a.tiles) / items;
+    a.R = (int)(R < 1 ? 1 : R > kRScore ? kRScore : R);
+  }
   RowArgs b;
   memset(&b, 0, sizeof(b));
   if (rows) {
@@ -985,15 +1035,17 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
     b.order = order; b.count = count; b.P = P; b.pi = pi; b.perm = leaf_perm; b.tstate = leaf_tstate; b.ell_part = ell_part;
     b.Sp = leaf_sort_stride(n_sites);
     b.tiles = b.Sp / kRowTile;
-    split_work(K, b.tiles, items, &b.R, &b.tiles_per_item, &b.n_chunks);
+    b.items = (int)items;
+    b.R = kRScore;
   }
-  const int parts = rows && b.n_chunks > a.n_chunks ? b.n_chunks : a.n_chunks;
-  a.n_parts = parts;
-  b.n_parts = parts;
-  if (n_parts) *n_parts = parts;
+  a.n_parts = kScoreParts;
+  b.n_parts = kScoreParts;
+  if (n_parts) *n_parts = kScoreParts;
   const int64_t cap = 148 * 2 * 8;
   {
-    const int64_t total = ((K + a.R - 1) / a.R) * a.n_chunks;
+    int tpi, nc;
+    chunking(K, a.R, a.tiles, a.items, a.n_parts, &tpi, &nc);
+    const int64_t total = ((K + a.R - 1) / a.R) * (order ? (int64_t)kScoreParts : (int64_t)nc);   // upper bound of the work items
     const unsigned grid = (unsigned)(total < cap ? total : cap);
     if (jc) merge_score_kernel<true, 4><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
     else if (spt == 4) merge_score_kernel<false, 4><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
@@ -1001,7 +1053,7 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
     VCSMC_LAUNCH_CHECK("merge_score_kernel");
   }
   if (rows) {
-    const int64_t total = ((K + b.R - 1) / b.R) * b.n_chunks;
+    const int64_t total = ((K + b.R - 1) / b.R) * kScoreParts;
     const unsigned grid = (unsigned)(total < cap ? total : cap);
     merge_score_rows_kernel<<<grid, kTileThreads, kScoreSmemBytes, st>>>(b);
     VCSMC_LAUNCH_CHECK("merge_score_rows_kernel");

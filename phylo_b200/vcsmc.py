@@ -186,6 +186,13 @@ class VCSMC:
         self.cost = -elbo
         return elbo
 
+    def release(self) -> None:
+        """Drops the sweep engines (and with them their device workspaces and peer mappings)."""
+        self._sweeps.clear()
+        self._last = None
+        self.elbo = None      # (its autograd node holds the sweep it came from)
+        self.cost = None
+
     def _allreduce_grads(self):
         if self.world > 1:
             import torch.distributed as dist
