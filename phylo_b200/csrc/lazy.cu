@@ -109,7 +109,9 @@ struct EvArgs {
   int32_t* loc;
   int32_t* slot_id;
   int32_t* pend;
-  int32_t* mat_list;
+  int32_t* mat_list;          // survivors (GLOBAL particle index) whose node this rank writes in this launch
+  int32_t* mat_ls;            // their child slots
+  int32_t* mat_rs;
   int32_t* fetch_e;
   int32_t* fetch_src;
   int32_t* counts;            // [0] survivors to materialise, [1] nodes to pull, [2] occupied hash slots, [3..4] last-CTA tickets
@@ -149,6 +151,12 @@ __device__ __forceinline__ void stamp(const EvArgs& a, int i) {
   }
 }
 
+// hash key of a child pair ((min + 256) << 32 | (max + 256)) + 1: exactly one of the two references is a leaf (< 0)
+__device__ __forceinline__ bool one_leaf(unsigned long long key) {
+  key -= 1ull;
+  return (key >> 32) < 256ull && (key & 0xffffffffull) >= 256ull;
+}
+
 __device__ __forceinline__ int warp_sum_int(int v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -170,32 +178,33 @@ __device__ __forceinline__ bool last_cta(int32_t* ticket, int* s_flag) {
   return *s_flag != 0;
 }
 
-// Cross-GPU barrier without the host: after a grid barrier CTA 0 stores this rank's epoch into every peer's flag array
-// (peer store over NVLink, system scope); every CTA then polls its own rank's array until all peers have arrived.
-// A timeout (~30 s) turns a lost peer into a reported error instead of a hang.
-__device__ __forceinline__ void cross_sync(const EvArgs& a, int index, cg::grid_group& grid) {
-  __threadfence_system();
+// Cross-GPU synchronisation without the host: after a grid barrier CTA 0 stores this rank's epoch into every peer's
+// flag array (peer store over NVLink, system scope; the grid barrier ordered every thread's writes before the signalling
+// threads' fence, which is cumulative); with `wait` every CTA then polls its own rank's array until all peers have
+// arrived.  A timeout (~30 s) turns a lost peer into a reported error instead of a hang.
+__device__ __forceinline__ void cross_sync(const EvArgs& a, int index, bool wait, cg::grid_group& grid) {
   grid.sync();
   const int epoch = *a.epoch_base + index;
   const int g = threadIdx.x;
   if (blockIdx.x == 0 && g < a.world) {
+    __threadfence_system();
     volatile int32_t* out = a.peer_sig[g] + a.rank;
     *out = epoch;
-    __threadfence_system();
   }
-  if (g < a.world) {
-    volatile int32_t* in = a.peer_sig[a.rank] + g;
-    const long long t0 = clock64();
-    while (*in - epoch < 0) {
-      if (clock64() - t0 > 60000000000ll) {   // ~30 s at 1.9 GHz
-        a.status[0] = VCSMC_ERR_STATE;
-        break;
+  if (wait) {
+    if (g < a.world) {
+      volatile int32_t* in = a.peer_sig[a.rank] + g;
+      const long long t0 = clock64();
+      while (*in - epoch < 0) {
+        if (clock64() - t0 > 60000000000ll) {   // ~30 s at 1.9 GHz
+          a.status[0] = VCSMC_ERR_STATE;
+          break;
+        }
       }
-      __nanosleep(100);
+      __threadfence_system();
     }
-    __threadfence_system();
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -235,7 +244,7 @@ __device__ __forceinline__ double particle_weight(const EvArgs& a, int64_t k, do
   a.lw[e] = lw;
   a.vminus[k] = vm;
   if (a.world > 1) {   // the per-event record (field-major inside the rank's chunk)
-    char* base = a.rec + (int64_t)a.rank * a.rec_stride;
+    char* base = a.rec + ((int64_t)(a.r & 1) * a.world + a.rank) * a.rec_stride;   // (two buffers, by launch parity)
     double* d = reinterpret_cast<double*>(base);
     d[0 * a.Kl + kl] = lw;
     d[1 * a.Kl + kl] = LLr;
@@ -253,30 +262,41 @@ __device__ __forceinline__ double particle_weight(const EvArgs& a, int64_t k, do
   return lw;
 }
 
-__device__ __forceinline__ double particle_unpack(const EvArgs& a, int64_t k) {
+// a remote particle's record: the log-weight first (the CDF waits for it) ...
+__device__ __forceinline__ double particle_unpack_lw(const EvArgs& a, int64_t k) {
+  const int r = a.r - 1;
+  const int g = (int)(k / a.Kl);
+  const int64_t kl = k - (int64_t)g * a.Kl;
+  const double* d = reinterpret_cast<const double*>(a.peer_rec[g] + ((int64_t)(a.r & 1) * a.world + g) * a.rec_stride);
+  const double lw = d[0 * a.Kl + kl];
+  a.lw[(int64_t)r * a.K + k] = lw;
+  return lw;
+}
+
+// ... and the rest, by the CTAs the CDF's tile stages leave idle (all loads first: they cross the NVLink)
+__device__ __forceinline__ void particle_unpack_rest(const EvArgs& a, int64_t k) {
   const int r = a.r - 1;
   const int g = (int)(k / a.Kl);
   const int64_t kl = k - (int64_t)g * a.Kl;
   const int64_t e = (int64_t)r * a.K + k;
-  const char* base = a.peer_rec[g] + (int64_t)g * a.rec_stride;
+  const char* base = a.peer_rec[g] + ((int64_t)(a.r & 1) * a.world + g) * a.rec_stride;
   const double* d = reinterpret_cast<const double*>(base);
-  const double lw = d[0 * a.Kl + kl];
-  a.lw[e] = lw;
-  a.LL[e] = d[1 * a.Kl + kl];
-  a.ell_node[a.N + e] = d[2 * a.Kl + kl];
-  const double bl = d[3 * a.Kl + kl], br = d[4 * a.Kl + kl];
+  const int32_t* qi = reinterpret_cast<const int32_t*>(base + 56 * a.Kl);
+  const double LL = d[1 * a.Kl + kl], ell = d[2 * a.Kl + kl], bl = d[3 * a.Kl + kl], br = d[4 * a.Kl + kl];
+  const double cl = d[5 * a.Kl + kl], cr = d[6 * a.Kl + kl];
+  const int lref = qi[0 * a.Kl + kl], rref = qi[1 * a.Kl + kl], nleaf = qi[2 * a.Kl + kl], vm = qi[3 * a.Kl + kl];
+  a.LL[e] = LL;
+  a.ell_node[a.N + e] = ell;
   a.b_l[e] = bl;
   a.b_r[e] = br;
   a.t2[2 * e] = bl;
   a.t2[2 * e + 1] = br;
-  a.cum_l[e] = d[5 * a.Kl + kl];
-  a.cum_r[e] = d[6 * a.Kl + kl];
-  const int32_t* qi = reinterpret_cast<const int32_t*>(base + 56 * a.Kl);
-  a.lref[e] = qi[0 * a.Kl + kl];
-  a.rref[e] = qi[1 * a.Kl + kl];
-  a.nleaf[e] = qi[2 * a.Kl + kl];
-  a.vminus[k] = qi[3 * a.Kl + kl];
-  return lw;
+  a.cum_l[e] = cl;
+  a.cum_r[e] = cr;
+  a.lref[e] = lref;
+  a.rref[e] = rref;
+  a.nleaf[e] = nleaf;
+  a.vminus[k] = vm;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -423,13 +443,38 @@ __device__ __forceinline__ void survivor_row(const EvArgs& a, int64_t k, int lan
   if (!own && !kid) return;
   const int32_t* ids = a.row_ids[r & 1] + k * N;
   const int64_t newest = (int64_t)r * a.K + k;
+  // the survivor's own node: the owner writes it; a rank whose particles descend from a REMOTE survivor writes its own
+  // copy when it holds both children (the rule with ESS ~ 1: every rank follows the same one or two lineages), so that
+  // nothing has to cross the NVLink and nobody waits for the owner; otherwise the node is pulled from the owner
+  int ls = 0, rs = 0;
+  bool compute = own;
+  if (own) {
+    const int64_t kl = k - a.k0;
+    ls = a.lsrc[r & 1][kl];
+    rs = a.rsrc[r & 1][kl];
+  } else {
+    const int lid = a.lref[newest], rid = a.rref[newest];
+    compute = true;
+    if (lid < N) {
+      ls = -(lid + 1);
+    } else {
+      ls = a.loc[lid - N];
+      compute = compute && (!a.gc || (ls >= 0 && a.slot_id[ls] == lid - N));
+    }
+    if (rid < N) {
+      rs = -(rid + 1);
+    } else {
+      rs = a.loc[rid - N];
+      compute = compute && (!a.gc || (rs >= 0 && a.slot_id[rs] == rid - N));
+    }
+  }
   for (int pos = lane; pos < m; pos += 32) {
     const int id = ids[pos];
     if (id < N) continue;
     const int e = id - N;
     bool have;
     if (e == newest) {
-      have = own;                       // gets its slot from the allocator through the survivor list
+      have = compute;                    // gets its slot from the allocator through the survivor list
     } else {
       const int s = a.loc[e];
       have = !a.gc || (s >= 0 && a.slot_id[s] == e);
@@ -445,13 +490,35 @@ __device__ __forceinline__ void survivor_row(const EvArgs& a, int64_t k, int lan
       }
     }
   }
-  if (own && lane == 0) {
-    const int64_t kl = k - a.k0;
-    a.mat_list[atomicAdd(a.counts, 1)] = (int32_t)kl;
-    if (a.gc) {   // the children the node is about to be computed from
-      const int ls = a.lsrc[r & 1][kl], rs = a.rsrc[r & 1][kl];
-      if (ls >= 0) a.flags[ls] = 1;
-      if (rs >= 0) a.flags[rs] = 1;
+  if (compute) {
+    if (!own && lane < 2) {
+      // the remote survivor's transition matrices, from its gathered branch lengths (vcsmc.py:181-184)
+      const double ti = a.t2[2 * newest + lane];
+      M4 X;
+      if (a.jc) {
+        const double o = -0.25 * expm1(-ti);
+        const double d = 0.25 + 0.75 * exp(-ti);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) X.a[q] = (q % 5 == 0) ? d : o;
+      } else {
+        M4 A;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) A.a[q] = a.Q[q] * ti;
+        X = m4_expm(A);
+      }
+      double* Pout = a.P + newest * 32 + lane * 16;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) Pout[q] = X.a[q];
+    }
+    if (lane == 0) {
+      const int j = atomicAdd(a.counts, 1);
+      a.mat_list[j] = (int32_t)k;
+      a.mat_ls[j] = ls;
+      a.mat_rs[j] = rs;
+      if (a.gc) {   // the children the node is about to be computed from
+        if (ls >= 0) a.flags[ls] = 1;
+        if (rs >= 0) a.flags[rs] = 1;
+      }
     }
   }
 }
@@ -465,7 +532,7 @@ __device__ void allocate_slots(const EvArgs& a, int64_t* warp_off) {
   const int64_t n_fetch = counts[1] < a.fetch_cap ? counts[1] : a.fetch_cap;
   const int64_t Kn = n_mat + n_fetch;
   if (Kn == 0) return;
-  const int64_t e_base_prev = (int64_t)(a.r - 1) * a.K + a.k0;
+  const int64_t e_base_prev = (int64_t)(a.r - 1) * a.K;   // (the survivor list holds global particle indices)
   // every live slot lies below the running peak, so the Kn lowest free slots are below peak + Kn
   int64_t P = a.pool_slots;
   const int64_t peak = a.status[1];
@@ -804,11 +871,14 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
     }
     if (a.world > 1) {
       // the other ranks' chunks of the step record, straight out of their buffers; the own weights join the maximum here
-      cross_sync(a, a.bar_index + 1, grid);
+      stamp(a, 12);
+      cross_sync(a, a.bar_index + 1, true, grid);
+      stamp(a, 13);
       double m = -INFINITY;
-      for (int64_t k = gtid; k < K; k += gthreads) m = fmax(m, (k >= k0 && k < k0 + Kl) ? lw[k] : particle_unpack(a, k));
+      for (int64_t k = gtid; k < K; k += gthreads) m = fmax(m, (k >= k0 && k < k0 + Kl) ? lw[k] : particle_unpack_lw(a, k));
       m = warp_max(m);
       if (lane == 0 && m > -INFINITY) atomicMax(a.lw_max, ordered_bits(m));
+      stamp(a, 14);
     }
     grid.sync();
     stamp(a, 1);
@@ -823,6 +893,13 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
       a.gcount[1] = 0;
     }
     for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_sumexp(vb, lw, K, M, psum, sm);
+    if (a.world > 1) {
+      // the rest of the other ranks' records: needed from phase 5 on, fetched by the CTAs that have no CDF tile
+      const int first = nb < (int)gridDim.x ? nb : 0, n_cta = (int)gridDim.x - first;
+      if ((int)blockIdx.x >= first)
+        for (int64_t k = (int64_t)(blockIdx.x - first) * kEvThreads + tid; k < K; k += (int64_t)n_cta * kEvThreads)
+          if (!(k >= k0 && k < k0 + Kl)) particle_unpack_rest(a, k);
+    }
     grid.sync();
     stamp(a, 3);
     for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_weights(vb, lw, K, nb, M, psum, a.cdf, pw, pq, a.live, sm);
@@ -855,7 +932,7 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
       }
       if (a.world > 1) {
         // nobody starts the next sweep's record before everybody has read this one; then the epochs move on
-        cross_sync(a, a.bar_index + 2, grid);
+        cross_sync(a, a.bar_index + 2, true, grid);
         grid.sync();
         if (gtid == 0) *a.epoch_base += a.n_barriers_total;
       }
@@ -949,17 +1026,16 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
   if (r > 0) {
     const int n_mat = a.counts[0];
     const int tiles = (a.S + kEvThreads * kMatSptEv - 1) / (kEvThreads * kMatSptEv);
-    const int64_t e_base = (int64_t)(r - 1) * K + k0;
-    const int pp = (r - 1) & 1;
+    const int64_t e_base = (int64_t)(r - 1) * K;
     for (int64_t w = blockIdx.x; w < (int64_t)n_mat * tiles; w += gridDim.x) {
       const int64_t j = w / tiles;
       const int t = (int)(w - j * tiles);
-      const int kl = a.mat_list[j];
-      const int ds = a.loc[e_base + kl];
+      const int kg = a.mat_list[j];
+      const int ds = a.loc[e_base + kg];
       if (ds < 0) continue;  // pool exhausted (reported through the status word)
-      const ChildRef ra = child_ref(a.lsrc[pp][kl], a.codes, a.S, a.pool, a.slot_sites);
-      const ChildRef rb = child_ref(a.rsrc[pp][kl], a.codes, a.S, a.pool, a.slot_sites);
-      const double* Pk = a.P + (e_base + kl) * 32;
+      const ChildRef ra = child_ref(a.mat_ls[j], a.codes, a.S, a.pool, a.slot_sites);
+      const ChildRef rb = child_ref(a.mat_rs[j], a.codes, a.S, a.pool, a.slot_sites);
+      const double* Pk = a.P + (e_base + kg) * 32;
       double* out = a.pool + (int64_t)ds * a.slot_sites * 4;
       if (a.jc) {
         Trans<true> Pl, Pr;
@@ -1013,7 +1089,7 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
     int mine[2] = {0, 0};
     for (int i = i0; i < i1; ++i) {
       const int sl = ((volatile int32_t*)a.gocc)[i];
-      const bool leafy = !a.two_lists || ((((volatile unsigned long long*)a.gtab)[sl] - 1ull) >> 32) < 256ull;   // the smaller reference is a leaf
+      const bool leafy = !a.two_lists || one_leaf(((volatile unsigned long long*)a.gtab)[sl]);   // the smaller reference is a leaf
       mine[leafy ? 0 : 1] += ((volatile int32_t*)a.gcnt)[sl];
     }
     int incl[2] = {mine[0], mine[1]};
@@ -1038,7 +1114,7 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
     }
     for (int i = i0; i < i1; ++i) {
       const int sl = ((volatile int32_t*)a.gocc)[i];
-      const bool leafy = !a.two_lists || ((((volatile unsigned long long*)a.gtab)[sl] - 1ull) >> 32) < 256ull;
+      const bool leafy = !a.two_lists || one_leaf(((volatile unsigned long long*)a.gtab)[sl]);
       const int c = ((volatile int32_t*)a.gcnt)[sl];
       if (leafy) {
         a.goff[sl] = base[0];
@@ -1053,7 +1129,8 @@ __global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
       a.gcount[1] = base[1];
     }
   }
-  if (a.world > 1) cross_sync(a, a.bar_index + 2, grid);
+  // particle sharding: "my survivors' nodes are written"; only a rank that has nodes to pull waits for the others
+  if (a.world > 1) cross_sync(a, a.bar_index + 2, r > 0 && ((volatile int32_t*)a.counts)[1] > 0, grid);
   else grid.sync();
   stamp(a, 10);
   // ---- phase 8: grouped visiting order; particle sharding: pull the missing nodes out of the owners' pools
@@ -1139,7 +1216,9 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     if (h->allreduce(h->allreduce_user, ell_node, N, st)) { set_error("allreduce hook failed"); return VCSMC_ERR_CUDA; }
   }
   const int32_t* leaf_hist = nullptr;
-  if (h->leaf_patterns) {  // site patterns of every leaf pair, once per sweep: cherries are scored from these counts
+  // site patterns of every leaf pair, once per sweep: cherries are scored from these counts by the proposing thread
+  // (not under site sharding: a cherry's sum over this rank's sites would bypass the all-reduce of the scoring kernels' sums)
+  if (h->leaf_patterns && !h->allreduce) {
     rc = launch_leaf_pair_hist(codes, S, N, S, h->p<int32_t>(h->o_leaf_hist), st);
     if (rc) return rc;
     leaf_hist = h->p<int32_t>(h->o_leaf_hist);
@@ -1182,7 +1261,7 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
   a.live = h->p<int32_t>(h->o_live); a.surv = h->p<int32_t>(h->o_surv); a.haskid = h->p<int32_t>(h->o_haskid);
   a.pool = h->p<double>(h->o_pool); a.flags = h->p<int32_t>(h->o_flags); a.loc = h->p<int32_t>(h->o_loc);
   a.slot_id = gc ? h->p<int32_t>(h->o_slot_id) : nullptr; a.pend = h->p<int32_t>(h->o_pend);
-  a.mat_list = h->p<int32_t>(h->o_mat_list); a.fetch_e = h->p<int32_t>(h->o_fetch_e); a.fetch_src = h->p<int32_t>(h->o_fetch_src);
+  a.mat_list = h->p<int32_t>(h->o_mat_list); a.mat_ls = h->p<int32_t>(h->o_mat_ls); a.mat_rs = h->p<int32_t>(h->o_mat_rs); a.fetch_e = h->p<int32_t>(h->o_fetch_e); a.fetch_src = h->p<int32_t>(h->o_fetch_src);
   a.counts = h->p<int32_t>(h->o_counts); a.status = status;
   a.gtab = h->p<unsigned long long>(h->o_gtab); a.gcnt = h->p<int32_t>(h->o_gcnt); a.goff = h->p<int32_t>(h->o_goff);
   a.gslot = h->p<int32_t>(h->o_gslot); a.grank = h->p<int32_t>(h->o_grank); a.gocc = h->p<int32_t>(h->o_gocc);

@@ -816,6 +816,8 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_pV = L.take<int32_t>(K);
     h->o_pLLt = L.take<double>(K);
     h->o_pEll = L.take<double>(K);
+    h->o_mat_ls = L.take<int32_t>(K);
+    h->o_mat_rs = L.take<int32_t>(K);
     h->o_pDirect = L.take<int32_t>(K);
     h->o_lsrc2 = L.take<int32_t>(K);
     h->o_rsrc2 = L.take<int32_t>(K);
@@ -833,7 +835,7 @@ int64_t plan(vcsmc_sweep* h) {
       h->o_vm[i] = L.take<int32_t>(K);
     }
     h->rec_stride = align_up((h->Kl > 0 ? h->Kl : K) * (int64_t)(72 + N), 16);
-    h->o_rec = L.take<char>(K * (int64_t)(72 + N) + 16 * kMaxPeers + 256);
+    h->o_rec = L.take<char>(2 * (K * (int64_t)(72 + N) + 16 * kMaxPeers + 256));   // two buffers (by launch parity)
   }
   h->o_keys_in = L.take<uint64_t>(K);
   h->o_keys_out = L.take<uint64_t>(K);

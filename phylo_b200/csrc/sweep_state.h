@@ -109,7 +109,7 @@ struct vcsmc_sweep {
   void* comm_user = nullptr;
   int site_begin = 0, site_end = -1;   // site slice of the reverse sweep (particle-sharded runs shard the backward by site)
   int64_t o_loc = 0, o_slot_id = 0, o_pend = 0, o_surv = 0, o_mat_list = 0, o_fetch_e = 0, o_fetch_src = 0, o_counts = 0,
-          o_pF = 0, o_pT = 0, o_pV = 0, o_pLLt = 0, o_pEll = 0, o_pDirect = 0, o_lsrc2 = 0, o_rsrc2 = 0, o_F0 = 0, o_live = 0, o_haskid = 0, o_gocc = 0, o_leaf_perm = 0, o_leaf_tstate = 0,
+          o_pF = 0, o_pT = 0, o_pV = 0, o_pLLt = 0, o_mat_ls = 0, o_mat_rs = 0, o_pEll = 0, o_pDirect = 0, o_lsrc2 = 0, o_rsrc2 = 0, o_F0 = 0, o_live = 0, o_haskid = 0, o_gocc = 0, o_leaf_perm = 0, o_leaf_tstate = 0,
           o_lz_ids = 0, o_lz_cnt = 0, o_u_res_all = 0, o_rec = 0, o_cdf_scratch = 0, o_gtab = 0, o_gcnt = 0, o_goff = 0, o_gslot = 0, o_grank = 0, o_leaf_hist = 0, o_F[2] = {0, 0}, o_topo[2] = {0, 0}, o_vm[2] = {0, 0};
   int event_timing = 0;                // option "event_timing": CTA 0 of the event kernel stamps %globaltimer at every phase boundary
   int64_t o_ev_timing = 0;

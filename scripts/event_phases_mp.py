@@ -41,6 +41,9 @@ out = ["rank %d per launch, us (median / mean over r = 1..N-2):" % rank]
 lab = ["weights+pack", "xsync1+unpack", "sumexp", "w+live", "scan", "anc+rows", "survivors+alloc", "materialise", "propose", "offsets+xsync2", "scatter+pull"]
 for i, nm in enumerate(lab):
     out.append("  %-18s %7.1f %7.1f" % (nm, np.median(d[:, i]), d[:, i].mean()))
+for nm, i0, i1 in (("  W + zeroing", 0, 12), ("  grid+signal+wait", 12, 13), ("  unpack", 13, 14), ("  grid sync", 14, 1)):
+    dd = (mid[:, i1] - mid[:, i0]) / 1e3
+    out.append("  %-18s %7.1f %7.1f" % (nm, np.median(dd), dd.mean()))
 out.append("  %-18s %7.1f %7.1f" % ("kernel total", np.median(mid[:, 11] - mid[:, 0]) / 1e3, (mid[:, 11] - mid[:, 0]).mean() / 1e3))
 gap = (t[2:N - 1, 0] - t[1:N - 2, 11]) / 1e3
 out.append("  %-18s %7.1f %7.1f" % ("between launches", np.median(gap), gap.mean()))

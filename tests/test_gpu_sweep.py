@@ -353,9 +353,9 @@ def test_seeded_sweep_matches_oracle_fed_the_same_philox_uniforms(ops, primate_g
     np.testing.assert_array_equal(sw.output("ancestors").cpu().numpy()[1:], res.ancestors[1:])
 
 
-@pytest.mark.parametrize("leaf_rows", [True, False])
+@pytest.mark.parametrize("leaf_rows,patterns", [(True, True), (False, True), (True, False)])
 @pytest.mark.parametrize("jc", [True, False])
-def test_grouped_scoring_kernels_against_oracle(ops, primate_genome, jc, leaf_rows):
+def test_grouped_scoring_kernels_against_oracle(ops, primate_genome, jc, leaf_rows, patterns):
     """The grouped visiting order and its three scoring kernels (site patterns for two leaves, state-sorted rows for a
     leaf + an internal node, the bilinear form for two internal nodes) are what large runs use; `force_sorted` puts a
     small run on that path so that it can be checked against the oracle: gaps, ambiguity codes other than gaps (class
@@ -375,6 +375,7 @@ def test_grouped_scoring_kernels_against_oracle(ops, primate_genome, jc, leaf_ro
     sw.set_uniforms(*gpu_uniforms(U))
     sw.set_option("force_sorted", 1.0)
     sw.set_option("leaf_rows", 1.0 if leaf_rows else 0.0)
+    sw.set_option("leaf_patterns", 1.0 if patterns else 0.0)   # 0: cherries go through the generic kernel, site by site
     for it in range(2):   # the second sweep replays the captured graph
         elbo = sw.forward(codes, dev(lam_l), dev(lam_r), None if jc else dev(Q), dev(pi.reshape(-1)))
         out = {k: sw.output(k).cpu().numpy().copy() for k in
