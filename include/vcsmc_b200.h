@@ -190,6 +190,9 @@ int vcsmc_sweep_set_comm(vcsmc_sweep_t* h, int rank, int world, vcsmc_comm_fn fn
  * results are identical;
  * "leaf_patterns" (default 1; lazy forward): merges of two leaves are scored from the site-pattern counts of the leaf
  * pair (tabulated once per sweep) instead of site by site -- same sum, different summation order;
+ * "sparse_bwd" (default 1): when at most 1024 particle-events carry an adjoint (the rule with ESS ~ 1), the per-site part
+ * of the reverse sweep is ONE site-parallel launch per chunk (a thread owns its site through all rank events) instead of
+ * three launches per rank event; 0 keeps the per-event kernels -- same sums up to the order of the dP reduction;
  * "leaf_rows" (default 1; lazy forward, grouped order): merges of a leaf and an internal node are scored by the rows
  * kernel on the leaf's state-sorted sites (one row of the bilinear form per 256-site sub-tile) -- same sum, different
  * summation order; 0 leaves them to the generic scoring kernel;

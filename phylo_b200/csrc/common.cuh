@@ -141,19 +141,28 @@ __device__ __forceinline__ int expm_scale(double norm) {
   return s;
 }
 
-// expm(A) by scaling-and-squaring Taylor (Horner).  Stands in for tf.linalg.expm (vcsmc.py:183-184).
+// expm(A) by scaling-and-squaring on the degree-14 Taylor polynomial (||B||_1 <= 1/2: remainder 0.5^15/15! ~ 2e-17),
+// evaluated in Paterson-Stockmeyer form on I, B, B^2, B^3 and powers of B^4: 6 matrix products instead of the 14 of a
+// Horner scheme.  Stands in for tf.linalg.expm (vcsmc.py:183-184).
 __device__ __forceinline__ M4 m4_expm(const M4& A) {
   const int s = expm_scale(m4_norm1(A));
   const double sc = ldexp(1.0, -s);
   M4 B;
 #pragma unroll
   for (int i = 0; i < 16; ++i) B.a[i] = A.a[i] * sc;
-  M4 X = m4_eye();
-  for (int k = kTaylorDegree; k >= 1; --k) {
-    M4 T = m4_mul(B, X);
-    const double ik = 1.0 / (double)k;
+  const M4 B2 = m4_mul(B, B), B3 = m4_mul(B2, B), B4 = m4_mul(B2, B2);
+  // 1/k!, k = 0..14
+  constexpr double c[15] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
+                            1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0, 1.0 / 87178291200.0};
+  M4 X;   // c12 I + c13 B + c14 B^2
 #pragma unroll
-    for (int i = 0; i < 16; ++i) X.a[i] = ((i % 5 == 0) ? 1.0 : 0.0) + T.a[i] * ik;
+  for (int i = 0; i < 16; ++i) X.a[i] = fma(c[14], B2.a[i], fma(c[13], B.a[i], (i % 5 == 0) ? c[12] : 0.0));
+#pragma unroll
+  for (int blk = 2; blk >= 0; --blk) {   // X <- (c_{4b} I + c_{4b+1} B + c_{4b+2} B^2 + c_{4b+3} B^3) + B^4 X
+    const M4 T = m4_mul(B4, X);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      X.a[i] = fma(c[4 * blk + 3], B3.a[i], fma(c[4 * blk + 2], B2.a[i], fma(c[4 * blk + 1], B.a[i], T.a[i] + ((i % 5 == 0) ? c[4 * blk] : 0.0))));
   }
   for (int j = 0; j < s; ++j) X = m4_mul(X, X);
   return X;

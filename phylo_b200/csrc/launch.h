@@ -17,6 +17,10 @@ int launch_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* p
                      const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc, const int32_t* order,
                      const int32_t* count, const double* P, const double* pi, const double* coef, int64_t K,
                      int64_t n_active, int n_sites, int jc, int skip_zero, double skip_below, double* dP, double* dpi_acc, cudaStream_t st);
+int launch_bwd_sparse(const uint8_t* codes, int64_t codes_stride, double* pool, double* gpool, int64_t slot_sites, int n_sites,
+                      int N, int64_t K, int recompute, int jc, int skip_zero, double skip_below, const int32_t* order,
+                      const int32_t* count, const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc, const int32_t* dst,
+                      const double* P, const double* pi, const double* coef, double* dP, double* dpi_acc, cudaStream_t st);
 
 // score.cu (lazy forward: likelihood-only scoring, survivor materialisation, peer pulls)
 constexpr int kLeafPairInts = 512;   // ints per leaf pair in the site-pattern table (see leaf_pair_hist_kernel)

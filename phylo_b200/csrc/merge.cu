@@ -392,6 +392,190 @@ __global__ void __launch_bounds__(kTileThreads, JC ? 2 : 1) merge_bwd_kernel(con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The per-site pass of the reverse sweep when only a handful of particles per rank event carry an adjoint (the rule with
+// ESS ~ 1: one or two lineages).  Sites are independent, so a THREAD owns its site through the whole pass: it recomputes
+// the consumed nodes of the visited particles in event order (reading what it wrote itself an event earlier), then walks
+// the events backwards accumulating child adjoints with plain read-modify-writes -- no launch per rank event, no grid
+// barrier, no atomics on the node adjoints.  The per-particle 4x4 adjoints dP = sum_s L (x) (g * rp) are reduced per CTA
+// (halving-butterfly transpose in the warp, one shared-memory round) and added to the table once per CTA.
+// Same arithmetic per site as merge_fwd_kernel / merge_bwd_kernel.
+// ---------------------------------------------------------------------------------------------
+struct SparseArgs {
+  const uint8_t* codes;
+  int64_t codes_stride;
+  double* pool;
+  double* gpool;
+  int64_t slot_sites;
+  int n_sites, N, recompute, skip_zero;
+  int64_t K;
+  double skip_below;
+  const int32_t* order;   // [N-1][K] visit lists
+  const int32_t* count;   // [N-1]
+  const int32_t* lsrc;    // [N-1][K] child / adjoint / output slots of every event
+  const int32_t* rsrc;
+  const int32_t* gsrc;
+  const int32_t* dst;
+  const double* P;        // [N-1][K][32]
+  const double* pi;
+  const double* coef;     // [N-1][K]
+  double* dP;             // [N-1][K][32]
+  double* dpi_acc;
+};
+
+template <bool JC>
+__global__ void __launch_bounds__(kTileThreads) bwd_sparse_kernel(const SparseArgs a) {
+  __shared__ double s_red[32];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int s = blockIdx.x * kTileThreads + tid;
+  const bool valid = s < a.n_sites;
+  const int64_t K = a.K;
+  double pi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) pi[j] = __ldg(a.pi + j);
+  if (tid < 32) s_red[tid] = 0.0;
+  // ---- the adjoint slots of the consumed nodes, this thread's site
+  for (int r = 0; r < a.N - 1; ++r) {
+    const int cnt = a.count[r];
+    for (int i = 0; i < cnt; ++i) {
+      const int64_t e = (int64_t)r * K + a.order[(int64_t)r * K + i];
+      const int g = a.gsrc[e];
+      if (g >= 0 && valid) st_site(a.gpool + ((int64_t)g * a.slot_sites + s) * 4, zero4());
+    }
+  }
+  // ---- forward: the consumed nodes of the visited particles, in event order
+  if (a.recompute) {
+    for (int r = 0; r < a.N - 1; ++r) {
+      const int cnt = a.count[r];
+      for (int i = 0; i < cnt; ++i) {
+        const int64_t e = (int64_t)r * K + a.order[(int64_t)r * K + i];
+        const int d = a.dst[e];
+        if (d < 0 || !valid) continue;
+        const ChildRef ra = child_ref(a.lsrc[e], a.codes, a.codes_stride, a.pool, a.slot_sites);
+        const ChildRef rb = child_ref(a.rsrc[e], a.codes, a.codes_stride, a.pool, a.slot_sites);
+        Trans<JC> Pa, Pb;
+        Pa.load(a.P + e * 32);
+        Pb.load(a.P + e * 32 + 16);
+        const d4 lp = Pa.apply(load_child(ra, s)), rp = Pb.apply(load_child(rb, s));
+        d4 nw;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nw.v[j] = lp.v[j] * rp.v[j];
+        st_site(a.pool + ((int64_t)d * a.slot_sites + s) * 4, nw);
+      }
+    }
+  }
+  // ---- backward
+  double dpi[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int r = a.N - 2; r >= 0; --r) {
+    const int cnt = a.count[r];
+    for (int i = 0; i < cnt; ++i) {
+      const int64_t e = (int64_t)r * K + a.order[(int64_t)r * K + i];
+      const double c = a.coef[e];
+      const int gs = a.gsrc[e];
+      if (a.skip_zero && fabs(c) <= a.skip_below && gs < 0) continue;  // (numerically) zero adjoint: nothing to propagate
+      const int ca = a.lsrc[e], cb = a.rsrc[e];
+      double acc[JC ? 4 : 32];
+#pragma unroll
+      for (int j = 0; j < (JC ? 4 : 32); ++j) acc[j] = 0.0;
+      if (valid) {
+        const ChildRef ra = child_ref(ca, a.codes, a.codes_stride, a.pool, a.slot_sites);
+        const ChildRef rb = child_ref(cb, a.codes, a.codes_stride, a.pool, a.slot_sites);
+        const d4 La = load_child(ra, s), Lb = load_child(rb, s);
+        Trans<JC> Pa, Pb;
+        Pa.load(a.P + e * 32);
+        Pb.load(a.P + e * 32 + 16);
+        const d4 gin = gs >= 0 ? ld_site(a.gpool + ((int64_t)gs * a.slot_sites + s) * 4) : zero4();
+        const d4 lp = Pa.apply(La), rp = Pb.apply(Lb);
+        double nw[4], x = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          nw[j] = lp.v[j] * rp.v[j];
+          x = fma(pi[j], nw[j], x);
+        }
+        const double inv = c / x;
+        d4 gl, gr;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double gi = fma(inv, pi[j], gin.v[j]);
+          dpi[j] = fma(inv, nw[j], dpi[j]);  // d ell / d pi_j = new_j / x
+          gl.v[j] = gi * rp.v[j];
+          gr.v[j] = gi * lp.v[j];
+        }
+        if (ca >= 0) {   // this thread is the only one that touches site s of any slot
+          double* g = a.gpool + ((int64_t)ca * a.slot_sites + s) * 4;
+          const d4 tt = Pa.apply_t(gl);
+          d4 cur = ld_site(g);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cur.v[j] += tt.v[j];
+          st_site(g, cur);
+        }
+        if (cb >= 0) {
+          double* g = a.gpool + ((int64_t)cb * a.slot_sites + s) * 4;
+          const d4 tt = Pb.apply_t(gr);
+          d4 cur = ld_site(g);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cur.v[j] += tt.v[j];
+          st_site(g, cur);
+        }
+        if (JC) {
+          double dl = 0.0, dr = 0.0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            dl = fma(La.v[j], gl.v[j], dl);
+            dr = fma(Lb.v[j], gr.v[j], dr);
+          }
+          const double sl = ((La.v[0] + La.v[1]) + (La.v[2] + La.v[3])) * ((gl.v[0] + gl.v[1]) + (gl.v[2] + gl.v[3]));
+          const double sr = ((Lb.v[0] + Lb.v[1]) + (Lb.v[2] + Lb.v[3])) * ((gr.v[0] + gr.v[1]) + (gr.v[2] + gr.v[3]));
+          acc[0] = dl;
+          acc[1] = sl - dl;
+          acc[2] = dr;
+          acc[3] = sr - dr;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              acc[j * 4 + jj] = La.v[j] * gl.v[jj];
+              acc[16 + j * 4 + jj] = Lb.v[j] * gr.v[jj];
+            }
+        }
+      }
+      // the CTA's share of this particle's dP: warp totals into shared memory, one add per value to the table
+      if (JC) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = warp_sum(acc[j]);
+        if (lane == 0) {
+          atomicAdd(&s_red[0], acc[0]);
+          atomicAdd(&s_red[1], acc[1]);
+          atomicAdd(&s_red[16], acc[2]);
+          atomicAdd(&s_red[17], acc[3]);
+        }
+      } else {
+        double(&v32)[32] = *reinterpret_cast<double(*)[32]>(acc);
+        warp_transpose_sum32(v32, lane);
+        atomicAdd(&s_red[lane], v32[0]);
+      }
+      __syncthreads();
+      if (tid < 32) {
+        const double v = s_red[tid];
+        if (v != 0.0) atomicAdd(a.dP + e * 32 + tid, v);
+        s_red[tid] = 0.0;
+      }
+      __syncthreads();
+    }
+  }
+  if (a.dpi_acc) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dpi[j] = warp_sum(dpi[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (dpi[j] != 0.0) atomicAdd(a.dpi_acc + j, dpi[j]);
+    }
+  }
+}
+
+
 constexpr int kSptFwd = 2;
 constexpr int kSptBwdJC = 2;
 constexpr int kSptBwdGeneral = 2;  // measured at 64x10kx65,536 dense: 1078 ms (SPT 2) vs 1278 ms (SPT 1)
@@ -509,6 +693,23 @@ int launch_merge_bwd(const uint8_t* codes, int64_t codes_stride, const double* p
   else if (spt == 2) merge_bwd_kernel<false, 2><<<grid, kTileThreads, 0, st>>>(a);
   else merge_bwd_kernel<false, 1><<<grid, kTileThreads, 0, st>>>(a);
   VCSMC_LAUNCH_CHECK("merge_bwd_kernel");
+  return VCSMC_OK;
+}
+
+int launch_bwd_sparse(const uint8_t* codes, int64_t codes_stride, double* pool, double* gpool, int64_t slot_sites, int n_sites,
+                      int N, int64_t K, int recompute, int jc, int skip_zero, double skip_below, const int32_t* order,
+                      const int32_t* count, const int32_t* lsrc, const int32_t* rsrc, const int32_t* gsrc, const int32_t* dst,
+                      const double* P, const double* pi, const double* coef, double* dP, double* dpi_acc, cudaStream_t st) {
+  if (n_sites <= 0 || N < 2) return VCSMC_OK;
+  SparseArgs a;
+  a.codes = codes; a.codes_stride = codes_stride; a.pool = pool; a.gpool = gpool; a.slot_sites = slot_sites;
+  a.n_sites = n_sites; a.N = N; a.recompute = recompute; a.skip_zero = skip_zero; a.K = K; a.skip_below = skip_below;
+  a.order = order; a.count = count; a.lsrc = lsrc; a.rsrc = rsrc; a.gsrc = gsrc; a.dst = dst; a.P = P; a.pi = pi;
+  a.coef = coef; a.dP = dP; a.dpi_acc = dpi_acc;
+  const unsigned grid = (unsigned)((n_sites + kTileThreads - 1) / kTileThreads);
+  if (jc) bwd_sparse_kernel<true><<<grid, kTileThreads, 0, st>>>(a);
+  else bwd_sparse_kernel<false><<<grid, kTileThreads, 0, st>>>(a);
+  VCSMC_LAUNCH_CHECK("bwd_sparse_kernel");
   return VCSMC_OK;
 }
 

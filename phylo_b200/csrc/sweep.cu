@@ -1070,6 +1070,7 @@ int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value) {
   }
   else if (!strcmp(name, "leaf_patterns")) { h->leaf_patterns = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
   else if (!strcmp(name, "force_sorted")) { h->force_sorted = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
+  else if (!strcmp(name, "sparse_bwd")) h->sparse_bwd = value != 0.0;
   else if (!strcmp(name, "leaf_rows")) { h->leaf_rows = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
   else if (!strcmp(name, "graph")) h->use_graph = value != 0.0;
   else if (!strcmp(name, "event_timing")) { h->event_timing = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
@@ -1506,10 +1507,24 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     Sc = (int)sc;
     gpool = lpool + n_cons * (int64_t)Sc * 4;
   }
+  // few particles to visit (ESS ~ 1): one site-parallel launch per chunk instead of three launches per rank event
+  int64_t visited_total = 0;
+  for (int r = 0; r < N - 1; ++r) visited_total += cnt_bwd[r];
+  const bool sparse = fused && h->skip_zero && h->sparse_bwd && visited_total <= 1024;
   int n_chunks = 0;
   for (int s0 = sb; s0 < se; s0 += Sc, ++n_chunks) {
     const int nc = (se - s0 < Sc) ? se - s0 : Sc;
     const uint8_t* codes_c = h->codes + s0;
+    if (sparse) {
+      h->prof_begin(2, st);
+      rc = launch_bwd_sparse(codes_c, S, lpool, gpool, Sc, nc, N, K, h->retain ? 0 : 1, h->jc, h->skip_zero, h->skip_below * fabs(grad_elbo),
+                             h->p<int32_t>(h->o_order_bwd), h->p<int32_t>(h->o_count_bwd), h->p<int32_t>(h->o_bsrc_l), h->p<int32_t>(h->o_bsrc_r),
+                             h->p<int32_t>(h->o_bsrc_g), h->p<int32_t>(h->o_bdst), h->p<double>(h->o_P), h->pi, h->p<double>(h->o_cnew),
+                             h->p<double>(h->o_dP), dpi, st);
+      h->prof_end(st);
+      if (rc) return rc;
+      continue;
+    }
     if (!h->retain) {
       // recompute the forward for this chunk, materialising only nodes that are consumed later
       for (int r = 0; r < N - 1; ++r) {

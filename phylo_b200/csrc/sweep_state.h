@@ -113,6 +113,7 @@ struct vcsmc_sweep {
           o_lz_ids = 0, o_lz_cnt = 0, o_u_res_all = 0, o_rec = 0, o_cdf_scratch = 0, o_gtab = 0, o_gcnt = 0, o_goff = 0, o_gslot = 0, o_grank = 0, o_leaf_hist = 0, o_F[2] = {0, 0}, o_topo[2] = {0, 0}, o_vm[2] = {0, 0};
   int event_timing = 0;                // option "event_timing": CTA 0 of the event kernel stamps %globaltimer at every phase boundary
   int64_t o_ev_timing = 0;
+  int sparse_bwd = 1;                  // reverse sweep: one site-parallel launch when few particles carry an adjoint (option "sparse_bwd")
   int force_sorted = 0;                // testing aid: grouped visiting order (and the rows kernel) even for small K
   int leaf_rows = 1;                   // score leaf + internal merges with the rows kernel on state-sorted sites (option "leaf_rows")
   int leaf_patterns = 1;               // score leaf-leaf merges from the site-pattern histogram (option "leaf_patterns")
