@@ -1308,9 +1308,10 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
   rc = NQ == 1 ? event_blocks<1>(smem, &blocks) : NQ == 2 ? event_blocks<2>(smem, &blocks) : NQ == 4 ? event_blocks<4>(smem, &blocks) : event_blocks<8>(smem, &blocks);
   if (rc) return rc;
   {
-    // no more CTAs than there is work for the widest phase (a warp per particle), at least one
-    const int64_t want = (K + kEvWarps - 1) / kEvWarps;
-    if (want < blocks) blocks = (int)(want < 1 ? 1 : want);
+    // no more CTAs than the widest phase has work for: grid barriers get cheaper with fewer CTAs
+    int64_t want = (K + kEvWarps - 1) / kEvWarps;   // (a warp per particle: the row phase when every particle is live)
+    if (want < 8) want = 8;
+    if (want < blocks) blocks = (int)want;
   }
 
   int64_t pair_off = 0;

@@ -1510,7 +1510,11 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   // few particles to visit (ESS ~ 1): one site-parallel launch per chunk instead of three launches per rank event
   int64_t visited_total = 0;
   for (int r = 0; r < N - 1; ++r) visited_total += cnt_bwd[r];
-  const bool sparse = fused && h->skip_zero && h->sparse_bwd && visited_total <= 1024;
+  // (cost model: the site-parallel pass walks the visited particle-events one after the other, ~2.5 us each on a short alignment; the
+  // per-event path pays three launches, ~6 us each, for every rank event that has something to visit)
+  int nonempty = 0;
+  for (int r = 0; r < N - 1; ++r) nonempty += cnt_bwd[r] > 0;
+  const bool sparse = fused && h->skip_zero && h->sparse_bwd && visited_total <= 1024 && 2.5 * (double)visited_total < 18.0 * nonempty;
   int n_chunks = 0;
   for (int s0 = sb; s0 < se; s0 += Sc, ++n_chunks) {
     const int nc = (se - s0 < Sc) ? se - s0 : Sc;
