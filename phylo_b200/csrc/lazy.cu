@@ -814,7 +814,7 @@ __device__ __forceinline__ void propose_particle(const EvArgs& a, int64_t kl, bo
 }
 
 template <int NQ>
-__global__ void __launch_bounds__(kEvThreads) lz_event_kernel(const EvArgs a) {
+__global__ void __launch_bounds__(kEvThreads, 2) lz_event_kernel(const EvArgs a) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) float su_all[];
   __shared__ double sm[8];
