@@ -406,7 +406,7 @@ def run_native(args):
     if rank == 0 and not args.no_hbm_kernels and not args.nested:
         torch.cuda.empty_cache()
         try:
-            hbm_k = hbm_kernels_run(K=2048, S=min(S, 10000), jc=jc, reps=5)
+            hbm_k = hbm_kernels_run(K=4096, S=10000, jc=jc, reps=5)
             for nm, kk in hbm_k["kernels"].items():
                 kk["traffic"] = traffic_file.get("hbm_" + nm + sfx)
         except torch.OutOfMemoryError:

@@ -17,8 +17,9 @@ namespace vcsmc {
 namespace {
 
 constexpr int kLookThreads = 256;
-constexpr int kLookTile = 128;   // sites per staged tile: n * 128 * 32 B of shared memory (n <= 48 fits 227 KB)
-constexpr int kMaxNestedRoots = 48;
+constexpr int kLookTile = 128;   // sites per staged tile when n <= 48: n * tile * 32 B of shared memory must fit 192 KB
+constexpr int kLookSmem = 48 * kLookTile * 32;
+constexpr int kMaxNestedRoots = kMaxRoots;   // larger forests stage shorter tiles (slower: every round of 256 (pair, sub-sample) combinations re-reads the roots)
 
 __device__ __forceinline__ void pair_of(int t, int n, int& r1, int& r2) {
   // r1-major enumeration of vncsmc.py:324-377: t = sum_{i<r1} (n-1-i) + (r2 - r1 - 1)
@@ -99,7 +100,7 @@ __global__ void nested_inherit_kernel(const InheritArgs a) {
 }
 
 struct LookArgs {
-  int r, n, N, M, jc, gc, S;
+  int r, n, N, M, jc, gc, S, tile;
   int64_t K;
   const int32_t* ids;
   const int32_t* cnt;
@@ -122,7 +123,7 @@ struct LookArgs {
 
 template <bool JC>
 __global__ void __launch_bounds__(kLookThreads) lookahead_kernel(const LookArgs a) {
-  extern __shared__ __align__(32) double roots[];  // [n][kLookTile][4]
+  extern __shared__ __align__(32) double roots[];  // [n][tile][4]
   __shared__ int s_ref[kMaxNestedRoots];            // < 0: leaf -(ref+1); else pool slot
   __shared__ double s_ell[kMaxNestedRoots], s_prior[kMaxNestedRoots];
   __shared__ int s_cnt[kMaxNestedRoots];
@@ -176,22 +177,23 @@ __global__ void __launch_bounds__(kLookThreads) lookahead_kernel(const LookArgs 
     }
     double pr = 1.0;
     int ex = 0;
-    for (int s0 = 0; s0 < a.S; s0 += kLookTile) {
-      const int nt = min(kLookTile, a.S - s0);
+    const int tile = a.tile;
+    for (int s0 = 0; s0 < a.S; s0 += tile) {
+      const int nt = min(tile, a.S - s0);
       __syncthreads();
-      for (int e = tid; e < n * kLookTile; e += kLookThreads) {
-        const int p = e / kLookTile, sl = e - p * kLookTile;
+      for (int e = tid; e < n * tile; e += kLookThreads) {
+        const int p = e / tile, sl = e - p * tile;
         if (sl < nt) {
           const int ref = s_ref[p];
           const d4 v = ref < 0 ? leaf_site(__ldg(a.codes + (int64_t)(-ref - 1) * a.codes_stride + s0 + sl))
                                : ld_site(a.pool + ((int64_t)ref * a.slot_sites + s0 + sl) * 4);
-          *reinterpret_cast<d4*>(roots + ((int64_t)p * kLookTile + sl) * 4) = v;
+          *reinterpret_cast<d4*>(roots + ((int64_t)p * tile + sl) * 4) = v;
         }
       }
       __syncthreads();
       if (on) {
-        const double* A1 = roots + (int64_t)r1 * kLookTile * 4;
-        const double* A2 = roots + (int64_t)r2 * kLookTile * 4;
+        const double* A1 = roots + (int64_t)r1 * tile * 4;
+        const double* A2 = roots + (int64_t)r2 * tile * 4;
         for (int sl = g; sl < nt; sl += G) {
           const d4 L1 = *reinterpret_cast<const d4*>(A1 + sl * 4), L2 = *reinterpret_cast<const d4*>(A2 + sl * 4);
           double x = 0.0;
@@ -527,13 +529,17 @@ int launch_lookahead(int r, int n, int N, int M, int jc, int gc, int S, int64_t 
                      const double* lam_r, const double* u_bl, const double* u_br, uint64_t seed, double* pot,
                      cudaStream_t st) {
   if (n > kMaxNestedRoots) { set_error("nested look-ahead supports at most %d live subtrees (got %d)", kMaxNestedRoots, n); return VCSMC_ERR_ARG; }
-  LookArgs a{r, n, N, M, jc, gc, S, K, ids, cnt, slot, codes, codes_stride, pool, slot_sites, ell_node, ldf, Q, pi,
+  int tile = kLookSmem / (n * 32);
+  if (tile > kLookTile) tile = kLookTile;
+  if (tile < 8) tile = 8;
+  LookArgs a{r, n, N, M, jc, gc, S, tile, K, ids, cnt, slot, codes, codes_stride, pool, slot_sites, ell_node, ldf, Q, pi,
              lam_l, lam_r, u_bl, u_br, seed, pot};
-  const size_t smem = (size_t)n * kLookTile * 32;
+  size_t smem = (size_t)n * tile * 32;
+  if (smem < 256 * 8 * 2) smem = 256 * 8 * 2;   // (the buffer doubles as the [G][combos] scratch of the site-slice sum)
   static bool configured = false;
   if (!configured) {
-    VCSMC_CUDA(cudaFuncSetAttribute(lookahead_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxNestedRoots * kLookTile * 32));
-    VCSMC_CUDA(cudaFuncSetAttribute(lookahead_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxNestedRoots * kLookTile * 32));
+    VCSMC_CUDA(cudaFuncSetAttribute(lookahead_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxRoots * 8 * 32 > kLookSmem ? kMaxRoots * 8 * 32 : kLookSmem));
+    VCSMC_CUDA(cudaFuncSetAttribute(lookahead_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxRoots * 8 * 32 > kLookSmem ? kMaxRoots * 8 * 32 : kLookSmem));
     configured = true;
   }
   if (jc) lookahead_kernel<true><<<(unsigned)K, kLookThreads, smem, st>>>(a);

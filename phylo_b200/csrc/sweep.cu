@@ -514,6 +514,34 @@ __global__ void __launch_bounds__(256) bwd_scalar_kernel(const ScalarArgs a) {
   }
 }
 
+// particle sharding: the forward filled P only for this rank's particles; the reverse sweep needs the matrices of the
+// particles it visits (any rank's), from the gathered branch lengths -- matrix i of event blockIdx.y is child (i & 1) of
+// particle order[r][i >> 1]
+__global__ void __launch_bounds__(64) transition_visited_kernel(const double* __restrict__ Q, const double* __restrict__ t2,
+                                                                const int32_t* __restrict__ order, const int32_t* __restrict__ count,
+                                                                int64_t K, int jc, double* __restrict__ P) {
+  const int r = blockIdx.y;
+  const int64_t n = 2 * (int64_t)count[r];
+  for (int64_t i = (int64_t)blockIdx.x * 64 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 64) {
+    const int64_t m = 2 * ((int64_t)r * K + order[(int64_t)r * K + (i >> 1)]) + (i & 1);
+    const double ti = t2[m];
+    double* out = P + m * 16;
+    if (jc) {
+      const double o = -0.25 * expm1(-ti);
+      const double d = 0.25 + 0.75 * exp(-ti);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) out[e] = (e % 5 == 0) ? d : o;
+    } else {
+      M4 A;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) A.a[e] = __ldg(Q + e) * ti;
+      const M4 X = m4_expm(A);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) out[e] = X.a[e];
+    }
+  }
+}
+
 // dP rows of the particles the reverse merge is going to visit (instead of clearing the whole [N-1][K][32] table)
 __global__ void __launch_bounds__(256) zero_dP_rows_kernel(const int32_t* __restrict__ order, const int32_t* __restrict__ count,
                                                            int64_t K, double* __restrict__ dP) {
@@ -1311,8 +1339,9 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
   VCSMC_CUDA(cudaMemsetAsync(h->p<char>(h->o_suf_r), 0, K * sizeof(double), st));
   count_launch(14);
 
-  if (h->world > 1) {
+  if (h->world > 1 && h->M > 0) {
     // the forward filled P only for this rank's particles: rebuild all of it from the gathered branch lengths
+    // (the VCSMC path rebuilds the visited particles' matrices only, once the visit lists are known)
     rc = launch_transition_fwd(h->Q, h->p<double>(h->o_t2), 2 * E, h->jc, h->p<double>(h->o_P), st);
     if (rc) return rc;
   }
@@ -1448,6 +1477,12 @@ int vcsmc_sweep_backward(vcsmc_sweep_t* h, double grad_elbo, double* dlam_l, dou
     cnt_rec = cnt_bwd;
     int32_t max_cnt = 0;
     for (int r = 0; r < N - 1; ++r) max_cnt = cnt_bwd[r] > max_cnt ? cnt_bwd[r] : max_cnt;
+    if (max_cnt > 0 && h->world > 1) {
+      const int64_t bx = (2 * (int64_t)max_cnt + 63) / 64;
+      transition_visited_kernel<<<dim3((unsigned)(bx < 4096 ? bx : 4096), N - 1), 64, 0, st>>>(
+          h->Q, h->p<double>(h->o_t2), h->p<int32_t>(h->o_order_bwd), h->p<int32_t>(h->o_count_bwd), K, h->jc, h->p<double>(h->o_P));
+      VCSMC_LAUNCH_CHECK("transition_visited_kernel");
+    }
     if (max_cnt > 0) {
       const unsigned bx = (unsigned)((max_cnt + 7) / 8 < 2048 ? (max_cnt + 7) / 8 : 2048);
       zero_dP_rows_kernel<<<dim3(bx, N - 1), 256, 0, st>>>(h->p<int32_t>(h->o_order_bwd), h->p<int32_t>(h->o_count_bwd), K, h->p<double>(h->o_dP));

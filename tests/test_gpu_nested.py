@@ -116,3 +116,14 @@ def test_nested_class_and_seeded_mode(ops, primate_genome):
     m3 = VCSMC(dd, 64, argparse.Namespace(nested=False, **base), seed=3)
     e3 = float(m3.sample_phylogenies(need_grad=False, seed=99))
     assert e1 > e3 + 100          # README figure: VNCSMC sits far above VCSMC on primates
+
+
+def test_nested_more_than_48_taxa(ops):
+    """The look-ahead stages a particle's roots in shared memory; beyond 48 roots it stages shorter site tiles."""
+    N, K, M = 52, 3, 2
+    g = synthetic_genome(N, 40, seed=8, gaps=0.05)
+    p = random_params(N, False, seed=2)
+    U = O.UniformsNested.draw(N, K, M, seed=4)
+    res, g_ref = oracle_nested(g, K, M, p, U)
+    out, grads = run_nested(ops, g, K, M, p, U, False)
+    compare(out, res, grads, g_ref, False, N, K)
