@@ -79,7 +79,7 @@ int launch_lookahead(int r, int n, int N, int M, int jc, int gc, int S, int64_t 
                      const int32_t* slot, const uint8_t* codes, int64_t codes_stride, const double* pool, int64_t slot_sites,
                      const double* ell_node, const double* ldf, const double* Q, const double* pi, const double* lam_l,
                      const double* lam_r, const double* u_bl, const double* u_br, uint64_t seed, double* pot,
-                     cudaStream_t st);
+                     double share, cudaStream_t st);
 int launch_nested_choose(int r, int n, int N, int M, int gc, int64_t K, double* pot, const double* u_cat, const double* u_bl,
                          const double* u_br, uint64_t seed, const double* lam_l, const double* lam_r, const int32_t* ids,
                          const int32_t* cnt, const int32_t* slot, int32_t* ids_new, int32_t* cnt_new, int32_t* slot_new,

@@ -119,6 +119,7 @@ struct LookArgs {
   const double* u_br;
   uint64_t seed;
   double* pot;  // [K][C*M] raw potentials
+  double share; // site sharding: fraction of the site-independent terms this rank contributes before the all-reduce (1 otherwise)
 };
 
 template <bool JC>
@@ -239,7 +240,10 @@ __global__ void __launch_bounds__(kLookThreads) lookahead_kernel(const LookArgs 
       const int cm = s_cnt[r1] + s_cnt[r2];
       const double prior12 = -a.ldf[2 * max(cm, 2) - 3];
       // vncsmc.py:363-365: joint(merged) - joint(left) - joint(right)
-      a.pot[k * combos + c] = ((val + prior12) - (s_ell[r1] + s_prior[r1])) - (s_ell[r2] + s_prior[r2]);
+      if (a.share == 1.0)
+        a.pot[k * combos + c] = ((val + prior12) - (s_ell[r1] + s_prior[r1])) - (s_ell[r2] + s_prior[r2]);
+      else   // this rank's sites only: the all-reduce completes the site sum, one rank contributes the site-free terms
+        a.pot[k * combos + c] = val + a.share * ((prior12 - (s_ell[r1] + s_prior[r1])) - (s_ell[r2] + s_prior[r2]));
     }
   }
 }
@@ -527,13 +531,13 @@ int launch_lookahead(int r, int n, int N, int M, int jc, int gc, int S, int64_t 
                      const int32_t* slot, const uint8_t* codes, int64_t codes_stride, const double* pool, int64_t slot_sites,
                      const double* ell_node, const double* ldf, const double* Q, const double* pi, const double* lam_l,
                      const double* lam_r, const double* u_bl, const double* u_br, uint64_t seed, double* pot,
-                     cudaStream_t st) {
+                     double share, cudaStream_t st) {
   if (n > kMaxNestedRoots) { set_error("nested look-ahead supports at most %d live subtrees (got %d)", kMaxNestedRoots, n); return VCSMC_ERR_ARG; }
   int tile = kLookSmem / (n * 32);
   if (tile > kLookTile) tile = kLookTile;
   if (tile < 8) tile = 8;
   LookArgs a{r, n, N, M, jc, gc, S, tile, K, ids, cnt, slot, codes, codes_stride, pool, slot_sites, ell_node, ldf, Q, pi,
-             lam_l, lam_r, u_bl, u_br, seed, pot};
+             lam_l, lam_r, u_bl, u_br, seed, pot, share};
   size_t smem = (size_t)n * tile * 32;
   if (smem < 256 * 8 * 2) smem = 256 * 8 * 2;   // (the buffer doubles as the [G][combos] scratch of the site-slice sum)
   static bool configured = false;

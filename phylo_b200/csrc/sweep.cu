@@ -1227,9 +1227,13 @@ int vcsmc_sweep_forward(vcsmc_sweep_t* h, const uint8_t* codes, const double* la
       double* pot = h->p<double>(h->o_pot) + h->pot_off[r];
       h->prof_begin(3, st);
       rc = launch_lookahead(r, n, N, h->M, h->jc, h->fwd_gc, S, K, inh_ids, inh_cnt, inh_slot, codes, S, pool, S, ell_node,
-                            h->p<double>(h->o_ldf), Q, pi, lam_l, lam_r, lk_bl, lk_br, h->seed, pot, st);
+                            h->p<double>(h->o_ldf), Q, pi, lam_l, lam_r, lk_bl, lk_br, h->seed, pot, h->allreduce ? h->scalar_share : 1.0, st);
       h->prof_end(st);
       if (rc) return rc;
+      if (h->allreduce) {   // site sharding: the look-ahead's site sums are completed across ranks before the options are drawn
+        rc = h->allreduce(h->allreduce_user, pot, K * (int64_t)(n * (n - 1) / 2) * h->M, st);
+        if (rc) { set_error("allreduce hook failed (%d)", rc); return VCSMC_ERR_CUDA; }
+      }
       rc = launch_nested_choose(r, n, N, h->M, h->fwd_gc, K, pot, u_cat, lk_bl, lk_br, h->seed, lam_l, lam_r, inh_ids, inh_cnt,
                                 inh_slot, a.ids_new, a.cnt_new, a.slot_new, a.lref, a.rref, a.nleaf, a.rempos,
                                 h->p<int32_t>(h->o_choice) + (int64_t)r * K, a.b_l, a.b_r, a.t2, h->p<double>(h->o_qlog),
