@@ -31,7 +31,8 @@ int launch_leaf_sort(const uint8_t* codes, int64_t stride, int N, int S, int32_t
 int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double* pool, int64_t slot_sites,
                        const int32_t* lsrc, const int32_t* rsrc, const int32_t* order, const double* P, const double* pi,
                        int64_t K, const int32_t* count, int n_sites, int jc, int skip_leaf_pairs,
-                       const int32_t* leaf_perm, const uint8_t* leaf_tstate, double* ell_part, int* n_parts, cudaStream_t st);
+                       const int32_t* leaf_perm, const uint8_t* leaf_tstate, double* ell_part, int* n_parts, cudaStream_t st,
+                       cudaStream_t st_generic = nullptr);
 int launch_materialise(const uint8_t* codes, int64_t codes_stride, double* pool, int64_t slot_sites, const int32_t* lsrc,
                        const int32_t* rsrc, const int32_t* list, const int32_t* count, int64_t max_count, const int32_t* loc,
                        int64_t e_base, const double* P, int n_sites, int jc, cudaStream_t st);

@@ -1341,11 +1341,28 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
     const int cur = r & 1;
     const double* P = h->p<double>(h->o_P) + ((int64_t)r * K + k0) * 32;
     int tiles = 0;
+    // the two scoring kernels are independent: the generic one runs on a side stream beside the rows kernel (fork / join
+    // through events; inside a capture these become graph edges)
+    const bool fork = leaf_perm != nullptr && h->score_streams && !h->profile;
+    if (fork) {
+      if (!h->side_stream) {
+        VCSMC_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+        VCSMC_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        VCSMC_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+      }
+      VCSMC_CUDA(cudaEventRecord(h->ev_fork, st));
+      VCSMC_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    }
     h->prof_begin(0, st);
     rc = launch_merge_score(codes, S, h->p<double>(h->o_pool), S, a.lsrc[cur], a.rsrc[cur], sorted ? a.order : nullptr, P, pi, Kl,
-                            sorted ? a.gcount : nullptr, S, h->jc, leaf_hist != nullptr, leaf_perm, leaf_tstate, h->p<double>(h->o_ell_part), &tiles, st);
+                            sorted ? a.gcount : nullptr, S, h->jc, leaf_hist != nullptr, leaf_perm, leaf_tstate, h->p<double>(h->o_ell_part), &tiles, st,
+                            fork ? h->side_stream : nullptr);
     h->prof_end(st);
     if (rc) return rc;
+    if (fork) {
+      VCSMC_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
+      VCSMC_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+    }
     a.ell_part = h->p<double>(h->o_ell_part);
     a.tiles = tiles;
     if (h->allreduce) {

@@ -995,7 +995,9 @@ constexpr int kScoreParts = 8;   // partial sums per particle (upper bound of th
 int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double* pool, int64_t slot_sites,
                        const int32_t* lsrc, const int32_t* rsrc, const int32_t* order, const double* P, const double* pi,
                        int64_t K, const int32_t* count, int n_sites, int jc, int skip_leaf_pairs,
-                       const int32_t* leaf_perm, const uint8_t* leaf_tstate, double* ell_part, int* n_parts, cudaStream_t st) {
+                       const int32_t* leaf_perm, const uint8_t* leaf_tstate, double* ell_part, int* n_parts, cudaStream_t st,
+                       cudaStream_t st_generic) {
+  // st_generic (optional): the generic kernel runs there, beside the rows kernel on `st` (the caller joins the streams)
   if (n_parts) *n_parts = 0;
   if (K <= 0 || n_sites <= 0) return VCSMC_OK;
   static int spt_general = 0;
@@ -1047,9 +1049,10 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
     chunking(K, a.R, a.tiles, a.items, a.n_parts, &tpi, &nc);
     const int64_t total = ((K + a.R - 1) / a.R) * (order ? (int64_t)kScoreParts : (int64_t)nc);   // upper bound of the work items
     const unsigned grid = (unsigned)(total < cap ? total : cap);
-    if (jc) merge_score_kernel<true, 4><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
-    else if (spt == 4) merge_score_kernel<false, 4><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
-    else merge_score_kernel<false, 2><<<grid, kTileThreads, kScoreSmemBytes, st>>>(a);
+    cudaStream_t sg = (rows && st_generic) ? st_generic : st;
+    if (jc) merge_score_kernel<true, 4><<<grid, kTileThreads, kScoreSmemBytes, sg>>>(a);
+    else if (spt == 4) merge_score_kernel<false, 4><<<grid, kTileThreads, kScoreSmemBytes, sg>>>(a);
+    else merge_score_kernel<false, 2><<<grid, kTileThreads, kScoreSmemBytes, sg>>>(a);
     VCSMC_LAUNCH_CHECK("merge_score_kernel");
   }
   if (rows) {

@@ -1099,6 +1099,7 @@ int vcsmc_sweep_set_option(vcsmc_sweep_t* h, const char* name, double value) {
   else if (!strcmp(name, "leaf_patterns")) { h->leaf_patterns = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
   else if (!strcmp(name, "force_sorted")) { h->force_sorted = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
   else if (!strcmp(name, "sparse_bwd")) h->sparse_bwd = value != 0.0;
+  else if (!strcmp(name, "score_streams")) { h->score_streams = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
   else if (!strcmp(name, "leaf_rows")) { h->leaf_rows = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }
   else if (!strcmp(name, "graph")) h->use_graph = value != 0.0;
   else if (!strcmp(name, "event_timing")) { h->event_timing = value != 0.0; if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; } }

@@ -114,6 +114,9 @@ struct vcsmc_sweep {
   int event_timing = 0;                // option "event_timing": CTA 0 of the event kernel stamps %globaltimer at every phase boundary
   int64_t o_ev_timing = 0;
   int sparse_bwd = 1;                  // reverse sweep: one site-parallel launch when few particles carry an adjoint (option "sparse_bwd")
+  int score_streams = 1;               // the two scoring kernels of a rank event on two streams (option "score_streams")
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int force_sorted = 0;                // testing aid: grouped visiting order (and the rows kernel) even for small K
   int leaf_rows = 1;                   // score leaf + internal merges with the rows kernel on state-sorted sites (option "leaf_rows")
   int leaf_patterns = 1;               // score leaf-leaf merges from the site-pattern histogram (option "leaf_patterns")
@@ -169,6 +172,9 @@ struct vcsmc_sweep {
     for (auto e : ev) cudaEventDestroy(e);
     if (fwd_graph) cudaGraphExecDestroy(fwd_graph);
     if (cap_stream) cudaStreamDestroy(cap_stream);
+    if (side_stream) cudaStreamDestroy(side_stream);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
   }
 
   template <typename T>
