@@ -832,7 +832,7 @@ __global__ void __launch_bounds__(kEvThreads, 2) lz_event_kernel(const EvArgs a)
   if (r > 0) {
     const int64_t e_row = (int64_t)(r - 1) * K;
     double* lw = a.lw + e_row;
-    double *psum = a.cdf_scratch + nb, *pw = psum + nb, *pq = pw + nb;
+    double *pw = a.cdf_scratch + 2 * nb, *pq = pw + nb;
     // ---- phase 1: weights of event r-1 for the own particles (one thread each; the few partial log-likelihoods of a
     // particle are summed in a fixed order), and the maximum log-weight (exact in any order: an atomic max on the
     // order-preserving integer image of the doubles)
@@ -884,7 +884,7 @@ __global__ void __launch_bounds__(kEvThreads, 2) lz_event_kernel(const EvArgs a)
     stamp(a, 1);
     const double M = from_ordered_bits(*(volatile long long*)a.lw_max);
     stamp(a, 2);
-    // ---- phases 2-4: log-sum-exp, normalised weights + live flags, CDF (resample, vcsmc.py:284-285)
+    // ---- phases 2-3: weights exp(lw - max) + live flags, CDF, log-sum-exp (resample, vcsmc.py:284-285)
     if (gtid == 0) {
       a.counts[0] = 0;
       a.counts[1] = 0;
@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(kEvThreads, 2) lz_event_kernel(const EvArgs a)
       a.gcount[0] = 0;
       a.gcount[1] = 0;
     }
-    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_sumexp(vb, lw, K, M, psum, sm);
+    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_weights(vb, lw, K, M, a.cdf, pw, pq, a.live, sm);
     if (a.world > 1) {
       // the rest of the other ranks' records: needed from phase 5 on, fetched by the CTAs that have no CDF tile
       const int first = nb < (int)gridDim.x ? nb : 0, n_cta = (int)gridDim.x - first;
@@ -902,10 +902,8 @@ __global__ void __launch_bounds__(kEvThreads, 2) lz_event_kernel(const EvArgs a)
     }
     grid.sync();
     stamp(a, 3);
-    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_weights(vb, lw, K, nb, M, psum, a.cdf, pw, pq, a.live, sm);
-    grid.sync();
     stamp(a, 4);
-    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_scan(vb, K, nb, M, psum, pw, pq, a.cdf, a.stats + (r - 1) * 4, sm, wsum);
+    for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_scan(vb, K, nb, M, pw, pq, a.cdf, a.stats + (r - 1) * 4, sm, wsum);
     grid.sync();
     if (r == N - 1) {
       // ---- last launch: ELBO (vcsmc.py:276), log_likelihood_R (vcsmc.py:254-268, incl. quirk Q4), log_likelihood_tilde

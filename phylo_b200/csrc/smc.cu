@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kCdfThreads) resample_cdf_kernel(const double*
   }
   __syncthreads();
   const double lse = bc[1];
-  const double mlog = M - lse;  // max of the normalised logits (vcsmc.py:284)
+
 
   // segment totals of w = exp(logit - max) and of w^2
   double run = 0.0, sq = 0.0;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kCdfThreads) resample_cdf_kernel(const double*
     for (int q = 0; q < 4; ++q) v[q] = (i0 + 32 * q < e) ? lw[i0 + 32 * q] : -INFINITY;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const double w = exp((v[q] - lse) - mlog);
+      const double w = exp(v[q] - M);
       run += w;
       sq = fma(w, w, sq);
     }
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kCdfThreads) resample_cdf_kernel(const double*
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int64_t i = i0 + 32 * q + lane;
-      v[q] = i < e ? exp((lw[i] - lse) - mlog) : 0.0;
+      v[q] = i < e ? exp(lw[i] - M) : 0.0;
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kCdfThreads) resample_cdf_kernel(const double*
   }
 }
 
-// ---- the same statistics and CDF with ceil(K / 2048) CTAs (four tiny launches instead of one 80 us single-CTA kernel
+// ---- the same statistics and CDF with ceil(K / 2048) CTAs (three tiny launches instead of one 80 us single-CTA kernel
 // at K = 65,536).  Every reduction runs in a fixed order (cdf_stage_* in smc_device.cuh, shared with the lazy forward's
 // event kernel), so every GPU -- and every schedule -- derives bit-identical ancestors.
 __global__ void __launch_bounds__(256) cdf_max_kernel(const double* __restrict__ lw, int64_t K, double* __restrict__ pmax) {
@@ -158,46 +158,35 @@ __global__ void __launch_bounds__(256) cdf_max_kernel(const double* __restrict__
   cdf_stage_max((int)blockIdx.x, lw, K, pmax, sm);
 }
 
-__global__ void __launch_bounds__(256) cdf_sumexp_kernel(const double* __restrict__ lw, int64_t K, int nb,
-                                                         const double* __restrict__ pmax, double* __restrict__ psum) {
-  __shared__ double sm[8];
-  const double M = block_reduce_array(pmax, nb, true, sm);
-  cdf_stage_sumexp((int)blockIdx.x, lw, K, M, psum, sm);
-}
-
 __global__ void __launch_bounds__(256) cdf_weights_kernel(const double* __restrict__ lw, int64_t K, int nb,
-                                                          const double* __restrict__ pmax, const double* __restrict__ psum,
-                                                          double* __restrict__ w_out, double* __restrict__ pw,
-                                                          double* __restrict__ pq) {
+                                                          const double* __restrict__ pmax, double* __restrict__ w_out,
+                                                          double* __restrict__ pw, double* __restrict__ pq) {
   __shared__ double sm[8];
   const double M = block_reduce_array(pmax, nb, true, sm);
-  cdf_stage_weights((int)blockIdx.x, lw, K, nb, M, psum, w_out, pw, pq, nullptr, sm);
+  cdf_stage_weights((int)blockIdx.x, lw, K, M, w_out, pw, pq, nullptr, sm);
 }
 
 __global__ void __launch_bounds__(256) cdf_scan_kernel(int64_t K, int nb, const double* __restrict__ pmax,
-                                                       const double* __restrict__ psum, const double* __restrict__ pw,
-                                                       const double* __restrict__ pq, double* __restrict__ cdf,
-                                                       double* __restrict__ stats) {
+                                                       const double* __restrict__ pw, const double* __restrict__ pq,
+                                                       double* __restrict__ cdf, double* __restrict__ stats) {
   __shared__ double sm[8];
   __shared__ double wsum[8];
   const double M = block_reduce_array(pmax, nb, true, sm);
-  cdf_stage_scan((int)blockIdx.x, K, nb, M, psum, pw, pq, cdf, stats, sm, wsum);
+  cdf_stage_scan((int)blockIdx.x, K, nb, M, pw, pq, cdf, stats, sm, wsum);
 }
 
-// small K: the same four stages, tile after tile, by ONE CTA in one launch (identical arithmetic)
+// small K: the same three stages, tile after tile, by ONE CTA in one launch (identical arithmetic)
 __global__ void __launch_bounds__(256) cdf_one_cta_kernel(const double* __restrict__ lw, int64_t K, int nb, double* __restrict__ scratch,
                                                           double* __restrict__ cdf, double* __restrict__ stats) {
   __shared__ double sm[8];
   __shared__ double wsum[8];
-  double *pmax = scratch, *psum = scratch + nb, *pw = scratch + 2 * nb, *pq = scratch + 3 * nb;
+  double *pmax = scratch, *pw = scratch + 2 * nb, *pq = scratch + 3 * nb;
   for (int vb = 0; vb < nb; ++vb) cdf_stage_max(vb, lw, K, pmax, sm);
   __syncthreads();
   const double M = block_reduce_array(pmax, nb, true, sm);
-  for (int vb = 0; vb < nb; ++vb) cdf_stage_sumexp(vb, lw, K, M, psum, sm);
+  for (int vb = 0; vb < nb; ++vb) cdf_stage_weights(vb, lw, K, M, cdf, pw, pq, nullptr, sm);
   __syncthreads();
-  for (int vb = 0; vb < nb; ++vb) cdf_stage_weights(vb, lw, K, nb, M, psum, cdf, pw, pq, nullptr, sm);
-  __syncthreads();
-  for (int vb = 0; vb < nb; ++vb) cdf_stage_scan(vb, K, nb, M, psum, pw, pq, cdf, stats, sm, wsum);
+  for (int vb = 0; vb < nb; ++vb) cdf_stage_scan(vb, K, nb, M, pw, pq, cdf, stats, sm, wsum);
 }
 
 __global__ void resample_search_kernel(const double* __restrict__ cdf, const double* __restrict__ stats,
@@ -265,7 +254,7 @@ int launch_resample_cdf(const double* lw, int64_t K, double* cdf, double* stats,
     return VCSMC_OK;
   }
   const int nb = (int)((K + kCdfTile - 1) / kCdfTile);
-  double *pmax = scratch, *psum = scratch + nb, *pw = scratch + 2 * nb, *pq = scratch + 3 * nb;
+  double *pmax = scratch, *pw = scratch + 2 * nb, *pq = scratch + 3 * nb;
   if (nb <= 2) {   // one launch; same arithmetic as the four-launch path and as the lazy forward's event kernel
     cdf_one_cta_kernel<<<1, 256, 0, st>>>(lw, K, nb, scratch, cdf, stats);
     VCSMC_LAUNCH_CHECK("cdf_one_cta_kernel");
@@ -273,11 +262,9 @@ int launch_resample_cdf(const double* lw, int64_t K, double* cdf, double* stats,
   }
   cdf_max_kernel<<<nb, 256, 0, st>>>(lw, K, pmax);
   VCSMC_LAUNCH_CHECK("cdf_max_kernel");
-  cdf_sumexp_kernel<<<nb, 256, 0, st>>>(lw, K, nb, pmax, psum);
-  VCSMC_LAUNCH_CHECK("cdf_sumexp_kernel");
-  cdf_weights_kernel<<<nb, 256, 0, st>>>(lw, K, nb, pmax, psum, cdf, pw, pq);
+  cdf_weights_kernel<<<nb, 256, 0, st>>>(lw, K, nb, pmax, cdf, pw, pq);
   VCSMC_LAUNCH_CHECK("cdf_weights_kernel");
-  cdf_scan_kernel<<<nb, 256, 0, st>>>(K, nb, pmax, psum, pw, pq, cdf, stats);
+  cdf_scan_kernel<<<nb, 256, 0, st>>>(K, nb, pmax, pw, pq, cdf, stats);
   VCSMC_LAUNCH_CHECK("cdf_scan_kernel");
   return VCSMC_OK;
 }

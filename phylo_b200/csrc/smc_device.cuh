@@ -52,7 +52,7 @@ __device__ __forceinline__ int upper_bound_cdf(const double* __restrict__ cdf, i
 
 // ---------------------------------------------------------------------------------------------
 // log-sum-exp, ESS and the categorical CDF of K log-weights in tiles of 2048 elements (resample, vcsmc.py:284-285; also
-// compute_log_ZSMC's reduce_logsumexp, vcsmc.py:276).  Four stages, each needing the previous one's partials of ALL tiles;
+// compute_log_ZSMC's reduce_logsumexp, vcsmc.py:276).  Three stages, each needing the previous one's partials of ALL tiles;
 // `vb` is the tile a CTA of exactly 256 threads works on.  Every reduction has a fixed order that depends on K only, so
 // whoever runs the stages (four launches, one CTA, the lazy forward's cooperative event kernel; 1 or 8 GPUs) gets the
 // same bits, hence the same ancestors.
@@ -91,29 +91,20 @@ __device__ __forceinline__ void cdf_stage_max(int vb, const double* lw, int64_t 
   }
 }
 
-// M: the maximum of all K log-weights (exact in any order: the tile maxima of stage 1 reduced, or an atomic max)
-__device__ __forceinline__ void cdf_stage_sumexp(int vb, const double* lw, int64_t K, double M, double* psum, double* sm) {
-  const int64_t b = (int64_t)vb * kCdfTile + threadIdx.x;
-  double s = 0.0;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) s += b + q * 256 < K ? exp(lw[b + q * 256] - M) : 0.0;
-  const double t = block_sum<256>(s, sm);
-  if (threadIdx.x == 0) psum[vb] = t;
-}
-
-// live (optional): 1 where the normalised weight is not zero in double precision -- the particles that can be drawn by
-// the next resampling or carry a gradient
-__device__ __forceinline__ void cdf_stage_weights(int vb, const double* lw, int64_t K, int nb, double M,
-                                                  const double* psum, double* w_out, double* pw, double* pq, int32_t* live,
-                                                  double* sm) {
-  const double lse = M + log(block_reduce_array(psum, nb, false, sm));
-  const double mlog = M - lse;  // max of the normalised logits (vcsmc.py:284)
+// Stage 2: unnormalised weights w = exp(lw - M), M = the maximum of all K log-weights (exact in any order: the tile
+// maxima of stage 1 reduced, or an atomic max), and their tile sums.  tf.random.categorical draws from exp(logit - max
+// logit) with logit = lw - logsumexp(lw) (vcsmc.py:284-285), i.e. from the same numbers up to the rounding of two
+// subtractions instead of one; logsumexp = M + log(sum w) needs no pass of its own.
+// live (optional): 1 where the weight is not zero in double precision -- the particles that can be drawn by the next
+// resampling or carry a gradient
+__device__ __forceinline__ void cdf_stage_weights(int vb, const double* lw, int64_t K, double M, double* w_out, double* pw,
+                                                  double* pq, int32_t* live, double* sm) {
   const int64_t b = (int64_t)vb * kCdfTile + (int64_t)threadIdx.x * 8;   // 8 CONSECUTIVE elements per thread
   double s = 0.0, q2 = 0.0;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     if (b + q < K) {
-      const double w = exp((lw[b + q] - lse) - mlog);
+      const double w = exp(lw[b + q] - M);
       w_out[b + q] = w;
       if (live) live[b + q] = w != 0.0;
       s += w;
@@ -128,9 +119,8 @@ __device__ __forceinline__ void cdf_stage_weights(int vb, const double* lw, int6
   }
 }
 
-__device__ __forceinline__ void cdf_stage_scan(int vb, int64_t K, int nb, double M, const double* psum,
-                                               const double* pw, const double* pq, double* cdf, double* stats, double* sm,
-                                               double* wsum) {
+__device__ __forceinline__ void cdf_stage_scan(int vb, int64_t K, int nb, double M, const double* pw, const double* pq,
+                                               double* cdf, double* stats, double* sm, double* wsum) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const double offset = block_reduce_array(pw, vb, false, sm);   // sum of the tiles before this one
   const int64_t b = (int64_t)vb * kCdfTile + (int64_t)tid * 8;
@@ -158,11 +148,10 @@ __device__ __forceinline__ void cdf_stage_scan(int vb, int64_t K, int nb, double
     if (b + q < K) cdf[b + q] = base + w[q];
   if (vb == 0) {
     __syncthreads();
-    const double lse = M + log(block_reduce_array(psum, nb, false, sm));
     const double t = block_reduce_array(pw, nb, false, sm);
     const double q = block_reduce_array(pq, nb, false, sm);
     if (tid == 0) {
-      stats[0] = lse;
+      stats[0] = M + log(t);
       stats[1] = t;
       stats[2] = t * t / q;
       stats[3] = M;

@@ -22,7 +22,7 @@ for it in range(3):
     torch.cuda.synchronize()
     print("forward %.3f ms" % e0.elapsed_time(e1))
 t = sw.event_timing().astype(np.float64)
-names = ["weights", "unpack+max", "sumexp", "w+live", "scan", "anc+rows", "survivors+alloc", "materialise", "propose", "offsets+sync", "scatter+pull"]
+names = ["weights", "unpack+max", "w+live", "-", "scan", "anc+rows", "survivors+alloc", "materialise", "propose", "offsets+sync", "scatter+pull"]
 mid = t[1:N - 1]                       # full launches (r = 1 .. N-2)
 d = np.diff(mid[:, :12], axis=1) / 1e3
 print("per launch, us (median / mean over r = 1..N-2):")

@@ -38,7 +38,7 @@ names = ["weights+pack", "xsync1+unpack", "(max read)", "sumexp", "w+live", "sca
 mid = t[1:N - 1]
 d = np.diff(mid[:, :12], axis=1) / 1e3
 out = ["rank %d per launch, us (median / mean over r = 1..N-2):" % rank]
-lab = ["weights+pack", "xsync1+unpack", "sumexp", "w+live", "scan", "anc+rows", "survivors+alloc", "materialise", "propose", "offsets+xsync2", "scatter+pull"]
+lab = ["weights+pack", "xsync1+unpack", "w+live", "-", "scan", "anc+rows", "survivors+alloc", "materialise", "propose", "offsets+xsync2", "scatter+pull"]
 for i, nm in enumerate(lab):
     out.append("  %-18s %7.1f %7.1f" % (nm, np.median(d[:, i]), d[:, i].mean()))
 for nm, i0, i1 in (("  W + zeroing", 0, 12), ("  grid+signal+wait", 12, 13), ("  unpack", 13, 14), ("  grid sync", 14, 1)):
