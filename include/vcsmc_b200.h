@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VCSMC_ABI_VERSION 2
+#define VCSMC_ABI_VERSION 3
 
 #define VCSMC_OK 0
 #define VCSMC_ERR_ARG (-1)      /* bad argument */

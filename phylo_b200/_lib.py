@@ -86,7 +86,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.vcsmc_abi_version() != 2:
+    if lib.vcsmc_abi_version() != 3:
         raise ImportError("libvcsmc_b200 ABI version mismatch")
     _lib = lib
     return lib

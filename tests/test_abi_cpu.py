@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libvcsmc_b200.so does not export %s" % name
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared
-    assert lib.vcsmc_abi_version() == 2
+    assert lib.vcsmc_abi_version() == 3
 
 
 def test_arguments_are_validated_without_a_gpu():
