@@ -353,14 +353,15 @@ def run_native(args):
     if args.nested:
         # the look-ahead evaluates C(n,2) M merges per particle on roots it reads once: FP64-bound
         la_ms, la_n = prof["lookahead"]
-        look_ops = 20.0 * look_merges * args.steps               # 20 DFMA per look-ahead particle.site (bilinear form)
+        # 20 DFMA per look-ahead particle.site (bilinear form); this rank's launches cover its own sites only
+        look_ops = 20.0 * look_merges * (float(S_fwd) / S) * args.steps
         tops = look_ops / (la_ms * 1e-3) / 1e12 if la_ms > 0 else 0.0
-        roots_bytes = float(K) * S * 32.0 * sum(N - r for r in range(N - 1)) * args.steps   # every root read once per event
+        roots_bytes = float(K) * S_fwd * 32.0 * sum(N - r for r in range(N - 1)) * args.steps   # every root read once per event
         roofline = {"bound": "fp64", "kernel": "lookahead_kernel", "achieved": tops, "peak": FP64_PEAK_TFMA,
                     "unit": "T FP64 op/s", "frac": tops / FP64_PEAK_TFMA, "traffic": traffic_file.get("lookahead" + sfx),
                     "peak_source": "scripts/microbench.cu on this pool's B200s (DFMA, 64 warps/SM)", "launches": la_n,
                     "avg_launch_ms": la_ms / max(la_n, 1), "ops_per_lookahead_merge": 20.0,
-                    "lookahead_merges_per_s": look_merges * args.steps / (la_ms * 1e-3) if la_ms > 0 else 0.0,
+                    "lookahead_merges_per_s_this_rank": look_merges * (float(S_fwd) / S) * args.steps / (la_ms * 1e-3) if la_ms > 0 else 0.0,
                     "hbm": {"algorithmic_gbs": roots_bytes / (la_ms * 1e-3) / 1e9 if la_ms > 0 else 0.0, "peak": peak,
                             "frac": roots_bytes / (la_ms * 1e-3) / 1e9 / peak if la_ms > 0 else 0.0,
                             "note": "every root of every particle read once per rank event (32 B per site)"},
