@@ -10,13 +10,16 @@ forward and the same number backward; `value` = K*S*(N-1) / seconds per step (fw
 Workload (BASELINE.json configs[4], the one the metric's target is quoted on): 64 taxa x 10,000 sites x 65,536
 particles, i.i.d. uniform nucleotides (numpy PCG64 seed 0), reference initial parameters (rates 10, `GTR' logits
 1/4, uniform pi), float64.  N GPUs: the PARTICLES are sharded, K/N per GPU (strong scaling: K and S stay fixed; per
-rank event one all-gather of the step record, nodes of remote ancestors pulled over NVLink, reverse sweep sharded by
-site).  --sharding sites selects the site-sharded layout instead.
+rank event the step record is exchanged over peer memory, surviving nodes recomputed where their children are, reverse
+sweep sharded by site).  --sharding sites selects the site-sharded layout instead.
+--config c1..c5 selects the BASELINE.json configurations (c1: the training epoch as named, GPU or --impl reference).
 
 The default path is the production one: the forward scores every particle and materialises only the particles that the
-next resampling draws ("lazy"); the reverse sweep skips events whose adjoint is exactly zero.  Results are identical to
-the eager / dense schedule, which is also timed (N = 1) and reported under "eager_dense" with the HBM roofline
-fractions of its two streaming kernels.
+next resampling draws ("lazy"); the reverse sweep skips events whose adjoint coefficient is below 2^-64 of dELBO.  The
+line says what was executed (`merges_by_children`, `executed`), reports the scoring kernels -- the dominant kernels of
+the step -- against the FP64 peak (`roofline`), the HBM-bound merge kernels on distinct children against the HBM peak
+(`roofline.hbm_kernels`), the eager / dense schedule (`eager_dense`, N = 1), checksums of the integer tables and, at
+N > 1, a comparison with a single-GPU sweep of the same seed (`single_gpu_check`).
 
 --impl reference times the restated reference (oracle/vcsmc_oracle.py: TensorFlow 1.15 cannot be installed
 in this image) on the host cores on a bounded sample of the same workload.
@@ -512,9 +515,10 @@ def run_native(args):
     if single is not None:
         line["single_gpu_check"] = single
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cval, cores, desc, per = cpu_sample_run(args.cpu_sample, jc, 1, 0)
+        n_cpu = 6                                    # about 10 s of CPU work
+        cval, cores, desc, per = cpu_sample_run(args.cpu_sample, jc, n_cpu, 0)
         line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": desc + " (1 sweep, %.1f s)" % per}
+                                "sample": desc + " (%d sweeps, %.1f s each)" % (n_cpu, per)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
