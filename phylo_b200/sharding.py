@@ -55,3 +55,16 @@ def choose_sharding(requested, n_particles: int, world: int, nested: bool) -> st
             raise ValueError("particle sharding needs the VCSMC proposal and n_particles divisible by the number of ranks")
         return requested
     return "sites" if (nested or n_particles % world != 0) else "particles"
+
+
+def shared_seed(seed, dist=None) -> int:
+    """The run's seed: rank 0's (explicit, or drawn when ``seed`` is None) on every rank.  Particle sharding needs every
+    rank to derive identical ancestors, pairs and branch lengths from the same counter-based uniforms, site sharding
+    identical draws for all particles, and both the same site minibatches; the reference seeds nothing, so an unseeded
+    multi-process run would otherwise diverge silently."""
+    s = int(seed if seed is not None else np.random.SeedSequence().entropy % (2 ** 63))
+    if dist is not None:
+        box = [s]
+        dist.broadcast_object_list(box, src=0)
+        s = int(box[0])
+    return s

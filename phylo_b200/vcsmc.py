@@ -26,7 +26,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .sharding import choose_sharding, local_sites, scalar_share, site_slice
+from .sharding import choose_sharding, local_sites, scalar_share, shared_seed, site_slice
 
 F64 = torch.float64
 
@@ -74,13 +74,7 @@ class VCSMC:
             self.y_station = None
         dist = _dist()
         self.rank, self.world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
-        self.seed = int(seed if seed is not None else np.random.SeedSequence().entropy % (2 ** 63))
-        if dist:
-            # every rank must derive the same ancestors, pairs and branch lengths from the same counter-based uniforms
-            # and train on the same site minibatches: rank 0's seed (explicit or drawn) is the run's seed
-            box = [self.seed]
-            dist.broadcast_object_list(box, src=0)
-            self.seed = int(box[0])
+        self.seed = shared_seed(seed, dist)   # rank 0's seed (explicit or drawn) on every rank
         self._slice_rng = random.Random(self.seed) if (dist or seed is not None) else random
         self._step_counter = 0
         self._sweeps: Dict[tuple, ops.Sweep] = {}

@@ -70,3 +70,28 @@ def test_site_sharding_world2_jc():
 
 def test_site_sharding_world2_gtr():
     _run(False, 29612)
+
+
+def _seed_worker(rank, world, port, explicit, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import random
+    from phylo_b200.sharding import shared_seed
+    seed = shared_seed((100 + rank) if explicit else None, dist)      # ranks start from different seeds (or none at all)
+    rng = random.Random(seed)
+    sites = list(range(50))
+    out[rank] = (seed, [rng.sample(sites, 8) for _ in range(3)])      # what VCSMC.batch_slices draws from
+    dist.destroy_process_group()
+
+
+def test_seed_and_minibatches_are_shared_across_ranks():
+    """runner.py's default is seed=None: without a shared seed every rank would draw its own ancestors and its own site
+    minibatches.  Rank 0's seed, explicit or drawn, is the run's."""
+    for explicit, port in ((False, 29641), (True, 29642)):
+        mgr = mp.Manager()
+        out = mgr.dict()
+        mp.spawn(_seed_worker, args=(2, port, explicit, out), nprocs=2, join=True)
+        assert out[0] == out[1]
+        if explicit:
+            assert out[0][0] == 100
