@@ -34,17 +34,38 @@ constexpr int kRScore = 32;  // particles per scoring group
 constexpr int kCoef = 20;    // doubles per particle in shared memory: M[4][4] (or the 4 JC coefficients) + the column sums of M
 
 // Work items of a scoring launch: groups of R particles x chunks of tiles.  `count` (how many particles the launch really
-// has to score) is only known on the device, so the kernel itself splits a group's tiles into as many chunks as it takes
-// to reach about `items` work items (at most n_parts: a particle has that many partial sums).
-__host__ __device__ __forceinline__ void chunking(int64_t count, int R, int tiles, int items, int n_parts, int* tiles_per_item,
-                                                  int* n_chunks) {
-  int64_t groups = (count + R - 1) / R;
-  if (groups < 1) groups = 1;
-  int64_t nc = (items + groups - 1) / groups;
-  if (nc > n_parts) nc = n_parts;
-  if (nc > tiles) nc = tiles;
-  if (nc < 1) nc = 1;
-  *tiles_per_item = (int)((tiles + nc - 1) / nc);
+// has to score) is only known on the device, so the kernel itself decides into how many chunks a group's tiles are split
+// (at most n_parts: a particle has that many partial sums).
+//   fixed2 == 0: as many chunks as it takes to reach about 4 work items per resident CTA (`slots` of them);
+//   fixed2 > 0:  a work item costs a fixed part (staging the group, the final reduction: about fixed2 / 2 tiles' worth
+//                of time) plus its tiles, and the items run in rounds of `slots` resident CTAs: the number of chunks that
+//                minimises rounds x (fixed + tiles per item).
+// (measured with scripts/score_bench: the second rule suits the rows kernel, the first the generic one)
+__host__ __device__ __noinline__ void chunking(int64_t count, int R, int tiles, int slots, int fixed2, int n_parts,
+                                                  int* tiles_per_item, int* n_chunks) {
+  unsigned groups = (unsigned)((count + R - 1) / R);
+  if (groups < 1u) groups = 1u;
+  int nc_max = n_parts < tiles ? n_parts : tiles;
+  if (nc_max < 1) nc_max = 1;
+  int best = 1;
+  if (fixed2 == 0) {
+    best = (int)((4u * (unsigned)slots + groups - 1u) / groups);
+    best = best > nc_max ? nc_max : best;
+  } else {
+    int64_t best_cost = -1;
+    for (int nc = 1; nc <= nc_max; ++nc) {
+      const int tpi = (tiles + nc - 1) / nc;
+      const int real = (tiles + tpi - 1) / tpi;
+      if (real != nc) continue;   // (the same split as fewer chunks)
+      const unsigned rounds = (groups * (unsigned)nc + (unsigned)slots - 1u) / (unsigned)slots;
+      const int64_t cost = (int64_t)rounds * (fixed2 + 2 * tpi);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best = nc;
+      }
+    }
+  }
+  *tiles_per_item = (tiles + best - 1) / best;
   *n_chunks = (tiles + *tiles_per_item - 1) / *tiles_per_item;
 }
 
@@ -62,7 +83,8 @@ struct ScoreArgs {
   int64_t K;
   int n_sites;
   int tiles;
-  int items;            // work items wanted per launch (the kernel splits a group's tiles into chunks accordingly)
+  int items;            // resident CTAs of a launch (the kernel splits a group's tiles into chunks accordingly)
+  int fixed2;           // twice the fixed cost of a work item, in tiles
   int R;
   int skip_leaf_pairs;  // particles whose children are both leaves are scored from the pattern histogram instead
   int n_parts;          // partial sums per particle in ell_part (>= n_chunks; the tail is zero-filled)
@@ -303,8 +325,10 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int R = a.R;
   const int64_t count = a.count ? (int64_t)*a.count : a.K;
-  int tiles_per_item, n_chunks;
-  chunking(count, R, a.tiles, a.items, a.n_parts, &tiles_per_item, &n_chunks);
+  __shared__ int s_chunking[2];
+  if (tid == 0) chunking(count, R, a.tiles, a.items, a.fixed2, a.n_parts, &s_chunking[0], &s_chunking[1]);   // (divisions: one thread)
+  __syncthreads();
+  const int tiles_per_item = s_chunking[0], n_chunks = s_chunking[1];
   const int64_t total = ((count + R - 1) / R) * n_chunks;
   double pi[4];
 #pragma unroll
@@ -447,15 +471,17 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
 // ---------------------------------------------------------------------------------------------
 // When child a is a LEAF, L_a[s] is a 0/1 mask and the site likelihood is row `state` of M (the column sums of M for a
 // gap) dotted with L_b[s].  leaf_sort_kernel lists every leaf's sites by state class once per sweep (A, C, G, T, gap,
-// other ambiguity codes; every class padded to whole 256-site sub-tiles with -1), so that the 256 sites a CTA visits
-// together use the SAME row: it is fetched once per particle (a broadcast read), the four sites of a thread cost 16
-// DFMA, and their product is folded into the running (mantissa, exponent) with ONE split -- against a per-lane row
-// fetch, 4 + 1 FP64 ops and a split per site in the generic kernel's leaf path, which was bound by instruction issue,
-// not by the FP64 pipe.  The internal child is read through the permutation (32 B per site: whole sectors, so the
-// gather costs nothing extra).
-constexpr int kRowTile = 1024;            // sorted positions per tile: 256 threads x 4 sub-tiles
-constexpr int kRowSub = 256;              // positions per sub-tile (one state class each)
+// other ambiguity codes; every class padded to whole 128-position units with -1).  A warp visits one unit per step (a
+// lane: four consecutive positions), so all its sites use the SAME row: it is fetched once per particle (a broadcast
+// read), the four sites of a lane cost 16 DFMA, and their product is folded into the running (mantissa, exponent) with
+// ONE split -- against a per-lane row fetch, 4 + 1 FP64 ops and a split per site in the generic kernel's leaf path, which
+// was bound by instruction issue, not by the FP64 pipe.  Class boundaries fall between warps, never inside one, so
+// every unit takes the same path; a warp whose unit is empty (class tails, the end of the list) skips it.  The
+// internal child is read through the permutation (32 B per site: whole sectors, so the gather costs nothing extra).
+constexpr int kRowTile = 1024;            // sorted positions per tile: 8 warps x one unit
+constexpr int kRowSub = 128;              // positions per unit: 32 lanes x 4 consecutive positions, ONE state class
 constexpr int kLeafClasses = 6;
+constexpr int kRenorm = 4;                // tiles between two renormalisations of the running products (power of two)
 
 __device__ __forceinline__ int leaf_class(int code) {
   code &= 15;
@@ -526,8 +552,8 @@ struct RowArgs {
   const double* P;
   const double* pi;
   const int32_t* perm;    // [N][Sp] sites of every leaf in state order (-1: padding)
-  const uint8_t* tstate;  // [N][Sp / 256] state class of every sub-tile (255: empty)
-  int Sp, tiles, items, R, n_parts;
+  const uint8_t* tstate;  // [N][Sp / 128] state class of every unit (255: empty)
+  int Sp, tiles, items, fixed2, R, n_parts;
   double* ell_part;
 };
 
@@ -554,15 +580,36 @@ __device__ __noinline__ double rows_slow(const RowArgs a, int leaf, int cb, cons
   return acc;
 }
 
-// fold the product v of a thread's four site likelihoods into a particle's running (mantissa product, biased exponent
-// sum): one split; a product that is not a positive normal number poisons the mantissa (the particle is redone site by site)
-__device__ __forceinline__ void fold_product(double v, double* pp, int* pe) {
-  const int hi = __double2hiint(v);
-  const unsigned e = (unsigned)hi >> 20;
-  double pr = *pp * __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(v));
-  if ((e - 1u) >= 0x7feu) pr = __longlong_as_double(0x7ff8000000000000ll);
-  *pp = pr;
-  *pe += (int)e;
+// Two particles of a run against the four sites of a lane: their rows of M from shared memory (broadcast reads), 32 DFMA
+// in eight independent chains, and the product of each particle's four site likelihoods multiplied into its running
+// product (shared memory; distinct words per particle, which the compiler cannot know: loads first, stores last).
+__device__ __forceinline__ void rows_trip(const double* rowp, double* pp, const double (&Lb)[4][4], const double (&x0)[4]) {
+  const double2 a0 = *reinterpret_cast<const double2*>(rowp), a1 = *reinterpret_cast<const double2*>(rowp + 2);
+  const double2 b0 = *reinterpret_cast<const double2*>(rowp + kCoef), b1 = *reinterpret_cast<const double2*>(rowp + kCoef + 2);
+  const double pa = pp[0], pb = pp[kTileThreads];
+  double xa[4], xb[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    xa[q] = fma(a0.x, Lb[q][0], x0[q]);
+    xb[q] = fma(b0.x, Lb[q][0], x0[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    xa[q] = fma(a0.y, Lb[q][1], xa[q]);
+    xb[q] = fma(b0.y, Lb[q][1], xb[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    xa[q] = fma(a1.x, Lb[q][2], xa[q]);
+    xb[q] = fma(b1.x, Lb[q][2], xb[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    xa[q] = fma(a1.y, Lb[q][3], xa[q]);
+    xb[q] = fma(b1.y, Lb[q][3], xb[q]);
+  }
+  pp[0] = pa * ((xa[0] * xa[1]) * (xa[2] * xa[3]));
+  pp[kTileThreads] = pb * ((xb[0] * xb[1]) * (xb[2] * xb[3]));
 }
 
 __global__ void __launch_bounds__(kTileThreads, 2) merge_score_rows_kernel(const RowArgs a) {
@@ -578,9 +625,11 @@ __global__ void __launch_bounds__(kTileThreads, 2) merge_score_rows_kernel(const
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int R = a.R;
   const int64_t count = (int64_t)*a.count;
-  // chunks of tiles per group of particles: as many as it takes to fill the machine with the particles there really are
-  int tiles_per_item, n_chunks;
-  chunking(count, R, a.tiles, a.items, a.n_parts, &tiles_per_item, &n_chunks);
+  // chunks of tiles per group of particles, for the particles there really are
+  __shared__ int s_chunking[2];
+  if (tid == 0) chunking(count, R, a.tiles, a.items, a.fixed2, a.n_parts, &s_chunking[0], &s_chunking[1]);   // (divisions: one thread)
+  __syncthreads();
+  const int tiles_per_item = s_chunking[0], n_chunks = s_chunking[1];
   const int64_t total = ((count + R - 1) / R) * n_chunks;
   const int n_sub = a.Sp / kRowSub;
   double pi[4];
@@ -638,161 +687,148 @@ __global__ void __launch_bounds__(kTileThreads, 2) merge_score_rows_kernel(const
 
     const int t_begin = tc * tiles_per_item;
     const int t_end = min(a.tiles, t_begin + tiles_per_item);
-    for (int t = t_begin; t < t_end; ++t) {
-      for (int run = 0; run < n_runs; ++run) {
-        const int jb = s_run[run], je = s_run[run + 1];
-        const int ca = s_a[jb], cb = s_b[jb];
-        // the four sub-tiles of the leaf's tile t: state classes and this thread's four sites
-        const uchar4 c4 = *reinterpret_cast<const uchar4*>(a.tstate + (int64_t)ca * n_sub + (int64_t)t * 4);
-        if (c4.x == 255) continue;   // (classes are packed from the front: nothing of this leaf in tile t)
-        const int cls[4] = {c4.x, c4.y, c4.z, c4.w};
-        const int32_t* pm = a.perm + (int64_t)ca * a.Sp + (int64_t)t * kRowTile + tid;
-        const double* node = a.pool + (int64_t)cb * a.slot_sites * 4;
-        double Lb[4][4], x0[4];
-        int code[4];
-        bool other = false;
+    for (int run = 0; run < n_runs; ++run) {
+      const int jb = s_run[run], len = s_run[run + 1] - jb;
+      const int ca = s_a[jb], cb = s_b[jb];
+      const double* node = a.pool + (int64_t)cb * a.slot_sites * 4;
+      const int4* pm = reinterpret_cast<const int4*>(a.perm + (int64_t)ca * a.Sp) + tid;   // + t * 256: the lane's four positions of tile t
+      const uint8_t* ts = a.tstate + (int64_t)ca * n_sub + wid;                            // + t * 8: the class of the warp's unit of tile t
+      double* const pp0 = my_prod + jb * kTileThreads;
+      int* const pe0 = my_exp + jb * kTileThreads;
+      const double* const Mj = sC + jb * kCoef;
+      int erun = 0;   // exponents taken out of this lane's sites: common to every particle of the run
+      int cls_n = ts[t_begin * kWarps];
+      int4 s4_n = __ldg(pm + t_begin * kTileThreads);
+      for (int t = t_begin; t < t_end; ++t) {
+        const int cls = cls_n;
+        const int4 s4 = s4_n;
+        if (t + 1 < t_end) {   // the next unit's class and positions are fetched while this one is scored
+          cls_n = ts[(t + 1) * kWarps];
+          s4_n = __ldg(pm + (t + 1) * kTileThreads);
+        }
+        if (cls != 255) {   // (warp-uniform: 255 = nothing of this leaf in the unit)
+          const int sq[4] = {s4.x, s4.y, s4.z, s4.w};
+          double Lb[4][4], x0[4];
+          int code[4] = {0, 0, 0, 0};
+          d4 Lraw[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int s = cls[q] != 255 ? __ldg(pm + q * kTileThreads) : -1;
-          code[q] = 0;
-          other = other || cls[q] == 5;
-          if (s >= 0) {
-            const d4 L = ld_site(node + (int64_t)s * 4);
+          for (int q = 0; q < 4; ++q) Lraw[q] = ld_site(node + (int64_t)max(sq[q], 0) * 4);   // (no branch: the four loads are in flight together)
+          if (cls == 5) {
 #pragma unroll
-            for (int m = 0; m < 4; ++m) Lb[q][m] = L.v[m];
-            x0[q] = 0.0;
-            if (cls[q] == 5) code[q] = __ldg(a.codes + (int64_t)ca * a.codes_stride + s) & 15;
+            for (int q = 0; q < 4; ++q) code[q] = sq[q] >= 0 ? __ldg(a.codes + (int64_t)ca * a.codes_stride + sq[q]) & 15 : 0;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            // the site's partials scaled by a power of two so that the largest lies in [1, 2): the site likelihoods of
+            // all particles are then O(M), the running products need no split per step, and the exponent taken out
+            // is the same for every particle of the run
+            const d4& L = Lraw[q];
+            // (non-negative doubles order like their high words; a negative or NaN partial gives an exponent out of range)
+            const unsigned eu = max(max((unsigned)__double2hiint(L.v[0]), (unsigned)__double2hiint(L.v[1])),
+                                    max((unsigned)__double2hiint(L.v[2]), (unsigned)__double2hiint(L.v[3]))) >> 20;
+            const bool valid = sq[q] >= 0;                                // padding: no site, likelihood 1
+            const int em = eu - 1u < 0x7feu ? (int)eu : 1023;             // zero / subnormal / non-finite / negative partials stay as they are (and poison the product)
+            const double sc = valid ? __hiloint2double((2046 - em) << 20, 0) : 0.0;
+            erun += valid ? em - 1023 : 0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) Lb[q][m] = L.v[m] * sc;
+            x0[q] = valid ? 0.0 : 1.0;
+          }
+          double* pp = pp0;
+          if (cls != 5) {
+            // one row of M (or its column sums) for the whole unit: a broadcast read per particle
+            const double* rowp = Mj + (cls == 4 ? 16 : 4 * cls);
+            // two particles per trip (rows_trip), two trips unrolled so that the shared-memory addresses are immediates
+            const int pairs = len >> 1;
+#pragma unroll 2
+            for (int i = 0; i < pairs; ++i) rows_trip(rowp + 2 * kCoef * i, pp + 2 * kTileThreads * i, Lb, x0);
+            if (len & 1) {
+              rowp += 2 * kCoef * pairs;
+              pp += 2 * kTileThreads * pairs;
+              const double2 r0 = *reinterpret_cast<const double2*>(rowp), r1 = *reinterpret_cast<const double2*>(rowp + 2);
+              double x[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                x[q] = fma(r1.y, Lb[q][3], fma(r1.x, Lb[q][2], fma(r0.y, Lb[q][1], fma(r0.x, Lb[q][0], x0[q]))));
+              pp[0] *= (x[0] * x[1]) * (x[2] * x[3]);
+            }
           } else {
+            // other ambiguity codes in the unit: the rows each site's mask covers, summed per site
+            const double* Mi = Mj;
+            for (int i = 0; i < len; ++i, pp += kTileThreads, Mi += kCoef) {
+              double x[4];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) Lb[q][m] = 0.0;
-            x0[q] = 1.0;   // padding: the site likelihood of "no site" is 1
-          }
-        }
-        double* pp = my_prod + jb * kTileThreads;
-        int* pe = my_exp + jb * kTileThreads;
-        const double* Mj = sC + jb * kCoef;
-        const int len = je - jb;
-        if (!other && c4.x == c4.y && c4.x == c4.z && c4.x == c4.w) {
-          // one row of M (or its column sums) for all four sub-tiles: a broadcast read per particle
-          const double* rowp = Mj + (c4.x == 4 ? 16 : 4 * c4.x);
-          int i = 0;
-          // two particles per trip, loads first: the particles' accumulators are distinct shared-memory words, which the
-          // compiler cannot know, so the interleaving (two independent chains per site) is written out by hand
-          for (; i + 1 < len; i += 2, pp += 2 * kTileThreads, pe += 2 * kTileThreads, rowp += 2 * kCoef) {
-            const double2 a0 = *reinterpret_cast<const double2*>(rowp), a1 = *reinterpret_cast<const double2*>(rowp + 2);
-            const double2 b0 = *reinterpret_cast<const double2*>(rowp + kCoef), b1 = *reinterpret_cast<const double2*>(rowp + kCoef + 2);
-            const double pa = pp[0], pb = pp[kTileThreads];
-            const int ea = pe[0], eb = pe[kTileThreads];
-            double xa[4], xb[4];
+              for (int q = 0; q < 4; ++q) {
+                double acc = x0[q];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              xa[q] = fma(a0.x, Lb[q][0], x0[q]);
-              xb[q] = fma(b0.x, Lb[q][0], x0[q]);
-            }
+                for (int jj = 0; jj < 4; ++jj) {
+                  if (code[q] >> jj & 1) {
+                    double d = Mi[jj * 4] * Lb[q][0];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              xa[q] = fma(a0.y, Lb[q][1], xa[q]);
-              xb[q] = fma(b0.y, Lb[q][1], xb[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              xa[q] = fma(a1.x, Lb[q][2], xa[q]);
-              xb[q] = fma(b1.x, Lb[q][2], xb[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              xa[q] = fma(a1.y, Lb[q][3], xa[q]);
-              xb[q] = fma(b1.y, Lb[q][3], xb[q]);
-            }
-            const double va = (xa[0] * xa[1]) * (xa[2] * xa[3]), vb = (xb[0] * xb[1]) * (xb[2] * xb[3]);
-            const int ha = __double2hiint(va), hb = __double2hiint(vb);
-            const unsigned sa = (unsigned)ha >> 20, sb = (unsigned)hb >> 20;
-            double na = pa * __hiloint2double((ha & 0x000fffff) | 0x3ff00000, __double2loint(va));
-            double nb = pb * __hiloint2double((hb & 0x000fffff) | 0x3ff00000, __double2loint(vb));
-            if ((sa - 1u) >= 0x7feu) na = __longlong_as_double(0x7ff8000000000000ll);
-            if ((sb - 1u) >= 0x7feu) nb = __longlong_as_double(0x7ff8000000000000ll);
-            pp[0] = na;
-            pp[kTileThreads] = nb;
-            pe[0] = ea + (int)sa;
-            pe[kTileThreads] = eb + (int)sb;
-          }
-          if (i < len) {
-            const double2 r0 = *reinterpret_cast<const double2*>(rowp), r1 = *reinterpret_cast<const double2*>(rowp + 2);
-            double x[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              x[q] = fma(r1.y, Lb[q][3], fma(r1.x, Lb[q][2], fma(r0.y, Lb[q][1], fma(r0.x, Lb[q][0], x0[q]))));
-            fold_product((x[0] * x[1]) * (x[2] * x[3]), pp, pe);
-          }
-        } else if (!other) {
-          // sub-tiles of different classes (a class boundary inside the tile): a row per sub-tile
-          int roff[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) roff[q] = cls[q] == 4 ? 16 : cls[q] == 255 ? 0 : 4 * cls[q];
-          for (int i = 0; i < len; ++i, pp += kTileThreads, pe += kTileThreads, Mj += kCoef) {
-            double x[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const double2 r0 = *reinterpret_cast<const double2*>(Mj + roff[q]), r1 = *reinterpret_cast<const double2*>(Mj + roff[q] + 2);
-              x[q] = fma(r1.y, Lb[q][3], fma(r1.x, Lb[q][2], fma(r0.y, Lb[q][1], fma(r0.x, Lb[q][0], x0[q]))));
-            }
-            fold_product((x[0] * x[1]) * (x[2] * x[3]), pp, pe);
-          }
-        } else {
-          // other ambiguity codes somewhere in the tile: the rows each site's mask covers, summed per site
-          for (int i = 0; i < len; ++i, pp += kTileThreads, pe += kTileThreads, Mj += kCoef) {
-            double x[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int mask = cls[q] == 5 ? code[q] : cls[q] == 4 ? 15 : cls[q] == 255 ? 0 : 1 << cls[q];
-              double acc = x0[q];
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                if (mask >> jj & 1) {
-                  double d = Mj[jj * 4] * Lb[q][0];
-#pragma unroll
-                  for (int m = 1; m < 4; ++m) d = fma(Mj[jj * 4 + m], Lb[q][m], d);
-                  acc += d;
+                    for (int m = 1; m < 4; ++m) d = fma(Mi[jj * 4 + m], Lb[q][m], d);
+                    acc += d;
+                  }
                 }
+                x[q] = acc;
               }
-              x[q] = acc;
+              pp[0] *= (x[0] * x[1]) * (x[2] * x[3]);
             }
-            fold_product((x[0] * x[1]) * (x[2] * x[3]), pp, pe);
           }
         }
-      }
-      if (((t - t_begin) & 127) == 127) {   // keep the mantissa products far from 2^1024 (NaN stays NaN)
-        for (int j = 0; j < nj; ++j) {
-          const double pr = my_prod[j * kTileThreads];
-          const int h2 = __double2hiint(pr);
-          const unsigned e2 = ((unsigned)h2 >> 20) & 0x7ffu;
-          if (e2 != 0x7ffu) {
-            my_exp[j * kTileThreads] += (int)e2 - 1023;
-            my_prod[j * kTileThreads] = __hiloint2double((h2 & 0x000fffff) | 0x3ff00000, __double2loint(pr));
+        // At the end of the run's tiles the running products go back to [1, 2) and their exponents, with the ones taken
+        // out of the sites, to the integer sums; every kRenorm tiles in between only if some product has left
+        // [2^-480, 2^480) (a look at the high words).  kRenorm further steps keep a product a normal number unless some
+        // M_k or partial is below ~1e-9 (each step multiplies by four likelihoods of O(M_k)): a product found outside
+        // [2^-959, 2^1024) -- or negative, or NaN -- poisons the particle, which is then redone with one log per site.
+        bool renorm = t == t_end - 1;
+        if (!renorm && ((t - t_begin) & (kRenorm - 1)) == kRenorm - 1) {
+          int hmin = 0x7fffffff, hmax = 0;
+          for (int i = 0; i < len; ++i) {
+            const int h = reinterpret_cast<const int*>(pp0 + i * kTileThreads)[1];
+            hmin = min(hmin, h);
+            hmax = max(hmax, h);
           }
+          renorm = hmin < ((1023 - 480) << 20) || hmax >= ((1023 + 480) << 20);
+        }
+        if (renorm) {
+          for (int i = 0; i < len; ++i) {
+            const double pr = pp0[i * kTileThreads];
+            const int h2 = __double2hiint(pr);
+            const unsigned e2 = (unsigned)h2 >> 20;   // (sign included)
+            const bool sane = e2 - 64u < 0x7ffu - 64u;
+            pe0[i * kTileThreads] += sane ? (int)e2 - 1023 + erun : 0;
+            pp0[i * kTileThreads] = sane ? __hiloint2double((h2 & 0x000fffff) | 0x3ff00000, __double2loint(pr))
+                                         : __longlong_as_double(0x7ff8000000000000ll);
+          }
+          erun = 0;
         }
       }
     }
-    // sum_s log x_s = log(prod mantissas) + ln2 * sum (exponents - bias): one fold (bias 1023) per thread and non-empty tile
+    // sum_s log x_s = log(prod mantissas) + ln2 * sum of the exponents.  A warp combines the 256 per-thread products of a
+    // particle (8 entries per lane) before the log: 32 logs per particle instead of 256.  Entries are products of at most
+    // (tiles of the item) mantissas in [1, 2): with few tiles eight of them multiply without renormalisation.
+    const bool few = t_end - t_begin <= 100;
     __syncthreads();
     for (int j = wid; j < nj; j += kWarps) {
-      const int ca = s_a[j];
-      int folds = 0;
-      for (int t = t_begin + lane; t < t_end; t += 32) folds += a.tstate[(int64_t)ca * n_sub + (int64_t)t * 4] != 255;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) folds += __shfl_xor_sync(0xffffffffu, folds, o);
-      const int my_bias = 1023 * folds;
       double p = 1.0;
       int e = 0;
+      if (few) {
 #pragma unroll
-      for (int i = 0; i < kTileThreads / 32; ++i) {
-        p *= s_prod[j * kTileThreads + lane + 32 * i];
-        e += s_exp[j * kTileThreads + lane + 32 * i] - my_bias;
-        const int hi = __double2hiint(p);
-        const int ee = (hi >> 20) & 0x7ff;
-        if (ee != 0x7ff) {   // (a poisoned product stays NaN)
-          p = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(p));
-          e += ee - 1023;
+        for (int i = 0; i < kTileThreads / 32; ++i) {
+          p *= s_prod[j * kTileThreads + lane + 32 * i];
+          e += s_exp[j * kTileThreads + lane + 32 * i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < kTileThreads / 32; ++i) {
+          p *= s_prod[j * kTileThreads + lane + 32 * i];
+          e += s_exp[j * kTileThreads + lane + 32 * i];
+          const int hi = __double2hiint(p);
+          const int ee = (hi >> 20) & 0x7ff;
+          if (ee != 0x7ff) {   // (a poisoned product stays NaN)
+            p = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(p));
+            e += ee - 1023;
+          }
         }
       }
       const double ef = (double)e;
@@ -962,7 +998,7 @@ __global__ void __launch_bounds__(256) leaf_pair_hist_kernel(const uint8_t* __re
   }
 }
 
-constexpr int64_t kScoreItems = 148 * 8;  // work items wanted per launch (for the particles a launch really scores)
+constexpr int64_t kScoreItems = 148 * 2;  // resident CTAs of a scoring launch (two per SM): the rounds of the chunking cost model
 
 }  // namespace
 
@@ -1012,7 +1048,7 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
   }
   static int64_t items = 0;
   if (items == 0) {
-    const char* e = getenv("VCSMC_SCORE_ITEMS");   // tuning knob: work items wanted per launch
+    const char* e = getenv("VCSMC_SCORE_ITEMS");   // tuning knob: resident CTAs assumed by the chunking
     items = e ? atoll(e) : kScoreItems;
     if (items < 1) items = kScoreItems;
   }
@@ -1025,9 +1061,10 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
   a.from_end = rows ? 1 : 0;
   a.tiles = (n_sites + kTileThreads * spt - 1) / (kTileThreads * spt);
   a.items = (int)items;
+  a.fixed2 = 0;
   // groups as large as the machine fill allows (site data is amortised over the group); K bounds the particles of a launch
   {
-    int64_t R = (K * a.tiles) / items;
+    int64_t R = (K * a.tiles) / (4 * items);
     a.R = (int)(R < 1 ? 1 : R > kRScore ? kRScore : R);
   }
   RowArgs b;
@@ -1038,6 +1075,8 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
     b.Sp = leaf_sort_stride(n_sites);
     b.tiles = b.Sp / kRowTile;
     b.items = (int)items;
+    b.fixed2 = 3;
+    if (const char* e = getenv("VCSMC_ROWS_FIXED2")) b.fixed2 = atoi(e);   // tuning knob
     b.R = kRScore;
   }
   a.n_parts = kScoreParts;
@@ -1046,7 +1085,7 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
   const int64_t cap = 148 * 2 * 8;
   {
     int tpi, nc;
-    chunking(K, a.R, a.tiles, a.items, a.n_parts, &tpi, &nc);
+    chunking(K, a.R, a.tiles, a.items, a.fixed2, a.n_parts, &tpi, &nc);
     const int64_t total = ((K + a.R - 1) / a.R) * (order ? (int64_t)kScoreParts : (int64_t)nc);   // upper bound of the work items
     const unsigned grid = (unsigned)(total < cap ? total : cap);
     cudaStream_t sg = (rows && st_generic) ? st_generic : st;

@@ -855,7 +855,7 @@ int64_t plan(vcsmc_sweep* h) {
     h->o_gocc = L.take<int32_t>(K);
     h->o_ev_timing = L.take<unsigned long long>(16 * (int64_t)N);
     h->o_leaf_perm = L.take<int32_t>((int64_t)N * leaf_sort_stride(h->S));
-    h->o_leaf_tstate = L.take<uint8_t>((int64_t)N * (leaf_sort_stride(h->S) / 256) + 16);
+    h->o_leaf_tstate = L.take<uint8_t>((int64_t)N * (leaf_sort_stride(h->S) / 128) + 16);
     h->o_leaf_hist = L.take<int32_t>(leaf_pair_hist_ints(N));
     for (int i = 0; i < 2; ++i) {   // forest scalars that travel with a particle (lazy.cu)
       h->o_F[i] = L.take<double>(K);
