@@ -94,8 +94,8 @@ struct ScoreArgs {
 
 constexpr int kScoreSmemBytes = kRScore * kCoef * 8 + kRScore * kTileThreads * (8 + 4);
 
-// site products of one child pair for the SPT sites of a thread: general Q -> the 16 products L_a[i] L_b[m];
-// JC -> (sa sb, sa (pi.L_b), (pi.L_a) sb, sum_i pi_i L_a[i] L_b[i]).  Sites past the end get zeros.
+constexpr int kRenorm = 4;   // tiles between two looks at the running products of a run (power of two)
+
 struct ChildSpace {
   const uint8_t* codes;
   int64_t codes_stride;
@@ -105,191 +105,135 @@ struct ChildSpace {
   int skip_leaf_pairs;
 };
 
+// The power of two that brings the largest of a site's four partials into [1, 2); its exponent is added to *e_sum.
+// Non-negative doubles order like their high words; zero / subnormal / non-finite / negative partials get scale 1 and
+// then poison the particle's product, which is redone with one log per site.
+__device__ __forceinline__ double site_scale(const d4& L, int* e_sum) {
+  const unsigned eu = max(max((unsigned)__double2hiint(L.v[0]), (unsigned)__double2hiint(L.v[1])),
+                          max((unsigned)__double2hiint(L.v[2]), (unsigned)__double2hiint(L.v[3]))) >> 20;
+  const int em = eu - 1u < 0x7feu ? (int)eu : 1023;
+  *e_sum += em - 1023;
+  return __hiloint2double((2046 - em) << 20, 0);
+}
+
+// Site products of one child pair for the SPT sites of a thread, both children scaled per site (site_scale) so that the
+// site likelihoods of all particles are O(M_k) and the running products need no split per step: general Q -> the 16
+// products L_a[i] L_b[m]; JC -> (sa sb, sa (pi.L_b), (pi.L_a) sb, sum_i pi_i L_a[i] L_b[i]).  Sites past the end get
+// zeros and x0 = 1 (their "likelihood").  The exponents taken out are common to every particle of the run.
 template <bool JC, int SPT, int NC>
 __device__ __forceinline__ void site_products(const ChildSpace& a, int ca, int cb, int sbase, const double (&pi)[4],
-                                              double (&C)[SPT][NC]) {
+                                              double (&C)[SPT][NC], double (&x0)[SPT], int* e_sum) {
   const ChildRef ra = child_ref(ca, a.codes, a.codes_stride, a.pool, a.slot_sites);
   const ChildRef rb = child_ref(cb, a.codes, a.codes_stride, a.pool, a.slot_sites);
+  d4 La[SPT], Lb[SPT];
+#pragma unroll
+  for (int q = 0; q < SPT; ++q) {   // (no branch on the site: the loads are in flight together)
+    const int s = min(sbase + q * kTileThreads, a.n_sites - 1);
+    La[q] = load_child(ra, s);
+    Lb[q] = load_child(rb, s);
+  }
 #pragma unroll
   for (int q = 0; q < SPT; ++q) {
-    const int s = sbase + q * kTileThreads;
-    if (s < a.n_sites) {
-      const d4 La = load_child(ra, s), Lb = load_child(rb, s);
-      if (JC) {
-        const double sa = (La.v[0] + La.v[1]) + (La.v[2] + La.v[3]);
-        const double sb = (Lb.v[0] + Lb.v[1]) + (Lb.v[2] + Lb.v[3]);
-        double qa = pi[0] * La.v[0], qb = pi[0] * Lb.v[0], qab = pi[0] * La.v[0] * Lb.v[0];
+    const bool valid = sbase + q * kTileThreads < a.n_sites;
+    int e = 0;
+    const double sa_ = site_scale(La[q], &e), sb_ = site_scale(Lb[q], &e);
+    *e_sum += valid ? e : 0;
+    x0[q] = valid ? 0.0 : 1.0;
+    const double za = valid ? sa_ : 0.0;
 #pragma unroll
-        for (int i = 1; i < 4; ++i) {
-          qa = fma(pi[i], La.v[i], qa);
-          qb = fma(pi[i], Lb.v[i], qb);
-          qab = fma(pi[i] * La.v[i], Lb.v[i], qab);
-        }
-        C[q][0] = sa * sb;
-        C[q][1] = sa * qb;
-        C[q][2] = qa * sb;
-        C[q][3] = qab;
-      } else {
+    for (int i = 0; i < 4; ++i) {
+      La[q].v[i] *= za;
+      Lb[q].v[i] *= sb_;
+    }
+    if (JC) {
+      const double sa = (La[q].v[0] + La[q].v[1]) + (La[q].v[2] + La[q].v[3]);
+      const double sb = (Lb[q].v[0] + Lb[q].v[1]) + (Lb[q].v[2] + Lb[q].v[3]);
+      double qa = pi[0] * La[q].v[0], qb = pi[0] * Lb[q].v[0], qab = pi[0] * La[q].v[0] * Lb[q].v[0];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int m = 0; m < 4; ++m) C[q][(i * 4 + m) % NC] = La.v[i] * Lb.v[m];
+      for (int i = 1; i < 4; ++i) {
+        qa = fma(pi[i], La[q].v[i], qa);
+        qb = fma(pi[i], Lb[q].v[i], qb);
+        qab = fma(pi[i] * La[q].v[i], Lb[q].v[i], qab);
       }
+      C[q][0] = sa * sb;
+      C[q][1] = sa * qb;
+      C[q][2] = qa * sb;
+      C[q][3] = qab;
     } else {
 #pragma unroll
-      for (int c = 0; c < NC; ++c) C[q][c] = 0.0;
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) C[q][(i * 4 + m) % NC] = La[q].v[i] * Lb[q].v[m];
     }
   }
 }
 
-// fold the SPT site likelihoods x[] of one particle into its running (mantissa product, biased exponent sum)
 template <int SPT>
-__device__ __forceinline__ void fold_sites(const double (&x)[SPT], bool renorm, double* prod, int* expo) {
-  double pr = *prod;
-  int ex = *expo;
-  bool odd = false;
+__device__ __forceinline__ double site_product(const double (&x)[SPT]) {
+  if (SPT == 4) return (x[0] * x[1]) * (x[2] * x[3]);
+  double v = x[0];
 #pragma unroll
-  for (int q = 0; q < SPT; ++q) {
-    const int hi = __double2hiint(x[q]);
-    const unsigned e = (unsigned)hi >> 20;  // biased exponent (sign bit included: negative values are "odd")
-    odd |= (e - 1u) >= 0x7feu;
-    ex += (int)e;
-    pr *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x[q]));
-  }
-  if (odd) pr = __longlong_as_double(0x7ff8000000000000ll);
-  if (renorm) {  // keep the mantissa product far from 2^1024 (NaN stays NaN)
-    const int hi = __double2hiint(pr);
-    ex += (int)(((unsigned)hi >> 20) & 0x7ffu) - 1023;
-    if ((((unsigned)hi >> 20) & 0x7ffu) != 0x7ffu) pr = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(pr));
-  }
-  *prod = pr;
-  *expo = ex;
+  for (int q = 1; q < SPT; ++q) v *= x[q];
+  return v;
 }
 
 // NP particles (that share the current child pair) against the SPT sites of this thread: NP*SPT*2 independent FMA
 // chains (each site likelihood is accumulated in an even and an odd half) -- the FP64 pipe has a long dependent-issue
-// latency and only 4 warps per scheduler fit, so the instruction-level parallelism has to come from here.
+// latency and only 4 warps per scheduler fit, so the instruction-level parallelism has to come from here.  The product of
+// a particle's site likelihoods is multiplied into its running product (shared memory; loads first, stores last).
 template <bool JC, int SPT, int NP>
-__device__ __forceinline__ void score_particles(int j, const double (&C)[SPT][JC ? 4 : 16], const double (&x0)[SPT], bool renorm,
-                                                const double* sC, double* my_prod, int* my_exp) {
+__device__ __forceinline__ void score_particles(const double* coef, double* pp, const double (&C)[SPT][JC ? 4 : 16],
+                                                const double (&x0)[SPT]) {
   constexpr int NC = JC ? 4 : 16;
-  double xe[NP][SPT], xo[NP][SPT];
+  double xe[NP][SPT], xo[NP][SPT], p[NP];
 #pragma unroll
-  for (int p = 0; p < NP; ++p)
+  for (int n = 0; n < NP; ++n) {
+    p[n] = pp[n * kTileThreads];
 #pragma unroll
     for (int q = 0; q < SPT; ++q) {
-      xe[p][q] = x0[q];
-      xo[p][q] = 0.0;
+      xe[n][q] = x0[q];
+      xo[n][q] = 0.0;
     }
+  }
 #pragma unroll
   for (int c = 0; c < NC; c += 2) {
     double2 m[NP];
 #pragma unroll
-    for (int p = 0; p < NP; ++p) m[p] = *reinterpret_cast<const double2*>(sC + (j + p) * kCoef + c);
+    for (int n = 0; n < NP; ++n) m[n] = *reinterpret_cast<const double2*>(coef + n * kCoef + c);
 #pragma unroll
-    for (int p = 0; p < NP; ++p)
+    for (int n = 0; n < NP; ++n)
 #pragma unroll
       for (int q = 0; q < SPT; ++q) {
-        xe[p][q] = fma(m[p].x, C[q][c], xe[p][q]);
-        xo[p][q] = fma(m[p].y, C[q][c + 1], xo[p][q]);
+        xe[n][q] = fma(m[n].x, C[q][c], xe[n][q]);
+        xo[n][q] = fma(m[n].y, C[q][c + 1], xo[n][q]);
       }
   }
 #pragma unroll
-  for (int p = 0; p < NP; ++p) {
+  for (int n = 0; n < NP; ++n) {
     double x[SPT];
 #pragma unroll
-    for (int q = 0; q < SPT; ++q) x[q] = xe[p][q] + xo[p][q];
-    fold_sites<SPT>(x, renorm, my_prod + (j + p) * kTileThreads, my_exp + (j + p) * kTileThreads);
+    for (int q = 0; q < SPT; ++q) x[q] = xe[n][q] + xo[n][q];
+    pp[n * kTileThreads] = p[n] * site_product<SPT>(x);
   }
 }
 
 // The same when child a is a LEAF with a one-hot (or all-ones) state mask at every site of this thread: the site
 // likelihood is row `state` of M (or the column sums of M) dotted with L_b -- 4 DFMA per site instead of 16.  The row is
-// fetched from shared memory per lane (offset roff = 4 * state, or 16 for a gap).
-template <int SPT, int NP>
-__device__ __forceinline__ void score_particles_leaf(int j, const double (&Lb)[SPT][16], const int (&roff)[SPT],
-                                                     const double (&x0)[SPT], bool renorm, const double* sC, double* my_prod,
-                                                     int* my_exp) {
-#pragma unroll
-  for (int p = 0; p < NP; ++p) {
-    double x[SPT];
-#pragma unroll
-    for (int q = 0; q < SPT; ++q) {
-      const double2* row = reinterpret_cast<const double2*>(sC + (j + p) * kCoef + roff[q]);
-      const double2 r0 = row[0], r1 = row[1];
-      const double xe = fma(r0.y, Lb[q][1], fma(r0.x, Lb[q][0], x0[q]));
-      const double xo = fma(r1.y, Lb[q][3], r1.x * Lb[q][2]);
-      x[q] = xe + xo;
-    }
-    fold_sites<SPT>(x, renorm, my_prod + (j + p) * kTileThreads, my_exp + (j + p) * kTileThreads);
-  }
-}
-
-// One tile of SPT*256 sites for the nj particles of a group.  The running product of the site likelihoods of
-// (thread, particle) is kept as (mantissa product, BIASED exponent sum) in shared memory.  The split is three integer
-// ops per site; a likelihood that is not a positive normal number (0, subnormal, inf, NaN, negative) poisons the
-// mantissa product with NaN and the particle is re-evaluated with one log per site afterwards (never on sane inputs).
-// Sites past the end of the alignment have zero site products and x0 = 1, i.e. x = 1.
-template <bool JC, int SPT>
-__device__ __forceinline__ void score_tile(const ChildSpace& a, int nj, unsigned skip, int sbase, bool renorm, const double (&pi)[4],
-                                           const int* s_a, const int* s_b, const double* sC, double* my_prod, int* my_exp) {
-  constexpr int NC = JC ? 4 : 16;
-  int pa = kNone, pb = kNone;
-  double C[SPT][NC];
-  double x0[SPT];
-  int roff[SPT];
-  bool leaf_rows = false;  // current pair = (leaf with one-hot / gap masks, internal node): use the 4-DFMA path
+// fetched from shared memory per lane (offset roff = 4 * state, or 16 for a gap).  (The grouped order sends these
+// particles to the rows kernel; this path serves the identity order of small runs.)
+template <int SPT>
+__device__ __forceinline__ void score_particle_leaf(const double* coef, double* pp, const double (&Lb)[SPT][16],
+                                                    const int (&roff)[SPT], const double (&x0)[SPT]) {
+  double x[SPT];
 #pragma unroll
   for (int q = 0; q < SPT; ++q) {
-    x0[q] = (sbase + q * kTileThreads < a.n_sites) ? 0.0 : 1.0;
-    roff[q] = 0;
+    const double2* row = reinterpret_cast<const double2*>(coef + roff[q]);
+    const double2 r0 = row[0], r1 = row[1];
+    const double xe = fma(r0.y, Lb[q][1], fma(r0.x, Lb[q][0], x0[q]));
+    const double xo = fma(r1.y, Lb[q][3], r1.x * Lb[q][2]);
+    x[q] = xe + xo;
   }
-  int j = 0;
-  while (j < nj) {
-    const int ca = s_a[j], cb = s_b[j];
-    if (skip >> j & 1u) {  // a leaf pair (scored from site patterns)
-      ++j;
-      continue;
-    }
-    if (ca != pa || cb != pb) {
-      leaf_rows = false;
-      if (!JC && ca < 0 && cb >= 0) {
-        // leaf + internal node: try the row path (every site of this warp must have a one-hot or all-ones mask)
-        const uint8_t* crow = a.codes + (int64_t)(-ca - 1) * a.codes_stride;
-        const double* node = a.pool + (int64_t)cb * a.slot_sites * 4;
-        bool ok = true;
-#pragma unroll
-        for (int q = 0; q < SPT; ++q) {
-          const int s = sbase + q * kTileThreads;
-          if (s < a.n_sites) {
-            const int code = __ldg(crow + s) & 15;
-            const d4 L = ld_site(node + (int64_t)s * 4);
-#pragma unroll
-            for (int m = 0; m < 4; ++m) C[q][m % NC] = L.v[m];
-            roff[q] = code == 15 ? 16 : 4 * (__ffs(code) - 1);
-            ok = ok && (code == 15 || (code & (code - 1)) == 0);
-          } else {
-#pragma unroll
-            for (int m = 0; m < 4; ++m) C[q][m % NC] = 0.0;
-            roff[q] = 0;
-          }
-        }
-        leaf_rows = __all_sync(0xffffffffu, ok);
-      }
-      if (!leaf_rows) site_products<JC, SPT, NC>(a, ca, cb, sbase, pi, C);
-      pa = ca;
-      pb = cb;
-    }
-    const bool two = j + 1 < nj && !(skip >> (j + 1) & 1u) && s_a[j + 1] == ca && s_b[j + 1] == cb;
-    if (!JC && leaf_rows) {
-      if (two) score_particles_leaf<SPT, 2>(j, reinterpret_cast<const double(&)[SPT][16]>(C), roff, x0, renorm, sC, my_prod, my_exp);
-      else score_particles_leaf<SPT, 1>(j, reinterpret_cast<const double(&)[SPT][16]>(C), roff, x0, renorm, sC, my_prod, my_exp);
-    } else {
-      if (two) score_particles<JC, SPT, 2>(j, C, x0, renorm, sC, my_prod, my_exp);
-      else score_particles<JC, SPT, 1>(j, C, x0, renorm, sC, my_prod, my_exp);
-    }
-    j += two ? 2 : 1;
-  }
+  pp[0] *= site_product<SPT>(x);
 }
 
 // exact fallback for a particle whose product was poisoned: one log per site
@@ -297,35 +241,60 @@ template <bool JC>
 __device__ __noinline__ double score_slow(ChildSpace a, int ca, int cb, const double* cj, int s_begin, int s_end, double pi0,
                                           double pi1, double pi2, double pi3) {
   constexpr int NC = JC ? 4 : 16;
+  const ChildRef ra = child_ref(ca, a.codes, a.codes_stride, a.pool, a.slot_sites);
+  const ChildRef rb = child_ref(cb, a.codes, a.codes_stride, a.pool, a.slot_sites);
   const double pi[4] = {pi0, pi1, pi2, pi3};
   double acc = 0.0;
-  double C[1][NC], m[NC];
+  double m[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) m[c] = cj[c];
   for (int s = s_begin + threadIdx.x; s < s_end; s += kTileThreads) {
-    site_products<JC, 1, NC>(a, ca, cb, s, pi, C);
-    double x = m[0] * C[0][0];
+    const d4 La = load_child(ra, s), Lb = load_child(rb, s);
+    double x = 0.0;
+    if (JC) {
+      const double sa = (La.v[0] + La.v[1]) + (La.v[2] + La.v[3]);
+      const double sb = (Lb.v[0] + Lb.v[1]) + (Lb.v[2] + Lb.v[3]);
+      double qa = pi[0] * La.v[0], qb = pi[0] * Lb.v[0], qab = pi[0] * La.v[0] * Lb.v[0];
 #pragma unroll
-    for (int c = 1; c < NC; ++c) x = fma(m[c], C[0][c], x);
+      for (int i = 1; i < 4; ++i) {
+        qa = fma(pi[i], La.v[i], qa);
+        qb = fma(pi[i], Lb.v[i], qb);
+        qab = fma(pi[i] * La.v[i], Lb.v[i], qab);
+      }
+      x = fma(m[3], qab, fma(m[2], qa * sb, fma(m[1], sa * qb, m[0] * (sa * sb))));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int mm = 0; mm < 4; ++mm) x = fma(m[(i * 4 + mm) % NC], La.v[i] * Lb.v[mm], x);
+    }
     acc += log(x);
   }
   return acc;
 }
 
+// One work item: a group of <= R particles (runs of particles that share their child pair) x a chunk of tiles.  The
+// running product of the site likelihoods of (thread, particle) lives in shared memory and is only MULTIPLIED per step
+// (the children are scaled per site, see site_products); at the end of a run's tiles -- and every kRenorm tiles in
+// between if some product has left [2^-480, 2^480) -- the products go back to [1, 2) and their exponents, with the ones
+// taken out of the sites, to integer sums.  A product found outside [2^-959, 2^1024), negative or NaN poisons the
+// particle, which is re-evaluated with one log per site afterwards (never on sane inputs).
 template <bool JC, int SPT>
 __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_score_kernel(const ScoreArgs a) {
   constexpr int NC = JC ? 4 : 16;  // coefficients per particle == site products per site
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sC = reinterpret_cast<double*>(smem_raw);                    // [R][16] per-particle coefficients
-  double* s_prod = sC + kRScore * kCoef;                                 // [R][256] running mantissa products
-  int* s_exp = reinterpret_cast<int*>(s_prod + kRScore * kTileThreads); // [R][256] running (biased) exponent sums
+  double* sC = reinterpret_cast<double*>(smem_raw);                    // [R][20] per-particle coefficients (general: M and its column sums)
+  double* s_prod = sC + kRScore * kCoef;                                 // [R][256] running products
+  int* s_exp = reinterpret_cast<int*>(s_prod + kRScore * kTileThreads); // [R][256] running exponent sums
   __shared__ int s_k[kRScore], s_a[kRScore], s_b[kRScore];
+  __shared__ int s_run[kRScore + 1];   // first particle of every run of one child pair; s_run[n_runs] = nj
+  __shared__ int s_nruns, s_work;
   __shared__ double s_slow[kWarps];
-  __shared__ unsigned s_odd, s_skip;   // s_skip: particles of the group some other kernel scores (leaf pairs)
+  __shared__ unsigned s_odd;
+  __shared__ int s_chunking[2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int R = a.R;
   const int64_t count = a.count ? (int64_t)*a.count : a.K;
-  __shared__ int s_chunking[2];
   if (tid == 0) chunking(count, R, a.tiles, a.items, a.fixed2, a.n_parts, &s_chunking[0], &s_chunking[1]);   // (divisions: one thread)
   __syncthreads();
   const int tiles_per_item = s_chunking[0], n_chunks = s_chunking[1];
@@ -355,14 +324,17 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
     }
     __syncthreads();
     if (tid == 0) {
-      unsigned skip = 0u;
-      for (int j = 0; j < nj; ++j)
-        if (a.skip_leaf_pairs && s_b[j] < 0) skip |= 1u << j;
-      s_skip = skip;
+      int nr = 0, work = 0;
+      for (int j = 0; j < nj; ++j) {
+        if (j == 0 || s_a[j] != s_a[j - 1] || s_b[j] != s_b[j - 1]) s_run[nr++] = j;
+        work |= !(a.skip_leaf_pairs && s_b[j] < 0);   // a leaf pair is scored from its site patterns elsewhere
+      }
+      s_run[nr] = nj;
+      s_nruns = nr;
+      s_work = work;
     }
     __syncthreads();
-    const unsigned skip = s_skip;
-    if ((skip | (nj < 32 ? ~0u << nj : 0u)) == ~0u) continue;   // nothing of this group is ours
+    if (!s_work) continue;   // nothing of this group is ours
     if (JC) {
       if (tid < nj) {
         const int kk = s_k[tid];
@@ -396,38 +368,98 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
       }
     }
     for (int j = 0; j < nj; ++j) {
-      if (skip >> j & 1u) continue;
       my_prod[j * kTileThreads] = 1.0;
       my_exp[j * kTileThreads] = 0;
     }
     __syncthreads();
-
+    const int n_runs = s_nruns;
     const int t_begin = tc * tiles_per_item;
     const int t_end = min(a.tiles, t_begin + tiles_per_item);
-    for (int t = t_begin; t < t_end; ++t) {
-      const int sbase = t * (kTileThreads * SPT) + tid;
-      const bool renorm = ((t - t_begin) & 127) == 127;
-      score_tile<JC, SPT>(cs, nj, skip, sbase, renorm, pi, s_a, s_b, sC, my_prod, my_exp);
+
+    for (int run = 0; run < n_runs; ++run) {
+      const int jb = s_run[run], len = s_run[run + 1] - jb;
+      const int ca = s_a[jb], cb = s_b[jb];
+      if (a.skip_leaf_pairs && cb < 0) continue;
+      double* const pp0 = my_prod + jb * kTileThreads;
+      int* const pe0 = my_exp + jb * kTileThreads;
+      const double* const Mj = sC + jb * kCoef;
+      int erun = 0;   // exponents taken out of this thread's sites: common to every particle of the run
+      for (int t = t_begin; t < t_end; ++t) {
+        const int sbase = t * (kTileThreads * SPT) + tid;
+        double C[SPT][NC], x0[SPT];
+        bool leaf_rows = false;   // (leaf with one-hot / gap masks, internal node): the 4-DFMA path
+        int roff[SPT];
+        if (!JC && ca < 0 && cb >= 0) {
+          // every site of this warp must have a one-hot or all-ones mask
+          const uint8_t* crow = a.codes + (int64_t)(-ca - 1) * a.codes_stride;
+          bool ok = true;
+#pragma unroll
+          for (int q = 0; q < SPT; ++q) {
+            const int s = sbase + q * kTileThreads;
+            const int code = s < a.n_sites ? __ldg(crow + s) & 15 : 15;
+            roff[q] = code == 15 ? 16 : 4 * (__ffs(code) - 1);
+            ok = ok && (code == 15 || (code & (code - 1)) == 0);
+          }
+          leaf_rows = __all_sync(0xffffffffu, ok);
+        }
+        if (leaf_rows) {
+          const double* node = a.pool + (int64_t)cb * a.slot_sites * 4;
+          d4 L[SPT];
+#pragma unroll
+          for (int q = 0; q < SPT; ++q) L[q] = ld_site(node + (int64_t)min(sbase + q * kTileThreads, a.n_sites - 1) * 4);
+#pragma unroll
+          for (int q = 0; q < SPT; ++q) {
+            const bool valid = sbase + q * kTileThreads < a.n_sites;
+            int e = 0;
+            const double sc = site_scale(L[q], &e);
+            erun += valid ? e : 0;
+            x0[q] = valid ? 0.0 : 1.0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) C[q][m % NC] = valid ? L[q].v[m] * sc : 0.0;
+          }
+          for (int i = 0; i < len; ++i)
+            score_particle_leaf<SPT>(Mj + i * kCoef, pp0 + i * kTileThreads, reinterpret_cast<const double(&)[SPT][16]>(C), roff, x0);
+        } else {
+          site_products<JC, SPT, NC>(cs, ca, cb, sbase, pi, C, x0, &erun);
+          int i = 0;
+          for (; i + 1 < len; i += 2) score_particles<JC, SPT, 2>(Mj + i * kCoef, pp0 + i * kTileThreads, C, x0);
+          if (i < len) score_particles<JC, SPT, 1>(Mj + i * kCoef, pp0 + i * kTileThreads, C, x0);
+        }
+        bool renorm = t == t_end - 1;
+        if (!renorm && ((t - t_begin) & (kRenorm - 1)) == kRenorm - 1) {
+          int hmin = 0x7fffffff, hmax = 0;
+          for (int i = 0; i < len; ++i) {
+            const int h = reinterpret_cast<const int*>(pp0 + i * kTileThreads)[1];
+            hmin = min(hmin, h);
+            hmax = max(hmax, h);
+          }
+          renorm = hmin < ((1023 - 480) << 20) || hmax >= ((1023 + 480) << 20);
+        }
+        if (renorm) {
+          for (int i = 0; i < len; ++i) {
+            const double pr = pp0[i * kTileThreads];
+            const int h2 = __double2hiint(pr);
+            const unsigned e2 = (unsigned)h2 >> 20;   // (sign included)
+            const bool sane = e2 - 64u < 0x7ffu - 64u;
+            pe0[i * kTileThreads] += sane ? (int)e2 - 1023 + erun : 0;
+            pp0[i * kTileThreads] = sane ? __hiloint2double((h2 & 0x000fffff) | 0x3ff00000, __double2loint(pr))
+                                         : __longlong_as_double(0x7ff8000000000000ll);
+          }
+          erun = 0;
+        }
+      }
     }
-    // sum_s log x_s = log(prod mantissas) + ln2 * sum (exponents - bias).  The 256 per-thread products of a particle are
-    // combined by ONE warp (8 entries per lane, renormalised after every multiply) before the log: 32 logs per particle
-    // instead of 256.
-    const int bias = 1023 * SPT * (t_end - t_begin);
+    // sum_s log x_s = log(prod of the products) + ln2 * (exponents taken out).  A warp combines the 256 per-thread
+    // products of a particle (8 entries per lane, each in [1, 2)) before the log: 32 logs per particle instead of 256.
     __syncthreads();
     for (int j = wid; j < nj; j += kWarps) {
-      if (skip >> j & 1u) continue;  // written by score_leaf_pairs_kernel / merge_score_mma_kernel
+      if (a.skip_leaf_pairs && s_b[j] < 0) continue;
       double p = 1.0;
       int e = 0;
 #pragma unroll
       for (int i = 0; i < kTileThreads / 32; ++i) {
         p *= s_prod[j * kTileThreads + lane + 32 * i];
-        e += s_exp[j * kTileThreads + lane + 32 * i] - bias;
-        const int hi = __double2hiint(p);
-        const int ee = (hi >> 20) & 0x7ff;
-        if (ee != 0x7ff) {   // (a poisoned product stays NaN)
-          p = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(p));
-          e += ee - 1023;
-        }
+        e += s_exp[j * kTileThreads + lane + 32 * i];
       }
       const double ef = (double)e;
       double acc = fma(ef, 6.93147180369123816490e-01, fma(ef, 1.90821492927058770002e-10, log(p)));  // ln2 hi + lo
@@ -481,7 +513,6 @@ __global__ void __launch_bounds__(kTileThreads, (JC || SPT <= 2) ? 2 : 1) merge_
 constexpr int kRowTile = 1024;            // sorted positions per tile: 8 warps x one unit
 constexpr int kRowSub = 128;              // positions per unit: 32 lanes x 4 consecutive positions, ONE state class
 constexpr int kLeafClasses = 6;
-constexpr int kRenorm = 4;                // tiles between two renormalisations of the running products (power of two)
 
 __device__ __forceinline__ int leaf_class(int code) {
   code &= 15;
@@ -1082,7 +1113,11 @@ int launch_merge_score(const uint8_t* codes, int64_t codes_stride, const double*
   a.n_parts = kScoreParts;
   b.n_parts = kScoreParts;
   if (n_parts) *n_parts = kScoreParts;
-  const int64_t cap = 148 * 2 * 8;
+  static int64_t cap = 0;
+  if (cap == 0) {
+    const char* e = getenv("VCSMC_SCORE_GRID");   // tuning knob: CTAs per scoring launch (each loops over the work items)
+    cap = e ? atoll(e) : 148 * 4;   // two rounds of resident CTAs: few enough that a CTA's start-up does not show, enough to even out the items
+  }
   {
     int tpi, nc;
     chunking(K, a.R, a.tiles, a.items, a.fixed2, a.n_parts, &tpi, &nc);
