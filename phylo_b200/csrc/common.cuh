@@ -168,6 +168,47 @@ __device__ __forceinline__ M4 m4_expm(const M4& A) {
   return X;
 }
 
+// expm(t Q) for a FIXED Q and many t: with the matrices Q^k / k! (k = 0..14) tabulated once (expm_tq_table), the scaled
+// Taylor polynomial is a Horner scheme in the scalar t / 2^s on 16 independent entries -- 14 x 16 FMA and no matrix
+// product -- followed by the s squarings.  Same polynomial and the same scaling rule as m4_expm (||t Q||_1 / 2^s <= 1/2).
+// table: [15][16] matrices, then ||Q||_1.
+constexpr int kExpmTableDoubles = 15 * 16 + 4;
+__host__ __device__ inline void expm_tq_table(const double* Q, double* table) {
+  double cur[16];
+  for (int i = 0; i < 16; ++i) cur[i] = table[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  for (int k = 1; k <= 14; ++k) {
+    double nxt[16];
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        double v = 0.0;
+        for (int m = 0; m < 4; ++m) v = fma(cur[i * 4 + m], Q[m * 4 + j], v);
+        nxt[i * 4 + j] = v / (double)k;
+      }
+    for (int i = 0; i < 16; ++i) cur[i] = table[k * 16 + i] = nxt[i];
+  }
+  double nrm = 0.0;
+  for (int j = 0; j < 4; ++j) {
+    double c = 0.0;
+    for (int i = 0; i < 4; ++i) c += fabs(Q[i * 4 + j]);
+    nrm = fmax(nrm, c);
+  }
+  table[15 * 16] = nrm;
+}
+__device__ __forceinline__ M4 m4_expm_tq(const double* __restrict__ table, double t) {
+  const int s = expm_scale(fabs(t) * table[15 * 16]);
+  const double ts = ldexp(t, -s);
+  M4 X;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) X.a[i] = table[14 * 16 + i];
+#pragma unroll 1
+  for (int k = 13; k >= 0; --k) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) X.a[i] = fma(X.a[i], ts, table[k * 16 + i]);
+  }
+  for (int j = 0; j < s; ++j) X = m4_mul(X, X);
+  return X;
+}
+
 // Frechet derivative L(A, E) = d/de expm(A + eE) at e=0, by the same series on the block matrix
 // [[A, E], [0, A]]: pairs (X, Y) with (X1,Y1)(X2,Y2) = (X1X2, X1Y2 + Y1X2).
 __device__ __forceinline__ void m4_expm_frechet(const M4& A, const M4& E, M4& X, M4& Y) {

@@ -52,6 +52,7 @@ struct EvArgs {
   const double* lam_l;
   const double* lam_r;
   const double* Q;
+  const double* qpow;         // Q^k / k! and ||Q||_1 (expm_tq_table), general Q only
   const double* pi;
   const double* ldf;
   const float* u_pair_prev;   // [K][N-r+1] of event r-1
@@ -501,10 +502,7 @@ __device__ __forceinline__ void survivor_row(const EvArgs& a, int64_t k, int lan
 #pragma unroll
         for (int q = 0; q < 16; ++q) X.a[q] = (q % 5 == 0) ? d : o;
       } else {
-        M4 A;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) A.a[q] = a.Q[q] * ti;
-        X = m4_expm(A);
+        X = m4_expm_tq(a.qpow, ti);
       }
       double* Pout = a.P + newest * 32 + lane * 16;
 #pragma unroll
@@ -589,6 +587,121 @@ __device__ void allocate_slots(const EvArgs& a, int64_t* warp_off) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// The part of the proposal of event r that does not depend on the resampling: which two positions of the forest row
+// merge (extend_partial_state, vcsmc.py:298-305 -- the top-2 of the particle's uniforms), the branch lengths
+// (vcsmc.py:351-358) and both transition matrices (vcsmc.py:181-184).  One thread per own particle; run by the CTAs the
+// CDF's tile stages leave idle (the FP64 work of the two matrix exponentials disappears behind the scan).  The pick
+// travels to propose_particle in pDirect[kl] (free between the weights of event r-1 and the proposal of event r).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void predraw_pick(const EvArgs& a, int64_t kl) {
+  const int r = a.r, n = a.N - r;
+  const int64_t k = a.k0 + kl;
+  int c0 = 0, c1 = 1;
+  bool straddle = false;   // the 2nd and 3rd largest uniforms tie: tf.nn.top_k keeps a merged subtree and drops another
+  if (!a.u_pair_cur) {
+    uint32_t best = 0u, second = 0u;
+    const uint64_t seed = *a.seed_dev;
+    for (int j = 0; j < n; j += 4) {
+      uint32_t p[4] = {(uint32_t)k, (uint32_t)((uint64_t)k >> 32) | ((uint32_t)r << 8), 2u, (uint32_t)(j >> 2)};
+      philox4x32_10(p, (uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (j + q < n) {
+          const uint32_t key = (((p[q] >> 8) & 0xFFFF00u) | (uint32_t)((j + q) & 0xFF)) + 1u;   // > 0, tie-free
+          if (key > best) {
+            second = best;
+            best = key;
+          } else if (key > second) {
+            second = key;
+          }
+        }
+      }
+    }
+    c0 = (int)((best - 1u) & 0xFFu);
+    c1 = (int)((second - 1u) & 0xFFu);
+  } else {
+    const float* u = a.u_pair_cur + k * n;
+    float b0 = -1.f, b1 = -1.f, b2 = -1.f;   // uniforms are >= 0
+    int i0 = 0, i1 = 0;
+    for (int i = 0; i < n; ++i) {
+      const float v = u[i];
+      if (v > b0) {
+        b2 = b1;
+        b1 = b0; i1 = i0;
+        b0 = v; i0 = i;
+      } else if (v > b1) {
+        b2 = b1;
+        b1 = v; i1 = i;
+      } else if (v > b2) {
+        b2 = v;
+      }
+    }
+    c0 = i0;
+    c1 = i1;
+    straddle = (n > 2) && (b1 == b2);
+  }
+  a.pDirect[kl] = c0 | (c1 << 8) | ((int)straddle << 16);
+}
+
+// Branch lengths (vcsmc.py:351-358) and both transition matrices (vcsmc.py:181-184) of one own particle.  `qpow` is
+// the CTA's shared-memory copy of the table of m4_expm_tq (a thread per particle reading it from global memory spent
+// its time in the load/store unit: 448 loads each).
+__device__ __forceinline__ void predraw_transitions(const EvArgs& a, int64_t kl, const double* qpow) {
+  const int r = a.r;
+  const int64_t K = a.K;
+  const int64_t k = a.k0 + kl;
+  const int64_t e = (int64_t)r * K + k;
+  double ubl, ubr;
+  if (a.u_bl) {
+    ubl = a.u_bl[k];
+    ubr = a.u_br[k];
+  } else {
+    uint32_t c[4] = {(uint32_t)k, (uint32_t)((uint64_t)k >> 32) | ((uint32_t)r << 8), 0u, 0u};
+    const uint64_t seed = *a.seed_dev;
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double tiny = 2.2250738585072014e-308;
+    ubl = fmax(u64_to_unit_f64(c[0], c[1]), tiny);   // tfp Exponential: U in [tiny, 1)
+    ubr = fmax(u64_to_unit_f64(c[2], c[3]), tiny);
+  }
+  const double bl = -log(ubl) / a.lam_l[r];
+  const double br = -log(ubr) / a.lam_r[r];
+  a.b_l[e] = bl;
+  a.b_r[e] = br;
+  a.t2[2 * e] = bl;
+  a.t2[2 * e + 1] = br;
+  double* Pout = a.P + e * 32;   // (256-byte aligned: whole 32-byte sectors per store)
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) {
+    const double ti = side ? br : bl;
+    M4 X;
+    if (a.jc) {
+      const double o = -0.25 * expm1(-ti);
+      const double d = 0.25 + 0.75 * exp(-ti);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) X.a[q] = (q % 5 == 0) ? d : o;
+    } else {
+      X = m4_expm_tq(qpow, ti);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      d4 row;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) row.v[c] = X.a[q * 4 + c];
+      st_site(Pout + side * 16 + q * 4, row);
+    }
+  }
+}
+
+// own particles [Kl * part / parts, Kl * (part + 1) / parts) of this CTA
+__device__ __forceinline__ void predraw_share(const EvArgs& a, int part, int parts, int what, const double* qpow) {
+  const int64_t lo = a.Kl * part / parts, hi = a.Kl * (part + 1) / parts;
+  for (int64_t kl = lo + threadIdx.x; kl < hi; kl += kEvThreads) {
+    if (what & 1) predraw_pick(a, kl);
+    if (what & 2) predraw_transitions(a, kl, qpow);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // phase 7b: proposal of event r for one own particle (one thread)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void propose_particle(const EvArgs& a, int64_t kl, bool on, int lane) {
@@ -602,50 +715,9 @@ __device__ __forceinline__ void propose_particle(const EvArgs& a, int64_t kl, bo
     const int pa = (r & 1) ^ 1;
     const int32_t* row_ids = a.row_ids[pa] + anc * N;
     const int32_t* row_cnt = a.row_cnt[pa] + anc * N;
-    int c0 = 0, c1 = 1;
-    bool straddle = false;   // the 2nd and 3rd largest uniforms tie: tf.nn.top_k keeps a merged subtree and drops another
-    if (!a.u_pair_cur) {
-      uint32_t best = 0u, second = 0u;
-      const uint64_t seed = *a.seed_dev;
-      for (int j = 0; j < n; j += 4) {
-        uint32_t p[4] = {(uint32_t)k, (uint32_t)((uint64_t)k >> 32) | ((uint32_t)r << 8), 2u, (uint32_t)(j >> 2)};
-        philox4x32_10(p, (uint32_t)seed, (uint32_t)(seed >> 32));
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (j + q < n) {
-            const uint32_t key = (((p[q] >> 8) & 0xFFFF00u) | (uint32_t)((j + q) & 0xFF)) + 1u;   // > 0, tie-free
-            if (key > best) {
-              second = best;
-              best = key;
-            } else if (key > second) {
-              second = key;
-            }
-          }
-        }
-      }
-      c0 = (int)((best - 1u) & 0xFFu);
-      c1 = (int)((second - 1u) & 0xFFu);
-    } else {
-      const float* u = a.u_pair_cur + k * n;
-      float b0 = -1.f, b1 = -1.f, b2 = -1.f;   // uniforms are >= 0
-      int i0 = 0, i1 = 0;
-      for (int i = 0; i < n; ++i) {
-        const float v = u[i];
-        if (v > b0) {
-          b2 = b1;
-          b1 = b0; i1 = i0;
-          b0 = v; i0 = i;
-        } else if (v > b1) {
-          b2 = b1;
-          b1 = v; i1 = i;
-        } else if (v > b2) {
-          b2 = v;
-        }
-      }
-      c0 = i0;
-      c1 = i1;
-      straddle = (n > 2) && (b1 == b2);
-    }
+    const int pick = a.pDirect[kl];   // predraw_particle: the two positions that merge; whether the 2nd and 3rd largest uniforms tie
+    const int c0 = pick & 0xFF, c1 = (pick >> 8) & 0xFF;
+    const bool straddle = (pick >> 16) & 1;
     const int lid = first ? c0 : row_ids[c0];
     const int rid = first ? c1 : row_ids[c1];
     const int cl = first ? 1 : row_cnt[c0];
@@ -655,24 +727,6 @@ __device__ __forceinline__ void propose_particle(const EvArgs& a, int64_t kl, bo
     a.nleaf[e] = nl;
     a.lref[e] = lid;
     a.rref[e] = rid;
-    double ubl, ubr;
-    if (a.u_bl) {
-      ubl = a.u_bl[k];
-      ubr = a.u_br[k];
-    } else {
-      uint32_t c[4] = {(uint32_t)k, (uint32_t)((uint64_t)k >> 32) | ((uint32_t)r << 8), 0u, 0u};
-      const uint64_t seed = *a.seed_dev;
-      philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-      const double tiny = 2.2250738585072014e-308;
-      ubl = fmax(u64_to_unit_f64(c[0], c[1]), tiny);   // tfp Exponential: U in [tiny, 1)
-      ubr = fmax(u64_to_unit_f64(c[2], c[3]), tiny);
-    }
-    const double bl = -log(ubl) / a.lam_l[r];
-    const double br = -log(ubr) / a.lam_r[r];
-    a.b_l[e] = bl;
-    a.b_r[e] = br;
-    a.t2[2 * e] = bl;
-    a.t2[2 * e + 1] = br;
     a.pLLt[kl] = first ? log(1.0 / (double)K) : a.LL[(int64_t)(r - 1) * K + anc];
     if (!straddle) {
       const double F_anc = first ? *a.F0 : a.row_F[pa][anc];
@@ -706,30 +760,6 @@ __device__ __forceinline__ void propose_particle(const EvArgs& a, int64_t kl, bo
     rs = rid < N ? -(rid + 1) : a.loc[rid - N];
     a.lsrc[r & 1][kl] = ls;
     a.rsrc[r & 1][kl] = rs;
-    // transition matrices (vcsmc.py:181-184)
-    double* Pout = a.P + e * 32;   // (256-byte aligned: whole 32-byte sectors per store)
-    for (int side = 0; side < 2; ++side) {
-      const double ti = side ? br : bl;
-      M4 X;
-      if (a.jc) {
-        const double o = -0.25 * expm1(-ti);
-        const double d = 0.25 + 0.75 * exp(-ti);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) X.a[q] = (q % 5 == 0) ? d : o;
-      } else {
-        M4 A;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) A.a[q] = a.Q[q] * ti;
-        X = m4_expm(A);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        d4 row;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) row.v[c] = X.a[q * 4 + c];
-        st_site(Pout + side * 16 + q * 4, row);
-      }
-    }
   }
   // ---- two leaves: the site likelihood depends on the site only through the two state masks, so
   //   sum_s log x[s] = sum over patterns of count(c_a, c_b) log x(c_a, c_b),  x = sum_{j in c_a, m in c_b} M[j][m],
@@ -828,6 +858,10 @@ __global__ void __launch_bounds__(kEvThreads, 2) lz_event_kernel(const EvArgs a)
   const int64_t gthreads = (int64_t)gridDim.x * kEvThreads, gtid = (int64_t)blockIdx.x * kEvThreads + tid;
   const int64_t gwarps = (int64_t)gridDim.x * kEvWarps, gwid = (int64_t)blockIdx.x * kEvWarps + wid;
   float* su = su_all + wid * a.row_stride;
+  __shared__ __align__(16) double s_qpow[kExpmTableDoubles];   // the table of m4_expm_tq (general Q)
+  if (!a.jc)
+    for (int i = tid; i < kExpmTableDoubles; i += kEvThreads) s_qpow[i] = a.qpow[i];
+  __syncthreads();
 
   if (r > 0) {
     const int64_t e_row = (int64_t)(r - 1) * K;
@@ -893,17 +927,25 @@ __global__ void __launch_bounds__(kEvThreads, 2) lz_event_kernel(const EvArgs a)
       a.gcount[1] = 0;
     }
     for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_weights(vb, lw, K, M, a.cdf, pw, pq, a.live, sm);
-    if (a.world > 1) {
-      // the rest of the other ranks' records: needed from phase 5 on, fetched by the CTAs that have no CDF tile
+    {
+      // the CTAs that have no CDF tile: the rest of the other ranks' records (needed from phase 5 on), and the part of
+      // event r's proposal that does not depend on the resampling
       const int first = nb < (int)gridDim.x ? nb : 0, n_cta = (int)gridDim.x - first;
-      if ((int)blockIdx.x >= first)
-        for (int64_t k = (int64_t)(blockIdx.x - first) * kEvThreads + tid; k < K; k += (int64_t)n_cta * kEvThreads)
-          if (!(k >= k0 && k < k0 + Kl)) particle_unpack_rest(a, k);
+      if ((int)blockIdx.x >= first) {
+        if (a.world > 1)
+          for (int64_t k = (int64_t)(blockIdx.x - first) * kEvThreads + tid; k < K; k += (int64_t)n_cta * kEvThreads)
+            if (!(k >= k0 && k < k0 + Kl)) particle_unpack_rest(a, k);
+        if (r < N - 1) predraw_share(a, (int)blockIdx.x - first, n_cta, 1, s_qpow);
+      }
     }
     grid.sync();
     stamp(a, 3);
     stamp(a, 4);
     for (int vb = blockIdx.x; vb < nb; vb += gridDim.x) cdf_stage_scan(vb, K, nb, M, pw, pq, a.cdf, a.stats + (r - 1) * 4, sm, wsum);
+    if (r < N - 1) {   // (the CTAs without a CDF tile again: the transition matrices of event r)
+      const int first = nb < (int)gridDim.x ? nb : 0;
+      if ((int)blockIdx.x >= first) predraw_share(a, (int)blockIdx.x - first, (int)gridDim.x - first, 2, s_qpow);
+    }
     grid.sync();
     if (r == N - 1) {
       // ---- last launch: ELBO (vcsmc.py:276), log_likelihood_R (vcsmc.py:254-268, incl. quirk Q4), log_likelihood_tilde
@@ -938,6 +980,7 @@ __global__ void __launch_bounds__(kEvThreads, 2) lz_event_kernel(const EvArgs a)
     }
   }
 
+  if (r == 0) predraw_share(a, (int)blockIdx.x, (int)gridDim.x, 3, s_qpow);
   // ---- phase 5: ancestors of event r (all K), rows of the live particles of event r-1 (all K)
   stamp(a, 5);
   if (gtid == 0) *a.lw_max = LLONG_MIN;   // (every CTA has read the previous maximum by now)
@@ -1160,7 +1203,10 @@ __global__ void __launch_bounds__(kEvThreads, 2) lz_event_kernel(const EvArgs a)
   stamp(a, 11);
 }
 
-__global__ void lz_set_seed_kernel(uint64_t* seed_dev, uint64_t seed) { *seed_dev = seed; }
+__global__ void lz_set_seed_kernel(uint64_t* seed_dev, uint64_t seed, const double* Q, double* qpow) {
+  *seed_dev = seed;
+  if (Q) expm_tq_table(Q, qpow);   // once per sweep: the event kernel's transition matrices are Horner schemes on it
+}
 
 __global__ void lz_iota_kernel(int32_t* p, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1240,6 +1286,7 @@ int lazy_forward_body(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l,
   a.two_lists = leaf_perm != nullptr; a.skip_leaf_pairs = leaf_hist != nullptr; a.row_stride = (N + 3) & ~3; a.log2T = log2T;
   a.K = K; a.Kl = Kl; a.k0 = k0; a.pool_slots = h->pool_slots; a.fetch_cap = h->fetch_cap; a.slot_sites = S;
   a.lam_l = lam_l; a.lam_r = lam_r; a.Q = Q; a.pi = pi; a.ldf = h->p<double>(h->o_ldf);
+  a.qpow = h->p<double>(h->o_model) + 2 * (int64_t)N + 24;
   a.seed_dev = h->p<uint64_t>(h->o_seed_dev); a.codes = codes;
   a.anc = h->p<int32_t>(h->o_anc); a.lref = h->p<int32_t>(h->o_lref); a.rref = h->p<int32_t>(h->o_rref); a.nleaf = h->p<int32_t>(h->o_nleaf);
   a.b_l = h->p<double>(h->o_b_l); a.b_r = h->p<double>(h->o_b_r); a.t2 = h->p<double>(h->o_t2);
@@ -1393,7 +1440,7 @@ int sweep_forward_lazy(vcsmc_sweep* h, const uint8_t* codes, const double* lam_l
   VCSMC_CUDA(cudaMemcpyAsync(lam_r, lam_r_in, (N - 1) * sizeof(double), cudaMemcpyDeviceToDevice, st));
   if (Q_in) VCSMC_CUDA(cudaMemcpyAsync(Q, Q_in, 16 * sizeof(double), cudaMemcpyDeviceToDevice, st));
   VCSMC_CUDA(cudaMemcpyAsync(pi, pi_in, 4 * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  lz_set_seed_kernel<<<1, 1, 0, st>>>(h->p<uint64_t>(h->o_seed_dev), h->seed);
+  lz_set_seed_kernel<<<1, 1, 0, st>>>(h->p<uint64_t>(h->o_seed_dev), h->seed, Q_in ? Q : nullptr, m + 2 * (int64_t)N + 24);
   VCSMC_LAUNCH_CHECK("lz_set_seed_kernel");
   count_launch(4);
   h->lam_l = lam_l; h->lam_r = lam_r; h->Q = Q_in ? Q : nullptr; h->pi = pi;

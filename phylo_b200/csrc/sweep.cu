@@ -767,7 +767,7 @@ int64_t plan(vcsmc_sweep* h) {
   h->o_sig = L.take<int32_t>(64);
   h->o_epoch_dev = L.take<int32_t>(4);
   h->o_seed_dev = L.take<uint64_t>(2);
-  h->o_model = L.take<double>(2 * (int64_t)N + 24);
+  h->o_model = L.take<double>(2 * (int64_t)N + 24 + kExpmTableDoubles);   // lam_l, lam_r, Q, pi; the table of m4_expm_tq
   h->o_elbo = L.take<double>(1);
   h->o_anc = L.take<int32_t>(E);
   h->o_lref = L.take<int32_t>(E);
