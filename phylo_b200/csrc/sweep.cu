@@ -520,6 +520,11 @@ __global__ void __launch_bounds__(256) bwd_scalar_kernel(const ScalarArgs a) {
 __global__ void __launch_bounds__(64) transition_visited_kernel(const double* __restrict__ Q, const double* __restrict__ t2,
                                                                 const int32_t* __restrict__ order, const int32_t* __restrict__ count,
                                                                 int64_t K, int jc, double* __restrict__ P) {
+  __shared__ __align__(16) double s_tab[kExpmTableDoubles];   // the table of m4_expm_tq: the forward's own matrices, bit for bit
+  if (!jc) {
+    if (threadIdx.x == 0) expm_tq_table(Q, s_tab);
+    __syncthreads();
+  }
   const int r = blockIdx.y;
   const int64_t n = 2 * (int64_t)count[r];
   for (int64_t i = (int64_t)blockIdx.x * 64 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 64) {
@@ -532,10 +537,7 @@ __global__ void __launch_bounds__(64) transition_visited_kernel(const double* __
 #pragma unroll
       for (int e = 0; e < 16; ++e) out[e] = (e % 5 == 0) ? d : o;
     } else {
-      M4 A;
-#pragma unroll
-      for (int e = 0; e < 16; ++e) A.a[e] = __ldg(Q + e) * ti;
-      const M4 X = m4_expm(A);
+      const M4 X = m4_expm_tq(s_tab, ti);
 #pragma unroll
       for (int e = 0; e < 16; ++e) out[e] = X.a[e];
     }

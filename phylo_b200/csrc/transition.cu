@@ -3,8 +3,8 @@
 // Replaces tf.linalg.expm on [K,4,4] (vcsmc.py:181-184).  JC (vcsmc.py:126-129) has the closed form
 // P_ii = 1/4 + 3/4 e^-t, P_ij = 1/4 - 1/4 e^-t.  The reference's "GTR" Q (vcsmc.py:138-148) is a general
 // non-reversible rate matrix (complex eigenvalues are common, the initial Q has a triple eigenvalue), so the
-// general path is a per-matrix scaling-and-squaring Taylor series in registers -- 2K tiny matrices per rank
-// event are noise next to K*S merges.  The adjoint uses the Frechet derivative identity
+// general path is a scaling-and-squaring Taylor series: Q is the same for every matrix of a launch, so the powers
+// Q^k / k! are tabulated once and a matrix is a Horner scheme in its scalar t (common.cuh::m4_expm_tq).  The adjoint uses the Frechet derivative identity
 // L*(A, G) = L(A^T, G) evaluated with the same series on the block matrix [[A^T, G], [0, A^T]].
 #include "common.cuh"
 #include "launch.h"
@@ -14,6 +14,11 @@ namespace {
 
 __global__ void transition_fwd_kernel(const double* __restrict__ Q, const double* __restrict__ t, int64_t n, int jc,
                                       double* __restrict__ P) {
+  __shared__ __align__(16) double s_tab[kExpmTableDoubles];   // Q^k / k!: the table of m4_expm_tq (one Q, many t)
+  if (!jc) {
+    if (threadIdx.x == 0) expm_tq_table(Q, s_tab);
+    __syncthreads();
+  }
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double ti = t[i];
@@ -25,10 +30,7 @@ __global__ void transition_fwd_kernel(const double* __restrict__ Q, const double
     for (int e = 0; e < 16; ++e) out[e] = (e % 5 == 0) ? d : o;
     return;
   }
-  M4 A;
-#pragma unroll
-  for (int e = 0; e < 16; ++e) A.a[e] = __ldg(Q + e) * ti;
-  const M4 X = m4_expm(A);
+  const M4 X = m4_expm_tq(s_tab, ti);   // (the same bits as the event kernel's transition matrices)
 #pragma unroll
   for (int e = 0; e < 16; ++e) out[e] = X.a[e];
 }
