@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define VCSMC_ABI_VERSION 3
+#define VCSMC_ABI_VERSION 4
 
 #define VCSMC_OK 0
 #define VCSMC_ERR_ARG (-1)      /* bad argument */
@@ -59,12 +59,16 @@ int vcsmc_gather_sites(const uint8_t* codes, int n_taxa, int n_sites, const int3
 /* ---------------------------------------------------------------------------------------------
  * (b) transition matrices.  Replaces tf.linalg.expm(Q * b) on [K,4,4] (vcsmc.py:181-184).
  *     jc != 0: closed form for the reference's JC Q (vcsmc.py:126-129): P_ii = 1/4 + 3/4 e^-t,
- *     P_ij = 1/4 - 1/4 e^-t; Q is ignored.  jc == 0: scaling-and-squaring Taylor on t*Q per matrix.
+ *     P_ij = 1/4 - 1/4 e^-t; Q is ignored.  jc == 0: scaling-and-squaring Taylor (degree 14) on t*Q per matrix.
  *     bwd: given dP (adjoint of P) returns dt[i] = <dP_i, Q P_i> and dQ_each[i] = t_i * L(t_i Q^T, dP_i)
  *     (Frechet adjoint); dQ_each may be NULL (JC).  This is the piece of TF autodiff
  *     (vcsmc.py:488-491) that differentiates expm.
  * --------------------------------------------------------------------------------------------- */
 int vcsmc_transition_fwd(const double* Q, const double* t, int64_t n, int jc, double* P, void* stream);
+/* The general-Q arithmetic of transition_fwd on the HOST (host pointers, no GPU): Q is the same for every matrix of a
+ * call, so Q^k / k! (k <= 14) is tabulated once and P_i is a Horner scheme in the scalar t_i / 2^s on that table, then s
+ * squarings -- what the kernels execute, operation for operation.  For tests of that scheme without a device. */
+int vcsmc_transition_host(const double* Q, const double* t, int64_t n, double* P);
 int vcsmc_transition_bwd(const double* Q, const double* t, const double* dP, int64_t n, int jc, double* dt,
                          double* dQ_each, void* stream);
 

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "vcsmc_pack_alignment": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P]),
     "vcsmc_gather_sites": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "vcsmc_transition_fwd": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, _P]),
+    "vcsmc_transition_host": (C.c_int, [_P, _P, C.c_int64, _P]),
     "vcsmc_transition_bwd": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P, _P, _P]),
     "vcsmc_merge_tiles": (C.c_int, [C.c_int]),
     "vcsmc_merge_fwd": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P]),
@@ -86,7 +87,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.vcsmc_abi_version() != 3:
+    if lib.vcsmc_abi_version() != 4:
         raise ImportError("libvcsmc_b200 ABI version mismatch")
     _lib = lib
     return lib

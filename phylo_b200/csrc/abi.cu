@@ -55,6 +55,17 @@ int vcsmc_gather_sites(const uint8_t* codes, int n_taxa, int n_sites, const int3
   return launch_gather_sites(codes, n_taxa, n_sites, site_idx, n_sel, out, (cudaStream_t)stream);
 }
 
+int vcsmc_transition_host(const double* Q, const double* t, int64_t n, double* P) {
+  if (!Q || !t || !P || n < 0) { set_error("transition_host: bad argument"); return VCSMC_ERR_ARG; }
+  double table[kExpmTableDoubles];
+  expm_tq_table(Q, table);
+  for (int64_t i = 0; i < n; ++i) {
+    const M4 X = m4_expm_tq(table, t[i]);
+    for (int e = 0; e < 16; ++e) P[i * 16 + e] = X.a[e];
+  }
+  return VCSMC_OK;
+}
+
 int vcsmc_transition_fwd(const double* Q, const double* t, int64_t n, int jc, double* P, void* stream) {
   if ((!jc && !Q) || !t || !P || n < 0) { set_error("transition_fwd: bad argument"); return VCSMC_ERR_ARG; }
   return launch_transition_fwd(Q, t, n, jc, P, (cudaStream_t)stream);

@@ -96,13 +96,13 @@ __device__ __forceinline__ double block_sum(double x, double* sm) {
 struct M4 {
   double a[16];
 };
-__device__ __forceinline__ M4 m4_eye() {
+__host__ __device__ __forceinline__ M4 m4_eye() {
   M4 r;
 #pragma unroll
   for (int i = 0; i < 16; ++i) r.a[i] = (i % 5 == 0) ? 1.0 : 0.0;
   return r;
 }
-__device__ __forceinline__ M4 m4_mul(const M4& x, const M4& y) {
+__host__ __device__ __forceinline__ M4 m4_mul(const M4& x, const M4& y) {
   M4 r;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -129,7 +129,7 @@ __device__ __forceinline__ double m4_norm1(const M4& x) {
 
 constexpr int kTaylorDegree = 18;  // ||A||_1 <= 1/2 after scaling: remainder 0.5^19/19! ~ 1.6e-23
 
-__device__ __forceinline__ int expm_scale(double norm) {
+__host__ __device__ __forceinline__ int expm_scale(double norm) {
   // smallest s >= 0 with norm / 2^s <= 1/2
   int s = 0;
   if (norm > 0.5) {
@@ -194,7 +194,7 @@ __host__ __device__ inline void expm_tq_table(const double* Q, double* table) {
   }
   table[15 * 16] = nrm;
 }
-__device__ __forceinline__ M4 m4_expm_tq(const double* __restrict__ table, double t) {
+__host__ __device__ __forceinline__ M4 m4_expm_tq(const double* __restrict__ table, double t) {
   const int s = expm_scale(fabs(t) * table[15 * 16]);
   const double ts = ldexp(t, -s);
   M4 X;

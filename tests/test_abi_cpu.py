@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libvcsmc_b200.so does not export %s" % name
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared
-    assert lib.vcsmc_abi_version() == 3
+    assert lib.vcsmc_abi_version() == 4
 
 
 def test_arguments_are_validated_without_a_gpu():
@@ -98,3 +98,33 @@ def test_sweep_object_argument_checks_without_a_gpu():
         assert lib.vcsmc_sweep_set_comm(h, 0, 2, _lib.COMM_FN(lambda *a: 0), None, peers) == _lib.ERR_STATE
     finally:
         lib.vcsmc_sweep_destroy(h)
+
+
+def test_tabulated_expm_matches_scipy_on_the_host():
+    """The kernels' exp(tQ) -- Q^k / k! tabulated once, a Horner scheme in t / 2^s per matrix, s squarings
+    (common.cuh::m4_expm_tq; tf.linalg.expm at vcsmc.py:183-184) -- run on the HOST through vcsmc_transition_host:
+    the reference's initial Q, row-softmax rate matrices as vcsmc.py:138-148 builds them, branch lengths from 1e-12
+    to 60 (0 to 9 squarings)."""
+    import ctypes as C
+    import numpy as np
+    from scipy.linalg import expm
+    from phylo_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+
+    def rate_matrix(logits):
+        off = np.exp(logits - logits.max(axis=1, keepdims=True)) * (1 - np.eye(4))
+        off /= off.sum(axis=1, keepdims=True)
+        return off - np.eye(4)
+
+    t = np.concatenate([[0.0, 1e-12, 1e-6, 0.05, 0.1, 0.24, 0.26, 1.0, 7.3, 60.0], rng.exponential(0.1, 40)])
+    for Q in [rate_matrix(np.zeros((4, 4))), rate_matrix(rng.normal(size=(4, 4))), rate_matrix(3 * rng.normal(size=(4, 4)))]:
+        Q = np.ascontiguousarray(Q)
+        P = np.empty((t.size, 4, 4))
+        rc = lib.vcsmc_transition_host(Q.ctypes.data_as(C.c_void_p), t.ctypes.data_as(C.c_void_p), t.size, P.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        ref = np.stack([expm(Q * ti) for ti in t])
+        np.testing.assert_allclose(P, ref, rtol=1e-13, atol=1e-16)
+        np.testing.assert_allclose(P.sum(axis=2), 1.0, rtol=0, atol=1e-13)   # rows of a transition matrix (t = 60: nine squarings)
+    with pytest.raises(_lib.VcsmcError):
+        _lib.check(lib.vcsmc_transition_host(None, None, 1, None))
