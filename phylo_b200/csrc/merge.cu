@@ -576,7 +576,6 @@ __global__ void __launch_bounds__(kTileThreads) bwd_sparse_kernel(const SparseAr
 }
 
 
-constexpr int kSptFwd = 2;
 constexpr int kSptBwdJC = 2;
 constexpr int kSptBwdGeneral = 2;  // measured at 64x10kx65,536 dense: 1078 ms (SPT 2) vs 1278 ms (SPT 1)
 

@@ -11,12 +11,15 @@
 //                        O[s] = L_a[s] (x) L_b[s] (registers) and each particle costs 16 DFMA per site (general Q) or
 //                        4 DFMA (JC: x = a1 sa sb + a2 sa pb + a3 pa sb + a4 pab) instead of ~41; when child a is a
 //                        leaf with one-hot / all-ones masks it is row `state` of M dotted with L_b (4 DFMA).
-//                        Children come from L2; bound by instruction issue around the FP64 pipe.
+//                        Children come from L2 and are scaled per site by a power of two, so that a particle's running
+//                        product of site likelihoods is only multiplied per step and split into (mantissa, exponent)
+//                        at the end of a run; bound by the FP64 pipe and the latency around it.
 //   (particles whose children are both leaves are scored from the pair's site-pattern counts by the proposing thread
 //   of the event kernel, lazy.cu: leaf_pair_hist_kernel tabulates the patterns of every leaf pair once per sweep)
 //   merge_score_rows_kernel  particles whose children are a LEAF and an internal node (most of the scored work on
 //                        leaf-rich forests): the sites are visited in the leaf's state order (leaf_sort_kernel, once per
-//                        sweep), so a 1024-site tile shares ONE row of M per particle and a site costs 4 DFMA + 1/4 fold.
+//                        sweep), so the 128 positions a warp visits share ONE row of M per particle and a site costs
+//                        4 DFMA + one multiplication.
 //   materialise_kernel   after the next resampling, only particles that were drawn as an ancestor get their node
 //                        written (the plain merge formula; 32 B per site, streaming).
 //   pull_kernel          particle sharding: a rank that drew a remote ancestor copies the nodes it lacks straight out

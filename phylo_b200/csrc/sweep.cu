@@ -693,11 +693,6 @@ __global__ void __launch_bounds__(256) leaf_pi_grad_kernel(const uint8_t* __rest
   }
 }
 
-__global__ void zero_f64_kernel(double* p, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = 0.0;
-}
-
 }  // namespace
 }  // namespace vcsmc
 
