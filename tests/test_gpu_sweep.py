@@ -386,3 +386,35 @@ def test_grouped_scoring_kernels_against_oracle(ops, primate_genome, jc, leaf_ro
         sw.check_status()
         compare_forward(out, res, N, K)
         compare_grads(grads, g_ref, jc)
+
+
+@pytest.mark.parametrize("leaf_rows", [True, False])
+@pytest.mark.parametrize("jc", [True, False])
+def test_scoring_kernels_fall_back_to_one_log_per_site(ops, jc, leaf_rows):
+    """Branch rates of 1e80 give transition matrices I + O(1e-80): a site where the children disagree has a likelihood of
+    1e-80 .. 1e-240 (a normal double, its log is finite), but the product of a thread's four such sites -- or of a
+    run's tiles -- leaves the double range.  The scoring kernels then find the running product outside
+    [2^-959, 2^1024), poison the particle and redo it with one log per site, like the reference (score.cu:
+    rows_slow / score_slow): the results must still match the oracle.  i.i.d. nucleotides (three sites out of four
+    disagree), gaps, four taxa (a deeper tree would underflow per SITE, in the reference too)."""
+    g = synthetic_genome(4, 1301, seed=5, gaps=0.02)
+    N, K = 4, 48
+    p = O.Params.init(N, jc)
+    p.left_branches_param = torch.full((N - 1,), float(np.log(1e80)), dtype=torch.float64)
+    p.right_branches_param = torch.full((N - 1,), float(np.log(1e80)), dtype=torch.float64)
+    U = O.Uniforms.draw(N, K, seed=7)
+    lam_l, lam_r, Q, pi = O.model_from_params(p)
+    res = O.sweep(g, K, lam_l, lam_r, Q, pi, U)
+    assert np.isfinite(np.asarray(res.log_weights)).all() and float(np.asarray(res.log_likelihood).min()) < -4e5
+    codes = ops.pack_alignment(dev(g))
+    sw = ops.Sweep(N, g.shape[1], K, jc, keep_for_backward=False)
+    sw.set_uniforms(*gpu_uniforms(U))
+    sw.set_option("force_sorted", 1.0)
+    sw.set_option("leaf_rows", 1.0 if leaf_rows else 0.0)
+    elbo = sw.forward(codes, dev(lam_l.detach()), dev(lam_r.detach()), None if jc else dev(Q.detach()), dev(pi.detach().reshape(-1)))
+    sw.check_status()
+    out = {k: sw.output(k).cpu().numpy().copy() for k in
+           ("log_weights", "log_likelihood", "log_likelihood_tilde", "log_likelihood_R", "left_branches",
+            "right_branches", "v_minus", "ancestors", "left_ref", "right_ref", "leaf_counts")}
+    out["elbo"] = float(elbo.item())
+    compare_forward(out, res, N, K)
