@@ -476,7 +476,8 @@ def run_native(args):
     o_ii, o_li, o_ll = FP64_OPS_SCORE[args.model]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_step, "elbo_grad_steps_per_s": 1e3 / ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64",
         "data": "synthetic" if not args.dataset else "reference data file (%s)" % args.dataset,
         "config": {"workload": "%s %s fwd+grad sweep, %s x %d particles, reference initial parameters" % (
                        "VNCSMC(M=%d)" % args.nested if args.nested else "VCSMC", args.model.upper(), data_desc, K),
