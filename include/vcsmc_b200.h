@@ -198,7 +198,7 @@ int vcsmc_sweep_set_comm(vcsmc_sweep_t* h, int rank, int world, vcsmc_comm_fn fn
  * of the reverse sweep is ONE site-parallel launch per chunk (a thread owns its site through all rank events) instead of
  * three launches per rank event; 0 keeps the per-event kernels -- same sums up to the order of the dP reduction;
  * "leaf_rows" (default 1; lazy forward, grouped order): merges of a leaf and an internal node are scored by the rows
- * kernel on the leaf's state-sorted sites (one row of the bilinear form per 256-site sub-tile) -- same sum, different
+ * kernel on the leaf's state-sorted sites (one row of the bilinear form per 128-position unit) -- same sum, different
  * summation order; 0 leaves them to the generic scoring kernel;
  * "force_sorted" (default 0): grouped visiting order even when K is too small for it to pay (testing aid);
  * "event_timing" (default 0; lazy forward): CTA 0 of the event kernel stamps %globaltimer at every phase boundary

@@ -1045,7 +1045,7 @@ int launch_leaf_pair_hist(const uint8_t* codes, int64_t stride, int N, int S, in
   return VCSMC_OK;
 }
 
-int leaf_sort_stride(int n_sites) {   // padded length of a leaf's sorted site list: every class ends on a sub-tile boundary
+int leaf_sort_stride(int n_sites) {   // padded length of a leaf's sorted site list: every class ends on a unit boundary
   return (n_sites + kLeafClasses * kRowSub + kRowTile - 1) / kRowTile * kRowTile;
 }
 
