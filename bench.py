@@ -51,6 +51,26 @@ FP64_PEAK_TFMA = 18.2                # measured FP64 FMA rate of a B200 on this 
 FP64_OPS_SCORE = {"gtr": (18.0, 5.0, 0.0), "jc": (6.0, 5.0, 0.0)}
 
 
+_JSON_OUT = None
+
+
+def own_stdout():
+    """stdout carries ONE JSON line and nothing else: whatever a library writes to file descriptor 1 (NCCL's version
+    banner, which NCCL_DEBUG_FILE does not always catch; warnings of child processes) is sent to stderr from here on,
+    and the line goes to the descriptor that was stdout when the program started."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -119,7 +139,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -521,7 +541,7 @@ def run_native(args):
         line["cpu_baseline"] = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": desc + " (%d sweeps, %.1f s each)" % (n_cpu, per)}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         model.release()
         dist.barrier()
@@ -586,7 +606,7 @@ def run_c1(args):
         line.update(value=dt, elbo_after_epoch=float(ev.elbo), steps_per_s=897 / dt, impl="reference",
                     cpu_baseline={"value": dt, "unit": "s", "cores": cores, "kind": "port",
                                   "sample": "the whole epoch (897 steps + 2 evaluations), restated reference in torch-CPU fp64"})
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 CONFIGS = {  # BASELINE.json configs[1..4]
@@ -599,6 +619,7 @@ CONFIGS = {  # BASELINE.json configs[1..4]
 
 if __name__ == "__main__":
     a = parse()
+    own_stdout()
     if a.config == "c1":
         run_c1(a)
         sys.exit(0)
