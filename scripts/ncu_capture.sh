@@ -1,7 +1,7 @@
 #!/bin/bash
 # Measurements and ncu captures of round 2 (run on the GPU box through gpurun; one GPU).  Outputs under gpurun_out/,
 # summarised into profiles/ by scripts/ncu_summary.py.  Every command has run (exit 0) WITHOUT ncu before.
-#   gpurun --timeout 900 -- 'bash scripts/ncu_capture.sh [all]'
+#   make -C phylo_b200/csrc tools && gpurun --timeout 900 -- 'bash scripts/ncu_capture.sh [all]'
 set -u
 O=gpurun_out
 NCU="ncu --set full --clock-control none --import-source on -f"
